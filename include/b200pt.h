@@ -1,0 +1,220 @@
+/*
+ * b200pt.h — C ABI of the B200-native replacement for the ray-scene
+ * intersection + path-integration hot path of hackmad/pbrt-v3-rs.
+ *
+ * This is the drop-in boundary: exactly what a `b200pt-sys`
+ * FFI crate on the reference side would bind.  Plain pointers and sizes, no
+ * C++/torch types, no exceptions across the boundary.  Every call returns 0 on
+ * success or a negative b200pt_status; b200pt_last_error() gives the message
+ * (thread-local).  There is NO CPU fallback: without an sm_100 device
+ * b200pt_init() fails and every compute entry point returns
+ * B200PT_ERR_NO_DEVICE.
+ *
+ * file:line citations are relative to the reference repository root.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b200pt_status {
+    B200PT_OK = 0,
+    B200PT_ERR_NO_DEVICE = -1,   /* no CUDA device / not sm_100 */
+    B200PT_ERR_INVALID = -2,     /* bad argument */
+    B200PT_ERR_CUDA = -3,        /* CUDA runtime error, see last_error */
+    B200PT_ERR_OOM = -4,
+    B200PT_ERR_UNSUPPORTED = -5
+} b200pt_status;
+
+#define B200PT_MISS 0xffffffffu
+
+/* core/src/geometry/ray.rs:10-28 (o, d, t_max, time; differentials and medium
+ * are not carried on this path). 32 bytes, two 16-byte vectors. */
+typedef struct b200pt_ray {
+    float o[3];
+    float tmax;
+    float d[3];
+    float time;
+} b200pt_ray;
+
+/* Device form of the SurfaceInteraction returned by BVHAccel::intersect
+ * (accelerators/src/bvh/mod.rs:173-226): hit distance, ORIGINAL primitive
+ * index (position in RenderOptions.primitives; B200PT_MISS when nothing was
+ * hit) and the first two barycentrics. 16 bytes. */
+typedef struct b200pt_hit {
+    float t;
+    uint32_t prim;
+    float b0;
+    float b1;
+} b200pt_hit;
+
+/* accelerators/src/bvh/common.rs:163-179 LinearBVHNode, fixed to 32 bytes. */
+typedef struct b200pt_bvh_node {
+    float bounds[6];       /* p_min.xyz, p_max.xyz */
+    uint32_t offset;       /* leaf: first ordered primitive; interior: second child */
+    uint16_t n_primitives; /* > 0 => leaf */
+    uint8_t axis;
+    uint8_t pad;
+} b200pt_bvh_node;
+
+/* Per-primitive flags. */
+#define B200PT_PRIM_FLIP_NORMAL 1u        /* reverse_orientation ^ transform_swaps_handedness (shapes/src/triangle.rs:625-629) */
+#define B200PT_PRIM_ALPHA_ZERO 2u         /* constant "alpha" texture == 0 (triangle.rs:587-607) */
+#define B200PT_PRIM_SHADOW_ALPHA_ZERO 4u  /* constant "shadowalpha" texture == 0 (triangle.rs:840-899) */
+
+/* materials/src/{matte,plastic,glass,metal}.rs with constant textures. */
+enum { B200PT_MAT_MATTE = 0, B200PT_MAT_PLASTIC = 1, B200PT_MAT_GLASS = 2, B200PT_MAT_METAL = 3 };
+typedef struct b200pt_material {
+    int32_t type;
+    float kd[3];    /* matte/plastic "Kd" */
+    float ks[3];    /* plastic "Ks"; glass "Kr" */
+    float kt[3];    /* glass "Kt" */
+    float eta[3];   /* metal "eta" (RGB); glass "index"/"eta" in eta[0] */
+    float k[3];     /* metal "k" */
+    float sigma;    /* matte "sigma" (degrees) */
+    float urough;   /* plastic/metal "roughness", glass/metal "uroughness" — as written in the scene file */
+    float vrough;
+    int32_t remap_roughness;
+} b200pt_material;
+
+/* lights/src/{point,diffuse,infinite}.rs */
+enum { B200PT_LIGHT_POINT = 0, B200PT_LIGHT_AREA = 1, B200PT_LIGHT_INFINITE = 2 };
+typedef struct b200pt_light {
+    int32_t type;
+    float pos[3];             /* point: p_light (world) */
+    float L[3];               /* point: I*scale; area: L*scale; infinite: L*scale */
+    int32_t prim;             /* area: ORIGINAL primitive index of the emitting triangle (api/src/lib.rs:783-803: one light per triangle) */
+    int32_t two_sided;        /* area */
+    float light_to_world[16]; /* infinite (row-major 4x4) */
+    float world_to_light[16];
+} b200pt_light;
+
+/* cameras/src/perspective_camera.rs + core/src/camera.rs:276-306: the two
+ * matrices the reference's PerspectiveCamera holds (row-major 4x4). */
+typedef struct b200pt_camera {
+    float raster_to_camera[16];
+    float camera_to_world[16];
+    float lens_radius;
+    float focal_distance;
+    float shutter_open;
+    float shutter_close;
+} b200pt_camera;
+
+/* core/src/film/mod.rs:89-146 */
+typedef struct b200pt_film {
+    int32_t xres, yres;
+    int32_t crop[4];           /* cropped_pixel_bounds: x0, y0, x1, y1 */
+    float filter_radius[2];
+    float filter_table[256];   /* 16x16, film/mod.rs:113-125 */
+    float scale;
+    float max_sample_luminance; /* INFINITY when unset */
+} b200pt_film;
+
+enum { B200PT_SAMPLER_HALTON = 0, B200PT_SAMPLER_ZEROTWO = 1 };
+typedef struct b200pt_sampler {
+    int32_t type;
+    int32_t spp;               /* "pixelsamples" */
+    int32_t sample_at_center;  /* halton "samplepixelcenter" */
+    int32_t dimensions;        /* 02sequence "dimensions" */
+} b200pt_sampler;
+
+enum { B200PT_LIGHTS_UNIFORM = 0, B200PT_LIGHTS_POWER = 1 };
+/* integrators/src/path.rs:287-326 */
+typedef struct b200pt_integrator {
+    int32_t max_depth;         /* "maxdepth" (5) */
+    float rr_threshold;        /* "rrthreshold" (1.0) */
+    int32_t pixel_bounds[4];   /* x0,y0,x1,y1 (sample bounds ∩ "pixelbounds") */
+    int32_t light_strategy;    /* "lightsamplestrategy": uniform | power */
+} b200pt_integrator;
+
+typedef struct b200pt_scene_desc {
+    const b200pt_bvh_node* nodes;
+    int64_t n_nodes;
+    const uint32_t* ordered_prims; /* BVHAccel.primitives order: ordered position -> original index */
+    const float* tri_verts;        /* 9 floats per ORIGINAL primitive, world space (TriangleMesh::new transforms to world, triangle.rs:92) */
+    const uint32_t* prim_flags;    /* per original primitive, may be NULL */
+    const int32_t* prim_material;  /* per original primitive index into materials, may be NULL for accel-only scenes */
+    const int32_t* prim_light;     /* per original primitive index into lights or -1, may be NULL */
+    int64_t n_prims;
+    const b200pt_material* materials;
+    int32_t n_materials;
+    const b200pt_light* lights;
+    int32_t n_lights;
+    b200pt_camera camera;
+    b200pt_film film;
+    b200pt_sampler sampler;
+    b200pt_integrator integrator;
+} b200pt_scene_desc;
+
+typedef struct b200pt_accel b200pt_accel; /* opaque: device-resident BVHAccel */
+typedef struct b200pt_scene b200pt_scene; /* opaque: device-resident Scene + PathIntegrator state */
+
+/* ---- library ---------------------------------------------------------- */
+int b200pt_init(int device);
+const char* b200pt_last_error(void);
+int b200pt_version(void);
+/* number of SMs / L2 bytes of the bound device (0 before init) */
+int b200pt_device_sm_count(void);
+int64_t b200pt_device_l2_bytes(void);
+
+/* ---- host-side BVH build: BVHAccel::new with SplitMethod::SAH ----------
+ * (accelerators/src/bvh/mod.rs:43-153, sah.rs:26-367).  prim_bounds = 6
+ * floats per primitive (Primitive::world_bound).  nodes_out needs room for
+ * 2*n-1 nodes, ordered_out for n indices.  *n_nodes_out receives the node
+ * count.  max_prims_in_node is the reference's u8 "maxnodeprims". */
+int b200pt_bvh_build_sah(const float* prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* nodes_out,
+                         int64_t* n_nodes_out, uint32_t* ordered_out);
+/* Triangle::world_bound (shapes/src/triangle.rs:427-431) for n triangles. */
+int b200pt_triangle_bounds(const float* tri_verts, int64_t n, float* bounds_out);
+
+/* ---- accelerator: impl Primitive for BVHAccel --------------------------
+ * Copies the arrays to the device; the caller keeps ownership of its own. */
+int b200pt_accel_create(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered_prims, const float* tri_verts,
+                        const uint32_t* prim_flags, int64_t n_prims, b200pt_accel** out);
+void b200pt_accel_destroy(b200pt_accel* a);
+/* Primitive::world_bound (mod.rs:159-165): 6 floats. */
+int b200pt_accel_world_bound(const b200pt_accel* a, float* bounds6);
+/* Primitive::intersect / intersect_p for one ray (correctness path; the ray's
+ * tmax is lowered on a hit exactly as the trait requires). */
+int b200pt_accel_intersect1(const b200pt_accel* a, b200pt_ray* ray, b200pt_hit* hit);
+int b200pt_accel_occluded1(const b200pt_accel* a, const b200pt_ray* ray, uint8_t* occluded);
+/* Batched forms with HOST buffers (copies in and out inside the call). */
+int b200pt_intersect_batch(const b200pt_accel* a, const b200pt_ray* rays, int64_t n, b200pt_hit* hits);
+int b200pt_occluded_batch(const b200pt_accel* a, const b200pt_ray* rays, int64_t n, uint8_t* occluded);
+/* Batched forms with DEVICE buffers, enqueued on `stream` (a cudaStream_t; 0 =
+ * default stream), asynchronous. `variant` selects the traversal kernel
+ * (0 = default; others are kept for A/B measurement). */
+int b200pt_intersect_batch_device(const b200pt_accel* a, const void* d_rays, int64_t n, void* d_hits, void* stream, int variant);
+int b200pt_occluded_batch_device(const b200pt_accel* a, const void* d_rays, int64_t n, void* d_occluded, void* stream, int variant);
+/* Kernel launches issued by this library since init (bench.py's gpu_launches). */
+int64_t b200pt_launch_count(void);
+
+/* ---- scene + PathIntegrator -------------------------------------------- */
+int b200pt_scene_create(const b200pt_scene_desc* desc, b200pt_scene** out);
+void b200pt_scene_destroy(b200pt_scene* s);
+/* Integrator::render (core/src/integrator/sampler_integrator.rs:243-304) for
+ * the pixel rows [row_begin, row_end) of the cropped window (the multi-GPU
+ * shard; pass 0, height for the whole image).  film_xyzw: 4 floats per pixel
+ * of the FULL cropped window {X, Y, Z, filter_weight_sum}, zero outside the
+ * shard, HOST memory. */
+int b200pt_render_rows(b200pt_scene* s, int32_t row_begin, int32_t row_end, float* film_xyzw);
+/* Same, film stays on the device (d_film_xyzw: device pointer, full window). */
+int b200pt_render_rows_device(b200pt_scene* s, int32_t row_begin, int32_t row_end, void* d_film_xyzw, void* stream);
+/* Film::write_image normalisation (film/mod.rs:356-417): XYZ+weight -> RGB,
+ * 3 floats per pixel, HOST memory both sides. */
+int b200pt_film_resolve(const b200pt_film* film, const float* film_xyzw, float* rgb_out);
+/* Integrator::li for explicit (pixel x, pixel y, sample index) triples:
+ * out = 3 floats (RGB radiance) per entry; rays_out (optional) = camera ray. */
+int b200pt_li_batch(b200pt_scene* s, const int32_t* pixel_sample, int64_t n, float* li_out, b200pt_ray* rays_out);
+/* Rays traced by the last render on this scene: [camera, closest-hit, shadow]. */
+int b200pt_scene_ray_counts(const b200pt_scene* s, uint64_t counts[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */

@@ -1,0 +1,423 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// CPU restatement (C++17, f32, no FMA contraction, no fast-math) of the
+// hackmad/pbrt-v3-rs hot path.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may build or call this.
+//
+// PARITY UNPINNED: the reference (Rust) cannot be compiled in this image and
+// its own tests hold no golden vectors for this path.  The
+// oracle is pinned only by (i) the reference's geometry identities carried over
+// as self-tests, (ii) published PCG32 / radical-inverse known answers and
+// (iii) hand-checkable tiny scenes (tests/test_oracle_*.py).
+//
+// Every function cites the reference file:line (relative to /root/reference)
+// whose operation order it restates.  Rust never contracts a*b+c into an FMA
+// and never re-associates, so this file must be compiled with
+// -ffp-contract=off and without -ffast-math (see oracle/Makefile).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+
+namespace orc {
+
+typedef float Float;
+
+// core/src/pbrt/common.rs:13-49
+static const Float kInfinity = std::numeric_limits<Float>::infinity();
+static const Float kPi = 3.14159265358979323846f;
+static const Float kInvPi = 1.0f / kPi;
+static const Float kPiOver2 = kPi * 0.5f;
+static const Float kPiOver4 = kPi * 0.25f;
+static const Float kTwoPi = kPi * 2.0f;
+static const Float kInvTwoPi = 1.0f / kTwoPi;
+static const Float kFourPi = kPi * 4.0f;
+static const Float kInvFourPi = 1.0f / kFourPi;
+static const Float kMachineEpsilon = std::numeric_limits<Float>::epsilon() * 0.5f;
+static const Float kShadowEpsilon = 0.0001f;
+// core/src/rng.rs:6-12
+static const Float kOneMinusEpsilon = 0x1.fffffep-1f;
+
+// core/src/pbrt/common.rs:66-108 — comparisons exactly as written (NaN falls
+// through to the second operand).
+template <class T> inline T pmin(T a, T b) { return a < b ? a : b; }
+template <class T> inline T pmax(T a, T b) { return a > b ? a : b; }
+template <class T> inline T pabs(T a) { return a < T(0) ? -a : a; }
+// core/src/pbrt/clamp.rs
+template <class T> inline T pclamp(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+// core/src/pbrt/common.rs:111-124 (pbrt's Mod)
+template <class T> inline T prem(T a, T b) {
+    T r = a - (a / b) * b;
+    return r < T(0) ? r + b : r;
+}
+
+// core/src/pbrt/common.rs:130-133
+inline Float gamma(int n) { return ((Float)n * kMachineEpsilon) / (1.0f - (Float)n * kMachineEpsilon); }
+
+inline uint32_t f2bits(Float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline Float bits2f(uint32_t u) { Float f; std::memcpy(&f, &u, 4); return f; }
+
+// core/src/pbrt/common.rs:205-243
+inline Float next_float_up(Float v) {
+    if (std::isinf(v) && v > 0.0f) return v;
+    Float nv = (v == -0.0f) ? 0.0f : v;
+    uint32_t ui = f2bits(nv);
+    if (nv >= 0.0f) ui += 1; else ui -= 1;
+    return bits2f(ui);
+}
+inline Float next_float_down(Float v) {
+    if (std::isinf(v) && v < 0.0f) return v;
+    Float nv = (v == 0.0f) ? -0.0f : v;
+    uint32_t ui = f2bits(nv);
+    if (nv > 0.0f) ui -= 1; else ui += 1;
+    return bits2f(ui);
+}
+
+// core/src/pbrt/common.rs:178-200
+inline Float lerpf(Float t, Float a, Float b) { return (1.0f - t) * a + t * b; }
+
+// ---------------------------------------------------------------------------
+// 3-vectors.  Vector3 / Point3 / Normal3 share one representation here; the
+// reference's operators are identical across the three
+// (core/src/geometry/vector3.rs, point3.rs, normal.rs).
+struct V3 {
+    Float x, y, z;
+    V3() : x(0), y(0), z(0) {}
+    V3(Float a, Float b, Float c) : x(a), y(b), z(c) {}
+    Float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+    Float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
+};
+inline V3 operator+(V3 a, V3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(V3 a, V3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator-(V3 a) { return V3(-a.x, -a.y, -a.z); }
+// vector3.rs:355-398 (f * component)
+inline V3 operator*(Float f, V3 v) { return V3(f * v.x, f * v.y, f * v.z); }
+inline V3 operator*(V3 v, Float f) { return V3(f * v.x, f * v.y, f * v.z); }
+// vector3.rs:408-417 — division multiplies by the reciprocal.
+inline V3 operator/(V3 v, Float f) { Float inv = 1.0f / f; return V3(inv * v.x, inv * v.y, inv * v.z); }
+// vector3.rs:186-190
+inline Float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline Float abs_dot(V3 a, V3 b) { return pabs(dot(a, b)); }
+// vector3.rs:207-217 — pure f32 cross product (pbrt-v3 proper uses f64).
+inline V3 cross(V3 a, V3 b) {
+    return V3((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x));
+}
+inline Float length_squared(V3 v) { return v.x * v.x + v.y * v.y + v.z * v.z; }
+inline Float length(V3 v) { return std::sqrt(length_squared(v)); }
+inline V3 normalize(V3 v) { return v / length(v); }
+inline V3 vabs(V3 v) { return V3(pabs(v.x), pabs(v.y), pabs(v.z)); }
+// vector3.rs:114-128
+inline Float max_component(V3 v) {
+    if (v.x > v.y) return v.x > v.z ? v.x : v.z;
+    return v.y > v.z ? v.y : v.z;
+}
+// vector3.rs:133-148
+inline int max_dimension(V3 v) {
+    if (v.x > v.y) return v.x > v.z ? 0 : 2;
+    return v.y > v.z ? 1 : 2;
+}
+inline V3 permute(V3 v, int x, int y, int z) { return V3(v[x], v[y], v[z]); }
+// geometry/common.rs:36-48
+inline V3 face_forward(V3 n, V3 v) { return dot(n, v) < 0.0f ? -n : n; }
+inline Float distance_squared(V3 a, V3 b) { return length_squared(a - b); }
+inline Float distance(V3 a, V3 b) { return length(a - b); }
+
+// core/src/geometry/coordinate_system.rs:12-20
+inline void coordinate_system(V3 v1, V3* v2, V3* v3) {
+    if (pabs(v1.x) > pabs(v1.y))
+        *v2 = V3(-v1.z, 0.0f, v1.x) / std::sqrt(v1.x * v1.x + v1.z * v1.z);
+    else
+        *v2 = V3(0.0f, v1.z, -v1.y) / std::sqrt(v1.y * v1.y + v1.z * v1.z);
+    *v3 = cross(v1, *v2);
+}
+
+struct P2 {
+    Float x, y;
+    P2() : x(0), y(0) {}
+    P2(Float a, Float b) : x(a), y(b) {}
+    Float operator[](int i) const { return i == 0 ? x : y; }
+};
+
+// core/src/geometry/util.rs:12-56
+inline V3 spherical_direction(Float sin_theta, Float cos_theta, Float phi) {
+    return V3(sin_theta * std::cos(phi), sin_theta * std::sin(phi), cos_theta);
+}
+inline Float spherical_theta(V3 v) { return std::acos(pclamp(v.z, -1.0f, 1.0f)); }
+inline Float spherical_phi(V3 v) {
+    Float p = std::atan2(v.y, v.x);
+    return p < 0.0f ? p + kTwoPi : p;
+}
+
+// ---------------------------------------------------------------------------
+// core/src/geometry/bounds3.rs
+struct Bounds3 {
+    V3 pmin, pmax;
+    // bounds3.rs:26-29: EMPTY = {Point3f::MAX, Point3f::MIN} = {+f32::MAX, -f32::MAX}
+    Bounds3()
+        : pmin(std::numeric_limits<Float>::max(), std::numeric_limits<Float>::max(), std::numeric_limits<Float>::max()),
+          pmax(-std::numeric_limits<Float>::max(), -std::numeric_limits<Float>::max(), -std::numeric_limits<Float>::max()) {}
+    Bounds3(V3 a, V3 b) : pmin(a), pmax(b) {}
+    const V3& operator[](int i) const { return i == 0 ? pmin : pmax; }
+};
+// bounds3.rs:354-390
+inline Bounds3 bunion(const Bounds3& b, V3 p) {
+    return Bounds3(V3(pmin(b.pmin.x, p.x), pmin(b.pmin.y, p.y), pmin(b.pmin.z, p.z)),
+                   V3(pmax(b.pmax.x, p.x), pmax(b.pmax.y, p.y), pmax(b.pmax.z, p.z)));
+}
+inline Bounds3 bunion(const Bounds3& a, const Bounds3& b) {
+    return Bounds3(V3(pmin(a.pmin.x, b.pmin.x), pmin(a.pmin.y, b.pmin.y), pmin(a.pmin.z, b.pmin.z)),
+                   V3(pmax(a.pmax.x, b.pmax.x), pmax(a.pmax.y, b.pmax.y), pmax(a.pmax.z, b.pmax.z)));
+}
+inline bool bempty(const Bounds3& b) { return b.pmax.x < b.pmin.x || b.pmax.y < b.pmin.y || b.pmax.z < b.pmin.z; }
+inline V3 bdiagonal(const Bounds3& b) { return b.pmax - b.pmin; }
+// bounds3.rs:94-105
+inline Float surface_area(const Bounds3& b) {
+    if (bempty(b)) return 0.0f;
+    V3 d = bdiagonal(b);
+    Float h = d.x * d.y + d.x * d.z + d.y * d.z;
+    return h + h;
+}
+// bounds3.rs:122-134
+inline int maximum_extent(const Bounds3& b) {
+    V3 d = bdiagonal(b);
+    if (d.x > d.y && d.x > d.z) return 0;
+    if (d.y > d.z) return 1;
+    return 2;
+}
+// bounds3.rs:153-168
+inline V3 boffset(const Bounds3& b, V3 p) {
+    V3 o = p - b.pmin;
+    if (b.pmax.x > b.pmin.x) o.x /= b.pmax.x - b.pmin.x;
+    if (b.pmax.y > b.pmin.y) o.y /= b.pmax.y - b.pmin.y;
+    if (b.pmax.z > b.pmin.z) o.z /= b.pmax.z - b.pmin.z;
+    return o;
+}
+inline bool bcontains(const Bounds3& b, V3 p) {
+    return (p.x >= b.pmin.x && p.x <= b.pmax.x) && (p.y >= b.pmin.y && p.y <= b.pmax.y) &&
+           (p.z >= b.pmin.z && p.z <= b.pmax.z);
+}
+// bounds3.rs:196-208 (lerp(0.5, pmin, pmax) = (1-t)*p0 + t*p1 per component)
+inline void bounding_sphere(const Bounds3& b, V3* center, Float* radius) {
+    *center = (1.0f - 0.5f) * b.pmin + 0.5f * b.pmax;
+    *radius = bcontains(b, *center) ? distance(*center, b.pmax) : 0.0f;
+}
+
+// ---------------------------------------------------------------------------
+// core/src/geometry/ray.rs:10-28 (differentials and medium are not carried:
+// constant textures / no media on the in-scope path).
+struct Ray {
+    V3 o, d;
+    Float t_max, time;
+    Ray() : t_max(kInfinity), time(0) {}
+    Ray(V3 o_, V3 d_, Float tm, Float ti) : o(o_), d(d_), t_max(tm), time(ti) {}
+};
+
+// core/src/geometry/ray.rs:107-127
+inline V3 offset_ray_origin(V3 p, V3 p_error, V3 n, V3 w) {
+    Float d = dot(vabs(n), p_error);
+    V3 offset = d * n;
+    if (dot(w, n) < 0.0f) offset = -offset;
+    V3 po = p + offset;
+    for (int a = 0; a < 3; ++a) {
+        if (offset[a] > 0.0f) po[a] = next_float_up(po[a]);
+        else if (offset[a] < 0.0f) po[a] = next_float_down(po[a]);
+    }
+    return po;
+}
+
+// ---------------------------------------------------------------------------
+// core/src/geometry/matrix4x4.rs
+struct M4 {
+    Float m[4][4];
+    M4() { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) m[i][j] = (i == j) ? 1.0f : 0.0f; }
+};
+// matrix4x4.rs:137-151
+inline M4 mmul(const M4& a, const M4& b) {
+    M4 r;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j] + a.m[i][3] * b.m[3][j];
+    return r;
+}
+// matrix4x4.rs:55-123 — Gauss-Jordan with full pivoting.
+inline M4 minverse(const M4& src) {
+    int indxc[4], indxr[4], ipiv[4] = {0, 0, 0, 0};
+    Float minv[4][4];
+    std::memcpy(minv, src.m, sizeof(minv));
+    for (int i = 0; i < 4; ++i) {
+        int irow = 0, icol = 0;
+        Float big = 0.0f;
+        for (int j = 0; j < 4; ++j) {
+            if (ipiv[j] != 1) {
+                for (int k = 0; k < 4; ++k) {
+                    if (ipiv[k] == 0) {
+                        Float a = pabs(minv[j][k]);
+                        if (a >= big) { big = a; irow = j; icol = k; }
+                    }
+                }
+            }
+        }
+        ipiv[icol] += 1;
+        if (irow != icol)
+            for (int k = 0; k < 4; ++k) { Float t = minv[irow][k]; minv[irow][k] = minv[icol][k]; minv[icol][k] = t; }
+        indxr[i] = irow;
+        indxc[i] = icol;
+        Float pivinv = 1.0f / minv[icol][icol];
+        minv[icol][icol] = 1.0f;
+        for (int j = 0; j < 4; ++j) minv[icol][j] *= pivinv;
+        for (int j = 0; j < 4; ++j) {
+            if (j != icol) {
+                Float save = minv[j][icol];
+                minv[j][icol] = 0.0f;
+                for (int k = 0; k < 4; ++k) minv[j][k] -= minv[icol][k] * save;
+            }
+        }
+    }
+    for (int j = 3; j >= 0; --j) {
+        if (indxr[j] != indxc[j])
+            for (int k = 0; k < 4; ++k) { Float t = minv[k][indxr[j]]; minv[k][indxr[j]] = minv[k][indxc[j]]; minv[k][indxc[j]] = t; }
+    }
+    M4 r;
+    std::memcpy(r.m, minv, sizeof(minv));
+    return r;
+}
+
+// core/src/geometry/transform.rs
+struct Transform {
+    M4 m, m_inv;
+};
+inline Transform tinverse(const Transform& t) { Transform r; r.m = t.m_inv; r.m_inv = t.m; return r; }
+// transform.rs:644-656
+inline Transform tmul(const Transform& a, const Transform& b) {
+    Transform r; r.m = mmul(a.m, b.m); r.m_inv = mmul(b.m_inv, a.m_inv); return r;
+}
+inline Transform tfrom(const M4& m) { Transform r; r.m = m; r.m_inv = minverse(m); return r; }
+// transform.rs:60-98
+inline Transform ttranslate(V3 d) {
+    Transform r;
+    r.m.m[0][3] = d.x; r.m.m[1][3] = d.y; r.m.m[2][3] = d.z;
+    r.m_inv.m[0][3] = -d.x; r.m_inv.m[1][3] = -d.y; r.m_inv.m[2][3] = -d.z;
+    return r;
+}
+inline Transform tscale(Float x, Float y, Float z) {
+    Transform r;
+    r.m.m[0][0] = x; r.m.m[1][1] = y; r.m.m[2][2] = z;
+    r.m_inv.m[0][0] = 1.0f / x; r.m_inv.m[1][1] = 1.0f / y; r.m_inv.m[2][2] = 1.0f / z;
+    return r;
+}
+inline Float to_radians(Float deg) { return deg * (kPi / 180.0f); }  // f32::to_radians
+// transform.rs:234-246
+inline Transform tperspective(Float fov, Float n, Float f) {
+    M4 persp;
+    persp.m[2][2] = f / (f - n);
+    persp.m[2][3] = -f * n / (f - n);
+    persp.m[3][2] = 1.0f;
+    persp.m[3][3] = 0.0f;
+    Float inv_tan_ang = 1.0f / std::tan(to_radians(fov) / 2.0f);
+    return tmul(tscale(inv_tan_ang, inv_tan_ang, 1.0f), tfrom(persp));
+}
+// transform.rs:191-214 — returns the *world-to-camera* transform (m = inverse).
+inline Transform tlook_at(V3 pos, V3 look, V3 up) {
+    V3 dir = normalize(look - pos);
+    V3 right = cross(normalize(up), dir);
+    right = normalize(right);
+    V3 new_up = cross(dir, right);
+    M4 c2w;
+    c2w.m[0][0] = right.x; c2w.m[0][1] = new_up.x; c2w.m[0][2] = dir.x; c2w.m[0][3] = pos.x;
+    c2w.m[1][0] = right.y; c2w.m[1][1] = new_up.y; c2w.m[1][2] = dir.y; c2w.m[1][3] = pos.y;
+    c2w.m[2][0] = right.z; c2w.m[2][1] = new_up.z; c2w.m[2][2] = dir.z; c2w.m[2][3] = pos.z;
+    Transform r; r.m = minverse(c2w); r.m_inv = c2w; return r;
+}
+// transform.rs:288-302
+inline V3 xf_point(const M4& M, V3 p) {
+    const Float (*m)[4] = M.m;
+    Float xp = m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3];
+    Float yp = m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3];
+    Float zp = m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3];
+    Float wp = m[3][0] * p.x + m[3][1] * p.y + m[3][2] * p.z + m[3][3];
+    if (wp == 1.0f) return V3(xp, yp, zp);
+    return V3(xp, yp, zp) / wp;
+}
+// transform.rs:307-331
+inline V3 xf_point_err(const M4& M, V3 p, V3* err) {
+    const Float (*m)[4] = M.m;
+    Float x = p.x, y = p.y, z = p.z;
+    Float xp = (m[0][0] * x + m[0][1] * y) + (m[0][2] * z + m[0][3]);
+    Float yp = (m[1][0] * x + m[1][1] * y) + (m[1][2] * z + m[1][3]);
+    Float zp = (m[2][0] * x + m[2][1] * y) + (m[2][2] * z + m[2][3]);
+    Float wp = (m[3][0] * x + m[3][1] * y) + (m[3][2] * z + m[3][3]);
+    Float xs = pabs(m[0][0] * x) + pabs(m[0][1] * y) + pabs(m[0][2] * z) + pabs(m[0][3]);
+    Float ys = pabs(m[1][0] * x) + pabs(m[1][1] * y) + pabs(m[1][2] * z) + pabs(m[1][3]);
+    Float zs = pabs(m[2][0] * x) + pabs(m[2][1] * y) + pabs(m[2][2] * z) + pabs(m[2][3]);
+    *err = gamma(3) * V3(xs, ys, zs);
+    if (wp == 1.0f) return V3(xp, yp, zp);
+    return V3(xp, yp, zp) / wp;
+}
+// transform.rs:373-380
+inline V3 xf_vector(const M4& M, V3 v) {
+    const Float (*m)[4] = M.m;
+    return V3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z,
+              m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z);
+}
+// transform.rs:451-476
+inline Ray xf_ray(const M4& M, const Ray& r) {
+    V3 o_err;
+    V3 o = xf_point_err(M, r.o, &o_err);
+    V3 d = xf_vector(M, r.d);
+    Float l2 = length_squared(d);
+    Float t_max = r.t_max;
+    if (l2 > 0.0f) {
+        Float dt = dot(vabs(d), o_err) / l2;
+        o = o + d * dt;
+        t_max -= dt;
+    }
+    return Ray(o, d, t_max, r.time);
+}
+// transform.rs:593-599
+inline bool swaps_handedness(const M4& M) {
+    const Float (*m)[4] = M.m;
+    Float det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+                m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+    return det < 0.0f;
+}
+
+// core/src/spectrum/rgb_spectrum.rs — Spectrum = RGBSpectrum (3 x f32).
+struct RGB {
+    Float c[3];
+    RGB() { c[0] = c[1] = c[2] = 0.0f; }
+    explicit RGB(Float v) { c[0] = c[1] = c[2] = v; }
+    RGB(Float r, Float g, Float b) { c[0] = r; c[1] = g; c[2] = b; }
+};
+inline RGB operator+(RGB a, RGB b) { return RGB(a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2]); }
+inline RGB operator-(RGB a, RGB b) { return RGB(a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2]); }
+inline RGB operator*(RGB a, RGB b) { return RGB(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2]); }
+inline RGB operator/(RGB a, RGB b) { return RGB(a.c[0] / b.c[0], a.c[1] / b.c[1], a.c[2] / b.c[2]); }
+// spectrum/common.rs:206-211 scale: *s *= f
+inline RGB operator*(RGB a, Float f) { return RGB(a.c[0] * f, a.c[1] * f, a.c[2] * f); }
+inline RGB operator*(Float f, RGB a) { return a * f; }
+// rgb_spectrum.rs:329-358: division by a float scales by 1/f
+inline RGB operator/(RGB a, Float f) { return a * (1.0f / f); }
+inline RGB& operator+=(RGB& a, RGB b) { a = a + b; return a; }
+inline RGB& operator*=(RGB& a, RGB b) { a = a * b; return a; }
+inline bool is_black(RGB a) { return !(a.c[0] != 0.0f) && !(a.c[1] != 0.0f) && !(a.c[2] != 0.0f); }
+inline bool has_nans(RGB a) { return std::isnan(a.c[0]) || std::isnan(a.c[1]) || std::isnan(a.c[2]); }
+// rgb_spectrum.rs:131
+inline Float lum_y(RGB a) { return 0.212671f * a.c[0] + 0.715160f * a.c[1] + 0.072169f * a.c[2]; }
+// spectrum/common.rs:120-124
+inline Float max_component_value(RGB a) { return pmax(pmax(a.c[0], a.c[1]), a.c[2]); }
+inline RGB rgb_sqrt(RGB a) { return RGB(std::sqrt(a.c[0]), std::sqrt(a.c[1]), std::sqrt(a.c[2])); }
+inline RGB rgb_clamp0(RGB a) { return RGB(pclamp(a.c[0], 0.0f, kInfinity), pclamp(a.c[1], 0.0f, kInfinity), pclamp(a.c[2], 0.0f, kInfinity)); }
+// spectrum/common.rs:337-355
+inline void xyz_to_rgb(const Float xyz[3], Float rgb[3]) {
+    rgb[0] = 3.240479f * xyz[0] - 1.537150f * xyz[1] - 0.498535f * xyz[2];
+    rgb[1] = -0.969256f * xyz[0] + 1.875991f * xyz[1] + 0.041556f * xyz[2];
+    rgb[2] = 0.055648f * xyz[0] - 0.204043f * xyz[1] + 1.057311f * xyz[2];
+}
+inline void rgb_to_xyz(const Float rgb[3], Float xyz[3]) {
+    xyz[0] = 0.412453f * rgb[0] + 0.357580f * rgb[1] + 0.180423f * rgb[2];
+    xyz[1] = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];
+    xyz[2] = 0.019334f * rgb[0] + 0.119193f * rgb[1] + 0.950227f * rgb[2];
+}
+
+}  // namespace orc

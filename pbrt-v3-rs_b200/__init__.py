@@ -1,0 +1,249 @@
+"""pbrt-v3-rs_b200 — B200-native ray-intersection + path-integration hot path.
+
+Host-side mirror (Python, over the C ABI in include/b200pt.h) of the reference
+interfaces this path replaces:
+
+  * ``BVHAccel``        accelerators/src/bvh/mod.rs:22-360 (``new``, ``from_params``,
+                        ``world_bound``, ``intersect``, ``intersect_p``)
+  * ``PathIntegrator``  integrators/src/path.rs:22-326 (``from_params``, ``preprocess``,
+                        ``render``, ``li``)
+
+The directory name is not a valid Python identifier; load it with
+``__graft_entry__.load_package()`` which registers it as ``pbrt_v3_rs_b200``.
+
+All compute goes through ``libb200pt.so`` (hand-written sm_100a CUDA).  There is
+no CPU fallback: if the library is missing or no sm_100 device is bound, calls
+raise ``B200PTError``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+
+MISS = 0xFFFFFFFF
+PRIM_FLIP_NORMAL, PRIM_ALPHA_ZERO, PRIM_SHADOW_ALPHA_ZERO = 1, 2, 4
+MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_METAL = 0, 1, 2, 3
+LIGHT_POINT, LIGHT_AREA, LIGHT_INFINITE = 0, 1, 2
+SAMPLER_HALTON, SAMPLER_ZEROTWO = 0, 1
+LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
+
+# numpy views of the 32-byte ray, 16-byte hit and 32-byte node records
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmax", "<f4"), ("d", "<f4", 3), ("time", "<f4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("prim", "<u4"), ("b0", "<f4"), ("b1", "<f4")])
+NODE_DTYPE = np.dtype([("bounds", "<f4", 6), ("offset", "<u4"), ("n_primitives", "<u2"), ("axis", "u1"), ("pad", "u1")])
+assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16 and NODE_DTYPE.itemsize == 32
+
+
+class B200PTError(RuntimeError):
+    pass
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("ks", C.c_float * 3), ("kt", C.c_float * 3),
+                ("eta", C.c_float * 3), ("k", C.c_float * 3), ("sigma", C.c_float), ("urough", C.c_float),
+                ("vrough", C.c_float), ("remap_roughness", C.c_int32)]
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_int32), ("pos", C.c_float * 3), ("L", C.c_float * 3), ("prim", C.c_int32),
+                ("two_sided", C.c_int32), ("light_to_world", C.c_float * 16), ("world_to_light", C.c_float * 16)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("raster_to_camera", C.c_float * 16), ("camera_to_world", C.c_float * 16), ("lens_radius", C.c_float),
+                ("focal_distance", C.c_float), ("shutter_open", C.c_float), ("shutter_close", C.c_float)]
+
+
+class Film(C.Structure):
+    _fields_ = [("xres", C.c_int32), ("yres", C.c_int32), ("crop", C.c_int32 * 4), ("filter_radius", C.c_float * 2),
+                ("filter_table", C.c_float * 256), ("scale", C.c_float), ("max_sample_luminance", C.c_float)]
+
+
+class Sampler(C.Structure):
+    _fields_ = [("type", C.c_int32), ("spp", C.c_int32), ("sample_at_center", C.c_int32), ("dimensions", C.c_int32)]
+
+
+class Integrator(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("pixel_bounds", C.c_int32 * 4),
+                ("light_strategy", C.c_int32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("n_nodes", C.c_int64), ("ordered_prims", C.c_void_p), ("tri_verts", C.c_void_p),
+                ("prim_flags", C.c_void_p), ("prim_material", C.c_void_p), ("prim_light", C.c_void_p), ("n_prims", C.c_int64),
+                ("materials", C.c_void_p), ("n_materials", C.c_int32), ("lights", C.c_void_p), ("n_lights", C.c_int32),
+                ("camera", Camera), ("film", Film), ("sampler", Sampler), ("integrator", Integrator)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libb200pt.so; fails loudly when the CUDA extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200PTError("libb200pt.so is not built (run `python pbrt-v3-rs_b200/build.py`); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    L.b200pt_last_error.restype = C.c_char_p
+    L.b200pt_device_l2_bytes.restype = i64
+    L.b200pt_launch_count.restype = i64
+    L.b200pt_init.argtypes = [C.c_int]
+    L.b200pt_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
+    L.b200pt_triangle_bounds.argtypes = [vp, i64, vp]
+    L.b200pt_accel_create.argtypes = [vp, i64, vp, vp, vp, i64, C.POINTER(vp)]
+    L.b200pt_accel_destroy.argtypes = [vp]
+    L.b200pt_accel_destroy.restype = None
+    L.b200pt_accel_world_bound.argtypes = [vp, vp]
+    L.b200pt_accel_intersect1.argtypes = [vp, vp, vp]
+    L.b200pt_accel_occluded1.argtypes = [vp, vp, vp]
+    L.b200pt_intersect_batch.argtypes = [vp, vp, i64, vp]
+    L.b200pt_occluded_batch.argtypes = [vp, vp, i64, vp]
+    L.b200pt_intersect_batch_device.argtypes = [vp, vp, i64, vp, vp, C.c_int]
+    L.b200pt_occluded_batch_device.argtypes = [vp, vp, i64, vp, vp, C.c_int]
+    L.b200pt_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp)]
+    L.b200pt_scene_destroy.argtypes = [vp]
+    L.b200pt_scene_destroy.restype = None
+    L.b200pt_render_rows.argtypes = [vp, i32, i32, vp]
+    L.b200pt_render_rows_device.argtypes = [vp, i32, i32, vp, vp]
+    L.b200pt_film_resolve.argtypes = [C.POINTER(Film), vp, vp]
+    L.b200pt_li_batch.argtypes = [vp, vp, i64, vp, vp]
+    L.b200pt_scene_ray_counts.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise B200PTError("%s failed (%d): %s" % (what, rc, lib().b200pt_last_error().decode()))
+
+
+_inited = None
+
+
+def init(device=0):
+    """b200pt_init: binds the sm_100 device.  Raises when there is none."""
+    global _inited
+    if _inited == device:
+        return
+    _check(lib().b200pt_init(device), "b200pt_init")
+    _inited = device
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def triangle_bounds(tri_verts):
+    """Triangle::world_bound for n triangles (shapes/src/triangle.rs:427-431)."""
+    v = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
+    out = np.empty((v.shape[0], 6), dtype=np.float32)
+    _check(lib().b200pt_triangle_bounds(_ptr(v), v.shape[0], _ptr(out)), "b200pt_triangle_bounds")
+    return out
+
+
+def build_bvh_sah(prim_bounds, max_prims_in_node=4):
+    """BVHAccel::new(.., SplitMethod::SAH) on the host (mod.rs:43-153): returns (nodes, ordered_prims)."""
+    pb = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
+    n = pb.shape[0]
+    nodes = np.zeros(max(2 * n - 1, 1), dtype=NODE_DTYPE)
+    ordered = np.zeros(max(n, 1), dtype=np.uint32)
+    nn = C.c_int64(0)
+    _check(lib().b200pt_bvh_build_sah(_ptr(pb), n, int(max_prims_in_node), _ptr(nodes), C.byref(nn), _ptr(ordered)),
+           "b200pt_bvh_build_sah")
+    return nodes[:nn.value].copy(), ordered[:n].copy()
+
+
+class BVHAccel:
+    """Device-resident BVHAccel (accelerators/src/bvh/mod.rs).
+
+    ``BVHAccel.from_params({"splitmethod": "sah", "maxnodeprims": 4}, tri_verts)``
+    mirrors ``impl From<(&ParamSet, &[ArcPrimitive])> for BVHAccel`` (mod.rs:339-360)
+    for triangle primitives given as an (n, 9) float32 array of world-space vertices.
+    """
+
+    def __init__(self, tri_verts, nodes, ordered_prims, prim_flags=None):
+        init(_inited if _inited is not None else 0)
+        self.tri_verts = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
+        self.nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+        self.ordered_prims = np.ascontiguousarray(ordered_prims, dtype=np.uint32)
+        self.prim_flags = None if prim_flags is None else np.ascontiguousarray(prim_flags, dtype=np.uint32)
+        h = C.c_void_p()
+        _check(lib().b200pt_accel_create(_ptr(self.nodes), len(self.nodes), _ptr(self.ordered_prims), _ptr(self.tri_verts),
+                                         _ptr(self.prim_flags), self.tri_verts.shape[0], C.byref(h)), "b200pt_accel_create")
+        self._h = h
+
+    @classmethod
+    def from_params(cls, params, tri_verts, prim_flags=None):
+        split = params.get("splitmethod", "sah")
+        if split != "sah":
+            # hlbvh / middle / equal are outside this path
+            raise B200PTError("BVHAccel: only splitmethod 'sah' is built on this path, got %r" % split)
+        max_prims = int(params.get("maxnodeprims", 4)) & 0xFF
+        tv = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
+        nodes, ordered = build_bvh_sah(triangle_bounds(tv), max_prims)
+        return cls(tv, nodes, ordered, prim_flags)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200pt_accel_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    def world_bound(self):
+        out = np.empty(6, dtype=np.float32)
+        _check(lib().b200pt_accel_world_bound(self._h, _ptr(out)), "b200pt_accel_world_bound")
+        return out
+
+    def intersect(self, ray):
+        """Primitive::intersect for one ray record; lowers ray['tmax'] on a hit and returns the hit record or None."""
+        r = np.ascontiguousarray(ray, dtype=RAY_DTYPE).reshape(1)
+        h = np.zeros(1, dtype=HIT_DTYPE)
+        _check(lib().b200pt_accel_intersect1(self._h, _ptr(r), _ptr(h)), "b200pt_accel_intersect1")
+        if hasattr(ray, "dtype") and ray.dtype == RAY_DTYPE:
+            ray["tmax"] = r["tmax"][0]
+        return None if h["prim"][0] == MISS else h[0]
+
+    def intersect_p(self, ray):
+        r = np.ascontiguousarray(ray, dtype=RAY_DTYPE).reshape(1)
+        o = np.zeros(1, dtype=np.uint8)
+        _check(lib().b200pt_accel_occluded1(self._h, _ptr(r), _ptr(o)), "b200pt_accel_occluded1")
+        return bool(o[0])
+
+    def intersect_batch(self, rays):
+        """Closest hit for a HOST array of rays (copies in/out inside the call)."""
+        r = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        h = np.empty(r.shape[0], dtype=HIT_DTYPE)
+        _check(lib().b200pt_intersect_batch(self._h, _ptr(r), r.shape[0], _ptr(h)), "b200pt_intersect_batch")
+        return h
+
+    def occluded_batch(self, rays):
+        r = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        o = np.empty(r.shape[0], dtype=np.uint8)
+        _check(lib().b200pt_occluded_batch(self._h, _ptr(r), r.shape[0], _ptr(o)), "b200pt_occluded_batch")
+        return o
+
+    def intersect_batch_device(self, d_rays_ptr, n, d_hits_ptr, stream=0, variant=0):
+        _check(lib().b200pt_intersect_batch_device(self._h, d_rays_ptr, n, d_hits_ptr, stream, variant),
+               "b200pt_intersect_batch_device")
+
+    def occluded_batch_device(self, d_rays_ptr, n, d_out_ptr, stream=0, variant=0):
+        _check(lib().b200pt_occluded_batch_device(self._h, d_rays_ptr, n, d_out_ptr, stream, variant),
+               "b200pt_occluded_batch_device")
+
+
+def launch_count():
+    return int(lib().b200pt_launch_count())
+
+
+from .scene import PathIntegrator, SceneDescription  # noqa: E402,F401

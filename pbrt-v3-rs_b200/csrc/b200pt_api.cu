@@ -1,0 +1,267 @@
+// C ABI: library init/errors and the accelerator (impl Primitive for BVHAccel,
+// accelerators/src/bvh/mod.rs:156-283) entry points.  See include/b200pt.h.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2 {
+std::atomic<int64_t> g_launches{0};
+int g_device = -1;
+int g_sm_count = 0;
+int64_t g_l2_bytes = 0;
+static thread_local std::string t_error;
+
+int cuda_fail(cudaError_t e, const char* what) {
+    std::string m = std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e);
+    b200pt_set_error(m.c_str());
+    cudaGetLastError();  // clear sticky-less errors
+    return e == cudaErrorMemoryAllocation ? B200PT_ERR_OOM : B200PT_ERR_CUDA;
+}
+
+// Host scratch for the host-buffer batch calls: three chunk slots so the H2D
+// copy, the kernel and the D2H copy of consecutive chunks overlap on their own
+// streams (copies use the two DMA engines, PCIe is full duplex).
+struct BatchScratch {
+    static const int kSlots = 3;
+    static const int64_t kChunk = 1 << 20;  // rays per chunk (32 MB in, 16 MB out)
+    cudaStream_t stream[kSlots] = {nullptr, nullptr, nullptr};
+    void* d_rays[kSlots] = {nullptr, nullptr, nullptr};
+    void* d_out[kSlots] = {nullptr, nullptr, nullptr};
+    bool ready = false;
+    std::mutex mu;
+    int ensure() {
+        if (ready) return B200PT_OK;
+        for (int i = 0; i < kSlots; ++i) {
+            B2_CUDA(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
+            B2_CUDA(cudaMalloc(&d_rays[i], kChunk * sizeof(b200pt_ray)));
+            B2_CUDA(cudaMalloc(&d_out[i], kChunk * sizeof(b200pt_hit)));
+        }
+        ready = true;
+        return B200PT_OK;
+    }
+};
+static BatchScratch g_scratch;
+
+int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered, const float* tri_verts,
+                       const uint32_t* flags, int64_t n_prims, AccelImpl* a) {
+    a->n_nodes = n_nodes;
+    a->n_prims = n_prims;
+    std::memset(&a->dev, 0, sizeof(a->dev));
+    a->dev.root_code = B2_EMPTY_ROOT;
+    a->dev.n_nodes = (int)n_nodes;
+    a->dev.n_prims = n_prims;
+    const float m = 3.402823466e+38f;  // Bounds3f::EMPTY, bounds3.rs:26-29
+    float empty[6] = {m, m, m, -m, -m, -m};
+    std::memcpy(a->world_bound, empty, sizeof(empty));
+    if (n_nodes == 0) return B200PT_OK;
+    std::memcpy(a->world_bound, nodes[0].bounds, sizeof(empty));
+    std::memcpy(a->dev.root_bounds, nodes[0].bounds, sizeof(empty));
+
+    // wide index of every interior reference node, in pre-order
+    std::vector<int32_t> wide_of((size_t)n_nodes, -1);
+    int64_t n_wide = 0;
+    for (int64_t i = 0; i < n_nodes; ++i)
+        if (nodes[i].n_primitives == 0) wide_of[(size_t)i] = (int32_t)n_wide++;
+    a->n_wide = n_wide;
+    auto code_of = [&](int64_t i) -> int32_t {
+        return nodes[i].n_primitives == 0 ? wide_of[(size_t)i] : ~(int32_t)nodes[i].offset;
+    };
+    std::vector<float4> wide((size_t)std::max<int64_t>(n_wide, 1) * 4);
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        if (nodes[i].n_primitives != 0) continue;
+        int64_t c0 = i + 1, c1 = nodes[i].offset;
+        if (c1 <= i || c1 >= n_nodes || c0 >= n_nodes) { b200pt_set_error("b200pt_accel_create: malformed node array"); return B200PT_ERR_INVALID; }
+        const float* a0 = nodes[c0].bounds;
+        const float* a1 = nodes[c1].bounds;
+        float4* q = &wide[(size_t)wide_of[(size_t)i] * 4];
+        q[0] = make_float4(a0[0], a0[1], a0[2], a0[3]);
+        q[1] = make_float4(a0[4], a0[5], a1[0], a1[1]);
+        q[2] = make_float4(a1[2], a1[3], a1[4], a1[5]);
+        int32_t k0 = code_of(c0), k1 = code_of(c1), ax = nodes[i].axis;
+        float f0, f1, f2;
+        std::memcpy(&f0, &k0, 4); std::memcpy(&f1, &k1, 4); std::memcpy(&f2, &ax, 4);
+        q[3] = make_float4(f0, f1, f2, 0.0f);
+    }
+    a->dev.root_code = code_of(0);
+
+    // triangles in BVHAccel.primitives order
+    std::vector<float4> tris((size_t)std::max<int64_t>(n_prims, 1) * 3);
+    for (int64_t j = 0; j < n_prims; ++j) {
+        uint32_t p = ordered[j];
+        if ((int64_t)p >= n_prims) { b200pt_set_error("b200pt_accel_create: ordered_prims index out of range"); return B200PT_ERR_INVALID; }
+        const float* v = tri_verts + 9 * (size_t)p;
+        uint32_t fl = flags ? flags[p] : 0u, zero = 0u;
+        float fp, ff, fz;
+        std::memcpy(&fp, &p, 4); std::memcpy(&ff, &fl, 4); std::memcpy(&fz, &zero, 4);
+        tris[(size_t)j * 3 + 0] = make_float4(v[0], v[1], v[2], fp);
+        tris[(size_t)j * 3 + 1] = make_float4(v[3], v[4], v[5], ff);
+        tris[(size_t)j * 3 + 2] = make_float4(v[6], v[7], v[8], fz);
+    }
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        if (nodes[i].n_primitives == 0) continue;
+        uint32_t cnt = nodes[i].n_primitives;
+        if ((int64_t)nodes[i].offset + cnt > n_prims) { b200pt_set_error("b200pt_accel_create: leaf range out of bounds"); return B200PT_ERR_INVALID; }
+        float fc;
+        std::memcpy(&fc, &cnt, 4);
+        tris[(size_t)nodes[i].offset * 3 + 2].w = fc;
+    }
+    B2_CUDA(cudaMalloc(&a->d_wide, wide.size() * sizeof(float4)));
+    B2_CUDA(cudaMalloc(&a->d_tris, tris.size() * sizeof(float4)));
+    B2_CUDA(cudaMalloc(&a->d_ref, (size_t)n_nodes * 32));
+    B2_CUDA(cudaMemcpy(a->d_wide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(a->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(a->d_ref, nodes, (size_t)n_nodes * 32, cudaMemcpyHostToDevice));
+    a->dev.wide = a->d_wide;
+    a->dev.tris = a->d_tris;
+    a->dev.ref_nodes = a->d_ref;
+    return B200PT_OK;
+}
+
+void accel_free_device(AccelImpl* a) {
+    if (a->d_wide) cudaFree(a->d_wide);
+    if (a->d_tris) cudaFree(a->d_tris);
+    if (a->d_ref) cudaFree(a->d_ref);
+    a->d_wide = a->d_tris = a->d_ref = nullptr;
+}
+
+// Pipelined host-buffer batch (the e2e path): chunk i uses slot i % 3.
+template <class LaunchFn>
+static int run_host_batch(const void* rays, int64_t n, void* out, size_t out_elem, LaunchFn launch) {
+    std::lock_guard<std::mutex> g(g_scratch.mu);
+    int rc = g_scratch.ensure();
+    if (rc) return rc;
+    const int64_t C = BatchScratch::kChunk;
+    int64_t n_chunks = (n + C - 1) / C;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        int slot = (int)(c % BatchScratch::kSlots);
+        int64_t b = c * C, m = std::min<int64_t>(C, n - b);
+        cudaStream_t s = g_scratch.stream[slot];
+        B2_CUDA(cudaMemcpyAsync(g_scratch.d_rays[slot], (const char*)rays + b * sizeof(b200pt_ray), m * sizeof(b200pt_ray),
+                                cudaMemcpyHostToDevice, s));
+        rc = launch(g_scratch.d_rays[slot], m, g_scratch.d_out[slot], s);
+        if (rc) return rc;
+        B2_CUDA(cudaMemcpyAsync((char*)out + b * out_elem, g_scratch.d_out[slot], m * out_elem, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < BatchScratch::kSlots; ++i) B2_CUDA(cudaStreamSynchronize(g_scratch.stream[i]));
+    return B200PT_OK;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+int b200pt_set_error(const char* msg) {
+    t_error = msg ? msg : "";
+    return 0;
+}
+const char* b200pt_last_error(void) { return t_error.c_str(); }
+int b200pt_version(void) { return 100; }
+int b200pt_device_sm_count(void) { return g_sm_count; }
+int64_t b200pt_device_l2_bytes(void) { return g_l2_bytes; }
+int64_t b200pt_launch_count(void) { return g_launches.load(); }
+
+int b200pt_init(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        b200pt_set_error("b200pt_init: no CUDA device visible (this library has no CPU fallback)");
+        return B200PT_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) { b200pt_set_error("b200pt_init: device index out of range"); return B200PT_ERR_INVALID; }
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        b200pt_set_error("b200pt_init: device is not sm_100 (kernels are built for sm_100a only)");
+        return B200PT_ERR_NO_DEVICE;
+    }
+    B2_CUDA(cudaSetDevice(device));
+    g_device = device;
+    g_sm_count = prop.multiProcessorCount;
+    g_l2_bytes = prop.l2CacheSize;
+    return B200PT_OK;
+}
+
+int b200pt_accel_create(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered_prims, const float* tri_verts,
+                        const uint32_t* prim_flags, int64_t n_prims, b200pt_accel** out) {
+    if (!out) { b200pt_set_error("b200pt_accel_create: out is null"); return B200PT_ERR_INVALID; }
+    *out = nullptr;
+    int rc = require_device();
+    if (rc) return rc;
+    if (n_nodes < 0 || n_prims < 0 || (n_nodes > 0 && (!nodes || !ordered_prims || !tri_verts)) || n_nodes > 0x7ffffff0LL) {
+        b200pt_set_error("b200pt_accel_create: invalid argument");
+        return B200PT_ERR_INVALID;
+    }
+    B2_CUDA(cudaSetDevice(g_device));
+    b200pt_accel* a = new b200pt_accel();
+    rc = accel_build_device(nodes, n_nodes, ordered_prims, tri_verts, prim_flags, n_prims, &a->impl);
+    if (rc) { accel_free_device(&a->impl); delete a; return rc; }
+    *out = a;
+    return B200PT_OK;
+}
+
+void b200pt_accel_destroy(b200pt_accel* a) {
+    if (!a) return;
+    accel_free_device(&a->impl);
+    delete a;
+}
+
+int b200pt_accel_world_bound(const b200pt_accel* a, float* bounds6) {
+    if (!a || !bounds6) { b200pt_set_error("b200pt_accel_world_bound: null argument"); return B200PT_ERR_INVALID; }
+    std::memcpy(bounds6, a->impl.world_bound, 6 * sizeof(float));
+    return B200PT_OK;
+}
+
+int b200pt_intersect_batch_device(const b200pt_accel* a, const void* d_rays, int64_t n, void* d_hits, void* stream, int variant) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!a || n < 0 || (n > 0 && (!d_rays || !d_hits))) { b200pt_set_error("b200pt_intersect_batch_device: invalid argument"); return B200PT_ERR_INVALID; }
+    return launch_intersect(a->impl.dev, d_rays, n, d_hits, (cudaStream_t)stream, variant);
+}
+
+int b200pt_occluded_batch_device(const b200pt_accel* a, const void* d_rays, int64_t n, void* d_occluded, void* stream, int variant) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!a || n < 0 || (n > 0 && (!d_rays || !d_occluded))) { b200pt_set_error("b200pt_occluded_batch_device: invalid argument"); return B200PT_ERR_INVALID; }
+    return launch_occluded(a->impl.dev, d_rays, n, d_occluded, (cudaStream_t)stream, variant);
+}
+
+int b200pt_intersect_batch(const b200pt_accel* a, const b200pt_ray* rays, int64_t n, b200pt_hit* hits) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!a || n < 0 || (n > 0 && (!rays || !hits))) { b200pt_set_error("b200pt_intersect_batch: invalid argument"); return B200PT_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(g_device));
+    const DeviceAccel& A = a->impl.dev;
+    return run_host_batch(rays, n, hits, sizeof(b200pt_hit),
+                          [&](void* dr, int64_t m, void* dout, cudaStream_t s) { return launch_intersect(A, dr, m, dout, s, 0); });
+}
+
+int b200pt_occluded_batch(const b200pt_accel* a, const b200pt_ray* rays, int64_t n, uint8_t* occluded) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!a || n < 0 || (n > 0 && (!rays || !occluded))) { b200pt_set_error("b200pt_occluded_batch: invalid argument"); return B200PT_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(g_device));
+    const DeviceAccel& A = a->impl.dev;
+    return run_host_batch(rays, n, occluded, 1,
+                          [&](void* dr, int64_t m, void* dout, cudaStream_t s) { return launch_occluded(A, dr, m, dout, s, 0); });
+}
+
+int b200pt_accel_intersect1(const b200pt_accel* a, b200pt_ray* ray, b200pt_hit* hit) {
+    if (!ray || !hit) { b200pt_set_error("b200pt_accel_intersect1: null argument"); return B200PT_ERR_INVALID; }
+    int rc = b200pt_intersect_batch(a, ray, 1, hit);
+    if (rc) return rc;
+    if (hit->prim != B200PT_MISS) ray->tmax = hit->t;  // Primitive::intersect lowers r.t_max (geometric_primitive.rs:72)
+    return B200PT_OK;
+}
+
+int b200pt_accel_occluded1(const b200pt_accel* a, const b200pt_ray* ray, uint8_t* occluded) {
+    if (!ray || !occluded) { b200pt_set_error("b200pt_accel_occluded1: null argument"); return B200PT_ERR_INVALID; }
+    return b200pt_occluded_batch(a, ray, 1, occluded);
+}
+
+}  // extern "C"

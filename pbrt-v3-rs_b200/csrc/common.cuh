@@ -1,0 +1,60 @@
+// Shared host-side plumbing of libb200pt: error reporting, launch counting,
+// device buffers.  Internal header (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/b200pt.h"
+#include "traverse.cuh"
+
+extern "C" int b200pt_set_error(const char* msg);
+
+namespace b2 {
+
+extern std::atomic<int64_t> g_launches;
+extern int g_device;       // -1 until b200pt_init succeeds
+extern int g_sm_count;
+extern int64_t g_l2_bytes;
+
+int cuda_fail(cudaError_t e, const char* what);  // records message, returns B200PT_ERR_CUDA / OOM
+
+#define B2_CUDA(call)                                      \
+    do {                                                   \
+        cudaError_t _e = (call);                           \
+        if (_e != cudaSuccess) return b2::cuda_fail(_e, #call); \
+    } while (0)
+
+inline int require_device() {
+    if (g_device < 0) {
+        b200pt_set_error("b200pt: no device bound (call b200pt_init first; there is no CPU fallback)");
+        return B200PT_ERR_NO_DEVICE;
+    }
+    return B200PT_OK;
+}
+
+// Host mirror of the device accelerator: owns the device allocations.
+struct AccelImpl {
+    DeviceAccel dev;
+    float4* d_wide = nullptr;
+    float4* d_tris = nullptr;
+    float4* d_ref = nullptr;
+    int64_t n_nodes = 0, n_prims = 0, n_wide = 0;
+    float world_bound[6];
+};
+
+int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered, const float* tri_verts,
+                       const uint32_t* flags, int64_t n_prims, AccelImpl* out);
+void accel_free_device(AccelImpl* a);
+
+// Kernel launchers (traverse_kernels.cu)
+int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant);
+int launch_occluded(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant);
+
+}  // namespace b2
+
+struct b200pt_accel {
+    b2::AccelImpl impl;
+};

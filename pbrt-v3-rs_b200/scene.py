@@ -1,0 +1,377 @@
+"""Scene description + PathIntegrator mirror over the C ABI.
+
+``SceneDescription`` gathers what the reference's ``api`` crate holds when it
+reaches ``pbrt_world_end`` (api/src/lib.rs:447-507): the primitive list (here:
+triangles), materials, lights, camera, film, sampler and integrator parameters,
+keyed by the same ParamSet names.  ``to_desc()`` flattens it into the
+``b200pt_scene_desc`` of include/b200pt.h.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+F32 = np.float32
+
+
+# ---- host-side scene setup math (the reference does this in `api`, above the boundary) --
+def _m4_inverse(m):
+    """Matrix4x4::inverse (core/src/geometry/matrix4x4.rs:55-123), float32 Gauss-Jordan."""
+    minv = np.array(m, dtype=F32).copy()
+    indxc, indxr, ipiv = [0] * 4, [0] * 4, [0] * 4
+    for i in range(4):
+        irow = icol = 0
+        big = F32(0)
+        for j in range(4):
+            if ipiv[j] != 1:
+                for k in range(4):
+                    if ipiv[k] == 0 and abs(minv[j, k]) >= big:
+                        big, irow, icol = abs(minv[j, k]), j, k
+        ipiv[icol] += 1
+        if irow != icol:
+            minv[[irow, icol]] = minv[[icol, irow]]
+        indxr[i], indxc[i] = irow, icol
+        pivinv = F32(1) / minv[icol, icol]
+        minv[icol, icol] = F32(1)
+        minv[icol, :] = minv[icol, :] * pivinv
+        for j in range(4):
+            if j != icol:
+                save = minv[j, icol]
+                minv[j, icol] = F32(0)
+                minv[j, :] = minv[j, :] - minv[icol, :] * save
+    for j in range(3, -1, -1):
+        if indxr[j] != indxc[j]:
+            minv[:, [indxr[j], indxc[j]]] = minv[:, [indxc[j], indxr[j]]]
+    return minv
+
+
+def _m4_mul(a, b):
+    r = np.zeros((4, 4), dtype=F32)
+    for i in range(4):
+        for j in range(4):
+            r[i, j] = F32(F32(F32(a[i, 0] * b[0, j]) + F32(a[i, 1] * b[1, j])) + F32(a[i, 2] * b[2, j])) + F32(a[i, 3] * b[3, j])
+    return r
+
+
+def _norm(v):
+    v = np.asarray(v, dtype=F32)
+    l2 = F32(F32(v[0] * v[0] + v[1] * v[1]) + v[2] * v[2])
+    return v * (F32(1) / np.sqrt(l2, dtype=F32))
+
+
+def _cross(a, b):
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], dtype=F32)
+
+
+def look_at_camera_to_world(eye, look, up):
+    """Transform::look_at (core/src/geometry/transform.rs:191-214): returns camera_to_world."""
+    eye, look, up = (np.asarray(x, dtype=F32) for x in (eye, look, up))
+    d = _norm(look - eye)
+    right = _norm(_cross(_norm(up), d))
+    new_up = _cross(d, right)
+    m = np.eye(4, dtype=F32)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, new_up, d, eye
+    return m
+
+
+def perspective_raster_to_camera(fov, xres, yres, screen_window=None):
+    """PerspectiveCamera::new + ProjectiveCameraData::new (cameras/src/perspective_camera.rs:35-75,
+    core/src/camera.rs:276-306): raster_to_camera = inverse(camera_to_screen) * inverse(screen_to_raster)."""
+    n, f = F32(1e-2), F32(1000.0)
+    persp = np.eye(4, dtype=F32)
+    persp[2, 2] = f / (f - n)
+    persp[2, 3] = -f * n / (f - n)
+    persp[3, 2] = F32(1)
+    persp[3, 3] = F32(0)
+    inv_tan = F32(1) / F32(math.tan(float(F32(fov) * F32(math.pi / 180.0)) / 2.0))
+    # camera_to_screen = scale(inv_tan) * persp; Transform products keep m_inv = rhs.m_inv * lhs.m_inv (transform.rs:644-656)
+    c2s_inv = _m4_mul(_m4_inverse(persp), np.diag([F32(1) / inv_tan, F32(1) / inv_tan, F32(1), F32(1)]).astype(F32))
+    frame = F32(xres) / F32(yres)
+    if screen_window is None:
+        sw = [-frame, frame, F32(-1), F32(1)] if frame > 1 else [F32(-1), F32(1), F32(-1) / frame, F32(1) / frame]
+    else:
+        sw = [F32(x) for x in screen_window]
+    s2 = np.diag([F32(1) / (sw[1] - sw[0]), F32(1) / (sw[2] - sw[3]), F32(1), F32(1)]).astype(F32)
+    # screen_to_raster = scale(res) * scale(1/window) * translate(-window origin); inverse of the product = product of the stored inverses in reverse order (transform.rs:644-656)
+    s1i = np.diag([F32(1) / F32(xres), F32(1) / F32(yres), F32(1), F32(1)]).astype(F32)
+    s2i = np.diag([F32(1) / s2[0, 0], F32(1) / s2[1, 1], F32(1), F32(1)]).astype(F32)
+    tri = np.eye(4, dtype=F32)
+    tri[0, 3], tri[1, 3] = sw[0], sw[3]
+    r2s = _m4_mul(tri, _m4_mul(s2i, s1i))
+    return _m4_mul(c2s_inv, r2s)
+
+
+def filter_table(kind="box", radius=None, alpha=2.0):
+    """Film::new filter table (core/src/film/mod.rs:113-125), 16x16 floats."""
+    if radius is None:
+        radius = (0.5, 0.5) if kind == "box" else (2.0, 2.0)
+    rx, ry = F32(radius[0]), F32(radius[1])
+    tab = np.zeros(256, dtype=F32)
+    if kind == "box":
+        tab[:] = 1.0
+    elif kind == "gaussian":  # filters/src/gaussian.rs
+        a = F32(alpha)
+        ex, ey = np.exp(-a * rx * rx, dtype=F32), np.exp(-a * ry * ry, dtype=F32)
+        k = 0
+        for y in range(16):
+            for x in range(16):
+                px = (F32(x) + F32(0.5)) * rx * F32(1.0 / 16.0)
+                py = (F32(y) + F32(0.5)) * ry * F32(1.0 / 16.0)
+                gx = max(F32(0), np.exp(-a * px * px, dtype=F32) - ex)
+                gy = max(F32(0), np.exp(-a * py * py, dtype=F32) - ey)
+                tab[k] = gx * gy
+                k += 1
+    else:
+        raise ValueError("filter %r is outside this path (box, gaussian only)" % kind)
+    return tab, (float(rx), float(ry))
+
+
+class SceneDescription:
+    """Flat scene: triangles + per-primitive material/light + camera/film/sampler/integrator params."""
+
+    def __init__(self):
+        self.tri_verts = np.zeros((0, 9), dtype=F32)
+        self.prim_material = np.zeros(0, dtype=np.int32)
+        self.prim_light = np.zeros(0, dtype=np.int32)
+        self.prim_flags = np.zeros(0, dtype=np.uint32)
+        self.materials = []   # list of dicts
+        self.lights = []      # list of dicts
+        self.camera = dict(eye=(0, 0, -5), look=(0, 0, 0), up=(0, 1, 0), fov=45.0, lensradius=0.0, focaldistance=1e6,
+                           shutteropen=0.0, shutterclose=1.0)
+        self.film = dict(xresolution=64, yresolution=64, filter="box", scale=1.0, maxsampleluminance=float("inf"))
+        self.sampler = dict(type="halton", pixelsamples=16, samplepixelcenter=False, dimensions=4)
+        self.integrator = dict(maxdepth=5, rrthreshold=1.0, lightsamplestrategy="uniform", pixelbounds=None)
+        self.accel_params = dict(splitmethod="sah", maxnodeprims=4)
+        self.nodes = None
+        self.ordered_prims = None
+        self._keep = []
+
+    # -- scene assembly, mirroring Api::pbrt_shape / pbrt_light_source (api/src/lib.rs:751-811) --
+    def add_material(self, **m):
+        self.materials.append(m)
+        return len(self.materials) - 1
+
+    def add_mesh(self, tri_verts, material, area_light=None, reverse_orientation=False, alpha=1.0, shadowalpha=1.0):
+        """One GeometricPrimitive per triangle; with ``area_light={'L': (r,g,b), 'twosided': False}`` one
+        DiffuseAreaLight per triangle (api/src/lib.rs:783-803)."""
+        tv = np.ascontiguousarray(tri_verts, dtype=F32).reshape(-1, 9)
+        n0 = self.tri_verts.shape[0]
+        n = tv.shape[0]
+        self.tri_verts = np.concatenate([self.tri_verts, tv])
+        self.prim_material = np.concatenate([self.prim_material, np.full(n, material, dtype=np.int32)])
+        flags = (1 if reverse_orientation else 0) | (2 if alpha == 0.0 else 0) | (4 if shadowalpha == 0.0 else 0)
+        self.prim_flags = np.concatenate([self.prim_flags, np.full(n, flags, dtype=np.uint32)])
+        pl = np.full(n, -1, dtype=np.int32)
+        if area_light is not None:
+            for i in range(n):
+                pl[i] = len(self.lights)
+                self.lights.append(dict(type="diffuse", L=tuple(area_light.get("L", (1, 1, 1))), prim=n0 + i,
+                                        twosided=bool(area_light.get("twosided", False))))
+        self.prim_light = np.concatenate([self.prim_light, pl])
+        return n0
+
+    def add_point_light(self, pos, I):
+        self.lights.append(dict(type="point", pos=tuple(pos), L=tuple(I)))
+
+    def add_infinite_light(self, L):
+        self.lights.append(dict(type="infinite", L=tuple(L)))
+
+    # -- flattening --
+    def build_accel(self, builder):
+        """builder(prim_bounds, max_prims) -> (nodes, ordered).  Uses the product's host SAH builder by default."""
+        from . import build_bvh_sah, triangle_bounds  # noqa
+        self.nodes, self.ordered_prims = (builder or build_bvh_sah)(triangle_bounds(self.tri_verts), self.accel_params["maxnodeprims"])
+
+    def sample_bounds(self):
+        xres, yres = self.film["xresolution"], self.film["yresolution"]
+        _, (rx, ry) = filter_table(self.film["filter"], self.film.get("radius"))
+        return (int(math.floor(0 + 0.5 - rx)), int(math.floor(0 + 0.5 - ry)), int(math.ceil(xres - 0.5 + rx)), int(math.ceil(yres - 0.5 + ry)))
+
+    def to_desc(self):
+        from . import Camera, Film, Integrator, Light, Material, Sampler, SceneDesc
+        from . import (LIGHT_AREA, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
+                       MAT_PLASTIC, SAMPLER_HALTON, SAMPLER_ZEROTWO)
+        if self.nodes is None:
+            self.build_accel(None)
+        d = SceneDesc()
+        keep = self._keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data_as(C.c_void_p)
+
+        d.nodes, d.n_nodes = arr(self.nodes, self.nodes.dtype), len(self.nodes)
+        d.ordered_prims = arr(self.ordered_prims, np.uint32)
+        d.tri_verts = arr(self.tri_verts, F32)
+        d.prim_flags = arr(self.prim_flags, np.uint32)
+        d.prim_material = arr(self.prim_material, np.int32)
+        d.prim_light = arr(self.prim_light, np.int32)
+        d.n_prims = self.tri_verts.shape[0]
+
+        mats = (Material * max(1, len(self.materials)))()
+        for i, m in enumerate(self.materials):
+            t = m["type"]
+            M = mats[i]
+            M.remap_roughness = 1 if m.get("remaproughness", True) else 0
+            if t == "matte":     # materials/src/matte.rs:77-84
+                M.type = MAT_MATTE
+                M.kd[:] = m.get("Kd", (0.5, 0.5, 0.5))
+                M.sigma = m.get("sigma", 0.0)
+            elif t == "plastic":  # plastic.rs:104-113
+                M.type = MAT_PLASTIC
+                M.kd[:] = m.get("Kd", (0.25, 0.25, 0.25))
+                M.ks[:] = m.get("Ks", (0.25, 0.25, 0.25))
+                M.urough = M.vrough = m.get("roughness", 0.1)
+            elif t == "glass":   # glass.rs:130-146
+                M.type = MAT_GLASS
+                M.ks[:] = m.get("Kr", (1, 1, 1))
+                M.kt[:] = m.get("Kt", (1, 1, 1))
+                M.eta[0] = m.get("eta", m.get("index", 1.5))
+                M.urough, M.vrough = m.get("uroughness", 0.0), m.get("vroughness", 0.0)
+            elif t == "metal":   # metal.rs:109-133; the default copper SPD->RGB conversion is done by the caller
+                M.type = MAT_METAL
+                M.eta[:] = m.get("eta", (0.19999069, 0.92208463, 1.09987593))
+                M.k[:] = m.get("k", (3.90463543, 2.44763327, 2.13765264))
+                r = m.get("roughness", 0.01)
+                M.urough, M.vrough = m.get("uroughness", r), m.get("vroughness", r)
+            else:
+                raise ValueError("material %r is outside this path" % t)
+        keep.append(mats)
+        d.materials, d.n_materials = C.cast(mats, C.c_void_p), len(self.materials)
+
+        lights = (Light * max(1, len(self.lights)))()
+        ident = np.eye(4, dtype=F32).reshape(-1)
+        for i, l in enumerate(self.lights):
+            Lt = lights[i]
+            Lt.prim = -1
+            Lt.L[:] = l["L"]
+            Lt.light_to_world[:] = l.get("light_to_world", ident)
+            Lt.world_to_light[:] = l.get("world_to_light", ident)
+            if l["type"] == "point":
+                Lt.type = LIGHT_POINT
+                Lt.pos[:] = l["pos"]
+            elif l["type"] == "diffuse":
+                Lt.type = LIGHT_AREA
+                Lt.prim = l["prim"]
+                Lt.two_sided = 1 if l.get("twosided") else 0
+            elif l["type"] == "infinite":
+                Lt.type = LIGHT_INFINITE
+            else:
+                raise ValueError("light %r is outside this path" % l["type"])
+        keep.append(lights)
+        d.lights, d.n_lights = C.cast(lights, C.c_void_p), len(self.lights)
+
+        cam = self.camera
+        xres, yres = self.film["xresolution"], self.film["yresolution"]
+        d.camera.camera_to_world[:] = look_at_camera_to_world(cam["eye"], cam["look"], cam["up"]).reshape(-1)
+        d.camera.raster_to_camera[:] = perspective_raster_to_camera(cam["fov"], xres, yres, cam.get("screenwindow")).reshape(-1)
+        d.camera.lens_radius, d.camera.focal_distance = cam["lensradius"], cam["focaldistance"]
+        d.camera.shutter_open, d.camera.shutter_close = cam["shutteropen"], cam["shutterclose"]
+
+        tab, (rx, ry) = filter_table(self.film["filter"], self.film.get("radius"))
+        d.film.xres, d.film.yres = xres, yres
+        crop = self.film.get("cropwindow", (0.0, 1.0, 0.0, 1.0))  # film/mod.rs:101-110
+        d.film.crop[:] = [int(math.ceil(xres * crop[0])), int(math.ceil(yres * crop[2])), int(math.ceil(xres * crop[1])), int(math.ceil(yres * crop[3]))]
+        d.film.filter_radius[:] = [rx, ry]
+        d.film.filter_table[:] = tab
+        d.film.scale = self.film.get("scale", 1.0)
+        d.film.max_sample_luminance = self.film.get("maxsampleluminance", float("inf"))
+
+        d.sampler.type = SAMPLER_HALTON if self.sampler["type"] == "halton" else SAMPLER_ZEROTWO
+        d.sampler.spp = self.sampler["pixelsamples"]
+        d.sampler.sample_at_center = 1 if self.sampler.get("samplepixelcenter") else 0
+        d.sampler.dimensions = self.sampler.get("dimensions", 4)
+
+        d.integrator.max_depth = self.integrator["maxdepth"]
+        d.integrator.rr_threshold = self.integrator["rrthreshold"]
+        sb = [int(math.floor(d.film.crop[0] + 0.5 - rx)), int(math.floor(d.film.crop[1] + 0.5 - ry)),
+              int(math.ceil(d.film.crop[2] - 0.5 + rx)), int(math.ceil(d.film.crop[3] - 0.5 + ry))]
+        pb = self.integrator.get("pixelbounds")
+        if pb:  # path.rs:296-311
+            sb = [max(sb[0], pb[0]), max(sb[1], pb[1]), min(sb[2], pb[2]), min(sb[3], pb[3])]
+        d.integrator.pixel_bounds[:] = sb
+        strat = self.integrator.get("lightsamplestrategy", "uniform")
+        if strat not in ("uniform", "power"):
+            raise ValueError("lightsamplestrategy %r: the spatial strategy is racy in the reference and outside this path "
+                             "(SURVEY.md §2 row 24)" % strat)
+        d.integrator.light_strategy = LIGHTS_POWER if strat == "power" else LIGHTS_UNIFORM
+        return d
+
+
+class PathIntegrator:
+    """integrators/src/path.rs PathIntegrator over the CUDA wavefront path tracer.
+
+    ``PathIntegrator.from_params(params, sampler_params, camera/film...)`` is folded into the
+    SceneDescription; ``preprocess`` uploads the scene (Scene::new + Integrator::preprocess),
+    ``render`` runs Integrator::render and returns the RGB image (what Film::write_image stores).
+    """
+
+    def __init__(self, scene_description):
+        self.sd = scene_description
+        self._h = None
+
+    def preprocess(self):
+        from . import _check, init, lib, _inited
+        init(_inited if _inited is not None else 0)
+        d = self.sd.to_desc()
+        self._desc = d
+        h = C.c_void_p()
+        _check(lib().b200pt_scene_create(C.byref(d), C.byref(h)), "b200pt_scene_create")
+        self._h = h
+
+    def close(self):
+        from . import lib
+        if self._h:
+            lib().b200pt_scene_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    def film_shape(self):
+        c = self._desc.film.crop
+        return (c[3] - c[1], c[2] - c[0])
+
+    def render_rows(self, row_begin=0, row_end=None):
+        """Renders pixel rows [row_begin,row_end) of the cropped window; returns (H, W, 4) XYZ+weight."""
+        from . import _check, _ptr, lib
+        if self._h is None:
+            self.preprocess()
+        h, w = self.film_shape()
+        row_end = h if row_end is None else row_end
+        film = np.zeros((h, w, 4), dtype=F32)
+        _check(lib().b200pt_render_rows(self._h, row_begin, row_end, _ptr(film)), "b200pt_render_rows")
+        return film
+
+    def resolve(self, film_xyzw):
+        from . import _check, _ptr, lib
+        h, w = film_xyzw.shape[:2]
+        rgb = np.empty((h, w, 3), dtype=F32)
+        f = np.ascontiguousarray(film_xyzw, dtype=F32)
+        _check(lib().b200pt_film_resolve(C.byref(self._desc.film), _ptr(f), _ptr(rgb)), "b200pt_film_resolve")
+        return rgb
+
+    def render(self):
+        """Integrator::render: the whole image as (H, W, 3) RGB float32."""
+        return self.resolve(self.render_rows())
+
+    def li(self, pixel_sample):
+        """Integrator::li for explicit (x, y, sample) triples -> (n,3) radiance, (n,) camera rays."""
+        from . import RAY_DTYPE, _check, _ptr, lib
+        if self._h is None:
+            self.preprocess()
+        ps = np.ascontiguousarray(pixel_sample, dtype=np.int32).reshape(-1, 3)
+        out = np.empty((ps.shape[0], 3), dtype=F32)
+        rays = np.empty(ps.shape[0], dtype=RAY_DTYPE)
+        _check(lib().b200pt_li_batch(self._h, _ptr(ps), ps.shape[0], _ptr(out), _ptr(rays)), "b200pt_li_batch")
+        return out, rays
+
+    def ray_counts(self):
+        from . import _check, _ptr, lib
+        c = np.zeros(3, dtype=np.uint64)
+        _check(lib().b200pt_scene_ray_counts(self._h, _ptr(c)), "b200pt_scene_ray_counts")
+        return c

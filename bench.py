@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's headline metric on its quoted config.
+
+Metric : Mrays/s (closest-hit + any-hit/shadow traversal), whole job over N GPUs.
+Workload: C2 — 1 000 000-triangle displaced sphere, SAH BVH (maxnodeprims 4), per GPU and per step
+          2^24 closest-hit rays (2^23 primary + 2^23 shuffled diffuse-bounce) + 2^24 any-hit rays.
+A "step" = one pass of the hot path over that batch.  `value` is timed with the rays already
+resident in HBM (CUDA events on the launching stream); `e2e` goes through the C-ABI host-buffer
+calls with pinned host memory, copies inside the timed region.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--small]
+
+Under torchrun (N > 1) every rank traces its own batch (weak scaling, no data-path collective);
+the time is the max over ranks.  `--impl reference` times the CPU oracle (the reference cannot be
+built here: no Rust toolchain) on all host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "Mrays/s (closest+shadow) and path samples/s at 1080p on 1/2/4/8 B200 vs CPU ref"
+UNIT = "Mrays/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class _OracleAccelShim:
+    """Reference arm only: BVH built and primaries traced by the CPU oracle, no GPU involved."""
+
+    def __init__(self, tv):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        ge.build_oracle()
+        import oracle_lib as ol
+        self.nodes, self.ordered_prims = ol.build_bvh_sah(ol.triangle_bounds(tv), 4)
+        self._acc = ol.OracleAccel(self.nodes, self.ordered_prims, tv)
+
+    def intersect_batch(self, rays):
+        return self._acc.intersect(rays, counters=False, diag=False)[0]
+
+
+def build_workload(pkg, small, rank, use_oracle=False):
+    """Mesh, BVH (host SAH build), accelerator upload and the three ray sets of C2."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    cfg = wl.C2_SMALL if small else wl.C2_FULL
+    t0 = time.time()
+    tv = wl.c2_mesh(cfg)
+    accel = _OracleAccelShim(tv) if use_oracle else pkg.BVHAccel.from_params({"splitmethod": "sah", "maxnodeprims": 4}, tv)
+    # each rank looks at the mesh from its own side so the batches differ (weak scaling)
+    ang = 2.0 * np.pi * rank / 8.0
+    eye = (3.5 * np.sin(ang), 0.0, -3.5 * np.cos(ang))
+    prim = wl.primary_rays(cfg["width"], cfg["height"])
+    if rank:
+        c, s = np.float32(np.cos(ang)), np.float32(np.sin(ang))
+        d = prim["d"].copy()
+        prim["d"][:, 0] = c * d[:, 0] - s * d[:, 2]
+        prim["d"][:, 2] = s * d[:, 0] + c * d[:, 2]
+        prim["o"] = np.asarray(eye, dtype=np.float32)
+    hits = accel.intersect_batch(prim)
+    bounce = wl.bounce_rays(tv, prim, hits, prim.shape[0])
+    closest = np.concatenate([prim, bounce])
+    shadow = wl.shadow_rays(closest)
+    return dict(cfg=cfg, tv=tv, accel=accel, closest=closest, shadow=shadow, setup_s=time.time() - t0)
+
+
+def cpu_oracle_rate(w, seconds_budget, nthreads):
+    """Times the CPU oracle (closest + any-hit) on a bounded sample of the same rays."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    ge.build_oracle()
+    import oracle_lib as ol  # the one place bench.py executes oracle/: the CPU baseline
+    acc = ol.OracleAccel(w["accel"].nodes, w["accel"].ordered_prims, w["tv"])
+    n = w["closest"].shape[0]
+    m = min(n, 1 << 16)
+    sel = np.random.default_rng(0).choice(n, m, replace=False)
+    t0 = time.time()
+    acc.intersect(w["closest"][sel], nthreads=nthreads, counters=False, diag=False)
+    acc.occluded(w["shadow"][sel], nthreads=nthreads, counters=False)
+    rate = 2 * m / (time.time() - t0)
+    m2 = int(min(n, max(m, rate * seconds_budget / 2)))
+    sel = np.random.default_rng(1).choice(n, m2, replace=False)
+    rc, rs = np.ascontiguousarray(w["closest"][sel]), np.ascontiguousarray(w["shadow"][sel])
+    t0 = time.time()
+    acc.intersect(rc, nthreads=nthreads, counters=False, diag=False)
+    t1 = time.time()
+    acc.occluded(rs, nthreads=nthreads, counters=False)
+    t2 = time.time()
+    return dict(mrays=2 * m2 / (t2 - t0) / 1e6, closest=m2 / (t1 - t0) / 1e6, anyhit=m2 / (t2 - t1) / 1e6, sample_rays=2 * m2, secs=t2 - t0)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return 0
+    pkg = ge.load_package()  # workload generators only (numpy); no GPU, no product kernels on this arm
+    w = build_workload(pkg, args.small, 0, use_oracle=True)
+    nt = os.cpu_count() or 1
+    per_step = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_oracle_rate(w, per_step, nt)
+    res = [cpu_oracle_rate(w, per_step, nt) for _ in range(args.steps)]
+    val = float(np.mean([r["mrays"] for r in res]))
+    ms = float(np.mean([r["secs"] for r in res])) * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nt, "kind": "port",
+                             "sample": "%d rays per step (closest + any-hit halves) sampled from the same 2^25-ray batch; C++ oracle restatement, %d threads" % (res[-1]["sample_rays"], nt)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "closest_mrays": float(np.mean([r["closest"] for r in res])), "anyhit_mrays": float(np.mean([r["anyhit"] for r in res]))}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(w, args):
+    n = int(w["closest"].shape[0])
+    return {"workload": "C2 synthetic ray-cast microbench: %d-triangle displaced sphere, SAH BVH maxnodeprims=4, %d closest-hit rays (primary + shuffled diffuse-bounce) + %d any-hit rays per GPU per step"
+            % (w["tv"].shape[0], n, n), "rays_per_step_per_gpu": 2 * n, "l2_policy": "inputs_larger_than_l2 (1 GiB of rays streamed per step; BVH+triangles 84 MB may stay L2-resident, reported as such)",
+            "sharding": "independent ray batch per GPU, no collective", "variant": args.variant}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--small", action="store_true", help="10K-triangle / 2^14-ray variant (debug only; not a bench value)")
+    ap.add_argument("--variant", type=int, default=0, help="traversal kernel variant (0 default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = ge.load_package()
+    pkg.init(local_rank)
+    w = build_workload(pkg, args.small, rank)
+    accel = w["accel"]
+    n = int(w["closest"].shape[0])
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    d_closest = torch.from_numpy(w["closest"].view(np.float32).reshape(-1, 8)).cuda()
+    d_shadow = torch.from_numpy(w["shadow"].view(np.float32).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    d_occ = torch.empty(n, dtype=torch.uint8, device="cuda")
+
+    # algorithmic work of one step (reference-order walk, counted on the device)
+    nn_c, nt_c = pkg.count_work_device(accel, d_closest.data_ptr(), n, False)
+    nn_s, nt_s = pkg.count_work_device(accel, d_shadow.data_ptr(), n, True)
+    bytes_closest = 32 * nn_c + 36 * nt_c + (32 + 16) * n
+    bytes_shadow = 32 * nn_s + 36 * nt_s + (32 + 1) * n
+
+    def step():
+        accel.intersect_batch_device(d_closest.data_ptr(), n, d_hits.data_ptr(), sp, args.variant)
+        accel.occluded_batch_device(d_shadow.data_ptr(), n, d_occ.data_ptr(), sp, args.variant)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = pkg.launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for k in range(args.steps):
+        accel.intersect_batch_device(d_closest.data_ptr(), n, d_hits.data_ptr(), sp, args.variant)
+        ev[2 * k + 1].record(stream)
+        accel.occluded_batch_device(d_shadow.data_ptr(), n, d_occ.data_ptr(), sp, args.variant)
+        ev[2 * k + 2].record(stream)
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    closest_ms = float(np.mean([ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]))
+    shadow_ms = float(np.mean([ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)]))
+    launches = pkg.launch_count() - launches0
+    clk = clocks.stop()
+
+    # e2e: host buffers through the C-ABI batch calls (pinned memory, H2D + D2H inside the timed region)
+    e2e_ms = None
+    if not args.no_e2e:
+        h_closest = torch.from_numpy(w["closest"].view(np.float32).reshape(-1, 8)).pin_memory()
+        h_shadow = torch.from_numpy(w["shadow"].view(np.float32).reshape(-1, 8)).pin_memory()
+        h_hits = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        h_occ = torch.empty(n, dtype=torch.uint8).pin_memory()
+        L = pkg.lib()
+
+        def e2e_step():
+            pkg._check(L.b200pt_intersect_batch(accel.handle, h_closest.data_ptr(), n, h_hits.data_ptr()), "b200pt_intersect_batch")
+            pkg._check(L.b200pt_occluded_batch(accel.handle, h_shadow.data_ptr(), n, h_occ.data_ptr()), "b200pt_occluded_batch")
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        assert torch.equal(h_hits.view(torch.int32), d_hits.cpu().view(torch.int32)) and torch.equal(h_occ, d_occ.cpu()), "e2e results differ from the resident path"
+
+    # max over ranks
+    t = torch.tensor([total_ms, closest_ms, shadow_ms, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, closest_ms, shadow_ms, e2e_max = [float(x) for x in t.cpu()]
+    ms_per_step = total_ms / args.steps
+    value = world * 2 * n / (ms_per_step * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ach = bytes_closest / (closest_ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(w, args),
+                "closest_mrays": n / (closest_ms * 1e-3) / 1e6, "anyhit_mrays": n / (shadow_ms * 1e-3) / 1e6,
+                "roofline": {"bound": "hbm", "kernel": "k_trace_persistent<closest>" if args.variant == 0 else "k_trace_simple<closest,%d>" % args.variant,
+                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": bytes_closest, "nodes_per_ray": nn_c / n, "tris_per_ray": nt_c / n,
+                             "launch_ms": closest_ms,
+                             "anyhit": {"achieved": bytes_shadow / (shadow_ms * 1e-3) / 1e9, "frac": bytes_shadow / (shadow_ms * 1e-3) / 1e9 / peak,
+                                        "algorithmic_bytes_per_launch": bytes_shadow, "nodes_per_ray": nn_s / n, "tris_per_ray": nt_s / n, "launch_ms": shadow_ms}},
+                "gpu_launches": int(launches), "clocks": clk, "setup_s": w["setup_s"]}
+        if e2e_ms is not None:
+            line["e2e"] = {"value": world * 2 * n / (e2e_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n,
+                           "ms_per_step": e2e_max}
+        if not args.no_cpu_baseline:
+            nt = os.cpu_count() or 1
+            c = cpu_oracle_rate(w, 16.0, nt)
+            line["cpu_baseline"] = {"value": c["mrays"], "unit": UNIT, "cores": nt, "kind": "port", "closest_mrays": c["closest"], "anyhit_mrays": c["anyhit"],
+                                    "sample": "%d rays (closest + any-hit halves) sampled from the step's batch, C++ oracle restatement of the reference on %d threads, %.1f s" % (c["sample_rays"], nt, c["secs"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

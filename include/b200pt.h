@@ -191,6 +191,11 @@ int b200pt_occluded_batch(const b200pt_accel* a, const b200pt_ray* rays, int64_t
  * (0 = default; others are kept for A/B measurement). */
 int b200pt_intersect_batch_device(const b200pt_accel* a, const void* d_rays, int64_t n, void* d_hits, void* stream, int variant);
 int b200pt_occluded_batch_device(const b200pt_accel* a, const void* d_rays, int64_t n, void* d_occluded, void* stream, int variant);
+/* Work accounting for the roofline: totals[0] = nodes whose bounds are tested,
+ * totals[1] = triangle tests, summed over the batch, obtained by walking the 32-byte LinearBVHNode
+ * array in the reference order (BVHAccel::intersect when any_hit == 0, intersect_p otherwise).
+ * d_per_ray (optional, device): 2 x uint32 per ray. Synchronous. */
+int b200pt_count_work_device(const b200pt_accel* a, const void* d_rays, int64_t n, int any_hit, uint64_t totals[2], void* d_per_ray);
 /* Kernel launches issued by this library since init (bench.py's gpu_launches). */
 int64_t b200pt_launch_count(void);
 

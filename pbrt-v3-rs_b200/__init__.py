@@ -106,6 +106,7 @@ def lib():
     L.b200pt_occluded_batch.argtypes = [vp, vp, i64, vp]
     L.b200pt_intersect_batch_device.argtypes = [vp, vp, i64, vp, vp, C.c_int]
     L.b200pt_occluded_batch_device.argtypes = [vp, vp, i64, vp, vp, C.c_int]
+    L.b200pt_count_work_device.argtypes = [vp, vp, i64, C.c_int, vp, vp]
     L.b200pt_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp)]
     L.b200pt_scene_destroy.argtypes = [vp]
     L.b200pt_scene_destroy.restype = None
@@ -190,8 +191,11 @@ class BVHAccel:
         return cls(tv, nodes, ordered, prim_flags)
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().b200pt_accel_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            try:
+                _lib.b200pt_accel_destroy(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     __del__ = close
@@ -240,6 +244,14 @@ class BVHAccel:
     def occluded_batch_device(self, d_rays_ptr, n, d_out_ptr, stream=0, variant=0):
         _check(lib().b200pt_occluded_batch_device(self._h, d_rays_ptr, n, d_out_ptr, stream, variant),
                "b200pt_occluded_batch_device")
+
+
+def count_work_device(accel, d_rays_ptr, n, any_hit=False, d_per_ray_ptr=None):
+    """(N_node, N_tri) totals of the reference-order walk over a device ray batch (roofline accounting)."""
+    tot = np.zeros(2, dtype=np.uint64)
+    _check(lib().b200pt_count_work_device(accel.handle, d_rays_ptr, n, 1 if any_hit else 0, _ptr(tot), d_per_ray_ptr),
+           "b200pt_count_work_device")
+    return int(tot[0]), int(tot[1])
 
 
 def launch_count():

@@ -231,6 +231,21 @@ int b200pt_occluded_batch_device(const b200pt_accel* a, const void* d_rays, int6
     return launch_occluded(a->impl.dev, d_rays, n, d_occluded, (cudaStream_t)stream, variant);
 }
 
+int b200pt_count_work_device(const b200pt_accel* a, const void* d_rays, int64_t n, int any_hit, uint64_t totals[2], void* d_per_ray) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!a || n < 0 || !totals || (n > 0 && !d_rays)) { b200pt_set_error("b200pt_count_work_device: invalid argument"); return B200PT_ERR_INVALID; }
+    unsigned long long* d_tot = nullptr;
+    B2_CUDA(cudaMalloc(&d_tot, 16));
+    B2_CUDA(cudaMemset(d_tot, 0, 16));
+    rc = launch_count_work(a->impl.dev, d_rays, n, any_hit, d_tot, d_per_ray, 0);
+    if (rc) { cudaFree(d_tot); return rc; }
+    cudaError_t e = cudaMemcpy(totals, d_tot, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d_tot);
+    if (e != cudaSuccess) return cuda_fail(e, "count_work copy");
+    return B200PT_OK;
+}
+
 int b200pt_intersect_batch(const b200pt_accel* a, const b200pt_ray* rays, int64_t n, b200pt_hit* hits) {
     int rc = require_device();
     if (rc) return rc;

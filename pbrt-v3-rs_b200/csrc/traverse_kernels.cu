@@ -31,16 +31,6 @@ __global__ void __launch_bounds__(128) k_trace_simple(DeviceAccel A, const float
 // ray indices from a global counter (one atomicAdd per warp, distributed with
 // ballot/popc prefix) and the whole warp re-enters the traversal loop.  The
 // grid is sized to the machine (SMs x resident CTAs), not to the ray count.
-struct TravState {
-    RayCtx r;
-    TriCtx tc;
-    float t_max;
-    int cur;
-    int sp;
-    bool hit;
-    long long ray_id;
-    HitOut h;
-};
 
 template <bool ANY>
 __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, const float4* __restrict__ rays, long long n,
@@ -169,28 +159,122 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
     }
 }
 
+// Work accounting for the roofline: walks the 32-byte LinearBVHNode array in the
+// reference order and counts, per ray, the nodes whose bounds are tested and the triangle tests —
+// the implementation-independent N_node / N_tri of BVHAccel::intersect / intersect_p.
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_count(DeviceAccel A, const float4* __restrict__ rays, long long n, unsigned long long* __restrict__ totals,
+                                               uint2* __restrict__ per_ray) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned nn = 0, nt = 0;
+    if (i < n && A.root_code != B2_EMPTY_ROOT) {
+        float4 r0 = __ldg(rays + 2 * i), r1 = __ldg(rays + 2 * i + 1);
+        RayCtx r;
+        r.ox = r0.x; r.oy = r0.y; r.oz = r0.z;
+        r.ix = 1.0f / r1.x; r.iy = 1.0f / r1.y; r.iz = 1.0f / r1.z;
+        r.nx = r.ix < 0.0f; r.ny = r.iy < 0.0f; r.nz = r.iz < 0.0f;
+        float t_max = r0.w;
+        const TriCtx tc = make_tri_ctx(r1.x, r1.y, r1.z);
+        const V3 o = mk(r0.x, r0.y, r0.z);
+        int stack[B2_STACK];
+        int sp = 0, cur = 0;
+        bool done = false;
+        while (!done) {
+            float4 n0 = ldg4(A.ref_nodes + 2ll * cur), n1 = ldg4(A.ref_nodes + 2ll * cur + 1);
+            float te;
+            uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
+            uint32_t nprims = meta & 0xffffu, axis = (meta >> 16) & 0xffu;
+            ++nn;
+            if (slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, &te) && te < t_max) {
+                if (nprims > 0) {
+                    for (uint32_t k = 0; k < nprims && !done; ++k) {
+                        V3 p0, p1, p2;
+                        uint32_t prim, flags, dummy;
+                        load_tri(A.tris, (long long)offset + k, &p0, &p1, &p2, &prim, &flags, &dummy);
+                        float t, b0, b1, b2;
+                        ++nt;
+                        if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2)) {
+                            if (ANY) { if (!(flags & 6u)) done = true; }
+                            else if (!(flags & 2u)) t_max = t;
+                        }
+                    }
+                    if (sp == 0) done = true; else cur = stack[--sp];
+                } else {
+                    int neg = axis == 0 ? r.nx : (axis == 1 ? r.ny : r.nz);
+                    if (neg) { stack[sp++] = cur + 1; cur = (int)offset; }
+                    else { stack[sp++] = (int)offset; cur = cur + 1; }
+                }
+            } else {
+                if (sp == 0) done = true; else cur = stack[--sp];
+            }
+        }
+        if (per_ray) per_ray[i] = make_uint2(nn, nt);
+    }
+    // warp-aggregate, one atomic pair per warp
+    for (int d = 16; d > 0; d >>= 1) { nn += __shfl_down_sync(0xffffffffu, nn, d); nt += __shfl_down_sync(0xffffffffu, nt, d); }
+    if ((threadIdx.x & 31) == 0 && (nn | nt)) { atomicAdd(totals, (unsigned long long)nn); atomicAdd(totals + 1, (unsigned long long)nt); }
+}
+
+int launch_count_work(const DeviceAccel& A, const void* d_rays, int64_t n, int any_hit, unsigned long long* d_totals, void* d_per_ray, cudaStream_t s) {
+    if (n <= 0) return B200PT_OK;
+    int grid = (int)((n + 127) / 128);
+    if (any_hit) k_count<true><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_totals, (uint2*)d_per_ray);
+    else k_count<false><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_totals, (uint2*)d_per_ray);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_count launch");
+    return B200PT_OK;
+}
+
 static int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
 
-int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant) {
+// Work counters for the persistent kernels: one 8-byte counter per launch in
+// flight, rotated so launches on different streams never share one.
+static const int kCounterRing = 256;
+static unsigned long long* g_counters = nullptr;
+static std::atomic<unsigned> g_counter_next{0};
+static int g_persist_grid[2] = {0, 0};
+
+static int persistent_setup() {
+    if (g_counters) return B200PT_OK;
+    B2_CUDA(cudaMalloc(&g_counters, kCounterRing * sizeof(unsigned long long)));
+    int nb = 0;
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_persistent<false>, 128, 0));
+    g_persist_grid[0] = g_sm_count * (nb > 0 ? nb : 1);
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_persistent<true>, 128, 0));
+    g_persist_grid[1] = g_sm_count * (nb > 0 ? nb : 1);
+    return B200PT_OK;
+}
+
+template <bool ANY>
+static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant) {
     if (n <= 0) return B200PT_OK;
     const int block = 128;
-    if (variant == 1) k_trace_simple<false, 1><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_hits);
-    else k_trace_simple<false, 2><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_hits);
+    if (variant == 1) {
+        k_trace_simple<ANY, 1><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out);
+    } else if (variant == 2) {
+        k_trace_simple<ANY, 2><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out);
+    } else {
+        int rc = persistent_setup();
+        if (rc) return rc;
+        unsigned long long* ctr = g_counters + (g_counter_next.fetch_add(1) % kCounterRing);
+        B2_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
+        int grid = g_persist_grid[ANY ? 1 : 0];
+        int need = grid_for(n, block);
+        if (need < grid) grid = need;
+        k_trace_persistent<ANY><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr);
+    }
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_trace launch");
     return B200PT_OK;
 }
 
+int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant) {
+    return launch_any<false>(A, d_rays, n, d_hits, s, variant);
+}
 int launch_occluded(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant) {
-    if (n <= 0) return B200PT_OK;
-    const int block = 128;
-    if (variant == 1) k_trace_simple<true, 1><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out);
-    else k_trace_simple<true, 2><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out);
-    g_launches.fetch_add(1);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "k_trace launch");
-    return B200PT_OK;
+    return launch_any<true>(A, d_rays, n, d_out, s, variant);
 }
 
 }  // namespace b2

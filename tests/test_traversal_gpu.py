@@ -100,11 +100,20 @@ def test_edge_cases(gpu, oracle):
     rays["d"] = (0, 0, -1)
     pts = [(0.25, 0.25), (0.5, 0.5), (0.0, 0.0), (1.0, 0.0), (0.5, 0.0), (0.75, 0.75), (2.0, 2.0), (1.0, 1.0), (0.3, 0.7)]
     rays["o"] = [(x, y, 1.0) for x, y in pts]
-    rays["tmax"][5] = 1.0          # t == t_max accepted
+    rays["tmax"][5] = 1.0          # t == t_max: the triangle would accept, but the flat leaf box fails t_min < t_max
     g = accel.intersect_batch(rays)
     o, diag, _ = oacc.intersect(rays)
     assert np.array_equal(g["prim"], o["prim"]) and np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32))
-    assert g["prim"][6] == MISS and g["prim"][0] != MISS and g["prim"][5] != MISS
+    assert g["prim"][6] == MISS and g["prim"][0] != MISS and g["prim"][5] == MISS
+    # duplicated triangles: the second candidate has t == t_max and is ACCEPTED (triangle.rs:512-516),
+    # so the last tested primitive wins — traversal order is observable and must match
+    dup = np.concatenate([tv, tv, tv[:1] + np.float32([0, 0, 0.5] * 3)])
+    for mp in (1, 4):
+        ad = gpu.BVHAccel.from_params({"maxnodeprims": mp}, dup)
+        od = oracle.OracleAccel(ad.nodes, ad.ordered_prims, dup)
+        gd, odh = ad.intersect_batch(rays), od.intersect(rays)[0]
+        assert np.array_equal(gd["prim"], odh["prim"]) and np.array_equal(gd["t"].view(np.uint32), odh["t"].view(np.uint32))
+        assert (gd["prim"] != MISS).sum() >= 3
     # shared diagonal edge (0.5,0.5): both triangles accept with equal t -> the LAST tested wins in both
     assert g["prim"][1] == o["prim"][1]
     # single-ray entry points: Primitive::intersect lowers tmax

@@ -1,11 +1,975 @@
-// Scene + PathIntegrator entry points (wavefront path tracer) — under construction.
+// Scene + PathIntegrator entry points: the wavefront path tracer.
+//
+// Reference call stack replaced:
+//   SamplerIntegrator::render / render_tile   core/src/integrator/sampler_integrator.rs:243-415
+//   PathIntegrator::li                        integrators/src/path.rs:103-284
+//   uniform_sample_one_light, estimate_direct core/src/integrator/common.rs:89-299
+//   FilmTile::add_sample, Film::merge/write   core/src/film/film_tile.rs:62-108, film/mod.rs:220-417
+//
+// Wavefront organisation (one wave = up to kWaveCap paths, a path = one (pixel, sample)):
+//   K1 k_raygen     Halton dims 0-4 -> camera ray, path state init
+//   K2a closest-hit over the compacted ray queue            (traverse_kernels.cu)
+//   K4 k_shade      emission, BSDF frame, light pick + sample_li + BSDF MIS sample -> shadow / MIS ray
+//                   queues with pending contributions; BSDF sample -> next ray queue; Russian roulette
+//   K2b any-hit over the shadow queue, K2a closest-hit over the MIS queue
+//   K4' k_resolve   L += beta * (ld_light [if unoccluded] + ld_mis [if the MIS ray reached the light]) / pick_pdf
+//   ... next bounce on the compacted survivors ...
+//   K5 k_film       per pixel, gathers the per-sample radiances in pixel-major / sample order
+//                   (atomic-free, deterministic) and applies the filter table.
+// Per path the order of floating-point accumulation into L is the reference's.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
-extern "C" {
-int b200pt_scene_create(const b200pt_scene_desc*, b200pt_scene** out) { if (out) *out = nullptr; b200pt_set_error("scene: not implemented yet"); return B200PT_ERR_UNSUPPORTED; }
-void b200pt_scene_destroy(b200pt_scene*) {}
-int b200pt_render_rows(b200pt_scene*, int32_t, int32_t, float*) { return B200PT_ERR_UNSUPPORTED; }
-int b200pt_render_rows_device(b200pt_scene*, int32_t, int32_t, void*, void*) { return B200PT_ERR_UNSUPPORTED; }
-int b200pt_film_resolve(const b200pt_film*, const float*, float*) { return B200PT_ERR_UNSUPPORTED; }
-int b200pt_li_batch(b200pt_scene*, const int32_t*, int64_t, float*, b200pt_ray*) { return B200PT_ERR_UNSUPPORTED; }
-int b200pt_scene_ray_counts(const b200pt_scene*, uint64_t*) { return B200PT_ERR_UNSUPPORTED; }
+#include "host_sampler.h"
+#include "shade.cuh"
+
+namespace b2 {
+
+struct DeviceScene {
+    DeviceAccel accel;
+    const float4* prim_verts;  // 3 float4 per ORIGINAL primitive: (p0, bits material), (p1, bits light or -1), (p2, bits flags)
+    const DMaterial* materials;
+    const DLight* lights;
+    const int* infinite_lights;
+    const DInfDistr* inf_distr;
+    const float* light_func;
+    const float* light_cdf;
+    float light_func_int;
+    int n_lights, n_infinite;
+    DHalton halton;
+    DCamera camera;
+    int max_depth;
+    float rr_threshold;
+    float world_radius;
+    int pb[4];  // integrator pixel bounds
+    int sb[4];  // film sample bounds
+};
+
+// Wave buffers.  "slot" arrays are indexed by queue position, "path" arrays by path id within the wave.
+struct Wave {
+    // ray queues (double buffered) and their path ids
+    float4* ray[2];     // 2 float4 per slot
+    int* qpid[2];
+    float4* hit;        // per slot
+    float* hit_b2;
+    // shadow / MIS queues
+    float4* sh_ray;     // 2 float4 per slot
+    uint8_t* sh_occ;
+    float4* mis_ray;
+    float4* mis_hit;
+    // per path
+    float4* L;          // rgb, -
+    float4* beta;       // rgb, eta_scale
+    unsigned long long* hidx;
+    int* meta;          // dim (16) | bounces (8) | specular flag (8)
+    // pending direct lighting, per path
+    float4* pend_a;     // ld_light rgb, pick pdf
+    float4* pend_b;     // mis f rgb, mis weight
+    float4* pend_c;     // beta rgb at the vertex, mis scattering pdf
+    int4* pend_d;       // light index, shadow slot, mis slot, -
+    int* pend_q;        // path ids with a pending record
+    int* counters;      // [0] next rays, [1] shadow rays, [2] mis rays, [3] pending records
+};
+
+B2_D int meta_pack(int dim, int bounces, int spec) { return (dim & 0xffff) | ((bounces & 0xff) << 16) | ((spec & 0xff) << 24); }
+
+// ---- K1: camera rays --------------------------------------------------------------------------
+// Implicit mode (list == nullptr): path p of the wave covers sample (first_sample + p) in pixel-major
+// order over the shard's sample rows: global sample g -> pixel g / spp, sample g % spp.
+// Explicit mode: list holds (x, y, sample) triples.
+__global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long first_sample, int n, int spp, int row0, const int* __restrict__ list,
+                                                 float2* __restrict__ p_film_out, float4* __restrict__ rays_out) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int px, py, s;
+    long long g = first_sample + p;
+    if (list) { px = list[3 * p]; py = list[3 * p + 1]; s = list[3 * p + 2]; }
+    else {
+        long long pix = g / spp;
+        s = (int)(g - pix * spp);
+        int w = S.sb[2] - S.sb[0];
+        px = S.sb[0] + (int)(pix % w);
+        py = row0 + (int)(pix / w);
+    }
+    unsigned long long idx = halton_index(S.halton, px, py, (unsigned long long)s);
+    float u0 = halton_dim(S.halton, idx, 0), u1 = halton_dim(S.halton, idx, 1);
+    P2 pf = mk2((float)px + u0, (float)py + u1);  // sampler/mod.rs:43-51
+    float tu = halton_dim(S.halton, idx, 2);
+    P2 pl = mk2(halton_dim(S.halton, idx, 3), halton_dim(S.halton, idx, 4));
+    Ray32 r = camera_ray(S.camera, pf, tu, pl);
+    bool live = list || (px >= S.pb[0] && px < S.pb[2] && py >= S.pb[1] && py < S.pb[3]);  // sampler_integrator.rs:348
+    W.ray[0][2 * p] = make_float4(r.ox, r.oy, r.oz, live ? r.tmax : -1.0f);  // tmax < 0: the root test fails, the path dies as a miss
+    W.ray[0][2 * p + 1] = make_float4(r.dx, r.dy, r.dz, r.time);
+    W.qpid[0][p] = p;
+    W.L[p] = make_float4(0.0f, 0.0f, 0.0f, live ? 1.0f : 0.0f);
+    W.beta[p] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    W.hidx[p] = idx;
+    W.meta[p] = meta_pack(5, live ? 0 : 255, 0);
+    if (p_film_out) p_film_out[g] = make_float2(pf.x, pf.y);
+    if (rays_out) { rays_out[2 * p] = make_float4(r.ox, r.oy, r.oz, r.tmax); rays_out[2 * p + 1] = make_float4(r.dx, r.dy, r.dz, r.time); }
 }
+
+B2_D void load_prim(const DeviceScene& S, uint32_t prim, V3* p0, V3* p1, V3* p2, int* mat, int* light, uint32_t* flags) {
+    float4 a = ldg4(S.prim_verts + 3ll * prim), b = ldg4(S.prim_verts + 3ll * prim + 1), c = ldg4(S.prim_verts + 3ll * prim + 2);
+    *p0 = mk(a.x, a.y, a.z); *p1 = mk(b.x, b.y, b.z); *p2 = mk(c.x, c.y, c.z);
+    *mat = __float_as_int(a.w); *light = __float_as_int(b.w); *flags = __float_as_uint(c.w);
+}
+
+B2_D void store_ray(float4* q, int slot, V3 o, V3 d, float tmax, float time) {
+    q[2 * slot] = make_float4(o.x, o.y, o.z, tmax);
+    q[2 * slot + 1] = make_float4(d.x, d.y, d.z, time);
+}
+
+// ---- K4: shade --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, int n_active) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_active) return;
+    const int pid = W.qpid[cur][slot];
+    const float4 r0 = W.ray[cur][2 * slot], r1 = W.ray[cur][2 * slot + 1];
+    const float4 hit = W.hit[slot];
+    const float hb2 = W.hit_b2[slot];
+    const V3 ray_d = mk(r1.x, r1.y, r1.z);
+    const float time = r1.w;
+    int meta = W.meta[pid];
+    int dim = meta & 0xffff, bounces = (meta >> 16) & 0xff;
+    bool specular_bounce = ((meta >> 24) & 0xff) != 0;
+    if (bounces == 255) return;  // pixel outside the integrator's pixel bounds: no sample is taken
+    float4 Lw = W.L[pid], bw = W.beta[pid];
+    RGB L = rgb(Lw.x, Lw.y, Lw.z), beta = rgb(bw.x, bw.y, bw.z);
+    float eta_scale = bw.w;
+    const unsigned long long hidx = W.hidx[pid];
+    const uint32_t prim = __float_as_uint(hit.y);
+    const bool found = prim != 0xffffffffu;
+    (void)r0;
+
+    V3 p0, p1, p2;
+    int mat = 0, alight = -1;
+    uint32_t pflags = 0;
+    SurfHit sh;
+    if (found) {
+        load_prim(S, prim, &p0, &p1, &p2, &mat, &alight, &pflags);
+        sh = triangle_surface3(p0, p1, p2, hit.z, hit.w, hb2, (pflags & 1u) != 0);
+    }
+    // path.rs:123-134: emitted light at the vertex / from the environment
+    if (bounces == 0 || specular_bounce) {
+        if (found) {
+            if (alight >= 0) L = L + beta * area_l(S.lights[alight], sh.n, -ray_d);
+        } else {
+            for (int i = 0; i < S.n_infinite; ++i) L = L + beta * infinite_le(S.lights[S.infinite_lights[i]], ray_d);
+        }
+    }
+    if (!found || bounces >= S.max_depth) {  // path.rs:137
+        W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
+        return;
+    }
+    // Hit::new normalises wo (interaction/mod.rs:117-136); BSDF::new frame (bsdf.rs:100-120)
+    V3 wo_raw = -ray_d;
+    float l2 = length_squared(wo_raw);
+    V3 hit_wo = (l2 == 0.0f) ? wo_raw : wo_raw / sqrtf(l2);
+    BSDF bsdf;
+    bsdf.ns = sh.n; bsdf.ng = sh.n;
+    bsdf.ss = normalize(sh.dpdu);
+    bsdf.ts = cross(bsdf.ns, bsdf.ss);
+    bsdf.m = S.materials + mat;
+    const uint32_t kNoSpec = BSDF_ALL & ~BSDF_SPECULAR;
+
+    // path.rs:162-173 -> uniform_sample_one_light (integrator/common.rs:89-133)
+    if (bsdf_num_components(bsdf, kNoSpec) > 0 && S.n_lights > 0) {
+        float u_pick = halton_dim(S.halton, hidx, dim); dim += 1;
+        // Distribution1D::sample_discrete, distribution_1d.rs:81-94
+        int ln = find_interval_cdf(S.light_cdf, S.n_lights + 1, u_pick);
+        float pick_pdf = S.light_func_int > 0.0f ? S.light_func[ln] / (S.light_func_int * (float)S.n_lights) : 0.0f;
+        if (pick_pdf != 0.0f) {
+            P2 u_light = mk2(halton_dim(S.halton, hidx, dim), halton_dim(S.halton, hidx, dim + 1)); dim += 2;
+            P2 u_scatter = mk2(halton_dim(S.halton, hidx, dim), halton_dim(S.halton, hidx, dim + 1)); dim += 2;
+            const DLight& light = S.lights[ln];
+            // ---- estimate_direct (common.rs:146-299), light-sampling half ----
+            RGB ld_light = rgb1(0.0f);
+            int shadow_slot = -1, mis_slot = -1;
+            bool li_valid = false;
+            V3 wi = mk(0.0f, 0.0f, 0.0f), lp1 = wi, lp1_err = wi, lp1_n = wi;
+            float light_pdf = 0.0f;
+            RGB Li = rgb1(0.0f);
+            V3 q0 = mk(0, 0, 0), q1 = q0, q2 = q0;  // area light triangle
+            bool lflip = false;
+            if (light.type == LT_POINT) {  // point.rs:83-94
+                V3 pl = mk(light.pos[0], light.pos[1], light.pos[2]);
+                wi = normalize(pl - sh.p);
+                light_pdf = 1.0f;
+                lp1 = pl;
+                Li = ldrgb(light.L) / distance_squared(pl, sh.p);
+                li_valid = true;
+            } else if (light.type == LT_AREA) {
+                int m2, l2i; uint32_t f2;
+                load_prim(S, (uint32_t)light.prim, &q0, &q1, &q2, &m2, &l2i, &f2);
+                lflip = (f2 & 1u) != 0;
+                // Triangle::sample (triangle.rs:918-949) + Shape::sample_solid_angle (shape.rs:64-79)
+                float su0 = sqrtf(u_light.x);
+                float bx = 1.0f - su0, by = u_light.y * su0;
+                V3 p = bx * q0 + by * q1 + (1.0f - bx - by) * q2;
+                V3 n = normalize(cross(q1 - q0, q2 - q0));
+                if (lflip) n = -1.0f * n;
+                V3 pas = vabs(bx * q0) + vabs(by * q1) + vabs((1.0f - bx - by) * q2);
+                V3 p_err = kGamma6 * pas;
+                float pdf = 1.0f / light.area;
+                V3 w = p - sh.p;
+                if (length_squared(w) == 0.0f) pdf = 0.0f;
+                else {
+                    w = normalize(w);
+                    pdf *= distance_squared(sh.p, p) / abs_dot(n, -w);
+                    if (isinf(pdf)) pdf = 0.0f;
+                }
+                V3 w2 = p - sh.p;  // DiffuseAreaLight::sample_li, diffuse.rs:114-129
+                float wl2 = length_squared(w2);
+                if (!(pdf == 0.0f || wl2 == 0.0f)) {
+                    w2 = w2 / sqrtf(wl2);
+                    wi = w2; light_pdf = pdf;
+                    Li = area_l(light, n, -w2);
+                    lp1 = p; lp1_err = p_err; lp1_n = n;
+                    li_valid = true;
+                }
+            } else {  // InfiniteAreaLight::sample_li, infinite.rs:133-175
+                const DInfDistr& D = S.inf_distr[light.inf_slot];
+                float pdf1, pdf0; int v, dummy;
+                float d1 = distr_sample_continuous(D.mfunc, D.mcdf, D.mfunc_int, 2, u_light.y, &pdf1, &v);
+                float d0 = distr_sample_continuous(D.func[v], D.cdf[v], D.func_int[v], 2, u_light.x, &pdf0, &dummy);
+                float map_pdf = pdf0 * pdf1;
+                if (map_pdf != 0.0f) {
+                    float theta = d1 * kPi, phi = d0 * kTwoPi;
+                    float cos_t = cosf(theta), sin_t = sinf(theta);
+                    float sin_p = sinf(phi), cos_p = cosf(phi);
+                    wi = xf3(light.l2w, mk(sin_t * cos_p, sin_t * sin_p, cos_t));
+                    light_pdf = map_pdf / (kTwoPi * kPi * sin_t);
+                    if (sin_t == 0.0f) light_pdf = 0.0f;
+                    lp1 = sh.p + wi * (2.0f * S.world_radius);
+                    Li = inf_lookup(ldrgb(light.L), mk2(d0, d1));
+                    li_valid = true;
+                }
+            }
+            float scattering_pdf = 0.0f;
+            if (li_valid && light_pdf > 0.0f && !is_black(Li)) {
+                RGB f = bsdf_f(bsdf, hit_wo, wi, kNoSpec) * abs_dot(wi, sh.n);
+                scattering_pdf = bsdf_pdf(bsdf, hit_wo, wi, kNoSpec);
+                if (!is_black(f)) {
+                    // VisibilityTester -> Hit::spawn_ray_to_hit (interaction/mod.rs:212-223)
+                    V3 origin = offset_ray_origin(sh.p, sh.p_error, sh.n, lp1 - sh.p);
+                    V3 target = offset_ray_origin(lp1, lp1_err, lp1_n, origin - lp1);
+                    shadow_slot = atomicAdd(&W.counters[1], 1);
+                    store_ray(W.sh_ray, shadow_slot, origin, target - origin, 1.0f - kShadowEps, time);
+                    if (light.type == LT_POINT) ld_light = f * Li / light_pdf;
+                    else {
+                        float wgt = power_heuristic(light_pdf, scattering_pdf);
+                        ld_light = f * Li * wgt / light_pdf;
+                    }
+                }
+            }
+            // ---- BSDF-sampling half (non-delta lights only) ----
+            RGB mis_f = rgb1(0.0f);
+            float mis_w = 1.0f, mis_pdf = 0.0f;
+            if (light.type != LT_POINT) {
+                BxDFSample bs = bsdf_sample_f(bsdf, hit_wo, u_scatter, kNoSpec);
+                V3 wi2 = bs.wi;
+                RGB f = bs.f * abs_dot(wi2, sh.n);
+                bool sampled_specular = (bs.type & BSDF_SPECULAR) != 0;
+                if (!is_black(f) && bs.pdf > 0.0f) {
+                    float weight = 1.0f;
+                    bool ok = true;
+                    V3 ro = offset_ray_origin(sh.p, sh.p_error, sh.n, wi2);  // Hit::spawn_ray
+                    if (!sampled_specular) {
+                        float lp;
+                        if (light.type == LT_AREA) {  // Shape::pdf_solid_angle, shape.rs:81-107
+                            TriCtx tc = make_tri_ctx(wi2.x, wi2.y, wi2.z);
+                            float t, c0, c1, c2;
+                            lp = 0.0f;
+                            if (triangle_test(ro, tc, __int_as_float(0x7f800000), q0, q1, q2, &t, &c0, &c1, &c2) && triangle_nondegenerate(q0, q1, q2)) {
+                                SurfHit lh = triangle_surface3(q0, q1, q2, c0, c1, c2, lflip);
+                                lp = distance_squared(sh.p, lh.p) / (abs_dot(lh.n, -wi2) * light.area);
+                                if (isinf(lp)) lp = 0.0f;
+                            }
+                        } else {  // infinite.rs:201-211
+                            V3 w = xf3(light.w2l, wi2);
+                            float theta = spherical_theta(w), phi = spherical_phi(w);
+                            float sin_t = sinf(theta);
+                            if (sin_t == 0.0f) lp = 0.0f;
+                            else {
+                                const DInfDistr& D = S.inf_distr[light.inf_slot];
+                                float fu = phi * kInvTwoPi * 2.0f, fv = theta * kInvPi * 2.0f;  // Distribution2D::pdf, distribution_2d.rs
+                                int iu = (!(fu == fu) || fu <= 0.0f) ? 0 : (int)fu; iu = iu > 1 ? 1 : iu;
+                                int iv = (!(fv == fv) || fv <= 0.0f) ? 0 : (int)fv; iv = iv > 1 ? 1 : iv;
+                                lp = (D.func[iv][iu] / D.mfunc_int) / (kTwoPi * kPi * sin_t);
+                            }
+                        }
+                        if (lp == 0.0f) ok = false;  // common.rs:258-260: return ld
+                        else weight = power_heuristic(bs.pdf, lp);
+                    }
+                    if (ok) {
+                        mis_slot = atomicAdd(&W.counters[2], 1);
+                        store_ray(W.mis_ray, mis_slot, ro, wi2, __int_as_float(0x7f800000), time);
+                        mis_f = f; mis_w = weight; mis_pdf = bs.pdf;
+                    }
+                }
+            }
+            if (shadow_slot >= 0 || mis_slot >= 0) {
+                int k = atomicAdd(&W.counters[3], 1);
+                W.pend_q[k] = pid;
+                W.pend_a[pid] = make_float4(ld_light.r, ld_light.g, ld_light.b, pick_pdf);
+                W.pend_b[pid] = make_float4(mis_f.r, mis_f.g, mis_f.b, mis_w);
+                W.pend_c[pid] = make_float4(beta.r, beta.g, beta.b, mis_pdf);
+                W.pend_d[pid] = make_int4(ln, shadow_slot, mis_slot, 0);
+            }
+        }
+    }
+
+    // path.rs:175-206: sample the BSDF for the next direction
+    P2 u = mk2(halton_dim(S.halton, hidx, dim), halton_dim(S.halton, hidx, dim + 1)); dim += 2;
+    V3 wo = -ray_d;
+    BxDFSample bs = bsdf_sample_f(bsdf, wo, u, BSDF_ALL);
+    if (is_black(bs.f) || bs.pdf == 0.0f) {
+        W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
+        return;
+    }
+    beta = beta * (bs.f * abs_dot(bs.wi, sh.n) / bs.pdf);
+    specular_bounce = (bs.type & BSDF_SPECULAR) != 0;
+    if ((bs.type & BSDF_SPECULAR) && (bs.type & BSDF_TRANSMISSION)) {
+        float eta = 1.0f;  // BSDF::new(.., None): every in-scope material leaves bsdf.eta at 1.0
+        eta_scale *= dot(wo, sh.n) > 0.0f ? eta * eta : 1.0f / (eta * eta);
+    }
+    V3 next_o = offset_ray_origin(sh.p, sh.p_error, sh.n, bs.wi);
+    // path.rs:264-277: Russian roulette
+    RGB rr_beta = beta * eta_scale;
+    bool alive = true;
+    if (max_component_value(rr_beta) < S.rr_threshold && bounces > 3) {
+        float q = pmax(0.05f, 1.0f - max_component_value(rr_beta));
+        float ur = halton_dim(S.halton, hidx, dim); dim += 1;
+        if (ur < q) alive = false;
+        else beta = beta / (1.0f - q);
+    }
+    W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
+    if (!alive) return;
+    bounces += 1;
+    W.beta[pid] = make_float4(beta.r, beta.g, beta.b, eta_scale);
+    W.meta[pid] = meta_pack(dim, bounces, specular_bounce ? 1 : 0);
+    int ns = atomicAdd(&W.counters[0], 1);
+    store_ray(W.ray[cur ^ 1], ns, next_o, bs.wi, __int_as_float(0x7f800000), time);
+    W.qpid[cur ^ 1][ns] = pid;
+}
+
+// ---- K4': resolve pending direct lighting ------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resolve(DeviceScene S, Wave W, int n_pend) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pend) return;
+    const int pid = W.pend_q[i];
+    float4 a = W.pend_a[pid], b = W.pend_b[pid], c = W.pend_c[pid];
+    int4 d = W.pend_d[pid];
+    RGB ld = rgb1(0.0f);
+    if (d.y >= 0 && !W.sh_occ[d.y]) ld = ld + rgb(a.x, a.y, a.z);  // common.rs:205-225
+    if (d.z >= 0) {  // common.rs:266-296
+        const DLight& light = S.lights[d.x];
+        float4 mh = W.mis_hit[d.z];
+        float4 md = W.mis_ray[2 * d.z + 1];
+        V3 wi = mk(md.x, md.y, md.z);
+        uint32_t prim = __float_as_uint(mh.y);
+        RGB Li = rgb1(0.0f);
+        if (prim != 0xffffffffu) {
+            V3 p0, p1, p2; int mat, al; uint32_t fl;
+            load_prim(S, prim, &p0, &p1, &p2, &mat, &al, &fl);
+            if (al == d.x) {
+                V3 n = normalize(cross(p0 - p2, p1 - p2));
+                if (fl & 1u) n = -n;
+                Li = area_l(light, n, -wi);
+            }
+        } else if (light.type == LT_INFINITE) {
+            Li = infinite_le(light, wi);
+        }
+        if (!is_black(Li)) ld = ld + rgb(b.x, b.y, b.z) * Li * rgb1(1.0f) * b.w / c.w;
+    }
+    RGB add = rgb(c.x, c.y, c.z) * (ld / a.w);  // path.rs:165: beta * (estimate / light_pdf)
+    float4 Lw = W.L[pid];
+    W.L[pid] = make_float4(Lw.x + add.r, Lw.y + add.g, Lw.z + add.b, Lw.w);
+}
+
+// Copies the wave's final radiances into the per-sample store (sanitised, sampler_integrator.rs:374-401).
+__global__ void __launch_bounds__(256) k_store_samples(Wave W, int n, float4* __restrict__ out) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float4 l = W.L[p];
+    RGB c = rgb(l.x, l.y, l.z);
+    float y = lum_y(c);
+    if (isnan(c.r) || isnan(c.g) || isnan(c.b) || y < -1e-5f || isinf(y)) c = rgb1(0.0f);
+    out[p] = make_float4(c.r, c.g, c.b, l.w);
+}
+
+// ---- K5: film --------------------------------------------------------------------------------
+struct DFilm {
+    int crop[4];
+    float rx, ry, inv_rx, inv_ry;
+    float max_lum;
+    int sb[4];
+    int tile;  // reference tile size (16): a sample only reaches pixels of its own tile's pixel bounds
+};
+// One thread per film pixel of the rendered rows: gathers, in pixel-major then sample order, every
+// sample of this shard whose filter window covers the pixel (film_tile.rs:62-108).
+__global__ void __launch_bounds__(128) k_film(DFilm F, const float* __restrict__ table, const float4* __restrict__ sample_L,
+                                              const float2* __restrict__ p_film, int spp, int srow0, int srow1, int prow0, int prow1,
+                                              float4* __restrict__ film) {
+    int w = F.crop[2] - F.crop[0];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * (prow1 - prow0)) return;
+    int x = F.crop[0] + i % w, y = prow0 + i / w;
+    int sw = F.sb[2] - F.sb[0];
+    // candidate source pixels: those whose sample positions can reach (x, y)
+    int qx0 = (int)floorf((float)x + 0.5f - F.rx) - 1, qx1 = (int)ceilf((float)x + 0.5f + F.rx) + 1;
+    int qy0 = (int)floorf((float)y + 0.5f - F.ry) - 1, qy1 = (int)ceilf((float)y + 0.5f + F.ry) + 1;
+    qx0 = max(qx0, F.sb[0]); qx1 = min(qx1, F.sb[2]);
+    qy0 = max(qy0, srow0); qy1 = min(qy1, srow1);
+    RGB sum = rgb1(0.0f);
+    float wsum = 0.0f;
+    for (int qy = qy0; qy < qy1; ++qy)
+        for (int qx = qx0; qx < qx1; ++qx) {
+            // pixel bounds of the reference tile that owns sample pixel (qx, qy) (film/mod.rs:182-198)
+            int tx0 = F.sb[0] + ((qx - F.sb[0]) / F.tile) * F.tile, ty0 = F.sb[1] + ((qy - F.sb[1]) / F.tile) * F.tile;
+            int tx1 = min(tx0 + F.tile, F.sb[2]), ty1 = min(ty0 + F.tile, F.sb[3]);
+            int bx0 = max((int)ceilf((float)tx0 - 0.5f - F.rx), F.crop[0]), by0 = max((int)ceilf((float)ty0 - 0.5f - F.ry), F.crop[1]);
+            int bx1 = min((int)floorf((float)tx1 - 0.5f + F.rx) + 1, F.crop[2]), by1 = min((int)floorf((float)ty1 - 0.5f + F.ry) + 1, F.crop[3]);
+            if (x < bx0 || x >= bx1 || y < by0 || y >= by1) continue;
+            long long base = ((long long)(qy - srow0) * sw + (qx - F.sb[0])) * spp;
+            for (int s = 0; s < spp; ++s) {
+                float4 l = sample_L[base + s];
+                if (l.w == 0.0f) continue;  // pixel outside the integrator's pixel bounds
+                float2 pf = p_film[base + s];
+                float dx = pf.x - 0.5f, dy = pf.y - 0.5f;
+                int p0x = (int)ceilf(dx - F.rx), p0y = (int)ceilf(dy - F.ry);
+                int p1x = (int)floorf(dx + F.rx) + 1, p1y = (int)floorf(dy + F.ry) + 1;
+                if (x < p0x || x >= p1x || y < p0y || y >= p1y) continue;
+                RGB c = rgb(l.x, l.y, l.z);
+                float ly = lum_y(c);
+                if (ly > F.max_lum) c = c * F.max_lum / ly;
+                float fx = pabs(((float)x - dx) * F.inv_rx * 16.0f), fy = pabs(((float)y - dy) * F.inv_ry * 16.0f);
+                int ix = (int)pmin(floorf(fx), 15.0f), iy = (int)pmin(floorf(fy), 15.0f);
+                float fw = table[iy * 16 + ix];
+                sum = sum + c * 1.0f * fw;  // contrib_sum += l * sample_weight * filter_weight
+                wsum += fw;
+            }
+        }
+    // Film::merge_film_tile: tile RGB -> XYZ (film/mod.rs:243-248); accumulated into the shard's film
+    float X = 0.412453f * sum.r + 0.357580f * sum.g + 0.180423f * sum.b;
+    float Y = 0.212671f * sum.r + 0.715160f * sum.g + 0.072169f * sum.b;
+    float Z = 0.019334f * sum.r + 0.119193f * sum.g + 0.950227f * sum.b;
+    long long o = (long long)(y - F.crop[1]) * w + (x - F.crop[0]);
+    film[o] = make_float4(X, Y, Z, wsum);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SceneImpl {
+    AccelImpl accel;
+    DeviceScene dev;
+    b200pt_film film;
+    b200pt_sampler sampler;
+    std::vector<void*> allocs;
+    float* d_filter_table = nullptr;
+    Wave wave;
+    int wave_cap = 0;
+    uint64_t rays[3] = {0, 0, 0};
+    std::mutex mu;
+    int sample_bounds[4];
+};
+
+static const int kWaveCap = 1 << 22;
+
+template <class T> static int dev_upload(SceneImpl* s, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    B2_CUDA(cudaMalloc(&p, bytes));
+    s->allocs.push_back(p);
+    if (!v.empty()) B2_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)p;
+    return B200PT_OK;
+}
+template <class T> static int dev_alloc(SceneImpl* s, size_t n, T** out) {
+    void* p = nullptr;
+    B2_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    s->allocs.push_back(p);
+    *out = (T*)p;
+    return B200PT_OK;
+}
+
+// TrowbridgeReitzDistribution::roughness_to_alpha (trowbridge_reitz.rs:45-53), host f32
+static float roughness_to_alpha(float roughness) {
+    roughness = roughness > 1e-3f ? roughness : 1e-3f;
+    float x = std::log(roughness);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+static float clamp0(float v) { return v < 0.0f ? 0.0f : (v > INFINITY ? INFINITY : v); }
+static bool black3(const float* c) { return !(c[0] != 0.0f) && !(c[1] != 0.0f) && !(c[2] != 0.0f); }
+static float alpha_clamp(float a) { return 0.001f > a ? 0.001f : a; }  // TrowbridgeReitzDistribution::new: max(0.001, alpha)
+
+// materials/src/{matte,plastic,glass,metal}.rs compute_scattering_functions with constant textures,
+// evaluated once per material instead of once per intersection.
+static DMaterial make_material(const b200pt_material& m) {
+    DMaterial d;
+    std::memset(&d, 0, sizeof(d));
+    auto lobe = [&](int kind, uint32_t type) -> DBxDF& {
+        DBxDF& x = d.bx[d.n_bxdf++];
+        x.kind = kind; x.type = type;
+        x.fr_eta_i = x.fr_eta_t = 1.0f; x.ax = x.ay = 1.0f; x.eta_a = x.eta_b = 1.0f;
+        return x;
+    };
+    switch (m.type) {
+        case B200PT_MAT_MATTE: {
+            float r[3] = {clamp0(m.kd[0]), clamp0(m.kd[1]), clamp0(m.kd[2])};
+            float sig = m.sigma < 0.0f ? 0.0f : (m.sigma > 90.0f ? 90.0f : m.sigma);
+            if (!black3(r)) {
+                if (sig == 0.0f) { DBxDF& x = lobe(BX_LAMBERT, BSDF_REFLECTION | BSDF_DIFFUSE); std::memcpy(x.r, r, 12); }
+                else {
+                    DBxDF& x = lobe(BX_OREN_NAYAR, BSDF_REFLECTION | BSDF_DIFFUSE);
+                    std::memcpy(x.r, r, 12);
+                    float sg = sig * (3.14159265358979323846f / 180.0f), s2 = sg * sg;  // oren_nayar.rs:20-31
+                    x.on_a = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));
+                    x.on_b = 0.45f * s2 / (s2 + 0.09f);
+                }
+            }
+            break;
+        }
+        case B200PT_MAT_PLASTIC: {
+            float kd[3] = {clamp0(m.kd[0]), clamp0(m.kd[1]), clamp0(m.kd[2])}, ks[3] = {clamp0(m.ks[0]), clamp0(m.ks[1]), clamp0(m.ks[2])};
+            if (!black3(kd)) { DBxDF& x = lobe(BX_LAMBERT, BSDF_REFLECTION | BSDF_DIFFUSE); std::memcpy(x.r, kd, 12); }
+            if (!black3(ks)) {
+                DBxDF& x = lobe(BX_MF_REFL, BSDF_REFLECTION | BSDF_GLOSSY);
+                std::memcpy(x.r, ks, 12);
+                x.conductor = 0; x.fr_eta_i = 1.5f; x.fr_eta_t = 1.0f;
+                float rough = m.urough;
+                if (m.remap_roughness) rough = roughness_to_alpha(rough);
+                x.ax = x.ay = alpha_clamp(rough);
+            }
+            break;
+        }
+        case B200PT_MAT_GLASS: {
+            float eta = m.eta[0], ur = m.urough, vr = m.vrough;
+            float r[3] = {clamp0(m.ks[0]), clamp0(m.ks[1]), clamp0(m.ks[2])}, t[3] = {clamp0(m.kt[0]), clamp0(m.kt[1]), clamp0(m.kt[2])};
+            if (!(black3(r) && black3(t))) {
+                bool is_spec = ur == 0.0f && vr == 0.0f;
+                if (is_spec) {  // allow_multiple_lobes is always true on the path integrator (path.rs:145)
+                    DBxDF& x = lobe(BX_FRESNEL_SPECULAR, BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR);
+                    std::memcpy(x.r, r, 12); std::memcpy(x.t, t, 12);
+                    x.eta_a = 1.0f; x.eta_b = eta;
+                } else {
+                    if (m.remap_roughness) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+                    if (!black3(r)) {
+                        DBxDF& x = lobe(BX_MF_REFL, BSDF_REFLECTION | BSDF_GLOSSY);
+                        std::memcpy(x.r, r, 12);
+                        x.conductor = 0; x.fr_eta_i = 1.0f; x.fr_eta_t = eta;
+                        x.ax = alpha_clamp(ur); x.ay = alpha_clamp(vr);
+                    }
+                    if (!black3(t)) {
+                        DBxDF& x = lobe(BX_MF_TRANS, BSDF_TRANSMISSION | BSDF_GLOSSY);
+                        std::memcpy(x.t, t, 12);
+                        x.eta_a = 1.0f; x.eta_b = eta;
+                        x.ax = alpha_clamp(ur); x.ay = alpha_clamp(vr);
+                    }
+                }
+            }
+            break;
+        }
+        case B200PT_MAT_METAL: {
+            float ur = m.urough, vr = m.vrough;
+            if (m.remap_roughness) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+            DBxDF& x = lobe(BX_MF_REFL, BSDF_REFLECTION | BSDF_GLOSSY);
+            x.r[0] = x.r[1] = x.r[2] = 1.0f;
+            x.conductor = 1;
+            std::memcpy(x.c_eta_t, m.eta, 12); std::memcpy(x.c_k, m.k, 12);
+            x.ax = alpha_clamp(ur); x.ay = alpha_clamp(vr);
+            break;
+        }
+    }
+    return d;
+}
+
+// Host f32 helpers with the reference's operation order (host code is built with -ffp-contract=off).
+static RGB h_inf_lookup(const float* L, float sx, float sy) {
+    float s = sx * 1.0f - 0.5f, t = sy * 1.0f - 0.5f;
+    float s0 = std::floor(s), t0 = std::floor(t);
+    float ds = s - s0, dt = t - t0;
+    RGB l = rgb(L[0], L[1], L[2]);
+    return l * (1.0f - ds) * (1.0f - dt) + l * (1.0f - ds) * dt + l * ds * (1.0f - dt) + l * ds * dt;
+}
+struct HostDistr1D {  // core/src/sampling/distribution_1d.rs:22-48
+    std::vector<float> func, cdf;
+    float func_int = 0.0f;
+    void init(const std::vector<float>& f) {
+        func = f;
+        size_t n = f.size();
+        cdf.assign(n + 1, 0.0f);
+        for (size_t i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + f[i - 1] / (float)n;
+        func_int = cdf[n];
+        if (func_int == 0.0f) { for (size_t i = 1; i < n + 1; ++i) cdf[i] = (float)i / (float)n; }
+        else { for (size_t i = 1; i < n + 1; ++i) cdf[i] /= func_int; }
+    }
+};
+
+static int wave_alloc(SceneImpl* s, int cap) {
+    Wave& W = s->wave;
+    for (int k = 0; k < 2; ++k) {
+        int rc = dev_alloc(s, (size_t)cap * 2, &W.ray[k]); if (rc) return rc;
+        rc = dev_alloc(s, (size_t)cap, &W.qpid[k]); if (rc) return rc;
+    }
+    int rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.hit))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.hit_b2))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap * 2, &W.sh_ray))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.sh_occ))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap * 2, &W.mis_ray))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.mis_hit))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.L))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.beta))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.hidx))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.meta))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.pend_a))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.pend_b))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.pend_c))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.pend_d))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.pend_q))) return rc;
+    if ((rc = dev_alloc(s, (size_t)8, &W.counters))) return rc;
+    s->wave_cap = cap;
+    return B200PT_OK;
+}
+
+// Runs the bounce loop for the n paths currently initialised in the wave (queue 0).
+static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
+    Wave& W = s->wave;
+    int cur = 0, n_active = n;
+    s->rays[0] += (uint64_t)n;
+    for (int iter = 0; n_active > 0 && iter <= s->dev.max_depth + 1; ++iter) {
+        int rc = launch_intersect(s->dev.accel, W.ray[cur], n_active, W.hit, st, 0, W.hit_b2);
+        if (rc) return rc;
+        s->rays[1] += (uint64_t)n_active;
+        B2_CUDA(cudaMemsetAsync(W.counters, 0, 4 * sizeof(int), st));
+        k_shade<<<(n_active + 127) / 128, 128, 0, st>>>(s->dev, W, cur, n_active);
+        g_launches.fetch_add(1);
+        int cnt[4];
+        B2_CUDA(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        if (cnt[1] > 0) { rc = launch_occluded(s->dev.accel, W.sh_ray, cnt[1], W.sh_occ, st, 0); if (rc) return rc; s->rays[2] += (uint64_t)cnt[1]; }
+        if (cnt[2] > 0) { rc = launch_intersect(s->dev.accel, W.mis_ray, cnt[2], W.mis_hit, st, 0, nullptr); if (rc) return rc; s->rays[1] += (uint64_t)cnt[2]; }
+        if (cnt[3] > 0) { k_resolve<<<(cnt[3] + 255) / 256, 256, 0, st>>>(s->dev, W, cnt[3]); g_launches.fetch_add(1); }
+        cur ^= 1;
+        n_active = cnt[0];
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wavefront kernels");
+    return B200PT_OK;
+}
+
+}  // namespace b2
+
+struct b200pt_scene {
+    b2::SceneImpl impl;
+};
+
+using namespace b2;
+
+extern "C" {
+
+int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
+    if (!out) { b200pt_set_error("b200pt_scene_create: out is null"); return B200PT_ERR_INVALID; }
+    *out = nullptr;
+    int rc = require_device();
+    if (rc) return rc;
+    if (!d || d->n_prims < 0 || d->n_nodes < 0 || (d->n_prims > 0 && (!d->nodes || !d->ordered_prims || !d->tri_verts || !d->prim_material)) ||
+        (d->n_materials > 0 && !d->materials) || (d->n_lights > 0 && !d->lights)) {
+        b200pt_set_error("b200pt_scene_create: invalid scene description");
+        return B200PT_ERR_INVALID;
+    }
+    if (d->sampler.type != B200PT_SAMPLER_HALTON) {
+        b200pt_set_error("b200pt_scene_create: only the Halton sampler is implemented on the device in this round (02sequence: SURVEY §7, next)");
+        return B200PT_ERR_UNSUPPORTED;
+    }
+    for (int64_t i = 0; i < d->n_prims; ++i)
+        if (d->prim_material[i] < 0 || d->prim_material[i] >= d->n_materials) { b200pt_set_error("b200pt_scene_create: primitive without a material (null-BSDF pass-through is outside this path)"); return B200PT_ERR_UNSUPPORTED; }
+    B2_CUDA(cudaSetDevice(g_device));
+    b200pt_scene* sc = new b200pt_scene();
+    SceneImpl* s = &sc->impl;
+    auto fail = [&](int code) { b200pt_scene_destroy(sc); return code; };
+    rc = accel_build_device(d->nodes, d->n_nodes, d->ordered_prims, d->tri_verts, d->prim_flags, d->n_prims, &s->accel);
+    if (rc) return fail(rc);
+    DeviceScene& D = s->dev;
+    std::memset(&D, 0, sizeof(D));
+    D.accel = s->accel.dev;
+    s->film = d->film;
+    s->sampler = d->sampler;
+
+    // primitives in original order with their material / light / flags
+    std::vector<float4> pv((size_t)d->n_prims * 3);
+    for (int64_t i = 0; i < d->n_prims; ++i) {
+        const float* v = d->tri_verts + 9 * i;
+        int32_t mat = d->prim_material[i], lt = d->prim_light ? d->prim_light[i] : -1;
+        uint32_t fl = d->prim_flags ? d->prim_flags[i] : 0u;
+        float fm, fl2, ff;
+        std::memcpy(&fm, &mat, 4); std::memcpy(&fl2, &lt, 4); std::memcpy(&ff, &fl, 4);
+        pv[3 * i] = make_float4(v[0], v[1], v[2], fm);
+        pv[3 * i + 1] = make_float4(v[3], v[4], v[5], fl2);
+        pv[3 * i + 2] = make_float4(v[6], v[7], v[8], ff);
+    }
+    if ((rc = dev_upload(s, pv, &D.prim_verts))) return fail(rc);
+
+    std::vector<DMaterial> mats;
+    for (int i = 0; i < d->n_materials; ++i) mats.push_back(make_material(d->materials[i]));
+    if ((rc = dev_upload(s, mats, &D.materials))) return fail(rc);
+
+    // Scene::new (core/src/scene.rs:50-77): world bound, infinite lights, Light::preprocess
+    V3 wc = mk(0, 0, 0);
+    float radius = 0.0f;
+    if (d->n_nodes > 0) {  // Bounds3::bounding_sphere, bounds3.rs:196-208
+        const float* b = d->nodes[0].bounds;
+        V3 lo = mk(b[0], b[1], b[2]), hi = mk(b[3], b[4], b[5]);
+        wc = (1.0f - 0.5f) * lo + 0.5f * hi;
+        bool inside = (wc.x >= lo.x && wc.x <= hi.x) && (wc.y >= lo.y && wc.y <= hi.y) && (wc.z >= lo.z && wc.z <= hi.z);
+        radius = inside ? std::sqrt(length_squared(wc - hi)) : 0.0f;
+    }
+    D.world_radius = radius;
+    std::vector<DLight> lights((size_t)d->n_lights);
+    std::vector<int> inf_ids;
+    std::vector<DInfDistr> inf_distr;
+    std::vector<float> power_y((size_t)d->n_lights);
+    for (int i = 0; i < d->n_lights; ++i) {
+        const b200pt_light& l = d->lights[i];
+        DLight& o = lights[(size_t)i];
+        std::memset(&o, 0, sizeof(o));
+        o.type = l.type; o.prim = l.prim; o.two_sided = l.two_sided; o.inf_slot = -1;
+        std::memcpy(o.pos, l.pos, 12); std::memcpy(o.L, l.L, 12);
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) { o.l2w[3 * r + c] = l.light_to_world[4 * r + c]; o.w2l[3 * r + c] = l.world_to_light[4 * r + c]; }
+        RGB Lr = rgb(l.L[0], l.L[1], l.L[2]);
+        RGB power = rgb1(0.0f);
+        if (l.type == B200PT_LIGHT_POINT) power = kFourPi * Lr;  // point.rs:96-98
+        else if (l.type == B200PT_LIGHT_AREA) {
+            if (l.prim < 0 || l.prim >= d->n_prims) { b200pt_set_error("b200pt_scene_create: area light primitive out of range"); return fail(B200PT_ERR_INVALID); }
+            const float* v = d->tri_verts + 9 * (size_t)l.prim;
+            V3 p0 = mk(v[0], v[1], v[2]), p1 = mk(v[3], v[4], v[5]), p2 = mk(v[6], v[7], v[8]);
+            o.area = 0.5f * std::sqrt(length_squared(cross(p1 - p0, p2 - p0)));  // Triangle::area, triangle.rs:906-911
+            float sgn = l.two_sided ? 2.0f : 1.0f;
+            power = sgn * Lr * o.area * kPi;  // diffuse.rs:131-134
+        } else if (l.type == B200PT_LIGHT_INFINITE) {
+            o.inf_slot = (int)inf_distr.size();
+            inf_ids.push_back(i);
+            DInfDistr dd;  // compute_scalar_image + Distribution2D::new, infinite.rs:326-369
+            std::vector<float> mf;
+            for (int v = 0; v < 2; ++v) {
+                float vp = ((float)v + 0.5f) / 2.0f;
+                float sin_t = std::sin(kPi * ((float)v + 0.5f) / 2.0f);
+                std::vector<float> row;
+                for (int u = 0; u < 2; ++u) {
+                    float up = ((float)u + 0.5f) / 2.0f;
+                    row.push_back(lum_y(h_inf_lookup(l.L, up, vp)) * sin_t);
+                }
+                HostDistr1D h; h.init(row);
+                for (int u = 0; u < 2; ++u) dd.func[v][u] = h.func[u];
+                for (int u = 0; u < 3; ++u) dd.cdf[v][u] = h.cdf[u];
+                dd.func_int[v] = h.func_int;
+                mf.push_back(h.func_int);
+            }
+            HostDistr1D m; m.init(mf);
+            for (int u = 0; u < 2; ++u) dd.mfunc[u] = m.func[u];
+            for (int u = 0; u < 3; ++u) dd.mcdf[u] = m.cdf[u];
+            dd.mfunc_int = m.func_int;
+            inf_distr.push_back(dd);
+            RGB spec = h_inf_lookup(l.L, 0.5f, 0.5f);  // infinite.rs:177-186
+            power = kPi * radius * radius * spec;
+        } else { b200pt_set_error("b200pt_scene_create: unknown light type"); return fail(B200PT_ERR_INVALID); }
+        power_y[(size_t)i] = lum_y(power);
+    }
+    if ((rc = dev_upload(s, lights, &D.lights))) return fail(rc);
+    if ((rc = dev_upload(s, inf_ids, &D.infinite_lights))) return fail(rc);
+    if ((rc = dev_upload(s, inf_distr, &D.inf_distr))) return fail(rc);
+    D.n_lights = d->n_lights;
+    D.n_infinite = (int)inf_ids.size();
+    // create_light_sample_distribution (light_distrib/mod.rs:59-70)
+    int strat = d->n_lights == 1 ? B200PT_LIGHTS_UNIFORM : d->integrator.light_strategy;
+    HostDistr1D ld;
+    std::vector<float> lf;
+    for (int i = 0; i < d->n_lights; ++i) lf.push_back(strat == B200PT_LIGHTS_UNIFORM ? 1.0f : power_y[(size_t)i]);
+    ld.init(lf);
+    if ((rc = dev_upload(s, ld.func, &D.light_func))) return fail(rc);
+    if ((rc = dev_upload(s, ld.cdf, &D.light_cdf))) return fail(rc);
+    D.light_func_int = ld.func_int;
+
+    // Film::get_sample_bounds (film/mod.rs:150-159)
+    const b200pt_film& f = d->film;
+    s->sample_bounds[0] = (int)std::floor((float)f.crop[0] + 0.5f - f.filter_radius[0]);
+    s->sample_bounds[1] = (int)std::floor((float)f.crop[1] + 0.5f - f.filter_radius[1]);
+    s->sample_bounds[2] = (int)std::ceil((float)f.crop[2] - 0.5f + f.filter_radius[0]);
+    s->sample_bounds[3] = (int)std::ceil((float)f.crop[3] - 0.5f + f.filter_radius[1]);
+    std::memcpy(D.sb, s->sample_bounds, 16);
+    std::memcpy(D.pb, d->integrator.pixel_bounds, 16);
+    D.max_depth = d->integrator.max_depth;
+    D.rr_threshold = d->integrator.rr_threshold;
+
+    // HaltonSampler::new over the sample bounds (samplers/src/halton.rs:61-100, 262-275)
+    const b2host::HaltonTables& ht = b2host::halton_tables();
+    b2host::HaltonParams hp = b2host::halton_params(D.sb[2] - D.sb[0], D.sb[3] - D.sb[1]);
+    if ((rc = dev_upload(s, ht.perms, &D.halton.perms))) return fail(rc);
+    if ((rc = dev_upload(s, ht.primes, &D.halton.primes))) return fail(rc);
+    if ((rc = dev_upload(s, ht.prime_sums, &D.halton.prime_sums))) return fail(rc);
+    for (int i = 0; i < 2; ++i) { D.halton.base_scale[i] = hp.base_scale[i]; D.halton.base_exp[i] = hp.base_exp[i]; D.halton.mult_inv[i] = hp.mult_inv[i]; }
+    D.halton.stride = hp.stride;
+    D.halton.sample_at_center = d->sampler.sample_at_center;
+
+    std::memcpy(D.camera.r2c, d->camera.raster_to_camera, 64);
+    std::memcpy(D.camera.c2w, d->camera.camera_to_world, 64);
+    D.camera.lens_radius = d->camera.lens_radius; D.camera.focal_distance = d->camera.focal_distance;
+    D.camera.shutter_open = d->camera.shutter_open; D.camera.shutter_close = d->camera.shutter_close;
+
+    std::vector<float> tab(f.filter_table, f.filter_table + 256);
+    const float* dt = nullptr;
+    if ((rc = dev_upload(s, tab, &dt))) return fail(rc);
+    s->d_filter_table = (float*)dt;
+    *out = sc;
+    return B200PT_OK;
+}
+
+void b200pt_scene_destroy(b200pt_scene* sc) {
+    if (!sc) return;
+    for (void* p : sc->impl.allocs) cudaFree(p);
+    accel_free_device(&sc->impl.accel);
+    delete sc;
+}
+
+int b200pt_scene_ray_counts(const b200pt_scene* s, uint64_t counts[3]) {
+    if (!s || !counts) { b200pt_set_error("b200pt_scene_ray_counts: null argument"); return B200PT_ERR_INVALID; }
+    counts[0] = s->impl.rays[0]; counts[1] = s->impl.rays[1]; counts[2] = s->impl.rays[2];
+    return B200PT_OK;
+}
+
+int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_end, void* d_film_xyzw, void* stream) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!sc || !d_film_xyzw) { b200pt_set_error("b200pt_render_rows_device: null argument"); return B200PT_ERR_INVALID; }
+    SceneImpl* s = &sc->impl;
+    std::lock_guard<std::mutex> g(s->mu);  // render serialises per scene
+    B2_CUDA(cudaSetDevice(g_device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const b200pt_film& f = s->film;
+    const int cw = f.crop[2] - f.crop[0], ch = f.crop[3] - f.crop[1];
+    if (row_begin < 0 || row_end > ch || row_begin > row_end) { b200pt_set_error("b200pt_render_rows_device: row range outside the cropped window"); return B200PT_ERR_INVALID; }
+    B2_CUDA(cudaMemsetAsync(d_film_xyzw, 0, (size_t)cw * ch * sizeof(float4), st));
+    s->rays[0] = s->rays[1] = s->rays[2] = 0;
+    if (row_begin == row_end) return B200PT_OK;
+    // sample rows owned by this shard: the pixel rows, extended to the sample bounds at the image's top/bottom edge
+    const int* sb = s->sample_bounds;
+    int prow0 = f.crop[1] + row_begin, prow1 = f.crop[1] + row_end;
+    int srow0 = row_begin == 0 ? sb[1] : prow0, srow1 = row_end == ch ? sb[3] : prow1;
+    const int sw = sb[2] - sb[0], spp = s->sampler.spp;
+    const long long n_samples = (long long)(srow1 - srow0) * sw * spp;
+    if (!s->wave_cap && (rc = wave_alloc(s, kWaveCap))) return rc;
+    float4* d_L = nullptr;
+    float2* d_pf = nullptr;
+    B2_CUDA(cudaMalloc(&d_L, (size_t)std::max<long long>(n_samples, 1) * sizeof(float4)));
+    cudaError_t e = cudaMalloc(&d_pf, (size_t)std::max<long long>(n_samples, 1) * sizeof(float2));
+    if (e != cudaSuccess) { cudaFree(d_L); return cuda_fail(e, "cudaMalloc p_film"); }
+    for (long long first = 0; first < n_samples && !rc; first += s->wave_cap) {
+        int n = (int)std::min<long long>(s->wave_cap, n_samples - first);
+        k_raygen<<<(n + 255) / 256, 256, 0, st>>>(s->dev, s->wave, first, n, spp, srow0, nullptr, d_pf, nullptr);
+        g_launches.fetch_add(1);
+        rc = run_wave(s, n, st);
+        if (rc) break;
+        k_store_samples<<<(n + 255) / 256, 256, 0, st>>>(s->wave, n, d_L + first);
+        g_launches.fetch_add(1);
+    }
+    if (!rc) {
+        DFilm F;
+        std::memcpy(F.crop, f.crop, 16);
+        F.rx = f.filter_radius[0]; F.ry = f.filter_radius[1];
+        F.inv_rx = 1.0f / F.rx; F.inv_ry = 1.0f / F.ry;
+        F.max_lum = f.max_sample_luminance;
+        std::memcpy(F.sb, sb, 16);
+        F.tile = 16;
+        // This shard's samples also reach pixel rows of the neighbouring shards when the filter is wider than a
+        // pixel: accumulate them too (apron); the shards' films are summed afterwards, each contribution counted once.
+        int apron = (int)std::ceil(F.ry + 0.5f);
+        int frow0 = std::max(f.crop[1], prow0 - apron), frow1 = std::min(f.crop[3], prow1 + apron);
+        int npix = cw * (frow1 - frow0);
+        k_film<<<(npix + 127) / 128, 128, 0, st>>>(F, s->d_filter_table, d_L, d_pf, spp, srow0, srow1, frow0, frow1, (float4*)d_film_xyzw);
+        g_launches.fetch_add(1);
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "render");
+    }
+    cudaFree(d_L);
+    cudaFree(d_pf);
+    return rc;
+}
+
+int b200pt_render_rows(b200pt_scene* sc, int32_t row_begin, int32_t row_end, float* film_xyzw) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!sc || !film_xyzw) { b200pt_set_error("b200pt_render_rows: null argument"); return B200PT_ERR_INVALID; }
+    const b200pt_film& f = sc->impl.film;
+    size_t bytes = (size_t)(f.crop[2] - f.crop[0]) * (f.crop[3] - f.crop[1]) * sizeof(float4);
+    void* d = nullptr;
+    B2_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+    rc = b200pt_render_rows_device(sc, row_begin, row_end, d, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy(film_xyzw, d, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "film download");
+    }
+    cudaFree(d);
+    return rc;
+}
+
+// Film::write_image / get_pixel_rgb (film/mod.rs:356-417), no splats on this path.
+int b200pt_film_resolve(const b200pt_film* f, const float* film_xyzw, float* rgb_out) {
+    if (!f || !film_xyzw || !rgb_out) { b200pt_set_error("b200pt_film_resolve: null argument"); return B200PT_ERR_INVALID; }
+    size_t n = (size_t)(f->crop[2] - f->crop[0]) * (f->crop[3] - f->crop[1]);
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = film_xyzw + 4 * i;
+        float c[3];
+        c[0] = 3.240479f * p[0] - 1.537150f * p[1] - 0.498535f * p[2];
+        c[1] = -0.969256f * p[0] + 1.875991f * p[1] + 0.041556f * p[2];
+        c[2] = 0.055648f * p[0] - 0.204043f * p[1] + 1.057311f * p[2];
+        for (int k = 0; k < 3; ++k) {
+            float v = c[k];
+            if (p[3] != 0.0f) { float inv = 1.0f / p[3]; v = (v * inv) > 0.0f ? (v * inv) : 0.0f; }
+            v *= f->scale;
+            rgb_out[3 * i + k] = v;
+        }
+    }
+    return B200PT_OK;
+}
+
+int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, float* li_out, b200pt_ray* rays_out) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!sc || n < 0 || (n > 0 && (!pixel_sample || !li_out))) { b200pt_set_error("b200pt_li_batch: invalid argument"); return B200PT_ERR_INVALID; }
+    SceneImpl* s = &sc->impl;
+    std::lock_guard<std::mutex> g(s->mu);
+    B2_CUDA(cudaSetDevice(g_device));
+    if (!s->wave_cap && (rc = wave_alloc(s, kWaveCap))) return rc;
+    int* d_list = nullptr;
+    float4 *d_L = nullptr, *d_rays = nullptr;
+    const int cap = s->wave_cap;
+    B2_CUDA(cudaMalloc(&d_list, (size_t)cap * 3 * sizeof(int)));
+    cudaMalloc(&d_L, (size_t)cap * sizeof(float4));
+    cudaMalloc(&d_rays, (size_t)cap * 2 * sizeof(float4));
+    std::vector<float4> hL;
+    for (int64_t first = 0; first < n && !rc; first += cap) {
+        int m = (int)std::min<int64_t>(cap, n - first);
+        cudaMemcpy(d_list, pixel_sample + 3 * first, (size_t)m * 3 * sizeof(int), cudaMemcpyHostToDevice);
+        k_raygen<<<(m + 255) / 256, 256>>>(s->dev, s->wave, 0, m, s->sampler.spp, 0, d_list, nullptr, d_rays);
+        g_launches.fetch_add(1);
+        rc = run_wave(s, m, 0);
+        if (rc) break;
+        k_store_samples<<<(m + 255) / 256, 256>>>(s->wave, m, d_L);
+        g_launches.fetch_add(1);
+        hL.resize((size_t)m);
+        cudaError_t e = cudaMemcpy(hL.data(), d_L, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "li download"); break; }
+        for (int i = 0; i < m; ++i) { li_out[3 * (first + i)] = hL[i].x; li_out[3 * (first + i) + 1] = hL[i].y; li_out[3 * (first + i) + 2] = hL[i].z; }
+        if (rays_out) cudaMemcpy(rays_out + first, d_rays, (size_t)m * sizeof(b200pt_ray), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_list); cudaFree(d_L); cudaFree(d_rays);
+    return rc;
+}
+
+}  // extern "C"

@@ -50,7 +50,7 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
 void accel_free_device(AccelImpl* a);
 
 // Kernel launchers (traverse_kernels.cu)
-int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant);
+int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant, float* d_b2 = nullptr);
 int launch_occluded(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant);
 int launch_count_work(const DeviceAccel& A, const void* d_rays, int64_t n, int any_hit, unsigned long long* d_totals, void* d_per_ray, cudaStream_t s);
 

@@ -1,0 +1,20 @@
+// Host-side sampler tables (internal header).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace b2host {
+
+struct HaltonTables {
+    std::vector<int> primes, prime_sums;
+    std::vector<uint16_t> perms;
+};
+const HaltonTables& halton_tables();
+
+struct HaltonParams {
+    uint64_t base_scale[2], base_exp[2], stride;
+    int64_t mult_inv[2];
+};
+HaltonParams halton_params(int res_x, int res_y);
+
+}  // namespace b2host

@@ -163,6 +163,7 @@ struct HitOut {
     float t;
     uint32_t prim;
     float b0, b1;
+    float b2;  // third barycentric exactly as the test produced it (e2 * inv_det); kept for the path tracer
 };
 
 #ifndef B2_STACK
@@ -174,7 +175,7 @@ template <bool ANY>
 B2_D bool traverse_wide(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
     out->t = __int_as_float(0x7f800000);
     out->prim = 0xffffffffu;
-    out->b0 = 0.0f; out->b1 = 0.0f;
+    out->b0 = 0.0f; out->b1 = 0.0f; out->b2 = 0.0f;
     if (A.root_code == B2_EMPTY_ROOT) return false;
     RayCtx r;
     r.ox = ray.ox; r.oy = ray.oy; r.oz = ray.oz;
@@ -224,7 +225,7 @@ B2_D bool traverse_wide(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
                     } else if (!(flags & 2u)) {          // alpha == 0 reject (triangle.rs:587-607)
                         hit = true;
                         t_max = t;
-                        out->t = t; out->prim = prim; out->b0 = b0; out->b1 = b1;
+                        out->t = t; out->prim = prim; out->b0 = b0; out->b1 = b1; out->b2 = b2;
                     }
                 }
                 if (++i >= leaf_n) break;
@@ -248,7 +249,7 @@ template <bool ANY>
 B2_D bool traverse_ref(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
     out->t = __int_as_float(0x7f800000);
     out->prim = 0xffffffffu;
-    out->b0 = 0.0f; out->b1 = 0.0f;
+    out->b0 = 0.0f; out->b1 = 0.0f; out->b2 = 0.0f;
     if (A.root_code == B2_EMPTY_ROOT) return false;
     RayCtx r;
     r.ox = ray.ox; r.oy = ray.oy; r.oz = ray.oz;
@@ -278,7 +279,7 @@ B2_D bool traverse_ref(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
                         } else if (!(flags & 2u)) {
                             hit = true;
                             t_max = t;
-                            out->t = t; out->prim = prim; out->b0 = b0; out->b1 = b1;
+                            out->t = t; out->prim = prim; out->b0 = b0; out->b1 = b1; out->b2 = b2;
                         }
                     }
                 }

@@ -7,7 +7,8 @@ namespace b2 {
 // variant 2: wide nodes, one thread per ray.
 // variant 1: reference LinearBVHNode walk, one thread per ray (baseline).
 template <bool ANY, int VARIANT>
-__global__ void __launch_bounds__(128) k_trace_simple(DeviceAccel A, const float4* __restrict__ rays, long long n, void* __restrict__ out) {
+__global__ void __launch_bounds__(128) k_trace_simple(DeviceAccel A, const float4* __restrict__ rays, long long n, void* __restrict__ out,
+                                                      float* __restrict__ b2_out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 r0 = __ldg(rays + 2 * i), r1 = __ldg(rays + 2 * i + 1);
@@ -20,6 +21,7 @@ __global__ void __launch_bounds__(128) k_trace_simple(DeviceAccel A, const float
         float4 o;
         o.x = h.t; o.y = __uint_as_float(h.prim); o.z = h.b0; o.w = h.b1;
         ((float4*)out)[i] = o;
+        if (b2_out) b2_out[i] = h.b2;
     }
 }
 
@@ -34,7 +36,7 @@ __global__ void __launch_bounds__(128) k_trace_simple(DeviceAccel A, const float
 
 template <bool ANY>
 __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, const float4* __restrict__ rays, long long n,
-                                                              void* __restrict__ out, unsigned long long* __restrict__ counter) {
+                                                              void* __restrict__ out, unsigned long long* __restrict__ counter, float* __restrict__ b2_out) {
     const unsigned lane = threadIdx.x & 31u;
     int stack_code[B2_STACK];
     float stack_t[B2_STACK];
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
     int cur = kDone, sp = 0;
     bool hit = false;
     HitOut h;
-    h.t = 0.0f; h.prim = 0xffffffffu; h.b0 = 0.0f; h.b1 = 0.0f;
+    h.t = 0.0f; h.prim = 0xffffffffu; h.b0 = 0.0f; h.b1 = 0.0f; h.b2 = 0.0f;
     bool exhausted = false;  // warp-uniform: the global queue is empty
 
     for (;;) {
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
                     o = mk(r0.x, r0.y, r0.z);
                     sp = 0;
                     hit = false;
-                    h.t = __int_as_float(0x7f800000); h.prim = 0xffffffffu; h.b0 = 0.0f; h.b1 = 0.0f;
+                    h.t = __int_as_float(0x7f800000); h.prim = 0xffffffffu; h.b0 = 0.0f; h.b1 = 0.0f; h.b2 = 0.0f;
                     cur = A.root_code;
                     float te;
                     if (cur == kDone ||
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
                           te < t_max)) {
                         // miss at the root: retire immediately
                         if (ANY) ((uint8_t*)out)[id] = 0;
-                        else { float4 ov; ov.x = h.t; ov.y = __uint_as_float(h.prim); ov.z = 0.0f; ov.w = 0.0f; ((float4*)out)[id] = ov; }
+                        else { float4 ov; ov.x = h.t; ov.y = __uint_as_float(h.prim); ov.z = 0.0f; ov.w = 0.0f; ((float4*)out)[id] = ov; if (b2_out) b2_out[id] = 0.0f; }
                         cur = kDone;
                     }
                 }
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
                             } else if (!(flags & 2u)) {
                                 hit = true;
                                 t_max = t;
-                                h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1;
+                                h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;
                             }
                         }
                         if (++i >= leaf_n) break;
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
                     }
                     if (cur == kDone) {  // ray retired: write result
                         if (ANY) ((uint8_t*)out)[ray_id] = hit ? 1 : 0;
-                        else { float4 ov; ov.x = h.t; ov.y = __uint_as_float(h.prim); ov.z = h.b0; ov.w = h.b1; ((float4*)out)[ray_id] = ov; }
+                        else { float4 ov; ov.x = h.t; ov.y = __uint_as_float(h.prim); ov.z = h.b0; ov.w = h.b1; ((float4*)out)[ray_id] = ov; if (b2_out) b2_out[ray_id] = h.b2; }
                     }
                 }
             }
@@ -247,13 +249,13 @@ static int persistent_setup() {
 }
 
 template <bool ANY>
-static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant) {
+static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant, float* d_b2) {
     if (n <= 0) return B200PT_OK;
     const int block = 128;
     if (variant == 1) {
-        k_trace_simple<ANY, 1><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out);
+        k_trace_simple<ANY, 1><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out, d_b2);
     } else if (variant == 2) {
-        k_trace_simple<ANY, 2><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out);
+        k_trace_simple<ANY, 2><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out, d_b2);
     } else {
         int rc = persistent_setup();
         if (rc) return rc;
@@ -262,7 +264,7 @@ static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void*
         int grid = g_persist_grid[ANY ? 1 : 0];
         int need = grid_for(n, block);
         if (need < grid) grid = need;
-        k_trace_persistent<ANY><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr);
+        k_trace_persistent<ANY><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2);
     }
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
@@ -270,11 +272,11 @@ static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void*
     return B200PT_OK;
 }
 
-int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant) {
-    return launch_any<false>(A, d_rays, n, d_hits, s, variant);
+int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant, float* d_b2) {
+    return launch_any<false>(A, d_rays, n, d_hits, s, variant, d_b2);
 }
 int launch_occluded(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant) {
-    return launch_any<true>(A, d_rays, n, d_out, s, variant);
+    return launch_any<true>(A, d_rays, n, d_out, s, variant, nullptr);
 }
 
 }  // namespace b2

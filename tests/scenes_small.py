@@ -1,0 +1,42 @@
+"""Small path-tracing scenes shared by the CPU and GPU tests."""
+import numpy as np
+
+
+def one_material_scene(wl, mat, light="infinite", res=24, spp=8, maxdepth=5, nu=24, nv=12, strategy="uniform", filt="box"):
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    sd = SceneDescription()
+    m = sd.add_material(**mat)
+    g = sd.add_material(type="matte", Kd=(0.4, 0.4, 0.4))
+    sd.add_mesh(wl.displaced_sphere(nu, nv), m)
+    sd.add_mesh(wl.ground_quad(), g)
+    if light in ("infinite", "all"):
+        sd.add_infinite_light((1.2, 1.2, 1.1))
+    if light in ("point", "all"):
+        sd.add_point_light((1.5, 3.0, -3.0), (30, 30, 30))
+    if light in ("area", "all"):
+        lq = np.array([[-1.5, 3.0, -1.0], [1.5, 3.0, -1.0], [1.5, 3.0, 1.0], [-1.5, 3.0, 1.0]], dtype=np.float32)
+        lt = np.stack([np.concatenate([lq[0], lq[1], lq[2]]), np.concatenate([lq[0], lq[2], lq[3]])])
+        lm = sd.add_material(type="matte", Kd=(0.0, 0.0, 0.0))
+        sd.add_mesh(lt, lm, area_light=dict(L=(15, 15, 15)))
+    sd.camera.update(eye=(0.0, 1.2, -4.0), look=(0.0, -0.1, 0.0), up=(0, 1, 0), fov=40.0)
+    sd.film.update(xresolution=res, yresolution=res, filter=filt)
+    sd.sampler.update(type="halton", pixelsamples=spp)
+    sd.integrator.update(maxdepth=maxdepth, lightsamplestrategy=strategy)
+    return sd
+
+
+MATERIALS = {
+    "matte": dict(type="matte", Kd=(0.5, 0.45, 0.4)),
+    "oren_nayar": dict(type="matte", Kd=(0.5, 0.5, 0.5), sigma=30.0),
+    "plastic": dict(type="plastic"),
+    "glass": dict(type="glass", eta=1.5),
+    "rough_glass": dict(type="glass", eta=1.5, uroughness=0.2, vroughness=0.1),
+    "metal": dict(type="metal", roughness=0.01),
+    "rough_metal": dict(type="metal", uroughness=0.3, vroughness=0.1, remaproughness=False),
+}
+
+
+def rel_rmse(a, b, eps=1e-2):
+    """Per-pixel relative RMSE (north_star's image gate, <= 1e-3)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.sqrt(np.mean(((a - b) / (np.abs(b) + eps)) ** 2)))

@@ -1,0 +1,72 @@
+"""CPU tests of the oracle's renderer: properties the reference algorithm guarantees."""
+import numpy as np
+import pytest
+
+import scenes_small as ss
+
+
+def test_render_is_thread_count_independent_with_box_filter(pkg, oracle):
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="all", res=20, spp=4, strategy="power")
+    a = oracle.OracleScene(sd).render(nthreads=1)[0]
+    b = oracle.OracleScene(sd).render(nthreads=5)[0]
+    assert np.array_equal(a, b)  # each pixel belongs to exactly one tile (box filter r = 0.5)
+
+
+def test_no_lights_is_black_and_emitter_is_seen_directly(pkg, oracle):
+    from pbrt_v3_rs_b200 import workloads as wl
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    sd = ss.one_material_scene(wl, ss.MATERIALS["matte"], light="none", res=12, spp=2)
+    assert not oracle.OracleScene(sd).render()[0].any()
+    # a camera looking straight at a one-sided emitter sees exactly L (path.rs:123-127)
+    sd = SceneDescription()
+    m = sd.add_material(type="matte", Kd=(0, 0, 0))
+    q = np.array([[-5, -5, 2], [5, -5, 2], [5, 5, 2], [-5, 5, 2]], dtype=np.float32)
+    tris = np.stack([np.concatenate([q[0], q[2], q[1]]), np.concatenate([q[0], q[3], q[2]])])
+    sd.add_mesh(tris, m, area_light=dict(L=(3, 2, 1)))
+    sd.camera.update(eye=(0, 0, -1), look=(0, 0, 1), fov=30.0)
+    sd.film.update(xresolution=8, yresolution=8)
+    sd.sampler.update(pixelsamples=2)
+    img = oracle.OracleScene(sd).render()[0]
+    assert np.allclose(img, np.array([3, 2, 1], np.float32), rtol=1e-5)
+
+
+def test_white_furnace_bound(pkg, oracle):
+    """Energy conservation: a matte object under a constant environment L never reflects more than L."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, dict(type="matte", Kd=(1, 1, 1)), light="none", res=16, spp=16, maxdepth=8)
+    sd.add_infinite_light((1, 1, 1))
+    img = oracle.OracleScene(sd).render()[0]
+    assert img.max() <= 1.0 + 0.35 and img.min() >= 0.0  # MC noise allowance at 16 spp
+    assert 0.5 < img.mean() <= 1.0 + 1e-3
+
+
+@pytest.mark.parametrize("name", ["matte", "plastic", "glass", "metal", "rough_glass", "oren_nayar"])
+def test_every_material_renders_finite(pkg, oracle, name):
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS[name], light="all", res=16, spp=4, strategy="power")
+    img, stats, _ = oracle.OracleScene(sd).render()
+    assert np.isfinite(img).all() and (img >= 0).all() and img.mean() > 0
+    assert stats[0] == 16 * 16 * 4  # one camera ray per pixel sample
+
+
+def test_gaussian_filter_and_crop_window(pkg, oracle):
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["matte"], res=20, spp=2, filt="gaussian")
+    sd.film["cropwindow"] = (0.25, 0.75, 0.1, 0.9)
+    sc = oracle.OracleScene(sd)
+    assert sc.shape() == (16, 10)
+    img, stats, _ = sc.render(nthreads=1)
+    assert np.isfinite(img).all() and img.mean() > 0
+    assert stats[0] == (10 + 4) * (16 + 4) * 2  # sample bounds extend 2 px beyond the crop on each side
+
+
+def test_li_batch_equals_render_accumulation(pkg, oracle):
+    """Per-sample li values averaged per pixel reproduce the rendered image (box filter, weight 1)."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["matte"], res=8, spp=4)
+    sc = oracle.OracleScene(sd)
+    img = sc.render(nthreads=1)[0]
+    ps = np.array([(x, y, s) for y in range(8) for x in range(8) for s in range(4)], dtype=np.int32)
+    li = sc.li(ps, nthreads=1).reshape(8, 8, 4, 3)
+    assert np.allclose(li.mean(2), img, rtol=2e-4, atol=1e-6)  # RGB->XYZ->RGB matrices are inverse only to ~1e-5

@@ -62,11 +62,30 @@ def test_gaussian_filter_and_crop_window(pkg, oracle):
 
 
 def test_li_batch_equals_render_accumulation(pkg, oracle):
-    """Per-sample li values averaged per pixel reproduce the rendered image (box filter, weight 1)."""
+    """Per-sample li values pushed through FilmTile::add_sample (film_tile.rs:62-108, box filter) reproduce the
+    rendered image — including the reference's quirk that a sample with a jitter of exactly 0 also lands in the
+    neighbouring pixel (window [ceil(p - 0.5 - r), floor(p - 0.5 + r)])."""
+    import ctypes as C
     from pbrt_v3_rs_b200 import workloads as wl
-    sd = ss.one_material_scene(wl, ss.MATERIALS["matte"], res=8, spp=4)
+    res, spp = 8, 4
+    sd = ss.one_material_scene(wl, ss.MATERIALS["matte"], res=res, spp=spp)
     sc = oracle.OracleScene(sd)
     img = sc.render(nthreads=1)[0]
-    ps = np.array([(x, y, s) for y in range(8) for x in range(8) for s in range(4)], dtype=np.int32)
-    li = sc.li(ps, nthreads=1).reshape(8, 8, 4, 3)
-    assert np.allclose(li.mean(2), img, rtol=2e-4, atol=1e-6)  # RGB->XYZ->RGB matrices are inverse only to ~1e-5
+    ps = np.array([(x, y, s) for y in range(res) for x in range(res) for s in range(spp)], dtype=np.int32)
+    li = sc.li(ps, nthreads=1).reshape(res, res, spp, 3)
+    acc = np.zeros((res, res, 3), np.float64)
+    wsum = np.zeros((res, res), np.float64)
+    u = np.zeros((spp, 2), np.float32)
+    doubles = 0
+    for y in range(res):
+        for x in range(res):
+            oracle.lib().orc_halton_pixel(spp, res, res, x, y, 2, u.ctypes.data_as(C.c_void_p))
+            for s in range(spp):
+                dx, dy = np.float32(x) + u[s, 0] - np.float32(0.5), np.float32(y) + u[s, 1] - np.float32(0.5)
+                for yy in range(max(int(np.ceil(dy - 0.5)), 0), min(int(np.floor(dy + 0.5)) + 1, res)):
+                    for xx in range(max(int(np.ceil(dx - 0.5)), 0), min(int(np.floor(dx + 0.5)) + 1, res)):
+                        acc[yy, xx] += li[y, x, s]
+                        wsum[yy, xx] += 1
+                        doubles += (xx, yy) != (x, y)
+    assert doubles > 0  # the quirk is exercised at this resolution
+    assert np.allclose(acc / wsum[..., None], img, rtol=2e-4, atol=1e-6)  # RGB->XYZ->RGB matrices are inverse only to ~1e-5

@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
                 float map_pdf = pdf0 * pdf1;
                 if (map_pdf != 0.0f) {
                     float theta = d1 * kPi, phi = d0 * kTwoPi;
-                    float cos_t = cosf(theta), sin_t = sinf(theta);
-                    float sin_p = sinf(phi), cos_p = cosf(phi);
+                    float cos_t = lmx::cosf_glibc(theta), sin_t = lmx::sinf_glibc(theta);
+                    float sin_p = lmx::sinf_glibc(phi), cos_p = lmx::cosf_glibc(phi);
                     wi = xf3(light.l2w, mk(sin_t * cos_p, sin_t * sin_p, cos_t));
                     light_pdf = map_pdf / (kTwoPi * kPi * sin_t);
                     if (sin_t == 0.0f) light_pdf = 0.0f;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
                         } else {  // infinite.rs:201-211
                             V3 w = xf3(light.w2l, wi2);
                             float theta = spherical_theta(w), phi = spherical_phi(w);
-                            float sin_t = sinf(theta);
+                            float sin_t = lmx::sinf_glibc(theta);
                             if (sin_t == 0.0f) lp = 0.0f;
                             else {
                                 const DInfDistr& D = S.inf_distr[light.inf_slot];

@@ -2,11 +2,13 @@
 // PathIntegrator::li (integrators/src/path.rs:103-284) that run between ray
 // casts in the wavefront loop.  Operation order follows the reference files
 // cited per function (f32, no FMA contraction: this TU is built with
-// -fmad=false).  Transcendentals (sinf, cosf, acosf, atan2f, logf) are CUDA's
-// IEEE-accurate versions (no --use_fast_math): they may differ from the host
-// libm by an ulp, which is why image parity is statistical (rel-RMSE <= 1e-3)
-// while traversal parity is bit-exact.
+// -fmad=false).  sin/cos — the only transcendentals that feed ray geometry — go
+// through libm_exact.cuh, which reproduces the host libm's sinf/cosf bit for bit,
+// so sampled directions (and therefore every later hit) match the CPU path.
+// acosf/atan2f (constant-environment lookups only) are CUDA's IEEE-accurate
+// versions and may differ from the host by an ulp in the radiance VALUE.
 #pragma once
+#include "libm_exact.cuh"
 #include "pt_math.cuh"
 #include "traverse.cuh"
 
@@ -41,7 +43,7 @@ B2_D P2 concentric_sample_disk(P2 u) {  // :138-155
     float r, theta;
     if (pabs(ox) > pabs(oy)) { r = ox; theta = kPiOver4 * (oy / ox); }
     else { r = oy; theta = kPiOver2 - kPiOver4 * (ox / oy); }
-    return mk2(r * cosf(theta), r * sinf(theta));
+    return mk2(r * lmx::cosf_glibc(theta), r * lmx::sinf_glibc(theta));
 }
 B2_D V3 cosine_sample_hemisphere(P2 u) {  // :207-211
     P2 d = concentric_sample_disk(u);
@@ -136,8 +138,8 @@ B2_D void tr_sample11(float cos_t, float u1, float u2, float* sx, float* sy) {  
     if (cos_t > 0.9999f) {
         float r = sqrtf(u1 / (1.0f - u1));
         float phi = kTwoPi * u2;
-        *sx = r * cosf(phi);
-        *sy = r * sinf(phi);
+        *sx = r * lmx::cosf_glibc(phi);
+        *sy = r * lmx::sinf_glibc(phi);
         return;
     }
     float sin_t = sqrtf(pmax(0.0f, 1.0f - cos_t * cos_t));

@@ -72,8 +72,12 @@ struct Wave {
     float4* pend_c;     // beta rgb at the vertex, mis scattering pdf
     int4* pend_d;       // light index, shadow slot, mis slot, -
     int* pend_q;        // path ids with a pending record
-    int* counters;      // [0] next rays, [1] shadow rays, [2] mis rays, [3] pending records
+    int* counters;      // [0] next rays, [1] shadow rays, [2] mis rays, [3] pending records, [8..15] bin counts, [16..23] bin cursors
+    // sort-by-material: key per slot (0 = miss / dead, 1 + material type otherwise) and the slots grouped by key
+    uint8_t* key;
+    int* sorted;
 };
+static const int kBins = 5;
 
 B2_D int meta_pack(int dim, int bounces, int spec) { return (dim & 0xffff) | ((bounces & 0xff) << 16) | ((spec & 0xff) << 24); }
 
@@ -124,10 +128,57 @@ B2_D void store_ray(float4* q, int slot, V3 o, V3 d, float tmax, float time) {
     q[2 * slot + 1] = make_float4(d.x, d.y, d.z, time);
 }
 
+// ---- K6: sort the ray queue by material so that a shading warp runs one BSDF model ---------------
+// Counting sort with 5 bins (miss, matte, plastic, glass, metal): pass 1 classifies every slot and
+// histograms per block (one global atomic per bin per block), pass 2 scatters slot ids to their bin with
+// one warp-aggregated atomic per bin per warp.  Order inside a bin is arbitrary; results do not depend on it.
+__global__ void __launch_bounds__(256) k_bin_count(DeviceScene S, Wave W, int n_active) {
+    __shared__ int hist[kBins];
+    if (threadIdx.x < kBins) hist[threadIdx.x] = 0;
+    __syncthreads();
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < n_active) {
+        uint32_t prim = __float_as_uint(W.hit[slot].y);
+        int key = 0;
+        if (prim != 0xffffffffu) {
+            int mat = __float_as_int(ldg4(S.prim_verts + 3ll * prim).w);
+            key = 1 + S.materials[mat].type;
+        }
+        W.key[slot] = (uint8_t)key;
+        atomicAdd(&hist[key], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < kBins && hist[threadIdx.x]) atomicAdd(&W.counters[8 + threadIdx.x], hist[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_bin_scatter(Wave W, int n_active) {
+    __shared__ int wcount[8][kBins];  // per warp: count, then start offset inside the bin
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    int key = slot < n_active ? (int)W.key[slot] : -1;
+    int base = 0;
+    for (int k = 0; k < kBins; ++k) if (k < key) base += W.counters[8 + k];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned mine = 0;
+    for (int k = 0; k < kBins; ++k) {
+        unsigned m = __ballot_sync(0xffffffffu, key == k);
+        if (key == k) mine = m;
+        if (lane == 0) wcount[warp][k] = __popc(m);
+    }
+    __syncthreads();
+    if (threadIdx.x < kBins) {  // one global atomic per bin per block, then an exclusive scan over the block's warps
+        int total = 0;
+        for (int w = 0; w < 8; ++w) total += wcount[w][threadIdx.x];
+        int run = total ? atomicAdd(&W.counters[16 + threadIdx.x], total) : 0;
+        for (int w = 0; w < 8; ++w) { int c = wcount[w][threadIdx.x]; wcount[w][threadIdx.x] = run; run += c; }
+    }
+    __syncthreads();
+    if (key >= 0) W.sorted[base + wcount[warp][key] + __popc(mine & ((1u << lane) - 1u))] = slot;
+}
+
 // ---- K4: shade --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, int n_active) {
-    int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_active) return;
+    int i_sorted = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i_sorted >= n_active) return;
+    const int slot = W.sorted[i_sorted];
     const int pid = W.qpid[cur][slot];
     const float4 r0 = W.ray[cur][2 * slot], r1 = W.ray[cur][2 * slot + 1];
     const float4 hit = W.hit[slot];
@@ -476,6 +527,12 @@ struct SceneImpl {
     uint64_t rays[3] = {0, 0, 0};
     std::mutex mu;
     int sample_bounds[4];
+    // per-sample store and film staging, grown on demand and kept across renders
+    float4* d_sample_L = nullptr;
+    float2* d_sample_pf = nullptr;
+    long long sample_cap = 0;
+    float4* d_film = nullptr;
+    size_t film_cap = 0;
 };
 
 static const int kWaveCap = 1 << 22;
@@ -512,6 +569,7 @@ static float alpha_clamp(float a) { return 0.001f > a ? 0.001f : a; }  // Trowbr
 static DMaterial make_material(const b200pt_material& m) {
     DMaterial d;
     std::memset(&d, 0, sizeof(d));
+    d.type = m.type;
     auto lobe = [&](int kind, uint32_t type) -> DBxDF& {
         DBxDF& x = d.bx[d.n_bxdf++];
         x.kind = kind; x.type = type;
@@ -632,7 +690,9 @@ static int wave_alloc(SceneImpl* s, int cap) {
     if ((rc = dev_alloc(s, (size_t)cap, &W.pend_c))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.pend_d))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.pend_q))) return rc;
-    if ((rc = dev_alloc(s, (size_t)8, &W.counters))) return rc;
+    if ((rc = dev_alloc(s, (size_t)32, &W.counters))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.key))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.sorted))) return rc;
     s->wave_cap = cap;
     return B200PT_OK;
 }
@@ -646,7 +706,10 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
         int rc = launch_intersect(s->dev.accel, W.ray[cur], n_active, W.hit, st, 0, W.hit_b2);
         if (rc) return rc;
         s->rays[1] += (uint64_t)n_active;
-        B2_CUDA(cudaMemsetAsync(W.counters, 0, 4 * sizeof(int), st));
+        B2_CUDA(cudaMemsetAsync(W.counters, 0, 32 * sizeof(int), st));
+        k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, n_active);
+        k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, n_active);
+        g_launches.fetch_add(2);
         k_shade<<<(n_active + 127) / 128, 128, 0, st>>>(s->dev, W, cur, n_active);
         g_launches.fetch_add(1);
         int cnt[4];
@@ -813,6 +876,8 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     if ((rc = dev_upload(s, ht.perms, &D.halton.perms))) return fail(rc);
     if ((rc = dev_upload(s, ht.primes, &D.halton.primes))) return fail(rc);
     if ((rc = dev_upload(s, ht.prime_sums, &D.halton.prime_sums))) return fail(rc);
+    if ((rc = dev_upload(s, ht.div_m, &D.halton.div_m))) return fail(rc);
+    if ((rc = dev_upload(s, ht.div_sh, &D.halton.div_sh))) return fail(rc);
     for (int i = 0; i < 2; ++i) { D.halton.base_scale[i] = hp.base_scale[i]; D.halton.base_exp[i] = hp.base_exp[i]; D.halton.mult_inv[i] = hp.mult_inv[i]; }
     D.halton.stride = hp.stride;
     D.halton.sample_at_center = d->sampler.sample_at_center;
@@ -833,6 +898,9 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
 void b200pt_scene_destroy(b200pt_scene* sc) {
     if (!sc) return;
     for (void* p : sc->impl.allocs) cudaFree(p);
+    if (sc->impl.d_sample_L) cudaFree(sc->impl.d_sample_L);
+    if (sc->impl.d_sample_pf) cudaFree(sc->impl.d_sample_pf);
+    if (sc->impl.d_film) cudaFree(sc->impl.d_film);
     accel_free_device(&sc->impl.accel);
     delete sc;
 }
@@ -864,11 +932,17 @@ int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_e
     const int sw = sb[2] - sb[0], spp = s->sampler.spp;
     const long long n_samples = (long long)(srow1 - srow0) * sw * spp;
     if (!s->wave_cap && (rc = wave_alloc(s, kWaveCap))) return rc;
-    float4* d_L = nullptr;
-    float2* d_pf = nullptr;
-    B2_CUDA(cudaMalloc(&d_L, (size_t)std::max<long long>(n_samples, 1) * sizeof(float4)));
-    cudaError_t e = cudaMalloc(&d_pf, (size_t)std::max<long long>(n_samples, 1) * sizeof(float2));
-    if (e != cudaSuccess) { cudaFree(d_L); return cuda_fail(e, "cudaMalloc p_film"); }
+    if (n_samples > s->sample_cap) {
+        if (s->d_sample_L) cudaFree(s->d_sample_L);
+        if (s->d_sample_pf) cudaFree(s->d_sample_pf);
+        s->d_sample_L = nullptr; s->d_sample_pf = nullptr; s->sample_cap = 0;
+        B2_CUDA(cudaMalloc(&s->d_sample_L, (size_t)n_samples * sizeof(float4)));
+        B2_CUDA(cudaMalloc(&s->d_sample_pf, (size_t)n_samples * sizeof(float2)));
+        s->sample_cap = n_samples;
+    }
+    float4* d_L = s->d_sample_L;
+    float2* d_pf = s->d_sample_pf;
+    cudaError_t e;
     for (long long first = 0; first < n_samples && !rc; first += s->wave_cap) {
         int n = (int)std::min<long long>(s->wave_cap, n_samples - first);
         k_raygen<<<(n + 255) / 256, 256, 0, st>>>(s->dev, s->wave, first, n, spp, srow0, nullptr, d_pf, nullptr);
@@ -896,8 +970,6 @@ int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_e
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = cuda_fail(e, "render");
     }
-    cudaFree(d_L);
-    cudaFree(d_pf);
     return rc;
 }
 
@@ -907,14 +979,18 @@ int b200pt_render_rows(b200pt_scene* sc, int32_t row_begin, int32_t row_end, flo
     if (!sc || !film_xyzw) { b200pt_set_error("b200pt_render_rows: null argument"); return B200PT_ERR_INVALID; }
     const b200pt_film& f = sc->impl.film;
     size_t bytes = (size_t)(f.crop[2] - f.crop[0]) * (f.crop[3] - f.crop[1]) * sizeof(float4);
-    void* d = nullptr;
-    B2_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
-    rc = b200pt_render_rows_device(sc, row_begin, row_end, d, nullptr);
+    SceneImpl* s = &sc->impl;
+    if (bytes > s->film_cap) {
+        if (s->d_film) cudaFree(s->d_film);
+        s->d_film = nullptr; s->film_cap = 0;
+        B2_CUDA(cudaMalloc(&s->d_film, std::max<size_t>(bytes, 16)));
+        s->film_cap = bytes;
+    }
+    rc = b200pt_render_rows_device(sc, row_begin, row_end, s->d_film, nullptr);
     if (!rc) {
-        cudaError_t e = cudaMemcpy(film_xyzw, d, bytes, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpy(film_xyzw, s->d_film, bytes, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "film download");
     }
-    cudaFree(d);
     return rc;
 }
 

@@ -40,6 +40,13 @@ const HaltonTables& halton_tables() {
         }
         int s = 0;
         for (int p : t.primes) { t.prime_sums.push_back(s); s += p; }
+        for (int p : t.primes) {
+            int l = 0;
+            while ((1u << l) < (uint32_t)p) ++l;
+            uint64_t m = ((uint64_t(1) << 32) * ((uint64_t(1) << l) - (uint64_t)p)) / (uint64_t)p + 1;
+            t.div_m.push_back((uint32_t)m);
+            t.div_sh.push_back((uint32_t)(l < 1 ? l : 1) | ((uint32_t)(l - 1 > 0 ? l - 1 : 0) << 8));
+        }
         // compute_radical_inverse_permutations: identity per base, Fisher-Yates with RNG::shuffle (rng.rs:106-119)
         t.perms.resize((size_t)s);
         Pcg32 rng;

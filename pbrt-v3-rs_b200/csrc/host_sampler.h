@@ -8,6 +8,8 @@ namespace b2host {
 struct HaltonTables {
     std::vector<int> primes, prime_sums;
     std::vector<uint16_t> perms;
+    // exact u32 division by each prime without a divide (Granlund-Montgomery): q = (t + ((n - t) >> sh1)) >> sh2, t = mulhi(m, n)
+    std::vector<uint32_t> div_m, div_sh;  // div_sh = sh1 | sh2 << 8
 };
 const HaltonTables& halton_tables();
 

@@ -193,7 +193,8 @@ struct DBxDF {
 };
 struct DMaterial {
     int n_bxdf;
-    int pad[3];
+    int type;  // B200PT_MAT_* (sort key of the shade stage)
+    int pad[2];
     DBxDF bx[2];
 };
 
@@ -480,6 +481,8 @@ struct DHalton {
     const uint16_t* perms;      // compute_radical_inverse_permutations(RNG::default())
     const int* primes;          // first 1000 primes
     const int* prime_sums;
+    const uint32_t* div_m;      // per prime: magic multiplier / shifts for exact u32 division (host_sampler.cpp)
+    const uint32_t* div_sh;
     unsigned long long base_scale[2], base_exp[2], stride;
     long long mult_inv[2];
     int sample_at_center;
@@ -503,13 +506,18 @@ B2_D float radical_inverse_specialized(int base, unsigned long long a) {  // :40
     }
     return pmin(__ull2float_rn(rev) * inv_base_n, kOneMinusEps);
 }
-B2_D float scrambled_radical_inverse(int base, unsigned long long a, const uint16_t* perm) {  // :428-448
+B2_D float scrambled_radical_inverse(int base, unsigned long long a, const uint16_t* perm, uint32_t dm, uint32_t dsh) {  // :428-448
     float inv_base = 1.0f / (float)base;
     unsigned long long rev = 0;
     float inv_base_n = 1.0f;
     if (a <= 0xffffffffull) {
-        uint32_t x = (uint32_t)a, b = (uint32_t)base;
-        while (x != 0) { uint32_t next = x / b, digit = x - next * b; rev = rev * b + perm[digit]; inv_base_n *= inv_base; x = next; }
+        // same integer digits as the reference's u64 division; the quotient comes from a multiply-high (exact for every u32)
+        uint32_t x = (uint32_t)a, b = (uint32_t)base, sh1 = dsh & 0xffu, sh2 = dsh >> 8;
+        while (x != 0) {
+            uint32_t t = __umulhi(dm, x);
+            uint32_t next = (t + ((x - t) >> sh1)) >> sh2, digit = x - next * b;
+            rev = rev * b + perm[digit]; inv_base_n *= inv_base; x = next;
+        }
     } else {
         unsigned long long b = (unsigned long long)base;
         while (a != 0) { unsigned long long next = a / b, digit = a - next * b; rev = rev * b + perm[digit]; inv_base_n *= inv_base; a = next; }
@@ -541,7 +549,7 @@ B2_D float halton_dim(const DHalton& h, unsigned long long index, int dim) {
     if (h.sample_at_center && (dim == 0 || dim == 1)) return 0.5f;
     if (dim == 0) return radical_inverse_base2(index >> h.base_exp[0]);
     if (dim == 1) return radical_inverse_specialized(3, index / h.base_scale[1]);
-    return scrambled_radical_inverse(h.primes[dim], index, h.perms + h.prime_sums[dim]);
+    return scrambled_radical_inverse(h.primes[dim], index, h.perms + h.prime_sums[dim], h.div_m[dim], h.div_sh[dim]);
 }
 
 // ---- camera: PerspectiveCamera::generate_ray_differential without differentials ------

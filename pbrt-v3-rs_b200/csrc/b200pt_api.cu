@@ -88,7 +88,7 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
     a->dev.root_code = code_of(0);
 
     // triangles in BVHAccel.primitives order
-    std::vector<float4> tris((size_t)std::max<int64_t>(n_prims, 1) * 3);
+    std::vector<float4> tris((size_t)std::max<int64_t>(n_prims, 1) * 4);
     for (int64_t j = 0; j < n_prims; ++j) {
         uint32_t p = ordered[j];
         if ((int64_t)p >= n_prims) { b200pt_set_error("b200pt_accel_create: ordered_prims index out of range"); return B200PT_ERR_INVALID; }
@@ -96,9 +96,10 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
         uint32_t fl = flags ? flags[p] : 0u, zero = 0u;
         float fp, ff, fz;
         std::memcpy(&fp, &p, 4); std::memcpy(&ff, &fl, 4); std::memcpy(&fz, &zero, 4);
-        tris[(size_t)j * 3 + 0] = make_float4(v[0], v[1], v[2], fp);
-        tris[(size_t)j * 3 + 1] = make_float4(v[3], v[4], v[5], ff);
-        tris[(size_t)j * 3 + 2] = make_float4(v[6], v[7], v[8], fz);
+        tris[(size_t)j * 4 + 0] = make_float4(v[0], v[1], v[2], v[3]);
+        tris[(size_t)j * 4 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        tris[(size_t)j * 4 + 2] = make_float4(v[8], fp, ff, fz);
+        tris[(size_t)j * 4 + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     for (int64_t i = 0; i < n_nodes; ++i) {
         if (nodes[i].n_primitives == 0) continue;
@@ -106,7 +107,7 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
         if ((int64_t)nodes[i].offset + cnt > n_prims) { b200pt_set_error("b200pt_accel_create: leaf range out of bounds"); return B200PT_ERR_INVALID; }
         float fc;
         std::memcpy(&fc, &cnt, 4);
-        tris[(size_t)nodes[i].offset * 3 + 2].w = fc;
+        tris[(size_t)nodes[i].offset * 4 + 2].w = fc;
     }
     B2_CUDA(cudaMalloc(&a->d_wide, wide.size() * sizeof(float4)));
     B2_CUDA(cudaMalloc(&a->d_tris, tris.size() * sizeof(float4)));

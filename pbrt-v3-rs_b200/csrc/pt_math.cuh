@@ -96,5 +96,13 @@ B2_D V3 offset_ray_origin(V3 p, V3 p_error, V3 n, V3 w) {
 
 // 16-byte vector loads through the read-only path (ld.global.nc.v4.f32).
 B2_D float4 ldg4(const float4* p) { return __ldg(p); }
+// 32-byte vector load (sm_100: LDG.E.256).  For scattered per-lane records the L1 tag stage is the limiter
+// (one 128-B line per lane per instruction), so fetching a 64-byte node as 2 x 256-bit instead of 4 x 128-bit
+// halves the L1 wavefronts per traversal step.  p must be 32-byte aligned.
+B2_D void ldg8(const float4* p, float4* a, float4* b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w)
+                 : "l"(p));
+}
 
 }  // namespace b2

@@ -16,10 +16,9 @@
 //     c0 = first child (reference index i+1), c1 = second child (node.offset).
 //     code >= 0: wide-node index of an interior child; code < 0: leaf, first
 //     ordered triangle = ~code.
-//   * triangles in BVHAccel.primitives (leaf) order, 48 B = 3 x float4:
-//        t0 = p0.xyz, bits(original primitive index)
-//        t1 = p1.xyz, bits(flags)
-//        t2 = p2.xyz, bits(leaf primitive count)   (valid in the first triangle of a leaf)
+//   * triangles in BVHAccel.primitives (leaf) order, 64 B = 2 x 256-bit loads:
+//        p0.xyz p1.xyz p2.xy | p2.z, bits(original primitive index), bits(flags),
+//        bits(leaf primitive count; valid in the first triangle of a leaf), 4 x pad
 //   Equivalence with the reference's "test the node when it is popped": the
 //   slab test of the far child is evaluated early, its entry distance is kept
 //   on the stack and re-compared with the (possibly shrunk) ray.t_max when the
@@ -35,7 +34,7 @@ struct Ray32 {  // b200pt_ray
 
 struct DeviceAccel {
     const float4* wide;   // 4 float4 per interior node
-    const float4* tris;   // 3 float4 per ordered triangle
+    const float4* tris;   // 4 float4 (64 B) per ordered triangle
     const float4* ref_nodes;  // 2 float4 per reference LinearBVHNode (baseline variant)
     float root_bounds[6];
     int root_code;        // code of the root (>=0 interior 0, <0 leaf), INT_MIN/empty => no nodes
@@ -154,9 +153,11 @@ B2_D bool triangle_nondegenerate(V3 p0, V3 p1, V3 p2) {
 }
 
 B2_D void load_tri(const float4* tris, long long i, V3* p0, V3* p1, V3* p2, uint32_t* prim, uint32_t* flags, uint32_t* leaf_n) {
-    float4 a = ldg4(tris + 3 * i), b = ldg4(tris + 3 * i + 1), c = ldg4(tris + 3 * i + 2);
-    *p0 = mk(a.x, a.y, a.z); *p1 = mk(b.x, b.y, b.z); *p2 = mk(c.x, c.y, c.z);
-    *prim = __float_as_uint(a.w); *flags = __float_as_uint(b.w); *leaf_n = __float_as_uint(c.w);
+    float4 a, b, c, d;
+    ldg8(tris + 4 * i, &a, &b);
+    ldg8(tris + 4 * i + 2, &c, &d);
+    *p0 = mk(a.x, a.y, a.z); *p1 = mk(a.w, b.x, b.y); *p2 = mk(b.z, b.w, c.x);
+    *prim = __float_as_uint(c.y); *flags = __float_as_uint(c.z); *leaf_n = __float_as_uint(c.w);
 }
 
 struct HitOut {
@@ -196,7 +197,9 @@ B2_D bool traverse_wide(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
     for (;;) {
         if (cur >= 0) {
             const float4* q = A.wide + 4ll * cur;
-            float4 q0 = ldg4(q), q1 = ldg4(q + 1), q2 = ldg4(q + 2), q3 = ldg4(q + 3);
+            float4 q0, q1, q2, q3;
+            ldg8(q, &q0, &q1);
+            ldg8(q + 2, &q2, &q3);
             float t0, t1;
             bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0) && t0 < t_max;
             bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1) && t1 < t_max;
@@ -262,7 +265,8 @@ B2_D bool traverse_ref(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
     int sp = 0, cur = 0;
     bool hit = false;
     for (;;) {
-        float4 n0 = ldg4(A.ref_nodes + 2ll * cur), n1 = ldg4(A.ref_nodes + 2ll * cur + 1);
+        float4 n0, n1;
+        ldg8(A.ref_nodes + 2ll * cur, &n0, &n1);
         float te;
         uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
         uint32_t nprims = meta & 0xffffu, axis = (meta >> 16) & 0xffu;

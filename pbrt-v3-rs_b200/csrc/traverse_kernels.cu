@@ -1,6 +1,7 @@
 // Traversal kernels (K2a closest-hit, K2b any-hit; K3 triangle test inlined).
 // See traverse.cuh for the data layout and the equivalence argument.
 #include "common.cuh"
+#include "traverse_phased.cuh"
 
 namespace b2 {
 
@@ -25,7 +26,8 @@ __global__ void __launch_bounds__(128) k_trace_simple(DeviceAccel A, const float
     }
 }
 
-// variant 0 (default): persistent warps with dynamic ray fetch.
+// variant 3: persistent warps with dynamic ray fetch, every lane does what it needs next ("if-if").
+// Kept as the A/B baseline of the phase-scheduled kernel in traverse_phased.cuh (variant 0, default).
 // Incoherent rays finish after very different numbers of steps, so in the
 // one-thread-per-ray kernel a warp runs until its slowest ray is done with most
 // lanes idle.  Here each warp keeps pulling work: whenever the number of lanes
@@ -98,7 +100,9 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
                 bool finished = false;
                 if (cur >= 0) {
                     const float4* q = A.wide + 4ll * cur;
-                    float4 q0 = ldg4(q), q1 = ldg4(q + 1), q2 = ldg4(q + 2), q3 = ldg4(q + 3);
+                    float4 q0, q1, q2, q3;
+                    ldg8(q, &q0, &q1);
+                    ldg8(q + 2, &q2, &q3);
                     float t0, t1;
                     bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0) && t0 < t_max;
                     bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1) && t1 < t_max;
@@ -182,7 +186,8 @@ __global__ void __launch_bounds__(128) k_count(DeviceAccel A, const float4* __re
         int sp = 0, cur = 0;
         bool done = false;
         while (!done) {
-            float4 n0 = ldg4(A.ref_nodes + 2ll * cur), n1 = ldg4(A.ref_nodes + 2ll * cur + 1);
+            float4 n0, n1;
+            ldg8(A.ref_nodes + 2ll * cur, &n0, &n1);
             float te;
             uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
             uint32_t nprims = meta & 0xffffu, axis = (meta >> 16) & 0xffu;
@@ -235,7 +240,7 @@ static int grid_for(long long n, int block) { return (int)((n + block - 1) / blo
 static const int kCounterRing = 256;
 static unsigned long long* g_counters = nullptr;
 static std::atomic<unsigned> g_counter_next{0};
-static int g_persist_grid[2] = {0, 0};
+static int g_persist_grid[4] = {0, 0, 0, 0};
 
 static int persistent_setup() {
     if (g_counters) return B200PT_OK;
@@ -245,6 +250,10 @@ static int persistent_setup() {
     g_persist_grid[0] = g_sm_count * (nb > 0 ? nb : 1);
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_persistent<true>, 128, 0));
     g_persist_grid[1] = g_sm_count * (nb > 0 ? nb : 1);
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_phased<false, 16, 16, 0, 7>, 128, 0));
+    g_persist_grid[2] = g_sm_count * (nb > 0 ? nb : 1);
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_phased<true, 16, 16, 0, 8>, 128, 0));
+    g_persist_grid[3] = g_sm_count * (nb > 0 ? nb : 1);
     return B200PT_OK;
 }
 
@@ -261,10 +270,15 @@ static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void*
         if (rc) return rc;
         unsigned long long* ctr = g_counters + (g_counter_next.fetch_add(1) % kCounterRing);
         B2_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
-        int grid = g_persist_grid[ANY ? 1 : 0];
+        int grid = g_persist_grid[(variant != 3 ? 2 : 0) + (ANY ? 1 : 0)];
         int need = grid_for(n, block);
         if (need < grid) grid = need;
-        k_trace_persistent<ANY><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2);
+        // closest-hit: 72 registers -> 7 CTAs/SM; any-hit: 64 registers -> 8 CTAs/SM (profiles/r1_variants.txt)
+        if (variant != 3) {
+            if (ANY) k_trace_phased<true, 16, 16, 0, 8><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2);
+            else k_trace_phased<false, 16, 16, 0, 7><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2);
+        }
+        else k_trace_persistent<ANY><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2);
     }
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();

@@ -1,0 +1,15 @@
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+import __graft_entry__ as ge
+import bench
+pkg = ge.load_package(); pkg.init(0)
+w = bench.build_workload(pkg, False, 0)
+accel = w['accel']; n = w['closest'].shape[0]; h = n // 2
+rays = np.ascontiguousarray(w['closest'][h:])
+d_r = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
+d_o = torch.zeros((h, 4), dtype=torch.float32, device='cuda')
+for v in (2, 3):
+    for _ in range(2):
+        accel.intersect_batch_device(d_r.data_ptr(), h, d_o.data_ptr(), 0, v)
+torch.cuda.synchronize()
+import os; os._exit(0)

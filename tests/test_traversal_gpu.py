@@ -27,7 +27,7 @@ def _check_closest(gpu_hits, o_hits, diag, oracle):
     return int((~(same_prim & same_t)).sum())
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_closest_and_any_hit_bit_exact_small(gpu, oracle, variant):
     import torch
     from pbrt_v3_rs_b200 import workloads as wl

@@ -48,7 +48,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -166,6 +166,48 @@ def run_reference(args, rank):
     return 0
 
 
+def path_tracing_leg(pkg, args, rank, world):
+    """Second half of BASELINE.json's metric: path samples/s at 1920x1080 (config C3: 871 200 triangles, matte /
+    plastic / glass / metal, area + point light, maxdepth 8, 64 spp Halton), screen rows sharded over the ranks
+    in interleaved bands, film summed with one all-reduce.  Strong scaling: the image is fixed."""
+    import torch
+    import torch.distributed as dist
+    from pbrt_v3_rs_b200 import multigpu
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = wl.scene_c3(nu=40, nv=40, xres=160, yres=90, spp=8) if args.small else wl.scene_c3()
+    integ = pkg.PathIntegrator(sd)
+    integ.preprocess()
+    h, w = integ.film_shape()
+    spp = sd.sampler["pixelsamples"]
+    times, red = [], []
+    for it in range(1 + args.path_iters):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        film = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        integ.render_shard_device(rank, world, film.data_ptr(), multigpu.BAND_ROWS, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        multigpu.reduce_film(film)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        if it:  # first iteration is the warm-up
+            times.append(t2 - t0)
+            red.append(t2 - t1)
+    rc = integ.ray_counts()
+    t = torch.tensor([float(np.mean(times)), float(np.mean(red)), float(rc[1] + rc[2])], dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    secs, red_s = float(tmax[0]), float(tmax[1])
+    return {"metric": "path samples/s", "value": h * w * spp / secs, "unit": "samples/s", "ms_per_image": secs * 1e3, "n_gpus": world,
+            "scaling": "strong", "film_allreduce_ms": red_s * 1e3, "rays_per_image": float(t[2]), "mrays_in_render": float(t[2]) / secs / 1e6,
+            "config": "C3: %d triangles, matte/plastic/glass/metal, area+point light, power light sampling, maxdepth %d, %dx%d @ %d spp Halton, box filter; rows in bands of %d dealt round-robin to the ranks"
+                      % (sd.tri_verts.shape[0], sd.integrator["maxdepth"], w, h, spp, multigpu.BAND_ROWS)}
+
+
 def workload_config(w, args):
     n = int(w["closest"].shape[0])
     return {"workload": "C2 synthetic ray-cast microbench: %d-triangle displaced sphere, SAH BVH maxnodeprims=4, %d closest-hit rays (primary + shuffled diffuse-bounce) + %d any-hit rays per GPU per step"
@@ -183,6 +225,8 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="traversal kernel variant (0 default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-path", action="store_true", help="skip the path-tracing (samples/s) leg")
+    ap.add_argument("--path-iters", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -227,12 +271,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(args.warmup):
         step()
     barrier()
     launches0 = pkg.launch_count()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     barrier()
     ev[0].record(stream)
@@ -270,6 +314,8 @@ def main():
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         assert torch.equal(h_hits.view(torch.int32), d_hits.cpu().view(torch.int32)) and torch.equal(h_occ, d_occ.cpu()), "e2e results differ from the resident path"
 
+    path = None if args.no_path else path_tracing_leg(pkg, args, rank, world)
+
     # max over ranks
     t = torch.tensor([total_ms, closest_ms, shadow_ms, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -284,13 +330,15 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(w, args),
                 "closest_mrays": n / (closest_ms * 1e-3) / 1e6, "anyhit_mrays": n / (shadow_ms * 1e-3) / 1e6,
-                "roofline": {"bound": "hbm", "kernel": "k_trace_persistent<closest>" if args.variant == 0 else "k_trace_simple<closest,%d>" % args.variant,
+                "roofline": {"bound": "hbm", "kernel": {0: "k_trace_phased<closest>", 3: "k_trace_persistent<closest>"}.get(args.variant, "k_trace_simple<closest,%d>" % args.variant),
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": bytes_closest, "nodes_per_ray": nn_c / n, "tris_per_ray": nt_c / n,
                              "launch_ms": closest_ms,
                              "anyhit": {"achieved": bytes_shadow / (shadow_ms * 1e-3) / 1e9, "frac": bytes_shadow / (shadow_ms * 1e-3) / 1e9 / peak,
                                         "algorithmic_bytes_per_launch": bytes_shadow, "nodes_per_ray": nn_s / n, "tris_per_ray": nt_s / n, "launch_ms": shadow_ms}},
                 "gpu_launches": int(launches), "clocks": clk, "setup_s": w["setup_s"]}
+        if path is not None:
+            line["path_tracing"] = path
         if e2e_ms is not None:
             line["e2e"] = {"value": world * 2 * n / (e2e_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n,
                            "ms_per_step": e2e_max}

@@ -210,6 +210,10 @@ void b200pt_scene_destroy(b200pt_scene* s);
 int b200pt_render_rows(b200pt_scene* s, int32_t row_begin, int32_t row_end, float* film_xyzw);
 /* Same, film stays on the device (d_film_xyzw: device pointer, full window). */
 int b200pt_render_rows_device(b200pt_scene* s, int32_t row_begin, int32_t row_end, void* d_film_xyzw, void* stream);
+/* Multi-GPU decomposition: the pixel rows are cut into bands of `band_rows` rows dealt round-robin to `n_shards`
+ * shards (interleaving balances sky and geometry); this call renders shard `shard` into a zero-initialised film of
+ * the full window (device memory).  Summing the shards' films (NCCL all-reduce) gives the whole image. */
+int b200pt_render_shard_device(b200pt_scene* s, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream);
 /* Film::write_image normalisation (film/mod.rs:356-417): XYZ+weight -> RGB,
  * 3 floats per pixel, HOST memory both sides. */
 int b200pt_film_resolve(const b200pt_film* film, const float* film_xyzw, float* rgb_out);

@@ -85,7 +85,7 @@ B2_D int meta_pack(int dim, int bounces, int spec) { return (dim & 0xffff) | ((b
 // Implicit mode (list == nullptr): path p of the wave covers sample (first_sample + p) in pixel-major
 // order over the shard's sample rows: global sample g -> pixel g / spp, sample g % spp.
 // Explicit mode: list holds (x, y, sample) triples.
-__global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long first_sample, int n, int spp, int row0, const int* __restrict__ list,
+__global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long first_sample, int n, int spp, const int* __restrict__ rows, const int* __restrict__ list,
                                                  float2* __restrict__ p_film_out, float4* __restrict__ rays_out) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long
         s = (int)(g - pix * spp);
         int w = S.sb[2] - S.sb[0];
         px = S.sb[0] + (int)(pix % w);
-        py = row0 + (int)(pix / w);
+        py = rows[(int)(pix / w)];
     }
     unsigned long long idx = halton_index(S.halton, px, py, (unsigned long long)s);
     float u0 = halton_dim(S.halton, idx, 0), u1 = halton_dim(S.halton, idx, 1);
@@ -465,21 +465,25 @@ struct DFilm {
 // One thread per film pixel of the rendered rows: gathers, in pixel-major then sample order, every
 // sample of this shard whose filter window covers the pixel (film_tile.rs:62-108).
 __global__ void __launch_bounds__(128) k_film(DFilm F, const float* __restrict__ table, const float4* __restrict__ sample_L,
-                                              const float2* __restrict__ p_film, int spp, int srow0, int srow1, int prow0, int prow1,
+                                              const float2* __restrict__ p_film, int spp, const int* __restrict__ row_index,
                                               float4* __restrict__ film) {
     int w = F.crop[2] - F.crop[0];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w * (prow1 - prow0)) return;
-    int x = F.crop[0] + i % w, y = prow0 + i / w;
+    if (i >= w * (F.crop[3] - F.crop[1])) return;
+    int x = F.crop[0] + i % w, y = F.crop[1] + i / w;
     int sw = F.sb[2] - F.sb[0];
     // candidate source pixels: those whose sample positions can reach (x, y)
     int qx0 = (int)floorf((float)x + 0.5f - F.rx) - 1, qx1 = (int)ceilf((float)x + 0.5f + F.rx) + 1;
     int qy0 = (int)floorf((float)y + 0.5f - F.ry) - 1, qy1 = (int)ceilf((float)y + 0.5f + F.ry) + 1;
     qx0 = max(qx0, F.sb[0]); qx1 = min(qx1, F.sb[2]);
-    qy0 = max(qy0, srow0); qy1 = min(qy1, srow1);
+    qy0 = max(qy0, F.sb[1]); qy1 = min(qy1, F.sb[3]);
     RGB sum = rgb1(0.0f);
     float wsum = 0.0f;
-    for (int qy = qy0; qy < qy1; ++qy)
+    bool any = false;
+    for (int qy = qy0; qy < qy1; ++qy) {
+        const int krow = row_index[qy - F.sb[1]];  // position of sample row qy among this shard's rows, -1 = not ours
+        if (krow < 0) continue;
+        any = true;
         for (int qx = qx0; qx < qx1; ++qx) {
             // pixel bounds of the reference tile that owns sample pixel (qx, qy) (film/mod.rs:182-198)
             int tx0 = F.sb[0] + ((qx - F.sb[0]) / F.tile) * F.tile, ty0 = F.sb[1] + ((qy - F.sb[1]) / F.tile) * F.tile;
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(128) k_film(DFilm F, const float* __restrict__
             int bx0 = max((int)ceilf((float)tx0 - 0.5f - F.rx), F.crop[0]), by0 = max((int)ceilf((float)ty0 - 0.5f - F.ry), F.crop[1]);
             int bx1 = min((int)floorf((float)tx1 - 0.5f + F.rx) + 1, F.crop[2]), by1 = min((int)floorf((float)ty1 - 0.5f + F.ry) + 1, F.crop[3]);
             if (x < bx0 || x >= bx1 || y < by0 || y >= by1) continue;
-            long long base = ((long long)(qy - srow0) * sw + (qx - F.sb[0])) * spp;
+            long long base = ((long long)krow * sw + (qx - F.sb[0])) * spp;
             for (int s = 0; s < spp; ++s) {
                 float4 l = sample_L[base + s];
                 if (l.w == 0.0f) continue;  // pixel outside the integrator's pixel bounds
@@ -506,6 +510,8 @@ __global__ void __launch_bounds__(128) k_film(DFilm F, const float* __restrict__
                 wsum += fw;
             }
         }
+    }
+    if (!any) return;  // no sample row of this shard reaches the pixel: leave the zero written by the memset
     // Film::merge_film_tile: tile RGB -> XYZ (film/mod.rs:243-248); accumulated into the shard's film
     float X = 0.412453f * sum.r + 0.357580f * sum.g + 0.180423f * sum.b;
     float Y = 0.212671f * sum.r + 0.715160f * sum.g + 0.072169f * sum.b;
@@ -533,6 +539,8 @@ struct SceneImpl {
     long long sample_cap = 0;
     float4* d_film = nullptr;
     size_t film_cap = 0;
+    int* d_rows = nullptr;       // sample rows owned by the current shard
+    int* d_row_index = nullptr;  // sample row -> position in d_rows, -1 = not owned
 };
 
 static const int kWaveCap = 1 << 22;
@@ -901,6 +909,8 @@ void b200pt_scene_destroy(b200pt_scene* sc) {
     if (sc->impl.d_sample_L) cudaFree(sc->impl.d_sample_L);
     if (sc->impl.d_sample_pf) cudaFree(sc->impl.d_sample_pf);
     if (sc->impl.d_film) cudaFree(sc->impl.d_film);
+    if (sc->impl.d_rows) cudaFree(sc->impl.d_rows);
+    if (sc->impl.d_row_index) cudaFree(sc->impl.d_row_index);
     accel_free_device(&sc->impl.accel);
     delete sc;
 }
@@ -911,26 +921,18 @@ int b200pt_scene_ray_counts(const b200pt_scene* s, uint64_t counts[3]) {
     return B200PT_OK;
 }
 
-int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_end, void* d_film_xyzw, void* stream) {
-    int rc = require_device();
-    if (rc) return rc;
-    if (!sc || !d_film_xyzw) { b200pt_set_error("b200pt_render_rows_device: null argument"); return B200PT_ERR_INVALID; }
-    SceneImpl* s = &sc->impl;
-    std::lock_guard<std::mutex> g(s->mu);  // render serialises per scene
-    B2_CUDA(cudaSetDevice(g_device));
-    cudaStream_t st = (cudaStream_t)stream;
+// Renders the sample rows listed in `srows` (ascending, inside the sample bounds) into a zero-initialised film of
+// the full cropped window.  Shards with disjoint row sets sum to the whole image (each sample is taken once).
+static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d_film_xyzw, cudaStream_t st) {
+    int rc = B200PT_OK;
     const b200pt_film& f = s->film;
     const int cw = f.crop[2] - f.crop[0], ch = f.crop[3] - f.crop[1];
-    if (row_begin < 0 || row_end > ch || row_begin > row_end) { b200pt_set_error("b200pt_render_rows_device: row range outside the cropped window"); return B200PT_ERR_INVALID; }
     B2_CUDA(cudaMemsetAsync(d_film_xyzw, 0, (size_t)cw * ch * sizeof(float4), st));
     s->rays[0] = s->rays[1] = s->rays[2] = 0;
-    if (row_begin == row_end) return B200PT_OK;
-    // sample rows owned by this shard: the pixel rows, extended to the sample bounds at the image's top/bottom edge
+    if (srows.empty()) { B2_CUDA(cudaStreamSynchronize(st)); return B200PT_OK; }
     const int* sb = s->sample_bounds;
-    int prow0 = f.crop[1] + row_begin, prow1 = f.crop[1] + row_end;
-    int srow0 = row_begin == 0 ? sb[1] : prow0, srow1 = row_end == ch ? sb[3] : prow1;
-    const int sw = sb[2] - sb[0], spp = s->sampler.spp;
-    const long long n_samples = (long long)(srow1 - srow0) * sw * spp;
+    const int sw = sb[2] - sb[0], sh = sb[3] - sb[1], spp = s->sampler.spp;
+    const long long n_samples = (long long)srows.size() * sw * spp;
     if (!s->wave_cap && (rc = wave_alloc(s, kWaveCap))) return rc;
     if (n_samples > s->sample_cap) {
         if (s->d_sample_L) cudaFree(s->d_sample_L);
@@ -940,12 +942,20 @@ int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_e
         B2_CUDA(cudaMalloc(&s->d_sample_pf, (size_t)n_samples * sizeof(float2)));
         s->sample_cap = n_samples;
     }
+    if (!s->d_rows) {
+        B2_CUDA(cudaMalloc(&s->d_rows, (size_t)sh * sizeof(int)));
+        B2_CUDA(cudaMalloc(&s->d_row_index, (size_t)sh * sizeof(int)));
+    }
+    std::vector<int> row_index((size_t)sh, -1);
+    for (size_t k = 0; k < srows.size(); ++k) row_index[(size_t)(srows[k] - sb[1])] = (int)k;
+    B2_CUDA(cudaMemcpyAsync(s->d_rows, srows.data(), srows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(s->d_row_index, row_index.data(), (size_t)sh * sizeof(int), cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
     float4* d_L = s->d_sample_L;
     float2* d_pf = s->d_sample_pf;
-    cudaError_t e;
     for (long long first = 0; first < n_samples && !rc; first += s->wave_cap) {
         int n = (int)std::min<long long>(s->wave_cap, n_samples - first);
-        k_raygen<<<(n + 255) / 256, 256, 0, st>>>(s->dev, s->wave, first, n, spp, srow0, nullptr, d_pf, nullptr);
+        k_raygen<<<(n + 255) / 256, 256, 0, st>>>(s->dev, s->wave, first, n, spp, s->d_rows, nullptr, d_pf, nullptr);
         g_launches.fetch_add(1);
         rc = run_wave(s, n, st);
         if (rc) break;
@@ -960,17 +970,53 @@ int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_e
         F.max_lum = f.max_sample_luminance;
         std::memcpy(F.sb, sb, 16);
         F.tile = 16;
-        // This shard's samples also reach pixel rows of the neighbouring shards when the filter is wider than a
-        // pixel: accumulate them too (apron); the shards' films are summed afterwards, each contribution counted once.
-        int apron = (int)std::ceil(F.ry + 0.5f);
-        int frow0 = std::max(f.crop[1], prow0 - apron), frow1 = std::min(f.crop[3], prow1 + apron);
-        int npix = cw * (frow1 - frow0);
-        k_film<<<(npix + 127) / 128, 128, 0, st>>>(F, s->d_filter_table, d_L, d_pf, spp, srow0, srow1, frow0, frow1, (float4*)d_film_xyzw);
+        // every film pixel gathers from the sample rows this shard owns (also rows of a neighbouring shard's pixels
+        // when the filter is wider than a pixel); the shards' films are summed afterwards
+        int npix = cw * ch;
+        k_film<<<(npix + 127) / 128, 128, 0, st>>>(F, s->d_filter_table, d_L, d_pf, spp, s->d_row_index, (float4*)d_film_xyzw);
         g_launches.fetch_add(1);
-        e = cudaStreamSynchronize(st);
+        cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = cuda_fail(e, "render");
     }
     return rc;
+}
+
+// sample rows of the pixel rows [r0, r1) of the cropped window; the rows of the sample bounds above / below the
+// window (filters wider than a pixel) go with the first / last pixel row
+static void append_rows(const SceneImpl* s, int r0, int r1, std::vector<int>* out) {
+    const b200pt_film& f = s->film;
+    const int ch = f.crop[3] - f.crop[1];
+    const int* sb = s->sample_bounds;
+    int a = r0 == 0 ? sb[1] : f.crop[1] + r0, b = r1 == ch ? sb[3] : f.crop[1] + r1;
+    for (int y = a; y < b; ++y) out->push_back(y);
+}
+
+int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_end, void* d_film_xyzw, void* stream) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!sc || !d_film_xyzw) { b200pt_set_error("b200pt_render_rows_device: null argument"); return B200PT_ERR_INVALID; }
+    SceneImpl* s = &sc->impl;
+    std::lock_guard<std::mutex> g(s->mu);  // render serialises per scene
+    B2_CUDA(cudaSetDevice(g_device));
+    const int ch = s->film.crop[3] - s->film.crop[1];
+    if (row_begin < 0 || row_end > ch || row_begin > row_end) { b200pt_set_error("b200pt_render_rows_device: row range outside the cropped window"); return B200PT_ERR_INVALID; }
+    std::vector<int> rows;
+    if (row_begin < row_end) append_rows(s, row_begin, row_end, &rows);
+    return render_rows_impl(s, rows, d_film_xyzw, (cudaStream_t)stream);
+}
+
+int b200pt_render_shard_device(b200pt_scene* sc, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!sc || !d_film_xyzw || n_shards < 1 || shard < 0 || shard >= n_shards || band_rows < 1) { b200pt_set_error("b200pt_render_shard_device: invalid argument"); return B200PT_ERR_INVALID; }
+    SceneImpl* s = &sc->impl;
+    std::lock_guard<std::mutex> g(s->mu);
+    B2_CUDA(cudaSetDevice(g_device));
+    const int ch = s->film.crop[3] - s->film.crop[1];
+    std::vector<int> rows;
+    for (int r0 = 0, band = 0; r0 < ch; r0 += band_rows, ++band)
+        if (band % n_shards == shard) append_rows(s, r0, std::min(ch, r0 + band_rows), &rows);
+    return render_rows_impl(s, rows, d_film_xyzw, (cudaStream_t)stream);
 }
 
 int b200pt_render_rows(b200pt_scene* sc, int32_t row_begin, int32_t row_end, float* film_xyzw) {
@@ -1032,7 +1078,7 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
     for (int64_t first = 0; first < n && !rc; first += cap) {
         int m = (int)std::min<int64_t>(cap, n - first);
         cudaMemcpy(d_list, pixel_sample + 3 * first, (size_t)m * 3 * sizeof(int), cudaMemcpyHostToDevice);
-        k_raygen<<<(m + 255) / 256, 256>>>(s->dev, s->wave, 0, m, s->sampler.spp, 0, d_list, nullptr, d_rays);
+        k_raygen<<<(m + 255) / 256, 256>>>(s->dev, s->wave, 0, m, s->sampler.spp, nullptr, d_list, nullptr, d_rays);
         g_launches.fetch_add(1);
         rc = run_wave(s, m, 0);
         if (rc) break;

@@ -347,6 +347,19 @@ class PathIntegrator:
         _check(lib().b200pt_render_rows(self._h, row_begin, row_end, _ptr(film)), "b200pt_render_rows")
         return film
 
+    def render_shard_device(self, shard, n_shards, d_film_ptr, band_rows=8, stream=0):
+        """Renders shard `shard` of `n_shards` (interleaved row bands) into a device film (H*W*4 float32, full window)."""
+        from . import _check, lib
+        if self._h is None:
+            self.preprocess()
+        _check(lib().b200pt_render_shard_device(self._h, shard, n_shards, band_rows, d_film_ptr, stream), "b200pt_render_shard_device")
+
+    def render_rows_device(self, row_begin, row_end, d_film_ptr, stream=0):
+        from . import _check, lib
+        if self._h is None:
+            self.preprocess()
+        _check(lib().b200pt_render_rows_device(self._h, row_begin, row_end, d_film_ptr, stream), "b200pt_render_rows_device")
+
     def resolve(self, film_xyzw):
         from . import _check, _ptr, lib
         h, w = film_xyzw.shape[:2]

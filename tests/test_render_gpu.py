@@ -80,6 +80,24 @@ def test_c1_config_small_and_row_shards(gpu, oracle):
     assert np.array_equal(parts[..., 3], full[..., 3])
 
 
+def test_interleaved_shards_sum_to_full_image(gpu):
+    """The multi-GPU decomposition, emulated on one device: shards of interleaved row bands sum to the full film
+    (box filter: disjoint rows; gaussian: aprons add up)."""
+    import torch
+    from pbrt_v3_rs_b200 import workloads as wl
+    for filt in ("box", "gaussian"):
+        sd = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="all", res=40, spp=4, strategy="power", filt=filt)
+        integ = gpu.PathIntegrator(sd)
+        full = integ.render_rows()
+        for n in (2, 3):
+            acc = torch.zeros((40, 40, 4), dtype=torch.float32, device="cuda")
+            for r in range(n):
+                part = torch.zeros_like(acc)
+                integ.render_shard_device(r, n, part.data_ptr(), band_rows=8)
+                acc += part
+            assert np.allclose(acc.cpu().numpy(), full, rtol=2e-6, atol=1e-6), (filt, n)
+
+
 def test_c3_config_small(gpu, oracle):
     from pbrt_v3_rs_b200 import workloads as wl
     sd = wl.scene_c3(nu=40, nv=40, xres=160, yres=90, spp=16, maxdepth=8)

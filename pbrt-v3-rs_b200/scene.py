@@ -321,9 +321,12 @@ class PathIntegrator:
         self._h = h
 
     def close(self):
-        from . import lib
-        if self._h:
-            lib().b200pt_scene_destroy(self._h)
+        if getattr(self, "_h", None):
+            try:
+                from . import lib
+                lib().b200pt_scene_destroy(self._h)
+            except Exception:  # interpreter shutdown: the import machinery may already be gone
+                pass
             self._h = None
 
     __del__ = close

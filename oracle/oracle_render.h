@@ -928,10 +928,40 @@ inline Ray camera_ray(const RenderScene& sc, int px, int py, Sampler& sampler, P
     return xf_ray(sc.camera_to_world, ray);
 }
 
-inline Sampler* make_sampler(const RenderScene& sc, uint64_t /*seed*/) {
-    // samplers/src/halton.rs From<(&ParamSet, Bounds2i)>; the (0,2)-sequence sampler lives in a later round.
+inline Sampler* make_sampler(const RenderScene& sc, uint64_t seed) {
+    // SamplerIntegrator::render_tile: data.sampler.clone_sampler(tile_idx) (sampler_integrator.rs:323).
+    // Halton ignores the seed (halton.rs:176-182); the (0,2) sampler seeds its PCG32 with it (zero_two_sequence.rs:45-51).
+    if (sc.sampler.type == B200PT_SAMPLER_ZEROTWO) return new ZeroTwoSequenceSampler(sc.sampler.spp, sc.sampler.dimensions, seed);
     return new HaltonSampler(sc.sampler.spp, sc.sample_bounds[2] - sc.sample_bounds[0], sc.sample_bounds[3] - sc.sample_bounds[1],
                              sc.sampler.sample_at_center != 0);
+}
+
+// Positions a fresh tile sampler on sample `s` of pixel (px, py) exactly as render_tile would have reached it:
+// for the (0,2) sampler every earlier pixel of the tile advances the tile's RNG in start_pixel.
+inline Sampler* sampler_at(const RenderScene& sc, int px, int py, int s) {
+    const int tile_size = 16;
+    int ex = sc.sample_bounds[2] - sc.sample_bounds[0];
+    int ntx = (ex + tile_size - 1) / tile_size;
+    int tx = (px - sc.sample_bounds[0]) / tile_size, ty = (py - sc.sample_bounds[1]) / tile_size;
+    Sampler* smp = make_sampler(sc, (uint64_t)(ty * ntx + tx));
+    if (sc.sampler.type == B200PT_SAMPLER_ZEROTWO) {
+        int x0 = sc.sample_bounds[0] + tx * tile_size, x1 = pmin(x0 + tile_size, sc.sample_bounds[2]);
+        int y0 = sc.sample_bounds[1] + ty * tile_size;
+        for (int y = y0; y <= py; ++y)
+            for (int x = x0; x < x1; ++x) {
+                if (y == py && x == px) break;
+                smp->start_pixel(x, y);
+            }
+        smp->start_pixel(px, py);
+        ((ZeroTwoSequenceSampler*)smp)->set_sample_number(s);
+    } else {
+        HaltonSampler* h = (HaltonSampler*)smp;
+        h->start_pixel(px, py);
+        h->cur_sample = s;
+        h->dimension = 0;
+        h->interval_sample_index = h->get_index_for_sample((uint64_t)s);
+    }
+    return smp;
 }
 
 // sampler_integrator.rs:374-401 radiance sanitisation.
@@ -1072,18 +1102,14 @@ inline double render(RenderScene* scp, float* rgb_out, uint64_t* stats_out, int 
 inline void li_batch(RenderScene* scp, const int32_t* ps, int64_t n, float* out, int nthreads) {
     RenderScene& sc = *scp;
     auto body = [&](size_t b, size_t e) {
-        HaltonSampler* s = (HaltonSampler*)make_sampler(sc, 0);
         for (size_t i = b; i < e; ++i) {
-            s->start_pixel(ps[3 * i], ps[3 * i + 1]);
-            s->cur_sample = ps[3 * i + 2];
-            s->dimension = 0;
-            s->interval_sample_index = s->get_index_for_sample((uint64_t)ps[3 * i + 2]);
+            Sampler* s = sampler_at(sc, ps[3 * i], ps[3 * i + 1], ps[3 * i + 2]);
             P2 pf;
             Ray ray = camera_ray(sc, ps[3 * i], ps[3 * i + 1], *s, &pf);
             RGB l = sanitize_radiance(path_li(sc, ray, *s));
             out[3 * i] = l.c[0]; out[3 * i + 1] = l.c[1]; out[3 * i + 2] = l.c[2];
+            delete s;
         }
-        delete s;
     };
     if (nthreads <= 1 || n < 64) { body(0, (size_t)n); return; }
     std::vector<std::thread> th;
@@ -1096,18 +1122,15 @@ inline void li_batch(RenderScene* scp, const int32_t* ps, int64_t n, float* out,
 }
 inline void camera_rays(RenderScene* scp, const int32_t* ps, int64_t n, float* out8) {
     RenderScene& sc = *scp;
-    HaltonSampler* s = (HaltonSampler*)make_sampler(sc, 0);
     for (int64_t i = 0; i < n; ++i) {
-        s->start_pixel(ps[3 * i], ps[3 * i + 1]);
-        s->dimension = 0;
-        s->interval_sample_index = s->get_index_for_sample((uint64_t)ps[3 * i + 2]);
+        Sampler* s = sampler_at(sc, ps[3 * i], ps[3 * i + 1], ps[3 * i + 2]);
         P2 pf;
         Ray r = camera_ray(sc, ps[3 * i], ps[3 * i + 1], *s, &pf);
         float* o = out8 + 8 * i;
         o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.t_max;
         o[4] = r.d.x; o[5] = r.d.y; o[6] = r.d.z; o[7] = r.time;
+        delete s;
     }
-    delete s;
 }
 
 }  // namespace orc

@@ -41,6 +41,8 @@ struct DeviceScene {
     float light_func_int;
     int n_lights, n_infinite;
     DHalton halton;
+    DZeroTwo zt;
+    int sampler_type;  // B200PT_SAMPLER_*
     DCamera camera;
     int max_depth;
     float rr_threshold;
@@ -81,6 +83,24 @@ static const int kBins = 5;
 
 B2_D int meta_pack(int dim, int bounces, int spec) { return (dim & 0xffff) | ((bounces & 0xff) << 16) | ((spec & 0xff) << 24); }
 
+// Sampler::get_1d / get_2d for the path's current sample.  `key` is the Halton sample index, or for the (0,2)
+// sampler (owned pixel index << 16 | sample number); `dim` is the Halton dimension counter, or the 1-D slot counter
+// in its low byte and the 2-D slot counter in the next byte (core/src/sampler/pixel_sampler.rs:88-110).
+B2_D float smp_1d(const DeviceScene& S, unsigned long long key, int& dim) {
+    if (S.sampler_type == B200PT_SAMPLER_HALTON) { float v = halton_dim(S.halton, key, dim); dim += 1; return v; }
+    int d1 = dim & 0xff;
+    float v = zt_1d(S.zt, (long long)(key >> 16), d1, (int)(key & 0xffff));
+    dim += 1;
+    return v;
+}
+B2_D P2 smp_2d(const DeviceScene& S, unsigned long long key, int& dim) {
+    if (S.sampler_type == B200PT_SAMPLER_HALTON) { P2 v = mk2(halton_dim(S.halton, key, dim), halton_dim(S.halton, key, dim + 1)); dim += 2; return v; }
+    int d2 = (dim >> 8) & 0xff;
+    P2 v = zt_2d(S.zt, (long long)(key >> 16), d2, (int)(key & 0xffff));
+    dim += 0x100;
+    return v;
+}
+
 // ---- K1: camera rays --------------------------------------------------------------------------
 // Implicit mode (list == nullptr): path p of the wave covers sample (first_sample + p) in pixel-major
 // order over the shard's sample rows: global sample g -> pixel g / spp, sample g % spp.
@@ -99,11 +119,17 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long
         px = S.sb[0] + (int)(pix % w);
         py = rows[(int)(pix / w)];
     }
-    unsigned long long idx = halton_index(S.halton, px, py, (unsigned long long)s);
-    float u0 = halton_dim(S.halton, idx, 0), u1 = halton_dim(S.halton, idx, 1);
-    P2 pf = mk2((float)px + u0, (float)py + u1);  // sampler/mod.rs:43-51
-    float tu = halton_dim(S.halton, idx, 2);
-    P2 pl = mk2(halton_dim(S.halton, idx, 3), halton_dim(S.halton, idx, 4));
+    unsigned long long idx;
+    if (S.sampler_type == B200PT_SAMPLER_HALTON) idx = halton_index(S.halton, px, py, (unsigned long long)s);
+    else {  // owned pixel index: position of the row among this shard's rows (explicit lists own every row)
+        long long krow = list ? (long long)(py - S.sb[1]) : (g / spp) / (S.sb[2] - S.sb[0]);
+        idx = ((unsigned long long)(krow * (S.sb[2] - S.sb[0]) + (px - S.sb[0])) << 16) | (unsigned long long)s;
+    }
+    int dim = 0;
+    P2 fs = smp_2d(S, idx, dim);  // Sampler::get_camera_sample, sampler/mod.rs:43-51
+    P2 pf = mk2((float)px + fs.x, (float)py + fs.y);
+    float tu = smp_1d(S, idx, dim);
+    P2 pl = smp_2d(S, idx, dim);
     Ray32 r = camera_ray(S.camera, pf, tu, pl);
     bool live = list || (px >= S.pb[0] && px < S.pb[2] && py >= S.pb[1] && py < S.pb[3]);  // sampler_integrator.rs:348
     W.ray[0][2 * p] = make_float4(r.ox, r.oy, r.oz, live ? r.tmax : -1.0f);  // tmax < 0: the root test fails, the path dies as a miss
@@ -112,7 +138,7 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long
     W.L[p] = make_float4(0.0f, 0.0f, 0.0f, live ? 1.0f : 0.0f);
     W.beta[p] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     W.hidx[p] = idx;
-    W.meta[p] = meta_pack(5, live ? 0 : 255, 0);
+    W.meta[p] = meta_pack(dim, live ? 0 : 255, 0);
     if (p_film_out) p_film_out[g] = make_float2(pf.x, pf.y);
     if (rays_out) { rays_out[2 * p] = make_float4(r.ox, r.oy, r.oz, r.tmax); rays_out[2 * p + 1] = make_float4(r.dx, r.dy, r.dz, r.time); }
 }
@@ -230,13 +256,13 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
 
     // path.rs:162-173 -> uniform_sample_one_light (integrator/common.rs:89-133)
     if (bsdf_num_components(bsdf, kNoSpec) > 0 && S.n_lights > 0) {
-        float u_pick = halton_dim(S.halton, hidx, dim); dim += 1;
+        float u_pick = smp_1d(S, hidx, dim);
         // Distribution1D::sample_discrete, distribution_1d.rs:81-94
         int ln = find_interval_cdf(S.light_cdf, S.n_lights + 1, u_pick);
         float pick_pdf = S.light_func_int > 0.0f ? S.light_func[ln] / (S.light_func_int * (float)S.n_lights) : 0.0f;
         if (pick_pdf != 0.0f) {
-            P2 u_light = mk2(halton_dim(S.halton, hidx, dim), halton_dim(S.halton, hidx, dim + 1)); dim += 2;
-            P2 u_scatter = mk2(halton_dim(S.halton, hidx, dim), halton_dim(S.halton, hidx, dim + 1)); dim += 2;
+            P2 u_light = smp_2d(S, hidx, dim);
+            P2 u_scatter = smp_2d(S, hidx, dim);
             const DLight& light = S.lights[ln];
             // ---- estimate_direct (common.rs:146-299), light-sampling half ----
             RGB ld_light = rgb1(0.0f);
@@ -376,7 +402,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
     }
 
     // path.rs:175-206: sample the BSDF for the next direction
-    P2 u = mk2(halton_dim(S.halton, hidx, dim), halton_dim(S.halton, hidx, dim + 1)); dim += 2;
+    P2 u = smp_2d(S, hidx, dim);
     V3 wo = -ray_d;
     BxDFSample bs = bsdf_sample_f(bsdf, wo, u, BSDF_ALL);
     if (is_black(bs.f) || bs.pdf == 0.0f) {
@@ -395,7 +421,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
     bool alive = true;
     if (max_component_value(rr_beta) < S.rr_threshold && bounces > 3) {
         float q = pmax(0.05f, 1.0f - max_component_value(rr_beta));
-        float ur = halton_dim(S.halton, hidx, dim); dim += 1;
+        float ur = smp_1d(S, hidx, dim);
         if (ur < q) alive = false;
         else beta = beta / (1.0f - q);
     }
@@ -407,6 +433,52 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
     int ns = atomicAdd(&W.counters[0], 1);
     store_ray(W.ray[cur ^ 1], ns, next_o, bs.wi, __int_as_float(0x7f800000), time);
     W.qpid[cur ^ 1][ns] = pid;
+}
+
+// ---- (0,2)-sequence prepass: one thread per reference tile replays the tile sampler's PCG32 stream ------------
+// ZeroTwoSequenceSampler::start_pixel for every pixel of the tile in row-major order (zero_two_sequence.rs:65-111,
+// sampler_integrator.rs:323-345): per slot one (two) scramble draw(s), spp one-element shuffles (one draw each, the
+// rejection threshold of bounded_uniform_u32(0, 1) is 0) and one Fisher-Yates shuffle of the spp samples.
+__global__ void __launch_bounds__(64) k_zerotwo_tiles(int sb0, int sb1, int sb2, int sb3, int ntx, int nty, int dims, int n1, int n2, int spp,
+                                                      const int* __restrict__ row_index, uint32_t* __restrict__ scr1, uint16_t* __restrict__ perm1,
+                                                      uint32_t* __restrict__ scr2, uint16_t* __restrict__ perm2, uint16_t* __restrict__ scratch) {
+    int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= ntx * nty) return;
+    const int tx = tile % ntx, ty = tile / ntx, sw = sb2 - sb0;
+    DPcg32 rng;
+    pcg_set_sequence(rng, (unsigned long long)tile);  // clone_sampler(tile_idx) -> RNG::new(seed)
+    uint16_t* idx = scratch + (size_t)tile * spp;
+    const int x0 = sb0 + tx * 16, x1 = min(x0 + 16, sb2), y0 = sb1 + ty * 16, y1 = min(y0 + 16, sb3);
+    for (int y = y0; y < y1; ++y) {
+        const int krow = row_index[y - sb1];
+        for (int x = x0; x < x1; ++x) {
+            const long long pix = (long long)krow * sw + (x - sb0);
+            for (int pass = 0; pass < 2; ++pass) {       // pass 0: van_der_corput slots, pass 1: sobol_2d slots
+                const int keep = pass == 0 ? n1 : n2;
+                for (int d = 0; d < dims; ++d) {
+                    uint32_t s0 = pcg_next(rng), s1 = pass ? pcg_next(rng) : 0u;
+                    for (int i = 0; i < spp; ++i) (void)pcg_next(rng);
+                    const bool store = krow >= 0 && d < keep;
+                    if (store) for (int i = 0; i < spp; ++i) idx[i] = (uint16_t)i;
+                    for (int i = 0; i < spp; ++i) {
+                        int other = i + (int)pcg_bounded(rng, (uint32_t)(spp - i));
+                        if (store) { uint16_t t = idx[i]; idx[i] = idx[other]; idx[other] = t; }
+                    }
+                    if (store) {
+                        if (pass == 0) {
+                            scr1[pix * n1 + d] = s0;
+                            uint16_t* o = perm1 + (pix * n1 + d) * spp;
+                            for (int i = 0; i < spp; ++i) o[i] = idx[i];
+                        } else {
+                            scr2[(pix * n2 + d) * 2] = s0; scr2[(pix * n2 + d) * 2 + 1] = s1;
+                            uint16_t* o = perm2 + (pix * n2 + d) * spp;
+                            for (int i = 0; i < spp; ++i) o[i] = idx[i];
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 
 // ---- K4': resolve pending direct lighting ------------------------------------------------------
@@ -539,6 +611,11 @@ struct SceneImpl {
     long long sample_cap = 0;
     float4* d_film = nullptr;
     size_t film_cap = 0;
+    // (0,2)-sequence tables of the current shard
+    uint32_t *d_zt_scr1 = nullptr, *d_zt_scr2 = nullptr;
+    uint16_t *d_zt_perm1 = nullptr, *d_zt_perm2 = nullptr, *d_zt_scratch = nullptr;
+    long long zt_pix_cap = 0;
+    int spp = 1;                 // samples per pixel actually taken (rounded up to a power of two for the (0,2) sampler)
     int* d_rows = nullptr;       // sample rows owned by the current shard
     int* d_row_index = nullptr;  // sample row -> position in d_rows, -1 = not owned
 };
@@ -754,9 +831,20 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         b200pt_set_error("b200pt_scene_create: invalid scene description");
         return B200PT_ERR_INVALID;
     }
-    if (d->sampler.type != B200PT_SAMPLER_HALTON) {
-        b200pt_set_error("b200pt_scene_create: only the Halton sampler is implemented on the device in this round (02sequence: SURVEY §7, next)");
+    if (d->sampler.type != B200PT_SAMPLER_HALTON && d->sampler.type != B200PT_SAMPLER_ZEROTWO) {
+        b200pt_set_error("b200pt_scene_create: unknown sampler type (halton and 02sequence are on this path)");
         return B200PT_ERR_UNSUPPORTED;
+    }
+    if (d->sampler.type == B200PT_SAMPLER_ZEROTWO) {
+        // Past its pre-generated slots the reference's PixelSampler draws from the TILE's RNG inside li(), which makes the
+        // stream position of every later pixel depend on earlier path lengths (SURVEY §7 "ZeroTwo sequencing"): inherently
+        // sequential.  Supported here when "dimensions" covers the path's worst case, so li() never touches the RNG.
+        int need1 = 1 + 2 * d->integrator.max_depth, need2 = 2 + 3 * d->integrator.max_depth;
+        if (d->sampler.dimensions < need1 || d->sampler.dimensions < need2 || d->sampler.dimensions > 255) {
+            b200pt_set_error("b200pt_scene_create: 02sequence needs \"dimensions\" >= 2 + 3 * maxdepth (and <= 255) so that li() never draws from the tile RNG");
+            return B200PT_ERR_UNSUPPORTED;
+        }
+        if (d->sampler.spp > 32768) { b200pt_set_error("b200pt_scene_create: 02sequence pixelsamples > 32768"); return B200PT_ERR_UNSUPPORTED; }
     }
     for (int64_t i = 0; i < d->n_prims; ++i)
         if (d->prim_material[i] < 0 || d->prim_material[i] >= d->n_materials) { b200pt_set_error("b200pt_scene_create: primitive without a material (null-BSDF pass-through is outside this path)"); return B200PT_ERR_UNSUPPORTED; }
@@ -771,6 +859,9 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     D.accel = s->accel.dev;
     s->film = d->film;
     s->sampler = d->sampler;
+    s->spp = d->sampler.spp;
+    if (d->sampler.type == B200PT_SAMPLER_ZEROTWO) { int p2 = 1; while (p2 < s->spp) p2 <<= 1; s->spp = p2; }  // zero_two_sequence.rs:23-32
+    D.sampler_type = d->sampler.type;
 
     // primitives in original order with their material / light / flags
     std::vector<float4> pv((size_t)d->n_prims * 3);
@@ -909,6 +1000,8 @@ void b200pt_scene_destroy(b200pt_scene* sc) {
     if (sc->impl.d_sample_L) cudaFree(sc->impl.d_sample_L);
     if (sc->impl.d_sample_pf) cudaFree(sc->impl.d_sample_pf);
     if (sc->impl.d_film) cudaFree(sc->impl.d_film);
+    for (void* p : {(void*)sc->impl.d_zt_scr1, (void*)sc->impl.d_zt_scr2, (void*)sc->impl.d_zt_perm1, (void*)sc->impl.d_zt_perm2, (void*)sc->impl.d_zt_scratch})
+        if (p) cudaFree(p);
     if (sc->impl.d_rows) cudaFree(sc->impl.d_rows);
     if (sc->impl.d_row_index) cudaFree(sc->impl.d_row_index);
     accel_free_device(&sc->impl.accel);
@@ -918,6 +1011,33 @@ void b200pt_scene_destroy(b200pt_scene* sc) {
 int b200pt_scene_ray_counts(const b200pt_scene* s, uint64_t counts[3]) {
     if (!s || !counts) { b200pt_set_error("b200pt_scene_ray_counts: null argument"); return B200PT_ERR_INVALID; }
     counts[0] = s->impl.rays[0]; counts[1] = s->impl.rays[1]; counts[2] = s->impl.rays[2];
+    return B200PT_OK;
+}
+
+// Builds the (0,2)-sequence tables for the rows currently described by s->d_row_index (no-op for Halton).
+static int zerotwo_prepare(SceneImpl* s, long long n_pix, cudaStream_t st) {
+    if (s->dev.sampler_type != B200PT_SAMPLER_ZEROTWO) return B200PT_OK;
+    const int* sb = s->sample_bounds;
+    const int spp = s->spp, dims = s->sampler.dimensions;
+    const int n1 = 1 + 2 * s->dev.max_depth, n2 = 2 + 3 * s->dev.max_depth;
+    const int ntx = (sb[2] - sb[0] + 15) / 16, nty = (sb[3] - sb[1] + 15) / 16;
+    if (n_pix > s->zt_pix_cap) {
+        for (void** p : {(void**)&s->d_zt_scr1, (void**)&s->d_zt_scr2, (void**)&s->d_zt_perm1, (void**)&s->d_zt_perm2}) { if (*p) cudaFree(*p); *p = nullptr; }
+        s->zt_pix_cap = 0;
+        B2_CUDA(cudaMalloc(&s->d_zt_scr1, (size_t)n_pix * n1 * sizeof(uint32_t)));
+        B2_CUDA(cudaMalloc(&s->d_zt_scr2, (size_t)n_pix * n2 * 2 * sizeof(uint32_t)));
+        B2_CUDA(cudaMalloc(&s->d_zt_perm1, (size_t)n_pix * n1 * spp * sizeof(uint16_t)));
+        B2_CUDA(cudaMalloc(&s->d_zt_perm2, (size_t)n_pix * n2 * spp * sizeof(uint16_t)));
+        s->zt_pix_cap = n_pix;
+    }
+    if (!s->d_zt_scratch) B2_CUDA(cudaMalloc(&s->d_zt_scratch, (size_t)ntx * nty * spp * sizeof(uint16_t)));
+    k_zerotwo_tiles<<<(ntx * nty + 63) / 64, 64, 0, st>>>(sb[0], sb[1], sb[2], sb[3], ntx, nty, dims, n1, n2, spp, s->d_row_index, s->d_zt_scr1,
+                                                          s->d_zt_perm1, s->d_zt_scr2, s->d_zt_perm2, s->d_zt_scratch);
+    g_launches.fetch_add(1);
+    s->dev.zt.scr1 = s->d_zt_scr1; s->dev.zt.perm1 = s->d_zt_perm1; s->dev.zt.scr2 = s->d_zt_scr2; s->dev.zt.perm2 = s->d_zt_perm2;
+    s->dev.zt.n1 = n1; s->dev.zt.n2 = n2; s->dev.zt.spp = spp;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_zerotwo_tiles");
     return B200PT_OK;
 }
 
@@ -931,7 +1051,7 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
     s->rays[0] = s->rays[1] = s->rays[2] = 0;
     if (srows.empty()) { B2_CUDA(cudaStreamSynchronize(st)); return B200PT_OK; }
     const int* sb = s->sample_bounds;
-    const int sw = sb[2] - sb[0], sh = sb[3] - sb[1], spp = s->sampler.spp;
+    const int sw = sb[2] - sb[0], sh = sb[3] - sb[1], spp = s->spp;
     const long long n_samples = (long long)srows.size() * sw * spp;
     if (!s->wave_cap && (rc = wave_alloc(s, kWaveCap))) return rc;
     if (n_samples > s->sample_cap) {
@@ -951,6 +1071,7 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
     B2_CUDA(cudaMemcpyAsync(s->d_rows, srows.data(), srows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(s->d_row_index, row_index.data(), (size_t)sh * sizeof(int), cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+    if ((rc = zerotwo_prepare(s, (long long)srows.size() * sw, st))) return rc;
     float4* d_L = s->d_sample_L;
     float2* d_pf = s->d_sample_pf;
     for (long long first = 0; first < n_samples && !rc; first += s->wave_cap) {
@@ -1068,6 +1189,25 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
     std::lock_guard<std::mutex> g(s->mu);
     B2_CUDA(cudaSetDevice(g_device));
     if (!s->wave_cap && (rc = wave_alloc(s, kWaveCap))) return rc;
+    if (s->dev.sampler_type == B200PT_SAMPLER_ZEROTWO) {  // explicit lists may name any pixel: own every sample row
+        const int* sb = s->sample_bounds;
+        const int sw = sb[2] - sb[0], sh = sb[3] - sb[1];
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t* e = pixel_sample + 3 * i;
+            if (e[0] < sb[0] || e[0] >= sb[2] || e[1] < sb[1] || e[1] >= sb[3] || e[2] < 0 || e[2] >= s->spp) {
+                b200pt_set_error("b200pt_li_batch: (pixel, sample) outside the sample bounds / sample count");
+                return B200PT_ERR_INVALID;
+            }
+        }
+        if (!s->d_rows) {
+            B2_CUDA(cudaMalloc(&s->d_rows, (size_t)sh * sizeof(int)));
+            B2_CUDA(cudaMalloc(&s->d_row_index, (size_t)sh * sizeof(int)));
+        }
+        std::vector<int> ident((size_t)sh);
+        for (int k = 0; k < sh; ++k) ident[(size_t)k] = k;
+        B2_CUDA(cudaMemcpy(s->d_row_index, ident.data(), (size_t)sh * sizeof(int), cudaMemcpyHostToDevice));
+        if ((rc = zerotwo_prepare(s, (long long)sh * sw, 0))) return rc;
+    }
     int* d_list = nullptr;
     float4 *d_L = nullptr, *d_rays = nullptr;
     const int cap = s->wave_cap;
@@ -1078,7 +1218,7 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
     for (int64_t first = 0; first < n && !rc; first += cap) {
         int m = (int)std::min<int64_t>(cap, n - first);
         cudaMemcpy(d_list, pixel_sample + 3 * first, (size_t)m * 3 * sizeof(int), cudaMemcpyHostToDevice);
-        k_raygen<<<(m + 255) / 256, 256>>>(s->dev, s->wave, 0, m, s->sampler.spp, nullptr, d_list, nullptr, d_rays);
+        k_raygen<<<(m + 255) / 256, 256>>>(s->dev, s->wave, 0, m, s->spp, nullptr, d_list, nullptr, d_rays);
         g_launches.fetch_add(1);
         rc = run_wave(s, m, 0);
         if (rc) break;

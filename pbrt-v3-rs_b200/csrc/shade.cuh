@@ -552,6 +552,62 @@ B2_D float halton_dim(const DHalton& h, unsigned long long index, int dim) {
     return scrambled_radical_inverse(h.primes[dim], index, h.perms + h.prime_sums[dim], h.div_m[dim], h.div_sh[dim]);
 }
 
+// ---- sampler: ZeroTwoSequenceSampler (samplers/src/zero_two_sequence.rs, core/src/sampler/pixel_sampler.rs) ------
+// The reference generates, per pixel and per 1-D / 2-D slot, spp gray-code samples of a scrambled van der Corput /
+// Sobol' (0,2) sequence and shuffles them with the TILE's PCG32 stream (low_discrepency.rs:1676-1763).  A prepass
+// (k_zerotwo_tiles, one thread per 16x16 tile, replaying that stream in pixel order) stores per (pixel, slot) the
+// scramble(s) and the shuffle as a source-index permutation; a sample is then scramble ^ G * gray(perm[s]).
+struct DZeroTwo {
+    const uint32_t* scr1;   // [pixel][n1]
+    const uint16_t* perm1;  // [pixel][n1][spp]
+    const uint32_t* scr2;   // [pixel][n2][2]
+    const uint16_t* perm2;  // [pixel][n2][spp]
+    int n1, n2, spp;
+};
+__device__ __constant__ uint32_t kCSobol1[32] = {
+    0x80000000, 0xc0000000, 0xa0000000, 0xf0000000, 0x88000000, 0xcc000000, 0xaa000000, 0xff000000, 0x80800000, 0xc0c00000, 0xa0a00000,
+    0xf0f00000, 0x88880000, 0xcccc0000, 0xaaaa0000, 0xffff0000, 0x80008000, 0xc000c000, 0xa000a000, 0xf000f000, 0x88008800, 0xcc00cc00,
+    0xaa00aa00, 0xff00ff00, 0x80808080, 0xc0c0c0c0, 0xa0a0a0a0, 0xf0f0f0f0, 0x88888888, 0xcccccccc, 0xaaaaaaaa, 0xffffffff};
+B2_D float u32_to_unit(uint32_t v) { return pmin(__uint2float_rn(v) * 0x1.0p-32f, kOneMinusEps); }  // low_discrepency.rs:1603-1607
+// value after i gray-code steps from `scramble`: scramble ^ (G * gray(i))
+B2_D uint32_t gray_vdc(uint32_t i) { return __brev(i ^ (i >> 1)); }  // C_VANDER_CORPUT[b] = 1 << (31 - b)
+B2_D uint32_t gray_sobol1(uint32_t i) {
+    uint32_t g = i ^ (i >> 1), v = 0;
+    while (g) { int b = __ffs(g) - 1; v ^= kCSobol1[b]; g &= g - 1; }
+    return v;
+}
+B2_D float zt_1d(const DZeroTwo& z, long long pix, int slot, int s) {
+    uint32_t scr = z.scr1[pix * z.n1 + slot];
+    uint32_t j = z.perm1[(pix * z.n1 + slot) * z.spp + s];
+    return u32_to_unit(scr ^ gray_vdc(j));
+}
+B2_D P2 zt_2d(const DZeroTwo& z, long long pix, int slot, int s) {
+    const uint32_t* scr = z.scr2 + (pix * z.n2 + slot) * 2;
+    uint32_t j = z.perm2[(pix * z.n2 + slot) * z.spp + s];
+    return mk2(u32_to_unit(scr[0] ^ gray_vdc(j)), u32_to_unit(scr[1] ^ gray_sobol1(j)));
+}
+
+// core/src/rng.rs PCG32 (device copy for the (0,2) prepass)
+struct DPcg32 {
+    unsigned long long state, inc;
+};
+B2_D uint32_t pcg_next(DPcg32& r) {
+    unsigned long long old = r.state;
+    r.state = old * 0x5851f42d4c957f2dULL + r.inc;
+    uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27), rot = (uint32_t)(old >> 59);
+    return (xs >> rot) | (xs << ((~rot + 1u) & 31u));
+}
+B2_D void pcg_set_sequence(DPcg32& r, unsigned long long seq) {  // rng.rs:39-59
+    r.state = 0; r.inc = (seq << 1) | 1ULL;
+    (void)pcg_next(r);
+    r.state += 0x853c49e6748fea9bULL;
+    (void)pcg_next(r);
+}
+B2_D uint32_t pcg_bounded(DPcg32& r, uint32_t b) {  // rng.rs:86-96, lower bound 0
+    uint32_t threshold = (~b + 1u) % b;
+    for (;;) { uint32_t v = pcg_next(r); if (v >= threshold) return v % b; }
+}
+
 // ---- camera: PerspectiveCamera::generate_ray_differential without differentials ------
 struct DCamera {
     float r2c[16], c2w[16];

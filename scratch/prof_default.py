@@ -1,0 +1,15 @@
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+import __graft_entry__ as ge
+import bench
+pkg = ge.load_package(); pkg.init(0)
+w = bench.build_workload(pkg, False, 0)
+accel = w['accel']; n = w['closest'].shape[0]
+d_c = torch.from_numpy(w['closest'].view(np.float32).reshape(-1, 8)).cuda()
+d_s = torch.from_numpy(w['shadow'].view(np.float32).reshape(-1, 8)).cuda()
+d_h = torch.zeros((n, 4), dtype=torch.float32, device='cuda'); d_o = torch.zeros(n, dtype=torch.uint8, device='cuda')
+for _ in range(3):
+    accel.intersect_batch_device(d_c.data_ptr(), n, d_h.data_ptr(), 0, 0)
+    accel.occluded_batch_device(d_s.data_ptr(), n, d_o.data_ptr(), 0, 0)
+torch.cuda.synchronize()
+import os; os._exit(0)

@@ -132,6 +132,24 @@ typedef struct b200pt_integrator {
     int32_t light_strategy;    /* "lightsamplestrategy": uniform | power */
 } b200pt_integrator;
 
+/* ObjectBegin/ObjectEnd: the triangles [first_prim, first_prim + n_prims) of the scene's per-primitive arrays with their
+ * own BVHAccel (nodes / ordered_prims index the object's triangles locally, 0-based) — api/src/lib.rs:952-968. */
+typedef struct b200pt_object {
+    const b200pt_bvh_node* nodes;
+    int64_t n_nodes;
+    const uint32_t* ordered_prims;
+    int64_t first_prim;
+    int64_t n_prims;
+} b200pt_object;
+
+/* ObjectInstance -> TransformedPrimitive with a static transform (core/src/primitives/transformed_primitive.rs:16-73):
+ * primitive_to_world and its inverse, row-major 4x4, affine (last row 0 0 0 1). */
+typedef struct b200pt_instance {
+    int32_t object;
+    float instance_to_world[16];
+    float world_to_instance[16];
+} b200pt_instance;
+
 typedef struct b200pt_scene_desc {
     const b200pt_bvh_node* nodes;
     int64_t n_nodes;
@@ -149,6 +167,14 @@ typedef struct b200pt_scene_desc {
     b200pt_film film;
     b200pt_sampler sampler;
     b200pt_integrator integrator;
+    /* Instancing (optional; n_objects == 0 => every primitive is a top-level triangle).  With objects, the top-level
+     * `nodes` / `ordered_prims` are built over n_top_tris + n_instances primitives: index p < n_top_tris is triangle p,
+     * otherwise instance p - n_top_tris; triangles [n_top_tris, n_prims) belong to the objects. */
+    int64_t n_top_tris;
+    const b200pt_object* objects;
+    int32_t n_objects;
+    const b200pt_instance* instances;
+    int32_t n_instances;
 } b200pt_scene_desc;
 
 typedef struct b200pt_accel b200pt_accel; /* opaque: device-resident BVHAccel */

@@ -452,6 +452,133 @@ inline bool bvh_intersect_p(const Accel& a, const Ray& r, TraversalCounters* ctr
     return false;
 }
 
+// ---------------------------------------------------------------------------
+// Two-level scenes: TransformedPrimitive (core/src/primitives/transformed_primitive.rs:43-73) with a static
+// transform, as created by Api::pbrt_object_instance (api/src/lib.rs:937-987): the object's primitives get their own
+// BVHAccel, the scene aggregate holds one TransformedPrimitive per ObjectInstance among its primitives.
+struct Instance {
+    int object;
+    M4 i2w, w2i;  // primitive_to_world.m and its inverse
+};
+struct TopLevel {
+    Accel top;                 // nodes / ordered over the TOP-LEVEL primitives; verts / flags of ALL triangles (global ids)
+    int64_t n_top_tris = 0;    // top-level primitive p < n_top_tris is triangle p, otherwise instance p - n_top_tris
+    std::vector<Accel> objects;            // per object: own nodes / ordered (local ids) and a copy of its vertices
+    std::vector<int64_t> object_first_prim;  // global id of the object's first triangle
+    std::vector<Instance> instances;
+};
+
+// Transform::transform_bounds, transform.rs:552-561 (TransformedPrimitive::world_bound for a static transform)
+inline Bounds3 xf_bounds(const M4& m, const Bounds3& b) {
+    Bounds3 r(xf_point(m, V3(b.pmin.x, b.pmin.y, b.pmin.z)), xf_point(m, V3(b.pmin.x, b.pmin.y, b.pmin.z)));
+    r = bunion(r, xf_point(m, V3(b.pmax.x, b.pmin.y, b.pmin.z)));
+    r = bunion(r, xf_point(m, V3(b.pmin.x, b.pmax.y, b.pmin.z)));
+    r = bunion(r, xf_point(m, V3(b.pmin.x, b.pmin.y, b.pmax.z)));
+    r = bunion(r, xf_point(m, V3(b.pmin.x, b.pmax.y, b.pmax.z)));
+    r = bunion(r, xf_point(m, V3(b.pmax.x, b.pmax.y, b.pmin.z)));
+    r = bunion(r, xf_point(m, V3(b.pmax.x, b.pmin.y, b.pmax.z)));
+    r = bunion(r, xf_point(m, V3(b.pmax.x, b.pmax.y, b.pmax.z)));
+    return r;
+}
+
+// TransformedPrimitive::intersect, transformed_primitive.rs:51-64: the ray goes to instance space through
+// Transform::transform_ray (origin nudged by its error bound, t_max shortened), the nested aggregate is intersected and
+// the INSTANCE-space t_max is written back to the world ray.  The hit's geometry is transformed by the caller.
+inline bool instance_intersect(const TopLevel& s, int inst, Ray& r, HitRecord* out, TraversalCounters* ctr) {
+    const Instance& I = s.instances[(size_t)inst];
+    Ray ray = xf_ray(I.w2i, r);
+    HitRecord h;
+    if (!bvh_intersect(s.objects[(size_t)I.object], ray, &h, ctr)) return false;
+    r.t_max = ray.t_max;
+    *out = h;
+    out->prim = (uint32_t)(s.object_first_prim[(size_t)I.object] + h.prim);
+    return true;
+}
+inline bool instance_intersect_p(const TopLevel& s, int inst, const Ray& r, TraversalCounters* ctr) {
+    const Instance& I = s.instances[(size_t)inst];
+    Ray ray = xf_ray(I.w2i, r);
+    return bvh_intersect_p(s.objects[(size_t)I.object], ray, ctr);
+}
+
+// BVHAccel::intersect over the scene aggregate whose primitives are triangles and TransformedPrimitives.
+// *inst_out = instance index of the accepted hit, -1 for a top-level triangle.
+inline bool top_intersect(const TopLevel& s, Ray& r, HitRecord* out, int* inst_out, TraversalCounters* ctr = nullptr) {
+    const Accel& a = s.top;
+    bool hit = false;
+    out->prim = 0xffffffffu; out->t = kInfinity; out->second_t = kInfinity;
+    *inst_out = -1;
+    if (a.nodes.empty()) return false;
+    V3 inv_dir(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    int neg[3] = {inv_dir.x < 0.0f ? 1 : 0, inv_dir.y < 0.0f ? 1 : 0, inv_dir.z < 0.0f ? 1 : 0};
+    size_t to_visit = 0, cur = 0;
+    size_t stack[64];
+    for (;;) {
+        const LinearBVHNode& node = a.nodes[cur];
+        if (ctr) ctr->nodes += 1;
+        if (bounds_intersect_p_inv(node.bounds, r, inv_dir, neg)) {
+            if (node.n_primitives > 0) {
+                for (uint32_t i = 0; i < node.n_primitives; ++i) {
+                    uint32_t prim = a.ordered[node.offset + i];
+                    if ((int64_t)prim < s.n_top_tris) {
+                        if (ctr) ctr->tris += 1;
+                        TriHit th;
+                        if (prim_intersect(a, prim, r, &th)) {
+                            hit = true; r.t_max = th.t; *inst_out = -1;
+                            out->t = th.t; out->prim = prim; out->b0 = th.b0; out->b1 = th.b1; out->b2 = th.b2;
+                            out->det = th.det; out->min_e_abs = th.min_e_abs;
+                        }
+                    } else {
+                        int inst = (int)((int64_t)prim - s.n_top_tris);
+                        HitRecord h;
+                        if (instance_intersect(s, inst, r, &h, ctr)) { hit = true; *out = h; *inst_out = inst; }
+                    }
+                }
+                if (to_visit == 0) break;
+                cur = stack[--to_visit];
+            } else {
+                if (neg[node.axis] == 1) { stack[to_visit++] = cur + 1; cur = node.offset; }
+                else { stack[to_visit++] = node.offset; cur = cur + 1; }
+            }
+        } else {
+            if (to_visit == 0) break;
+            cur = stack[--to_visit];
+        }
+    }
+    return hit;
+}
+inline bool top_intersect_p(const TopLevel& s, const Ray& r, TraversalCounters* ctr = nullptr) {
+    const Accel& a = s.top;
+    if (a.nodes.empty()) return false;
+    V3 inv_dir(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    int neg[3] = {inv_dir.x < 0.0f ? 1 : 0, inv_dir.y < 0.0f ? 1 : 0, inv_dir.z < 0.0f ? 1 : 0};
+    size_t to_visit = 0, cur = 0;
+    size_t stack[64];
+    for (;;) {
+        const LinearBVHNode& node = a.nodes[cur];
+        if (ctr) ctr->nodes += 1;
+        if (bounds_intersect_p_inv(node.bounds, r, inv_dir, neg)) {
+            if (node.n_primitives > 0) {
+                for (uint32_t i = 0; i < node.n_primitives; ++i) {
+                    uint32_t prim = a.ordered[node.offset + i];
+                    if ((int64_t)prim < s.n_top_tris) {
+                        if (ctr) ctr->tris += 1;
+                        if (prim_intersect_p(a, prim, r)) return true;
+                    } else if (instance_intersect_p(s, (int)((int64_t)prim - s.n_top_tris), r, ctr)) return true;
+                }
+                if (to_visit == 0) break;
+                cur = stack[--to_visit];
+            } else {
+                if (neg[node.axis] == 1) { stack[to_visit++] = cur + 1; cur = node.offset; }
+                else { stack[to_visit++] = node.offset; cur = cur + 1; }
+            }
+        } else {
+            if (to_visit == 0) break;
+            cur = stack[--to_visit];
+        }
+    }
+    return false;
+}
+
 // Triangle::world_bound, triangle.rs:427-431.
 inline void triangle_world_bound(V3 p0, V3 p1, V3 p2, Float out[6]) {
     Bounds3 b(p0, p0);

@@ -486,6 +486,8 @@ inline Ray spawn_ray_to(V3 p0, V3 e0, V3 n0, V3 p1, V3 e1, V3 n1, Float time) {
 
 struct RenderScene {
     Accel accel;
+    TopLevel top;          // used instead of `accel` for traversal when has_instances
+    bool has_instances = false;
     std::vector<int32_t> prim_material, prim_light;
     std::vector<b200pt_material> materials;
     std::vector<b200pt_light> lights;
@@ -544,11 +546,35 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
     RenderScene* s = new RenderScene();
     s->accel.nodes.resize((size_t)d->n_nodes);
     std::memcpy(s->accel.nodes.data(), d->nodes, (size_t)d->n_nodes * sizeof(LinearBVHNode));
-    s->accel.ordered.assign(d->ordered_prims, d->ordered_prims + d->n_prims);
+    const int64_t n_top = d->n_objects > 0 ? d->n_top_tris + d->n_instances : d->n_prims;  // primitives of the scene aggregate
+    s->accel.ordered.assign(d->ordered_prims, d->ordered_prims + n_top);
     s->accel.verts.assign(d->tri_verts, d->tri_verts + 9 * d->n_prims);
     if (d->prim_flags) s->accel.flags.assign(d->prim_flags, d->prim_flags + d->n_prims);
     if (d->prim_material) s->prim_material.assign(d->prim_material, d->prim_material + d->n_prims);
     if (d->prim_light) s->prim_light.assign(d->prim_light, d->prim_light + d->n_prims);
+    if (d->n_objects > 0) {
+        s->has_instances = true;
+        s->top.top = s->accel;  // top-level nodes / ordered + all vertices and flags (global ids)
+        s->top.n_top_tris = d->n_top_tris;
+        for (int o = 0; o < d->n_objects; ++o) {
+            const b200pt_object& ob = d->objects[o];
+            Accel a;
+            a.nodes.resize((size_t)ob.n_nodes);
+            std::memcpy(a.nodes.data(), ob.nodes, (size_t)ob.n_nodes * sizeof(LinearBVHNode));
+            a.ordered.assign(ob.ordered_prims, ob.ordered_prims + ob.n_prims);
+            a.verts.assign(d->tri_verts + 9 * ob.first_prim, d->tri_verts + 9 * (ob.first_prim + ob.n_prims));
+            if (d->prim_flags) a.flags.assign(d->prim_flags + ob.first_prim, d->prim_flags + ob.first_prim + ob.n_prims);
+            s->top.objects.push_back(a);
+            s->top.object_first_prim.push_back(ob.first_prim);
+        }
+        for (int i = 0; i < d->n_instances; ++i) {
+            Instance I;
+            I.object = d->instances[i].object;
+            I.i2w = m4_from(d->instances[i].instance_to_world);
+            I.w2i = m4_from(d->instances[i].world_to_instance);
+            s->top.instances.push_back(I);
+        }
+    }
     s->materials.assign(d->materials, d->materials + d->n_materials);
     s->lights.assign(d->lights, d->lights + d->n_lights);
     s->camera = d->camera; s->film = d->film; s->sampler = d->sampler; s->integ = d->integrator;
@@ -601,24 +627,73 @@ inline void scene_destroy(RenderScene* s) { delete s; }
 
 // Scene::intersect -> SurfaceInteraction (scene.rs:88-91, triangle.rs:547-629,
 // surface_interaction.rs:56-99, interaction/mod.rs:117-136).
+// Transform::transform_point_with_abs_error, transform.rs:338-368 (affine: wp == 1)
+inline V3 xf_point_abs_err(const M4& M, V3 p, V3 pe, V3* err) {
+    const Float (*m)[4] = M.m;
+    Float x = p.x, y = p.y, z = p.z;
+    Float xp = (m[0][0] * x + m[0][1] * y) + (m[0][2] * z + m[0][3]);
+    Float yp = (m[1][0] * x + m[1][1] * y) + (m[1][2] * z + m[1][3]);
+    Float zp = (m[2][0] * x + m[2][1] * y) + (m[2][2] * z + m[2][3]);
+    Float wp = (m[3][0] * x + m[3][1] * y) + (m[3][2] * z + m[3][3]);
+    Float g3 = gamma(3);
+    *err = V3((g3 + 1.0f) * (pabs(m[0][0]) * pe.x + pabs(m[0][1]) * pe.y + pabs(m[0][2]) * pe.z) +
+                  g3 * (pabs(m[0][0] * x) + pabs(m[0][1] * y) + pabs(m[0][2] * z) + pabs(m[0][3])),
+              (g3 + 1.0f) * (pabs(m[1][0]) * pe.x + pabs(m[1][1]) * pe.y + pabs(m[1][2]) * pe.z) +
+                  g3 * (pabs(m[1][0] * x) + pabs(m[1][1] * y) + pabs(m[1][2] * z) + pabs(m[1][3])),
+              (g3 + 1.0f) * (pabs(m[2][0]) * pe.x + pabs(m[2][1]) * pe.y + pabs(m[2][2]) * pe.z) +
+                  g3 * (pabs(m[2][0] * x) + pabs(m[2][1] * y) + pabs(m[2][2] * z) + pabs(m[2][3])));
+    if (wp == 1.0f) return V3(xp, yp, zp);
+    return V3(xp, yp, zp) / wp;
+}
+// Transform::transform_normal, transform.rs:439-446 (inverse transpose)
+inline V3 xf_normal(const M4& Minv, V3 n) {
+    const Float (*mi)[4] = Minv.m;
+    return V3(mi[0][0] * n.x + mi[1][0] * n.y + mi[2][0] * n.z, mi[0][1] * n.x + mi[1][1] * n.y + mi[2][1] * n.z,
+              mi[0][2] * n.x + mi[1][2] * n.y + mi[2][2] * n.z);
+}
+
 inline bool scene_intersect(RenderScene& sc, Ray& ray, SurfHit* sh) {
     sc.n_closest.fetch_add(1, std::memory_order_relaxed);
     HitRecord h;
     V3 d_in = ray.d;
-    if (!bvh_intersect(sc.accel, ray, &h)) return false;
+    int inst = -1;
+    if (sc.has_instances) { if (!top_intersect(sc.top, ray, &h, &inst)) return false; }
+    else if (!bvh_intersect(sc.accel, ray, &h)) return false;
     V3 p0 = sc.accel.vert(h.prim, 0), p1 = sc.accel.vert(h.prim, 1), p2 = sc.accel.vert(h.prim, 2);
     TriGeom g;
     triangle_geometry(p0, p1, p2, h.b0, h.b1, h.b2, (sc.accel.flag(h.prim) & PRIM_FLIP_NORMAL) != 0, &g);
-    sh->p = g.p; sh->p_error = g.p_error; sh->n = g.n; sh->shading_n = g.n; sh->dpdu = g.dpdu;
-    V3 wo = -d_in;
-    Float l2 = length_squared(wo);
-    sh->wo = (l2 == 0.0f) ? wo : wo / std::sqrt(l2);
     sh->prim = h.prim;
     sh->time = ray.time;
+    if (inst < 0) {
+        sh->p = g.p; sh->p_error = g.p_error; sh->n = g.n; sh->shading_n = g.n; sh->dpdu = g.dpdu;
+        V3 wo = -d_in;
+        Float l2 = length_squared(wo);
+        sh->wo = (l2 == 0.0f) ? wo : wo / std::sqrt(l2);
+        return true;
+    }
+    // Hit built in instance space from the instance-space ray (Hit::new normalises wo), then
+    // Transform::transform_surface_interaction (transform.rs:566-590) with primitive_to_world.
+    const Instance& I = sc.top.instances[(size_t)inst];
+    V3 wo_i = -xf_vector(I.w2i, d_in);
+    Float l2 = length_squared(wo_i);
+    wo_i = (l2 == 0.0f) ? wo_i : wo_i / std::sqrt(l2);
+    bool identity = true;
+    { M4 id; for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) if (I.i2w.m[a][b] != id.m[a][b]) identity = false; }
+    if (identity) {  // transformed_primitive.rs:57-59
+        sh->p = g.p; sh->p_error = g.p_error; sh->n = g.n; sh->shading_n = g.n; sh->dpdu = g.dpdu; sh->wo = wo_i;
+        return true;
+    }
+    sh->p = xf_point_abs_err(I.i2w, g.p, g.p_error, &sh->p_error);
+    sh->wo = normalize(xf_vector(I.i2w, wo_i));
+    sh->n = normalize(xf_normal(I.w2i, g.n));
+    V3 sn = normalize(xf_normal(I.w2i, g.n));
+    sh->shading_n = face_forward(sn, sh->n);
+    sh->dpdu = xf_vector(I.i2w, g.dpdu);
     return true;
 }
 inline bool scene_intersect_p(RenderScene& sc, const Ray& ray) {
     sc.n_shadow.fetch_add(1, std::memory_order_relaxed);
+    if (sc.has_instances) return top_intersect_p(sc.top, ray);
     return bvh_intersect_p(sc.accel, ray);
 }
 

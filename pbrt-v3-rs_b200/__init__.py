@@ -71,11 +71,20 @@ class Integrator(C.Structure):
                 ("light_strategy", C.c_int32)]
 
 
+class Object(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("n_nodes", C.c_int64), ("ordered_prims", C.c_void_p), ("first_prim", C.c_int64), ("n_prims", C.c_int64)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("object", C.c_int32), ("instance_to_world", C.c_float * 16), ("world_to_instance", C.c_float * 16)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("nodes", C.c_void_p), ("n_nodes", C.c_int64), ("ordered_prims", C.c_void_p), ("tri_verts", C.c_void_p),
                 ("prim_flags", C.c_void_p), ("prim_material", C.c_void_p), ("prim_light", C.c_void_p), ("n_prims", C.c_int64),
                 ("materials", C.c_void_p), ("n_materials", C.c_int32), ("lights", C.c_void_p), ("n_lights", C.c_int32),
-                ("camera", Camera), ("film", Film), ("sampler", Sampler), ("integrator", Integrator)]
+                ("camera", Camera), ("film", Film), ("sampler", Sampler), ("integrator", Integrator),
+                ("n_top_tris", C.c_int64), ("objects", C.c_void_p), ("n_objects", C.c_int32), ("instances", C.c_void_p), ("n_instances", C.c_int32)]
 
 
 _lib = None

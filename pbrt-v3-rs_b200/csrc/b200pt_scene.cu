@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "host_sampler.h"
+#include "instancing.cuh"
 #include "shade.cuh"
 
 namespace b2 {
@@ -36,6 +37,7 @@ struct DeviceScene {
     const DLight* lights;
     const int* infinite_lights;
     const DInfDistr* inf_distr;
+    const DInstance* instances;  // null unless the scene has TransformedPrimitives
     const float* light_func;
     const float* light_cdf;
     float light_func_int;
@@ -58,6 +60,7 @@ struct Wave {
     int* qpid[2];
     float4* hit;        // per slot
     float* hit_b2;
+    int* hit_inst;      // instance of the hit (two-level scenes), -1 = top-level triangle
     // shadow / MIS queues
     float4* sh_ray;     // 2 float4 per slot
     uint8_t* sh_occ;
@@ -227,9 +230,40 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
     int mat = 0, alight = -1;
     uint32_t pflags = 0;
     SurfHit sh;
+    // Hit::new normalises wo (interaction/mod.rs:117-136)
+    V3 wo_raw = -ray_d;
+    float l2 = length_squared(wo_raw);
+    V3 hit_wo = (l2 == 0.0f) ? wo_raw : wo_raw / sqrtf(l2);
     if (found) {
         load_prim(S, prim, &p0, &p1, &p2, &mat, &alight, &pflags);
         sh = triangle_surface3(p0, p1, p2, hit.z, hit.w, hb2, (pflags & 1u) != 0);
+        const int inst = S.instances ? W.hit_inst[slot] : -1;
+        if (inst >= 0) {
+            // The hit was built in instance space from the instance-space ray, then
+            // Transform::transform_surface_interaction(primitive_to_world) (transform.rs:566-590).
+            const DInstance I = S.instances[inst];
+            V3 wo_i = -mk(I.w2i[0] * ray_d.x + I.w2i[1] * ray_d.y + I.w2i[2] * ray_d.z, I.w2i[4] * ray_d.x + I.w2i[5] * ray_d.y + I.w2i[6] * ray_d.z,
+                          I.w2i[8] * ray_d.x + I.w2i[9] * ray_d.y + I.w2i[10] * ray_d.z);
+            float li2 = length_squared(wo_i);
+            wo_i = (li2 == 0.0f) ? wo_i : wo_i / sqrtf(li2);
+            if (I.identity) hit_wo = wo_i;
+            else {
+                const float* m = I.i2w;
+                float x = sh.p.x, y = sh.p.y, z = sh.p.z;
+                V3 pe = sh.p_error;
+                V3 pw = mk((m[0] * x + m[1] * y) + (m[2] * z + m[3]), (m[4] * x + m[5] * y) + (m[6] * z + m[7]), (m[8] * x + m[9] * y) + (m[10] * z + m[11]));
+                V3 ew = mk((kGamma3 + 1.0f) * (pabs(m[0]) * pe.x + pabs(m[1]) * pe.y + pabs(m[2]) * pe.z) + kGamma3 * (pabs(m[0] * x) + pabs(m[1] * y) + pabs(m[2] * z) + pabs(m[3])),
+                           (kGamma3 + 1.0f) * (pabs(m[4]) * pe.x + pabs(m[5]) * pe.y + pabs(m[6]) * pe.z) + kGamma3 * (pabs(m[4] * x) + pabs(m[5] * y) + pabs(m[6] * z) + pabs(m[7])),
+                           (kGamma3 + 1.0f) * (pabs(m[8]) * pe.x + pabs(m[9]) * pe.y + pabs(m[10]) * pe.z) + kGamma3 * (pabs(m[8] * x) + pabs(m[9] * y) + pabs(m[10] * z) + pabs(m[11])));
+                sh.p = pw; sh.p_error = ew;
+                hit_wo = normalize(mk(m[0] * wo_i.x + m[1] * wo_i.y + m[2] * wo_i.z, m[4] * wo_i.x + m[5] * wo_i.y + m[6] * wo_i.z, m[8] * wo_i.x + m[9] * wo_i.y + m[10] * wo_i.z));
+                const float* mi = I.w2i;  // transform_normal: inverse transpose (transform.rs:439-446)
+                V3 n = sh.n;
+                sh.n = normalize(mk(mi[0] * n.x + mi[4] * n.y + mi[8] * n.z, mi[1] * n.x + mi[5] * n.y + mi[9] * n.z, mi[2] * n.x + mi[6] * n.y + mi[10] * n.z));
+                V3 du = sh.dpdu;
+                sh.dpdu = mk(m[0] * du.x + m[1] * du.y + m[2] * du.z, m[4] * du.x + m[5] * du.y + m[6] * du.z, m[8] * du.x + m[9] * du.y + m[10] * du.z);
+            }
+        }
     }
     // path.rs:123-134: emitted light at the vertex / from the environment
     if (bounces == 0 || specular_bounce) {
@@ -243,10 +277,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
         W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
         return;
     }
-    // Hit::new normalises wo (interaction/mod.rs:117-136); BSDF::new frame (bsdf.rs:100-120)
-    V3 wo_raw = -ray_d;
-    float l2 = length_squared(wo_raw);
-    V3 hit_wo = (l2 == 0.0f) ? wo_raw : wo_raw / sqrtf(l2);
+    // BSDF::new frame (bsdf.rs:100-120)
     BSDF bsdf;
     bsdf.ns = sh.n; bsdf.ng = sh.n;
     bsdf.ss = normalize(sh.dpdu);
@@ -595,6 +626,8 @@ __global__ void __launch_bounds__(128) k_film(DFilm F, const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 struct SceneImpl {
     AccelImpl accel;
+    Accel2Impl accel2;        // two-level scenes (instancing)
+    bool instanced = false;
     DeviceScene dev;
     b200pt_film film;
     b200pt_sampler sampler;
@@ -762,6 +795,7 @@ static int wave_alloc(SceneImpl* s, int cap) {
     int rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.hit))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.hit_b2))) return rc;
+    if ((rc = dev_alloc(s, (size_t)cap, &W.hit_inst))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap * 2, &W.sh_ray))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.sh_occ))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap * 2, &W.mis_ray))) return rc;
@@ -788,7 +822,8 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
     int cur = 0, n_active = n;
     s->rays[0] += (uint64_t)n;
     for (int iter = 0; n_active > 0 && iter <= s->dev.max_depth + 1; ++iter) {
-        int rc = launch_intersect(s->dev.accel, W.ray[cur], n_active, W.hit, st, 0, W.hit_b2);
+        int rc = s->instanced ? launch_intersect2(s->accel2.dev, W.ray[cur], n_active, W.hit, st, W.hit_b2, W.hit_inst)
+                              : launch_intersect(s->dev.accel, W.ray[cur], n_active, W.hit, st, 0, W.hit_b2);
         if (rc) return rc;
         s->rays[1] += (uint64_t)n_active;
         B2_CUDA(cudaMemsetAsync(W.counters, 0, 32 * sizeof(int), st));
@@ -800,8 +835,17 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
         int cnt[4];
         B2_CUDA(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         B2_CUDA(cudaStreamSynchronize(st));
-        if (cnt[1] > 0) { rc = launch_occluded(s->dev.accel, W.sh_ray, cnt[1], W.sh_occ, st, 0); if (rc) return rc; s->rays[2] += (uint64_t)cnt[1]; }
-        if (cnt[2] > 0) { rc = launch_intersect(s->dev.accel, W.mis_ray, cnt[2], W.mis_hit, st, 0, nullptr); if (rc) return rc; s->rays[1] += (uint64_t)cnt[2]; }
+        if (cnt[1] > 0) {
+            rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, cnt[1], W.sh_occ, st) : launch_occluded(s->dev.accel, W.sh_ray, cnt[1], W.sh_occ, st, 0);
+            if (rc) return rc;
+            s->rays[2] += (uint64_t)cnt[1];
+        }
+        if (cnt[2] > 0) {
+            rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, cnt[2], W.mis_hit, st, nullptr, nullptr)
+                              : launch_intersect(s->dev.accel, W.mis_ray, cnt[2], W.mis_hit, st, 0, nullptr);
+            if (rc) return rc;
+            s->rays[1] += (uint64_t)cnt[2];
+        }
         if (cnt[3] > 0) { k_resolve<<<(cnt[3] + 255) / 256, 256, 0, st>>>(s->dev, W, cnt[3]); g_launches.fetch_add(1); }
         cur ^= 1;
         n_active = cnt[0];
@@ -852,11 +896,25 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     b200pt_scene* sc = new b200pt_scene();
     SceneImpl* s = &sc->impl;
     auto fail = [&](int code) { b200pt_scene_destroy(sc); return code; };
-    rc = accel_build_device(d->nodes, d->n_nodes, d->ordered_prims, d->tri_verts, d->prim_flags, d->n_prims, &s->accel);
-    if (rc) return fail(rc);
     DeviceScene& D = s->dev;
     std::memset(&D, 0, sizeof(D));
-    D.accel = s->accel.dev;
+    if (d->n_objects > 0) {
+        if (!d->objects || (d->n_instances > 0 && !d->instances) || d->n_top_tris < 0 || d->n_top_tris > d->n_prims) {
+            b200pt_set_error("b200pt_scene_create: invalid instancing description");
+            return fail(B200PT_ERR_INVALID);
+        }
+        for (int64_t i = d->n_top_tris; i < d->n_prims; ++i)
+            if (d->prim_light && d->prim_light[i] >= 0) { b200pt_set_error("b200pt_scene_create: area lights inside object instances are not supported (as in pbrt)"); return fail(B200PT_ERR_UNSUPPORTED); }
+        rc = accel2_build_device(d, &s->accel2);
+        if (rc) return fail(rc);
+        s->instanced = true;
+        D.accel = s->accel2.dev.top;
+        D.instances = s->accel2.dev.instances;
+    } else {
+        rc = accel_build_device(d->nodes, d->n_nodes, d->ordered_prims, d->tri_verts, d->prim_flags, d->n_prims, &s->accel);
+        if (rc) return fail(rc);
+        D.accel = s->accel.dev;
+    }
     s->film = d->film;
     s->sampler = d->sampler;
     s->spp = d->sampler.spp;
@@ -1005,6 +1063,7 @@ void b200pt_scene_destroy(b200pt_scene* sc) {
     if (sc->impl.d_rows) cudaFree(sc->impl.d_rows);
     if (sc->impl.d_row_index) cudaFree(sc->impl.d_row_index);
     accel_free_device(&sc->impl.accel);
+    accel2_free_device(&sc->impl.accel2);
     delete sc;
 }
 

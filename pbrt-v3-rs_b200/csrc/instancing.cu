@@ -1,0 +1,300 @@
+// Two-level traversal: TransformedPrimitive (core/src/primitives/transformed_primitive.rs:43-73) with a static
+// transform among the primitives of the scene aggregate, each referring to an object's own BVHAccel
+// (api/src/lib.rs:937-987).  Config C5 (ecosys-style instancing).
+//
+// Device layout: ONE wide-node array and ONE 64-byte record array hold the top-level BVH followed by every object's
+// BVH with global indices, so the single-level walk (traverse_wide) is reused unchanged for the nested call.  A
+// top-level leaf record is either a triangle or — flag bit 31 — an instance (id in the primitive field).
+// TransformedPrimitive::intersect semantics kept: the ray is taken to instance space by Transform::transform_ray
+// (origin nudged by its error bound, t_max shortened by the same dt, transform.rs:451-476), the nested aggregate is
+// intersected, and the INSTANCE-space t_max is written back to the world ray (transformed_primitive.rs:52-56).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "instancing.cuh"
+
+namespace b2 {
+
+// Transform::transform_ray for an affine matrix (rows 0..2), transform.rs:307-331, 373-380, 451-476
+B2_D Ray32 xf_ray_affine(const float* m, const Ray32& r) {
+    float x = r.ox, y = r.oy, z = r.oz;
+    float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
+    float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
+    float zp = (m[8] * x + m[9] * y) + (m[10] * z + m[11]);
+    float xs = pabs(m[0] * x) + pabs(m[1] * y) + pabs(m[2] * z) + pabs(m[3]);
+    float ys = pabs(m[4] * x) + pabs(m[5] * y) + pabs(m[6] * z) + pabs(m[7]);
+    float zs = pabs(m[8] * x) + pabs(m[9] * y) + pabs(m[10] * z) + pabs(m[11]);
+    V3 o_err = kGamma3 * mk(xs, ys, zs);
+    V3 o = mk(xp, yp, zp);
+    V3 d = mk(m[0] * r.dx + m[1] * r.dy + m[2] * r.dz, m[4] * r.dx + m[5] * r.dy + m[6] * r.dz, m[8] * r.dx + m[9] * r.dy + m[10] * r.dz);
+    float l2 = length_squared(d);
+    float t_max = r.tmax;
+    if (l2 > 0.0f) {
+        float dt = dot(vabs(d), o_err) / l2;
+        o = o + d * dt;
+        t_max -= dt;
+    }
+    Ray32 q;
+    q.ox = o.x; q.oy = o.y; q.oz = o.z; q.tmax = t_max; q.dx = d.x; q.dy = d.y; q.dz = d.z; q.time = r.time;
+    return q;
+}
+
+// BVHAccel::intersect / intersect_p over the scene aggregate (same walk as traverse_wide; leaves may hold instances).
+template <bool ANY>
+B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, int* inst_out) {
+    const DeviceAccel& A = A2.top;
+    out->t = __int_as_float(0x7f800000);
+    out->prim = 0xffffffffu;
+    out->b0 = 0.0f; out->b1 = 0.0f; out->b2 = 0.0f;
+    *inst_out = -1;
+    if (A.root_code == B2_EMPTY_ROOT) return false;
+    RayCtx r;
+    r.ox = ray.ox; r.oy = ray.oy; r.oz = ray.oz;
+    r.ix = 1.0f / ray.dx; r.iy = 1.0f / ray.dy; r.iz = 1.0f / ray.dz;
+    r.nx = r.ix < 0.0f; r.ny = r.iy < 0.0f; r.nz = r.iz < 0.0f;
+    float t_max = ray.tmax;
+    float te;
+    if (!(slab(r, A.root_bounds[0], A.root_bounds[1], A.root_bounds[2], A.root_bounds[3], A.root_bounds[4], A.root_bounds[5], &te) && te < t_max)) return false;
+    const TriCtx tc = make_tri_ctx(ray.dx, ray.dy, ray.dz);
+    const V3 o = mk(ray.ox, ray.oy, ray.oz);
+    int stack_code[B2_STACK];
+    float stack_t[B2_STACK];
+    int sp = 0, cur = A.root_code;
+    bool hit = false;
+    for (;;) {
+        if (cur >= 0) {
+            const float4* q = A.wide + 4ll * cur;
+            float4 q0, q1, q2, q3;
+            ldg8(q, &q0, &q1);
+            ldg8(q + 2, &q2, &q3);
+            float t0, t1;
+            bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0) && t0 < t_max;
+            bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1) && t1 < t_max;
+            int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y), axis = __float_as_int(q3.z);
+            int neg = axis == 0 ? r.nx : (axis == 1 ? r.ny : r.nz);
+            int near_c = neg ? c1 : c0, far_c = neg ? c0 : c1;
+            bool near_h = neg ? h1 : h0, far_h = neg ? h0 : h1;
+            float far_t = neg ? t0 : t1;
+            if (near_h) {
+                if (far_h) { stack_code[sp] = far_c; stack_t[sp] = far_t; ++sp; }
+                cur = near_c;
+                continue;
+            }
+            if (far_h) { cur = far_c; continue; }
+        } else {
+            long long first = (long long)(~cur);
+            V3 p0, p1, p2;
+            uint32_t prim, flags, leaf_n;
+            load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n);
+            for (uint32_t i = 0;;) {
+                if (flags & 0x80000000u) {  // TransformedPrimitive
+                    const DInstance I = A2.instances[prim];
+                    Ray32 wr = ray;
+                    wr.tmax = t_max;
+                    Ray32 ir = xf_ray_affine(I.w2i, wr);
+                    const DObject ob = A2.objects[I.object];
+                    DeviceAccel oa = A;
+                    oa.root_code = ob.root_code;
+                    for (int k = 0; k < 6; ++k) oa.root_bounds[k] = ob.root_bounds[k];
+                    HitOut h2;
+                    if (traverse_wide<ANY>(oa, ir, &h2)) {
+                        if (ANY) return true;
+                        hit = true;
+                        t_max = h2.t;  // r.t_max = ray.t_max (instance-space value), transformed_primitive.rs:55
+                        *out = h2;
+                        *inst_out = (int)prim;
+                    }
+                } else {
+                    float t, b0, b1, b2;
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2)) {
+                        if (ANY) {
+                            if (!(flags & 6u)) return true;
+                        } else if (!(flags & 2u)) {
+                            hit = true;
+                            t_max = t;
+                            out->t = t; out->prim = prim; out->b0 = b0; out->b1 = b1; out->b2 = b2;
+                            *inst_out = -1;
+                        }
+                    }
+                }
+                if (++i >= leaf_n) break;
+                uint32_t dummy;
+                load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy);
+            }
+        }
+        for (;;) {
+            if (sp == 0) return hit;
+            --sp;
+            cur = stack_code[sp];
+            if (ANY || stack_t[sp] < t_max) break;
+        }
+    }
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_trace_twolevel(DeviceAccel2 A, const float4* __restrict__ rays, long long n, void* __restrict__ out,
+                                                        float* __restrict__ b2_out, int* __restrict__ inst_out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 r0 = __ldg(rays + 2 * i), r1 = __ldg(rays + 2 * i + 1);
+    Ray32 ray{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    HitOut h;
+    int inst;
+    bool hit = traverse_top<ANY>(A, ray, &h, &inst);
+    if (ANY) ((uint8_t*)out)[i] = hit ? 1 : 0;
+    else {
+        ((float4*)out)[i] = make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1);
+        if (b2_out) b2_out[i] = h.b2;
+        if (inst_out) inst_out[i] = inst;
+    }
+}
+
+int launch_intersect2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, float* d_b2, int* d_inst) {
+    if (n <= 0) return B200PT_OK;
+    k_trace_twolevel<false><<<(int)((n + 127) / 128), 128, 0, s>>>(A, (const float4*)d_rays, n, d_hits, d_b2, d_inst);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200PT_OK : cuda_fail(e, "k_trace_twolevel launch");
+}
+int launch_occluded2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s) {
+    if (n <= 0) return B200PT_OK;
+    k_trace_twolevel<true><<<(int)((n + 127) / 128), 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, nullptr, nullptr);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200PT_OK : cuda_fail(e, "k_trace_twolevel launch");
+}
+
+// Appends one BVH (wide nodes + leaf records) to the shared arrays; returns its root code.
+template <class RecordFn>
+static int append_bvh(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered, int64_t n_ordered, RecordFn record,
+                      std::vector<float4>& wide, std::vector<float4>& recs, int* root_code) {
+    const int64_t wbase = (int64_t)wide.size() / 4, rbase = (int64_t)recs.size() / 4;
+    std::vector<int32_t> wide_of((size_t)n_nodes, -1);
+    int64_t n_wide = 0;
+    for (int64_t i = 0; i < n_nodes; ++i)
+        if (nodes[i].n_primitives == 0) wide_of[(size_t)i] = (int32_t)(wbase + n_wide++);
+    auto code_of = [&](int64_t i) -> int32_t { return nodes[i].n_primitives == 0 ? wide_of[(size_t)i] : ~(int32_t)(rbase + nodes[i].offset); };
+    wide.resize((size_t)(wbase + n_wide) * 4);
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        if (nodes[i].n_primitives != 0) continue;
+        int64_t c0 = i + 1, c1 = nodes[i].offset;
+        if (c1 <= i || c1 >= n_nodes || c0 >= n_nodes) { b200pt_set_error("b200pt_scene_create: malformed node array"); return B200PT_ERR_INVALID; }
+        const float* a0 = nodes[c0].bounds;
+        const float* a1 = nodes[c1].bounds;
+        float4* q = &wide[(size_t)wide_of[(size_t)i] * 4];
+        q[0] = make_float4(a0[0], a0[1], a0[2], a0[3]);
+        q[1] = make_float4(a0[4], a0[5], a1[0], a1[1]);
+        q[2] = make_float4(a1[2], a1[3], a1[4], a1[5]);
+        int32_t k0 = code_of(c0), k1 = code_of(c1), ax = nodes[i].axis;
+        float f0, f1, f2;
+        std::memcpy(&f0, &k0, 4); std::memcpy(&f1, &k1, 4); std::memcpy(&f2, &ax, 4);
+        q[3] = make_float4(f0, f1, f2, 0.0f);
+    }
+    recs.resize((size_t)(rbase + n_ordered) * 4);
+    for (int64_t j = 0; j < n_ordered; ++j) {
+        int rc = record(ordered[j], &recs[(size_t)(rbase + j) * 4]);
+        if (rc) return rc;
+    }
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        if (nodes[i].n_primitives == 0) continue;
+        uint32_t cnt = nodes[i].n_primitives;
+        if ((int64_t)nodes[i].offset + cnt > n_ordered) { b200pt_set_error("b200pt_scene_create: leaf range out of bounds"); return B200PT_ERR_INVALID; }
+        float fc;
+        std::memcpy(&fc, &cnt, 4);
+        recs[(size_t)(rbase + nodes[i].offset) * 4 + 2].w = fc;
+    }
+    *root_code = n_nodes > 0 ? code_of(0) : B2_EMPTY_ROOT;
+    return B200PT_OK;
+}
+
+int accel2_build_device(const b200pt_scene_desc* d, Accel2Impl* a) {
+    std::vector<float4> wide, recs;
+    auto tri_record = [&](int64_t gp, float4* q) {
+        const float* v = d->tri_verts + 9 * (size_t)gp;
+        uint32_t p = (uint32_t)gp, fl = d->prim_flags ? d->prim_flags[gp] & 0x7fffffffu : 0u, zero = 0u;
+        float fp, ff, fz;
+        std::memcpy(&fp, &p, 4); std::memcpy(&ff, &fl, 4); std::memcpy(&fz, &zero, 4);
+        q[0] = make_float4(v[0], v[1], v[2], v[3]);
+        q[1] = make_float4(v[4], v[5], v[6], v[7]);
+        q[2] = make_float4(v[8], fp, ff, fz);
+        q[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    };
+    const int64_t n_top = d->n_top_tris + d->n_instances;
+    std::memset(&a->dev, 0, sizeof(a->dev));
+    int root = B2_EMPTY_ROOT;
+    int rc = append_bvh(d->nodes, d->n_nodes, d->ordered_prims, n_top, [&](uint32_t p, float4* q) -> int {
+        if ((int64_t)p < d->n_top_tris) { tri_record(p, q); return 0; }
+        int64_t inst = (int64_t)p - d->n_top_tris;
+        if (inst >= d->n_instances) { b200pt_set_error("b200pt_scene_create: top-level primitive index out of range"); return B200PT_ERR_INVALID; }
+        uint32_t id = (uint32_t)inst, fl = 0x80000000u, zero = 0u;
+        float fp, ff, fz;
+        std::memcpy(&fp, &id, 4); std::memcpy(&ff, &fl, 4); std::memcpy(&fz, &zero, 4);
+        q[0] = q[1] = q[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        q[2] = make_float4(0.0f, fp, ff, fz);
+        return 0;
+    }, wide, recs, &root);
+    if (rc) return rc;
+    a->dev.top.root_code = root;
+    if (d->n_nodes > 0) std::memcpy(a->dev.top.root_bounds, d->nodes[0].bounds, 24);
+    a->dev.top.n_nodes = (int)d->n_nodes;
+    a->dev.top.n_prims = d->n_prims;
+    std::vector<DObject> objs((size_t)d->n_objects);
+    for (int o = 0; o < d->n_objects; ++o) {
+        const b200pt_object& ob = d->objects[o];
+        if (ob.n_nodes < 1 || ob.first_prim < d->n_top_tris || ob.first_prim + ob.n_prims > d->n_prims) {
+            b200pt_set_error("b200pt_scene_create: object without a BVH or with a primitive range outside [n_top_tris, n_prims)");
+            return B200PT_ERR_INVALID;
+        }
+        int oroot;
+        rc = append_bvh(ob.nodes, ob.n_nodes, ob.ordered_prims, ob.n_prims, [&](uint32_t p, float4* q) -> int {
+            if ((int64_t)p >= ob.n_prims) { b200pt_set_error("b200pt_scene_create: object ordered_prims index out of range"); return B200PT_ERR_INVALID; }
+            tri_record(ob.first_prim + p, q);
+            return 0;
+        }, wide, recs, &oroot);
+        if (rc) return rc;
+        objs[(size_t)o].root_code = oroot;
+        std::memcpy(objs[(size_t)o].root_bounds, ob.nodes[0].bounds, 24);
+    }
+    std::vector<DInstance> insts((size_t)d->n_instances);
+    for (int i = 0; i < d->n_instances; ++i) {
+        const b200pt_instance& in = d->instances[i];
+        const float* w = in.world_to_instance;
+        const float* m = in.instance_to_world;
+        if (in.object < 0 || in.object >= d->n_objects || w[12] != 0.0f || w[13] != 0.0f || w[14] != 0.0f || w[15] != 1.0f || m[12] != 0.0f || m[13] != 0.0f ||
+            m[14] != 0.0f || m[15] != 1.0f) {
+            b200pt_set_error("b200pt_scene_create: instance with a bad object index or a non-affine transform");
+            return B200PT_ERR_UNSUPPORTED;
+        }
+        DInstance& I = insts[(size_t)i];
+        std::memcpy(I.w2i, w, 48);
+        std::memcpy(I.i2w, m, 48);
+        I.object = in.object;
+        bool ident = true;
+        for (int k = 0; k < 16; ++k) if (m[k] != ((k % 5 == 0) ? 1.0f : 0.0f)) ident = false;
+        I.identity = ident ? 1 : 0;  // Transform::is_identity, transformed_primitive.rs:57
+    }
+    B2_CUDA(cudaMalloc(&a->d_wide, std::max<size_t>(wide.size(), 4) * sizeof(float4)));
+    B2_CUDA(cudaMalloc(&a->d_recs, std::max<size_t>(recs.size(), 4) * sizeof(float4)));
+    B2_CUDA(cudaMalloc(&a->d_objs, std::max<size_t>(objs.size(), 1) * sizeof(DObject)));
+    B2_CUDA(cudaMalloc(&a->d_insts, std::max<size_t>(insts.size(), 1) * sizeof(DInstance)));
+    if (!wide.empty()) B2_CUDA(cudaMemcpy(a->d_wide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    if (!recs.empty()) B2_CUDA(cudaMemcpy(a->d_recs, recs.data(), recs.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    if (!objs.empty()) B2_CUDA(cudaMemcpy(a->d_objs, objs.data(), objs.size() * sizeof(DObject), cudaMemcpyHostToDevice));
+    if (!insts.empty()) B2_CUDA(cudaMemcpy(a->d_insts, insts.data(), insts.size() * sizeof(DInstance), cudaMemcpyHostToDevice));
+    a->dev.top.wide = a->d_wide;
+    a->dev.top.tris = a->d_recs;
+    a->dev.top.ref_nodes = nullptr;
+    a->dev.objects = a->d_objs;
+    a->dev.instances = a->d_insts;
+    return B200PT_OK;
+}
+
+void accel2_free_device(Accel2Impl* a) {
+    for (void* p : {(void*)a->d_wide, (void*)a->d_recs, (void*)a->d_objs, (void*)a->d_insts})
+        if (p) cudaFree(p);
+    a->d_wide = a->d_recs = nullptr; a->d_objs = nullptr; a->d_insts = nullptr;
+}
+
+}  // namespace b2

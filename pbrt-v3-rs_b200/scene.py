@@ -144,6 +144,8 @@ class SceneDescription:
         self.accel_params = dict(splitmethod="sah", maxnodeprims=4)
         self.nodes = None
         self.ordered_prims = None
+        self.objects = []     # dicts: tri_verts, material, flags, nodes, ordered
+        self.instances = []   # (object id, instance_to_world, world_to_instance)
         self._keep = []
 
     # -- scene assembly, mirroring Api::pbrt_shape / pbrt_light_source (api/src/lib.rs:751-811) --
@@ -177,10 +179,36 @@ class SceneDescription:
         self.lights.append(dict(type="infinite", L=tuple(L)))
 
     # -- flattening --
+    # -- instancing: ObjectBegin/ObjectEnd + ObjectInstance (api/src/lib.rs:880-987) --
+    def add_object(self, tri_verts, material, reverse_orientation=False):
+        """Defines a named object (its triangles get their own BVHAccel); returns the object id."""
+        tv = np.ascontiguousarray(tri_verts, dtype=F32).reshape(-1, 9)
+        self.objects.append(dict(tri_verts=tv, material=material, flags=1 if reverse_orientation else 0, nodes=None, ordered=None))
+        return len(self.objects) - 1
+
+    def add_instance(self, obj, instance_to_world):
+        """ObjectInstance: a TransformedPrimitive with a static, affine instance-to-world matrix (4x4, row-major)."""
+        m = np.asarray(instance_to_world, dtype=F32).reshape(4, 4)
+        self.instances.append((obj, m, _m4_inverse(m)))
+
     def build_accel(self, builder):
-        """builder(prim_bounds, max_prims) -> (nodes, ordered).  Uses the product's host SAH builder by default."""
+        """builder(prim_bounds, max_prims) -> (nodes, ordered).  Uses the product's host SAH builder by default.
+        With objects, every object gets its own BVH and the scene aggregate is built over the top-level triangles
+        followed by one primitive per instance (TransformedPrimitive::world_bound = transform_bounds of the object's root)."""
         from . import build_bvh_sah, triangle_bounds  # noqa
-        self.nodes, self.ordered_prims = (builder or build_bvh_sah)(triangle_bounds(self.tri_verts), self.accel_params["maxnodeprims"])
+        builder = builder or build_bvh_sah
+        mp = self.accel_params["maxnodeprims"]
+        bounds = triangle_bounds(self.tri_verts)
+        for o in self.objects:
+            o["nodes"], o["ordered"] = builder(triangle_bounds(o["tri_verts"]), mp)
+        ib = np.zeros((len(self.instances), 6), dtype=F32)
+        for k, (obj, m, _) in enumerate(self.instances):
+            b = self.objects[obj]["nodes"][0]["bounds"]
+            corners = [(b[0], b[1], b[2]), (b[3], b[1], b[2]), (b[0], b[4], b[2]), (b[0], b[1], b[5]), (b[0], b[4], b[5]), (b[3], b[4], b[2]),
+                       (b[3], b[1], b[5]), (b[3], b[4], b[5])]  # Transform::transform_bounds order, transform.rs:552-561
+            pts = np.array([[F32(F32(F32(m[r, 0] * c[0]) + F32(m[r, 1] * c[1])) + F32(m[r, 2] * c[2])) + m[r, 3] for r in range(3)] for c in corners], dtype=F32)
+            ib[k, :3], ib[k, 3:] = pts.min(0), pts.max(0)
+        self.nodes, self.ordered_prims = builder(np.concatenate([bounds, ib]) if len(ib) else bounds, mp)
 
     def sample_bounds(self):
         xres, yres = self.film["xresolution"], self.film["yresolution"]
@@ -201,13 +229,38 @@ class SceneDescription:
             keep.append(a)
             return a.ctypes.data_as(C.c_void_p)
 
+        from . import Instance, Object
+        tv, pf, pm, pl = [self.tri_verts], [self.prim_flags], [self.prim_material], [self.prim_light]
+        n_top = self.tri_verts.shape[0]
+        objs = (Object * max(1, len(self.objects)))()
+        first = n_top
+        for k, o in enumerate(self.objects):
+            n = o["tri_verts"].shape[0]
+            tv.append(o["tri_verts"])
+            pf.append(np.full(n, o["flags"], dtype=np.uint32))
+            pm.append(np.full(n, o["material"], dtype=np.int32))
+            pl.append(np.full(n, -1, dtype=np.int32))  # no area lights inside object instances (as in pbrt)
+            objs[k].nodes, objs[k].n_nodes = arr(o["nodes"], o["nodes"].dtype), len(o["nodes"])
+            objs[k].ordered_prims = arr(o["ordered"], np.uint32)
+            objs[k].first_prim, objs[k].n_prims = first, n
+            first += n
+        insts = (Instance * max(1, len(self.instances)))()
+        for k, (obj, m, minv) in enumerate(self.instances):
+            insts[k].object = obj
+            insts[k].instance_to_world[:] = m.reshape(-1)
+            insts[k].world_to_instance[:] = minv.reshape(-1)
+        keep.extend([objs, insts])
         d.nodes, d.n_nodes = arr(self.nodes, self.nodes.dtype), len(self.nodes)
         d.ordered_prims = arr(self.ordered_prims, np.uint32)
-        d.tri_verts = arr(self.tri_verts, F32)
-        d.prim_flags = arr(self.prim_flags, np.uint32)
-        d.prim_material = arr(self.prim_material, np.int32)
-        d.prim_light = arr(self.prim_light, np.int32)
-        d.n_prims = self.tri_verts.shape[0]
+        all_tv = np.concatenate(tv)
+        d.tri_verts = arr(all_tv, F32)
+        d.prim_flags = arr(np.concatenate(pf), np.uint32)
+        d.prim_material = arr(np.concatenate(pm), np.int32)
+        d.prim_light = arr(np.concatenate(pl), np.int32)
+        d.n_prims = all_tv.shape[0]
+        d.n_top_tris = n_top
+        d.objects, d.n_objects = C.cast(objs, C.c_void_p), len(self.objects)
+        d.instances, d.n_instances = C.cast(insts, C.c_void_p), len(self.instances)
 
         mats = (Material * max(1, len(self.materials)))()
         for i, m in enumerate(self.materials):

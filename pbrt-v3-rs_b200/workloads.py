@@ -241,3 +241,35 @@ def scene_c3(nu=330, nv=330, xres=1920, yres=1080, spp=64, maxdepth=8):
     sd.sampler.update(type="halton", pixelsamples=spp)
     sd.integrator.update(maxdepth=maxdepth, lightsamplestrategy="power")
     return sd
+
+
+def rigid_transform(rng, scale_range=(0.7, 1.3), extent=8.0, y_range=(-0.9, 1.5)):
+    """Random rotation about a random axis, uniform scale and translation (instance_to_world, 4x4 row-major f32)."""
+    axis = rng.normal(size=3)
+    axis /= np.linalg.norm(axis)
+    ang = rng.uniform(0, 2 * np.pi)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+    M = np.eye(4, dtype=F32)
+    M[:3, :3] = (rng.uniform(*scale_range) * R).astype(F32)
+    M[:3, 3] = [rng.uniform(-extent, extent), rng.uniform(*y_range), rng.uniform(-extent, extent)]
+    return M
+
+
+def scene_c5(nu=224, nv=224, n_instances=1000, xres=1920, yres=1080, spp=128, maxdepth=5, seed=4):
+    """C5: ecosys-style instancing — one displaced-sphere object (2*nu*nv ~ 100 K triangles) placed n_instances times
+    with random rigid transforms (two-level BVH), a ground quad, constant infinite light L=[1 1 1]."""
+    sd = SceneDescription()
+    m = sd.add_material(type="matte", Kd=(0.45, 0.5, 0.35))
+    g = sd.add_material(type="matte", Kd=(0.4, 0.4, 0.4))
+    sd.add_mesh(ground_quad(y=-1.3, half=14.0), g)
+    obj = sd.add_object(displaced_sphere(nu, nv, radius=0.35), m)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    for _ in range(n_instances):
+        sd.add_instance(obj, rigid_transform(rng))
+    sd.add_infinite_light((1.0, 1.0, 1.0))
+    sd.camera.update(eye=(0.0, 4.0, -13.0), look=(0.0, 0.0, 0.0), up=(0, 1, 0), fov=38.0)
+    sd.film.update(xresolution=xres, yresolution=yres, filter="box")
+    sd.sampler.update(type="halton", pixelsamples=spp)
+    sd.integrator.update(maxdepth=maxdepth, lightsamplestrategy="uniform")
+    return sd

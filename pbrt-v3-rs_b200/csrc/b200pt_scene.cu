@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
                 V3 ew = mk((kGamma3 + 1.0f) * (pabs(m[0]) * pe.x + pabs(m[1]) * pe.y + pabs(m[2]) * pe.z) + kGamma3 * (pabs(m[0] * x) + pabs(m[1] * y) + pabs(m[2] * z) + pabs(m[3])),
                            (kGamma3 + 1.0f) * (pabs(m[4]) * pe.x + pabs(m[5]) * pe.y + pabs(m[6]) * pe.z) + kGamma3 * (pabs(m[4] * x) + pabs(m[5] * y) + pabs(m[6] * z) + pabs(m[7])),
                            (kGamma3 + 1.0f) * (pabs(m[8]) * pe.x + pabs(m[9]) * pe.y + pabs(m[10]) * pe.z) + kGamma3 * (pabs(m[8] * x) + pabs(m[9] * y) + pabs(m[10] * z) + pabs(m[11])));
+                const float wp = (m[12] * x + m[13] * y) + (m[14] * z + m[15]);  // transform.rs:338-368
+                if (!(wp == 1.0f)) pw = pw / wp;
                 sh.p = pw; sh.p_error = ew;
                 hit_wo = normalize(mk(m[0] * wo_i.x + m[1] * wo_i.y + m[2] * wo_i.z, m[4] * wo_i.x + m[5] * wo_i.y + m[6] * wo_i.z, m[8] * wo_i.x + m[9] * wo_i.y + m[10] * wo_i.z));
                 const float* mi = I.w2i;  // transform_normal: inverse transpose (transform.rs:439-446)

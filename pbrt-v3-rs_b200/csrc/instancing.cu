@@ -9,6 +9,7 @@
 // (origin nudged by its error bound, t_max shortened by the same dt, transform.rs:451-476), the nested aggregate is
 // intersected, and the INSTANCE-space t_max is written back to the world ray (transformed_primitive.rs:52-56).
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <vector>
 
@@ -17,18 +18,22 @@
 
 namespace b2 {
 
-// Transform::transform_ray for an affine matrix (rows 0..2), transform.rs:307-331, 373-380, 451-476
-B2_D Ray32 xf_ray_affine(const float* m, const Ray32& r) {
+// Transform::transform_ray (transform.rs:307-331, 373-380, 451-476) with the full 4x4 world_to_instance: the
+// reference inverts with Gauss-Jordan, so the last row of the inverse is not always exactly (0,0,0,1) and the
+// homogeneous divide `if wp == 1 { p } else { p / wp }` is kept.  m0..m3 = rows 0..3.
+B2_D Ray32 xf_ray(float4 m0, float4 m1, float4 m2, float4 m3, const Ray32& r) {
     float x = r.ox, y = r.oy, z = r.oz;
-    float xp = (m[0] * x + m[1] * y) + (m[2] * z + m[3]);
-    float yp = (m[4] * x + m[5] * y) + (m[6] * z + m[7]);
-    float zp = (m[8] * x + m[9] * y) + (m[10] * z + m[11]);
-    float xs = pabs(m[0] * x) + pabs(m[1] * y) + pabs(m[2] * z) + pabs(m[3]);
-    float ys = pabs(m[4] * x) + pabs(m[5] * y) + pabs(m[6] * z) + pabs(m[7]);
-    float zs = pabs(m[8] * x) + pabs(m[9] * y) + pabs(m[10] * z) + pabs(m[11]);
+    float xp = (m0.x * x + m0.y * y) + (m0.z * z + m0.w);
+    float yp = (m1.x * x + m1.y * y) + (m1.z * z + m1.w);
+    float zp = (m2.x * x + m2.y * y) + (m2.z * z + m2.w);
+    float wp = (m3.x * x + m3.y * y) + (m3.z * z + m3.w);
+    float xs = pabs(m0.x * x) + pabs(m0.y * y) + pabs(m0.z * z) + pabs(m0.w);
+    float ys = pabs(m1.x * x) + pabs(m1.y * y) + pabs(m1.z * z) + pabs(m1.w);
+    float zs = pabs(m2.x * x) + pabs(m2.y * y) + pabs(m2.z * z) + pabs(m2.w);
     V3 o_err = kGamma3 * mk(xs, ys, zs);
     V3 o = mk(xp, yp, zp);
-    V3 d = mk(m[0] * r.dx + m[1] * r.dy + m[2] * r.dz, m[4] * r.dx + m[5] * r.dy + m[6] * r.dz, m[8] * r.dx + m[9] * r.dy + m[10] * r.dz);
+    if (!(wp == 1.0f)) o = o / wp;
+    V3 d = mk(m0.x * r.dx + m0.y * r.dy + m0.z * r.dz, m1.x * r.dx + m1.y * r.dy + m1.z * r.dz, m2.x * r.dx + m2.y * r.dy + m2.z * r.dz);
     float l2 = length_squared(d);
     float t_max = r.tmax;
     if (l2 > 0.0f) {
@@ -90,14 +95,15 @@ B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, in
             load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n);
             for (uint32_t i = 0;;) {
                 if (flags & 0x80000000u) {  // TransformedPrimitive
-                    const DInstance I = A2.instances[prim];
+                    const float4* T = A2.inst_trav + 6ll * prim;
+                    const float4 m0 = __ldg(T), m1 = __ldg(T + 1), m2 = __ldg(T + 2), m3 = __ldg(T + 3), b0q = __ldg(T + 4), b1q = __ldg(T + 5);
                     Ray32 wr = ray;
                     wr.tmax = t_max;
-                    Ray32 ir = xf_ray_affine(I.w2i, wr);
-                    const DObject ob = A2.objects[I.object];
+                    Ray32 ir = xf_ray(m0, m1, m2, m3, wr);
                     DeviceAccel oa = A;
-                    oa.root_code = ob.root_code;
-                    for (int k = 0; k < 6; ++k) oa.root_bounds[k] = ob.root_bounds[k];
+                    oa.root_code = __float_as_int(b1q.z);
+                    oa.root_bounds[0] = b0q.x; oa.root_bounds[1] = b0q.y; oa.root_bounds[2] = b0q.z;
+                    oa.root_bounds[3] = b0q.w; oa.root_bounds[4] = b1q.x; oa.root_bounds[5] = b1q.y;
                     HitOut h2;
                     if (traverse_wide<ANY>(oa, ir, &h2)) {
                         if (ANY) return true;
@@ -151,15 +157,228 @@ __global__ void __launch_bounds__(128) k_trace_twolevel(DeviceAccel2 A, const fl
     }
 }
 
-int launch_intersect2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, float* d_b2, int* d_inst) {
+// Phase-scheduled persistent two-level walk (variant 0, default): the kernel of traverse_phased.cuh with the instance
+// entered and left inside the same loop, so a warp keeps lanes that walk the scene aggregate and lanes that walk an
+// object's BVH in the same NODE / TRI phases (both levels share one node array and one record array).
+// Per lane: `sp_base` is the stack height at which the instance was entered (the nested walk pops down to it),
+// the interrupted top-level leaf is kept in (saved_cur, saved_i, saved_left) and the world ray is re-read from the
+// input when the instance is left.  Per ray the order of node tests, triangle tests and t_max updates is
+// TransformedPrimitive::intersect's (transformed_primitive.rs:51-64): on a hit the INSTANCE-space t_max stays in the
+// world ray, without one the world t_max is restored.
+#define B2_STACK2 96  // scene aggregate + object walk share one stack (the reference has 64 entries per level)
+
+template <bool ANY, int kSwitch, int kRefill, int kBlocks>
+__global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2, const float4* __restrict__ rays, long long n, void* __restrict__ out,
+                                                                unsigned long long* __restrict__ counter, float* __restrict__ b2_out, int* __restrict__ inst_out) {
+    const DeviceAccel& A = A2.top;
+    const unsigned lane = threadIdx.x & 31u;
+    const int kIdle = (int)0x80000000;
+    int stack_code[B2_STACK2];
+    float stack_t[B2_STACK2];
+
+    long long ray_id = -1;
+    RayCtx r;
+    TriCtx tc;
+    V3 o;
+    float t_max = 0.0f, world_t_max = 0.0f;
+    int cur = kIdle, sp = 0, sp_base = 0;
+    long long tri_i = 0, saved_i = 0;
+    uint32_t tri_left = 0, saved_left = 0;
+    int saved_cur = 0;
+    int in_inst = -1;        // instance being walked, -1 at the top level
+    bool inst_hit = false;   // the current instance produced a hit
+    bool hit = false;
+    HitOut h;
+    int h_inst = -1;
+    h.t = 0.0f; h.prim = 0xffffffffu; h.b0 = h.b1 = h.b2 = 0.0f;
+    bool exhausted = false;
+    bool node_phase = true;
+
+    auto set_ray = [&](float ox, float oy, float oz, float dx, float dy, float dz) {
+        r.ox = ox; r.oy = oy; r.oz = oz;
+        r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
+        r.nx = r.ix < 0.0f; r.ny = r.iy < 0.0f; r.nz = r.iz < 0.0f;
+        tc = make_tri_ctx(dx, dy, dz);
+        o = mk(ox, oy, oz);
+    };
+
+    for (;;) {
+        const unsigned idle_mask = __ballot_sync(0xffffffffu, cur == kIdle);
+        if (idle_mask == 0xffffffffu && exhausted) break;
+        if (!exhausted && __popc(idle_mask) >= kRefill) {
+            const int want = __popc(idle_mask);
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if ((long long)b + want >= n) exhausted = true;
+            if (cur == kIdle) {
+                const long long id = (long long)b + __popc(idle_mask & ((1u << lane) - 1u));
+                if (id < n) {
+                    float4 r0 = __ldg(rays + 2 * id), r1 = __ldg(rays + 2 * id + 1);
+                    ray_id = id;
+                    set_ray(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                    t_max = r0.w;
+                    sp = 0; sp_base = 0; hit = false; tri_left = 0; in_inst = -1; h_inst = -1;
+                    h.t = __int_as_float(0x7f800000); h.prim = 0xffffffffu; h.b0 = h.b1 = h.b2 = 0.0f;
+                    float te;
+                    bool enter = A.root_code != B2_EMPTY_ROOT &&
+                                 slab(r, A.root_bounds[0], A.root_bounds[1], A.root_bounds[2], A.root_bounds[3], A.root_bounds[4], A.root_bounds[5], &te) && te < t_max;
+                    if (enter) cur = A.root_code;
+                    else {
+                        if (ANY) ((uint8_t*)out)[id] = 0;
+                        else {
+                            ((float4*)out)[id] = make_float4(h.t, __uint_as_float(h.prim), 0.0f, 0.0f);
+                            if (b2_out) b2_out[id] = 0.0f;
+                            if (inst_out) inst_out[id] = -1;
+                        }
+                    }
+                }
+            }
+        }
+        for (;;) {
+            const unsigned m_node = __ballot_sync(0xffffffffu, cur >= 0);
+            const unsigned m_tri = __ballot_sync(0xffffffffu, cur < 0 && cur != kIdle);
+            if (!(m_node | m_tri)) break;
+            if (!exhausted && __popc(~(m_node | m_tri)) >= kRefill) break;
+            const int nn = __popc(m_node), nt = __popc(m_tri);
+            if (node_phase) { if (nn < kSwitch && nt > nn) node_phase = false; }
+            else            { if (nt < kSwitch && nn > nt) node_phase = true; }
+            if (nt == 0) node_phase = true;
+            if (nn == 0) node_phase = false;
+
+            bool retire = false;
+            if (node_phase) {
+                if (cur >= 0) {
+                    const float4* q = A.wide + 4ll * cur;
+                    float4 q0, q1, q2, q3;
+                    ldg8(q, &q0, &q1);
+                    ldg8(q + 2, &q2, &q3);
+                    float t0, t1;
+                    bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0) && t0 < t_max;
+                    bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1) && t1 < t_max;
+                    int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y), axis = __float_as_int(q3.z);
+                    int neg = axis == 0 ? r.nx : (axis == 1 ? r.ny : r.nz);
+                    int near_c = neg ? c1 : c0, far_c = neg ? c0 : c1;
+                    bool near_h = neg ? h1 : h0, far_h = neg ? h0 : h1;
+                    float far_t = neg ? t0 : t1;
+                    if (near_h) {
+                        if (far_h) { stack_code[sp] = far_c; stack_t[sp] = far_t; ++sp; }
+                        cur = near_c;
+                    } else if (far_h) {
+                        cur = far_c;
+                    } else {
+                        retire = true;
+                    }
+                    tri_left = 0;
+                }
+            } else if (cur < 0 && cur != kIdle) {
+                V3 p0, p1, p2;
+                uint32_t prim, flags, leaf_n;
+                if (tri_left == 0) tri_i = (long long)(~cur);
+                load_tri(A.tris, tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n);
+                if (tri_left == 0) tri_left = leaf_n;
+                ++tri_i;
+                --tri_left;
+                if (flags & 0x80000000u) {
+                    // TransformedPrimitive: take the ray to instance space and start the object's walk at its root.
+                    const float4* T = A2.inst_trav + 6ll * prim;
+                    const float4 m0 = __ldg(T), m1 = __ldg(T + 1), m2 = __ldg(T + 2), m3 = __ldg(T + 3), b0q = __ldg(T + 4), b1q = __ldg(T + 5);
+                    const float4 w1 = __ldg(rays + 2 * ray_id + 1);
+                    Ray32 wr{o.x, o.y, o.z, t_max, w1.x, w1.y, w1.z, w1.w};
+                    const Ray32 ir = xf_ray(m0, m1, m2, m3, wr);
+                    RayCtx ri;
+                    ri.ox = ir.ox; ri.oy = ir.oy; ri.oz = ir.oz;
+                    ri.ix = 1.0f / ir.dx; ri.iy = 1.0f / ir.dy; ri.iz = 1.0f / ir.dz;
+                    ri.nx = ri.ix < 0.0f; ri.ny = ri.iy < 0.0f; ri.nz = ri.iz < 0.0f;
+                    float te;
+                    const int root = __float_as_int(b1q.z);
+                    if (root != B2_EMPTY_ROOT && slab(ri, b0q.x, b0q.y, b0q.z, b0q.w, b1q.x, b1q.y, &te) && te < ir.tmax) {
+                        saved_cur = cur; saved_i = tri_i; saved_left = tri_left;
+                        world_t_max = t_max;
+                        in_inst = (int)prim; inst_hit = false;
+                        sp_base = sp;
+                        r = ri;
+                        tc = make_tri_ctx(ir.dx, ir.dy, ir.dz);
+                        o = mk(ir.ox, ir.oy, ir.oz);
+                        t_max = ir.tmax;
+                        cur = root;
+                        tri_left = 0;
+                    } else if (tri_left == 0) retire = true;
+                } else {
+                    float t, b0, b1, b2;
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2)) {
+                        if (ANY) {
+                            if (!(flags & 6u)) { hit = true; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
+                        } else if (!(flags & 2u)) {
+                            hit = true;
+                            t_max = t;
+                            h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;
+                            h_inst = in_inst;
+                            inst_hit = true;
+                        }
+                    }
+                    if (tri_left == 0) retire = true;
+                }
+            }
+            if (retire) {
+                for (;;) {
+                    cur = kIdle;
+                    while (sp > sp_base) {
+                        --sp;
+                        if (ANY || stack_t[sp] < t_max) { cur = stack_code[sp]; break; }
+                    }
+                    tri_left = 0;
+                    if (cur != kIdle || in_inst < 0) break;
+                    // the object's walk is finished: back to the interrupted leaf of the scene aggregate
+                    if (!inst_hit) t_max = world_t_max;
+                    in_inst = -1;
+                    sp_base = 0;
+                    const float4 w0 = __ldg(rays + 2 * ray_id), w1 = __ldg(rays + 2 * ray_id + 1);
+                    set_ray(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
+                    if (saved_left > 0) { cur = saved_cur; tri_i = saved_i; tri_left = saved_left; break; }
+                }
+                if (cur == kIdle) {
+                    if (ANY) ((uint8_t*)out)[ray_id] = hit ? 1 : 0;
+                    else {
+                        ((float4*)out)[ray_id] = make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1);
+                        if (b2_out) b2_out[ray_id] = h.b2;
+                        if (inst_out) inst_out[ray_id] = h_inst;
+                    }
+                }
+            }
+        }
+    }
+}
+
+static const int kCounterRing2 = 64;  // one work counter per launch in flight (launches on different streams never share one)
+static unsigned long long* g_counter2 = nullptr;
+static std::atomic<unsigned> g_counter2_next{0};
+
+template <bool ANY>
+static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, float* d_b2, int* d_inst) {
+    if (!g_counter2) B2_CUDA(cudaMalloc(&g_counter2, kCounterRing2 * sizeof(unsigned long long)));
+    unsigned long long* ctr = g_counter2 + (g_counter2_next.fetch_add(1) % kCounterRing2);
+    B2_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
+    constexpr int kBlocks = 5;
+    int64_t want = (n + 127) / 128;
+    int grid = (int)std::min<int64_t>(want, (int64_t)g_sm_count * kBlocks);
+    k_trace_phased2<ANY, 16, 16, kBlocks><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200PT_OK : cuda_fail(e, "k_trace_phased2 launch");
+}
+
+int launch_intersect2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, float* d_b2, int* d_inst, int variant) {
     if (n <= 0) return B200PT_OK;
+    if (variant == 0) return launch_phased2<false>(A, d_rays, n, d_hits, s, d_b2, d_inst);
     k_trace_twolevel<false><<<(int)((n + 127) / 128), 128, 0, s>>>(A, (const float4*)d_rays, n, d_hits, d_b2, d_inst);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200PT_OK : cuda_fail(e, "k_trace_twolevel launch");
 }
-int launch_occluded2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s) {
+int launch_occluded2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant) {
     if (n <= 0) return B200PT_OK;
+    if (variant == 0) return launch_phased2<true>(A, d_rays, n, d_out, s, nullptr, nullptr);
     k_trace_twolevel<true><<<(int)((n + 127) / 128), 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, nullptr, nullptr);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
@@ -240,7 +459,8 @@ int accel2_build_device(const b200pt_scene_desc* d, Accel2Impl* a) {
     if (d->n_nodes > 0) std::memcpy(a->dev.top.root_bounds, d->nodes[0].bounds, 24);
     a->dev.top.n_nodes = (int)d->n_nodes;
     a->dev.top.n_prims = d->n_prims;
-    std::vector<DObject> objs((size_t)d->n_objects);
+    struct ObjRoot { float bounds[6]; int root_code; };
+    std::vector<ObjRoot> objs((size_t)d->n_objects);
     for (int o = 0; o < d->n_objects; ++o) {
         const b200pt_object& ob = d->objects[o];
         if (ob.n_nodes < 1 || ob.first_prim < d->n_top_tris || ob.first_prim + ob.n_prims > d->n_prims) {
@@ -255,46 +475,54 @@ int accel2_build_device(const b200pt_scene_desc* d, Accel2Impl* a) {
         }, wide, recs, &oroot);
         if (rc) return rc;
         objs[(size_t)o].root_code = oroot;
-        std::memcpy(objs[(size_t)o].root_bounds, ob.nodes[0].bounds, 24);
+        std::memcpy(objs[(size_t)o].bounds, ob.nodes[0].bounds, 24);
     }
     std::vector<DInstance> insts((size_t)d->n_instances);
+    std::vector<float4> trav((size_t)d->n_instances * 6);
     for (int i = 0; i < d->n_instances; ++i) {
         const b200pt_instance& in = d->instances[i];
         const float* w = in.world_to_instance;
         const float* m = in.instance_to_world;
-        if (in.object < 0 || in.object >= d->n_objects || w[12] != 0.0f || w[13] != 0.0f || w[14] != 0.0f || w[15] != 1.0f || m[12] != 0.0f || m[13] != 0.0f ||
-            m[14] != 0.0f || m[15] != 1.0f) {
-            b200pt_set_error("b200pt_scene_create: instance with a bad object index or a non-affine transform");
-            return B200PT_ERR_UNSUPPORTED;
+        if (in.object < 0 || in.object >= d->n_objects) {
+            b200pt_set_error("b200pt_scene_create: instance with a bad object index");
+            return B200PT_ERR_INVALID;
         }
         DInstance& I = insts[(size_t)i];
-        std::memcpy(I.w2i, w, 48);
-        std::memcpy(I.i2w, m, 48);
+        std::memcpy(I.w2i, w, 64);
+        std::memcpy(I.i2w, m, 64);
         I.object = in.object;
         bool ident = true;
         for (int k = 0; k < 16; ++k) if (m[k] != ((k % 5 == 0) ? 1.0f : 0.0f)) ident = false;
         I.identity = ident ? 1 : 0;  // Transform::is_identity, transformed_primitive.rs:57
+        I.pad[0] = I.pad[1] = 0;
+        float4* T = &trav[(size_t)i * 6];
+        for (int k = 0; k < 4; ++k) T[k] = make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+        const ObjRoot& ob = objs[(size_t)in.object];
+        float frc, fob;
+        std::memcpy(&frc, &ob.root_code, 4); std::memcpy(&fob, &in.object, 4);
+        T[4] = make_float4(ob.bounds[0], ob.bounds[1], ob.bounds[2], ob.bounds[3]);
+        T[5] = make_float4(ob.bounds[4], ob.bounds[5], frc, fob);
     }
     B2_CUDA(cudaMalloc(&a->d_wide, std::max<size_t>(wide.size(), 4) * sizeof(float4)));
     B2_CUDA(cudaMalloc(&a->d_recs, std::max<size_t>(recs.size(), 4) * sizeof(float4)));
-    B2_CUDA(cudaMalloc(&a->d_objs, std::max<size_t>(objs.size(), 1) * sizeof(DObject)));
+    B2_CUDA(cudaMalloc(&a->d_trav, std::max<size_t>(trav.size(), 6) * sizeof(float4)));
     B2_CUDA(cudaMalloc(&a->d_insts, std::max<size_t>(insts.size(), 1) * sizeof(DInstance)));
     if (!wide.empty()) B2_CUDA(cudaMemcpy(a->d_wide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice));
     if (!recs.empty()) B2_CUDA(cudaMemcpy(a->d_recs, recs.data(), recs.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    if (!objs.empty()) B2_CUDA(cudaMemcpy(a->d_objs, objs.data(), objs.size() * sizeof(DObject), cudaMemcpyHostToDevice));
+    if (!trav.empty()) B2_CUDA(cudaMemcpy(a->d_trav, trav.data(), trav.size() * sizeof(float4), cudaMemcpyHostToDevice));
     if (!insts.empty()) B2_CUDA(cudaMemcpy(a->d_insts, insts.data(), insts.size() * sizeof(DInstance), cudaMemcpyHostToDevice));
     a->dev.top.wide = a->d_wide;
     a->dev.top.tris = a->d_recs;
     a->dev.top.ref_nodes = nullptr;
-    a->dev.objects = a->d_objs;
+    a->dev.inst_trav = a->d_trav;
     a->dev.instances = a->d_insts;
     return B200PT_OK;
 }
 
 void accel2_free_device(Accel2Impl* a) {
-    for (void* p : {(void*)a->d_wide, (void*)a->d_recs, (void*)a->d_objs, (void*)a->d_insts})
+    for (void* p : {(void*)a->d_wide, (void*)a->d_recs, (void*)a->d_trav, (void*)a->d_insts})
         if (p) cudaFree(p);
-    a->d_wide = a->d_recs = nullptr; a->d_objs = nullptr; a->d_insts = nullptr;
+    a->d_wide = a->d_recs = a->d_trav = nullptr; a->d_insts = nullptr;
 }
 
 }  // namespace b2

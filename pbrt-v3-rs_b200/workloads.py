@@ -243,6 +243,33 @@ def scene_c3(nu=330, nv=330, xres=1920, yres=1080, spp=64, maxdepth=8):
     return sd
 
 
+def scene_c4(n_objects=46, nu=330, nv=330, xres=1920, yres=1080, spp=256, maxdepth=8):
+    """C4: San-Miguel-scale stand-in — n_objects displaced spheres (46 x 217 800 = 10.0 M triangles) on an 8-wide grid
+    with the four C3 materials in turn, ground quad, a two-triangle area light, a point light and a dim constant
+    environment, lightsamplestrategy "power"; every triangle is a top-level primitive of ONE BVH (no instancing)."""
+    sd = SceneDescription()
+    mats = [sd.add_material(type="matte", Kd=(0.5, 0.45, 0.4)), sd.add_material(type="plastic"),
+            sd.add_material(type="glass", eta=1.5), sd.add_material(type="metal", eta=COPPER_ETA, k=COPPER_K, roughness=0.01)]
+    g = sd.add_material(type="matte", Kd=(0.4, 0.4, 0.4))
+    cols = 8
+    for i in range(n_objects):
+        cx = (i % cols - (cols - 1) / 2.0) * 2.4
+        cz = (i // cols) * 2.4
+        sd.add_mesh(displaced_sphere(nu, nv, seed=1 + 10 * i, center=(cx, 0.0, cz)), mats[i % 4])
+    sd.add_mesh(ground_quad(y=-1.3, half=30.0), g)
+    lq = np.array([[-6.0, 6.0, 2.0], [6.0, 6.0, 2.0], [6.0, 6.0, 10.0], [-6.0, 6.0, 10.0]], dtype=F32)
+    light_tris = np.stack([np.concatenate([lq[0], lq[1], lq[2]]), np.concatenate([lq[0], lq[2], lq[3]])])
+    lm = sd.add_material(type="matte", Kd=(0.0, 0.0, 0.0))
+    sd.add_mesh(light_tris, lm, area_light=dict(L=(20, 20, 20)))
+    sd.add_point_light((0.0, 5.0, -8.0), (120, 120, 120))
+    sd.add_infinite_light((0.3, 0.35, 0.45))
+    sd.camera.update(eye=(0.0, 7.5, -13.0), look=(0.0, 0.0, 5.5), up=(0, 1, 0), fov=42.0)
+    sd.film.update(xresolution=xres, yresolution=yres, filter="box")
+    sd.sampler.update(type="halton", pixelsamples=spp)
+    sd.integrator.update(maxdepth=maxdepth, lightsamplestrategy="power")
+    return sd
+
+
 def rigid_transform(rng, scale_range=(0.7, 1.3), extent=8.0, y_range=(-0.9, 1.5)):
     """Random rotation about a random axis, uniform scale and translation (instance_to_world, 4x4 row-major f32)."""
     axis = rng.normal(size=3)

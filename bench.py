@@ -339,7 +339,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(w, args),
                 "closest_mrays": n / (closest_ms * 1e-3) / 1e6, "anyhit_mrays": n / (shadow_ms * 1e-3) / 1e6,
-                "roofline": {"bound": "hbm", "kernel": {0: "k_trace_phased<closest>", 3: "k_trace_persistent<closest>"}.get(args.variant, "k_trace_simple<closest,%d>" % args.variant),
+                "roofline": {"bound": "hbm", "kernel": {0: "k_trace_spec2<closest>", 3: "k_trace_persistent<closest>", 4: "k_trace_phased<closest>", 5: "k_trace_spec<closest>"}.get(args.variant, "k_trace_simple<closest,%d>" % args.variant),
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": tr["closest_dram_bytes_per_launch"] if tr else None,
                              "traffic_source": tr["source"] if tr else None, "peak_source": peak_src,
                              "note": "algorithmic bytes (32 B/node test + 36 B/triangle test + ray in + hit out, counted in reference order) over launch time; the 1 M-triangle BVH is L2-resident so DRAM traffic is ~3 % of the algorithmic bytes and the kernel is issue-bound (profiles/README.md)",

@@ -72,6 +72,49 @@ B2_D bool slab(const RayCtx& r, float lox, float loy, float loz, float hix, floa
     return t_max > 0.0f;
 }
 
+// Same test without early-out branches: every comparison keeps the reference's direction and NaN behaviour
+// (`a > b` false on NaN), the results of the later axes are simply ignored when an earlier one already failed.
+B2_D bool slab_bf(const RayCtx& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float* t_entry) {
+    float t_min = ((r.nx ? hix : lox) - r.ox) * r.ix;
+    float t_max = ((r.nx ? lox : hix) - r.ox) * r.ix;
+    float t_y_min = ((r.ny ? hiy : loy) - r.oy) * r.iy;
+    float t_y_max = ((r.ny ? loy : hiy) - r.oy) * r.iy;
+    float t_z_min = ((r.nz ? hiz : loz) - r.oz) * r.iz;
+    float t_z_max = ((r.nz ? loz : hiz) - r.oz) * r.iz;
+    t_max *= kSlabInflate;
+    t_y_max *= kSlabInflate;
+    bool ok = !(t_min > t_y_max) & !(t_y_min > t_max);
+    t_min = t_y_min > t_min ? t_y_min : t_min;
+    t_max = t_y_max < t_max ? t_y_max : t_max;
+    ok &= !(t_min > t_z_max) & !(t_z_min > t_max);
+    t_min = t_z_min > t_min ? t_z_min : t_min;
+    t_max = t_z_max < t_max ? t_z_max : t_max;
+    *t_entry = t_min;
+    return ok & (t_max > 0.0f);
+}
+
+// Min/max form of the same test for rays whose direction components are all finite and non-zero and whose origin is
+// finite (slab_fast_ok): then no product below is NaN, `neg ? hi : lo` picks exactly min / max of the two plane
+// distances (f32 subtraction and multiplication are monotonic), the running t_min / t_max of the reference are
+// max3 / min3 of the per-axis values, and the reference's six cross-axis comparisons are `t_min <= t_max`: the three
+// same-axis pairs that form adds can only fail when an inflated far distance is negative, where the reference
+// rejects through `t_max > 0`.  Same boolean, same t_entry (up to the sign of zero, which no comparison sees);
+// 25 instead of 37 instructions per box (FMNMX3 on sm_100).
+B2_D bool slab_fast(const RayCtx& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float* t_entry) {
+    float ax = (lox - r.ox) * r.ix, bx = (hix - r.ox) * r.ix;
+    float ay = (loy - r.oy) * r.iy, by = (hiy - r.oy) * r.iy;
+    float az = (loz - r.oz) * r.iz, bz = (hiz - r.oz) * r.iz;
+    float t_min = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    float t_max = fminf(fminf(fmaxf(ax, bx) * kSlabInflate, fmaxf(ay, by) * kSlabInflate), fmaxf(az, bz));
+    *t_entry = t_min;
+    return (t_min <= t_max) & (t_max > 0.0f);
+}
+B2_D bool slab_fast_ok(float ox, float oy, float oz, float ix, float iy, float iz) {
+    const float big = __int_as_float(0x7f7fffff);
+    return (pabs(ix) <= big) & (pabs(iy) <= big) & (pabs(iz) <= big) & (ix != 0.0f) & (iy != 0.0f) & (iz != 0.0f) & (pabs(ox) <= big) & (pabs(oy) <= big) &
+           (pabs(oz) <= big);
+}
+
 // ---- triangle ---------------------------------------------------------------
 struct TriCtx {  // per-ray constants of the watertight test
     int kx, ky, kz;

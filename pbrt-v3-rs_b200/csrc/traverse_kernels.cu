@@ -2,6 +2,7 @@
 // See traverse.cuh for the data layout and the equivalence argument.
 #include "common.cuh"
 #include "traverse_phased.cuh"
+#include "traverse_spec.cuh"
 
 namespace b2 {
 
@@ -250,9 +251,9 @@ static int persistent_setup() {
     g_persist_grid[0] = g_sm_count * (nb > 0 ? nb : 1);
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_persistent<true>, 128, 0));
     g_persist_grid[1] = g_sm_count * (nb > 0 ? nb : 1);
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_phased<false, 16, 16, 0, 7>, 128, 0));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_spec2<false, 20, 20, 7, 1>, 128, 0));
     g_persist_grid[2] = g_sm_count * (nb > 0 ? nb : 1);
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_phased<true, 16, 16, 0, 8>, 128, 0));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_spec2<true, 20, 16, 8, 1>, 128, 0));
     g_persist_grid[3] = g_sm_count * (nb > 0 ? nb : 1);
     return B200PT_OK;
 }
@@ -266,19 +267,28 @@ static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void*
     } else if (variant == 2) {
         k_trace_simple<ANY, 2><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out, d_b2);
     } else {
+        // Persistent kernels.  0 (default) = loop-free postponed-leaf walk (traverse_spec.cuh); A/B baselines:
+        // 3 = "if-if" persistent warps, 4 = phase-scheduled without postponement, 5 = postponed leaf with pop loops.
         int rc = persistent_setup();
         if (rc) return rc;
+        if (n >= 0x7fffffffLL) { b200pt_set_error("traversal: at most 2^31-2 rays per launch"); return B200PT_ERR_INVALID; }
         unsigned long long* ctr = g_counters + (g_counter_next.fetch_add(1) % kCounterRing);
         B2_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
         int grid = g_persist_grid[(variant != 3 ? 2 : 0) + (ANY ? 1 : 0)];
         int need = grid_for(n, block);
         if (need < grid) grid = need;
-        // closest-hit: 72 registers -> 7 CTAs/SM; any-hit: 64 registers -> 8 CTAs/SM (profiles/r1_variants.txt)
-        if (variant != 3) {
-            if (ANY) k_trace_phased<true, 16, 16, 0, 8><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2);
-            else k_trace_phased<false, 16, 16, 0, 7><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2);
+        const float4* R = (const float4*)d_rays;
+        // closest-hit: <= 72 registers -> 7 CTAs/SM; any-hit: 64 registers -> 8 CTAs/SM (profiles/r1_variants.txt)
+        if (variant == 3) k_trace_persistent<ANY><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
+        else if (variant == 4) {
+            if (ANY) k_trace_phased<true, 16, 16, 0, 8><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
+            else k_trace_phased<false, 16, 16, 0, 7><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
+        } else if (variant == 5) {
+            k_trace_spec<ANY, 16, 16, ANY ? 8 : 7><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
+        } else {
+            if (ANY) k_trace_spec2<true, 20, 16, 8, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
+            else k_trace_spec2<false, 20, 20, 7, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
         }
-        else k_trace_persistent<ANY><<<grid, block, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2);
     }
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();

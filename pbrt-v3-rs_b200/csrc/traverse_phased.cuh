@@ -19,13 +19,32 @@
 
 namespace b2 {
 
-template <bool ANY, int kSwitch, int kRefill, int kChunk, int kBlocks>
+template <bool ANY> struct StackEntry;
+template <> struct StackEntry<false> {
+    int2 v;
+    B2_D void set(int code, float t) { v = make_int2(code, __float_as_int(t)); }
+    B2_D int code() const { return v.x; }
+    B2_D float t() const { return __int_as_float(v.y); }
+};
+template <> struct StackEntry<true> {
+    int v;
+    B2_D void set(int code, float) { v = code; }
+    B2_D int code() const { return v; }
+    B2_D float t() const { return 0.0f; }
+};
+
+// Stack: the newest entry lives in registers (top_code / top_t); a pop takes it from there and only PREFETCHES the
+// entry below it from local memory, so the local-memory load latency is off the pop -> next-node-fetch critical path
+// (the pop section runs with 3-4 active lanes, profiles/r1_*).  Entries are 8 bytes {code, bits(t_entry)}: one
+// STL.64 / LDL.64 per spill / refill.  The box tests have no early-out branches (slab_bf).
+// kOpt bit 0: warps in which every live ray has finite non-zero direction components take the min/max box test
+//             (slab_fast, 25 vs 37 instructions per box); a warp holding an axis-parallel ray keeps the literal one.
+template <bool ANY, int kSwitch, int kRefill, int kChunk, int kBlocks, int kOpt = 1>
 __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, const float4* __restrict__ rays, long long n, void* __restrict__ out,
                                                          unsigned long long* __restrict__ counter, float* __restrict__ b2_out) {
     const unsigned lane = threadIdx.x & 31u;
     const int kIdle = (int)0x80000000;  // no ray in this lane (leaf codes are ~first >= -2^31 + 1)
-    int stack_code[B2_STACK];
-    float stack_t[B2_STACK];
+    StackEntry<ANY> stack[B2_STACK];    // closest: {code, bits(t_entry)}; any-hit: code only (t_max never shrinks)
 
     long long ray_id = -1;
     RayCtx r;
@@ -33,6 +52,9 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
     V3 o;
     float t_max = 0.0f;
     int cur = kIdle, sp = 0;
+    int top_code = kIdle;      // newest stack entry (kIdle = none)
+    float top_t = 0.0f;
+    int negmask = 0;           // dir_is_neg bits
     long long tri_i = 0;       // next triangle of the current leaf
     uint32_t tri_left = 0;     // triangles left in the current leaf (0 = leaf header not read yet)
     bool hit = false;
@@ -40,6 +62,8 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
     h.t = 0.0f; h.prim = 0xffffffffu; h.b0 = h.b1 = h.b2 = 0.0f;
     bool exhausted = false;  // warp-uniform: the global ray counter ran past n
     bool node_phase = true;
+    bool lane_slow = false;  // this lane's ray needs the literal box test
+    bool warp_slow = false;  // warp-uniform: some lane's ray does
     long long chunk_next = 0, chunk_end = 0;  // warp-uniform: this warp's reserved ray range
 
     for (;;) {
@@ -61,6 +85,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
             const long long take = (chunk_end - chunk_next) < (long long)__popc(idle_mask) ? (chunk_end - chunk_next) : (long long)__popc(idle_mask);
             chunk_next += take;
             if (cur == kIdle) {
+                lane_slow = false;
                 const long long id = base + rank;
                 if (rank < take) {
                     float4 r0 = __ldg(rays + 2 * id), r1 = __ldg(rays + 2 * id + 1);
@@ -68,21 +93,25 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
                     r.ox = r0.x; r.oy = r0.y; r.oz = r0.z;
                     r.ix = 1.0f / r1.x; r.iy = 1.0f / r1.y; r.iz = 1.0f / r1.z;
                     r.nx = r.ix < 0.0f; r.ny = r.iy < 0.0f; r.nz = r.iz < 0.0f;
+                    negmask = r.nx | (r.ny << 1) | (r.nz << 2);
                     t_max = r0.w;
                     tc = make_tri_ctx(r1.x, r1.y, r1.z);
                     o = mk(r0.x, r0.y, r0.z);
-                    sp = 0; hit = false; tri_left = 0;
+                    sp = 0; hit = false; tri_left = 0; top_code = kIdle;
                     h.t = __int_as_float(0x7f800000); h.prim = 0xffffffffu; h.b0 = h.b1 = h.b2 = 0.0f;
                     float te;
                     bool enter = A.root_code != B2_EMPTY_ROOT &&
                                  slab(r, A.root_bounds[0], A.root_bounds[1], A.root_bounds[2], A.root_bounds[3], A.root_bounds[4], A.root_bounds[5], &te) && te < t_max;
-                    if (enter) cur = A.root_code;
-                    else {
+                    if (enter) {
+                        cur = A.root_code;
+                        if (kOpt & 1) lane_slow = !slab_fast_ok(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz);
+                    } else {
                         if (ANY) ((uint8_t*)out)[id] = 0;
                         else { ((float4*)out)[id] = make_float4(h.t, __uint_as_float(h.prim), 0.0f, 0.0f); if (b2_out) b2_out[id] = 0.0f; }
                     }
                 }
             }
+            if (kOpt & 1) warp_slow = __any_sync(0xffffffffu, lane_slow);
         }
         // ---- run phases until enough lanes went idle ------------------------------------------------
         for (;;) {
@@ -105,15 +134,25 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
                     ldg8(q, &q0, &q1);
                     ldg8(q + 2, &q2, &q3);
                     float t0, t1;
-                    bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0) && t0 < t_max;
-                    bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1) && t1 < t_max;
-                    int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y), axis = __float_as_int(q3.z);
-                    int neg = axis == 0 ? r.nx : (axis == 1 ? r.ny : r.nz);
-                    int near_c = neg ? c1 : c0, far_c = neg ? c0 : c1;
-                    bool near_h = neg ? h1 : h0, far_h = neg ? h0 : h1;
-                    float far_t = neg ? t0 : t1;
+                    bool h0, h1;
+                    if ((kOpt & 1) && !warp_slow) {
+                        h0 = slab_fast(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0) & (t0 < t_max);
+                        h1 = slab_fast(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1) & (t1 < t_max);
+                    } else {
+                        h0 = slab_bf(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0) & (t0 < t_max);
+                        h1 = slab_bf(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1) & (t1 < t_max);
+                    }
+                    const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y), axis = __float_as_int(q3.z);
+                    const bool neg = (negmask >> axis) & 1;
+                    // reference order: neg ? (second first, push first) : (first first, push second)
+                    const int near_c = neg ? c1 : c0, far_c = neg ? c0 : c1;
+                    const bool near_h = neg ? h1 : h0, far_h = neg ? h0 : h1;
+                    const float far_t = neg ? t0 : t1;
                     if (near_h) {
-                        if (far_h) { stack_code[sp] = far_c; stack_t[sp] = far_t; ++sp; }
+                        if (far_h) {
+                            if (top_code != kIdle) { stack[sp].set(top_code, top_t); ++sp; }
+                            top_code = far_c; top_t = far_t;
+                        }
                         cur = near_c;
                     } else if (far_h) {
                         cur = far_c;
@@ -131,7 +170,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
                 float t, b0, b1, b2;
                 if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2)) {
                     if (ANY) {
-                        if (!(flags & 6u)) { hit = true; sp = 0; tri_left = 1; }
+                        if (!(flags & 6u)) { hit = true; sp = 0; top_code = kIdle; tri_left = 1; }
                     } else if (!(flags & 2u)) {
                         hit = true;
                         t_max = t;
@@ -143,9 +182,12 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
             }
             if (retire) {
                 cur = kIdle;
-                while (sp > 0) {
-                    --sp;
-                    if (ANY || stack_t[sp] < t_max) { cur = stack_code[sp]; break; }
+                while (top_code != kIdle) {
+                    const int c = top_code;
+                    const float t = top_t;
+                    if (sp > 0) { --sp; const StackEntry<ANY> e = stack[sp]; top_code = e.code(); top_t = e.t(); }
+                    else top_code = kIdle;
+                    if (ANY || t < t_max) { cur = c; break; }
                 }
                 tri_left = 0;
                 if (cur == kIdle) {

@@ -27,7 +27,7 @@ def _check_closest(gpu_hits, o_hits, diag, oracle):
     return int((~(same_prim & same_t)).sum())
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_closest_and_any_hit_bit_exact_small(gpu, oracle, variant):
     import torch
     from pbrt_v3_rs_b200 import workloads as wl
@@ -136,6 +136,61 @@ def test_edge_cases(gpu, oracle):
     # empty accelerator
     e = gpu.BVHAccel(np.zeros((0, 9), np.float32), np.zeros(0, gpu.NODE_DTYPE), np.zeros(0, np.uint32))
     assert (e.intersect_batch(rays)["prim"] == MISS).all() and not e.occluded_batch(rays).any()
+
+
+@pytest.mark.parametrize("variant", [0, 2, 4, 5])
+def test_axis_parallel_rays_mixed_with_general_rays(gpu, oracle, variant):
+    """Warps holding rays with zero / denormal direction components (inv = +-inf: the 0 * inf NaN
+    cases of the slab test) next to general rays: the min/max box test must hand such warps to the literal one."""
+    import torch
+    from pbrt_v3_rs_b200 import workloads as wl
+    rng = np.random.Generator(np.random.PCG64(21))
+    # axis-aligned quads on integer planes (box faces coincide with ray origins) + a displaced sphere
+    quads = []
+    for k in range(-2, 3):
+        for ax in range(3):
+            c = np.zeros((4, 3), dtype=np.float32)
+            u, v = (ax + 1) % 3, (ax + 2) % 3
+            c[:, ax] = k
+            c[:, u] = [-2, 2, 2, -2]
+            c[:, v] = [-2, -2, 2, 2]
+            quads += [np.concatenate([c[0], c[1], c[2]]), np.concatenate([c[0], c[2], c[3]])]
+    tv = np.concatenate([np.stack(quads).astype(np.float32), wl.displaced_sphere(40, 20, radius=1.5)])
+    accel = gpu.BVHAccel.from_params({"maxnodeprims": 4}, tv)
+    oacc = oracle.OracleAccel(accel.nodes, accel.ordered_prims, tv)
+    n = 1 << 14
+    rays = np.zeros(n, dtype=gpu.RAY_DTYPE)
+    rays["o"] = rng.uniform(-3, 3, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    rays["tmax"] = np.inf
+    special = np.arange(n) % 5 == 0
+    k = np.arange(n)
+    d[special & (k % 3 == 0), 0] = 0.0
+    d[special & (k % 3 == 1), 1] = -0.0
+    d[special & (k % 7 == 0), 2] = 0.0
+    # denormal: 1/d overflows to inf (kept off the rays whose other components were zeroed: an all-denormal direction
+    # yields NaN hit distances, whose payload bits differ between x86 and sm_100)
+    d[special & (k % 11 == 0) & (k % 3 == 2) & (k % 7 != 0), 0] = 1e-42
+    rays["d"] = d
+    snap = special & (k % 2 == 0)
+    rays["o"][snap] = np.round(rays["o"][snap])     # origins on the integer planes of the quads
+    d_r = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
+    d_h = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    accel.intersect_batch_device(d_r.data_ptr(), n, d_h.data_ptr(), torch.cuda.current_stream().cuda_stream, variant)
+    torch.cuda.synchronize()
+    g = d_h.cpu().numpy().view(gpu.HIT_DTYPE).reshape(-1)
+    o, diag, _ = oacc.intersect(rays)
+    assert np.array_equal(g["prim"], o["prim"]), np.nonzero(g["prim"] != o["prim"])[0][:8]
+    assert np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32)), np.nonzero(g["t"].view(np.uint32) != o["t"].view(np.uint32))[0][:8]
+    assert (g["prim"][special] != MISS).sum() > 100
+    sr = rays.copy()
+    sr["tmax"] = 2.0
+    d_o = torch.empty(n, dtype=torch.uint8, device="cuda")
+    accel.occluded_batch_device(d_r.data_ptr(), n, d_o.data_ptr(), torch.cuda.current_stream().cuda_stream, variant)
+    d_r2 = torch.from_numpy(sr.view(np.float32).reshape(-1, 8)).cuda()
+    accel.occluded_batch_device(d_r2.data_ptr(), n, d_o.data_ptr(), torch.cuda.current_stream().cuda_stream, variant)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_o.cpu().numpy(), oacc.occluded(sr)[0])
 
 
 def test_full_size_microbench_parity(gpu, oracle):

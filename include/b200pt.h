@@ -66,6 +66,10 @@ typedef struct b200pt_bvh_node {
 #define B200PT_PRIM_FLIP_NORMAL 1u        /* reverse_orientation ^ transform_swaps_handedness (shapes/src/triangle.rs:625-629) */
 #define B200PT_PRIM_ALPHA_ZERO 2u         /* constant "alpha" texture == 0 (triangle.rs:587-607) */
 #define B200PT_PRIM_SHADOW_ALPHA_ZERO 4u  /* constant "shadowalpha" texture == 0 (triangle.rs:840-899) */
+#define B200PT_PRIM_REVERSE_ORIENTATION 8u /* reverse_orientation alone: flips the shading bitangent (triangle.rs:714-716) */
+#define B200PT_PRIM_HAS_UV 16u            /* the primitive's mesh has "uv"/"st": tri_uvs holds its three uvs (triangle.rs:384-394) */
+#define B200PT_PRIM_HAS_NORMALS 32u       /* ... has "N": tri_normals (triangle.rs:631-653) */
+#define B200PT_PRIM_HAS_TANGENTS 64u      /* ... has "S": tri_tangents (triangle.rs:655-670) */
 
 /* materials/src/{matte,plastic,glass,metal}.rs with constant textures. */
 enum { B200PT_MAT_MATTE = 0, B200PT_MAT_PLASTIC = 1, B200PT_MAT_GLASS = 2, B200PT_MAT_METAL = 3 };
@@ -175,6 +179,12 @@ typedef struct b200pt_scene_desc {
     int32_t n_objects;
     const b200pt_instance* instances;
     int32_t n_instances;
+    /* Optional vertex attributes, de-indexed like tri_verts and already in world space (TriangleMesh::new applies
+     * transform_normal / transform_vector and does not renormalise, triangle.rs:92-99).  Each may be NULL; a primitive
+     * uses an array only when its flag bit (B200PT_PRIM_HAS_*) is set. */
+    const float* tri_uvs;      /* 6 floats per ORIGINAL primitive: uv0 uv1 uv2 */
+    const float* tri_normals;  /* 9 floats per ORIGINAL primitive: n0 n1 n2 */
+    const float* tri_tangents; /* 9 floats per ORIGINAL primitive: s0 s1 s2 */
 } b200pt_scene_desc;
 
 typedef struct b200pt_accel b200pt_accel; /* opaque: device-resident BVHAccel */
@@ -202,6 +212,10 @@ int b200pt_triangle_bounds(const float* tri_verts, int64_t n, float* bounds_out)
  * Copies the arrays to the device; the caller keeps ownership of its own. */
 int b200pt_accel_create(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered_prims, const float* tri_verts,
                         const uint32_t* prim_flags, int64_t n_prims, b200pt_accel** out);
+/* Same for meshes with "uv"/"st": tri_uvs = 6 floats per ORIGINAL primitive (used by the primitives whose flags carry
+ * B200PT_PRIM_HAS_UV).  The uvs reach the traversal through the degenerate-hit rejection of triangle.rs:551-572. */
+int b200pt_accel_create_uv(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered_prims, const float* tri_verts,
+                           const float* tri_uvs, const uint32_t* prim_flags, int64_t n_prims, b200pt_accel** out);
 void b200pt_accel_destroy(b200pt_accel* a);
 /* Primitive::world_bound (mod.rs:159-165): 6 floats. */
 int b200pt_accel_world_bound(const b200pt_accel* a, float* bounds6);

@@ -286,16 +286,25 @@ inline bool triangle_test(const Ray& r, V3 p0, V3 p1, V3 p2, TriHit* h) {
     return true;
 }
 
-// Hit geometry of an accepted candidate (triangle.rs:547-629, default uvs
-// :384-394; meshes on the in-scope path carry no N/S/uv arrays).
+// Hit geometry of an accepted candidate (triangle.rs:547-725).  Optional per-triangle vertex attributes: uv (get_uvs,
+// triangle.rs:384-394: defaults (0,0),(1,0),(1,1)), normals N and tangents S (already in world space:
+// TriangleMesh::new transforms them and does NOT renormalise, triangle.rs:92-99).
+struct TriAttr {
+    const Float* uv = nullptr;   // 6 floats: uv0 uv1 uv2
+    const Float* n = nullptr;    // 9 floats: n0 n1 n2
+    const Float* s = nullptr;    // 9 floats: s0 s1 s2
+    bool flip = false;           // reverse_orientation ^ transform_swaps_handedness
+    bool reverse = false;        // reverse_orientation
+};
 struct TriGeom {
     V3 p, p_error, n, dpdu, dpdv;
     P2 uv;
+    V3 shading_n, shading_dpdu;  // Shading::{n, dpdu} after set_shading_geometry (== n, dpdu without N / S)
 };
-// Returns false when the reference rejects the hit as degenerate
-// (triangle.rs:567-572).  flip = reverse_orientation ^ transform_swaps_handedness.
-inline bool triangle_geometry(V3 p0, V3 p1, V3 p2, Float b0, Float b1, Float b2, bool flip, TriGeom* g) {
-    const P2 uv0(0.0f, 0.0f), uv1(1.0f, 0.0f), uv2(1.0f, 1.0f);
+// Returns false when the reference rejects the hit as degenerate (triangle.rs:567-572).
+inline bool triangle_geometry(V3 p0, V3 p1, V3 p2, Float b0, Float b1, Float b2, const TriAttr& at, TriGeom* g) {
+    P2 uv0(0.0f, 0.0f), uv1(1.0f, 0.0f), uv2(1.0f, 1.0f);
+    if (at.uv) { uv0 = P2(at.uv[0], at.uv[1]); uv1 = P2(at.uv[2], at.uv[3]); uv2 = P2(at.uv[4], at.uv[5]); }
     Float duv02x = uv0.x - uv2.x, duv02y = uv0.y - uv2.y;
     Float duv12x = uv1.x - uv2.x, duv12y = uv1.y - uv2.y;
     V3 dp02 = p0 - p2, dp12 = p1 - p2;
@@ -321,8 +330,34 @@ inline bool triangle_geometry(V3 p0, V3 p1, V3 p2, Float b0, Float b1, Float b2,
     g->dpdu = dpdu;
     g->dpdv = dpdv;
     V3 n = normalize(cross(dp02, dp12));  // triangle.rs:625
-    if (flip) n = -n;
+    if (at.flip) n = -n;
     g->n = n;
+    g->shading_n = n;
+    g->shading_dpdu = dpdu;
+    if (at.n || at.s) {  // triangle.rs:631-721
+        V3 ns = n;
+        if (at.n) {
+            V3 ns2 = b0 * V3(at.n[0], at.n[1], at.n[2]) + b1 * V3(at.n[3], at.n[4], at.n[5]) + b2 * V3(at.n[6], at.n[7], at.n[8]);
+            if (length_squared(ns2) > 0.0f) ns = normalize(ns2);
+        }
+        V3 ss = normalize(dpdu);
+        if (at.s) {
+            V3 ss2 = b0 * V3(at.s[0], at.s[1], at.s[2]) + b1 * V3(at.s[3], at.s[4], at.s[5]) + b2 * V3(at.s[6], at.s[7], at.s[8]);
+            if (length_squared(ss2) > 0.0f) ss = normalize(ss2);
+        }
+        V3 ts = cross(ss, ns);
+        if (length_squared(ts) > 0.0f) {
+            ts = normalize(ts);
+            ss = cross(ts, ns);
+        } else {
+            coordinate_system(ns, &ss, &ts);
+        }
+        if (at.reverse) ts = -ts;
+        // SurfaceInteraction::set_shading_geometry(ss, ts, .., orientation_is_authoritative = true), surface_interaction.rs:152-173
+        g->shading_n = normalize(cross(ss, ts));
+        g->n = face_forward(g->n, g->shading_n);
+        g->shading_dpdu = ss;
+    }
     return true;
 }
 
@@ -332,6 +367,10 @@ enum : uint32_t {
     PRIM_FLIP_NORMAL = 1u,        // reverse_orientation ^ transform_swaps_handedness
     PRIM_ALPHA_ZERO = 2u,         // constant alpha texture evaluates to exactly 0
     PRIM_SHADOW_ALPHA_ZERO = 4u,  // constant shadowalpha texture evaluates to exactly 0
+    PRIM_REVERSE_ORIENTATION = 8u,  // reverse_orientation alone (flips the shading bitangent, triangle.rs:714-716)
+    PRIM_HAS_UV = 16u,            // the primitive's mesh has "uv"/"st" (tri_uvs holds its three uvs)
+    PRIM_HAS_NORMALS = 32u,       // ... has "N" (tri_normals)
+    PRIM_HAS_TANGENTS = 64u,      // ... has "S" (tri_tangents)
 };
 
 // Flattened accelerator: nodes + triangles in ordered_prims order.
@@ -340,8 +379,19 @@ struct Accel {
     std::vector<uint32_t> ordered;     // ordered position -> original primitive index
     std::vector<Float> verts;          // 9 floats per ORIGINAL primitive
     std::vector<uint32_t> flags;       // per ORIGINAL primitive
+    std::vector<Float> uvs, normals, tangents;  // optional: 6 / 9 / 9 floats per ORIGINAL primitive (empty = the mesh has none)
     V3 vert(size_t prim, int k) const { const Float* v = &verts[9 * prim + 3 * k]; return V3(v[0], v[1], v[2]); }
     uint32_t flag(size_t prim) const { return flags.empty() ? 0u : flags[prim]; }
+    TriAttr attr(size_t prim) const {
+        TriAttr at;
+        const uint32_t fl = flag(prim);
+        if (!uvs.empty() && (fl & PRIM_HAS_UV)) at.uv = &uvs[6 * prim];
+        if (!normals.empty() && (fl & PRIM_HAS_NORMALS)) at.n = &normals[9 * prim];
+        if (!tangents.empty() && (fl & PRIM_HAS_TANGENTS)) at.s = &tangents[9 * prim];
+        at.flip = (fl & PRIM_FLIP_NORMAL) != 0;
+        at.reverse = (fl & PRIM_REVERSE_ORIENTATION) != 0;
+        return at;
+    }
 };
 
 struct HitRecord {
@@ -364,7 +414,7 @@ inline bool prim_intersect(const Accel& a, uint32_t prim, const Ray& r, TriHit* 
     if (!triangle_test(r, p0, p1, p2, th)) return false;
     TriGeom g;
     uint32_t fl = a.flag(prim);
-    if (!triangle_geometry(p0, p1, p2, th->b0, th->b1, th->b2, (fl & PRIM_FLIP_NORMAL) != 0, &g)) return false;
+    if (!triangle_geometry(p0, p1, p2, th->b0, th->b1, th->b2, a.attr(prim), &g)) return false;
     if (fl & PRIM_ALPHA_ZERO) return false;  // triangle.rs:587-607
     return true;
 }
@@ -375,7 +425,7 @@ inline bool prim_intersect_p(const Accel& a, uint32_t prim, const Ray& r) {
     if (!triangle_test(r, p0, p1, p2, &th)) return false;
     TriGeom g;
     uint32_t fl = a.flag(prim);
-    if (!triangle_geometry(p0, p1, p2, th.b0, th.b1, th.b2, false, &g)) return false;
+    if (!triangle_geometry(p0, p1, p2, th.b0, th.b1, th.b2, a.attr(prim), &g)) return false;
     if (fl & (PRIM_ALPHA_ZERO | PRIM_SHADOW_ALPHA_ZERO)) return false;
     return true;
 }

@@ -154,7 +154,25 @@ void* orc_accel_create(const void* nodes, int64_t n_nodes, const uint32_t* order
     if (flags) a->flags.assign(flags, flags + n_prims);
     return a;
 }
+// Optional "uv"/"st" of the meshes (6 floats per primitive; flags carry PRIM_HAS_UV): they enter the traversal through the
+// degenerate-hit rejection of triangle.rs:551-572.
+void orc_accel_set_uvs(void* accel, const float* uvs, int64_t n_prims) {
+    Accel* a = (Accel*)accel;
+    a->uvs.assign(uvs, uvs + 6 * n_prims);
+}
 void orc_accel_destroy(void* a) { delete (Accel*)a; }
+// Hit geometry of a triangle at barycentrics b (triangle.rs:547-725).  attrs: uv6 / n9 / s9 may be null.
+// out: p(3) p_error(3) n(3) dpdu(3) dpdv(3) shading_n(3) shading_dpdu(3) = 21 floats.  Returns 0 for a degenerate hit.
+int orc_triangle_geometry(const float* verts9, const float* b3, const float* uv6, const float* n9, const float* s9, int flip, int reverse, float* out21) {
+    V3 p0(verts9[0], verts9[1], verts9[2]), p1(verts9[3], verts9[4], verts9[5]), p2(verts9[6], verts9[7], verts9[8]);
+    TriAttr at;
+    at.uv = uv6; at.n = n9; at.s = s9; at.flip = flip != 0; at.reverse = reverse != 0;
+    TriGeom g;
+    if (!triangle_geometry(p0, p1, p2, b3[0], b3[1], b3[2], at, &g)) return 0;
+    const V3 v[7] = {g.p, g.p_error, g.n, g.dpdu, g.dpdv, g.shading_n, g.shading_dpdu};
+    for (int i = 0; i < 7; ++i) { out21[3 * i] = v[i].x; out21[3 * i + 1] = v[i].y; out21[3 * i + 2] = v[i].z; }
+    return 1;
+}
 
 // Closest hit over a batch.  counters (optional): 2 x u32 per ray = nodes
 // tested, triangles tested (SURVEY §8d algorithmic-bytes accounting).
@@ -197,7 +215,7 @@ int orc_triangle_intersect(const float* ray8, const float* verts9, float* out4) 
     V3 p0(verts9[0], verts9[1], verts9[2]), p1(verts9[3], verts9[4], verts9[5]), p2(verts9[6], verts9[7], verts9[8]);
     if (!triangle_test(r, p0, p1, p2, &th)) return 0;
     TriGeom g;
-    if (!triangle_geometry(p0, p1, p2, th.b0, th.b1, th.b2, false, &g)) return 0;
+    if (!triangle_geometry(p0, p1, p2, th.b0, th.b1, th.b2, TriAttr(), &g)) return 0;
     out4[0] = th.t; out4[1] = th.b0; out4[2] = th.b1; out4[3] = th.b2;
     return 1;
 }

@@ -550,6 +550,9 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
     s->accel.ordered.assign(d->ordered_prims, d->ordered_prims + n_top);
     s->accel.verts.assign(d->tri_verts, d->tri_verts + 9 * d->n_prims);
     if (d->prim_flags) s->accel.flags.assign(d->prim_flags, d->prim_flags + d->n_prims);
+    if (d->tri_uvs) s->accel.uvs.assign(d->tri_uvs, d->tri_uvs + 6 * d->n_prims);
+    if (d->tri_normals) s->accel.normals.assign(d->tri_normals, d->tri_normals + 9 * d->n_prims);
+    if (d->tri_tangents) s->accel.tangents.assign(d->tri_tangents, d->tri_tangents + 9 * d->n_prims);
     if (d->prim_material) s->prim_material.assign(d->prim_material, d->prim_material + d->n_prims);
     if (d->prim_light) s->prim_light.assign(d->prim_light, d->prim_light + d->n_prims);
     if (d->n_objects > 0) {
@@ -564,6 +567,7 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
             a.ordered.assign(ob.ordered_prims, ob.ordered_prims + ob.n_prims);
             a.verts.assign(d->tri_verts + 9 * ob.first_prim, d->tri_verts + 9 * (ob.first_prim + ob.n_prims));
             if (d->prim_flags) a.flags.assign(d->prim_flags + ob.first_prim, d->prim_flags + ob.first_prim + ob.n_prims);
+            if (d->tri_uvs) a.uvs.assign(d->tri_uvs + 6 * ob.first_prim, d->tri_uvs + 6 * (ob.first_prim + ob.n_prims));
             s->top.objects.push_back(a);
             s->top.object_first_prim.push_back(ob.first_prim);
         }
@@ -661,11 +665,11 @@ inline bool scene_intersect(RenderScene& sc, Ray& ray, SurfHit* sh) {
     else if (!bvh_intersect(sc.accel, ray, &h)) return false;
     V3 p0 = sc.accel.vert(h.prim, 0), p1 = sc.accel.vert(h.prim, 1), p2 = sc.accel.vert(h.prim, 2);
     TriGeom g;
-    triangle_geometry(p0, p1, p2, h.b0, h.b1, h.b2, (sc.accel.flag(h.prim) & PRIM_FLIP_NORMAL) != 0, &g);
+    triangle_geometry(p0, p1, p2, h.b0, h.b1, h.b2, sc.accel.attr(h.prim), &g);
     sh->prim = h.prim;
     sh->time = ray.time;
     if (inst < 0) {
-        sh->p = g.p; sh->p_error = g.p_error; sh->n = g.n; sh->shading_n = g.n; sh->dpdu = g.dpdu;
+        sh->p = g.p; sh->p_error = g.p_error; sh->n = g.n; sh->shading_n = g.shading_n; sh->dpdu = g.shading_dpdu;
         V3 wo = -d_in;
         Float l2 = length_squared(wo);
         sh->wo = (l2 == 0.0f) ? wo : wo / std::sqrt(l2);
@@ -680,15 +684,15 @@ inline bool scene_intersect(RenderScene& sc, Ray& ray, SurfHit* sh) {
     bool identity = true;
     { M4 id; for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) if (I.i2w.m[a][b] != id.m[a][b]) identity = false; }
     if (identity) {  // transformed_primitive.rs:57-59
-        sh->p = g.p; sh->p_error = g.p_error; sh->n = g.n; sh->shading_n = g.n; sh->dpdu = g.dpdu; sh->wo = wo_i;
+        sh->p = g.p; sh->p_error = g.p_error; sh->n = g.n; sh->shading_n = g.shading_n; sh->dpdu = g.shading_dpdu; sh->wo = wo_i;
         return true;
     }
     sh->p = xf_point_abs_err(I.i2w, g.p, g.p_error, &sh->p_error);
     sh->wo = normalize(xf_vector(I.i2w, wo_i));
     sh->n = normalize(xf_normal(I.w2i, g.n));
-    V3 sn = normalize(xf_normal(I.w2i, g.n));
+    V3 sn = normalize(xf_normal(I.w2i, g.shading_n));
     sh->shading_n = face_forward(sn, sh->n);
-    sh->dpdu = xf_vector(I.i2w, g.dpdu);
+    sh->dpdu = xf_vector(I.i2w, g.shading_dpdu);
     return true;
 }
 inline bool scene_intersect_p(RenderScene& sc, const Ray& ray) {
@@ -808,7 +812,11 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
         P2 b = uniform_sample_triangle(u);
         V3 p = b.x * p0 + b.y * p1 + (1.0f - b.x - b.y) * p2;
         V3 n = normalize(cross(p1 - p0, p2 - p0));
-        if (sc.accel.flag(l.prim) & PRIM_FLIP_NORMAL) n = -1.0f * n;
+        const TriAttr at = sc.accel.attr(l.prim);
+        if (at.n) {  // triangle.rs:931-937: orient like intersect() does
+            V3 ns = b.x * V3(at.n[0], at.n[1], at.n[2]) + b.y * V3(at.n[3], at.n[4], at.n[5]) + (1.0f - b.x - b.y) * V3(at.n[6], at.n[7], at.n[8]);
+            n = face_forward(n, ns);
+        } else if (at.flip) n = -1.0f * n;
         V3 pas = vabs(b.x * p0) + vabs(b.y * p1) + vabs((1.0f - b.x - b.y) * p2);
         V3 p_err = gamma(6) * V3(pas.x, pas.y, pas.z);
         Float pdf = 1.0f / sc.light_area[li];
@@ -858,7 +866,7 @@ inline Float light_pdf_li(const RenderScene& sc, int li, const SurfHit& hit, V3 
         TriHit th;
         if (!triangle_test(ray, p0, p1, p2, &th)) return 0.0f;
         TriGeom g;
-        if (!triangle_geometry(p0, p1, p2, th.b0, th.b1, th.b2, (sc.accel.flag(l.prim) & PRIM_FLIP_NORMAL) != 0, &g)) return 0.0f;
+        if (!triangle_geometry(p0, p1, p2, th.b0, th.b1, th.b2, sc.accel.attr(l.prim), &g)) return 0.0f;
         Float pdf = distance_squared(hit.p, g.p) / (abs_dot(g.n, -wi) * sc.light_area[li]);
         return std::isinf(pdf) ? 0.0f : pdf;
     }

@@ -25,6 +25,7 @@ LIB_PATH = os.path.join(_HERE, "libb200pt.so")
 
 MISS = 0xFFFFFFFF
 PRIM_FLIP_NORMAL, PRIM_ALPHA_ZERO, PRIM_SHADOW_ALPHA_ZERO = 1, 2, 4
+PRIM_REVERSE_ORIENTATION, PRIM_HAS_UV, PRIM_HAS_NORMALS, PRIM_HAS_TANGENTS = 8, 16, 32, 64
 MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_METAL = 0, 1, 2, 3
 LIGHT_POINT, LIGHT_AREA, LIGHT_INFINITE = 0, 1, 2
 SAMPLER_HALTON, SAMPLER_ZEROTWO = 0, 1
@@ -84,7 +85,8 @@ class SceneDesc(C.Structure):
                 ("prim_flags", C.c_void_p), ("prim_material", C.c_void_p), ("prim_light", C.c_void_p), ("n_prims", C.c_int64),
                 ("materials", C.c_void_p), ("n_materials", C.c_int32), ("lights", C.c_void_p), ("n_lights", C.c_int32),
                 ("camera", Camera), ("film", Film), ("sampler", Sampler), ("integrator", Integrator),
-                ("n_top_tris", C.c_int64), ("objects", C.c_void_p), ("n_objects", C.c_int32), ("instances", C.c_void_p), ("n_instances", C.c_int32)]
+                ("n_top_tris", C.c_int64), ("objects", C.c_void_p), ("n_objects", C.c_int32), ("instances", C.c_void_p), ("n_instances", C.c_int32),
+                ("tri_uvs", C.c_void_p), ("tri_normals", C.c_void_p), ("tri_tangents", C.c_void_p)]
 
 
 _lib = None
@@ -106,6 +108,7 @@ def lib():
     L.b200pt_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_triangle_bounds.argtypes = [vp, i64, vp]
     L.b200pt_accel_create.argtypes = [vp, i64, vp, vp, vp, i64, C.POINTER(vp)]
+    L.b200pt_accel_create_uv.argtypes = [vp, i64, vp, vp, vp, vp, i64, C.POINTER(vp)]
     L.b200pt_accel_destroy.argtypes = [vp]
     L.b200pt_accel_destroy.restype = None
     L.b200pt_accel_world_bound.argtypes = [vp, vp]
@@ -178,19 +181,23 @@ class BVHAccel:
     for triangle primitives given as an (n, 9) float32 array of world-space vertices.
     """
 
-    def __init__(self, tri_verts, nodes, ordered_prims, prim_flags=None):
+    def __init__(self, tri_verts, nodes, ordered_prims, prim_flags=None, tri_uvs=None):
         init(_inited if _inited is not None else 0)
         self.tri_verts = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
         self.nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
         self.ordered_prims = np.ascontiguousarray(ordered_prims, dtype=np.uint32)
         self.prim_flags = None if prim_flags is None else np.ascontiguousarray(prim_flags, dtype=np.uint32)
+        self.tri_uvs = None if tri_uvs is None else np.ascontiguousarray(tri_uvs, dtype=np.float32).reshape(-1, 6)
+        if self.tri_uvs is not None:  # every primitive of a mesh with "uv"/"st" uses them
+            fl = np.zeros(self.tri_verts.shape[0], dtype=np.uint32) if self.prim_flags is None else self.prim_flags
+            self.prim_flags = fl | np.uint32(PRIM_HAS_UV)
         h = C.c_void_p()
-        _check(lib().b200pt_accel_create(_ptr(self.nodes), len(self.nodes), _ptr(self.ordered_prims), _ptr(self.tri_verts),
-                                         _ptr(self.prim_flags), self.tri_verts.shape[0], C.byref(h)), "b200pt_accel_create")
+        _check(lib().b200pt_accel_create_uv(_ptr(self.nodes), len(self.nodes), _ptr(self.ordered_prims), _ptr(self.tri_verts), _ptr(self.tri_uvs),
+                                            _ptr(self.prim_flags), self.tri_verts.shape[0], C.byref(h)), "b200pt_accel_create_uv")
         self._h = h
 
     @classmethod
-    def from_params(cls, params, tri_verts, prim_flags=None):
+    def from_params(cls, params, tri_verts, prim_flags=None, tri_uvs=None):
         split = params.get("splitmethod", "sah")
         if split != "sah":
             # hlbvh / middle / equal are outside this path (SURVEY.md §2 row 1)
@@ -198,7 +205,7 @@ class BVHAccel:
         max_prims = int(params.get("maxnodeprims", 4)) & 0xFF
         tv = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
         nodes, ordered = build_bvh_sah(triangle_bounds(tv), max_prims)
-        return cls(tv, nodes, ordered, prim_flags)
+        return cls(tv, nodes, ordered, prim_flags, tri_uvs)
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:

@@ -45,8 +45,14 @@ struct BatchScratch {
 };
 static BatchScratch g_scratch;
 
+// Fourth float4 of a triangle record: uv0 - uv2, uv1 - uv2 (get_uvs, triangle.rs:384-394, 551-552).
+float4 record_duv(const float* uv6) {
+    if (!uv6) return make_float4(0.0f - 1.0f, 0.0f - 1.0f, 1.0f - 1.0f, 0.0f - 1.0f);
+    return make_float4(uv6[0] - uv6[4], uv6[1] - uv6[5], uv6[2] - uv6[4], uv6[3] - uv6[5]);
+}
+
 int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered, const float* tri_verts,
-                       const uint32_t* flags, int64_t n_prims, AccelImpl* a) {
+                       const uint32_t* flags, int64_t n_prims, AccelImpl* a, const float* tri_uvs) {
     a->n_nodes = n_nodes;
     a->n_prims = n_prims;
     std::memset(&a->dev, 0, sizeof(a->dev));
@@ -99,7 +105,7 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
         tris[(size_t)j * 4 + 0] = make_float4(v[0], v[1], v[2], v[3]);
         tris[(size_t)j * 4 + 1] = make_float4(v[4], v[5], v[6], v[7]);
         tris[(size_t)j * 4 + 2] = make_float4(v[8], fp, ff, fz);
-        tris[(size_t)j * 4 + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        tris[(size_t)j * 4 + 3] = record_duv(tri_uvs && (fl & B200PT_PRIM_HAS_UV) ? tri_uvs + 6 * (size_t)p : nullptr);
     }
     for (int64_t i = 0; i < n_nodes; ++i) {
         if (nodes[i].n_primitives == 0) continue;
@@ -190,6 +196,11 @@ int b200pt_init(int device) {
 
 int b200pt_accel_create(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered_prims, const float* tri_verts,
                         const uint32_t* prim_flags, int64_t n_prims, b200pt_accel** out) {
+    return b200pt_accel_create_uv(nodes, n_nodes, ordered_prims, tri_verts, nullptr, prim_flags, n_prims, out);
+}
+
+int b200pt_accel_create_uv(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered_prims, const float* tri_verts,
+                           const float* tri_uvs, const uint32_t* prim_flags, int64_t n_prims, b200pt_accel** out) {
     if (!out) { b200pt_set_error("b200pt_accel_create: out is null"); return B200PT_ERR_INVALID; }
     *out = nullptr;
     int rc = require_device();
@@ -200,7 +211,7 @@ int b200pt_accel_create(const b200pt_bvh_node* nodes, int64_t n_nodes, const uin
     }
     B2_CUDA(cudaSetDevice(g_device));
     b200pt_accel* a = new b200pt_accel();
-    rc = accel_build_device(nodes, n_nodes, ordered_prims, tri_verts, prim_flags, n_prims, &a->impl);
+    rc = accel_build_device(nodes, n_nodes, ordered_prims, tri_verts, prim_flags, n_prims, &a->impl, tri_uvs);
     if (rc) { accel_free_device(&a->impl); delete a; return rc; }
     *out = a;
     return B200PT_OK;

@@ -33,6 +33,9 @@ namespace b2 {
 struct DeviceScene {
     DeviceAccel accel;
     const float4* prim_verts;  // 3 float4 per ORIGINAL primitive: (p0, bits material), (p1, bits light or -1), (p2, bits flags)
+    const float4* prim_duv;    // optional (meshes with uvs): uv0 - uv2, uv1 - uv2 per ORIGINAL primitive
+    const float* prim_n;       // optional (meshes with N): 9 floats per ORIGINAL primitive
+    const float* prim_s;       // optional (meshes with S): 9 floats per ORIGINAL primitive
     const DMaterial* materials;
     const DLight* lights;
     const int* infinite_lights;
@@ -236,7 +239,10 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
     V3 hit_wo = (l2 == 0.0f) ? wo_raw : wo_raw / sqrtf(l2);
     if (found) {
         load_prim(S, prim, &p0, &p1, &p2, &mat, &alight, &pflags);
-        sh = triangle_surface3(p0, p1, p2, hit.z, hit.w, hb2, (pflags & 1u) != 0);
+        const float4 duv = (S.prim_duv && (pflags & B200PT_PRIM_HAS_UV)) ? ldg4(S.prim_duv + prim) : default_duv();
+        const float* vn = (S.prim_n && (pflags & B200PT_PRIM_HAS_NORMALS)) ? S.prim_n + 9ll * prim : nullptr;
+        const float* vs = (S.prim_s && (pflags & B200PT_PRIM_HAS_TANGENTS)) ? S.prim_s + 9ll * prim : nullptr;
+        sh = triangle_surface(p0, p1, p2, hit.z, hit.w, hb2, pflags, duv, vn, vs);
         const int inst = S.instances ? W.hit_inst[slot] : -1;
         if (inst >= 0) {
             // The hit was built in instance space from the instance-space ray, then
@@ -262,6 +268,9 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
                 const float* mi = I.w2i;  // transform_normal: inverse transpose (transform.rs:439-446)
                 V3 n = sh.n;
                 sh.n = normalize(mk(mi[0] * n.x + mi[4] * n.y + mi[8] * n.z, mi[1] * n.x + mi[5] * n.y + mi[9] * n.z, mi[2] * n.x + mi[6] * n.y + mi[10] * n.z));
+                V3 sn = sh.ns;  // si.shading.n = transform_normal(shading.n).normalize().face_forward(hit.n)
+                sn = normalize(mk(mi[0] * sn.x + mi[4] * sn.y + mi[8] * sn.z, mi[1] * sn.x + mi[5] * sn.y + mi[9] * sn.z, mi[2] * sn.x + mi[6] * sn.y + mi[10] * sn.z));
+                sh.ns = face_forward(sn, sh.n);
                 V3 du = sh.dpdu;
                 sh.dpdu = mk(m[0] * du.x + m[1] * du.y + m[2] * du.z, m[4] * du.x + m[5] * du.y + m[6] * du.z, m[8] * du.x + m[9] * du.y + m[10] * du.z);
             }
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
     }
     // BSDF::new frame (bsdf.rs:100-120)
     BSDF bsdf;
-    bsdf.ns = sh.n; bsdf.ng = sh.n;
+    bsdf.ns = sh.ns; bsdf.ng = sh.n;
     bsdf.ss = normalize(sh.dpdu);
     bsdf.ts = cross(bsdf.ns, bsdf.ss);
     bsdf.m = S.materials + mat;
@@ -306,6 +315,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
             RGB Li = rgb1(0.0f);
             V3 q0 = mk(0, 0, 0), q1 = q0, q2 = q0;  // area light triangle
             bool lflip = false;
+            uint32_t lflags = 0;
             if (light.type == LT_POINT) {  // point.rs:83-94
                 V3 pl = mk(light.pos[0], light.pos[1], light.pos[2]);
                 wi = normalize(pl - sh.p);
@@ -317,6 +327,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
                 int m2, l2i; uint32_t f2;
                 load_prim(S, (uint32_t)light.prim, &q0, &q1, &q2, &m2, &l2i, &f2);
                 lflip = (f2 & 1u) != 0;
+                lflags = f2;
                 // Triangle::sample (triangle.rs:918-949) + Shape::sample_solid_angle (shape.rs:64-79)
                 float su0 = sqrtf(u_light.x);
                 float bx = 1.0f - su0, by = u_light.y * su0;
@@ -362,7 +373,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
             }
             float scattering_pdf = 0.0f;
             if (li_valid && light_pdf > 0.0f && !is_black(Li)) {
-                RGB f = bsdf_f(bsdf, hit_wo, wi, kNoSpec) * abs_dot(wi, sh.n);
+                RGB f = bsdf_f(bsdf, hit_wo, wi, kNoSpec) * abs_dot(wi, sh.ns);
                 scattering_pdf = bsdf_pdf(bsdf, hit_wo, wi, kNoSpec);
                 if (!is_black(f)) {
                     // VisibilityTester -> Hit::spawn_ray_to_hit (interaction/mod.rs:212-223)
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
             if (light.type != LT_POINT) {
                 BxDFSample bs = bsdf_sample_f(bsdf, hit_wo, u_scatter, kNoSpec);
                 V3 wi2 = bs.wi;
-                RGB f = bs.f * abs_dot(wi2, sh.n);
+                RGB f = bs.f * abs_dot(wi2, sh.ns);
                 bool sampled_specular = (bs.type & BSDF_SPECULAR) != 0;
                 if (!is_black(f) && bs.pdf > 0.0f) {
                     float weight = 1.0f;
@@ -395,8 +406,9 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
                             TriCtx tc = make_tri_ctx(wi2.x, wi2.y, wi2.z);
                             float t, c0, c1, c2;
                             lp = 0.0f;
-                            if (triangle_test(ro, tc, __int_as_float(0x7f800000), q0, q1, q2, &t, &c0, &c1, &c2) && triangle_nondegenerate(q0, q1, q2)) {
-                                SurfHit lh = triangle_surface3(q0, q1, q2, c0, c1, c2, lflip);
+                            const float4 lduv = (S.prim_duv && (lflags & B200PT_PRIM_HAS_UV)) ? ldg4(S.prim_duv + light.prim) : default_duv();
+                            if (triangle_test(ro, tc, __int_as_float(0x7f800000), q0, q1, q2, &t, &c0, &c1, &c2) && triangle_nondegenerate(q0, q1, q2, lduv)) {
+                                SurfHit lh = triangle_surface(q0, q1, q2, c0, c1, c2, lflags, lduv, nullptr, nullptr);
                                 lp = distance_squared(sh.p, lh.p) / (abs_dot(lh.n, -wi2) * light.area);
                                 if (isinf(lp)) lp = 0.0f;
                             }
@@ -442,7 +454,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
         W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
         return;
     }
-    beta = beta * (bs.f * abs_dot(bs.wi, sh.n) / bs.pdf);
+    beta = beta * (bs.f * abs_dot(bs.wi, sh.ns) / bs.pdf);
     specular_bounce = (bs.type & BSDF_SPECULAR) != 0;
     if ((bs.type & BSDF_SPECULAR) && (bs.type & BSDF_TRANSMISSION)) {
         float eta = 1.0f;  // BSDF::new(.., None): every in-scope material leaves bsdf.eta at 1.0
@@ -913,7 +925,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         D.accel = s->accel2.dev.top;
         D.instances = s->accel2.dev.instances;
     } else {
-        rc = accel_build_device(d->nodes, d->n_nodes, d->ordered_prims, d->tri_verts, d->prim_flags, d->n_prims, &s->accel);
+        rc = accel_build_device(d->nodes, d->n_nodes, d->ordered_prims, d->tri_verts, d->prim_flags, d->n_prims, &s->accel, d->tri_uvs);
         if (rc) return fail(rc);
         D.accel = s->accel.dev;
     }
@@ -936,6 +948,33 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         pv[3 * i + 2] = make_float4(v[6], v[7], v[8], ff);
     }
     if ((rc = dev_upload(s, pv, &D.prim_verts))) return fail(rc);
+    // optional vertex attributes (triangle.rs:384-394, 631-721)
+    bool any_uv = false, any_n = false, any_s = false;
+    for (int64_t i = 0; i < d->n_prims && d->prim_flags; ++i) {
+        const uint32_t fl = d->prim_flags[i];
+        any_uv |= (fl & B200PT_PRIM_HAS_UV) != 0; any_n |= (fl & B200PT_PRIM_HAS_NORMALS) != 0; any_s |= (fl & B200PT_PRIM_HAS_TANGENTS) != 0;
+        if ((fl & B200PT_PRIM_HAS_NORMALS) && d->prim_light && d->prim_light[i] >= 0) {
+            b200pt_set_error("b200pt_scene_create: area light on a mesh with vertex normals is not supported");
+            return fail(B200PT_ERR_UNSUPPORTED);
+        }
+    }
+    if ((any_uv && !d->tri_uvs) || (any_n && !d->tri_normals) || (any_s && !d->tri_tangents)) {
+        b200pt_set_error("b200pt_scene_create: a primitive flag announces uvs / normals / tangents but the array is NULL");
+        return fail(B200PT_ERR_INVALID);
+    }
+    if (any_uv) {
+        std::vector<float4> duv((size_t)d->n_prims);
+        for (int64_t i = 0; i < d->n_prims; ++i) duv[(size_t)i] = record_duv((d->prim_flags[i] & B200PT_PRIM_HAS_UV) ? d->tri_uvs + 6 * i : nullptr);
+        if ((rc = dev_upload(s, duv, &D.prim_duv))) return fail(rc);
+    }
+    if (any_n) {
+        std::vector<float> vn(d->tri_normals, d->tri_normals + 9 * d->n_prims);
+        if ((rc = dev_upload(s, vn, &D.prim_n))) return fail(rc);
+    }
+    if (any_s) {
+        std::vector<float> vs(d->tri_tangents, d->tri_tangents + 9 * d->n_prims);
+        if ((rc = dev_upload(s, vs, &D.prim_s))) return fail(rc);
+    }
 
     std::vector<DMaterial> mats;
     for (int i = 0; i < d->n_materials; ++i) mats.push_back(make_material(d->materials[i]));

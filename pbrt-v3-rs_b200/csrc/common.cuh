@@ -46,7 +46,8 @@ struct AccelImpl {
 };
 
 int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered, const float* tri_verts,
-                       const uint32_t* flags, int64_t n_prims, AccelImpl* out);
+                       const uint32_t* flags, int64_t n_prims, AccelImpl* out, const float* tri_uvs = nullptr);
+float4 record_duv(const float* uv6);  // uv0 - uv2, uv1 - uv2; uv6 == nullptr: the default uvs
 void accel_free_device(AccelImpl* a);
 
 // Kernel launchers (traverse_kernels.cu)

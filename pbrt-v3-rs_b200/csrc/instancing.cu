@@ -91,8 +91,9 @@ B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, in
         } else {
             long long first = (long long)(~cur);
             V3 p0, p1, p2;
+            float4 duv;
             uint32_t prim, flags, leaf_n;
-            load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n);
+            load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
             for (uint32_t i = 0;;) {
                 if (flags & 0x80000000u) {  // TransformedPrimitive
                     const float4* T = A2.inst_trav + 6ll * prim;
@@ -114,7 +115,7 @@ B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, in
                     }
                 } else {
                     float t, b0, b1, b2;
-                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2)) {
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
                         if (ANY) {
                             if (!(flags & 6u)) return true;
                         } else if (!(flags & 2u)) {
@@ -127,7 +128,7 @@ B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, in
                 }
                 if (++i >= leaf_n) break;
                 uint32_t dummy;
-                load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy);
+                load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy, &duv);
             }
         }
         for (;;) {
@@ -273,9 +274,10 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
                 }
             } else if (cur < 0 && cur != kIdle) {
                 V3 p0, p1, p2;
+                float4 duv;
                 uint32_t prim, flags, leaf_n;
                 if (tri_left == 0) tri_i = (long long)(~cur);
-                load_tri(A.tris, tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n);
+                load_tri(A.tris, tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
                 if (tri_left == 0) tri_left = leaf_n;
                 ++tri_i;
                 --tri_left;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
                     } else if (tri_left == 0) retire = true;
                 } else {
                     float t, b0, b1, b2;
-                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2)) {
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
                         if (ANY) {
                             if (!(flags & 6u)) { hit = true; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
                         } else if (!(flags & 2u)) {
@@ -438,7 +440,7 @@ int accel2_build_device(const b200pt_scene_desc* d, Accel2Impl* a) {
         q[0] = make_float4(v[0], v[1], v[2], v[3]);
         q[1] = make_float4(v[4], v[5], v[6], v[7]);
         q[2] = make_float4(v[8], fp, ff, fz);
-        q[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        q[3] = record_duv(d->tri_uvs && (fl & B200PT_PRIM_HAS_UV) ? d->tri_uvs + 6 * (size_t)gp : nullptr);
     };
     const int64_t n_top = d->n_top_tris + d->n_instances;
     std::memset(&a->dev, 0, sizeof(a->dev));

@@ -660,17 +660,26 @@ B2_D Ray32 camera_ray(const DCamera& c, P2 p_film, float time_u, P2 p_lens) {
     return r;
 }
 
-// ---- hit geometry: Triangle::intersect tail (shapes/src/triangle.rs:547-629) -----------
+// ---- hit geometry: Triangle::intersect tail (shapes/src/triangle.rs:547-725) -----------
 struct SurfHit {
-    V3 p, p_error, n, dpdu;  // shading.n == n, shading.dpdu == dpdu (no vertex normals / bump)
+    V3 p, p_error, n;   // Hit::{p, p_error, n}
+    V3 ns, dpdu;        // Shading::{n, dpdu} (== n and der.dpdu unless the mesh has N / S)
 };
-B2_D SurfHit triangle_surface3(V3 p0, V3 p1, V3 p2, float b0, float b1, float b2, bool flip) {
+// duv = {uv0 - uv2, uv1 - uv2}; nrm / tan: the three vertex normals / tangents (9 floats) or null.
+// flags: B200PT_PRIM_FLIP_NORMAL, B200PT_PRIM_REVERSE_ORIENTATION.
+B2_D SurfHit triangle_surface(V3 p0, V3 p1, V3 p2, float b0, float b1, float b2, uint32_t flags, float4 duv, const float* nrm, const float* tan) {
     SurfHit s;
     V3 dp02 = p0 - p2, dp12 = p1 - p2;
-    // default uvs (0,0),(1,0),(1,1): duv02 = (-1,-1), duv12 = (0,-1), determinant = 1 (triangle.rs:384-394, 551-565)
-    V3 dpdu = ((-1.0f) * dp02 - (-1.0f) * dp12) * 1.0f;
-    V3 dpdv = (-(0.0f) * dp02 + (-1.0f) * dp12) * 1.0f;
-    if (length_squared(cross(dpdu, dpdv)) == 0.0f) {
+    const float duv02x = duv.x, duv02y = duv.y, duv12x = duv.z, duv12y = duv.w;
+    float determinant = duv02x * duv12y - duv02y * duv12x;
+    bool degenerate_uv = pabs(determinant) < 1e-8f;
+    V3 dpdu = mk(0.0f, 0.0f, 0.0f), dpdv = dpdu;
+    if (!degenerate_uv) {
+        float invdet = 1.0f / determinant;
+        dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+        dpdv = (-duv12x * dp02 + duv02x * dp12) * invdet;
+    }
+    if (degenerate_uv || length_squared(cross(dpdu, dpdv)) == 0.0f) {
         V3 ng = cross(p2 - p0, p1 - p0);
         coordinate_system(normalize(ng), &dpdu, &dpdv);
     }
@@ -680,10 +689,36 @@ B2_D SurfHit triangle_surface3(V3 p0, V3 p1, V3 p2, float b0, float b1, float b2
     s.p_error = kGamma7 * mk(xs, ys, zs);
     s.p = b0 * p0 + b1 * p1 + b2 * p2;
     V3 n = normalize(cross(dp02, dp12));
-    if (flip) n = -n;
+    if (flags & 1u) n = -n;
     s.n = n;
+    s.ns = n;
     s.dpdu = dpdu;
+    if (nrm || tan) {  // triangle.rs:631-721
+        V3 ns = n;
+        if (nrm) {
+            V3 ns2 = b0 * mk(nrm[0], nrm[1], nrm[2]) + b1 * mk(nrm[3], nrm[4], nrm[5]) + b2 * mk(nrm[6], nrm[7], nrm[8]);
+            if (length_squared(ns2) > 0.0f) ns = normalize(ns2);
+        }
+        V3 ss = normalize(dpdu);
+        if (tan) {
+            V3 ss2 = b0 * mk(tan[0], tan[1], tan[2]) + b1 * mk(tan[3], tan[4], tan[5]) + b2 * mk(tan[6], tan[7], tan[8]);
+            if (length_squared(ss2) > 0.0f) ss = normalize(ss2);
+        }
+        V3 ts = cross(ss, ns);
+        if (length_squared(ts) > 0.0f) {
+            ts = normalize(ts);
+            ss = cross(ts, ns);
+        } else {
+            coordinate_system(ns, &ss, &ts);
+        }
+        if (flags & 8u) ts = -ts;
+        // set_shading_geometry(ss, ts, .., orientation_is_authoritative = true), surface_interaction.rs:152-173
+        s.ns = normalize(cross(ss, ts));
+        s.n = face_forward(s.n, s.ns);
+        s.dpdu = ss;
+    }
     return s;
 }
+B2_D float4 default_duv() { return make_float4(0.0f - 1.0f, 0.0f - 1.0f, 1.0f - 1.0f, 0.0f - 1.0f); }
 
 }  // namespace b2

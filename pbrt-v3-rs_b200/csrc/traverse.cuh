@@ -18,7 +18,7 @@
 //     ordered triangle = ~code.
 //   * triangles in BVHAccel.primitives (leaf) order, 64 B = 2 x 256-bit loads:
 //        p0.xyz p1.xyz p2.xy | p2.z, bits(original primitive index), bits(flags),
-//        bits(leaf primitive count; valid in the first triangle of a leaf), 4 x pad
+//        bits(leaf primitive count; valid in the first triangle of a leaf), uv0 - uv2, uv1 - uv2
 //   Equivalence with the reference's "test the node when it is popped": the
 //   slab test of the far child is evaluated early, its entry distance is kept
 //   on the stack and re-compared with the (possibly shrunk) ray.t_max when the
@@ -180,27 +180,35 @@ B2_D bool triangle_test(V3 o, const TriCtx& c, float t_max, V3 p0, V3 p1, V3 p2,
     return true;
 }
 
-// triangle.rs:547-572 with the default uv parameterisation (0,0),(1,0),(1,1):
-// an accepted candidate is still rejected when its partial derivatives AND its
-// geometric normal are degenerate.  Returns false for "bogus" hits.
-B2_D bool triangle_nondegenerate(V3 p0, V3 p1, V3 p2) {
-    // duv02 = (-1,-1), duv12 = (0,-1), determinant = 1, invdet = 1
+// triangle.rs:547-572: an accepted candidate is still rejected when its partial derivatives AND its geometric normal
+// are degenerate.  The uvs (get_uvs, triangle.rs:384-394) enter only through duv = {uv0 - uv2, uv1 - uv2}, carried in
+// the fourth float4 of the triangle record ((-1,-1),(0,-1) for the default uvs).  Returns false for "bogus" hits.
+B2_D bool triangle_nondegenerate(V3 p0, V3 p1, V3 p2, float4 duv) {
+    const float duv02x = duv.x, duv02y = duv.y, duv12x = duv.z, duv12y = duv.w;
     V3 dp02 = p0 - p2, dp12 = p1 - p2;
-    V3 dpdu = ((-1.0f) * dp02 - (-1.0f) * dp12) * 1.0f;
-    V3 dpdv = (-(0.0f) * dp02 + (-1.0f) * dp12) * 1.0f;
-    if (length_squared(cross(dpdu, dpdv)) == 0.0f) {
+    float determinant = duv02x * duv12y - duv02y * duv12x;
+    bool degenerate_uv = pabs(determinant) < 1e-8f;
+    bool bad = degenerate_uv;
+    if (!degenerate_uv) {
+        float invdet = 1.0f / determinant;
+        V3 dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+        V3 dpdv = (-duv12x * dp02 + duv02x * dp12) * invdet;
+        bad = length_squared(cross(dpdu, dpdv)) == 0.0f;
+    }
+    if (bad) {
         V3 ng = cross(p2 - p0, p1 - p0);
         if (length_squared(ng) == 0.0f) return false;
     }
     return true;
 }
 
-B2_D void load_tri(const float4* tris, long long i, V3* p0, V3* p1, V3* p2, uint32_t* prim, uint32_t* flags, uint32_t* leaf_n) {
+B2_D void load_tri(const float4* tris, long long i, V3* p0, V3* p1, V3* p2, uint32_t* prim, uint32_t* flags, uint32_t* leaf_n, float4* duv) {
     float4 a, b, c, d;
     ldg8(tris + 4 * i, &a, &b);
     ldg8(tris + 4 * i + 2, &c, &d);
     *p0 = mk(a.x, a.y, a.z); *p1 = mk(a.w, b.x, b.y); *p2 = mk(b.z, b.w, c.x);
     *prim = __float_as_uint(c.y); *flags = __float_as_uint(c.z); *leaf_n = __float_as_uint(c.w);
+    *duv = d;
 }
 
 struct HitOut {
@@ -261,11 +269,12 @@ B2_D bool traverse_wide(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
         } else {
             long long first = (long long)(~cur);
             V3 p0, p1, p2;
+            float4 duv;
             uint32_t prim, flags, leaf_n;
-            load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n);
+            load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
             for (uint32_t i = 0;;) {
                 float t, b0, b1, b2;
-                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2)) {
+                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
                     if (ANY) {
                         if (!(flags & 6u)) return true;  // alpha / shadow-alpha == 0 reject (triangle.rs:886-899)
                     } else if (!(flags & 2u)) {          // alpha == 0 reject (triangle.rs:587-607)
@@ -276,7 +285,7 @@ B2_D bool traverse_wide(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
                 }
                 if (++i >= leaf_n) break;
                 uint32_t dummy;
-                load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy);
+                load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy, &duv);
             }
         }
         // pop
@@ -317,10 +326,11 @@ B2_D bool traverse_ref(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
             if (nprims > 0) {
                 for (uint32_t i = 0; i < nprims; ++i) {
                     V3 p0, p1, p2;
+                    float4 duv;
                     uint32_t prim, flags, dummy;
-                    load_tri(A.tris, (long long)offset + i, &p0, &p1, &p2, &prim, &flags, &dummy);
+                    load_tri(A.tris, (long long)offset + i, &p0, &p1, &p2, &prim, &flags, &dummy, &duv);
                     float t, b0, b1, b2;
-                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2)) {
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
                         if (ANY) {
                             if (!(flags & 6u)) return true;
                         } else if (!(flags & 2u)) {

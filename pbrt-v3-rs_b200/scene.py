@@ -144,6 +144,7 @@ class SceneDescription:
         self.accel_params = dict(splitmethod="sah", maxnodeprims=4)
         self.nodes = None
         self.ordered_prims = None
+        self.tri_uvs = self.tri_normals = self.tri_tangents = None  # optional (n, 6) / (n, 9) / (n, 9), rows of zeros for meshes without
         self.objects = []     # dicts: tri_verts, material, flags, nodes, ordered
         self.instances = []   # (object id, instance_to_world, world_to_instance)
         self._keep = []
@@ -153,15 +154,34 @@ class SceneDescription:
         self.materials.append(m)
         return len(self.materials) - 1
 
-    def add_mesh(self, tri_verts, material, area_light=None, reverse_orientation=False, alpha=1.0, shadowalpha=1.0):
+    @staticmethod
+    def _mesh_flags(reverse_orientation, swaps_handedness, alpha, shadowalpha, uv, normals, tangents):
+        return ((1 if bool(reverse_orientation) != bool(swaps_handedness) else 0) | (2 if alpha == 0.0 else 0) | (4 if shadowalpha == 0.0 else 0) |
+                (8 if reverse_orientation else 0) | (16 if uv is not None else 0) | (32 if normals is not None else 0) | (64 if tangents is not None else 0))
+
+    @staticmethod
+    def _attr(a, n, width, old, n_old):
+        """Appends an optional per-triangle attribute block (zeros where a mesh has none)."""
+        if a is None and old is None:
+            return None
+        base = old if old is not None else np.zeros((n_old, width), dtype=F32)
+        blk = np.zeros((n, width), dtype=F32) if a is None else np.ascontiguousarray(a, dtype=F32).reshape(n, width)
+        return np.concatenate([base, blk])
+
+    def add_mesh(self, tri_verts, material, area_light=None, reverse_orientation=False, alpha=1.0, shadowalpha=1.0, uv=None, normals=None,
+                 tangents=None, swaps_handedness=False):
         """One GeometricPrimitive per triangle; with ``area_light={'L': (r,g,b), 'twosided': False}`` one
-        DiffuseAreaLight per triangle (api/src/lib.rs:783-803)."""
+        DiffuseAreaLight per triangle (api/src/lib.rs:783-803).  Optional de-indexed vertex attributes in world space:
+        ``uv`` (n, 6), ``normals`` (n, 9), ``tangents`` (n, 9) — the mesh's "uv"/"st", "N", "S" (triangle.rs:384-394, 631-721)."""
         tv = np.ascontiguousarray(tri_verts, dtype=F32).reshape(-1, 9)
         n0 = self.tri_verts.shape[0]
         n = tv.shape[0]
+        self.tri_uvs = self._attr(uv, n, 6, self.tri_uvs, n0)
+        self.tri_normals = self._attr(normals, n, 9, self.tri_normals, n0)
+        self.tri_tangents = self._attr(tangents, n, 9, self.tri_tangents, n0)
         self.tri_verts = np.concatenate([self.tri_verts, tv])
         self.prim_material = np.concatenate([self.prim_material, np.full(n, material, dtype=np.int32)])
-        flags = (1 if reverse_orientation else 0) | (2 if alpha == 0.0 else 0) | (4 if shadowalpha == 0.0 else 0)
+        flags = self._mesh_flags(reverse_orientation, swaps_handedness, alpha, shadowalpha, uv, normals, tangents)
         self.prim_flags = np.concatenate([self.prim_flags, np.full(n, flags, dtype=np.uint32)])
         pl = np.full(n, -1, dtype=np.int32)
         if area_light is not None:
@@ -180,10 +200,11 @@ class SceneDescription:
 
     # -- flattening --
     # -- instancing: ObjectBegin/ObjectEnd + ObjectInstance (api/src/lib.rs:880-987) --
-    def add_object(self, tri_verts, material, reverse_orientation=False):
+    def add_object(self, tri_verts, material, reverse_orientation=False, uv=None, normals=None, tangents=None):
         """Defines a named object (its triangles get their own BVHAccel); returns the object id."""
         tv = np.ascontiguousarray(tri_verts, dtype=F32).reshape(-1, 9)
-        self.objects.append(dict(tri_verts=tv, material=material, flags=1 if reverse_orientation else 0, nodes=None, ordered=None))
+        self.objects.append(dict(tri_verts=tv, material=material, flags=self._mesh_flags(reverse_orientation, False, 1.0, 1.0, uv, normals, tangents),
+                                 nodes=None, ordered=None, uv=uv, normals=normals, tangents=tangents))
         return len(self.objects) - 1
 
     def add_instance(self, obj, instance_to_world):
@@ -259,6 +280,16 @@ class SceneDescription:
         d.prim_light = arr(np.concatenate(pl), np.int32)
         d.n_prims = all_tv.shape[0]
         d.n_top_tris = n_top
+        # optional vertex attributes: top-level blocks first, then one block per object (zeros where a mesh has none)
+        for field, width, top, key in (("tri_uvs", 6, self.tri_uvs, "uv"), ("tri_normals", 9, self.tri_normals, "normals"),
+                                       ("tri_tangents", 9, self.tri_tangents, "tangents")):
+            if top is None and all(o.get(key) is None for o in self.objects):
+                continue
+            blocks = [top if top is not None else np.zeros((n_top, width), dtype=F32)]
+            for o in self.objects:
+                n = o["tri_verts"].shape[0]
+                blocks.append(np.zeros((n, width), dtype=F32) if o.get(key) is None else np.ascontiguousarray(o[key], dtype=F32).reshape(n, width))
+            setattr(d, field, arr(np.concatenate(blocks), F32))
         d.objects, d.n_objects = C.cast(objs, C.c_void_p), len(self.objects)
         d.instances, d.n_instances = C.cast(insts, C.c_void_p), len(self.instances)
 

@@ -47,10 +47,12 @@ def value_noise(p, freq, seed):
     return out
 
 
-def displaced_sphere(nu, nv, radius=1.0, amplitude=0.15, base_freq=8.0, seed=1, center=(0.0, 0.0, 0.0)):
+def displaced_sphere(nu, nv, radius=1.0, amplitude=0.15, base_freq=8.0, seed=1, center=(0.0, 0.0, 0.0), with_attrs=False):
     """nu x nv lat-long grid -> 2*nu*nv triangles (the pole rows yield zero-area
     triangles, which the reference rejects with det == 0), radially displaced by 4
-    octaves of value noise.  Returns (n_tris, 9) float32."""
+    octaves of value noise.  Returns (n_tris, 9) float32; with_attrs=True also returns de-indexed
+    "uv" (n_tris, 6) = (u / 2 pi, v / pi) and "N" (n_tris, 9) = 1.5 x the undisplaced radial direction
+    (smooth shading normals, deliberately not unit length: the reference does not renormalise N)."""
     u = (np.arange(nu, dtype=F32) / F32(nu)) * F32(2.0 * np.pi)
     v = (np.arange(nv + 1, dtype=F32) / F32(nv)) * F32(np.pi)
     uu, vv = np.meshgrid(u, v)  # (nv+1, nu)
@@ -71,7 +73,22 @@ def displaced_sphere(nu, nv, radius=1.0, amplitude=0.15, base_freq=8.0, seed=1, 
     a, b, c, e = p[:-1][:, i0], p[:-1][:, i1], p[1:][:, i0], p[1:][:, i1]
     tris[:, :, 0, 0:3], tris[:, :, 0, 3:6], tris[:, :, 0, 6:9] = a, c, b
     tris[:, :, 1, 0:3], tris[:, :, 1, 3:6], tris[:, :, 1, 6:9] = b, c, e
-    return tris.reshape(-1, 9)
+    if not with_attrs:
+        return tris.reshape(-1, 9)
+    dn = (F32(1.5) * d).astype(F32).reshape(nv + 1, nu, 3)
+    na, nb, nc, ne = dn[:-1][:, i0], dn[:-1][:, i1], dn[1:][:, i0], dn[1:][:, i1]
+    nrm = np.empty((nv, nu, 2, 9), dtype=F32)
+    nrm[:, :, 0, 0:3], nrm[:, :, 0, 3:6], nrm[:, :, 0, 6:9] = na, nc, nb
+    nrm[:, :, 1, 0:3], nrm[:, :, 1, 3:6], nrm[:, :, 1, 6:9] = nb, nc, ne
+    uu0 = (np.arange(nu, dtype=F32) / F32(nu))[None, :].repeat(nv, 0)
+    uu1 = ((np.arange(nu, dtype=F32) + F32(1)) / F32(nu))[None, :].repeat(nv, 0)   # no wrap at the seam
+    vv0 = (np.arange(nv, dtype=F32) / F32(nv))[:, None].repeat(nu, 1)
+    vv1 = ((np.arange(nv, dtype=F32) + F32(1)) / F32(nv))[:, None].repeat(nu, 1)
+    uv = np.empty((nv, nu, 2, 6), dtype=F32)
+    # vertex order matches the triangles: (a, c, b) and (b, c, e)
+    uv[:, :, 0, 0], uv[:, :, 0, 1], uv[:, :, 0, 2], uv[:, :, 0, 3], uv[:, :, 0, 4], uv[:, :, 0, 5] = uu0, vv0, uu0, vv1, uu1, vv0
+    uv[:, :, 1, 0], uv[:, :, 1, 1], uv[:, :, 1, 2], uv[:, :, 1, 3], uv[:, :, 1, 4], uv[:, :, 1, 5] = uu1, vv0, uu0, vv1, uu1, vv1
+    return tris.reshape(-1, 9), uv.reshape(-1, 6), nrm.reshape(-1, 9)
 
 
 def triangle_soup(n, edge=0.02, seed=2):

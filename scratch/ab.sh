@@ -1,2 +1,2 @@
-ncu --set full --clock-control none --import-source on -k regex:k_trace_spec -o gpurun_out/prof_r1_spec python scratch/prof_bounce.py 9 > gpurun_out/ncu_spec.log 2>&1
-tail -2 gpurun_out/ncu_spec.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c5.csv python tools/run_config.py c5 --spp 4 --li 0 --reps 1 > gpurun_out/ncu_c5.log 2>&1
+tail -2 gpurun_out/ncu_c5.log

@@ -46,6 +46,8 @@ def lib():
         L.orc_accel_create.restype = vp
         L.orc_accel_create.argtypes = [vp, i64, vp, vp, vp, i64]
         L.orc_accel_destroy.argtypes = [vp]
+        L.orc_accel_set_uvs.argtypes = [vp, vp, i64]
+        L.orc_triangle_geometry.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
         L.orc_intersect_batch.argtypes = [vp, vp, i64, vp, vp, vp, C.c_int]
         L.orc_occluded_batch.argtypes = [vp, vp, i64, vp, vp, C.c_int]
         L.orc_triangle_intersect.argtypes = [vp, vp, vp]
@@ -93,12 +95,18 @@ def build_bvh_sah(prim_bounds, max_prims_in_node=4):
 
 
 class OracleAccel:
-    def __init__(self, nodes, ordered, tri_verts, flags=None):
+    def __init__(self, nodes, ordered, tri_verts, flags=None, tri_uvs=None):
         self.nodes = np.ascontiguousarray(nodes)
         self.ordered = np.ascontiguousarray(ordered, dtype=np.uint32)
         self.verts = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
         self.flags = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint32)
+        if tri_uvs is not None:
+            fl = np.zeros(self.verts.shape[0], dtype=np.uint32) if self.flags is None else self.flags
+            self.flags = fl | np.uint32(16)  # PRIM_HAS_UV
         self.h = lib().orc_accel_create(_p(self.nodes), len(self.nodes), _p(self.ordered), _p(self.verts), _p(self.flags), self.verts.shape[0])
+        if tri_uvs is not None:
+            uv = np.ascontiguousarray(tri_uvs, dtype=np.float32).reshape(-1, 6)
+            lib().orc_accel_set_uvs(self.h, _p(uv), uv.shape[0])
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -121,6 +129,17 @@ class OracleAccel:
         ct = np.empty((n, 2), dtype=np.uint32) if counters else None
         lib().orc_occluded_batch(self.h, _p(r), n, _p(out), _p(ct), nthreads or ncpu())
         return out, ct
+
+
+def triangle_geometry(verts9, b, uv=None, normals=None, tangents=None, flip=False, reverse=False):
+    """Triangle::intersect's hit geometry -> dict of 3-vectors, or None for a degenerate hit."""
+    f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+    v, bb, out = f(verts9), f(b), np.zeros(21, dtype=np.float32)
+    u, n, s_ = f(uv), f(normals), f(tangents)
+    if not lib().orc_triangle_geometry(_p(v), _p(bb), _p(u), _p(n), _p(s_), int(flip), int(reverse), _p(out)):
+        return None
+    names = ["p", "p_error", "n", "dpdu", "dpdv", "shading_n", "shading_dpdu"]
+    return {k: out[3 * i:3 * i + 3].copy() for i, k in enumerate(names)}
 
 
 class OracleScene:

@@ -2,12 +2,16 @@
 import numpy as np
 
 
-def one_material_scene(wl, mat, light="infinite", res=24, spp=8, maxdepth=5, nu=24, nv=12, strategy="uniform", filt="box"):
+def one_material_scene(wl, mat, light="infinite", res=24, spp=8, maxdepth=5, nu=24, nv=12, strategy="uniform", filt="box", smooth=False):
     from pbrt_v3_rs_b200.scene import SceneDescription
     sd = SceneDescription()
     m = sd.add_material(**mat)
     g = sd.add_material(type="matte", Kd=(0.4, 0.4, 0.4))
-    sd.add_mesh(wl.displaced_sphere(nu, nv), m)
+    if smooth:  # the mesh carries "uv" and "N" (triangle.rs:384-394, 631-721)
+        tv, uv, nrm = wl.displaced_sphere(nu, nv, with_attrs=True)
+        sd.add_mesh(tv, m, uv=uv, normals=nrm)
+    else:
+        sd.add_mesh(wl.displaced_sphere(nu, nv), m)
     sd.add_mesh(wl.ground_quad(), g)
     if light in ("infinite", "all"):
         sd.add_infinite_light((1.2, 1.2, 1.1))

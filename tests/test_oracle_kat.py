@@ -224,3 +224,58 @@ def test_sah_bvh_invariants_and_frozen_hash(oracle, pkg):
     digest = hashlib.sha256(nodes.tobytes() + ordered.tobytes()).hexdigest()
     gold = json.load(open(os.path.join(GOLD, "bvh_c2_small_sha256.json")))
     assert digest == gold["sha256"], "SAH BVH of the C2_SMALL mesh changed"
+
+
+def test_triangle_shading_geometry_hand_checked(oracle):
+    """Triangle::intersect's tail (triangle.rs:547-725) on a triangle in the z = 0 plane.
+
+    default uvs: dpdu = p1 - p0... by hand: uv = (0,0),(1,0),(1,1) gives dpdu = p1 - p0 and dpdv = p2 - p1."""
+    v = np.float32([0, 0, 0, 2, 0, 0, 2, 1, 0])
+    b = np.float32([0.25, 0.25, 0.5])
+    g = oracle.triangle_geometry(v, b)
+    assert np.array_equal(g["p"], np.float32([1.5, 0.5, 0])) and np.array_equal(g["dpdu"], [2, 0, 0]) and np.array_equal(g["dpdv"], [0, 1, 0])
+    # n = normalize((p0 - p2) x (p1 - p2)) = +z for this winding; flipped by reverse_orientation ^ swaps_handedness
+    assert np.array_equal(g["n"], [0, 0, 1]) and np.array_equal(g["shading_n"], g["n"]) and np.array_equal(g["shading_dpdu"], g["dpdu"])
+    assert np.array_equal(oracle.triangle_geometry(v, b, flip=True)["n"], [0, 0, -1])
+    # explicit uvs: u along y, v along x  ->  dpdu = (0,1,0) * (1 / du) ...
+    uv = np.float32([0, 0, 0, 4, 2, 4])  # uv0=(0,0) uv1=(0,4) uv2=(2,4): p = p0 + (p1-p0) v/4 + (p2-p1) u/2
+    g = oracle.triangle_geometry(v, b, uv=uv)
+    assert np.allclose(g["dpdu"], [0, 0.5, 0]) and np.allclose(g["dpdv"], [0.5, 0, 0])
+    # vertex normals tilted towards +x, NOT unit length: ns = normalize(sum b_i n_i); ss = Gram-Schmidt of dpdu; hit.n faces ns
+    nrm = np.float32([3, 0, 3] * 3)
+    g = oracle.triangle_geometry(v, b, normals=nrm)
+    s = np.float32(np.sqrt(0.5))
+    assert np.allclose(g["shading_n"], [s, 0, s], atol=1e-6)
+    # ts = ss x ns = (0,-1,0), ss = ts x ns = (-s,0,s): the reference's Gram-Schmidt turns dpdu (+x) to the -x side
+    assert np.allclose(g["shading_dpdu"], [-s, 0, s], atol=1e-6)
+    assert np.array_equal(g["n"], [0, 0, 1])                           # already on ns's side
+    # normals pointing to the other side flip the GEOMETRIC normal (orientation_is_authoritative, surface_interaction.rs:161-165)
+    g = oracle.triangle_geometry(v, b, normals=-nrm)
+    assert np.array_equal(g["n"], [0, 0, -1]) and np.allclose(g["shading_n"], [-s, 0, -s], atol=1e-6)
+    # reverse_orientation flips ts, hence shading_n = ss x ts, hence the geometric normal follows it
+    g = oracle.triangle_geometry(v, b, normals=nrm, flip=True, reverse=True)
+    assert np.allclose(g["shading_n"], [-s, 0, -s], atol=1e-6) and np.array_equal(g["n"], [0, 0, -1])
+    # tangents: ss = normalize(sum b_i s_i) then Gram-Schmidt against ns
+    g = oracle.triangle_geometry(v, b, normals=np.float32([0, 0, 2] * 3), tangents=np.float32([0, 5, 0] * 3))
+    assert np.allclose(g["shading_dpdu"], [0, -1, 0], atol=1e-6) and np.allclose(g["shading_n"], [0, 0, 1], atol=1e-6)
+    # zero-length interpolated normal falls back to the geometric one; degenerate uvs to coordinate_system(ng)
+    g = oracle.triangle_geometry(v, b, normals=np.float32([0] * 9))
+    assert np.allclose(g["shading_n"], [0, 0, 1], atol=1e-6)
+    g = oracle.triangle_geometry(v, b, uv=np.float32([0.5] * 6))
+    assert abs(float(np.dot(g["dpdu"], g["dpdv"]))) < 1e-6 and abs(float(np.dot(g["dpdu"], [0, 0, 1]))) < 1e-6
+    # a zero-area triangle with degenerate uvs is a bogus hit (triangle.rs:567-572)
+    assert oracle.triangle_geometry(np.float32([0, 0, 0, 1, 1, 1, 2, 2, 2]), b, uv=np.float32([0.5] * 6)) is None
+
+
+def test_smooth_shading_changes_the_oracle_image(oracle):
+    """A mesh with uv + N renders differently from the faceted one and stays finite; same ray counts at depth 1."""
+    import scenes_small as ss
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    from pbrt_v3_rs_b200 import workloads as wl
+    a = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="all", res=16, spp=4, smooth=False)
+    b = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="all", res=16, spp=4, smooth=True)
+    ia, sa, _ = oracle.OracleScene(a).render(nthreads=2)
+    ib, sb, _ = oracle.OracleScene(b).render(nthreads=2)
+    assert np.isfinite(ib).all() and sa[0] == sb[0]
+    assert ss.rel_rmse(ia, ib) > 1e-2

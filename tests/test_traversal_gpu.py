@@ -224,3 +224,24 @@ def test_full_size_microbench_parity(gpu, oracle):
         o, diag, _ = oacc.intersect(rs[sel])
         _check_closest(gh[sel], o, diag, oracle)
     assert np.array_equal(occ[sel], oacc.occluded(sr[sel])[0])
+
+
+def test_uvs_reach_the_degenerate_hit_rejection(gpu, oracle):
+    """triangle.rs:551-572: with a mesh's own uvs a hit is rejected only when the uv-derived dpdu x dpdv (or the uv
+    determinant) AND the geometric normal degenerate.  Random uvs incl. degenerate ones must not change any hit, and
+    the device walk must agree with the oracle walk that uses the same uvs."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    cfg = wl.C2_SMALL
+    tv = wl.c2_mesh(cfg)
+    rng = np.random.Generator(np.random.PCG64(8))
+    uv = rng.uniform(0, 1, size=(tv.shape[0], 6)).astype(np.float32)
+    uv[::7] = 0.25                      # degenerate parameterisation -> coordinate_system(ng) branch
+    accel = gpu.BVHAccel.from_params({"maxnodeprims": 4}, tv, tri_uvs=uv)
+    plain = gpu.BVHAccel.from_params({"maxnodeprims": 4}, tv)
+    oacc = oracle.OracleAccel(accel.nodes, accel.ordered_prims, tv, tri_uvs=uv)
+    rays = wl.primary_rays(cfg["width"], cfg["height"])
+    g, o = accel.intersect_batch(rays), oacc.intersect(rays)[0]
+    assert np.array_equal(g["prim"], o["prim"]) and np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32))
+    assert np.array_equal(g["prim"], plain.intersect_batch(rays)["prim"])
+    sr = wl.shadow_rays(wl.bounce_rays(tv, rays, g, rays.shape[0]))
+    assert np.array_equal(accel.occluded_batch(sr), oacc.occluded(sr)[0])

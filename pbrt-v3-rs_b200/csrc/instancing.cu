@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "instancing.cuh"
+#include "traverse_phased.cuh"
 
 namespace b2 {
 
@@ -352,19 +353,255 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
     }
 }
 
+// Loop-free postponed-leaf form of the two-level walk (variant 0, default; the single-level kernel is k_trace_spec2 in
+// traverse_spec.cuh, where the equivalence argument is written down).  Inside an object's BVH a lane parks the leaf it
+// reached and keeps walking; at the scene-aggregate level a leaf is NOT walked past (cur = kHold): its records may be
+// TransformedPrimitives, and entering one replaces the lane's ray.  Entering spills the register-held stack top and
+// records sp_base; the object's walk pops down to sp_base only; leaving restores the world ray from the input, the
+// interrupted leaf (saved_*) and the stack top.
+template <bool ANY, int kSwitch, int kRefill, int kBlocks>
+__global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2, const float4* __restrict__ rays, long long n, void* __restrict__ out,
+                                                                 unsigned long long* __restrict__ counter, float* __restrict__ b2_out, int* __restrict__ inst_out) {
+    const DeviceAccel& A = A2.top;
+    const unsigned lane = threadIdx.x & 31u;
+    const int kIdle = (int)0x80000000;
+    const int kRetry = (int)0x80000001;  // pop (again) in the next NODE step
+    const int kHold = (int)0x80000002;   // scene-aggregate level: wait until the parked leaf has been processed, then pop
+    StackEntry<ANY> stack[B2_STACK2];
+
+    int ray_id = -1;
+    RayCtx r;
+    TriCtx tc;
+    V3 o;
+    float t_max = 0.0f, world_t_max = 0.0f;
+    int cur = kIdle;
+    float cur_t = 0.0f;
+    int pend = kIdle;
+    int sp = 0, sp_base = 0;
+    int top_code = kIdle;
+    float top_t = 0.0f;
+    int negmask = 0;
+    int tri_i = 0, saved_i = 0;
+    uint32_t tri_left = 0, saved_left = 0;
+    int in_inst = -1;
+    bool inst_hit = false;
+    HitOut h;
+    int h_inst = -1;
+    h.t = 0.0f; h.prim = 0xffffffffu; h.b0 = h.b1 = h.b2 = 0.0f;
+    bool exhausted = false;
+    bool node_phase = true;
+
+    auto set_ray = [&](float ox, float oy, float oz, float dx, float dy, float dz) {
+        r.ox = ox; r.oy = oy; r.oz = oz;
+        r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
+        r.nx = r.ix < 0.0f; r.ny = r.iy < 0.0f; r.nz = r.iz < 0.0f;
+        negmask = r.nx | (r.ny << 1) | (r.nz << 2);
+        tc = make_tri_ctx(dx, dy, dz);
+        o = mk(ox, oy, oz);
+    };
+
+    for (;;) {
+        const unsigned idle_mask = __ballot_sync(0xffffffffu, cur == kIdle && pend == kIdle);
+        if (idle_mask == 0xffffffffu && exhausted) break;
+        if (!exhausted && __popc(idle_mask) >= kRefill) {
+            const int want = __popc(idle_mask);
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if ((long long)b + want >= n) exhausted = true;
+            if (cur == kIdle && pend == kIdle) {
+                const long long id = (long long)b + __popc(idle_mask & ((1u << lane) - 1u));
+                if (id < n) {
+                    float4 r0 = __ldg(rays + 2 * id), r1 = __ldg(rays + 2 * id + 1);
+                    ray_id = (int)id;
+                    set_ray(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                    t_max = r0.w;
+                    sp = 0; sp_base = 0; tri_left = 0; top_code = kIdle; in_inst = -1; h_inst = -1;
+                    h.t = __int_as_float(0x7f800000); h.prim = 0xffffffffu; h.b0 = h.b1 = h.b2 = 0.0f;
+                    float te;
+                    bool enter = A.root_code != B2_EMPTY_ROOT &&
+                                 slab(r, A.root_bounds[0], A.root_bounds[1], A.root_bounds[2], A.root_bounds[3], A.root_bounds[4], A.root_bounds[5], &te) && te < t_max;
+                    if (enter) {
+                        if (A.root_code >= 0) { cur = A.root_code; cur_t = te; }
+                        else { pend = A.root_code; cur = kHold; }
+                    } else if (ANY) {
+                        ((uint8_t*)out)[id] = 0;
+                    } else {
+                        ((float4*)out)[id] = make_float4(h.t, __uint_as_float(h.prim), 0.0f, 0.0f);
+                        if (b2_out) b2_out[id] = 0.0f;
+                        if (inst_out) inst_out[id] = -1;
+                    }
+                }
+            }
+        }
+        for (;;) {
+            const unsigned m_node = __ballot_sync(0xffffffffu, cur >= 0 || cur == kRetry);
+            const unsigned m_tri = __ballot_sync(0xffffffffu, pend != kIdle);
+            if (!(m_node | m_tri)) break;
+            if (!exhausted && __popc(~(m_node | m_tri)) >= kRefill) break;
+            const int nn = __popc(m_node), nt = __popc(m_tri);
+            if (node_phase) { if (nn < kSwitch && nt > nn) node_phase = false; }
+            else            { if (nt < kSwitch && nn > nt) node_phase = true; }
+            if (nt == 0) node_phase = true;
+            if (nn == 0) node_phase = false;
+
+            bool fin = false;  // this level's walk is finished (cur and pend both empty)
+            if (node_phase) {
+                bool need_pop = cur == kRetry;
+                if (cur >= 0) {
+                    const float4* q = A.wide + 4ll * cur;
+                    float4 q0, q1, q2, q3;
+                    ldg8(q, &q0, &q1);
+                    ldg8(q + 2, &q2, &q3);
+                    float t0, t1;
+                    // literal box test: an instance-space ray may be axis-parallel where the world ray is not, and the
+                    // min/max form is chosen per warp at refills only
+                    const bool h0 = slab_bf(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &t0) & (t0 < t_max);
+                    const bool h1 = slab_bf(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &t1) & (t1 < t_max);
+                    const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y), axis = __float_as_int(q3.z);
+                    const bool neg = (negmask >> axis) & 1;
+                    const int near_c = neg ? c1 : c0, far_c = neg ? c0 : c1;
+                    const bool near_h = neg ? h1 : h0, far_h = neg ? h0 : h1;
+                    const float near_t = neg ? t1 : t0, far_t = neg ? t0 : t1;
+                    const bool push = near_h & far_h;
+                    const bool spill = push & (top_code != kIdle);
+                    if (spill) stack[sp].set(top_code, top_t);
+                    sp += spill ? 1 : 0;
+                    top_code = push ? far_c : top_code;
+                    top_t = push ? far_t : top_t;
+                    cur = near_h ? near_c : far_c;
+                    cur_t = near_h ? near_t : far_t;
+                    need_pop = !(near_h | far_h);
+                    const bool park = !need_pop & (cur < 0) & (pend == kIdle);
+                    pend = park ? cur : pend;
+                    tri_left = park ? 0u : tri_left;
+                    if (park) { if (in_inst >= 0) need_pop = true; else cur = kHold; }
+                }
+                if (need_pop) {
+                    const int c = top_code;
+                    const float t = top_t;
+                    const bool have = c != kIdle;
+                    const bool refill = have & (sp > sp_base);
+                    sp -= refill ? 1 : 0;
+                    StackEntry<ANY> e;
+                    e.set(kIdle, 0.0f);
+                    if (refill) e = stack[sp];
+                    top_code = e.code(); top_t = e.t();
+                    const bool valid = have & (ANY || t < t_max);
+                    cur = valid ? c : (have ? kRetry : kIdle);
+                    cur_t = t;
+                    const bool park = valid & (c < 0) & (pend == kIdle);
+                    pend = park ? c : pend;
+                    tri_left = park ? 0u : tri_left;
+                    cur = park ? (in_inst >= 0 ? kRetry : kHold) : cur;
+                    fin = (cur == kIdle) & (pend == kIdle);
+                }
+            } else if (pend != kIdle) {
+                V3 p0, p1, p2;
+                float4 duv;
+                uint32_t prim, flags, leaf_n;
+                if (tri_left == 0) tri_i = ~pend;
+                load_tri(A.tris, (long long)tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
+                if (tri_left == 0) tri_left = leaf_n;
+                ++tri_i;
+                --tri_left;
+                bool entered = false;
+                if (flags & 0x80000000u) {
+                    // TransformedPrimitive (only in leaves of the scene aggregate, where cur == kHold)
+                    const float4* T = A2.inst_trav + 6ll * prim;
+                    const float4 m0 = __ldg(T), m1 = __ldg(T + 1), m2 = __ldg(T + 2), m3 = __ldg(T + 3), b0q = __ldg(T + 4), b1q = __ldg(T + 5);
+                    const float4 w1 = __ldg(rays + 2ll * ray_id + 1);
+                    Ray32 wr{o.x, o.y, o.z, t_max, w1.x, w1.y, w1.z, w1.w};
+                    const Ray32 ir = xf_ray(m0, m1, m2, m3, wr);
+                    RayCtx ri;
+                    ri.ox = ir.ox; ri.oy = ir.oy; ri.oz = ir.oz;
+                    ri.ix = 1.0f / ir.dx; ri.iy = 1.0f / ir.dy; ri.iz = 1.0f / ir.dz;
+                    ri.nx = ri.ix < 0.0f; ri.ny = ri.iy < 0.0f; ri.nz = ri.iz < 0.0f;
+                    float te;
+                    const int root = __float_as_int(b1q.z);
+                    if (root != B2_EMPTY_ROOT && slab(ri, b0q.x, b0q.y, b0q.z, b0q.w, b1q.x, b1q.y, &te) && te < ir.tmax) {
+                        entered = true;
+                        saved_i = tri_i; saved_left = tri_left;
+                        world_t_max = t_max;
+                        in_inst = (int)prim; inst_hit = false;
+                        if (top_code != kIdle) { stack[sp].set(top_code, top_t); ++sp; top_code = kIdle; }
+                        sp_base = sp;
+                        r = ri;
+                        negmask = r.nx | (r.ny << 1) | (r.nz << 2);
+                        tc = make_tri_ctx(ir.dx, ir.dy, ir.dz);
+                        o = mk(ir.ox, ir.oy, ir.oz);
+                        t_max = ir.tmax;
+                        tri_left = 0;
+                        if (root >= 0) { cur = root; cur_t = te; pend = kIdle; }
+                        else { pend = root; cur = kRetry; }  // single-leaf object
+                    }
+                } else {
+                    float t, b0, b1, b2;
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                        if (ANY) {
+                            if (!(flags & 6u)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
+                        } else if (!(flags & 2u)) {
+                            t_max = t;
+                            h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;
+                            h_inst = in_inst;
+                            inst_hit = true;
+                        }
+                    }
+                }
+                if (!entered && tri_left == 0) {
+                    // leaf done, t_max current again: re-validate what was reached speculatively (object level only)
+                    pend = kIdle;
+                    const bool live = cur != kIdle && cur != kRetry && cur != kHold;
+                    if (cur == kHold) cur = kRetry;
+                    else if (!ANY && live && !(cur_t < t_max)) cur = kRetry;
+                    else if (live && cur < 0) { pend = cur; cur = kRetry; }
+                    fin = cur == kIdle;
+                }
+            }
+            if (fin && in_inst >= 0) {
+                // the object's walk is finished: back to the interrupted leaf of the scene aggregate
+                fin = false;
+                if (!inst_hit) t_max = world_t_max;
+                in_inst = -1;
+                sp_base = 0;
+                const float4 w0 = __ldg(rays + 2ll * ray_id), w1 = __ldg(rays + 2ll * ray_id + 1);
+                set_ray(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
+                if (sp > 0) { --sp; const StackEntry<ANY> e = stack[sp]; top_code = e.code(); top_t = e.t(); }
+                if (saved_left > 0) { pend = -1; tri_i = saved_i; tri_left = saved_left; cur = kHold; }  // pend: any leaf code, tri_i / tri_left carry the position
+                else cur = kRetry;
+            }
+            if (fin) {
+                if (ANY) ((uint8_t*)out)[ray_id] = h.prim != 0xffffffffu ? 1 : 0;
+                else {
+                    ((float4*)out)[ray_id] = make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1);
+                    if (b2_out) b2_out[ray_id] = h.b2;
+                    if (inst_out) inst_out[ray_id] = h_inst;
+                }
+            }
+        }
+    }
+}
+
 static const int kCounterRing2 = 64;  // one work counter per launch in flight (launches on different streams never share one)
 static unsigned long long* g_counter2 = nullptr;
 static std::atomic<unsigned> g_counter2_next{0};
 
 template <bool ANY>
-static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, float* d_b2, int* d_inst) {
+static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, float* d_b2, int* d_inst, int variant) {
     if (!g_counter2) B2_CUDA(cudaMalloc(&g_counter2, kCounterRing2 * sizeof(unsigned long long)));
     unsigned long long* ctr = g_counter2 + (g_counter2_next.fetch_add(1) % kCounterRing2);
     B2_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
-    constexpr int kBlocks = 5;
+    if (n >= 0x7fffffffLL) { b200pt_set_error("two-level traversal: at most 2^31-2 rays per launch"); return B200PT_ERR_INVALID; }
     int64_t want = (n + 127) / 128;
-    int grid = (int)std::min<int64_t>(want, (int64_t)g_sm_count * kBlocks);
-    k_trace_phased2<ANY, 16, 16, kBlocks><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+    if (variant == 4) {
+        constexpr int kBlocks = 5;
+        int grid = (int)std::min<int64_t>(want, (int64_t)g_sm_count * kBlocks);
+        k_trace_phased2<ANY, 16, 16, kBlocks><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+    } else {
+        constexpr int kBlocks = ANY ? 7 : 6;
+        int grid = (int)std::min<int64_t>(want, (int64_t)g_sm_count * kBlocks);
+        k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, kBlocks><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+    }
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200PT_OK : cuda_fail(e, "k_trace_phased2 launch");
@@ -372,7 +609,7 @@ static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, 
 
 int launch_intersect2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, float* d_b2, int* d_inst, int variant) {
     if (n <= 0) return B200PT_OK;
-    if (variant == 0) return launch_phased2<false>(A, d_rays, n, d_hits, s, d_b2, d_inst);
+    if (variant == 0 || variant == 4) return launch_phased2<false>(A, d_rays, n, d_hits, s, d_b2, d_inst, variant);
     k_trace_twolevel<false><<<(int)((n + 127) / 128), 128, 0, s>>>(A, (const float4*)d_rays, n, d_hits, d_b2, d_inst);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
@@ -380,7 +617,7 @@ int launch_intersect2(const DeviceAccel2& A, const void* d_rays, int64_t n, void
 }
 int launch_occluded2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant) {
     if (n <= 0) return B200PT_OK;
-    if (variant == 0) return launch_phased2<true>(A, d_rays, n, d_out, s, nullptr, nullptr);
+    if (variant == 0 || variant == 4) return launch_phased2<true>(A, d_rays, n, d_out, s, nullptr, nullptr, variant);
     k_trace_twolevel<true><<<(int)((n + 127) / 128), 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, nullptr, nullptr);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();

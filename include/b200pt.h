@@ -96,6 +96,11 @@ typedef struct b200pt_light {
     int32_t two_sided;        /* area */
     float light_to_world[16]; /* infinite (row-major 4x4) */
     float world_to_light[16];
+    /* infinite: the "mapname" image, already decoded (image IO stays with the caller): map_width x map_height RGB
+     * texels, row-major from the top row, NOT yet multiplied by L (lights/src/infinite.rs:66-79).  NULL = no map
+     * (the reference then uses the 1x1 image [L]). */
+    const float* map_rgb;
+    int32_t map_width, map_height;
 } b200pt_light;
 
 /* cameras/src/perspective_camera.rs + core/src/camera.rs:276-306: the two
@@ -207,6 +212,13 @@ int b200pt_bvh_build_sah(const float* prim_bounds, int64_t n, int max_prims_in_n
                          int64_t* n_nodes_out, uint32_t* ordered_out);
 /* Triangle::world_bound (shapes/src/triangle.rs:427-431) for n triangles. */
 int b200pt_triangle_bounds(const float* tri_verts, int64_t n, float* bounds_out);
+
+/* Host-only: what InfiniteAreaLight::new prepares for an environment image (lights/src/infinite.rs:61-92, 326-369;
+ * core/src/mipmap/mod.rs): level 0 of the MIPMap (sides rounded up to powers of two by the Lanczos resampler) and the
+ * (2w x 2h) importance image y * sin(theta) the light's Distribution2D is built over.  Call with the out pointers
+ * NULL to get the sizes: size4 = {level0_width, level0_height, importance_width, importance_height}. */
+int b200pt_envmap_prepare(const float* map_rgb, int32_t map_width, int32_t map_height, const float L[3], int32_t size4[4],
+                          float* level0_rgb_out, float* importance_out, float power_lookup_out[3]);
 
 /* ---- accelerator: impl Primitive for BVHAccel --------------------------
  * Copies the arrays to the device; the caller keeps ownership of its own. */

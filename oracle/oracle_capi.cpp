@@ -226,6 +226,42 @@ int orc_bounds_intersect(const float* bounds6, const float* ray8) {
     return bounds_intersect_p_inv(bounds6, r, inv_dir, neg) ? 1 : 0;
 }
 
+// Environment map preparation (oracle_envmap.h + compute_scalar_image): level 0 texels, importance image, power lookup.
+// Call with null outputs to get size4 = {w0, h0, 2*w0, 2*h0}.
+void orc_envmap_prepare(const float* rgb, int w, int h, const float* L, int32_t* size4, float* level0_out, float* importance_out, float* power_out) {
+    std::vector<RGB> tex;
+    int mw = 1, mh = 1;
+    RGB l(L[0], L[1], L[2]);
+    if (rgb && w > 0 && h > 0) {
+        mw = w; mh = h;
+        for (size_t k = 0; k < (size_t)w * h; ++k) tex.push_back(RGB(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2]) * l);
+    } else tex.push_back(l);
+    MipMap m;
+    m.build(mw, mh, tex);
+    const int nu = 2 * m.width(), nv = 2 * m.height();
+    size4[0] = m.width(); size4[1] = m.height(); size4[2] = nu; size4[3] = nv;
+    if (level0_out)
+        for (size_t k = 0; k < m.pyramid[0].px.size(); ++k)
+            for (int c = 0; c < 3; ++c) level0_out[3 * k + c] = m.pyramid[0].px[k].c[c];
+    if (importance_out) {
+        const Float fwidth = 0.5f / (Float)(nu < nv ? nu : nv);
+        for (int v = 0; v < nv; ++v) {
+            Float vp = ((Float)v + 0.5f) / (Float)nv, sin_t = std::sin(kPi * ((Float)v + 0.5f) / (Float)nv);
+            for (int u = 0; u < nu; ++u) importance_out[(size_t)v * nu + u] = lum_y(m.lookup_triangle(P2(((Float)u + 0.5f) / (Float)nu, vp), fwidth)) * sin_t;
+        }
+    }
+    if (power_out) { RGB p = m.lookup_triangle(P2(0.5f, 0.5f), 0.5f); power_out[0] = p.c[0]; power_out[1] = p.c[1]; power_out[2] = p.c[2]; }
+}
+// One MIPMap::lookup_triangle on a freshly built map (KATs).
+void orc_envmap_lookup(const float* rgb, int w, int h, const float* st2, float width, float* out3) {
+    std::vector<RGB> tex;
+    for (size_t k = 0; k < (size_t)w * h; ++k) tex.push_back(RGB(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2]));
+    MipMap m;
+    m.build(w, h, tex);
+    RGB v = m.lookup_triangle(P2(st2[0], st2[1]), width);
+    out3[0] = v.c[0]; out3[1] = v.c[1]; out3[2] = v.c[2];
+}
+
 // ---- rendering (oracle_render.h) ------------------------------------------
 void* orc_scene_create(const b200pt_scene_desc* d) { return scene_create(d); }
 void orc_scene_destroy(void* s) { scene_destroy((RenderScene*)s); }

@@ -13,6 +13,7 @@
 
 #include "../include/b200pt.h"
 #include "oracle_bvh.h"
+#include "oracle_envmap.h"
 #include "oracle_math.h"
 #include "oracle_rng.h"
 
@@ -503,6 +504,7 @@ struct RenderScene {
     Distribution1D light_distr;
     // per infinite light (indexed by light id): 2x2 distribution of the constant map
     std::vector<Distribution2D> inf_distr;
+    std::vector<MipMap> inf_map;           // per light (built for infinite lights only)
     std::vector<Float> light_area;  // area lights: Triangle::area
     int sample_bounds[4];           // Film::get_sample_bounds
     std::atomic<uint64_t> n_camera{0}, n_closest{0}, n_shadow{0};
@@ -510,21 +512,15 @@ struct RenderScene {
 
 inline M4 m4_from(const float* a) { M4 m; std::memcpy(m.m, a, 64); return m; }
 
-// lights/src/infinite.rs + core/src/mipmap/mod.rs:226-311 for a 1x1 constant map:
-// every texel is L, the bilinear blend keeps its four weights.
-inline RGB inf_lookup(RGB L, P2 st) {
-    Float s = st.x * 1.0f - 0.5f, t = st.y * 1.0f - 0.5f;
-    Float s0 = std::floor(s), t0 = std::floor(t);
-    Float ds = s - s0, dt = t - t0;
-    return L * (1.0f - ds) * (1.0f - dt) + L * (1.0f - ds) * dt + L * ds * (1.0f - dt) + L * ds * dt;
-}
 inline RGB light_L(const b200pt_light& l) { return RGB(l.L[0], l.L[1], l.L[2]); }
 
-// InfiniteAreaLight::le, infinite.rs:188-199
-inline RGB infinite_le(const b200pt_light& l, const Ray& ray) {
+// InfiniteAreaLight::le, infinite.rs:188-199 (l_map.lookup_triangle(st, 0.0): level-0 bilinear lookup, wrap = repeat;
+// without a "mapname" the map is the 1x1 image [L], infinite.rs:66-79)
+inline RGB infinite_le(const RenderScene& sc, int li, const Ray& ray) {
+    const b200pt_light& l = sc.lights[(size_t)li];
     V3 w = normalize(xf_vector(m4_from(l.world_to_light), ray.d));
     P2 st(spherical_phi(w) * kInvTwoPi, spherical_theta(w) * kInvPi);
-    return inf_lookup(light_L(l), st);
+    return sc.inf_map[(size_t)li].lookup_triangle(st, 0.0f);
 }
 
 // Triangle::area, triangle.rs:906-911
@@ -538,7 +534,7 @@ inline RGB light_power(const RenderScene& sc, int li) {
         Float s = l.two_sided ? 2.0f : 1.0f;
         return s * light_L(l) * sc.light_area[li] * kPi;
     }
-    RGB spec = inf_lookup(light_L(l), P2(0.5f, 0.5f));
+    RGB spec = sc.inf_map[(size_t)li].lookup_triangle(P2(0.5f, 0.5f), 0.5f);  // infinite.rs:177-186
     return kPi * sc.world_radius * sc.world_radius * spec;
 }
 
@@ -592,21 +588,32 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
     bounding_sphere(s->world_bound, &s->world_center, &s->world_radius);  // infinite.rs:113-117
     s->light_area.assign(s->lights.size(), 0.0f);
     s->inf_distr.resize(s->lights.size());
+    s->inf_map.resize(s->lights.size());
     for (size_t i = 0; i < s->lights.size(); ++i) {
         const b200pt_light& l = s->lights[i];
         if (l.type == B200PT_LIGHT_AREA)
             s->light_area[i] = triangle_area(s->accel.vert(l.prim, 0), s->accel.vert(l.prim, 1), s->accel.vert(l.prim, 2));
         if (l.type == B200PT_LIGHT_INFINITE) {
             s->infinite_lights.push_back((int)i);
-            // compute_scalar_image, infinite.rs:326-369: 2x2 image of y * sin(theta)
-            const int width = 2, height = 2;
+            // InfiniteAreaLight::new, infinite.rs:61-92: texels = image * L (or the 1x1 image [L]), MIPMap over them
+            std::vector<RGB> texels;
+            int mw = 1, mh = 1;
+            if (l.map_rgb && l.map_width > 0 && l.map_height > 0) {
+                mw = l.map_width; mh = l.map_height;
+                texels.resize((size_t)mw * mh);
+                for (size_t k = 0; k < texels.size(); ++k) texels[k] = RGB(l.map_rgb[3 * k], l.map_rgb[3 * k + 1], l.map_rgb[3 * k + 2]) * light_L(l);
+            } else texels.push_back(light_L(l));
+            s->inf_map[i].build(mw, mh, texels);
+            // compute_scalar_image, infinite.rs:326-369: (2w x 2h) image of y * sin(theta)
+            const int width = 2 * s->inf_map[i].width(), height = 2 * s->inf_map[i].height();
+            const Float fwidth = 0.5f / (Float)(width < height ? width : height);
             std::vector<std::vector<Float>> img(height);
             for (int v = 0; v < height; ++v) {
                 Float vp = ((Float)v + 0.5f) / (Float)height;
                 Float sin_t = std::sin(kPi * ((Float)v + 0.5f) / (Float)height);
                 for (int u = 0; u < width; ++u) {
                     Float up = ((Float)u + 0.5f) / (Float)width;
-                    img[v].push_back(lum_y(inf_lookup(light_L(l), P2(up, vp))) * sin_t);
+                    img[v].push_back(lum_y(s->inf_map[i].lookup_triangle(P2(up, vp), fwidth)) * sin_t);
                 }
             }
             s->inf_distr[i].init(img);
@@ -851,7 +858,7 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
     if (sin_t == 0.0f) pdf = 0.0f;
     r.wi = wi; r.pdf = pdf;
     r.p1 = hit.p + wi * (2.0f * sc.world_radius);
-    r.value = inf_lookup(light_L(l), uv);
+    r.value = sc.inf_map[(size_t)li].lookup_triangle(uv, 0.0f);
     r.valid = true;
     return r;
 }
@@ -923,7 +930,7 @@ inline RGB estimate_direct(RenderScene& sc, const SurfHit& hit, const BSDF& bsdf
             if (scene_intersect(sc, ray, &lh)) {
                 if (!sc.prim_light.empty() && sc.prim_light[lh.prim] == li) Li2 = area_l(light, lh.n, -wi);
             } else if (light.type == B200PT_LIGHT_INFINITE) {
-                Li2 = infinite_le(light, ray);  // Light::le; zero for area lights (light/mod.rs default)
+                Li2 = infinite_le(sc, li, ray);  // Light::le; zero for area lights (light/mod.rs default)
             }
             if (!is_black(Li2)) ld += f * Li2 * RGB(1.0f) * weight / scattering_pdf;
         }
@@ -959,7 +966,7 @@ inline RGB path_li(RenderScene& sc, Ray ray, Sampler& sampler) {
                 int al = sc.prim_light.empty() ? -1 : sc.prim_light[isect.prim];
                 if (al >= 0) L += beta * area_l(sc.lights[al], isect.n, -ray_d);
             } else {
-                for (int li : sc.infinite_lights) L += beta * infinite_le(sc.lights[li], ray);
+                for (int li : sc.infinite_lights) L += beta * infinite_le(sc, li, ray);
             }
         }
         if (!found || bounces >= sc.integ.max_depth) break;

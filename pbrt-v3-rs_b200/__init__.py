@@ -50,7 +50,8 @@ class Material(C.Structure):
 
 class Light(C.Structure):
     _fields_ = [("type", C.c_int32), ("pos", C.c_float * 3), ("L", C.c_float * 3), ("prim", C.c_int32),
-                ("two_sided", C.c_int32), ("light_to_world", C.c_float * 16), ("world_to_light", C.c_float * 16)]
+                ("two_sided", C.c_int32), ("light_to_world", C.c_float * 16), ("world_to_light", C.c_float * 16),
+                ("map_rgb", C.c_void_p), ("map_width", C.c_int32), ("map_height", C.c_int32)]
 
 
 class Camera(C.Structure):
@@ -104,6 +105,7 @@ def lib():
     L.b200pt_last_error.restype = C.c_char_p
     L.b200pt_device_l2_bytes.restype = i64
     L.b200pt_launch_count.restype = i64
+    L.b200pt_envmap_prepare.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.b200pt_init.argtypes = [C.c_int]
     L.b200pt_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_triangle_bounds.argtypes = [vp, i64, vp]
@@ -171,6 +173,20 @@ def build_bvh_sah(prim_bounds, max_prims_in_node=4):
     _check(lib().b200pt_bvh_build_sah(_ptr(pb), n, int(max_prims_in_node), _ptr(nodes), C.byref(nn), _ptr(ordered)),
            "b200pt_bvh_build_sah")
     return nodes[:nn.value].copy(), ordered[:n].copy()
+
+
+def envmap_prepare(image, L=(1.0, 1.0, 1.0)):
+    """Host-side InfiniteAreaLight::new preparation (no GPU): -> (level0 (h0, w0, 3), importance (2 h0, 2 w0), power_lookup (3,))."""
+    img = None if image is None else np.ascontiguousarray(image, dtype=np.float32)
+    h, w = (0, 0) if img is None else img.shape[:2]
+    Lf = np.asarray(L, dtype=np.float32)
+    size = np.zeros(4, dtype=np.int32)
+    _check(lib().b200pt_envmap_prepare(_ptr(img), w, h, _ptr(Lf), _ptr(size), None, None, None), "b200pt_envmap_prepare")
+    lvl0 = np.zeros((size[1], size[0], 3), dtype=np.float32)
+    imp = np.zeros((size[3], size[2]), dtype=np.float32)
+    pw = np.zeros(3, dtype=np.float32)
+    _check(lib().b200pt_envmap_prepare(_ptr(img), w, h, _ptr(Lf), _ptr(size), _ptr(lvl0), _ptr(imp), _ptr(pw)), "b200pt_envmap_prepare")
+    return lvl0, imp, pw
 
 
 class BVHAccel:

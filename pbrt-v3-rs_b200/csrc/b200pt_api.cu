@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_envmap.h"
 
 namespace b2 {
 std::atomic<int64_t> g_launches{0};
@@ -191,6 +192,20 @@ int b200pt_init(int device) {
     g_device = device;
     g_sm_count = prop.multiProcessorCount;
     g_l2_bytes = prop.l2CacheSize;
+    return B200PT_OK;
+}
+
+int b200pt_envmap_prepare(const float* map_rgb, int32_t map_width, int32_t map_height, const float L[3], int32_t size4[4],
+                          float* level0_rgb_out, float* importance_out, float power_lookup_out[3]) {
+    if (!L || !size4 || map_width < 0 || map_height < 0) { b200pt_set_error("b200pt_envmap_prepare: invalid argument"); return B200PT_ERR_INVALID; }
+    b2host::EnvMapTables em;
+    b2host::build_envmap(map_rgb, map_width, map_height, L, &em);
+    size4[0] = em.width; size4[1] = em.height; size4[2] = em.nu; size4[3] = em.nv;
+    if (level0_rgb_out)
+        for (size_t k = 0; k < (size_t)em.width * em.height; ++k)
+            for (int c = 0; c < 3; ++c) level0_rgb_out[3 * k + c] = em.texels[4 * k + c];
+    if (importance_out) std::memcpy(importance_out, em.cond_func.data(), em.cond_func.size() * sizeof(float));
+    if (power_lookup_out) std::memcpy(power_lookup_out, em.power_lookup, 12);
     return B200PT_OK;
 }
 

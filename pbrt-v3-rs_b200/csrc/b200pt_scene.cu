@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "host_sampler.h"
+#include "host_envmap.h"
 #include "instancing.cuh"
 #include "shade.cuh"
 
@@ -281,7 +282,10 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
         if (found) {
             if (alight >= 0) L = L + beta * area_l(S.lights[alight], sh.n, -ray_d);
         } else {
-            for (int i = 0; i < S.n_infinite; ++i) L = L + beta * infinite_le(S.lights[S.infinite_lights[i]], ray_d);
+            for (int i = 0; i < S.n_infinite; ++i) {
+                const DLight& il = S.lights[S.infinite_lights[i]];
+                L = L + beta * infinite_le(il, S.inf_distr[il.inf_slot], ray_d);
+            }
         }
     }
     if (!found || bounces >= S.max_depth) {  // path.rs:137
@@ -356,8 +360,8 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
             } else {  // InfiniteAreaLight::sample_li, infinite.rs:133-175
                 const DInfDistr& D = S.inf_distr[light.inf_slot];
                 float pdf1, pdf0; int v, dummy;
-                float d1 = distr_sample_continuous(D.mfunc, D.mcdf, D.mfunc_int, 2, u_light.y, &pdf1, &v);
-                float d0 = distr_sample_continuous(D.func[v], D.cdf[v], D.func_int[v], 2, u_light.x, &pdf0, &dummy);
+                float d1 = distr_sample_continuous(D.mfunc, D.mcdf, D.mfunc_int, D.nv, u_light.y, &pdf1, &v);
+                float d0 = distr_sample_continuous(D.func + (long long)v * D.nu, D.cdf + (long long)v * (D.nu + 1), D.func_int[v], D.nu, u_light.x, &pdf0, &dummy);
                 float map_pdf = pdf0 * pdf1;
                 if (map_pdf != 0.0f) {
                     float theta = d1 * kPi, phi = d0 * kTwoPi;
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
                     light_pdf = map_pdf / (kTwoPi * kPi * sin_t);
                     if (sin_t == 0.0f) light_pdf = 0.0f;
                     lp1 = sh.p + wi * (2.0f * S.world_radius);
-                    Li = inf_lookup(ldrgb(light.L), mk2(d0, d1));
+                    Li = inf_lookup(D, mk2(d0, d1));
                     li_valid = true;
                 }
             }
@@ -419,10 +423,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
                             if (sin_t == 0.0f) lp = 0.0f;
                             else {
                                 const DInfDistr& D = S.inf_distr[light.inf_slot];
-                                float fu = phi * kInvTwoPi * 2.0f, fv = theta * kInvPi * 2.0f;  // Distribution2D::pdf, distribution_2d.rs
-                                int iu = (!(fu == fu) || fu <= 0.0f) ? 0 : (int)fu; iu = iu > 1 ? 1 : iu;
-                                int iv = (!(fv == fv) || fv <= 0.0f) ? 0 : (int)fv; iv = iv > 1 ? 1 : iv;
-                                lp = (D.func[iv][iu] / D.mfunc_int) / (kTwoPi * kPi * sin_t);
+                                lp = distr2d_pdf(D, phi * kInvTwoPi, theta * kInvPi) / (kTwoPi * kPi * sin_t);
                             }
                         }
                         if (lp == 0.0f) ok = false;  // common.rs:258-260: return ld
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(256) k_resolve(DeviceScene S, Wave W, int n_pe
                 Li = area_l(light, n, -wi);
             }
         } else if (light.type == LT_INFINITE) {
-            Li = infinite_le(light, wi);
+            Li = infinite_le(light, S.inf_distr[light.inf_slot], wi);
         }
         if (!is_black(Li)) ld = ld + rgb(b.x, b.y, b.z) * Li * rgb1(1.0f) * b.w / c.w;
     }
@@ -1016,28 +1017,22 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         } else if (l.type == B200PT_LIGHT_INFINITE) {
             o.inf_slot = (int)inf_distr.size();
             inf_ids.push_back(i);
-            DInfDistr dd;  // compute_scalar_image + Distribution2D::new, infinite.rs:326-369
-            std::vector<float> mf;
-            for (int v = 0; v < 2; ++v) {
-                float vp = ((float)v + 0.5f) / 2.0f;
-                float sin_t = std::sin(kPi * ((float)v + 0.5f) / 2.0f);
-                std::vector<float> row;
-                for (int u = 0; u < 2; ++u) {
-                    float up = ((float)u + 0.5f) / 2.0f;
-                    row.push_back(lum_y(h_inf_lookup(l.L, up, vp)) * sin_t);
-                }
-                HostDistr1D h; h.init(row);
-                for (int u = 0; u < 2; ++u) dd.func[v][u] = h.func[u];
-                for (int u = 0; u < 3; ++u) dd.cdf[v][u] = h.cdf[u];
-                dd.func_int[v] = h.func_int;
-                mf.push_back(h.func_int);
-            }
-            HostDistr1D m; m.init(mf);
-            for (int u = 0; u < 2; ++u) dd.mfunc[u] = m.func[u];
-            for (int u = 0; u < 3; ++u) dd.mcdf[u] = m.cdf[u];
-            dd.mfunc_int = m.func_int;
+            // InfiniteAreaLight::new (infinite.rs:61-92): MIPMap, importance image, Distribution2D
+            b2host::EnvMapTables em;
+            b2host::build_envmap(l.map_rgb, l.map_width, l.map_height, l.L, &em);
+            DInfDistr dd;
+            std::memset(&dd, 0, sizeof(dd));
+            dd.width = em.width; dd.height = em.height; dd.nu = em.nu; dd.nv = em.nv; dd.mfunc_int = em.marg_int;
+            const float* tex = nullptr;
+            if ((rc = dev_upload(s, em.texels, &tex))) return fail(rc);
+            dd.texels = (const float4*)tex;
+            if ((rc = dev_upload(s, em.cond_func, &dd.func))) return fail(rc);
+            if ((rc = dev_upload(s, em.cond_cdf, &dd.cdf))) return fail(rc);
+            if ((rc = dev_upload(s, em.cond_int, &dd.func_int))) return fail(rc);
+            if ((rc = dev_upload(s, em.marg_func, &dd.mfunc))) return fail(rc);
+            if ((rc = dev_upload(s, em.marg_cdf, &dd.mcdf))) return fail(rc);
             inf_distr.push_back(dd);
-            RGB spec = h_inf_lookup(l.L, 0.5f, 0.5f);  // infinite.rs:177-186
+            RGB spec = rgb(em.power_lookup[0], em.power_lookup[1], em.power_lookup[2]);  // infinite.rs:177-186
             power = kPi * radius * radius * spec;
         } else { b200pt_set_error("b200pt_scene_create: unknown light type"); return fail(B200PT_ERR_INVALID); }
         power_y[(size_t)i] = lum_y(power);

@@ -427,10 +427,18 @@ struct DLight {
     float l2w[9];    // infinite: upper 3x3 of light_to_world (row-major)
     float w2l[9];
 };
-// Distribution2D of a constant infinite light (2x2 image, infinite.rs:326-369) — tiny, by value.
+// Environment map of an InfiniteAreaLight (host_envmap.cpp): level 0 of its MIPMap (float4 texels already multiplied by
+// L; 1x1 without a "mapname") and the Distribution2D over the (2w x 2h) importance image (infinite.rs:326-369).
 struct DInfDistr {
-    float func[2][2], cdf[2][3], func_int[2];
-    float mfunc[2], mcdf[3], mfunc_int;
+    const float4* texels;
+    int width, height;
+    int nu, nv;
+    const float* func;      // nv x nu
+    const float* cdf;       // nv x (nu + 1)
+    const float* func_int;  // nv
+    const float* mfunc;     // nv
+    const float* mcdf;      // nv + 1
+    float mfunc_int;
 };
 
 // core/src/pbrt/common.rs:251-276 over a cdf array of `size` entries
@@ -455,12 +463,32 @@ B2_D float distr_sample_continuous(const float* func, const float* cdf, float fu
     return ((float)offset + du) / (float)n;
 }
 
-// 1x1 constant environment map through MIPMap::triangle (core/src/mipmap/mod.rs:280-311)
-B2_D RGB inf_lookup(RGB L, P2 st) {
-    float s = st.x * 1.0f - 0.5f, t = st.y * 1.0f - 0.5f;
-    float s0 = floorf(s), t0 = floorf(t);
-    float ds = s - s0, dt = t - t0;
-    return L * (1.0f - ds) * (1.0f - dt) + L * (1.0f - ds) * dt + L * ds * (1.0f - dt) + L * ds * dt;
+// l_map.lookup_triangle(st, 0.0): width 0 always selects MIPMap::triangle(0, st) (core/src/mipmap/mod.rs:226-247,
+// 280-311): bilinear blend of four level-0 texels, ImageWrap::Repeat (texel(), :577-608).
+B2_D int wrap_index(int a, int n) {  // pbrt::rem, common.rs:116-126
+    int r = a - (a / n) * n;
+    return r < 0 ? r + n : r;
+}
+B2_D RGB env_texel(const DInfDistr& D, int s, int t) {
+    float4 q = __ldg(D.texels + (long long)wrap_index(t, D.height) * D.width + wrap_index(s, D.width));
+    return rgb(q.x, q.y, q.z);
+}
+B2_D RGB inf_lookup(const DInfDistr& D, P2 st) {
+    float s = st.x * (float)D.width - 0.5f, t = st.y * (float)D.height - 0.5f;
+    float fs = floorf(s), ft = floorf(t);
+    int s0 = (int)fs, t0 = (int)ft;
+    float ds = s - (float)s0, dt = t - (float)t0;
+    return env_texel(D, s0, t0) * (1.0f - ds) * (1.0f - dt) + env_texel(D, s0, t0 + 1) * (1.0f - ds) * dt + env_texel(D, s0 + 1, t0) * ds * (1.0f - dt) +
+           env_texel(D, s0 + 1, t0 + 1) * ds * dt;
+}
+// Distribution2D::pdf, sampling/distribution_2d.rs (`as usize` saturates, then clamp)
+B2_D float distr2d_pdf(const DInfDistr& D, float u, float v) {
+    float fu = u * (float)D.nu, fv = v * (float)D.nv;
+    int iu = (!(fu == fu) || fu <= 0.0f) ? 0 : (fu >= 2147483520.0f ? D.nu - 1 : (int)fu);
+    int iv = (!(fv == fv) || fv <= 0.0f) ? 0 : (fv >= 2147483520.0f ? D.nv - 1 : (int)fv);
+    iu = iu > D.nu - 1 ? D.nu - 1 : iu;
+    iv = iv > D.nv - 1 ? D.nv - 1 : iv;
+    return D.func[(long long)iv * D.nu + iu] / D.mfunc_int;
 }
 B2_D V3 xf3(const float* m, V3 v) {  // Transform::transform_vector, transform.rs:373-380
     return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
@@ -468,10 +496,10 @@ B2_D V3 xf3(const float* m, V3 v) {  // Transform::transform_vector, transform.r
 B2_D float spherical_theta(V3 v) { return acosf(pclamp(v.z, -1.0f, 1.0f)); }  // geometry/util.rs:41-43
 B2_D float spherical_phi(V3 v) { float p = atan2f(v.y, v.x); return p < 0.0f ? p + kTwoPi : p; }  // :49-56
 // InfiniteAreaLight::le, infinite.rs:188-199
-B2_D RGB infinite_le(const DLight& l, V3 ray_d) {
+B2_D RGB infinite_le(const DLight& l, const DInfDistr& D, V3 ray_d) {
     V3 w = normalize(xf3(l.w2l, ray_d));
     P2 st = mk2(spherical_phi(w) * kInvTwoPi, spherical_theta(w) * kInvPi);
-    return inf_lookup(ldrgb(l.L), st);
+    return inf_lookup(D, st);
 }
 // DiffuseAreaLight::l, diffuse.rs:220-226
 B2_D RGB area_l(const DLight& l, V3 n, V3 w) { return (l.two_sided || dot(n, w) > 0.0f) ? ldrgb(l.L) : rgb1(0.0f); }

@@ -195,8 +195,17 @@ class SceneDescription:
     def add_point_light(self, pos, I):
         self.lights.append(dict(type="point", pos=tuple(pos), L=tuple(I)))
 
-    def add_infinite_light(self, L):
-        self.lights.append(dict(type="infinite", L=tuple(L)))
+    def add_infinite_light(self, L, image=None, light_to_world=None):
+        """LightSource "infinite": ``L`` (times "scale"), optional environment ``image`` = decoded "mapname" as an
+        (h, w, 3) float32 array (top row first, lat-long), optional 4x4 ``light_to_world``."""
+        l = dict(type="infinite", L=tuple(L))
+        if image is not None:
+            l["image"] = np.ascontiguousarray(image, dtype=F32)
+            assert l["image"].ndim == 3 and l["image"].shape[2] == 3
+        if light_to_world is not None:
+            m = np.asarray(light_to_world, dtype=F32).reshape(4, 4)
+            l["light_to_world"], l["world_to_light"] = m.reshape(-1), _m4_inverse(m).reshape(-1)
+        self.lights.append(l)
 
     # -- flattening --
     # -- instancing: ObjectBegin/ObjectEnd + ObjectInstance (api/src/lib.rs:880-987) --
@@ -341,6 +350,10 @@ class SceneDescription:
                 Lt.two_sided = 1 if l.get("twosided") else 0
             elif l["type"] == "infinite":
                 Lt.type = LIGHT_INFINITE
+                if l.get("image") is not None:
+                    keep.append(l["image"])
+                    Lt.map_rgb = l["image"].ctypes.data_as(C.c_void_p)
+                    Lt.map_height, Lt.map_width = l["image"].shape[:2]
             else:
                 raise ValueError("light %r is outside this path" % l["type"])
         keep.append(lights)

@@ -209,6 +209,24 @@ def shadow_rays(closest_rays, radius=2.5):
     return rays
 
 
+def sky_image(width, height, seed=7, sun=(0.3, 0.25), sun_radius=0.04, sun_radiance=400.0):
+    """Procedural HDR lat-long environment (height, width, 3) float32: a blue-to-white sky gradient over a brown
+    ground, value-noise clouds and a small, very bright sun at (u, v) = ``sun`` — a stand-in for the EXR maps of the
+    pbrt-v3 scenes (scenes/materials/matte.pbrt:18-19)."""
+    v = ((np.arange(height, dtype=F32) + F32(0.5)) / F32(height))[:, None].repeat(width, 1)
+    u = ((np.arange(width, dtype=F32) + F32(0.5)) / F32(width))[None, :].repeat(height, 0)
+    sky = np.stack([F32(0.35) + F32(0.5) * v, F32(0.55) + F32(0.35) * v, F32(1.0) - F32(0.1) * v], axis=-1).astype(F32)
+    ground = np.array([0.25, 0.2, 0.15], dtype=F32)
+    img = np.where((v < 0.5)[..., None], sky, ground[None, None, :]).astype(F32)
+    d = np.stack([np.cos(u * F32(2 * np.pi)), v * F32(2.0), np.sin(u * F32(2 * np.pi))], axis=-1).reshape(-1, 3).astype(F32)
+    clouds = value_noise(d, 3.0, seed).reshape(height, width)
+    img += (F32(0.6) * np.maximum(clouds - F32(0.55), F32(0)) * (v < 0.5))[..., None]
+    du = np.minimum(np.abs(u - F32(sun[0])), F32(1) - np.abs(u - F32(sun[0])))
+    r2 = du * du + (v - F32(sun[1])) ** 2
+    img += (F32(sun_radiance) * np.exp(-r2 / F32(sun_radius * sun_radius)))[..., None] * np.array([1.0, 0.9, 0.7], dtype=F32)
+    return img.astype(F32)
+
+
 C2_FULL = dict(nu=1000, nv=500, width=4096, height=2048)       # 1 000 000 tris, 2^23 primary + 2^23 bounce
 C2_SMALL = dict(nu=100, nv=50, width=128, height=64)           # 10 000 tris, 2^13 + 2^13 (CPU-test size)
 

@@ -47,6 +47,8 @@ def lib():
         L.orc_accel_create.argtypes = [vp, i64, vp, vp, vp, i64]
         L.orc_accel_destroy.argtypes = [vp]
         L.orc_accel_set_uvs.argtypes = [vp, vp, i64]
+        L.orc_envmap_prepare.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+        L.orc_envmap_lookup.argtypes = [vp, C.c_int, C.c_int, vp, C.c_float, vp]
         L.orc_triangle_geometry.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
         L.orc_intersect_batch.argtypes = [vp, vp, i64, vp, vp, vp, C.c_int]
         L.orc_occluded_batch.argtypes = [vp, vp, i64, vp, vp, C.c_int]
@@ -140,6 +142,27 @@ def triangle_geometry(verts9, b, uv=None, normals=None, tangents=None, flip=Fals
         return None
     names = ["p", "p_error", "n", "dpdu", "dpdv", "shading_n", "shading_dpdu"]
     return {k: out[3 * i:3 * i + 3].copy() for i, k in enumerate(names)}
+
+
+def envmap_prepare(image, L=(1.0, 1.0, 1.0)):
+    img = None if image is None else np.ascontiguousarray(image, dtype=np.float32)
+    h, w = (0, 0) if img is None else img.shape[:2]
+    Lf = np.asarray(L, dtype=np.float32)
+    size = np.zeros(4, dtype=np.int32)
+    lib().orc_envmap_prepare(_p(img), w, h, _p(Lf), _p(size), None, None, None)
+    lvl0 = np.zeros((size[1], size[0], 3), dtype=np.float32)
+    imp = np.zeros((size[3], size[2]), dtype=np.float32)
+    pw = np.zeros(3, dtype=np.float32)
+    lib().orc_envmap_prepare(_p(img), w, h, _p(Lf), _p(size), _p(lvl0), _p(imp), _p(pw))
+    return lvl0, imp, pw
+
+
+def envmap_lookup(image, st, width):
+    img = np.ascontiguousarray(image, dtype=np.float32)
+    out = np.zeros(3, dtype=np.float32)
+    s2 = np.asarray(st, dtype=np.float32)
+    lib().orc_envmap_lookup(_p(img), img.shape[1], img.shape[0], _p(s2), float(width), _p(out))
+    return out
 
 
 class OracleScene:

@@ -279,3 +279,67 @@ def test_smooth_shading_changes_the_oracle_image(oracle):
     ib, sb, _ = oracle.OracleScene(b).render(nthreads=2)
     assert np.isfinite(ib).all() and sa[0] == sb[0]
     assert ss.rel_rmse(ia, ib) > 1e-2
+
+
+def test_mipmap_pyramid_and_lookups_hand_checked(oracle):
+    """core/src/mipmap/mod.rs on a 2x2 and a 4x2 image: box-filtered pyramid, bilinear level-0 lookup with repeat
+    wrap, level selection of lookup_triangle."""
+    img = np.float32([[[1, 1, 1], [3, 3, 3]], [[5, 5, 5], [7, 7, 7]]])
+    # width 0 -> triangle(0): at a texel centre exactly that texel, halfway between two centres their mean
+    assert np.array_equal(oracle.envmap_lookup(img, (0.25, 0.25), 0.0), [1, 1, 1])
+    assert np.array_equal(oracle.envmap_lookup(img, (0.75, 0.75), 0.0), [7, 7, 7])
+    assert np.array_equal(oracle.envmap_lookup(img, (0.5, 0.25), 0.0), [2, 2, 2])
+    # repeat wrap: s = 0 lies between texel -1 (= texel 1) and texel 0
+    assert np.array_equal(oracle.envmap_lookup(img, (0.0, 0.25), 0.0), [2, 2, 2])
+    # width >= 1 selects the 1x1 top level = mean of the four texels
+    assert np.array_equal(oracle.envmap_lookup(img, (0.1, 0.9), 1.0), [4, 4, 4])
+    # 2 levels: width 0.5 -> level = 1 - 1 = 0 exactly -> triangle(0) (delta 0, blended with weight 0 of level 1)
+    assert np.array_equal(oracle.envmap_lookup(img, (0.25, 0.25), 0.5), [1, 1, 1])
+    # width 2^-0.5 -> level 0.5: halfway between the level-0 value and the level-1 mean
+    v = oracle.envmap_lookup(img, (0.25, 0.25), 2.0 ** -0.5)
+    assert np.allclose(v, [2.5] * 3, atol=1e-6)
+    # 4x2: level 1 is 2x1 with the two 2x2 block means
+    img2 = np.arange(24, dtype=np.float32).reshape(2, 4, 3)
+    lvl1_left = img2[:, :2].reshape(-1, 3).mean(0)
+    assert np.allclose(oracle.envmap_lookup(img2, (0.25, 0.5), 0.5), lvl1_left)  # level 1, at the centre of its left texel
+
+
+def test_envmap_resampler_and_importance_image(oracle, pkg):
+    """Non-power-of-two maps go through the Lanczos resampler (mod.rs:373-575).  A constant image stays constant,
+    first-texel taps saturate at 0 (float -> usize cast), and the product's host code reproduces the oracle's level 0,
+    importance image and power lookup bit for bit."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    const = np.full((3, 5, 3), 2.0, dtype=np.float32)
+    lvl0, imp, pw = oracle.envmap_prepare(const, (1.0, 0.5, 0.25))
+    assert lvl0.shape == (4, 8, 3) and imp.shape == (8, 16)
+    assert np.allclose(lvl0[..., 0], 2.0, atol=1e-5) and np.allclose(lvl0[..., 2], 0.5, atol=1e-5)
+    # independent numpy restatement of resample_weights for 3 -> 4
+    def weights(old, new):
+        out = []
+        for i in range(new):
+            c = np.float32((np.float32(i) + np.float32(0.5)) * np.float32(old) / np.float32(new))
+            first = max(0, int(np.floor(np.float32(c - np.float32(2.0)) + np.float32(0.5))))
+            w = []
+            for j in range(4):
+                x = abs((np.float32(first + j) + np.float32(0.5) - c) / np.float32(2.0))
+                w.append(1.0 if x < 1e-5 else (0.0 if x > 1.0 else float(np.sin(np.pi * x * 2) / (np.pi * x * 2) * np.sin(np.pi * x) / (np.pi * x))))
+            w = np.array(w) / sum(w)
+            out.append((first, w))
+        return out
+    row = np.float32([[[1, 1, 1], [4, 4, 4], [2, 2, 2]]])  # 3 x 1 -> 4 x 1
+    l0 = oracle.envmap_prepare(row)[0]
+    exp = []
+    for first, w in weights(3, 4):
+        exp.append(max(0.0, sum(w[j] * row[0, (first + j) % 3, 0] for j in range(4))))
+    assert np.allclose(l0[0, :, 0], exp, rtol=1e-5, atol=1e-6)
+    assert weights(3, 4)[0][0] == 0  # the saturating cast: taps of texel 0 start at 0, not at -1
+    # product host code == oracle, pow2 and non-pow2, with and without a map
+    for img in (None, wl.sky_image(16, 8), wl.sky_image(20, 9), wl.sky_image(64, 4)):
+        a = oracle.envmap_prepare(img, (0.9, 1.0, 1.1))
+        b = pkg.envmap_prepare(img, (0.9, 1.0, 1.1))
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and x.tobytes() == y.tobytes()
+    # the importance image follows the map: the sun's texels dominate
+    _, imp, _ = oracle.envmap_prepare(wl.sky_image(64, 32))
+    iv, iu = np.unravel_index(np.argmax(imp), imp.shape)
+    assert abs(iu / imp.shape[1] - 0.3) < 0.05 and abs(iv / imp.shape[0] - 0.25) < 0.05

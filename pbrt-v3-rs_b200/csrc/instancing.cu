@@ -92,9 +92,8 @@ B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, in
         } else {
             long long first = (long long)(~cur);
             V3 p0, p1, p2;
-            float4 duv;
             uint32_t prim, flags, leaf_n;
-            load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
+            load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n);
             for (uint32_t i = 0;;) {
                 if (flags & 0x80000000u) {  // TransformedPrimitive
                     const float4* T = A2.inst_trav + 6ll * prim;
@@ -116,7 +115,7 @@ B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, in
                     }
                 } else {
                     float t, b0, b1, b2;
-                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, first + i)) {
                         if (ANY) {
                             if (!(flags & 6u)) return true;
                         } else if (!(flags & 2u)) {
@@ -129,7 +128,7 @@ B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, in
                 }
                 if (++i >= leaf_n) break;
                 uint32_t dummy;
-                load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy, &duv);
+                load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy);
             }
         }
         for (;;) {
@@ -275,10 +274,9 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
                 }
             } else if (cur < 0 && cur != kIdle) {
                 V3 p0, p1, p2;
-                float4 duv;
                 uint32_t prim, flags, leaf_n;
                 if (tri_left == 0) tri_i = (long long)(~cur);
-                load_tri(A.tris, tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
+                load_tri(A.tris, tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n);
                 if (tri_left == 0) tri_left = leaf_n;
                 ++tri_i;
                 --tri_left;
@@ -309,7 +307,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
                     } else if (tri_left == 0) retire = true;
                 } else {
                     float t, b0, b1, b2;
-                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, tri_i - 1)) {
                         if (ANY) {
                             if (!(flags & 6u)) { hit = true; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
                         } else if (!(flags & 2u)) {
@@ -498,10 +496,9 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
                 }
             } else if (pend != kIdle) {
                 V3 p0, p1, p2;
-                float4 duv;
                 uint32_t prim, flags, leaf_n;
                 if (tri_left == 0) tri_i = ~pend;
-                load_tri(A.tris, (long long)tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
+                load_tri(A.tris, (long long)tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n);
                 if (tri_left == 0) tri_left = leaf_n;
                 ++tri_i;
                 --tri_left;
@@ -537,7 +534,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
                     }
                 } else {
                     float t, b0, b1, b2;
-                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)tri_i - 1)) {
                         if (ANY) {
                             if (!(flags & 6u)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
                         } else if (!(flags & 2u)) {

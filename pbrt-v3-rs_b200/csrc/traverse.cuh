@@ -202,13 +202,19 @@ B2_D bool triangle_nondegenerate(V3 p0, V3 p1, V3 p2, float4 duv) {
     return true;
 }
 
-B2_D void load_tri(const float4* tris, long long i, V3* p0, V3* p1, V3* p2, uint32_t* prim, uint32_t* flags, uint32_t* leaf_n, float4* duv) {
+// The uv differences are fetched only for a candidate that passed the triangle test (rare): keeping them live across
+// the test costs four registers, which pushed the default kernels over their occupancy boundary (-9 %).
+// Out of line on purpose: it runs once per accepted candidate and must not shape the register allocation of the walk.
+static __device__ __noinline__ bool triangle_nondegenerate(V3 p0, V3 p1, V3 p2, const float4* tris, long long i) {
+    return triangle_nondegenerate(p0, p1, p2, __ldg(tris + 4 * i + 3));
+}
+
+B2_D void load_tri(const float4* tris, long long i, V3* p0, V3* p1, V3* p2, uint32_t* prim, uint32_t* flags, uint32_t* leaf_n) {
     float4 a, b, c, d;
     ldg8(tris + 4 * i, &a, &b);
     ldg8(tris + 4 * i + 2, &c, &d);
     *p0 = mk(a.x, a.y, a.z); *p1 = mk(a.w, b.x, b.y); *p2 = mk(b.z, b.w, c.x);
     *prim = __float_as_uint(c.y); *flags = __float_as_uint(c.z); *leaf_n = __float_as_uint(c.w);
-    *duv = d;
 }
 
 struct HitOut {
@@ -269,12 +275,11 @@ B2_D bool traverse_wide(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
         } else {
             long long first = (long long)(~cur);
             V3 p0, p1, p2;
-            float4 duv;
             uint32_t prim, flags, leaf_n;
-            load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
+            load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n);
             for (uint32_t i = 0;;) {
                 float t, b0, b1, b2;
-                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, first + i)) {
                     if (ANY) {
                         if (!(flags & 6u)) return true;  // alpha / shadow-alpha == 0 reject (triangle.rs:886-899)
                     } else if (!(flags & 2u)) {          // alpha == 0 reject (triangle.rs:587-607)
@@ -285,7 +290,7 @@ B2_D bool traverse_wide(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
                 }
                 if (++i >= leaf_n) break;
                 uint32_t dummy;
-                load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy, &duv);
+                load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy);
             }
         }
         // pop
@@ -326,11 +331,10 @@ B2_D bool traverse_ref(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
             if (nprims > 0) {
                 for (uint32_t i = 0; i < nprims; ++i) {
                     V3 p0, p1, p2;
-                    float4 duv;
                     uint32_t prim, flags, dummy;
-                    load_tri(A.tris, (long long)offset + i, &p0, &p1, &p2, &prim, &flags, &dummy, &duv);
+                    load_tri(A.tris, (long long)offset + i, &p0, &p1, &p2, &prim, &flags, &dummy);
                     float t, b0, b1, b2;
-                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                    if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)offset + i)) {
                         if (ANY) {
                             if (!(flags & 6u)) return true;
                         } else if (!(flags & 2u)) {

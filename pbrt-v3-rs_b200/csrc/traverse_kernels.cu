@@ -124,13 +124,12 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
                 } else {
                     long long first = (long long)(~cur);
                     V3 p0, p1, p2;
-                    float4 duv;
                     uint32_t prim, flags, leaf_n;
-                    load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
+                    load_tri(A.tris, first, &p0, &p1, &p2, &prim, &flags, &leaf_n);
                     bool any_done = false;
                     for (uint32_t i = 0;;) {
                         float t, b0, b1, b2;
-                        if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                        if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, first + i)) {
                             if (ANY) {
                                 if (!(flags & 6u)) { any_done = true; break; }
                             } else if (!(flags & 2u)) {
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
                         }
                         if (++i >= leaf_n) break;
                         uint32_t dummy;
-                        load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy, &duv);
+                        load_tri(A.tris, first + i, &p0, &p1, &p2, &prim, &flags, &dummy);
                     }
                     if (ANY && any_done) { hit = true; sp = 0; }
                     cur = kDone;
@@ -198,12 +197,11 @@ __global__ void __launch_bounds__(128) k_count(DeviceAccel A, const float4* __re
                 if (nprims > 0) {
                     for (uint32_t k = 0; k < nprims && !done; ++k) {
                         V3 p0, p1, p2;
-                        float4 duv;
                         uint32_t prim, flags, dummy;
-                        load_tri(A.tris, (long long)offset + k, &p0, &p1, &p2, &prim, &flags, &dummy, &duv);
+                        load_tri(A.tris, (long long)offset + k, &p0, &p1, &p2, &prim, &flags, &dummy);
                         float t, b0, b1, b2;
                         ++nt;
-                        if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                        if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)offset + k)) {
                             if (ANY) { if (!(flags & 6u)) done = true; }
                             else if (!(flags & 2u)) t_max = t;
                         }

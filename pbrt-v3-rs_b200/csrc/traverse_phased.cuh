@@ -163,13 +163,12 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
                 }
             } else if (cur < 0 && cur != kIdle) {
                 V3 p0, p1, p2;
-                float4 duv;
                 uint32_t prim, flags, leaf_n;
                 if (tri_left == 0) tri_i = (long long)(~cur);
-                load_tri(A.tris, tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
+                load_tri(A.tris, tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n);
                 if (tri_left == 0) tri_left = leaf_n;
                 float t, b0, b1, b2;
-                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, tri_i)) {
                     if (ANY) {
                         if (!(flags & 6u)) { hit = true; sp = 0; top_code = kIdle; tri_left = 1; }
                     } else if (!(flags & 2u)) {

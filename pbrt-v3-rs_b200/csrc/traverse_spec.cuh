@@ -156,13 +156,12 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec(DeviceAccel A, cons
                 }
             } else if (pend != kIdle) {
                 V3 p0, p1, p2;
-                float4 duv;
                 uint32_t prim, flags, leaf_n;
                 if (tri_left == 0) tri_i = ~pend;
-                load_tri(A.tris, (long long)tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
+                load_tri(A.tris, (long long)tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n);
                 if (tri_left == 0) tri_left = leaf_n;
                 float t, b0, b1, b2;
-                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)tri_i)) {
                     if (ANY) {
                         if (!(flags & 6u)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; tri_left = 1; }  // occluded: drop the rest of the walk
                     } else if (!(flags & 2u)) {
@@ -340,13 +339,12 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2(DeviceAccel A, con
                 }
             } else if (pend != kIdle) {
                 V3 p0, p1, p2;
-                float4 duv;
                 uint32_t prim, flags, leaf_n;
                 if (tri_left == 0) tri_i = ~pend;
-                load_tri(A.tris, (long long)tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n, &duv);
+                load_tri(A.tris, (long long)tri_i, &p0, &p1, &p2, &prim, &flags, &leaf_n);
                 if (tri_left == 0) tri_left = leaf_n;
                 float t, b0, b1, b2;
-                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, duv)) {
+                if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)tri_i)) {
                     if (ANY) {
                         if (!(flags & 6u)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; tri_left = 1; }
                     } else if (!(flags & 2u)) {

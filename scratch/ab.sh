@@ -1,2 +1,2 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c5.csv python tools/run_config.py c5 --spp 4 --li 0 --reps 1 > gpurun_out/ncu_c5.log 2>&1
-tail -2 gpurun_out/ncu_c5.log
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_trace -o gpurun_out/prof_r1_spec2_final python tools/prof_traversal.py > gpurun_out/ncu_spec2.log 2>&1
+tail -3 gpurun_out/ncu_spec2.log

@@ -193,6 +193,7 @@ typedef struct b200pt_scene_desc {
 } b200pt_scene_desc;
 
 typedef struct b200pt_accel b200pt_accel; /* opaque: device-resident BVHAccel */
+typedef struct b200pt_loaded_scene b200pt_loaded_scene; /* opaque: a parsed scene file, owns the arrays of its scene_desc */
 typedef struct b200pt_scene b200pt_scene; /* opaque: device-resident Scene + PathIntegrator state */
 
 /* ---- library ---------------------------------------------------------- */
@@ -219,6 +220,21 @@ int b200pt_triangle_bounds(const float* tri_verts, int64_t n, float* bounds_out)
  * NULL to get the sizes: size4 = {level0_width, level0_height, importance_width, importance_height}. */
 int b200pt_envmap_prepare(const float* map_rgb, int32_t map_width, int32_t map_height, const float L[3], int32_t size4[4],
                           float* level0_rgb_out, float* importance_out, float power_lookup_out[3]);
+
+/* ---- scene ingestion (host only; api/src/lib.rs + api/src/parser, shapes/src/plymesh.rs, core/src/image_io.rs) ----
+ * Reads the subset of the pbrt-v3 scene format that reaches this path (perspective camera; image film; box / gaussian
+ * filter; halton / 02sequence sampler; path integrator; bvh accelerator; trianglemesh / plymesh shapes with P, N, S,
+ * uv/st, alpha, shadowalpha; matte / plastic / glass / metal with constant parameters; point / infinite (.pfm map) /
+ * diffuse area lights; transforms, attribute and transform stacks, named materials, object instancing, Include) and
+ * builds the BVHs with b200pt_bvh_build_sah.  Anything else returns B200PT_ERR_UNSUPPORTED with the offending directive
+ * in b200pt_last_error.  The returned desc stays valid until b200pt_loaded_scene_free. */
+int b200pt_load_pbrt(const char* path, b200pt_loaded_scene** out);
+const b200pt_scene_desc* b200pt_loaded_scene_desc(const b200pt_loaded_scene* s);
+const char* b200pt_loaded_scene_output(const b200pt_loaded_scene* s); /* Film "filename" */
+void b200pt_loaded_scene_free(b200pt_loaded_scene* s);
+/* PFM images, rgb = width x height x 3 floats, top row first. read: call with rgb_out NULL to get size2 = {w, h}. */
+int b200pt_write_pfm(const char* path, const float* rgb, int32_t width, int32_t height);
+int b200pt_read_pfm(const char* path, float* rgb_out, int32_t size2[2]);
 
 /* ---- accelerator: impl Primitive for BVHAccel --------------------------
  * Copies the arrays to the device; the caller keeps ownership of its own. */

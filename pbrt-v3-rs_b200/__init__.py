@@ -106,6 +106,15 @@ def lib():
     L.b200pt_device_l2_bytes.restype = i64
     L.b200pt_launch_count.restype = i64
     L.b200pt_envmap_prepare.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.b200pt_load_pbrt.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.b200pt_loaded_scene_desc.argtypes = [vp]
+    L.b200pt_loaded_scene_desc.restype = C.POINTER(SceneDesc)
+    L.b200pt_loaded_scene_output.argtypes = [vp]
+    L.b200pt_loaded_scene_output.restype = C.c_char_p
+    L.b200pt_loaded_scene_free.argtypes = [vp]
+    L.b200pt_loaded_scene_free.restype = None
+    L.b200pt_write_pfm.argtypes = [C.c_char_p, vp, i32, i32]
+    L.b200pt_read_pfm.argtypes = [C.c_char_p, vp, vp]
     L.b200pt_init.argtypes = [C.c_int]
     L.b200pt_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_triangle_bounds.argtypes = [vp, i64, vp]
@@ -173,6 +182,48 @@ def build_bvh_sah(prim_bounds, max_prims_in_node=4):
     _check(lib().b200pt_bvh_build_sah(_ptr(pb), n, int(max_prims_in_node), _ptr(nodes), C.byref(nn), _ptr(ordered)),
            "b200pt_bvh_build_sah")
     return nodes[:nn.value].copy(), ordered[:n].copy()
+
+
+class LoadedScene:
+    """A scene file read by the host-side loader (b200pt_load_pbrt): duck-types SceneDescription.to_desc() for
+    PathIntegrator, so ``PathIntegrator(load_pbrt("scene.pbrt")).render()`` is the reference's `pbrt scene.pbrt`."""
+
+    def __init__(self, path):
+        h = C.c_void_p()
+        _check(lib().b200pt_load_pbrt(os.fsencode(path), C.byref(h)), "b200pt_load_pbrt")
+        self._h = h
+        self.path = path
+
+    def to_desc(self):
+        return lib().b200pt_loaded_scene_desc(self._h).contents
+
+    @property
+    def output(self):
+        return lib().b200pt_loaded_scene_output(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.b200pt_loaded_scene_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def load_pbrt(path):
+    return LoadedScene(path)
+
+
+def write_pfm(path, rgb):
+    a = np.ascontiguousarray(rgb, dtype=np.float32)
+    _check(lib().b200pt_write_pfm(os.fsencode(path), _ptr(a), a.shape[1], a.shape[0]), "b200pt_write_pfm")
+
+
+def read_pfm(path):
+    size = np.zeros(2, dtype=np.int32)
+    _check(lib().b200pt_read_pfm(os.fsencode(path), None, _ptr(size)), "b200pt_read_pfm")
+    out = np.zeros((size[1], size[0], 3), dtype=np.float32)
+    _check(lib().b200pt_read_pfm(os.fsencode(path), _ptr(out), _ptr(size)), "b200pt_read_pfm")
+    return out
 
 
 def envmap_prepare(image, L=(1.0, 1.0, 1.0)):

@@ -316,3 +316,22 @@ def test_image_mapped_infinite_light_matches_oracle(gpu, oracle, name, size, ext
     # the map matters: the same scene lit by the constant light is a different image
     sd.lights[0].pop("image")
     assert ss.rel_rmse(gpu.PathIntegrator(sd).render(), img) > 10 * TOL
+
+
+@pytest.mark.parametrize("with_instances", [False, True])
+def test_scene_file_renders_like_the_oracle(gpu, oracle, tmp_path, with_instances):
+    """.pbrt + PLY + PFM environment map read by the host loader, rendered through b200pt_scene_create / render and
+    written as PFM: same image as the oracle renders from the same description."""
+    import test_scene_loader_cpu as tl
+    from pbrt_v3_rs_b200 import workloads as wl
+    path, _ = tl._build_pair(tmp_path, gpu, wl, with_instances)
+    ld = gpu.load_pbrt(path)
+    integ = gpu.PathIntegrator(ld)
+    img = integ.render()
+    ref, stats, _ = oracle.OracleScene(ld).render()
+    assert img.shape == ref.shape == (16, 20, 3) and img.any()
+    assert ss.rel_rmse(img, ref) <= TOL
+    assert integ.ray_counts()[0] == stats[0]
+    out = str(tmp_path / ld.output)
+    gpu.write_pfm(out, img)
+    assert np.array_equal(gpu.read_pfm(out), img)

@@ -1,0 +1,206 @@
+"""Host-side scene ingestion (b200pt_load_pbrt, PLY, PFM — SURVEY.md §8f rank 3), no GPU needed.
+
+The same scene is described twice — as a pbrt-v3 scene file (+ binary / ascii PLY meshes + a PFM environment map) read
+by the C++ loader, and through the Python SceneDescription mirror — and the two b200pt_scene_desc must agree: geometry,
+flags, materials, lights, film, sampler and integrator byte for byte, camera matrices to a few ulps (the two paths use
+different tan() implementations), BVH node arrays identical.  The oracle then renders both to the same image."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import scenes_small as ss
+
+
+def _index_mesh(tri, uv=None, nrm=None):
+    """De-indexed (n, 9) triangles -> (P, indices[, uv, N]) with one vertex per corner (keeps corner attributes exact)."""
+    P = tri.reshape(-1, 3)
+    idx = np.arange(P.shape[0], dtype=np.int32)
+    return P, idx, None if uv is None else uv.reshape(-1, 2), None if nrm is None else nrm.reshape(-1, 3)
+
+
+def _write_ply(path, P, idx, N=None, UV=None, binary=True, quads=False):
+    n_face = len(idx) // (4 if quads else 3)
+    props = ["property float x", "property float y", "property float z"]
+    if N is not None:
+        props += ["property float nx", "property float ny", "property float nz"]
+    if UV is not None:
+        props += ["property float u", "property float v"]
+    hdr = ["ply", "format %s 1.0" % ("binary_little_endian" if binary else "ascii"), "comment test mesh", "element vertex %d" % len(P)] + props + \
+          ["element face %d" % n_face, "property list uchar int vertex_indices", "end_header"]
+    cols = [P] + ([N] if N is not None else []) + ([UV] if UV is not None else [])
+    V = np.concatenate(cols, axis=1).astype("<f4")
+    k = 4 if quads else 3
+    with open(path, "wb") as f:
+        f.write(("\n".join(hdr) + "\n").encode())
+        if binary:
+            f.write(V.tobytes())
+            for i in range(n_face):
+                f.write(struct.pack("<B%di" % k, k, *[int(x) for x in idx[k * i:k * i + k]]))
+        else:
+            for row in V:
+                f.write((" ".join(repr(float(x)) for x in row) + "\n").encode())
+            for i in range(n_face):
+                f.write(("%d %s\n" % (k, " ".join(str(int(x)) for x in idx[k * i:k * i + k]))).encode())
+
+
+def _fl(a):
+    return " ".join(repr(float(np.float32(x))) for x in np.asarray(a).reshape(-1))
+
+
+def _build_pair(tmp_path, pkg, wl, with_instances=False):
+    """Returns (path of the .pbrt file, equivalent SceneDescription)."""
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    sd = SceneDescription()
+    img = wl.sky_image(16, 8)
+    pkg.write_pfm(str(tmp_path / "sky.pfm"), img)
+    tv, uv, nrm = wl.displaced_sphere(12, 6, radius=0.8, with_attrs=True)
+    quad = wl.ground_quad()
+    lq = np.array([[-1.5, 3.0, -1.0], [1.5, 3.0, -1.0], [1.5, 3.0, 1.0], [-1.5, 3.0, 1.0]], dtype=np.float32)
+    lt = np.stack([np.concatenate([lq[0], lq[1], lq[2]]), np.concatenate([lq[0], lq[2], lq[3]])])
+    tv2 = wl.displaced_sphere(8, 4, radius=0.3, seed=5)
+
+    P, idx, UV, N = _index_mesh(tv, uv, nrm)
+    _write_ply(str(tmp_path / "sphere.ply"), P, idx, N=N, UV=UV, binary=True)
+    P2, idx2, _, _ = _index_mesh(tv2)
+    _write_ply(str(tmp_path / "small.ply"), P2, idx2, binary=False)
+
+    m_plastic = sd.add_material(type="plastic", Kd=(0.3, 0.2, 0.1), Ks=(0.2, 0.2, 0.2), roughness=0.05)
+    m_matte = sd.add_material(type="matte", Kd=(0.4, 0.4, 0.4))
+    m_glass = sd.add_material(type="glass", eta=1.4)
+    m_black = sd.add_material(type="matte", Kd=(0.0, 0.0, 0.0))
+    m_metal = sd.add_material(type="metal", roughness=0.02)
+    sd.add_mesh(tv, m_plastic, uv=uv, normals=nrm)
+    sd.add_mesh(quad, m_matte)
+    sd.add_mesh(lt, m_black, area_light=dict(L=(15 * 0.5, 15 * 0.5, 15 * 0.5)))
+    lines = ['LookAt 0 1.2 -4  0 -0.1 0  0 1 0', 'Camera "perspective" "float fov" [ 40 ]',
+             'Film "image" "integer xresolution" [20] "integer yresolution" [16] "string filename" "out.pfm"',
+             'Sampler "halton" "integer pixelsamples" 4', 'PixelFilter "box"',
+             'Integrator "path" "integer maxdepth" [4] "string lightsamplestrategy" "power"',
+             'Accelerator "bvh" "integer maxnodeprims" [4]', '# a comment', 'WorldBegin',
+             'MakeNamedMaterial "shiny" "string type" "plastic" "rgb Kd" [0.3 0.2 0.1] "rgb Ks" [0.2 0.2 0.2] "float roughness" 0.05',
+             'AttributeBegin', '  NamedMaterial "shiny"', '  Shape "plymesh" "string filename" "sphere.ply"', 'AttributeEnd',
+             'AttributeBegin', '  Material "matte" "rgb Kd" [0.4 0.4 0.4]',
+             '  Shape "trianglemesh" "integer indices" [%s] "point P" [%s]' % (" ".join(str(i) for i in range(6)), _fl(quad)), 'AttributeEnd',
+             'AttributeBegin', '  Material "glass" "float eta" 1.4', 'AttributeEnd',   # defined but unused: material index 2 stays reserved
+             'AttributeBegin', '  Material "matte" "rgb Kd" [0 0 0]', '  AreaLightSource "diffuse" "rgb L" [15 15 15] "rgb scale" [0.5 0.5 0.5]',
+             '  Shape "trianglemesh" "integer indices" [0 1 2 3 4 5] "point P" [%s]' % _fl(lt), 'AttributeEnd']
+    if with_instances:
+        obj = sd.add_object(tv2, m_metal)
+        lines += ['ObjectBegin "ball"', '  Material "metal" "float roughness" 0.02', '  Shape "plymesh" "string filename" "small.ply"', 'ObjectEnd']
+        for k, (tx, sc) in enumerate([(-1.2, 1.0), (1.3, 0.7)]):
+            lines += ['AttributeBegin', '  Translate %r 0.9 -0.4' % tx, '  Rotate 30 0 1 0', '  Scale %r %r %r' % (sc, sc, sc), '  ObjectInstance "ball"', 'AttributeEnd']
+            T = np.eye(4, dtype=np.float32); T[0, 3], T[1, 3], T[2, 3] = tx, 0.9, -0.4
+            c, s_ = np.float32(np.cos(np.float32(np.deg2rad(np.float32(30))))), np.float32(np.sin(np.float32(np.deg2rad(np.float32(30)))))
+            R = np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0], [0, 0, 0, 1]], dtype=np.float32)
+            S = np.diag([sc, sc, sc, 1]).astype(np.float32)
+            sd.add_instance(obj, (T @ R @ S).astype(np.float32))
+    else:
+        sd.add_material(type="metal", roughness=0.02)  # keep material tables aligned (not needed without instances)
+        sd.materials.pop()
+    lines += ['LightSource "point" "point from" [1.5 3 -3] "rgb I" [30 30 30]',
+              'AttributeBegin', '  Rotate -90 1 0 0', '  LightSource "infinite" "rgb L" [1 0.9 0.8] "string mapname" "sky.pfm"', 'AttributeEnd', 'WorldEnd']
+    # lights in file order: area (2 triangles), point, infinite -> same order in the mirror
+    sd.add_point_light((1.5, 3.0, -3.0), (30, 30, 30))
+    c, s_ = np.float32(np.cos(np.float32(np.deg2rad(np.float32(-90))))), np.float32(np.sin(np.float32(np.deg2rad(np.float32(-90)))))
+    rot = np.array([[1, 0, 0, 0], [0, c, -s_, 0], [0, s_, c, 0], [0, 0, 0, 1]], dtype=np.float32)
+    sd.add_infinite_light((1.0, 0.9, 0.8), image=img, light_to_world=rot)
+    sd.camera.update(eye=(0.0, 1.2, -4.0), look=(0.0, -0.1, 0.0), up=(0, 1, 0), fov=40.0)
+    sd.film.update(xresolution=20, yresolution=16)
+    sd.sampler.update(type="halton", pixelsamples=4)
+    sd.integrator.update(maxdepth=4, lightsamplestrategy="power")
+    path = tmp_path / "scene.pbrt"
+    path.write_text("\n".join(lines) + "\n")
+    return str(path), sd
+
+
+def _arr(ptr, n, dtype):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dtype).itemsize,)).view(dtype).copy()
+
+
+@pytest.mark.parametrize("with_instances", [False, True])
+def test_loader_matches_python_mirror_and_oracle_renders_agree(tmp_path, pkg, oracle, with_instances):
+    from pbrt_v3_rs_b200 import workloads as wl
+    path, sd = _build_pair(tmp_path, pkg, wl, with_instances)
+    ld = pkg.load_pbrt(path)
+    a, b = ld.to_desc(), sd.to_desc()
+    assert ld.output == "out.pfm"
+    assert a.n_prims == b.n_prims and a.n_top_tris == b.n_top_tris and a.n_lights == b.n_lights and a.n_instances == b.n_instances
+    n = a.n_prims
+    assert _arr(a.tri_verts, 9 * n, np.float32).tobytes() == _arr(b.tri_verts, 9 * n, np.float32).tobytes()
+    assert np.array_equal(_arr(a.prim_flags, n, np.uint32), _arr(b.prim_flags, n, np.uint32))
+    assert np.array_equal(_arr(a.prim_light, n, np.int32), _arr(b.prim_light, n, np.int32))
+    fa, fb = _arr(a.prim_flags, n, np.uint32), _arr(b.prim_flags, n, np.uint32)
+    has_uv = (fa & 16) != 0
+    assert has_uv.sum() == 2 * 12 * 6
+    ua, ub = _arr(a.tri_uvs, 6 * n, np.float32).reshape(n, 6), _arr(b.tri_uvs, 6 * n, np.float32).reshape(n, 6)
+    na, nb = _arr(a.tri_normals, 9 * n, np.float32).reshape(n, 9), _arr(b.tri_normals, 9 * n, np.float32).reshape(n, 9)
+    assert ua[has_uv].tobytes() == ub[has_uv].tobytes() and na[has_uv].tobytes() == nb[has_uv].tobytes()
+    # materials referenced by the primitives are the same records (indices may differ: the file defines them in its own order)
+    ma = np.ctypeslib.as_array(C.cast(a.materials, C.POINTER(C.c_uint8)), shape=(a.n_materials * C.sizeof(pkg.Material),)).reshape(a.n_materials, -1)
+    mb = np.ctypeslib.as_array(C.cast(b.materials, C.POINTER(C.c_uint8)), shape=(b.n_materials * C.sizeof(pkg.Material),)).reshape(b.n_materials, -1)
+    pa, pb = _arr(a.prim_material, n, np.int32), _arr(b.prim_material, n, np.int32)
+    assert np.array_equal(ma[pa], mb[pb])
+    # lights: type, position, radiance, primitive; the infinite light's transform and map
+    for i in range(a.n_lights):
+        la, lb = C.cast(a.lights, C.POINTER(pkg.Light))[i], C.cast(b.lights, C.POINTER(pkg.Light))[i]
+        assert la.type == lb.type and list(la.L) == list(lb.L) and la.prim == lb.prim and list(la.pos) == list(lb.pos)
+        if la.type == pkg.LIGHT_INFINITE:
+            assert np.allclose(list(la.light_to_world), list(lb.light_to_world), atol=1e-7) and (la.map_width, la.map_height) == (16, 8)
+            assert np.array_equal(_arr(la.map_rgb, 16 * 8 * 3, np.float32), _arr(lb.map_rgb, 16 * 8 * 3, np.float32))
+    assert bytes(a.film) == bytes(b.film) and bytes(a.sampler) == bytes(b.sampler) and bytes(a.integrator) == bytes(b.integrator)
+    assert np.allclose(list(a.camera.camera_to_world), list(b.camera.camera_to_world), atol=1e-6)
+    assert np.allclose(list(a.camera.raster_to_camera), list(b.camera.raster_to_camera), rtol=1e-5, atol=1e-7)
+    # same BVH (the loader calls the same host builder over the same bounds)
+    assert a.n_nodes == b.n_nodes
+    assert _arr(a.nodes, a.n_nodes, pkg.NODE_DTYPE).tobytes() == _arr(b.nodes, b.n_nodes, pkg.NODE_DTYPE).tobytes()
+    if with_instances:
+        ia, ib = C.cast(a.instances, C.POINTER(pkg.Instance)), C.cast(b.instances, C.POINTER(pkg.Instance))
+        for i in range(a.n_instances):
+            assert ia[i].object == ib[i].object and np.allclose(list(ia[i].instance_to_world), list(ib[i].instance_to_world), atol=1e-6)
+            # the file's inverse is the PRODUCT of the directives' inverses (transform.rs:640-660), the mirror inverts numerically
+            assert np.allclose(list(ia[i].world_to_instance), list(ib[i].world_to_instance), atol=1e-5)
+    # the oracle renders both descriptions to (nearly) the same image
+    ra = oracle.OracleScene(ld).render(nthreads=4)[0]
+    rb = oracle.OracleScene(sd).render(nthreads=4)[0]
+    assert ra.shape == rb.shape == (16, 20, 3) and np.isfinite(ra).all() and ra.any()
+    assert ss.rel_rmse(ra, rb) <= 2e-2
+
+
+def test_ply_variants_pfm_roundtrip_and_transform_stack(tmp_path, pkg):
+    from pbrt_v3_rs_b200 import workloads as wl
+    # PFM round trip (top row first in memory, bottom row first on disk)
+    img = wl.sky_image(8, 4)
+    pkg.write_pfm(str(tmp_path / "a.pfm"), img)
+    assert np.array_equal(pkg.read_pfm(str(tmp_path / "a.pfm")), img)
+    raw = open(tmp_path / "a.pfm", "rb").read()
+    assert raw.startswith(b"PF\n8 4\n-1.0\n") and np.frombuffer(raw[-8 * 4 * 12:], dtype="<f4")[:3].tolist() == img[3, 0].tolist()
+    # quads split as (0 1 2)(3 0 2) (plymesh.rs:211-245); ascii == binary; CTM = Translate * Scale applied to P; ReverseOrientation
+    P = np.float32([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]])
+    for binary in (True, False):
+        _write_ply(str(tmp_path / "q.ply"), P, np.int32([0, 1, 2, 3]), binary=binary, quads=True)
+        (tmp_path / "s.pbrt").write_text('Camera "perspective"\nIntegrator "path" "string lightsamplestrategy" "uniform"\nWorldBegin\nTranslate 1 2 3\nScale 2 2 -2\n'
+                                         'ReverseOrientation\nShape "plymesh" "string filename" "q.ply"\nWorldEnd\n')
+        ld = pkg.load_pbrt(str(tmp_path / "s.pbrt"))  # owns the arrays the desc points into
+        d = ld.to_desc()
+        v = _arr(d.tri_verts, 18, np.float32).reshape(2, 3, 3)
+        assert np.array_equal(v[0], [[1, 2, 3], [3, 2, 3], [3, 4, 3]]) and np.array_equal(v[1], [[1, 4, 3], [1, 2, 3], [3, 4, 3]])
+        # Scale(2,2,-2) swaps handedness, ReverseOrientation is on: flip = reverse ^ swaps = false, bit 8 (reverse) set
+        assert _arr(d.prim_flags, 2, np.uint32).tolist() == [8, 8]
+        assert d.n_materials == 1 and d.film.xres == 1280 and d.sampler.spp == 16 and d.integrator.max_depth == 5
+    # unsupported input fails loudly, with the directive named
+    (tmp_path / "u.pbrt").write_text('Integrator "whitted"\nWorldBegin\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n')
+    with pytest.raises(pkg.B200PTError, match="whitted"):
+        pkg.load_pbrt(str(tmp_path / "u.pbrt"))
+    (tmp_path / "t.pbrt").write_text('WorldBegin\nTexture "x" "float" "constant"\nWorldEnd\n')
+    with pytest.raises(pkg.B200PTError, match="Texture"):
+        pkg.load_pbrt(str(tmp_path / "t.pbrt"))
+    (tmp_path / "sph.pbrt").write_text('WorldBegin\nShape "sphere"\nWorldEnd\n')
+    with pytest.raises(pkg.B200PTError, match="sphere"):
+        pkg.load_pbrt(str(tmp_path / "sph.pbrt"))
+    with pytest.raises(pkg.B200PTError):
+        pkg.load_pbrt(str(tmp_path / "missing.pbrt"))

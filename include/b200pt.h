@@ -214,6 +214,21 @@ int b200pt_bvh_build_sah(const float* prim_bounds, int64_t n, int max_prims_in_n
 /* Triangle::world_bound (shapes/src/triangle.rs:427-431) for n triangles. */
 int b200pt_triangle_bounds(const float* tri_verts, int64_t n, float* bounds_out);
 
+/* ---- the same build on the GPU (csrc/bvh_build.cu) ----------------------
+ * Results (node bytes, ordered_prims) are identical to b200pt_bvh_build_sah and therefore to the reference's
+ * BVHAccel::new(.., SplitMethod::SAH) (mod.rs:43-153, sah.rs:26-367): the level-parallel schedule only reorders
+ * min/max reductions and restates itertools::partition (sah.rs:354) through a prefix sum.  n < 2^31.
+ * _gpu: host buffers in / out (drop-in for b200pt_bvh_build_sah).  _device: device pointers, `stream` is a
+ * cudaStream_t (NULL = default stream); returns after the build has completed on that stream. */
+int b200pt_bvh_build_sah_gpu(const float* prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* nodes_out,
+                             int64_t* n_nodes_out, uint32_t* ordered_out);
+int b200pt_bvh_build_sah_device(const float* d_prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* d_nodes_out,
+                                int64_t* n_nodes_out, uint32_t* d_ordered_out, void* stream);
+int b200pt_triangle_bounds_device(const float* d_tri_verts, int64_t n, float* d_bounds_out, void* stream);
+/* The builder keeps its device scratch (about 160 bytes per primitive of the largest build so far) between calls;
+ * this frees it. */
+int b200pt_bvh_build_release(void);
+
 /* Host-only: what InfiniteAreaLight::new prepares for an environment image (lights/src/infinite.rs:61-92, 326-369;
  * core/src/mipmap/mod.rs): level 0 of the MIPMap (sides rounded up to powers of two by the Lanczos resampler) and the
  * (2w x 2h) importance image y * sin(theta) the light's Distribution2D is built over.  Call with the out pointers

@@ -118,6 +118,9 @@ def lib():
     L.b200pt_init.argtypes = [C.c_int]
     L.b200pt_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_triangle_bounds.argtypes = [vp, i64, vp]
+    L.b200pt_bvh_build_sah_gpu.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
+    L.b200pt_bvh_build_sah_device.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp, vp]
+    L.b200pt_triangle_bounds_device.argtypes = [vp, i64, vp, vp]
     L.b200pt_accel_create.argtypes = [vp, i64, vp, vp, vp, i64, C.POINTER(vp)]
     L.b200pt_accel_create_uv.argtypes = [vp, i64, vp, vp, vp, vp, i64, C.POINTER(vp)]
     L.b200pt_accel_destroy.argtypes = [vp]
@@ -172,15 +175,30 @@ def triangle_bounds(tri_verts):
     return out
 
 
-def build_bvh_sah(prim_bounds, max_prims_in_node=4):
-    """BVHAccel::new(.., SplitMethod::SAH) on the host (mod.rs:43-153): returns (nodes, ordered_prims)."""
+GPU_BUILD_MIN_PRIMS = 4096  # below this the sequential host build is faster than ~200 kernel launches
+
+
+def build_bvh_sah(prim_bounds, max_prims_in_node=4, where="auto"):
+    """BVHAccel::new(.., SplitMethod::SAH) (mod.rs:43-153): returns (nodes, ordered_prims).
+
+    where="host": the sequential C++ builder; where="gpu": the level-parallel CUDA builder (csrc/bvh_build.cu).
+    Both return the same bytes, so "auto" only picks the faster one: the GPU once a device is bound (init()) and
+    the input has at least GPU_BUILD_MIN_PRIMS primitives."""
     pb = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
     n = pb.shape[0]
+    if where == "auto":
+        where = "gpu" if (_inited is not None and n >= GPU_BUILD_MIN_PRIMS) else "host"
     nodes = np.zeros(max(2 * n - 1, 1), dtype=NODE_DTYPE)
     ordered = np.zeros(max(n, 1), dtype=np.uint32)
     nn = C.c_int64(0)
-    _check(lib().b200pt_bvh_build_sah(_ptr(pb), n, int(max_prims_in_node), _ptr(nodes), C.byref(nn), _ptr(ordered)),
-           "b200pt_bvh_build_sah")
+    if where == "gpu":
+        init(_inited if _inited is not None else 0)
+        fn, name = lib().b200pt_bvh_build_sah_gpu, "b200pt_bvh_build_sah_gpu"
+    elif where == "host":
+        fn, name = lib().b200pt_bvh_build_sah, "b200pt_bvh_build_sah"
+    else:
+        raise ValueError("where must be 'host' or 'gpu'")
+    _check(fn(_ptr(pb), n, int(max_prims_in_node), _ptr(nodes), C.byref(nn), _ptr(ordered)), name)
     return nodes[:nn.value].copy(), ordered[:n].copy()
 
 
@@ -271,6 +289,7 @@ class BVHAccel:
             raise B200PTError("BVHAccel: only splitmethod 'sah' is built on this path, got %r" % split)
         max_prims = int(params.get("maxnodeprims", 4)) & 0xFF
         tv = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
+        init(_inited if _inited is not None else 0)
         nodes, ordered = build_bvh_sah(triangle_bounds(tv), max_prims)
         return cls(tv, nodes, ordered, prim_flags, tri_uvs)
 

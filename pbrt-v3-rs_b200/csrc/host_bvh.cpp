@@ -211,6 +211,18 @@ extern "C" int b200pt_bvh_build_sah(const float* prim_bounds, int64_t n, int max
         work.push_back(Job{mid, job.end, me});       // second child: popped after the whole first subtree
         work.push_back(Job{job.begin, mid, -1});     // first child: next node, index me + 1
     }
+    // An interior node's bounds are union(child0, child1) in the reference (common.rs:150-159), not the fold over
+    // its range: same box, but min(a, b) = a < b ? a : b makes the sign of a zero order-dependent.  Children follow
+    // their parent in pre-order, so one reverse sweep reproduces the bottom-up construction.
+    for (int64_t i = n_nodes - 1; i >= 0; --i) {
+        b200pt_bvh_node& nd = nodes_out[i];
+        if (nd.n_primitives != 0) continue;
+        const b200pt_bvh_node &c0 = nodes_out[i + 1], &c1 = nodes_out[nd.offset];
+        for (int k = 0; k < 3; ++k) {
+            nd.bounds[k] = fmin_ref(c0.bounds[k], c1.bounds[k]);
+            nd.bounds[3 + k] = fmax_ref(c0.bounds[3 + k], c1.bounds[3 + k]);
+        }
+    }
     *n_nodes_out = n_nodes;
     return B200PT_OK;
 }

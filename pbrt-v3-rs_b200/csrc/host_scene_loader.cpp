@@ -708,7 +708,9 @@ void Builder::finish() {
         nodes->resize((size_t)(n > 0 ? 2 * n : 1));
         ordered->resize((size_t)n);
         int64_t n_nodes = 0;
-        if (n > 0 && b200pt_bvh_build_sah(bounds.data(), n, L->max_node_prims, nodes->data(), &n_nodes, ordered->data()) != B200PT_OK)
+        // same bytes either way; the GPU builder (csrc/bvh_build.cu) is used once a device is bound and the input is large enough to pay for its launches
+        auto fn = (b200pt_device_sm_count() > 0 && n >= 4096) ? b200pt_bvh_build_sah_gpu : b200pt_bvh_build_sah;
+        if (n > 0 && fn(bounds.data(), n, L->max_node_prims, nodes->data(), &n_nodes, ordered->data()) != B200PT_OK)
             throw Invalid(std::string("BVH build failed: ") + b200pt_last_error());
         nodes->resize((size_t)n_nodes);
     };

@@ -47,6 +47,29 @@ def test_host_sah_builder_matches_oracle(pkg, oracle, mesh, max_prims):
     assert np.array_equal(o1, o2), "ordered_prims differ"
 
 
+def test_host_sah_builder_keeps_the_reference_sign_of_zero(pkg, oracle):
+    """min(a, b) = a < b ? a : b (core/src/pbrt/common.rs:83-108) keeps the LAST of two equal operands, so whether a
+    box coordinate is +0 or -0 depends on the order the reference unites in: leaves fold their primitives, interior
+    nodes unite child0 with child1 (accelerators/src/bvh/common.rs:150-159)."""
+    rng = np.random.default_rng(11)
+    n = 400
+    lo = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    hi = lo + rng.uniform(0.01, 0.2, (n, 3)).astype(np.float32)
+    zero = rng.integers(0, 2, (n, 3)).astype(bool)
+    lo[zero] = np.where(rng.integers(0, 2, zero.sum()) == 1, np.float32(0.0), np.float32(-0.0))
+    hi = np.maximum(hi, lo + np.float32(0.01))
+    neg = rng.integers(0, 4, (n, 3)) == 0
+    hi[neg & zero] = np.where(rng.integers(0, 2, (neg & zero).sum()) == 1, np.float32(0.0), np.float32(-0.0))
+    lo[neg & zero] = hi[neg & zero] - np.float32(0.05)
+    pb = np.concatenate([lo, hi], axis=1).astype(np.float32)
+    for max_prims in (1, 4):
+        n1, o1 = pkg.build_bvh_sah(pb, max_prims)
+        n2, o2 = oracle.build_bvh_sah(pb, max_prims)
+        assert n1.tobytes() == n2.tobytes() and np.array_equal(o1, o2)
+    z = n1["bounds"][n1["bounds"] == 0]
+    assert np.signbit(z).any() and (~np.signbit(z)).any()  # the case is exercised
+
+
 def test_empty_and_single_primitive(pkg, oracle):
     n, o = pkg.build_bvh_sah(np.zeros((0, 6), np.float32))
     assert len(n) == 0  # BVHAccel::new with no primitives has no nodes (mod.rs:47-53)

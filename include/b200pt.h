@@ -214,6 +214,16 @@ int b200pt_bvh_build_sah(const float* prim_bounds, int64_t n, int max_prims_in_n
 /* Triangle::world_bound (shapes/src/triangle.rs:427-431) for n triangles. */
 int b200pt_triangle_bounds(const float* tri_verts, int64_t n, float* bounds_out);
 
+/* BVHAccel::new with SplitMethod::HLBVH (accelerators/src/bvh/hlbvh.rs:33-449, morton.rs:37-120): same argument
+ * meaning as b200pt_bvh_build_sah.  Keeps two reference behaviours that show in the result: encode_morton_3
+ * interleaves bits of the float BIT PATTERN of the scaled centroid offset (morton.rs:43-49, float_to_bits is a
+ * transmute; release-build semantics), and treelets are emitted in order (the reference's --nthreads 1 primitive order).
+ * Returns B200PT_ERR_INVALID where the reference asserts. */
+int b200pt_bvh_build_hlbvh(const float* prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* nodes_out,
+                           int64_t* n_nodes_out, uint32_t* ordered_out);
+/* the reference's Morton code of every primitive (before sorting) */
+int b200pt_hlbvh_morton_codes(const float* prim_bounds, int64_t n, uint32_t* codes_out);
+
 /* ---- the same build on the GPU (csrc/bvh_build.cu) ----------------------
  * Results (node bytes, ordered_prims) are identical to b200pt_bvh_build_sah and therefore to the reference's
  * BVHAccel::new(.., SplitMethod::SAH) (mod.rs:43-153, sah.rs:26-367): the level-parallel schedule only reorders

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "oracle_bvh.h"
+#include "oracle_hlbvh.h"
 #include "oracle_math.h"
 #include "oracle_rng.h"
 #include "oracle_render.h"
@@ -135,6 +136,18 @@ int64_t orc_bvh_build_sah(const float* prim_bounds, int64_t n, int max_prims_in_
     bvh_build_sah(prim_bounds, (size_t)n, max_prims_in_node, nodes, ordered);
     std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(LinearBVHNode));
     std::copy(ordered.begin(), ordered.end(), ordered_out);
+    return (int64_t)nodes.size();
+}
+// BVHAccel::new(.., SplitMethod::HLBVH).  Returns the node count, or -1 where the reference panics.
+// morton_sorted_out (optional): the n Morton codes after the radix sort.
+int64_t orc_bvh_build_hlbvh(const float* prim_bounds, int64_t n, int max_prims_in_node, void* nodes_out, uint32_t* ordered_out,
+                            uint32_t* morton_sorted_out) {
+    std::vector<LinearBVHNode> nodes;
+    std::vector<uint32_t> ordered, codes;
+    if (!bvh_build_hlbvh(prim_bounds, (size_t)n, max_prims_in_node, nodes, ordered, morton_sorted_out ? &codes : nullptr)) return -1;
+    std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(LinearBVHNode));
+    std::copy(ordered.begin(), ordered.end(), ordered_out);
+    if (morton_sorted_out) std::copy(codes.begin(), codes.end(), morton_sorted_out);
     return (int64_t)nodes.size();
 }
 void orc_triangle_bounds(const float* verts, int64_t n, float* out) {

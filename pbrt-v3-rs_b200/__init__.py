@@ -118,6 +118,8 @@ def lib():
     L.b200pt_init.argtypes = [C.c_int]
     L.b200pt_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_triangle_bounds.argtypes = [vp, i64, vp]
+    L.b200pt_bvh_build_hlbvh.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
+    L.b200pt_hlbvh_morton_codes.argtypes = [vp, i64, vp]
     L.b200pt_bvh_build_sah_gpu.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_bvh_build_sah_device.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp, vp]
     L.b200pt_triangle_bounds_device.argtypes = [vp, i64, vp, vp]
@@ -202,6 +204,24 @@ def build_bvh_sah(prim_bounds, max_prims_in_node=4, where="auto"):
     return nodes[:nn.value].copy(), ordered[:n].copy()
 
 
+def build_bvh_hlbvh(prim_bounds, max_prims_in_node=4):
+    """BVHAccel::new(.., SplitMethod::HLBVH) on the host (hlbvh.rs:33-449): returns (nodes, ordered_prims)."""
+    pb = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
+    n = pb.shape[0]
+    nodes = np.zeros(max(2 * n - 1, 1), dtype=NODE_DTYPE)
+    ordered = np.zeros(max(n, 1), dtype=np.uint32)
+    nn = C.c_int64(0)
+    _check(lib().b200pt_bvh_build_hlbvh(_ptr(pb), n, int(max_prims_in_node), _ptr(nodes), C.byref(nn), _ptr(ordered)), "b200pt_bvh_build_hlbvh")
+    return nodes[:nn.value].copy(), ordered[:n].copy()
+
+
+def hlbvh_morton_codes(prim_bounds):
+    pb = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
+    codes = np.zeros(max(pb.shape[0], 1), dtype=np.uint32)
+    _check(lib().b200pt_hlbvh_morton_codes(_ptr(pb), pb.shape[0], _ptr(codes)), "b200pt_hlbvh_morton_codes")
+    return codes[:pb.shape[0]]
+
+
 class LoadedScene:
     """A scene file read by the host-side loader (b200pt_load_pbrt): duck-types SceneDescription.to_desc() for
     PathIntegrator, so ``PathIntegrator(load_pbrt("scene.pbrt")).render()`` is the reference's `pbrt scene.pbrt`."""
@@ -284,13 +304,13 @@ class BVHAccel:
     @classmethod
     def from_params(cls, params, tri_verts, prim_flags=None, tri_uvs=None):
         split = params.get("splitmethod", "sah")
-        if split != "sah":
-            # hlbvh / middle / equal are outside this path
-            raise B200PTError("BVHAccel: only splitmethod 'sah' is built on this path, got %r" % split)
+        if split not in ("sah", "hlbvh"):
+            # middle / equal are outside this path
+            raise B200PTError("BVHAccel: splitmethod 'sah' and 'hlbvh' are built on this path, got %r" % split)
         max_prims = int(params.get("maxnodeprims", 4)) & 0xFF
         tv = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
         init(_inited if _inited is not None else 0)
-        nodes, ordered = build_bvh_sah(triangle_bounds(tv), max_prims)
+        nodes, ordered = (build_bvh_sah if split == "sah" else build_bvh_hlbvh)(triangle_bounds(tv), max_prims)
         return cls(tv, nodes, ordered, prim_flags, tri_uvs)
 
     def close(self):

@@ -698,7 +698,8 @@ void Builder::finish() {
 
     // --- Accelerator (accelerators/src/bvh/mod.rs:339-360) ---
     if (accel_name != "bvh") throw Unsupported("Accelerator \"" + accel_name + "\" is outside this path (bvh)");
-    if (accel_p.one_string("splitmethod", "sah") != "sah") throw Unsupported("Accelerator \"bvh\": only splitmethod \"sah\" is on this path");
+    const std::string split_method = accel_p.one_string("splitmethod", "sah");
+    if (split_method != "sah" && split_method != "hlbvh") throw Unsupported("Accelerator \"bvh\": splitmethod \"sah\" and \"hlbvh\" are on this path, got \"" + split_method + "\"");
     L->max_node_prims = accel_p.one_int("maxnodeprims", 4) & 0xff;
 
     // --- geometry: top-level triangles, then each object's block; BVHs with the product's host SAH builder ---
@@ -709,7 +710,7 @@ void Builder::finish() {
         ordered->resize((size_t)n);
         int64_t n_nodes = 0;
         // same bytes either way; the GPU builder (csrc/bvh_build.cu) is used once a device is bound and the input is large enough to pay for its launches
-        auto fn = (b200pt_device_sm_count() > 0 && n >= 4096) ? b200pt_bvh_build_sah_gpu : b200pt_bvh_build_sah;
+        auto fn = split_method == "hlbvh" ? b200pt_bvh_build_hlbvh : (b200pt_device_sm_count() > 0 && n >= 4096) ? b200pt_bvh_build_sah_gpu : b200pt_bvh_build_sah;
         if (n > 0 && fn(bounds.data(), n, L->max_node_prims, nodes->data(), &n_nodes, ordered->data()) != B200PT_OK)
             throw Invalid(std::string("BVH build failed: ") + b200pt_last_error());
         nodes->resize((size_t)n_nodes);

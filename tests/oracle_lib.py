@@ -42,6 +42,8 @@ def lib():
         L.orc_halton_pixel.argtypes = [C.c_int] * 6 + [vp]
         L.orc_bvh_build_sah.restype = i64
         L.orc_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, vp]
+        L.orc_bvh_build_hlbvh.restype = i64
+        L.orc_bvh_build_hlbvh.argtypes = [vp, i64, C.c_int, vp, vp, vp]
         L.orc_triangle_bounds.argtypes = [vp, i64, vp]
         L.orc_accel_create.restype = vp
         L.orc_accel_create.argtypes = [vp, i64, vp, vp, vp, i64]
@@ -94,6 +96,19 @@ def build_bvh_sah(prim_bounds, max_prims_in_node=4):
     ordered = np.zeros(max(n, 1), dtype=np.uint32)
     nn = lib().orc_bvh_build_sah(_p(pb), n, max_prims_in_node, _p(nodes), _p(ordered))
     return nodes[:nn].copy(), ordered[:n].copy()
+
+
+def build_bvh_hlbvh(prim_bounds, max_prims_in_node=4, with_codes=False):
+    """oracle restatement of BVHAccel::new(.., SplitMethod::HLBVH); raises where the reference panics."""
+    pb = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
+    n = pb.shape[0]
+    nodes = np.zeros(max(2 * n - 1, 1), dtype=NODE_DTYPE)
+    ordered = np.zeros(max(n, 1), dtype=np.uint32)
+    codes = np.zeros(max(n, 1), dtype=np.uint32)
+    nn = lib().orc_bvh_build_hlbvh(_p(pb), n, max_prims_in_node, _p(nodes), _p(ordered), _p(codes))
+    if nn < 0:
+        raise RuntimeError("the reference asserts on this input")
+    return (nodes[:nn].copy(), ordered[:n].copy()) + ((codes[:n].copy(),) if with_codes else ())
 
 
 class OracleAccel:

@@ -108,3 +108,89 @@ def test_workload_generators_are_deterministic(pkg):
     assert a.tobytes() == b.tobytes() and a.shape == (10000, 9)
     r = wl.primary_rays(64, 32)
     assert r.shape == (2048,) and np.allclose(np.linalg.norm(r["d"], axis=1), 1, atol=1e-6)
+
+
+# ---- SplitMethod::HLBVH (accelerators/src/bvh/hlbvh.rs, morton.rs) --------------------------------------------
+
+def _ref_morton_py(pb):
+    """Independent numpy restatement of compute_morton_primitives + encode_morton_3 (hlbvh.rs:104-141, morton.rs:43-49,
+    102-120): note float_to_bits -> the code interleaves bits of the float's bit pattern."""
+    lo, hi = pb[:, :3].min(0), pb[:, 3:].max(0)
+    cen = np.float32(0.5) * (pb[:, :3] + pb[:, 3:])
+    off = cen - lo
+    ext = hi - lo
+    off = np.where(hi > lo, off / np.where(hi > lo, ext, 1).astype(np.float32), off).astype(np.float32)
+    bits = (off * np.float32(1024.0)).astype(np.float32).view(np.uint32)
+
+    def spread(x):
+        x = np.where(x == 1024, x - 1, x).astype(np.uint64)
+        x = (x | (x << 16)) & 0x030000FF
+        x = (x | (x << 8)) & 0x0300F00F
+        x = (x | (x << 4)) & 0x030C30C3
+        x = (x | (x << 2)) & 0x09249249
+        return x
+    return ((spread(bits[:, 2]) << 2) | (spread(bits[:, 1]) << 1) | spread(bits[:, 0])).astype(np.uint32)
+
+
+def test_hlbvh_morton_codes_and_sort(pkg, oracle):
+    from pbrt_v3_rs_b200 import workloads as wl
+    pb = pkg.triangle_bounds(wl.triangle_soup(3000))
+    codes = pkg.hlbvh_morton_codes(pb)
+    assert np.array_equal(codes, _ref_morton_py(pb))
+    assert codes.max() < (1 << 30)
+    _, ordered, sorted_codes = oracle.build_bvh_hlbvh(pb, 4, with_codes=True)
+    order = np.argsort(codes, kind="stable")  # the reference's LSD radix sort is a stable sort of the 30-bit code
+    assert np.array_equal(sorted_codes, codes[order])
+    assert np.array_equal(ordered, order.astype(np.uint32))  # leaves take their primitives in sorted order
+
+
+@pytest.mark.parametrize("max_prims", [1, 4, 8, 255])
+@pytest.mark.parametrize("mesh", ["sphere", "soup", "tiny", "coincident+soup"])
+def test_host_hlbvh_builder_matches_oracle(pkg, oracle, mesh, max_prims):
+    from pbrt_v3_rs_b200 import workloads as wl
+    if mesh == "sphere":
+        tv = wl.displaced_sphere(60, 30)
+    elif mesh == "soup":
+        tv = wl.triangle_soup(5000)
+    elif mesh == "tiny":
+        tv = wl.ground_quad()
+    else:
+        tv = np.concatenate([np.tile(wl.ground_quad()[:1], (37, 1)), wl.triangle_soup(200)])
+    pb = pkg.triangle_bounds(tv)
+    n1, o1 = pkg.build_bvh_hlbvh(pb, max_prims)
+    n2, o2 = oracle.build_bvh_hlbvh(pb, max_prims)
+    assert len(n1) == len(n2)
+    assert np.array_equal(o1, o2), "ordered_prims differ"
+    assert n1.tobytes() == n2.tobytes(), "LinearBVHNode arrays differ"
+    # structural invariants: every primitive in exactly one leaf, children inside parents
+    leaves = n1[n1["n_primitives"] > 0]
+    assert leaves["n_primitives"].sum() == len(tv) and sorted(o1.tolist()) == list(range(len(tv)))
+    for i in np.flatnonzero(n1["n_primitives"] == 0)[:200]:
+        for c in (i + 1, n1["offset"][i]):
+            assert np.all(n1["bounds"][c][:3] >= n1["bounds"][i][:3]) and np.all(n1["bounds"][c][3:] <= n1["bounds"][i][3:])
+
+
+def test_hlbvh_tree_traces_like_brute_force(pkg, oracle):
+    """The HLBVH tree (whatever its quality) must return the same closest hits as the SAH tree: same primitive ids and t."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    tv = wl.displaced_sphere(40, 20)
+    pb = pkg.triangle_bounds(tv)
+    rays = wl.primary_rays(48, 24)
+    n1, o1 = pkg.build_bvh_hlbvh(pb, 4)
+    n2, o2 = pkg.build_bvh_sah(pb, 4, where="host")
+    h1 = oracle.OracleAccel(n1, o1, tv).intersect(rays, counters=False, diag=False)[0]
+    h2 = oracle.OracleAccel(n2, o2, tv).intersect(rays, counters=False, diag=False)[0]
+    assert (h1["prim"] != pkg.MISS).sum() > 100
+    assert np.array_equal(h1["t"].view(np.uint32), h2["t"].view(np.uint32))
+    same = h1["prim"] == h2["prim"]
+    assert same.mean() > 0.995  # equal-t ties on shared edges may go to the other triangle (different visiting order)
+
+
+def test_hlbvh_single_and_empty(pkg, oracle):
+    from pbrt_v3_rs_b200 import workloads as wl
+    n, o = pkg.build_bvh_hlbvh(np.zeros((0, 6), np.float32))
+    assert len(n) == 0
+    pb = pkg.triangle_bounds(wl.ground_quad()[:1])
+    n1, o1 = pkg.build_bvh_hlbvh(pb, 4)
+    n2, o2 = oracle.build_bvh_hlbvh(pb, 4)
+    assert len(n1) == 1 and n1.tobytes() == n2.tobytes() and list(o1) == [0]

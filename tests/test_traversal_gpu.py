@@ -245,3 +245,30 @@ def test_uvs_reach_the_degenerate_hit_rejection(gpu, oracle):
     assert np.array_equal(g["prim"], plain.intersect_batch(rays)["prim"])
     sr = wl.shadow_rays(wl.bounce_rays(tv, rays, g, rays.shape[0]))
     assert np.array_equal(accel.occluded_batch(sr), oacc.occluded(sr)[0])
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_hlbvh_accelerator_bit_exact(gpu, oracle, variant):
+    """splitmethod "hlbvh" (accelerators/src/bvh/hlbvh.rs): the device walk over the reference's HLBVH tree returns the
+    oracle's hits over the same tree bit for bit (the tree is poor — see oracle/oracle_hlbvh.h — but it is the reference's)."""
+    import torch
+    from pbrt_v3_rs_b200 import workloads as wl
+    tv = wl.displaced_sphere(120, 60)
+    accel = gpu.BVHAccel.from_params({"splitmethod": "hlbvh", "maxnodeprims": 4}, tv)
+    n2, o2 = oracle.build_bvh_hlbvh(gpu.triangle_bounds(tv), 4)
+    assert accel.nodes.tobytes() == n2.tobytes() and np.array_equal(accel.ordered_prims, o2)
+    oacc = oracle.OracleAccel(accel.nodes, accel.ordered_prims, tv)
+    rays = wl.primary_rays(256, 128)
+    hits = accel.intersect_batch(rays)
+    br = wl.bounce_rays(tv, rays, hits, rays.shape[0])
+    for rs in (rays, br):
+        d_r = torch.from_numpy(rs.view(np.float32).reshape(-1, 8)).cuda()
+        d_h = torch.empty((rs.shape[0], 4), dtype=torch.float32, device="cuda")
+        accel.intersect_batch_device(d_r.data_ptr(), rs.shape[0], d_h.data_ptr(), torch.cuda.current_stream().cuda_stream, variant)
+        torch.cuda.synchronize()
+        g = d_h.cpu().numpy().view(gpu.HIT_DTYPE).reshape(-1)
+        o, diag, _ = oacc.intersect(rs)
+        _check_closest(g, o, diag, oracle)
+    sr = wl.shadow_rays(br)
+    oo, _ = oacc.occluded(sr)
+    assert np.array_equal(accel.occluded_batch(sr), oo)

@@ -133,12 +133,17 @@ typedef struct b200pt_sampler {
 } b200pt_sampler;
 
 enum { B200PT_LIGHTS_UNIFORM = 0, B200PT_LIGHTS_POWER = 1 };
-/* integrators/src/path.rs:287-326 */
+/* B200PT_INTEGRATOR_PATH: PathIntegrator (integrators/src/path.rs:103-326).
+ * B200PT_INTEGRATOR_WHITTED: WhittedIntegrator (integrators/src/whitted.rs:60-158 with specular_reflect /
+ * specular_transmit of core/src/integrator/sampler_integrator.rs:79-238); reads max_depth and pixel_bounds only and
+ * needs the halton sampler (the number of sampler dimensions a camera sample consumes is not bounded in advance). */
+enum { B200PT_INTEGRATOR_PATH = 0, B200PT_INTEGRATOR_WHITTED = 1 };
 typedef struct b200pt_integrator {
     int32_t max_depth;         /* "maxdepth" (5) */
     float rr_threshold;        /* "rrthreshold" (1.0) */
     int32_t pixel_bounds[4];   /* x0,y0,x1,y1 (sample bounds ∩ "pixelbounds") */
     int32_t light_strategy;    /* "lightsamplestrategy": uniform | power */
+    int32_t type;              /* B200PT_INTEGRATOR_* */
 } b200pt_integrator;
 
 /* ObjectBegin/ObjectEnd: the triangles [first_prim, first_prim + n_prims) of the scene's per-primitive arrays with their

@@ -248,7 +248,7 @@ struct TRDist {
 // core/src/reflection/bsdf.rs:10-20
 enum : uint8_t { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
 
-enum BxDFKind { BX_LAMBERT, BX_OREN_NAYAR, BX_MF_REFL, BX_MF_TRANS, BX_FRESNEL_SPECULAR };
+enum BxDFKind { BX_LAMBERT, BX_OREN_NAYAR, BX_MF_REFL, BX_MF_TRANS, BX_FRESNEL_SPECULAR, BX_SPEC_REFL, BX_SPEC_TRANS };
 enum FresnelKind { FR_DIELECTRIC, FR_CONDUCTOR };
 
 struct BxDFSample {
@@ -315,6 +315,8 @@ struct BxDF {
                             (cos_i * cos_o * sqrt_denom * sqrt_denom));
             }
             case BX_FRESNEL_SPECULAR: return RGB();  // fresnel_specular.rs:63-66
+            case BX_SPEC_REFL: return RGB();         // specular_reflection.rs:40-43
+            case BX_SPEC_TRANS: return RGB();        // specular_transmission.rs:55-58
         }
         return RGB();
     }
@@ -339,6 +341,8 @@ struct BxDF {
                 return dist.pdf(wo, wh) * dwh_dwi;
             }
             case BX_FRESNEL_SPECULAR: return 0.0f;
+            case BX_SPEC_REFL: return 0.0f;   // specular_reflection.rs:53-55
+            case BX_SPEC_TRANS: return 0.0f;  // specular_transmission.rs:83-85
         }
         return 0.0f;
     }
@@ -376,6 +380,25 @@ struct BxDF {
                 if (!refract(wo, wh, eta, &wi)) return s;
                 s.pdf = pdf(wo, wi);
                 s.f = f(wo, wi);
+                s.wi = wi;
+                return s;
+            }
+            case BX_SPEC_REFL: {  // specular_reflection.rs:45-51 (fresnel = FresnelDielectric(fr_eta_i, fr_eta_t))
+                V3 wi(-wo.x, -wo.y, wo.z);
+                s.pdf = 1.0f;
+                s.f = fresnel(cos_theta(wi)) * r / abs_cos_theta(wi);
+                s.wi = wi;
+                return s;
+            }
+            case BX_SPEC_TRANS: {  // specular_transmission.rs:60-81 (fresnel = FresnelDielectric(eta_a, eta_b), Radiance mode)
+                bool entering = cos_theta(wo) > 0.0f;
+                Float eta_i = entering ? eta_a : eta_b, eta_t = entering ? eta_b : eta_a;
+                V3 wi;
+                if (!refract(wo, face_forward(V3(0.0f, 0.0f, 1.0f), wo), eta_i / eta_t, &wi)) return s;
+                s.pdf = 1.0f;
+                RGB ft = t * (RGB(1.0f) - RGB(fr_dielectric(cos_theta(wi), eta_a, eta_b)));
+                ft = ft * ((eta_i * eta_i) / (eta_t * eta_t));
+                s.f = ft / abs_cos_theta(wi);
                 s.wi = wi;
                 return s;
             }
@@ -711,7 +734,7 @@ inline bool scene_intersect_p(RenderScene& sc, const Ray& ray) {
 // materials/src/{matte,plastic,glass,metal}.rs compute_scattering_functions
 // with constant textures, no bump map, allow_multiple_lobes = true (path.rs:145).
 // BSDF::new is called with eta = None in all four, so bsdf.eta = 1.0.
-inline BSDF make_bsdf(const RenderScene& sc, const SurfHit& sh) {
+inline BSDF make_bsdf(const RenderScene& sc, const SurfHit& sh, bool allow_multiple_lobes = true) {
     BSDF b;
     b.ns = sh.shading_n; b.ng = sh.n;
     b.ss = normalize(sh.dpdu);
@@ -755,7 +778,17 @@ inline BSDF make_bsdf(const RenderScene& sc, const SurfHit& sh) {
             RGB r = rgb_clamp0(rgb(m.ks)), t = rgb_clamp0(rgb(m.kt));
             if (!(is_black(r) && is_black(t))) {
                 bool is_spec = ur == 0.0f && vr == 0.0f;
-                if (is_spec) {
+                if (is_spec && !allow_multiple_lobes) {  // glass.rs:112-120
+                    if (!is_black(r)) {
+                        BxDF x; x.kind = BX_SPEC_REFL; x.type = BSDF_REFLECTION | BSDF_SPECULAR; x.r = r;
+                        x.fr = FR_DIELECTRIC; x.fr_eta_i = 1.0f; x.fr_eta_t = eta;
+                        b.add(x);
+                    }
+                    if (!is_black(t)) {
+                        BxDF x; x.kind = BX_SPEC_TRANS; x.type = BSDF_TRANSMISSION | BSDF_SPECULAR; x.t = t; x.eta_a = 1.0f; x.eta_b = eta;
+                        b.add(x);
+                    }
+                } else if (is_spec) {
                     BxDF x; x.kind = BX_FRESNEL_SPECULAR; x.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
                     x.r = r; x.t = t; x.eta_a = 1.0f; x.eta_b = eta;
                     b.add(x);
@@ -997,6 +1030,54 @@ inline RGB path_li(RenderScene& sc, Ray ray, Sampler& sampler) {
     return L;
 }
 
+// integrators/src/whitted.rs:60-126 with specular_reflect / specular_transmit of
+// core/src/integrator/sampler_integrator.rs:79-238 (ray differentials only feed texture filtering: dropped).
+inline RGB whitted_li(RenderScene& sc, Ray ray, Sampler& sampler, int depth) {
+    RGB l;
+    SurfHit isect;
+    if (!scene_intersect(sc, ray, &isect)) {
+        for (int li : sc.infinite_lights) l += infinite_le(sc, li, ray);  // Light::le is zero for the other kinds
+        return l;
+    }
+    BSDF bsdf = make_bsdf(sc, isect, false);
+    const V3 n = isect.shading_n, wo = isect.wo;
+    int al = sc.prim_light.empty() ? -1 : sc.prim_light[isect.prim];
+    if (al >= 0) l += area_l(sc.lights[al], isect.n, wo);
+    for (size_t li = 0; li < sc.lights.size(); ++li) {
+        P2 u = sampler.get_2d();
+        LiSample ls = light_sample_li(sc, (int)li, isect, u);
+        if (!ls.valid) continue;
+        if (is_black(ls.value) || ls.pdf == 0.0f) continue;
+        RGB f = bsdf.f(wo, ls.wi, BSDF_ALL);
+        if (!is_black(f)) {
+            Ray sr = spawn_ray_to(isect.p, isect.p_error, isect.n, ls.p1, ls.p1_err, ls.p1_n, isect.time);
+            if (!scene_intersect_p(sc, sr)) l += f * ls.value * abs_dot(ls.wi, n) / ls.pdf;
+        }
+    }
+    if (depth + 1 < sc.integ.max_depth) {
+        RGB refl, trans;
+        {
+            P2 u = sampler.get_2d();
+            BxDFSample bs = bsdf.sample_f(wo, u, BSDF_REFLECTION | BSDF_SPECULAR);
+            if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(bs.wi, n) != 0.0f)
+                refl = bs.f * whitted_li(sc, spawn_ray(isect, bs.wi), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
+        }
+        {
+            P2 u = sampler.get_2d();
+            BxDFSample bs = bsdf.sample_f(wo, u, BSDF_TRANSMISSION | BSDF_SPECULAR);
+            if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(bs.wi, n) != 0.0f)
+                trans = bs.f * whitted_li(sc, spawn_ray(isect, bs.wi), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
+        }
+        l += refl + trans;
+    }
+    return l;
+}
+
+// Integrator::li of the scene's integrator
+inline RGB integrator_li(RenderScene& sc, Ray ray, Sampler& sampler) {
+    return sc.integ.type == B200PT_INTEGRATOR_WHITTED ? whitted_li(sc, ray, sampler, 0) : path_li(sc, ray, sampler);
+}
+
 // cameras/src/perspective_camera.rs:144-204 (differentials dropped) +
 // core/src/sampler/mod.rs:43-51.
 inline Ray camera_ray(const RenderScene& sc, int px, int py, Sampler& sampler, P2* p_film_out) {
@@ -1124,7 +1205,7 @@ inline FilmTile render_tile(RenderScene& sc, int tile_idx, int n_tiles_x, int ti
                 P2 p_film;
                 Ray ray = camera_ray(sc, x, y, *sampler, &p_film);
                 sc.n_camera.fetch_add(1, std::memory_order_relaxed);
-                RGB l = sanitize_radiance(path_li(sc, ray, *sampler));
+                RGB l = sanitize_radiance(integrator_li(sc, ray, *sampler));
                 tile_add_sample(sc, tile, p_film, l, 1.0f);
             } while (sampler->start_next_sample());
         }
@@ -1196,7 +1277,7 @@ inline void li_batch(RenderScene* scp, const int32_t* ps, int64_t n, float* out,
             Sampler* s = sampler_at(sc, ps[3 * i], ps[3 * i + 1], ps[3 * i + 2]);
             P2 pf;
             Ray ray = camera_ray(sc, ps[3 * i], ps[3 * i + 1], *s, &pf);
-            RGB l = sanitize_radiance(path_li(sc, ray, *s));
+            RGB l = sanitize_radiance(integrator_li(sc, ray, *s));
             out[3 * i] = l.c[0]; out[3 * i + 1] = l.c[1]; out[3 * i + 2] = l.c[2];
             delete s;
         }

@@ -85,6 +85,10 @@ struct Wave {
     // sort-by-material: key per slot (0 = miss / dead, 1 + material type otherwise) and the slots grouped by key
     uint8_t* key;
     int* sorted;
+    // Whitted integrator only: per-path stack of postponed specular-transmission children (3 float4 per entry,
+    // max_depth entries per path) and the per-shadow-ray contribution of the light loop (rgb, valid)
+    float4* wstack;
+    float4* sh_c;
 };
 static const int kBins = 5;
 
@@ -207,33 +211,19 @@ __global__ void __launch_bounds__(256) k_bin_scatter(Wave W, int n_active) {
     if (key >= 0) W.sorted[base + wcount[warp][key] + __popc(mine & ((1u << lane) - 1u))] = slot;
 }
 
-// ---- K4: shade --------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, int n_active) {
-    int i_sorted = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i_sorted >= n_active) return;
-    const int slot = W.sorted[i_sorted];
-    const int pid = W.qpid[cur][slot];
-    const float4 r0 = W.ray[cur][2 * slot], r1 = W.ray[cur][2 * slot + 1];
-    const float4 hit = W.hit[slot];
-    const float hb2 = W.hit_b2[slot];
-    const V3 ray_d = mk(r1.x, r1.y, r1.z);
-    const float time = r1.w;
-    int meta = W.meta[pid];
-    int dim = meta & 0xffff, bounces = (meta >> 16) & 0xff;
-    bool specular_bounce = ((meta >> 24) & 0xff) != 0;
-    if (bounces == 255) return;  // pixel outside the integrator's pixel bounds: no sample is taken
-    float4 Lw = W.L[pid], bw = W.beta[pid];
-    RGB L = rgb(Lw.x, Lw.y, Lw.z), beta = rgb(bw.x, bw.y, bw.z);
-    float eta_scale = bw.w;
-    const unsigned long long hidx = W.hidx[pid];
-    const uint32_t prim = __float_as_uint(hit.y);
-    const bool found = prim != 0xffffffffu;
-    (void)r0;
-
+// The SurfaceInteraction of a closest hit: Triangle::intersect's geometry (triangle.rs:548-725), Hit::new's normalised
+// wo (interaction/mod.rs:117-136) and, for a hit inside an object instance, transform_surface_interaction.
+struct HitCtx {
+    SurfHit sh;
+    V3 wo;
+    int mat, alight;
+    uint32_t pflags;
+};
+B2_D void surface_at(const DeviceScene& S, const Wave& W, int slot, uint32_t prim, float4 hit, float hb2, V3 ray_d, bool found, HitCtx* out) {
     V3 p0, p1, p2;
     int mat = 0, alight = -1;
     uint32_t pflags = 0;
-    SurfHit sh;
+    SurfHit& sh = out->sh;
     // Hit::new normalises wo (interaction/mod.rs:117-136)
     V3 wo_raw = -ray_d;
     float l2 = length_squared(wo_raw);
@@ -277,6 +267,119 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
             }
         }
     }
+    out->wo = hit_wo;
+    out->mat = mat;
+    out->alight = alight;
+    out->pflags = pflags;
+}
+
+// Light::sample_li for the three light kinds of this path (point.rs:83-94, diffuse.rs:114-129 over Triangle::sample
+// and Shape::sample_solid_angle, infinite.rs:133-175) plus the light-side endpoint of the VisibilityTester.
+struct LightSample {
+    bool valid;
+    V3 wi, p1, p1_err, p1_n;
+    float pdf;
+    RGB Li;
+    V3 q0, q1, q2;  // area light: its triangle
+    uint32_t lflags;
+};
+B2_D LightSample sample_light(const DeviceScene& S, const DLight& light, const SurfHit& sh, P2 u_light) {
+    bool li_valid = false;
+    V3 wi = mk(0.0f, 0.0f, 0.0f), lp1 = wi, lp1_err = wi, lp1_n = wi;
+    float light_pdf = 0.0f;
+    RGB Li = rgb1(0.0f);
+    V3 q0 = mk(0, 0, 0), q1 = q0, q2 = q0;  // area light triangle
+    bool lflip = false;
+    uint32_t lflags = 0;
+    if (light.type == LT_POINT) {  // point.rs:83-94
+        V3 pl = mk(light.pos[0], light.pos[1], light.pos[2]);
+        wi = normalize(pl - sh.p);
+        light_pdf = 1.0f;
+        lp1 = pl;
+        Li = ldrgb(light.L) / distance_squared(pl, sh.p);
+        li_valid = true;
+    } else if (light.type == LT_AREA) {
+        int m2, l2i; uint32_t f2;
+        load_prim(S, (uint32_t)light.prim, &q0, &q1, &q2, &m2, &l2i, &f2);
+        lflip = (f2 & 1u) != 0;
+        lflags = f2;
+        // Triangle::sample (triangle.rs:918-949) + Shape::sample_solid_angle (shape.rs:64-79)
+        float su0 = sqrtf(u_light.x);
+        float bx = 1.0f - su0, by = u_light.y * su0;
+        V3 p = bx * q0 + by * q1 + (1.0f - bx - by) * q2;
+        V3 n = normalize(cross(q1 - q0, q2 - q0));
+        if (lflip) n = -1.0f * n;
+        V3 pas = vabs(bx * q0) + vabs(by * q1) + vabs((1.0f - bx - by) * q2);
+        V3 p_err = kGamma6 * pas;
+        float pdf = 1.0f / light.area;
+        V3 w = p - sh.p;
+        if (length_squared(w) == 0.0f) pdf = 0.0f;
+        else {
+            w = normalize(w);
+            pdf *= distance_squared(sh.p, p) / abs_dot(n, -w);
+            if (isinf(pdf)) pdf = 0.0f;
+        }
+        V3 w2 = p - sh.p;  // DiffuseAreaLight::sample_li, diffuse.rs:114-129
+        float wl2 = length_squared(w2);
+        if (!(pdf == 0.0f || wl2 == 0.0f)) {
+            w2 = w2 / sqrtf(wl2);
+            wi = w2; light_pdf = pdf;
+            Li = area_l(light, n, -w2);
+            lp1 = p; lp1_err = p_err; lp1_n = n;
+            li_valid = true;
+        }
+    } else {  // InfiniteAreaLight::sample_li, infinite.rs:133-175
+        const DInfDistr& D = S.inf_distr[light.inf_slot];
+        float pdf1, pdf0; int v, dummy;
+        float d1 = distr_sample_continuous(D.mfunc, D.mcdf, D.mfunc_int, D.nv, u_light.y, &pdf1, &v);
+        float d0 = distr_sample_continuous(D.func + (long long)v * D.nu, D.cdf + (long long)v * (D.nu + 1), D.func_int[v], D.nu, u_light.x, &pdf0, &dummy);
+        float map_pdf = pdf0 * pdf1;
+        if (map_pdf != 0.0f) {
+            float theta = d1 * kPi, phi = d0 * kTwoPi;
+            float cos_t = lmx::cosf_glibc(theta), sin_t = lmx::sinf_glibc(theta);
+            float sin_p = lmx::sinf_glibc(phi), cos_p = lmx::cosf_glibc(phi);
+            wi = xf3(light.l2w, mk(sin_t * cos_p, sin_t * sin_p, cos_t));
+            light_pdf = map_pdf / (kTwoPi * kPi * sin_t);
+            if (sin_t == 0.0f) light_pdf = 0.0f;
+            lp1 = sh.p + wi * (2.0f * S.world_radius);
+            Li = inf_lookup(D, mk2(d0, d1));
+            li_valid = true;
+        }
+    }
+    LightSample r;
+    r.valid = li_valid; r.wi = wi; r.p1 = lp1; r.p1_err = lp1_err; r.p1_n = lp1_n; r.pdf = light_pdf; r.Li = Li;
+    r.q0 = q0; r.q1 = q1; r.q2 = q2; r.lflags = lflags;
+    return r;
+}
+
+// ---- K4: shade --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, int n_active) {
+    int i_sorted = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i_sorted >= n_active) return;
+    const int slot = W.sorted[i_sorted];
+    const int pid = W.qpid[cur][slot];
+    const float4 r0 = W.ray[cur][2 * slot], r1 = W.ray[cur][2 * slot + 1];
+    const float4 hit = W.hit[slot];
+    const float hb2 = W.hit_b2[slot];
+    const V3 ray_d = mk(r1.x, r1.y, r1.z);
+    const float time = r1.w;
+    int meta = W.meta[pid];
+    int dim = meta & 0xffff, bounces = (meta >> 16) & 0xff;
+    bool specular_bounce = ((meta >> 24) & 0xff) != 0;
+    if (bounces == 255) return;  // pixel outside the integrator's pixel bounds: no sample is taken
+    float4 Lw = W.L[pid], bw = W.beta[pid];
+    RGB L = rgb(Lw.x, Lw.y, Lw.z), beta = rgb(bw.x, bw.y, bw.z);
+    float eta_scale = bw.w;
+    const unsigned long long hidx = W.hidx[pid];
+    const uint32_t prim = __float_as_uint(hit.y);
+    const bool found = prim != 0xffffffffu;
+    (void)r0;
+
+    HitCtx hc;
+    surface_at(S, W, slot, prim, hit, hb2, ray_d, found, &hc);
+    const SurfHit& sh = hc.sh;
+    const V3 hit_wo = hc.wo;
+    const int mat = hc.mat, alight = hc.alight;
     // path.rs:123-134: emitted light at the vertex / from the environment
     if (bounces == 0 || specular_bounce) {
         if (found) {
@@ -313,68 +416,13 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
             // ---- estimate_direct (common.rs:146-299), light-sampling half ----
             RGB ld_light = rgb1(0.0f);
             int shadow_slot = -1, mis_slot = -1;
-            bool li_valid = false;
-            V3 wi = mk(0.0f, 0.0f, 0.0f), lp1 = wi, lp1_err = wi, lp1_n = wi;
-            float light_pdf = 0.0f;
-            RGB Li = rgb1(0.0f);
-            V3 q0 = mk(0, 0, 0), q1 = q0, q2 = q0;  // area light triangle
-            bool lflip = false;
-            uint32_t lflags = 0;
-            if (light.type == LT_POINT) {  // point.rs:83-94
-                V3 pl = mk(light.pos[0], light.pos[1], light.pos[2]);
-                wi = normalize(pl - sh.p);
-                light_pdf = 1.0f;
-                lp1 = pl;
-                Li = ldrgb(light.L) / distance_squared(pl, sh.p);
-                li_valid = true;
-            } else if (light.type == LT_AREA) {
-                int m2, l2i; uint32_t f2;
-                load_prim(S, (uint32_t)light.prim, &q0, &q1, &q2, &m2, &l2i, &f2);
-                lflip = (f2 & 1u) != 0;
-                lflags = f2;
-                // Triangle::sample (triangle.rs:918-949) + Shape::sample_solid_angle (shape.rs:64-79)
-                float su0 = sqrtf(u_light.x);
-                float bx = 1.0f - su0, by = u_light.y * su0;
-                V3 p = bx * q0 + by * q1 + (1.0f - bx - by) * q2;
-                V3 n = normalize(cross(q1 - q0, q2 - q0));
-                if (lflip) n = -1.0f * n;
-                V3 pas = vabs(bx * q0) + vabs(by * q1) + vabs((1.0f - bx - by) * q2);
-                V3 p_err = kGamma6 * pas;
-                float pdf = 1.0f / light.area;
-                V3 w = p - sh.p;
-                if (length_squared(w) == 0.0f) pdf = 0.0f;
-                else {
-                    w = normalize(w);
-                    pdf *= distance_squared(sh.p, p) / abs_dot(n, -w);
-                    if (isinf(pdf)) pdf = 0.0f;
-                }
-                V3 w2 = p - sh.p;  // DiffuseAreaLight::sample_li, diffuse.rs:114-129
-                float wl2 = length_squared(w2);
-                if (!(pdf == 0.0f || wl2 == 0.0f)) {
-                    w2 = w2 / sqrtf(wl2);
-                    wi = w2; light_pdf = pdf;
-                    Li = area_l(light, n, -w2);
-                    lp1 = p; lp1_err = p_err; lp1_n = n;
-                    li_valid = true;
-                }
-            } else {  // InfiniteAreaLight::sample_li, infinite.rs:133-175
-                const DInfDistr& D = S.inf_distr[light.inf_slot];
-                float pdf1, pdf0; int v, dummy;
-                float d1 = distr_sample_continuous(D.mfunc, D.mcdf, D.mfunc_int, D.nv, u_light.y, &pdf1, &v);
-                float d0 = distr_sample_continuous(D.func + (long long)v * D.nu, D.cdf + (long long)v * (D.nu + 1), D.func_int[v], D.nu, u_light.x, &pdf0, &dummy);
-                float map_pdf = pdf0 * pdf1;
-                if (map_pdf != 0.0f) {
-                    float theta = d1 * kPi, phi = d0 * kTwoPi;
-                    float cos_t = lmx::cosf_glibc(theta), sin_t = lmx::sinf_glibc(theta);
-                    float sin_p = lmx::sinf_glibc(phi), cos_p = lmx::cosf_glibc(phi);
-                    wi = xf3(light.l2w, mk(sin_t * cos_p, sin_t * sin_p, cos_t));
-                    light_pdf = map_pdf / (kTwoPi * kPi * sin_t);
-                    if (sin_t == 0.0f) light_pdf = 0.0f;
-                    lp1 = sh.p + wi * (2.0f * S.world_radius);
-                    Li = inf_lookup(D, mk2(d0, d1));
-                    li_valid = true;
-                }
-            }
+            const LightSample ls = sample_light(S, light, sh, u_light);
+            const bool li_valid = ls.valid;
+            const V3 wi = ls.wi, lp1 = ls.p1, lp1_err = ls.p1_err, lp1_n = ls.p1_n;
+            const float light_pdf = ls.pdf;
+            const RGB Li = ls.Li;
+            const V3 q0 = ls.q0, q1 = ls.q1, q2 = ls.q2;
+            const uint32_t lflags = ls.lflags;
             float scattering_pdf = 0.0f;
             if (li_valid && light_pdf > 0.0f && !is_black(Li)) {
                 RGB f = bsdf_f(bsdf, hit_wo, wi, kNoSpec) * abs_dot(wi, sh.ns);
@@ -479,6 +527,189 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
     int ns = atomicAdd(&W.counters[0], 1);
     store_ray(W.ray[cur ^ 1], ns, next_o, bs.wi, __int_as_float(0x7f800000), time);
     W.qpid[cur ^ 1][ns] = pid;
+}
+
+// ---- K4w: WhittedIntegrator::li (integrators/src/whitted.rs:60-126) as a wavefront stage ---------------------------
+// The reference recurses: reflect subtree, then transmit subtree, drawing sampler dimensions in that depth-first order.
+// Here every path walks its own tree depth-first, one node per wave iteration: the specular-transmission child of a
+// node is computed at the node (delta lobes ignore the sample value) and parked on the path's stack while the
+// reflection subtree runs; popping it consumes the two dimensions specular_transmit's get_2d() would have drawn at that
+// point, so every later light sample sees the reference's dimension.  A node's own radiance
+// l = Le + sum over ALL lights of f * Li * |wi . ns| / pdf (unoccluded) is formed in the reference's order by
+// k_resolve_whitted and enters the pixel as L += beta * l with beta the product of f * |wi . ns| / pdf down the tree
+// (the reference multiplies on the way back up: same value up to f32 rounding, identical for depth-0 nodes).
+// Shadow rays of pending record k live at slots [k * n_lights, (k + 1) * n_lights), one per light, invalid ones with
+// t_max = -1.
+B2_D void wstack_store(const Wave& W, int max_depth, int pid, int sp, V3 o, V3 d, float time, RGB beta, int depth, bool valid) {
+    float4* e = W.wstack + ((long long)pid * max_depth + sp) * 3;
+    e[0] = make_float4(o.x, o.y, o.z, time);
+    e[1] = make_float4(d.x, d.y, d.z, __int_as_float(valid ? depth : -1));
+    e[2] = make_float4(beta.r, beta.g, beta.b, 0.0f);
+}
+
+__global__ void __launch_bounds__(128) k_shade_whitted(DeviceScene S, Wave W, int cur, int n_active) {
+    int i_sorted = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i_sorted >= n_active) return;
+    const int slot = W.sorted[i_sorted];
+    const int pid = W.qpid[cur][slot];
+    const float4 r1 = W.ray[cur][2 * slot + 1];
+    const float4 hit = W.hit[slot];
+    const float hb2 = W.hit_b2[slot];
+    const V3 ray_d = mk(r1.x, r1.y, r1.z);
+    const float time = r1.w;
+    int meta = W.meta[pid];
+    int dim = meta & 0xffff, depth = (meta >> 16) & 0xff, sp = (meta >> 24) & 0xff;
+    if (depth == 255) return;  // pixel outside the integrator's pixel bounds: no sample is taken
+    const float4 Lw = W.L[pid], bw = W.beta[pid];
+    RGB L = rgb(Lw.x, Lw.y, Lw.z);
+    const RGB beta = rgb(bw.x, bw.y, bw.z);
+    const unsigned long long hidx = W.hidx[pid];
+    const uint32_t prim = __float_as_uint(hit.y);
+    const bool found = prim != 0xffffffffu;
+
+    bool have_next = false;
+    V3 next_o = mk(0, 0, 0), next_d = next_o;
+    RGB next_beta = beta;
+    int next_depth = 0;
+
+    if (!found) {  // whitted.rs:117-121
+        RGB l = rgb1(0.0f);
+        for (int i = 0; i < S.n_infinite; ++i) {
+            const DLight& il = S.lights[S.infinite_lights[i]];
+            l = l + infinite_le(il, S.inf_distr[il.inf_slot], ray_d);
+        }
+        L = L + beta * l;
+    } else {
+        if (dim + 2 * S.n_lights + 4 > 1000) {  // HaltonSampler can only sample 1000 dimensions (halton.rs:106-110 asserts)
+            atomicExch(&W.counters[4], 1);
+            return;
+        }
+        HitCtx hc;
+        surface_at(S, W, slot, prim, hit, hb2, ray_d, true, &hc);
+        const SurfHit& sh = hc.sh;
+        const V3 wo = hc.wo;
+        BSDF bsdf;
+        bsdf.ns = sh.ns; bsdf.ng = sh.n;
+        bsdf.ss = normalize(sh.dpdu);
+        bsdf.ts = cross(bsdf.ns, bsdf.ss);
+        bsdf.m = S.materials + hc.mat;  // built with allow_multiple_lobes = false (whitted.rs:76)
+        RGB le = rgb1(0.0f);
+        if (hc.alight >= 0) le = area_l(S.lights[hc.alight], sh.n, wo);  // isect.le(&wo), whitted.rs:87
+        // whitted.rs:89-112: one sample of every light
+        int rec = -1;
+        for (int li = 0; li < S.n_lights; ++li) {
+            P2 u = smp_2d(S, hidx, dim);
+            const DLight& light = S.lights[li];
+            const LightSample ls = sample_light(S, light, sh, u);
+            bool want = false;
+            RGB c = rgb1(0.0f);
+            if (ls.valid && !is_black(ls.Li) && ls.pdf != 0.0f) {
+                RGB f = bsdf_f(bsdf, wo, ls.wi, BSDF_ALL);
+                if (!is_black(f)) { want = true; c = f * ls.Li * abs_dot(ls.wi, sh.ns) / ls.pdf; }
+            }
+            if (want && rec < 0) {
+                rec = atomicAdd(&W.counters[3], 1);
+                for (int j = 0; j < li; ++j) {
+                    const long long sl = (long long)rec * S.n_lights + j;
+                    W.sh_c[sl] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    store_ray(W.sh_ray, (int)sl, mk(0, 0, 0), mk(0, 0, 1), -1.0f, 0.0f);
+                }
+            }
+            if (rec >= 0) {
+                const long long sl = (long long)rec * S.n_lights + li;
+                if (want) {
+                    V3 origin = offset_ray_origin(sh.p, sh.p_error, sh.n, ls.p1 - sh.p);  // Hit::spawn_ray_to_hit
+                    V3 target = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, origin - ls.p1);
+                    store_ray(W.sh_ray, (int)sl, origin, target - origin, 1.0f - kShadowEps, time);
+                    W.sh_c[sl] = make_float4(c.r, c.g, c.b, 1.0f);
+                } else {
+                    W.sh_c[sl] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    store_ray(W.sh_ray, (int)sl, mk(0, 0, 0), mk(0, 0, 1), -1.0f, 0.0f);
+                }
+            }
+        }
+        if (rec >= 0) {
+            W.pend_q[rec] = pid;
+            W.pend_a[pid] = make_float4(le.r, le.g, le.b, 0.0f);
+            W.pend_c[pid] = make_float4(beta.r, beta.g, beta.b, 0.0f);
+        } else {
+            L = L + beta * le;
+        }
+        // whitted.rs:113-116 -> specular_reflect / specular_transmit (sampler_integrator.rs:79-238)
+        if (depth + 1 < S.max_depth) {
+            const V3 wo_l = bsdf_to_local(bsdf, wo);
+            bool r_ok = false, t_ok = false;
+            V3 r_wi = mk(0, 0, 0), t_wi = r_wi;
+            RGB r_beta = beta, t_beta = beta;
+            for (int k = 0; k < bsdf.m->n_bxdf; ++k) {
+                const DBxDF& b = bsdf.m->bx[k];
+                if (wo_l.z == 0.0f) break;  // BSDF::sample_f, bsdf.rs:227-229
+                if (b.kind == BX_SPEC_REFL && !r_ok) {
+                    BxDFSample bs = spec_refl_sample_f(b, wo_l);
+                    V3 wi = bsdf_to_world(bsdf, bs.wi);
+                    if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(wi, sh.ns) != 0.0f) { r_ok = true; r_wi = wi; r_beta = beta * (bs.f * abs_dot(wi, sh.ns) / bs.pdf); }
+                } else if (b.kind == BX_SPEC_TRANS && !t_ok) {
+                    BxDFSample bs = spec_trans_sample_f(b, wo_l);
+                    V3 wi = bsdf_to_world(bsdf, bs.wi);
+                    if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(wi, sh.ns) != 0.0f) { t_ok = true; t_wi = wi; t_beta = beta * (bs.f * abs_dot(wi, sh.ns) / bs.pdf); }
+                }
+            }
+            dim += 2;  // specular_reflect: sampler.get_2d()
+            if (r_ok) {
+                have_next = true;
+                next_o = offset_ray_origin(sh.p, sh.p_error, sh.n, r_wi);  // Hit::spawn_ray
+                next_d = r_wi; next_beta = r_beta; next_depth = depth + 1;
+                // specular_transmit runs after the whole reflection subtree: park it (its get_2d is charged at the pop)
+                V3 to = t_ok ? offset_ray_origin(sh.p, sh.p_error, sh.n, t_wi) : mk(0, 0, 0);
+                wstack_store(W, S.max_depth, pid, sp, to, t_wi, time, t_beta, depth + 1, t_ok);
+                sp += 1;
+            } else {
+                dim += 2;  // specular_transmit: sampler.get_2d()
+                if (t_ok) {
+                    have_next = true;
+                    next_o = offset_ray_origin(sh.p, sh.p_error, sh.n, t_wi);
+                    next_d = t_wi; next_beta = t_beta; next_depth = depth + 1;
+                }
+            }
+        }
+    }
+    float next_time = time;
+    while (!have_next && sp > 0) {  // return to the innermost node that still owes its specular_transmit
+        sp -= 1;
+        const float4* e = W.wstack + ((long long)pid * S.max_depth + sp) * 3;
+        const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+        dim += 2;
+        const int d = __float_as_int(e1.w);
+        if (d >= 0) {
+            have_next = true;
+            next_o = mk(e0.x, e0.y, e0.z); next_d = mk(e1.x, e1.y, e1.z); next_time = e0.w;
+            next_beta = rgb(e2.x, e2.y, e2.z); next_depth = d;
+        }
+    }
+    W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
+    if (!have_next) return;
+    W.beta[pid] = make_float4(next_beta.r, next_beta.g, next_beta.b, bw.w);
+    W.meta[pid] = meta_pack(dim, next_depth, sp);
+    int ns = atomicAdd(&W.counters[0], 1);
+    store_ray(W.ray[cur ^ 1], ns, next_o, next_d, __int_as_float(0x7f800000), next_time);
+    W.qpid[cur ^ 1][ns] = pid;
+}
+
+// l = Le + sum of the unoccluded light contributions in light order; L += beta * l  (whitted.rs:87-112)
+__global__ void __launch_bounds__(256) k_resolve_whitted(DeviceScene S, Wave W, int n_pend) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pend) return;
+    const int pid = W.pend_q[i];
+    const float4 a = W.pend_a[pid], b = W.pend_c[pid];
+    RGB l = rgb(a.x, a.y, a.z);
+    for (int li = 0; li < S.n_lights; ++li) {
+        const long long sl = (long long)i * S.n_lights + li;
+        const float4 c = W.sh_c[sl];
+        if (c.w != 0.0f && !W.sh_occ[sl]) l = l + rgb(c.x, c.y, c.z);
+    }
+    float4 Lw = W.L[pid];
+    RGB L = rgb(Lw.x, Lw.y, Lw.z) + rgb(b.x, b.y, b.z) * l;
+    W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
 }
 
 // ---- (0,2)-sequence prepass: one thread per reference tile replays the tile sampler's PCG32 stream ------------
@@ -643,6 +874,7 @@ struct SceneImpl {
     AccelImpl accel;
     Accel2Impl accel2;        // two-level scenes (instancing)
     bool instanced = false;
+    bool whitted = false;     // WhittedIntegrator instead of PathIntegrator
     DeviceScene dev;
     b200pt_film film;
     b200pt_sampler sampler;
@@ -669,6 +901,12 @@ struct SceneImpl {
 };
 
 static const int kWaveCap = 1 << 22;
+// Whitted tests one shadow ray per light and node: keep paths x lights within 2^24 shadow slots
+static int wave_cap_for(const SceneImpl* s) {
+    if (!s->whitted) return kWaveCap;
+    long long c = (1ll << 24) / std::max(1, s->dev.n_lights);
+    return (int)std::min<long long>(kWaveCap, std::max<long long>(c, 1024));
+}
 
 template <class T> static int dev_upload(SceneImpl* s, const std::vector<T>& v, const T** out) {
     void* p = nullptr;
@@ -699,7 +937,7 @@ static float alpha_clamp(float a) { return 0.001f > a ? 0.001f : a; }  // Trowbr
 
 // materials/src/{matte,plastic,glass,metal}.rs compute_scattering_functions with constant textures,
 // evaluated once per material instead of once per intersection.
-static DMaterial make_material(const b200pt_material& m) {
+static DMaterial make_material(const b200pt_material& m, bool allow_multiple_lobes) {
     DMaterial d;
     std::memset(&d, 0, sizeof(d));
     d.type = m.type;
@@ -743,7 +981,18 @@ static DMaterial make_material(const b200pt_material& m) {
             float r[3] = {clamp0(m.ks[0]), clamp0(m.ks[1]), clamp0(m.ks[2])}, t[3] = {clamp0(m.kt[0]), clamp0(m.kt[1]), clamp0(m.kt[2])};
             if (!(black3(r) && black3(t))) {
                 bool is_spec = ur == 0.0f && vr == 0.0f;
-                if (is_spec) {  // allow_multiple_lobes is always true on the path integrator (path.rs:145)
+                if (is_spec && !allow_multiple_lobes) {  // whitted.rs:76 passes false: two delta lobes (glass.rs:112-120)
+                    if (!black3(r)) {
+                        DBxDF& x = lobe(BX_SPEC_REFL, BSDF_REFLECTION | BSDF_SPECULAR);
+                        std::memcpy(x.r, r, 12);
+                        x.conductor = 0; x.fr_eta_i = 1.0f; x.fr_eta_t = eta;
+                    }
+                    if (!black3(t)) {
+                        DBxDF& x = lobe(BX_SPEC_TRANS, BSDF_TRANSMISSION | BSDF_SPECULAR);
+                        std::memcpy(x.t, t, 12);
+                        x.eta_a = 1.0f; x.eta_b = eta;
+                    }
+                } else if (is_spec) {  // allow_multiple_lobes is true on the path integrator (path.rs:145)
                     DBxDF& x = lobe(BX_FRESNEL_SPECULAR, BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR);
                     std::memcpy(x.r, r, 12); std::memcpy(x.t, t, 12);
                     x.eta_a = 1.0f; x.eta_b = eta;
@@ -811,8 +1060,14 @@ static int wave_alloc(SceneImpl* s, int cap) {
     if ((rc = dev_alloc(s, (size_t)cap, &W.hit))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.hit_b2))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.hit_inst))) return rc;
-    if ((rc = dev_alloc(s, (size_t)cap * 2, &W.sh_ray))) return rc;
-    if ((rc = dev_alloc(s, (size_t)cap, &W.sh_occ))) return rc;
+    const size_t sh_cap = s->whitted ? (size_t)cap * (size_t)std::max(1, s->dev.n_lights) : (size_t)cap;
+    if ((rc = dev_alloc(s, sh_cap * 2, &W.sh_ray))) return rc;
+    if ((rc = dev_alloc(s, sh_cap, &W.sh_occ))) return rc;
+    W.wstack = nullptr; W.sh_c = nullptr;
+    if (s->whitted) {
+        if ((rc = dev_alloc(s, sh_cap, &W.sh_c))) return rc;
+        if ((rc = dev_alloc(s, (size_t)cap * (size_t)std::max(1, s->dev.max_depth) * 3, &W.wstack))) return rc;
+    }
     if ((rc = dev_alloc(s, (size_t)cap * 2, &W.mis_ray))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.mis_hit))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.L))) return rc;
@@ -870,6 +1125,46 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
     return B200PT_OK;
 }
 
+// WhittedIntegrator: one tree node per path and iteration until every path has walked its whole tree.
+static int run_wave_whitted(SceneImpl* s, int n, cudaStream_t st) {
+    Wave& W = s->wave;
+    int cur = 0, n_active = n;
+    s->rays[0] += (uint64_t)n;
+    const int nl = s->dev.n_lights;
+    const long long max_iter = 1ll << std::min(std::max(s->dev.max_depth, 1), 24);  // a binary tree of depth max_depth
+    for (long long iter = 0; n_active > 0 && iter < max_iter; ++iter) {
+        int rc = s->instanced ? launch_intersect2(s->accel2.dev, W.ray[cur], n_active, W.hit, st, W.hit_b2, W.hit_inst)
+                              : launch_intersect(s->dev.accel, W.ray[cur], n_active, W.hit, st, 0, W.hit_b2);
+        if (rc) return rc;
+        s->rays[1] += (uint64_t)n_active;
+        B2_CUDA(cudaMemsetAsync(W.counters, 0, 32 * sizeof(int), st));
+        k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, n_active);
+        k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, n_active);
+        k_shade_whitted<<<(n_active + 127) / 128, 128, 0, st>>>(s->dev, W, cur, n_active);
+        g_launches.fetch_add(3);
+        int cnt[5];
+        B2_CUDA(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        if (cnt[4]) {
+            b200pt_set_error("whitted: a camera sample needs more than 1000 sampler dimensions (lights x tree nodes); the reference's HaltonSampler asserts here (samplers/src/halton.rs:106-110)");
+            return B200PT_ERR_UNSUPPORTED;
+        }
+        if (cnt[3] > 0) {
+            const int64_t n_sh = (int64_t)cnt[3] * nl;
+            rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, n_sh, W.sh_occ, st) : launch_occluded(s->dev.accel, W.sh_ray, n_sh, W.sh_occ, st, 0);
+            if (rc) return rc;
+            s->rays[2] += (uint64_t)n_sh;
+            k_resolve_whitted<<<(cnt[3] + 255) / 256, 256, 0, st>>>(s->dev, W, cnt[3]);
+            g_launches.fetch_add(1);
+        }
+        cur ^= 1;
+        n_active = cnt[0];
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wavefront kernels (whitted)");
+    return B200PT_OK;
+}
+
 }  // namespace b2
 
 struct b200pt_scene {
@@ -893,6 +1188,17 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     if (d->sampler.type != B200PT_SAMPLER_HALTON && d->sampler.type != B200PT_SAMPLER_ZEROTWO) {
         b200pt_set_error("b200pt_scene_create: unknown sampler type (halton and 02sequence are on this path)");
         return B200PT_ERR_UNSUPPORTED;
+    }
+    if (d->integrator.type != B200PT_INTEGRATOR_PATH && d->integrator.type != B200PT_INTEGRATOR_WHITTED) {
+        b200pt_set_error("b200pt_scene_create: unknown integrator type (path and whitted are on this path)");
+        return B200PT_ERR_UNSUPPORTED;
+    }
+    if (d->integrator.type == B200PT_INTEGRATOR_WHITTED) {
+        // The number of get_2d() calls of one camera sample depends on the tree it spawns; the (0,2) sampler would fall
+        // back to the tile RNG (see below).  Halton is a pure function of (pixel, sample, dimension).
+        if (d->sampler.type != B200PT_SAMPLER_HALTON) { b200pt_set_error("b200pt_scene_create: the whitted integrator needs the halton sampler on this path"); return B200PT_ERR_UNSUPPORTED; }
+        if (d->integrator.max_depth < 0 || d->integrator.max_depth > 24) { b200pt_set_error("b200pt_scene_create: whitted maxdepth must be in [0, 24]"); return B200PT_ERR_UNSUPPORTED; }
+        if ((long long)d->n_lights * 1024 > (1ll << 24)) { b200pt_set_error("b200pt_scene_create: whitted: more than 16384 lights"); return B200PT_ERR_UNSUPPORTED; }
     }
     if (d->sampler.type == B200PT_SAMPLER_ZEROTWO) {
         // Past its pre-generated slots the reference's PixelSampler draws from the TILE's RNG inside li(), which makes the
@@ -978,7 +1284,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     }
 
     std::vector<DMaterial> mats;
-    for (int i = 0; i < d->n_materials; ++i) mats.push_back(make_material(d->materials[i]));
+    for (int i = 0; i < d->n_materials; ++i) mats.push_back(make_material(d->materials[i], d->integrator.type != B200PT_INTEGRATOR_WHITTED));
     if ((rc = dev_upload(s, mats, &D.materials))) return fail(rc);
 
     // Scene::new (core/src/scene.rs:50-77): world bound, infinite lights, Light::preprocess
@@ -1061,6 +1367,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     std::memcpy(D.sb, s->sample_bounds, 16);
     std::memcpy(D.pb, d->integrator.pixel_bounds, 16);
     D.max_depth = d->integrator.max_depth;
+    s->whitted = d->integrator.type == B200PT_INTEGRATOR_WHITTED;
     D.rr_threshold = d->integrator.rr_threshold;
 
     // HaltonSampler::new over the sample bounds (samplers/src/halton.rs:61-100, 262-275)
@@ -1148,7 +1455,7 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
     const int* sb = s->sample_bounds;
     const int sw = sb[2] - sb[0], sh = sb[3] - sb[1], spp = s->spp;
     const long long n_samples = (long long)srows.size() * sw * spp;
-    if (!s->wave_cap && (rc = wave_alloc(s, kWaveCap))) return rc;
+    if (!s->wave_cap && (rc = wave_alloc(s, wave_cap_for(s)))) return rc;
     if (n_samples > s->sample_cap) {
         if (s->d_sample_L) cudaFree(s->d_sample_L);
         if (s->d_sample_pf) cudaFree(s->d_sample_pf);
@@ -1173,7 +1480,7 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
         int n = (int)std::min<long long>(s->wave_cap, n_samples - first);
         k_raygen<<<(n + 255) / 256, 256, 0, st>>>(s->dev, s->wave, first, n, spp, s->d_rows, nullptr, d_pf, nullptr);
         g_launches.fetch_add(1);
-        rc = run_wave(s, n, st);
+        rc = s->whitted ? run_wave_whitted(s, n, st) : run_wave(s, n, st);
         if (rc) break;
         k_store_samples<<<(n + 255) / 256, 256, 0, st>>>(s->wave, n, d_L + first);
         g_launches.fetch_add(1);
@@ -1283,7 +1590,7 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
     SceneImpl* s = &sc->impl;
     std::lock_guard<std::mutex> g(s->mu);
     B2_CUDA(cudaSetDevice(g_device));
-    if (!s->wave_cap && (rc = wave_alloc(s, kWaveCap))) return rc;
+    if (!s->wave_cap && (rc = wave_alloc(s, wave_cap_for(s)))) return rc;
     if (s->dev.sampler_type == B200PT_SAMPLER_ZEROTWO) {  // explicit lists may name any pixel: own every sample row
         const int* sb = s->sample_bounds;
         const int sw = sb[2] - sb[0], sh = sb[3] - sb[1];
@@ -1315,7 +1622,7 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
         cudaMemcpy(d_list, pixel_sample + 3 * first, (size_t)m * 3 * sizeof(int), cudaMemcpyHostToDevice);
         k_raygen<<<(m + 255) / 256, 256>>>(s->dev, s->wave, 0, m, s->spp, nullptr, d_list, nullptr, d_rays);
         g_launches.fetch_add(1);
-        rc = run_wave(s, m, 0);
+        rc = s->whitted ? run_wave_whitted(s, m, 0) : run_wave(s, m, 0);
         if (rc) break;
         k_store_samples<<<(m + 255) / 256, 256>>>(s->wave, m, d_L);
         g_launches.fetch_add(1);

@@ -678,10 +678,11 @@ void Builder::finish() {
     } else throw Unsupported("Sampler \"" + sampler_name + "\" is outside this path (halton, 02sequence)");
 
     // --- Integrator (path.rs:287-326) ---
-    if (integrator_name != "path") throw Unsupported("Integrator \"" + integrator_name + "\" is outside this path (path)");
+    if (integrator_name != "path" && integrator_name != "whitted") throw Unsupported("Integrator \"" + integrator_name + "\" is outside this path (path, whitted)");
+    d.integrator.type = integrator_name == "whitted" ? B200PT_INTEGRATOR_WHITTED : B200PT_INTEGRATOR_PATH;  // whitted.rs:133-158 reads maxdepth and pixelbounds only
     d.integrator.max_depth = integrator_p.one_int("maxdepth", 5);
     d.integrator.rr_threshold = integrator_p.one_float("rrthreshold", 1.0f);
-    std::string strat = integrator_p.one_string("lightsamplestrategy", "spatial");
+    std::string strat = integrator_p.one_string("lightsamplestrategy", integrator_name == "whitted" ? "uniform" : "spatial");
     if (strat == "uniform") d.integrator.light_strategy = B200PT_LIGHTS_UNIFORM;
     else if (strat == "power") d.integrator.light_strategy = B200PT_LIGHTS_POWER;
     else throw Unsupported("lightsamplestrategy \"" + strat + "\": the spatial strategy is racy in the reference and outside this path; use \"uniform\" or \"power\"");

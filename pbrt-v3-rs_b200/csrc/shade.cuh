@@ -176,7 +176,7 @@ B2_D V3 tr_sample_wh(TRDist d, V3 wo, P2 u) {  // :100-141 (visible-area branch)
 
 // ---- BxDFs (core/src/reflection/*.rs) ----------------------------------------------
 enum : uint32_t { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
-enum : int { BX_LAMBERT = 0, BX_OREN_NAYAR = 1, BX_MF_REFL = 2, BX_MF_TRANS = 3, BX_FRESNEL_SPECULAR = 4 };
+enum : int { BX_LAMBERT = 0, BX_OREN_NAYAR = 1, BX_MF_REFL = 2, BX_MF_TRANS = 3, BX_FRESNEL_SPECULAR = 4, BX_SPEC_REFL = 5, BX_SPEC_TRANS = 6 };
 
 // One lobe with every per-material constant already evaluated on the host
 // (constant textures; roughness remap via ln() done once instead of per hit).
@@ -344,6 +344,33 @@ B2_D BxDFSample bx_sample_f(const DBxDF& b, V3 wo, P2 u) {
             return s;
         }
     }
+}
+
+// SpecularReflection::sample_f (specular_reflection.rs:45-51) and SpecularTransmission::sample_f
+// (specular_transmission.rs:60-81, TransportMode::Radiance): the two delta lobes glass gets when the integrator does
+// not allow multiple lobes (glass.rs:112-120; WhittedIntegrator).  Their f() and pdf() are zero (bx_f / bx_pdf defaults).
+B2_D BxDFSample spec_refl_sample_f(const DBxDF& b, V3 wo) {
+    BxDFSample s;
+    V3 wi = mk(-wo.x, -wo.y, wo.z);
+    s.type = b.type;
+    s.pdf = 1.0f;
+    s.f = rgb1(fr_dielectric(cos_theta(wi), b.fr_eta_i, b.fr_eta_t)) * ldrgb(b.r) / abs_cos_theta(wi);
+    s.wi = wi;
+    return s;
+}
+B2_D BxDFSample spec_trans_sample_f(const DBxDF& b, V3 wo) {
+    BxDFSample s;
+    s.f = rgb1(0.0f); s.pdf = 0.0f; s.wi = mk(0.0f, 0.0f, 0.0f); s.type = b.type;
+    bool entering = cos_theta(wo) > 0.0f;
+    float eta_i = entering ? b.eta_a : b.eta_b, eta_t = entering ? b.eta_b : b.eta_a;
+    V3 wi;
+    if (!refract(wo, face_forward(mk(0.0f, 0.0f, 1.0f), wo), eta_i / eta_t, &wi)) return s;
+    s.pdf = 1.0f;
+    RGB ft = ldrgb(b.t) * (rgb1(1.0f) - rgb1(fr_dielectric(cos_theta(wi), b.eta_a, b.eta_b)));
+    ft = ft * ((eta_i * eta_i) / (eta_t * eta_t));
+    s.f = ft / abs_cos_theta(wi);
+    s.wi = wi;
+    return s;
 }
 
 // core/src/reflection/bsdf.rs — frame + the material's lobes.

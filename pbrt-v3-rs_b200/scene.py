@@ -140,7 +140,7 @@ class SceneDescription:
                            shutteropen=0.0, shutterclose=1.0)
         self.film = dict(xresolution=64, yresolution=64, filter="box", scale=1.0, maxsampleluminance=float("inf"))
         self.sampler = dict(type="halton", pixelsamples=16, samplepixelcenter=False, dimensions=4)
-        self.integrator = dict(maxdepth=5, rrthreshold=1.0, lightsamplestrategy="uniform", pixelbounds=None)
+        self.integrator = dict(name="path", maxdepth=5, rrthreshold=1.0, lightsamplestrategy="uniform", pixelbounds=None)
         self.accel_params = dict(splitmethod="sah", maxnodeprims=4)
         self.nodes = None
         self.ordered_prims = None
@@ -247,7 +247,7 @@ class SceneDescription:
 
     def to_desc(self):
         from . import Camera, Film, Integrator, Light, Material, Sampler, SceneDesc
-        from . import (LIGHT_AREA, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
+        from . import (INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
                        MAT_PLASTIC, SAMPLER_HALTON, SAMPLER_ZEROTWO)
         if self.nodes is None:
             self.build_accel(None)
@@ -393,6 +393,10 @@ class SceneDescription:
             raise ValueError("lightsamplestrategy %r: the spatial strategy is racy in the reference and outside this path "
                              "(SURVEY.md §2 row 24)" % strat)
         d.integrator.light_strategy = LIGHTS_POWER if strat == "power" else LIGHTS_UNIFORM
+        name = self.integrator.get("name", "path")
+        if name not in ("path", "whitted"):
+            raise ValueError("Integrator %r is outside this path (path, whitted)" % name)
+        d.integrator.type = INTEGRATOR_WHITTED if name == "whitted" else INTEGRATOR_PATH
         return d
 
 

@@ -193,8 +193,8 @@ def test_ply_variants_pfm_roundtrip_and_transform_stack(tmp_path, pkg):
         assert _arr(d.prim_flags, 2, np.uint32).tolist() == [8, 8]
         assert d.n_materials == 1 and d.film.xres == 1280 and d.sampler.spp == 16 and d.integrator.max_depth == 5
     # unsupported input fails loudly, with the directive named
-    (tmp_path / "u.pbrt").write_text('Integrator "whitted"\nWorldBegin\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n')
-    with pytest.raises(pkg.B200PTError, match="whitted"):
+    (tmp_path / "u.pbrt").write_text('Integrator "bdpt"\nWorldBegin\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n')
+    with pytest.raises(pkg.B200PTError, match="bdpt"):
         pkg.load_pbrt(str(tmp_path / "u.pbrt"))
     (tmp_path / "t.pbrt").write_text('WorldBegin\nTexture "x" "float" "constant"\nWorldEnd\n')
     with pytest.raises(pkg.B200PTError, match="Texture"):

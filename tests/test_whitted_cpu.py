@@ -1,0 +1,95 @@
+"""CPU tests of the oracle's WhittedIntegrator restatement (integrators/src/whitted.rs:60-126,
+core/src/integrator/sampler_integrator.rs:79-238): hand-checkable radiances and structural properties."""
+import numpy as np
+import pytest
+
+import scenes_small as ss
+
+
+def _floor_scene(kd=(0.5, 0.25, 0.125), light_pos=(0.0, 2.0, 0.0), intensity=(8.0, 8.0, 8.0), res=9):
+    """A big matte floor at y = 0 seen from straight above, one point light: every quantity has a closed form."""
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    sd = SceneDescription()
+    m = sd.add_material(type="matte", Kd=kd)
+    q = np.array([[-50, 0, -50], [50, 0, -50], [50, 0, 50], [-50, 0, 50]], dtype=np.float32)
+    sd.add_mesh(np.stack([np.concatenate([q[0], q[2], q[1]]), np.concatenate([q[0], q[3], q[2]])]), m)
+    sd.add_point_light(light_pos, intensity)
+    sd.camera.update(eye=(0.0, 5.0, 0.0), look=(0.0, 0.0, 0.0), up=(0, 0, 1), fov=20.0)
+    sd.film.update(xresolution=res, yresolution=res)
+    sd.sampler.update(type="halton", pixelsamples=1)
+    sd.integrator.update(name="whitted", maxdepth=5)
+    return sd
+
+
+def test_point_light_on_matte_floor_closed_form(pkg, oracle):
+    """L = (Kd / pi) * I / d^2 * cos(theta)  (whitted.rs:89-112 with LambertianReflection::f and PointLight::sample_li),
+    evaluated in float64 at the point where the oracle's own camera ray meets the floor."""
+    kd, I, h = np.array([0.5, 0.25, 0.125]), 8.0, 2.0
+    sd = _floor_scene(kd=tuple(kd), light_pos=(0.0, h, 0.0), intensity=(I, I, I))
+    sc = oracle.OracleScene(sd)
+    ps = np.array([(x, y, 0) for y in range(9) for x in range(9)], dtype=np.int32)
+    li = sc.li(ps, nthreads=1).astype(np.float64)
+    rays = sc.camera_rays(ps)
+    o, d = rays["o"].astype(np.float64), rays["d"].astype(np.float64)
+    t = -o[:, 1] / d[:, 1]
+    p = o + t[:, None] * d  # floor hit
+    to_light = np.array([0.0, h, 0.0]) - p
+    d2 = (to_light ** 2).sum(1)
+    cos = to_light[:, 1] / np.sqrt(d2)
+    expect = (kd[None, :] / np.pi) * (I / d2)[:, None] * cos[:, None]
+    assert np.allclose(li, expect, rtol=2e-5)
+    assert np.argmax(li[:, 0]) == 40  # brightest under the light (centre pixel)
+
+
+def test_shadowed_point_is_black_and_emitter_is_seen(pkg, oracle):
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    sd = _floor_scene()
+    # an occluder between the light (y = 2) and the floor: the floor under it is black (visibility.unoccluded == false)
+    m = sd.add_material(type="matte", Kd=(0.5, 0.5, 0.5))
+    q = np.array([[-30, 1, -30], [30, 1, -30], [30, 1, 30], [-30, 1, 30]], dtype=np.float32)
+    sd.add_mesh(np.stack([np.concatenate([q[0], q[2], q[1]]), np.concatenate([q[0], q[3], q[2]])]), m)
+    sd.camera.update(eye=(0.0, 0.5, 0.0), look=(0.0, 0.0, 0.0), up=(0, 0, 1), fov=20.0)
+    img = oracle.OracleScene(sd).render(nthreads=1)[0]
+    assert not img.any()
+    # an emitter seen directly contributes Le once (whitted.rs:87), also under Whitted
+    sd = SceneDescription()
+    m = sd.add_material(type="matte", Kd=(0, 0, 0))
+    q = np.array([[-5, -5, 2], [5, -5, 2], [5, 5, 2], [-5, 5, 2]], dtype=np.float32)
+    sd.add_mesh(np.stack([np.concatenate([q[0], q[2], q[1]]), np.concatenate([q[0], q[3], q[2]])]), m, area_light=dict(L=(3, 2, 1)))
+    sd.camera.update(eye=(0, 0, -1), look=(0, 0, 1), fov=30.0)
+    sd.film.update(xresolution=8, yresolution=8)
+    sd.sampler.update(pixelsamples=2)
+    sd.integrator.update(name="whitted")
+    img = oracle.OracleScene(sd).render()[0]
+    assert np.allclose(img, np.array([3, 2, 1], np.float32), rtol=1e-5)
+
+
+def test_glass_spawns_reflection_and_transmission_trees(pkg, oracle):
+    """Glass without multiple lobes = SpecularReflection + SpecularTransmission (glass.rs:112-120): with maxdepth 1 the
+    sphere shows direct light only (nothing for glass: its lobes are deltas, f = 0), with maxdepth 5 the trees add
+    the environment seen through / mirrored by the sphere."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    imgs, stats = {}, {}
+    for md in (1, 2, 5):
+        sd = ss.one_material_scene(wl, ss.MATERIALS["glass"], light="all", res=24, spp=2, maxdepth=md)
+        sd.integrator.update(name="whitted")
+        imgs[md], stats[md], _ = oracle.OracleScene(sd).render()
+        assert np.isfinite(imgs[md]).all() and (imgs[md] >= 0).all()
+    assert stats[1][1] == stats[1][0]  # maxdepth 1: camera rays only
+    assert stats[2][1] > stats[1][1] and stats[5][1] > stats[2][1]  # deeper trees trace more closest-hit rays
+    assert imgs[5].mean() > imgs[1].mean()
+    # a binary tree: at most 2^maxdepth - 1 closest-hit rays per camera sample
+    assert stats[5][1] <= stats[5][0] * (2 ** 5 - 1)
+
+
+@pytest.mark.parametrize("name", ["matte", "plastic", "metal", "rough_glass"])
+def test_non_specular_materials_are_direct_lighting_only(pkg, oracle, name):
+    """No delta lobes -> specular_reflect / specular_transmit return zero: one closest-hit ray per sample, and every
+    light of the scene is sampled at every hit (one shadow ray per light with a non-black contribution)."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS[name], light="all", res=16, spp=2, maxdepth=5)
+    sd.integrator.update(name="whitted")
+    img, stats, _ = oracle.OracleScene(sd).render()
+    assert stats[1] == stats[0]
+    assert stats[2] <= 4 * stats[0]  # infinite + point + two area-light triangles
+    assert np.isfinite(img).all() and img.mean() > 0

@@ -136,14 +136,19 @@ enum { B200PT_LIGHTS_UNIFORM = 0, B200PT_LIGHTS_POWER = 1 };
 /* B200PT_INTEGRATOR_PATH: PathIntegrator (integrators/src/path.rs:103-326).
  * B200PT_INTEGRATOR_WHITTED: WhittedIntegrator (integrators/src/whitted.rs:60-158 with specular_reflect /
  * specular_transmit of core/src/integrator/sampler_integrator.rs:79-238); reads max_depth and pixel_bounds only and
- * needs the halton sampler (the number of sampler dimensions a camera sample consumes is not bounded in advance). */
-enum { B200PT_INTEGRATOR_PATH = 0, B200PT_INTEGRATOR_WHITTED = 1 };
+ * needs the halton sampler (the number of sampler dimensions a camera sample consumes is not bounded in advance).
+ * B200PT_INTEGRATOR_DIRECT: DirectLightingIntegrator (integrators/src/direct_lighting.rs:82-146) with "strategy"
+ * all | one; as the reference's tile samplers come from clone_sampler(), which drops the requested sample arrays
+ * (samplers/src/halton.rs:176-182), "all" takes one MIS estimate_direct per light from plain get_2d() pairs. */
+enum { B200PT_INTEGRATOR_PATH = 0, B200PT_INTEGRATOR_WHITTED = 1, B200PT_INTEGRATOR_DIRECT = 2 };
+enum { B200PT_DIRECT_ALL = 0, B200PT_DIRECT_ONE = 1 };
 typedef struct b200pt_integrator {
     int32_t max_depth;         /* "maxdepth" (5) */
     float rr_threshold;        /* "rrthreshold" (1.0) */
     int32_t pixel_bounds[4];   /* x0,y0,x1,y1 (sample bounds ∩ "pixelbounds") */
     int32_t light_strategy;    /* "lightsamplestrategy": uniform | power */
     int32_t type;              /* B200PT_INTEGRATOR_* */
+    int32_t direct_strategy;   /* B200PT_DIRECT_* (directlighting "strategy") */
 } b200pt_integrator;
 
 /* ObjectBegin/ObjectEnd: the triangles [first_prim, first_prim + n_prims) of the scene's per-primitive arrays with their

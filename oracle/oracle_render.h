@@ -1073,8 +1073,61 @@ inline RGB whitted_li(RenderScene& sc, Ray ray, Sampler& sampler, int depth) {
     return l;
 }
 
+// integrators/src/direct_lighting.rs:82-146.  The tile samplers come from clone_sampler(), which does not carry the
+// sample arrays requested in preprocess() (samplers/src/halton.rs:176-182): get_2d_array() returns empty arrays and
+// uniform_sample_all_lights always takes its single-sample branch (integrator/common.rs:38-52).
+inline RGB direct_li(RenderScene& sc, Ray ray, Sampler& sampler, int depth) {
+    RGB l;
+    SurfHit isect;
+    if (!scene_intersect(sc, ray, &isect)) {
+        for (int li : sc.infinite_lights) l += infinite_le(sc, li, ray);
+        return l;
+    }
+    BSDF bsdf = make_bsdf(sc, isect, false);
+    const V3 n = isect.shading_n, wo = isect.wo;
+    int al = sc.prim_light.empty() ? -1 : sc.prim_light[isect.prim];
+    if (al >= 0) l += area_l(sc.lights[al], isect.n, wo);
+    if (!sc.lights.empty()) {
+        if (sc.integ.direct_strategy == B200PT_DIRECT_ALL) {  // uniform_sample_all_lights, common.rs:25-87
+            RGB sum;
+            for (size_t j = 0; j < sc.lights.size(); ++j) {
+                P2 u_light = sampler.get_2d();
+                P2 u_scatter = sampler.get_2d();
+                sum += estimate_direct(sc, isect, bsdf, u_scatter, (int)j, u_light);
+            }
+            l += sum;
+        } else {  // uniform_sample_one_light without a distribution, common.rs:89-133
+            Float n_lights = (Float)sc.lights.size();
+            Float u = sampler.get_1d();
+            size_t ln = (size_t)pmin(u * n_lights, n_lights - 1.0f);
+            Float light_pdf = 1.0f / n_lights;
+            P2 u_light = sampler.get_2d();
+            P2 u_scatter = sampler.get_2d();
+            l += estimate_direct(sc, isect, bsdf, u_scatter, (int)ln, u_light) / light_pdf;
+        }
+    }
+    if (depth + 1 < sc.integ.max_depth) {
+        RGB refl, trans;
+        {
+            P2 u = sampler.get_2d();
+            BxDFSample bs = bsdf.sample_f(wo, u, BSDF_REFLECTION | BSDF_SPECULAR);
+            if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(bs.wi, n) != 0.0f)
+                refl = bs.f * direct_li(sc, spawn_ray(isect, bs.wi), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
+        }
+        {
+            P2 u = sampler.get_2d();
+            BxDFSample bs = bsdf.sample_f(wo, u, BSDF_TRANSMISSION | BSDF_SPECULAR);
+            if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(bs.wi, n) != 0.0f)
+                trans = bs.f * direct_li(sc, spawn_ray(isect, bs.wi), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
+        }
+        l += refl + trans;
+    }
+    return l;
+}
+
 // Integrator::li of the scene's integrator
 inline RGB integrator_li(RenderScene& sc, Ray ray, Sampler& sampler) {
+    if (sc.integ.type == B200PT_INTEGRATOR_DIRECT) return direct_li(sc, ray, sampler, 0);
     return sc.integ.type == B200PT_INTEGRATOR_WHITTED ? whitted_li(sc, ray, sampler, 0) : path_li(sc, ray, sampler);
 }
 

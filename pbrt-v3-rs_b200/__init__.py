@@ -30,7 +30,8 @@ MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_METAL = 0, 1, 2, 3
 LIGHT_POINT, LIGHT_AREA, LIGHT_INFINITE = 0, 1, 2
 SAMPLER_HALTON, SAMPLER_ZEROTWO = 0, 1
 LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
-INTEGRATOR_PATH, INTEGRATOR_WHITTED = 0, 1
+INTEGRATOR_PATH, INTEGRATOR_WHITTED, INTEGRATOR_DIRECT = 0, 1, 2
+DIRECT_ALL, DIRECT_ONE = 0, 1
 
 # numpy views of the 32-byte ray, 16-byte hit and 32-byte node records
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmax", "<f4"), ("d", "<f4", 3), ("time", "<f4")])
@@ -71,7 +72,7 @@ class Sampler(C.Structure):
 
 class Integrator(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("pixel_bounds", C.c_int32 * 4),
-                ("light_strategy", C.c_int32), ("type", C.c_int32)]
+                ("light_strategy", C.c_int32), ("type", C.c_int32), ("direct_strategy", C.c_int32)]
 
 
 class Object(C.Structure):

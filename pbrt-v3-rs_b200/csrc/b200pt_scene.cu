@@ -89,6 +89,9 @@ struct Wave {
     // max_depth entries per path) and the per-shadow-ray contribution of the light loop (rgb, valid)
     float4* wstack;
     float4* sh_c;
+    // DirectLighting integrator only: per-slot MIS record (f rgb, weight) and (scattering pdf, light index)
+    float4* dp_b;
+    float2* dp_c;
 };
 static const int kBins = 5;
 
@@ -352,6 +355,92 @@ B2_D LightSample sample_light(const DeviceScene& S, const DLight& light, const S
     return r;
 }
 
+// estimate_direct (core/src/integrator/common.rs:146-299) up to the two rays it traces: the light-sampling half gives
+// ld_light (added if the shadow ray is unoccluded), the BSDF-sampling half (non-delta lights) gives f, the MIS weight and
+// the pdf of a closest-hit ray whose hit decides whether the light is seen (resolved later, k_resolve).
+struct DirectEst {
+    RGB ld_light, mis_f;
+    float mis_w, mis_pdf;
+    bool shadow, mis;
+    V3 sh_o, sh_d, mis_o, mis_d;
+};
+B2_D DirectEst estimate_direct_rays(const DeviceScene& S, const DLight& light, const SurfHit& sh, V3 hit_wo, const BSDF& bsdf, P2 u_light, P2 u_scatter) {
+    const uint32_t kNoSpec = BSDF_ALL & ~BSDF_SPECULAR;
+    // ---- estimate_direct (common.rs:146-299), light-sampling half ----
+    DirectEst r;
+    r.shadow = false; r.mis = false;
+    r.sh_o = r.sh_d = r.mis_o = r.mis_d = mk(0.0f, 0.0f, 0.0f);
+    RGB ld_light = rgb1(0.0f);
+    const LightSample ls = sample_light(S, light, sh, u_light);
+    const bool li_valid = ls.valid;
+    const V3 wi = ls.wi, lp1 = ls.p1, lp1_err = ls.p1_err, lp1_n = ls.p1_n;
+    const float light_pdf = ls.pdf;
+    const RGB Li = ls.Li;
+    const V3 q0 = ls.q0, q1 = ls.q1, q2 = ls.q2;
+    const uint32_t lflags = ls.lflags;
+    float scattering_pdf = 0.0f;
+    if (li_valid && light_pdf > 0.0f && !is_black(Li)) {
+        RGB f = bsdf_f(bsdf, hit_wo, wi, kNoSpec) * abs_dot(wi, sh.ns);
+        scattering_pdf = bsdf_pdf(bsdf, hit_wo, wi, kNoSpec);
+        if (!is_black(f)) {
+            // VisibilityTester -> Hit::spawn_ray_to_hit (interaction/mod.rs:212-223)
+            V3 origin = offset_ray_origin(sh.p, sh.p_error, sh.n, lp1 - sh.p);
+            V3 target = offset_ray_origin(lp1, lp1_err, lp1_n, origin - lp1);
+            r.shadow = true; r.sh_o = origin; r.sh_d = target - origin;
+            if (light.type == LT_POINT) ld_light = f * Li / light_pdf;
+            else {
+                float wgt = power_heuristic(light_pdf, scattering_pdf);
+                ld_light = f * Li * wgt / light_pdf;
+            }
+        }
+    }
+    // ---- BSDF-sampling half (non-delta lights only) ----
+    RGB mis_f = rgb1(0.0f);
+    float mis_w = 1.0f, mis_pdf = 0.0f;
+    if (light.type != LT_POINT) {
+        BxDFSample bs = bsdf_sample_f(bsdf, hit_wo, u_scatter, kNoSpec);
+        V3 wi2 = bs.wi;
+        RGB f = bs.f * abs_dot(wi2, sh.ns);
+        bool sampled_specular = (bs.type & BSDF_SPECULAR) != 0;
+        if (!is_black(f) && bs.pdf > 0.0f) {
+            float weight = 1.0f;
+            bool ok = true;
+            V3 ro = offset_ray_origin(sh.p, sh.p_error, sh.n, wi2);  // Hit::spawn_ray
+            if (!sampled_specular) {
+                float lp;
+                if (light.type == LT_AREA) {  // Shape::pdf_solid_angle, shape.rs:81-107
+                    TriCtx tc = make_tri_ctx(wi2.x, wi2.y, wi2.z);
+                    float t, c0, c1, c2;
+                    lp = 0.0f;
+                    const float4 lduv = (S.prim_duv && (lflags & B200PT_PRIM_HAS_UV)) ? ldg4(S.prim_duv + light.prim) : default_duv();
+                    if (triangle_test(ro, tc, __int_as_float(0x7f800000), q0, q1, q2, &t, &c0, &c1, &c2) && triangle_nondegenerate(q0, q1, q2, lduv)) {
+                        SurfHit lh = triangle_surface(q0, q1, q2, c0, c1, c2, lflags, lduv, nullptr, nullptr);
+                        lp = distance_squared(sh.p, lh.p) / (abs_dot(lh.n, -wi2) * light.area);
+                        if (isinf(lp)) lp = 0.0f;
+                    }
+                } else {  // infinite.rs:201-211
+                    V3 w = xf3(light.w2l, wi2);
+                    float theta = spherical_theta(w), phi = spherical_phi(w);
+                    float sin_t = lmx::sinf_glibc(theta);
+                    if (sin_t == 0.0f) lp = 0.0f;
+                    else {
+                        const DInfDistr& D = S.inf_distr[light.inf_slot];
+                        lp = distr2d_pdf(D, phi * kInvTwoPi, theta * kInvPi) / (kTwoPi * kPi * sin_t);
+                    }
+                }
+                if (lp == 0.0f) ok = false;  // common.rs:258-260: return ld
+                else weight = power_heuristic(bs.pdf, lp);
+            }
+            if (ok) {
+                r.mis = true; r.mis_o = ro; r.mis_d = wi2;
+                mis_f = f; mis_w = weight; mis_pdf = bs.pdf;
+            }
+        }
+    }
+    r.ld_light = ld_light; r.mis_f = mis_f; r.mis_w = mis_w; r.mis_pdf = mis_pdf;
+    return r;
+}
+
 // ---- K4: shade --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, int n_active) {
     int i_sorted = blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,76 +502,18 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
             P2 u_light = smp_2d(S, hidx, dim);
             P2 u_scatter = smp_2d(S, hidx, dim);
             const DLight& light = S.lights[ln];
-            // ---- estimate_direct (common.rs:146-299), light-sampling half ----
-            RGB ld_light = rgb1(0.0f);
+            // ---- estimate_direct (common.rs:146-299): both halves, rays still to be traced ----
+            const DirectEst de = estimate_direct_rays(S, light, sh, hit_wo, bsdf, u_light, u_scatter);
+            const RGB ld_light = de.ld_light, mis_f = de.mis_f;
+            const float mis_w = de.mis_w, mis_pdf = de.mis_pdf;
             int shadow_slot = -1, mis_slot = -1;
-            const LightSample ls = sample_light(S, light, sh, u_light);
-            const bool li_valid = ls.valid;
-            const V3 wi = ls.wi, lp1 = ls.p1, lp1_err = ls.p1_err, lp1_n = ls.p1_n;
-            const float light_pdf = ls.pdf;
-            const RGB Li = ls.Li;
-            const V3 q0 = ls.q0, q1 = ls.q1, q2 = ls.q2;
-            const uint32_t lflags = ls.lflags;
-            float scattering_pdf = 0.0f;
-            if (li_valid && light_pdf > 0.0f && !is_black(Li)) {
-                RGB f = bsdf_f(bsdf, hit_wo, wi, kNoSpec) * abs_dot(wi, sh.ns);
-                scattering_pdf = bsdf_pdf(bsdf, hit_wo, wi, kNoSpec);
-                if (!is_black(f)) {
-                    // VisibilityTester -> Hit::spawn_ray_to_hit (interaction/mod.rs:212-223)
-                    V3 origin = offset_ray_origin(sh.p, sh.p_error, sh.n, lp1 - sh.p);
-                    V3 target = offset_ray_origin(lp1, lp1_err, lp1_n, origin - lp1);
-                    shadow_slot = atomicAdd(&W.counters[1], 1);
-                    store_ray(W.sh_ray, shadow_slot, origin, target - origin, 1.0f - kShadowEps, time);
-                    if (light.type == LT_POINT) ld_light = f * Li / light_pdf;
-                    else {
-                        float wgt = power_heuristic(light_pdf, scattering_pdf);
-                        ld_light = f * Li * wgt / light_pdf;
-                    }
-                }
+            if (de.shadow) {
+                shadow_slot = atomicAdd(&W.counters[1], 1);
+                store_ray(W.sh_ray, shadow_slot, de.sh_o, de.sh_d, 1.0f - kShadowEps, time);
             }
-            // ---- BSDF-sampling half (non-delta lights only) ----
-            RGB mis_f = rgb1(0.0f);
-            float mis_w = 1.0f, mis_pdf = 0.0f;
-            if (light.type != LT_POINT) {
-                BxDFSample bs = bsdf_sample_f(bsdf, hit_wo, u_scatter, kNoSpec);
-                V3 wi2 = bs.wi;
-                RGB f = bs.f * abs_dot(wi2, sh.ns);
-                bool sampled_specular = (bs.type & BSDF_SPECULAR) != 0;
-                if (!is_black(f) && bs.pdf > 0.0f) {
-                    float weight = 1.0f;
-                    bool ok = true;
-                    V3 ro = offset_ray_origin(sh.p, sh.p_error, sh.n, wi2);  // Hit::spawn_ray
-                    if (!sampled_specular) {
-                        float lp;
-                        if (light.type == LT_AREA) {  // Shape::pdf_solid_angle, shape.rs:81-107
-                            TriCtx tc = make_tri_ctx(wi2.x, wi2.y, wi2.z);
-                            float t, c0, c1, c2;
-                            lp = 0.0f;
-                            const float4 lduv = (S.prim_duv && (lflags & B200PT_PRIM_HAS_UV)) ? ldg4(S.prim_duv + light.prim) : default_duv();
-                            if (triangle_test(ro, tc, __int_as_float(0x7f800000), q0, q1, q2, &t, &c0, &c1, &c2) && triangle_nondegenerate(q0, q1, q2, lduv)) {
-                                SurfHit lh = triangle_surface(q0, q1, q2, c0, c1, c2, lflags, lduv, nullptr, nullptr);
-                                lp = distance_squared(sh.p, lh.p) / (abs_dot(lh.n, -wi2) * light.area);
-                                if (isinf(lp)) lp = 0.0f;
-                            }
-                        } else {  // infinite.rs:201-211
-                            V3 w = xf3(light.w2l, wi2);
-                            float theta = spherical_theta(w), phi = spherical_phi(w);
-                            float sin_t = lmx::sinf_glibc(theta);
-                            if (sin_t == 0.0f) lp = 0.0f;
-                            else {
-                                const DInfDistr& D = S.inf_distr[light.inf_slot];
-                                lp = distr2d_pdf(D, phi * kInvTwoPi, theta * kInvPi) / (kTwoPi * kPi * sin_t);
-                            }
-                        }
-                        if (lp == 0.0f) ok = false;  // common.rs:258-260: return ld
-                        else weight = power_heuristic(bs.pdf, lp);
-                    }
-                    if (ok) {
-                        mis_slot = atomicAdd(&W.counters[2], 1);
-                        store_ray(W.mis_ray, mis_slot, ro, wi2, __int_as_float(0x7f800000), time);
-                        mis_f = f; mis_w = weight; mis_pdf = bs.pdf;
-                    }
-                }
+            if (de.mis) {
+                mis_slot = atomicAdd(&W.counters[2], 1);
+                store_ray(W.mis_ray, mis_slot, de.mis_o, de.mis_d, __int_as_float(0x7f800000), time);
             }
             if (shadow_slot >= 0 || mis_slot >= 0) {
                 int k = atomicAdd(&W.counters[3], 1);
@@ -529,25 +560,42 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
     W.qpid[cur ^ 1][ns] = pid;
 }
 
-// ---- K4w: WhittedIntegrator::li (integrators/src/whitted.rs:60-126) as a wavefront stage ---------------------------
-// The reference recurses: reflect subtree, then transmit subtree, drawing sampler dimensions in that depth-first order.
+// ---- K4w: WhittedIntegrator::li (integrators/src/whitted.rs:60-126) and DirectLightingIntegrator::li
+// (integrators/src/direct_lighting.rs:82-146) as a wavefront stage ---------------------------------------------------
+// Both recurse: reflect subtree, then transmit subtree, drawing sampler dimensions in that depth-first order.
 // Here every path walks its own tree depth-first, one node per wave iteration: the specular-transmission child of a
 // node is computed at the node (delta lobes ignore the sample value) and parked on the path's stack while the
 // reflection subtree runs; popping it consumes the two dimensions specular_transmit's get_2d() would have drawn at that
-// point, so every later light sample sees the reference's dimension.  A node's own radiance
-// l = Le + sum over ALL lights of f * Li * |wi . ns| / pdf (unoccluded) is formed in the reference's order by
-// k_resolve_whitted and enters the pixel as L += beta * l with beta the product of f * |wi . ns| / pdf down the tree
-// (the reference multiplies on the way back up: same value up to f32 rounding, identical for depth-0 nodes).
-// Shadow rays of pending record k live at slots [k * n_lights, (k + 1) * n_lights), one per light, invalid ones with
-// t_max = -1.
+// point, so every later light sample sees the reference's dimension.  A node's own radiance l = Le + direct light is
+// formed in the reference's order by k_resolve_tree and enters the pixel as L += beta * l with beta the product of
+// f * |wi . ns| / pdf down the tree (the reference multiplies on the way back up: same value up to f32 rounding,
+// identical for depth-0 nodes).
+//
+// Direct light per node, kMode:
+//   kTreeWhitted    every light once: f * Li * |wi . ns| / pdf if unoccluded (whitted.rs:89-112)
+//   kTreeDirectAll  uniform_sample_all_lights (integrator/common.rs:25-87).  The tile samplers are made by
+//                   clone_sampler(), which drops the sample arrays the integrator requested in preprocess()
+//                   (halton.rs:176-182), so get_2d_array() is always empty and every light takes the single-sample
+//                   branch: u_light = get_2d(), u_scattering = get_2d(), one estimate_direct with MIS
+//   kTreeDirectOne  uniform_sample_one_light with no distribution: light = min(u * n, n - 1), estimate / (1 / n)
+// Pending record k owns the slots [k * stride, (k + 1) * stride) of the shadow and MIS queues (stride = number of
+// lights, or 1 for kTreeDirectOne); unused slots carry t_max = -1 rays.
+enum { kTreeWhitted = 0, kTreeDirectAll = 1, kTreeDirectOne = 2 };
+
 B2_D void wstack_store(const Wave& W, int max_depth, int pid, int sp, V3 o, V3 d, float time, RGB beta, int depth, bool valid) {
     float4* e = W.wstack + ((long long)pid * max_depth + sp) * 3;
     e[0] = make_float4(o.x, o.y, o.z, time);
     e[1] = make_float4(d.x, d.y, d.z, __int_as_float(valid ? depth : -1));
     e[2] = make_float4(beta.r, beta.g, beta.b, 0.0f);
 }
+B2_D void tree_slot_clear(const Wave& W, long long sl, bool with_mis) {
+    W.sh_c[sl] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    store_ray(W.sh_ray, (int)sl, mk(0, 0, 0), mk(0, 0, 1), -1.0f, 0.0f);
+    if (with_mis) store_ray(W.mis_ray, (int)sl, mk(0, 0, 0), mk(0, 0, 1), -1.0f, 0.0f);
+}
 
-__global__ void __launch_bounds__(128) k_shade_whitted(DeviceScene S, Wave W, int cur, int n_active) {
+template <int kMode>
+__global__ void __launch_bounds__(128) k_shade_tree(DeviceScene S, Wave W, int cur, int n_active) {
     int i_sorted = blockIdx.x * blockDim.x + threadIdx.x;
     if (i_sorted >= n_active) return;
     const int slot = W.sorted[i_sorted];
@@ -566,13 +614,14 @@ __global__ void __launch_bounds__(128) k_shade_whitted(DeviceScene S, Wave W, in
     const unsigned long long hidx = W.hidx[pid];
     const uint32_t prim = __float_as_uint(hit.y);
     const bool found = prim != 0xffffffffu;
+    const int stride = kMode == kTreeDirectOne ? 1 : S.n_lights;
 
     bool have_next = false;
     V3 next_o = mk(0, 0, 0), next_d = next_o;
     RGB next_beta = beta;
     int next_depth = 0;
 
-    if (!found) {  // whitted.rs:117-121
+    if (!found) {  // whitted.rs:117-121, direct_lighting.rs:138-143
         RGB l = rgb1(0.0f);
         for (int i = 0; i < S.n_infinite; ++i) {
             const DLight& il = S.lights[S.infinite_lights[i]];
@@ -580,7 +629,8 @@ __global__ void __launch_bounds__(128) k_shade_whitted(DeviceScene S, Wave W, in
         }
         L = L + beta * l;
     } else {
-        if (dim + 2 * S.n_lights + 4 > 1000) {  // HaltonSampler can only sample 1000 dimensions (halton.rs:106-110 asserts)
+        const int dims_here = kMode == kTreeWhitted ? 2 * S.n_lights : (kMode == kTreeDirectAll ? 4 * S.n_lights : 5);
+        if (dim + dims_here + 4 > 1000) {  // HaltonSampler can only sample 1000 dimensions (halton.rs:106-110 asserts)
             atomicExch(&W.counters[4], 1);
             return;
         }
@@ -592,42 +642,68 @@ __global__ void __launch_bounds__(128) k_shade_whitted(DeviceScene S, Wave W, in
         bsdf.ns = sh.ns; bsdf.ng = sh.n;
         bsdf.ss = normalize(sh.dpdu);
         bsdf.ts = cross(bsdf.ns, bsdf.ss);
-        bsdf.m = S.materials + hc.mat;  // built with allow_multiple_lobes = false (whitted.rs:76)
+        bsdf.m = S.materials + hc.mat;  // built with allow_multiple_lobes = false (whitted.rs:76, direct_lighting.rs:91)
         RGB le = rgb1(0.0f);
-        if (hc.alight >= 0) le = area_l(S.lights[hc.alight], sh.n, wo);  // isect.le(&wo), whitted.rs:87
-        // whitted.rs:89-112: one sample of every light
-        int rec = -1;
-        for (int li = 0; li < S.n_lights; ++li) {
-            P2 u = smp_2d(S, hidx, dim);
-            const DLight& light = S.lights[li];
-            const LightSample ls = sample_light(S, light, sh, u);
-            bool want = false;
-            RGB c = rgb1(0.0f);
-            if (ls.valid && !is_black(ls.Li) && ls.pdf != 0.0f) {
-                RGB f = bsdf_f(bsdf, wo, ls.wi, BSDF_ALL);
-                if (!is_black(f)) { want = true; c = f * ls.Li * abs_dot(ls.wi, sh.ns) / ls.pdf; }
+        if (hc.alight >= 0) le = area_l(S.lights[hc.alight], sh.n, wo);  // isect.le(&wo)
+        int rec = -1, n_real_sh = 0, n_real_mis = 0;
+        const int n_est = kMode == kTreeDirectOne ? (S.n_lights > 0 ? 1 : 0) : S.n_lights;
+        for (int e = 0; e < n_est; ++e) {
+            int li = e;
+            if (kMode == kTreeDirectOne) {  // common.rs:111-116
+                float u = smp_1d(S, hidx, dim);
+                float fn = (float)S.n_lights;
+                li = (int)pmin(u * fn, fn - 1.0f);
             }
+            const DLight& light = S.lights[li];
+            bool want_sh = false, want_mis = false;
+            RGB c = rgb1(0.0f);
+            DirectEst de;
+            if (kMode == kTreeWhitted) {
+                P2 u = smp_2d(S, hidx, dim);
+                const LightSample ls = sample_light(S, light, sh, u);
+                de.shadow = false; de.mis = false;
+                if (ls.valid && !is_black(ls.Li) && ls.pdf != 0.0f) {
+                    RGB f = bsdf_f(bsdf, wo, ls.wi, BSDF_ALL);
+                    if (!is_black(f)) {
+                        want_sh = true;
+                        c = f * ls.Li * abs_dot(ls.wi, sh.ns) / ls.pdf;
+                        de.sh_o = offset_ray_origin(sh.p, sh.p_error, sh.n, ls.p1 - sh.p);  // Hit::spawn_ray_to_hit
+                        V3 target = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, de.sh_o - ls.p1);
+                        de.sh_d = target - de.sh_o;
+                    }
+                }
+            } else {
+                P2 u_light = smp_2d(S, hidx, dim);
+                P2 u_scatter = smp_2d(S, hidx, dim);
+                de = estimate_direct_rays(S, light, sh, wo, bsdf, u_light, u_scatter);
+                want_sh = de.shadow; want_mis = de.mis;
+                c = de.ld_light;
+            }
+            const bool want = want_sh || want_mis;
+            n_real_sh += want_sh ? 1 : 0;
+            n_real_mis += want_mis ? 1 : 0;
             if (want && rec < 0) {
                 rec = atomicAdd(&W.counters[3], 1);
-                for (int j = 0; j < li; ++j) {
-                    const long long sl = (long long)rec * S.n_lights + j;
-                    W.sh_c[sl] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    store_ray(W.sh_ray, (int)sl, mk(0, 0, 0), mk(0, 0, 1), -1.0f, 0.0f);
-                }
+                for (int j = 0; j < e; ++j) tree_slot_clear(W, (long long)rec * stride + j, kMode != kTreeWhitted);
             }
             if (rec >= 0) {
-                const long long sl = (long long)rec * S.n_lights + li;
-                if (want) {
-                    V3 origin = offset_ray_origin(sh.p, sh.p_error, sh.n, ls.p1 - sh.p);  // Hit::spawn_ray_to_hit
-                    V3 target = offset_ray_origin(ls.p1, ls.p1_err, ls.p1_n, origin - ls.p1);
-                    store_ray(W.sh_ray, (int)sl, origin, target - origin, 1.0f - kShadowEps, time);
-                    W.sh_c[sl] = make_float4(c.r, c.g, c.b, 1.0f);
-                } else {
-                    W.sh_c[sl] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    store_ray(W.sh_ray, (int)sl, mk(0, 0, 0), mk(0, 0, 1), -1.0f, 0.0f);
+                const long long sl = (long long)rec * stride + e;
+                if (!want) tree_slot_clear(W, sl, kMode != kTreeWhitted);
+                else {
+                    if (want_sh) store_ray(W.sh_ray, (int)sl, de.sh_o, de.sh_d, 1.0f - kShadowEps, time);
+                    else store_ray(W.sh_ray, (int)sl, mk(0, 0, 0), mk(0, 0, 1), -1.0f, 0.0f);
+                    W.sh_c[sl] = make_float4(c.r, c.g, c.b, __int_as_float((want_sh ? 1 : 0) | (want_mis ? 2 : 0)));
+                    if (kMode != kTreeWhitted) {
+                        if (want_mis) store_ray(W.mis_ray, (int)sl, de.mis_o, de.mis_d, __int_as_float(0x7f800000), time);
+                        else store_ray(W.mis_ray, (int)sl, mk(0, 0, 0), mk(0, 0, 1), -1.0f, 0.0f);
+                        W.dp_b[sl] = make_float4(de.mis_f.r, de.mis_f.g, de.mis_f.b, de.mis_w);
+                        W.dp_c[sl] = make_float2(de.mis_pdf, __int_as_float(li));
+                    }
                 }
             }
         }
+        if (n_real_sh) atomicAdd(&W.counters[5], n_real_sh);  // rays the reference traces too (the placeholder slots are not counted)
+        if (n_real_mis) atomicAdd(&W.counters[6], n_real_mis);
         if (rec >= 0) {
             W.pend_q[rec] = pid;
             W.pend_a[pid] = make_float4(le.r, le.g, le.b, 0.0f);
@@ -635,7 +711,7 @@ __global__ void __launch_bounds__(128) k_shade_whitted(DeviceScene S, Wave W, in
         } else {
             L = L + beta * le;
         }
-        // whitted.rs:113-116 -> specular_reflect / specular_transmit (sampler_integrator.rs:79-238)
+        // specular_reflect / specular_transmit (sampler_integrator.rs:79-238)
         if (depth + 1 < S.max_depth) {
             const V3 wo_l = bsdf_to_local(bsdf, wo);
             bool r_ok = false, t_ok = false;
@@ -695,18 +771,54 @@ __global__ void __launch_bounds__(128) k_shade_whitted(DeviceScene S, Wave W, in
     W.qpid[cur ^ 1][ns] = pid;
 }
 
-// l = Le + sum of the unoccluded light contributions in light order; L += beta * l  (whitted.rs:87-112)
-__global__ void __launch_bounds__(256) k_resolve_whitted(DeviceScene S, Wave W, int n_pend) {
+// l = Le + the node's direct light in the reference's order; L += beta * l
+template <int kMode>
+__global__ void __launch_bounds__(256) k_resolve_tree(DeviceScene S, Wave W, int n_pend) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pend) return;
     const int pid = W.pend_q[i];
     const float4 a = W.pend_a[pid], b = W.pend_c[pid];
     RGB l = rgb(a.x, a.y, a.z);
-    for (int li = 0; li < S.n_lights; ++li) {
-        const long long sl = (long long)i * S.n_lights + li;
+    const int stride = kMode == kTreeDirectOne ? 1 : S.n_lights;
+    RGB direct = rgb1(0.0f);  // uniform_sample_all_lights accumulates its own sum (common.rs:33-86)
+    for (int e = 0; e < stride; ++e) {
+        const long long sl = (long long)i * stride + e;
         const float4 c = W.sh_c[sl];
-        if (c.w != 0.0f && !W.sh_occ[sl]) l = l + rgb(c.x, c.y, c.z);
+        const int flags = __float_as_int(c.w);
+        if (kMode == kTreeWhitted) {
+            if ((flags & 1) && !W.sh_occ[sl]) l = l + rgb(c.x, c.y, c.z);  // whitted.rs:104-109
+            continue;
+        }
+        if (flags == 0) { if (kMode == kTreeDirectAll) direct = direct + rgb1(0.0f); continue; }
+        RGB ld = rgb1(0.0f);
+        if ((flags & 1) && !W.sh_occ[sl]) ld = ld + rgb(c.x, c.y, c.z);  // common.rs:205-225
+        if (flags & 2) {                                                  // common.rs:266-296
+            const float4 mf = W.dp_b[sl];
+            const float2 mp = W.dp_c[sl];
+            const int li = __float_as_int(mp.y);
+            const DLight& light = S.lights[li];
+            const float4 mh = W.mis_hit[sl];
+            const float4 md = W.mis_ray[2 * sl + 1];
+            const V3 wi = mk(md.x, md.y, md.z);
+            const uint32_t prim = __float_as_uint(mh.y);
+            RGB Li = rgb1(0.0f);
+            if (prim != 0xffffffffu) {
+                V3 p0, p1, p2; int mat, al; uint32_t fl;
+                load_prim(S, prim, &p0, &p1, &p2, &mat, &al, &fl);
+                if (al == li) {
+                    V3 n = normalize(cross(p0 - p2, p1 - p2));
+                    if (fl & 1u) n = -n;
+                    Li = area_l(light, n, -wi);
+                }
+            } else if (light.type == LT_INFINITE) {
+                Li = infinite_le(light, S.inf_distr[light.inf_slot], wi);
+            }
+            if (!is_black(Li)) ld = ld + rgb(mf.x, mf.y, mf.z) * Li * rgb1(1.0f) * mf.w / mp.x;
+        }
+        if (kMode == kTreeDirectAll) direct = direct + ld;
+        else direct = ld / (1.0f / (float)S.n_lights);  // common.rs:115, 133: estimate / light_pdf
     }
+    if (kMode != kTreeWhitted) l = l + direct;
     float4 Lw = W.L[pid];
     RGB L = rgb(Lw.x, Lw.y, Lw.z) + rgb(b.x, b.y, b.z) * l;
     W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
@@ -874,7 +986,8 @@ struct SceneImpl {
     AccelImpl accel;
     Accel2Impl accel2;        // two-level scenes (instancing)
     bool instanced = false;
-    bool whitted = false;     // WhittedIntegrator instead of PathIntegrator
+    bool whitted = false;     // a recursive SamplerIntegrator (Whitted / DirectLighting) instead of PathIntegrator
+    int tree_mode = 0;        // kTreeWhitted / kTreeDirectAll / kTreeDirectOne
     DeviceScene dev;
     b200pt_film film;
     b200pt_sampler sampler;
@@ -903,7 +1016,7 @@ struct SceneImpl {
 static const int kWaveCap = 1 << 22;
 // Whitted tests one shadow ray per light and node: keep paths x lights within 2^24 shadow slots
 static int wave_cap_for(const SceneImpl* s) {
-    if (!s->whitted) return kWaveCap;
+    if (!s->whitted || s->tree_mode == kTreeDirectOne) return kWaveCap;
     long long c = (1ll << 24) / std::max(1, s->dev.n_lights);
     return (int)std::min<long long>(kWaveCap, std::max<long long>(c, 1024));
 }
@@ -1060,16 +1173,21 @@ static int wave_alloc(SceneImpl* s, int cap) {
     if ((rc = dev_alloc(s, (size_t)cap, &W.hit))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.hit_b2))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.hit_inst))) return rc;
-    const size_t sh_cap = s->whitted ? (size_t)cap * (size_t)std::max(1, s->dev.n_lights) : (size_t)cap;
+    const size_t sh_cap = (s->whitted && s->tree_mode != kTreeDirectOne) ? (size_t)cap * (size_t)std::max(1, s->dev.n_lights) : (size_t)cap;
+    const size_t mis_cap = (s->whitted && s->tree_mode != kTreeWhitted) ? sh_cap : (size_t)cap;
     if ((rc = dev_alloc(s, sh_cap * 2, &W.sh_ray))) return rc;
     if ((rc = dev_alloc(s, sh_cap, &W.sh_occ))) return rc;
-    W.wstack = nullptr; W.sh_c = nullptr;
+    W.wstack = nullptr; W.sh_c = nullptr; W.dp_b = nullptr; W.dp_c = nullptr;
     if (s->whitted) {
         if ((rc = dev_alloc(s, sh_cap, &W.sh_c))) return rc;
         if ((rc = dev_alloc(s, (size_t)cap * (size_t)std::max(1, s->dev.max_depth) * 3, &W.wstack))) return rc;
+        if (s->tree_mode != kTreeWhitted) {
+            if ((rc = dev_alloc(s, sh_cap, &W.dp_b))) return rc;
+            if ((rc = dev_alloc(s, sh_cap, &W.dp_c))) return rc;
+        }
     }
-    if ((rc = dev_alloc(s, (size_t)cap * 2, &W.mis_ray))) return rc;
-    if ((rc = dev_alloc(s, (size_t)cap, &W.mis_hit))) return rc;
+    if ((rc = dev_alloc(s, mis_cap * 2, &W.mis_ray))) return rc;
+    if ((rc = dev_alloc(s, mis_cap, &W.mis_hit))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.L))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.beta))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.hidx))) return rc;
@@ -1140,21 +1258,33 @@ static int run_wave_whitted(SceneImpl* s, int n, cudaStream_t st) {
         B2_CUDA(cudaMemsetAsync(W.counters, 0, 32 * sizeof(int), st));
         k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, n_active);
         k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, n_active);
-        k_shade_whitted<<<(n_active + 127) / 128, 128, 0, st>>>(s->dev, W, cur, n_active);
+        const int gs = (n_active + 127) / 128;
+        if (s->tree_mode == kTreeWhitted) k_shade_tree<kTreeWhitted><<<gs, 128, 0, st>>>(s->dev, W, cur, n_active);
+        else if (s->tree_mode == kTreeDirectAll) k_shade_tree<kTreeDirectAll><<<gs, 128, 0, st>>>(s->dev, W, cur, n_active);
+        else k_shade_tree<kTreeDirectOne><<<gs, 128, 0, st>>>(s->dev, W, cur, n_active);
         g_launches.fetch_add(3);
-        int cnt[5];
+        int cnt[7];
         B2_CUDA(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         B2_CUDA(cudaStreamSynchronize(st));
         if (cnt[4]) {
-            b200pt_set_error("whitted: a camera sample needs more than 1000 sampler dimensions (lights x tree nodes); the reference's HaltonSampler asserts here (samplers/src/halton.rs:106-110)");
+            b200pt_set_error("whitted / directlighting: a camera sample needs more than 1000 sampler dimensions (lights x tree nodes); the reference's HaltonSampler asserts here (samplers/src/halton.rs:106-110)");
             return B200PT_ERR_UNSUPPORTED;
         }
         if (cnt[3] > 0) {
-            const int64_t n_sh = (int64_t)cnt[3] * nl;
+            const int64_t n_sh = (int64_t)cnt[3] * (s->tree_mode == kTreeDirectOne ? 1 : nl);
             rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, n_sh, W.sh_occ, st) : launch_occluded(s->dev.accel, W.sh_ray, n_sh, W.sh_occ, st, 0);
             if (rc) return rc;
-            s->rays[2] += (uint64_t)n_sh;
-            k_resolve_whitted<<<(cnt[3] + 255) / 256, 256, 0, st>>>(s->dev, W, cnt[3]);
+            s->rays[2] += (uint64_t)cnt[5];
+            if (s->tree_mode != kTreeWhitted) {  // the BSDF-sampled MIS rays of estimate_direct
+                rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, n_sh, W.mis_hit, st, nullptr, nullptr)
+                                  : launch_intersect(s->dev.accel, W.mis_ray, n_sh, W.mis_hit, st, 0, nullptr);
+                if (rc) return rc;
+                s->rays[1] += (uint64_t)cnt[6];
+            }
+            const int gr = (cnt[3] + 255) / 256;
+            if (s->tree_mode == kTreeWhitted) k_resolve_tree<kTreeWhitted><<<gr, 256, 0, st>>>(s->dev, W, cnt[3]);
+            else if (s->tree_mode == kTreeDirectAll) k_resolve_tree<kTreeDirectAll><<<gr, 256, 0, st>>>(s->dev, W, cnt[3]);
+            else k_resolve_tree<kTreeDirectOne><<<gr, 256, 0, st>>>(s->dev, W, cnt[3]);
             g_launches.fetch_add(1);
         }
         cur ^= 1;
@@ -1189,15 +1319,19 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         b200pt_set_error("b200pt_scene_create: unknown sampler type (halton and 02sequence are on this path)");
         return B200PT_ERR_UNSUPPORTED;
     }
-    if (d->integrator.type != B200PT_INTEGRATOR_PATH && d->integrator.type != B200PT_INTEGRATOR_WHITTED) {
-        b200pt_set_error("b200pt_scene_create: unknown integrator type (path and whitted are on this path)");
+    if (d->integrator.type != B200PT_INTEGRATOR_PATH && d->integrator.type != B200PT_INTEGRATOR_WHITTED && d->integrator.type != B200PT_INTEGRATOR_DIRECT) {
+        b200pt_set_error("b200pt_scene_create: unknown integrator type (path, whitted and directlighting are on this path)");
         return B200PT_ERR_UNSUPPORTED;
     }
-    if (d->integrator.type == B200PT_INTEGRATOR_WHITTED) {
+    if (d->integrator.type == B200PT_INTEGRATOR_DIRECT && d->integrator.direct_strategy != B200PT_DIRECT_ALL && d->integrator.direct_strategy != B200PT_DIRECT_ONE) {
+        b200pt_set_error("b200pt_scene_create: unknown directlighting strategy");
+        return B200PT_ERR_INVALID;
+    }
+    if (d->integrator.type != B200PT_INTEGRATOR_PATH) {
         // The number of get_2d() calls of one camera sample depends on the tree it spawns; the (0,2) sampler would fall
         // back to the tile RNG (see below).  Halton is a pure function of (pixel, sample, dimension).
-        if (d->sampler.type != B200PT_SAMPLER_HALTON) { b200pt_set_error("b200pt_scene_create: the whitted integrator needs the halton sampler on this path"); return B200PT_ERR_UNSUPPORTED; }
-        if (d->integrator.max_depth < 0 || d->integrator.max_depth > 24) { b200pt_set_error("b200pt_scene_create: whitted maxdepth must be in [0, 24]"); return B200PT_ERR_UNSUPPORTED; }
+        if (d->sampler.type != B200PT_SAMPLER_HALTON) { b200pt_set_error("b200pt_scene_create: the whitted / directlighting integrators need the halton sampler on this path"); return B200PT_ERR_UNSUPPORTED; }
+        if (d->integrator.max_depth < 0 || d->integrator.max_depth > 24) { b200pt_set_error("b200pt_scene_create: whitted / directlighting maxdepth must be in [0, 24]"); return B200PT_ERR_UNSUPPORTED; }
         if ((long long)d->n_lights * 1024 > (1ll << 24)) { b200pt_set_error("b200pt_scene_create: whitted: more than 16384 lights"); return B200PT_ERR_UNSUPPORTED; }
     }
     if (d->sampler.type == B200PT_SAMPLER_ZEROTWO) {
@@ -1284,7 +1418,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     }
 
     std::vector<DMaterial> mats;
-    for (int i = 0; i < d->n_materials; ++i) mats.push_back(make_material(d->materials[i], d->integrator.type != B200PT_INTEGRATOR_WHITTED));
+    for (int i = 0; i < d->n_materials; ++i) mats.push_back(make_material(d->materials[i], d->integrator.type == B200PT_INTEGRATOR_PATH));
     if ((rc = dev_upload(s, mats, &D.materials))) return fail(rc);
 
     // Scene::new (core/src/scene.rs:50-77): world bound, infinite lights, Light::preprocess
@@ -1367,7 +1501,8 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     std::memcpy(D.sb, s->sample_bounds, 16);
     std::memcpy(D.pb, d->integrator.pixel_bounds, 16);
     D.max_depth = d->integrator.max_depth;
-    s->whitted = d->integrator.type == B200PT_INTEGRATOR_WHITTED;
+    s->whitted = d->integrator.type != B200PT_INTEGRATOR_PATH;
+    s->tree_mode = d->integrator.type == B200PT_INTEGRATOR_WHITTED ? kTreeWhitted : (d->integrator.direct_strategy == B200PT_DIRECT_ONE ? kTreeDirectOne : kTreeDirectAll);
     D.rr_threshold = d->integrator.rr_threshold;
 
     // HaltonSampler::new over the sample bounds (samplers/src/halton.rs:61-100, 262-275)

@@ -678,11 +678,14 @@ void Builder::finish() {
     } else throw Unsupported("Sampler \"" + sampler_name + "\" is outside this path (halton, 02sequence)");
 
     // --- Integrator (path.rs:287-326) ---
-    if (integrator_name != "path" && integrator_name != "whitted") throw Unsupported("Integrator \"" + integrator_name + "\" is outside this path (path, whitted)");
-    d.integrator.type = integrator_name == "whitted" ? B200PT_INTEGRATOR_WHITTED : B200PT_INTEGRATOR_PATH;  // whitted.rs:133-158 reads maxdepth and pixelbounds only
+    if (integrator_name != "path" && integrator_name != "whitted" && integrator_name != "directlighting")
+        throw Unsupported("Integrator \"" + integrator_name + "\" is outside this path (path, whitted, directlighting)");
+    // whitted.rs:133-158 reads maxdepth and pixelbounds only; direct_lighting.rs:155-196 also "strategy" (unknown -> all)
+    d.integrator.type = integrator_name == "whitted" ? B200PT_INTEGRATOR_WHITTED : integrator_name == "directlighting" ? B200PT_INTEGRATOR_DIRECT : B200PT_INTEGRATOR_PATH;
+    d.integrator.direct_strategy = integrator_p.one_string("strategy", "all") == "one" ? B200PT_DIRECT_ONE : B200PT_DIRECT_ALL;
     d.integrator.max_depth = integrator_p.one_int("maxdepth", 5);
     d.integrator.rr_threshold = integrator_p.one_float("rrthreshold", 1.0f);
-    std::string strat = integrator_p.one_string("lightsamplestrategy", integrator_name == "whitted" ? "uniform" : "spatial");
+    std::string strat = integrator_p.one_string("lightsamplestrategy", integrator_name != "path" ? "uniform" : "spatial");
     if (strat == "uniform") d.integrator.light_strategy = B200PT_LIGHTS_UNIFORM;
     else if (strat == "power") d.integrator.light_strategy = B200PT_LIGHTS_POWER;
     else throw Unsupported("lightsamplestrategy \"" + strat + "\": the spatial strategy is racy in the reference and outside this path; use \"uniform\" or \"power\"");

@@ -247,7 +247,7 @@ class SceneDescription:
 
     def to_desc(self):
         from . import Camera, Film, Integrator, Light, Material, Sampler, SceneDesc
-        from . import (INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
+        from . import (DIRECT_ALL, DIRECT_ONE, INTEGRATOR_DIRECT, INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
                        MAT_PLASTIC, SAMPLER_HALTON, SAMPLER_ZEROTWO)
         if self.nodes is None:
             self.build_accel(None)
@@ -394,9 +394,10 @@ class SceneDescription:
                              "(SURVEY.md §2 row 24)" % strat)
         d.integrator.light_strategy = LIGHTS_POWER if strat == "power" else LIGHTS_UNIFORM
         name = self.integrator.get("name", "path")
-        if name not in ("path", "whitted"):
-            raise ValueError("Integrator %r is outside this path (path, whitted)" % name)
-        d.integrator.type = INTEGRATOR_WHITTED if name == "whitted" else INTEGRATOR_PATH
+        if name not in ("path", "whitted", "directlighting"):
+            raise ValueError("Integrator %r is outside this path (path, whitted, directlighting)" % name)
+        d.integrator.type = {"path": INTEGRATOR_PATH, "whitted": INTEGRATOR_WHITTED, "directlighting": INTEGRATOR_DIRECT}[name]
+        d.integrator.direct_strategy = DIRECT_ONE if self.integrator.get("strategy", "all") == "one" else DIRECT_ALL  # direct_lighting.rs:161-169
         return d
 
 

@@ -93,3 +93,49 @@ def test_non_specular_materials_are_direct_lighting_only(pkg, oracle, name):
     assert stats[1] == stats[0]
     assert stats[2] <= 4 * stats[0]  # infinite + point + two area-light triangles
     assert np.isfinite(img).all() and img.mean() > 0
+
+
+# ---- DirectLightingIntegrator (integrators/src/direct_lighting.rs:82-146) --------------------------------------------
+
+@pytest.mark.parametrize("strategy", ["all", "one"])
+def test_directlighting_point_light_closed_form(pkg, oracle, strategy):
+    """One delta light: estimate_direct = f * |cos| * Li / 1 for both strategies (uniform pick of one light has pdf 1)."""
+    kd, I, h = np.array([0.5, 0.25, 0.125]), 8.0, 2.0
+    sd = _floor_scene(kd=tuple(kd), light_pos=(0.0, h, 0.0), intensity=(I, I, I))
+    sd.integrator.update(name="directlighting", strategy=strategy)
+    sc = oracle.OracleScene(sd)
+    ps = np.array([(x, y, 0) for y in range(9) for x in range(9)], dtype=np.int32)
+    li = sc.li(ps, nthreads=1).astype(np.float64)
+    rays = sc.camera_rays(ps)
+    o, d = rays["o"].astype(np.float64), rays["d"].astype(np.float64)
+    p = o + (-o[:, 1] / d[:, 1])[:, None] * d
+    to_light = np.array([0.0, h, 0.0]) - p
+    d2 = (to_light ** 2).sum(1)
+    expect = (kd[None, :] / np.pi) * (I / d2)[:, None] * (to_light[:, 1] / np.sqrt(d2))[:, None]
+    assert np.allclose(li, expect, rtol=2e-5)
+
+
+def test_directlighting_all_equals_whitted_for_delta_lights_and_one_converges_to_all(pkg, oracle):
+    """With only point lights the MIS half of estimate_direct is skipped, so "all" is Whitted's light loop with two
+    get_2d() per light instead of one (the values are unused by point lights): identical images.  "one" picks a light
+    uniformly and divides by 1/n: same expectation."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    def scene(name, **kw):
+        sd = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="point", res=20, spp=64, maxdepth=3)
+        sd.add_point_light((-2.0, 2.5, -2.0), (10, 12, 14))
+        sd.integrator.update(name=name, **kw)
+        return oracle.OracleScene(sd).render()[0]
+    w, a, o = scene("whitted"), scene("directlighting", strategy="all"), scene("directlighting", strategy="one")
+    assert np.allclose(a, w, rtol=1e-5, atol=1e-7)
+    assert abs(o.mean() - a.mean()) <= 0.03 * a.mean()
+
+
+def test_directlighting_area_light_all_vs_path_depth1(pkg, oracle):
+    """maxdepth-1 path tracing of a matte scene = emission + one uniform_sample_one_light; "one" direct lighting draws
+    the same estimator (uniform light pick) -> equal expectation."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["matte"], light="area", res=16, spp=128, maxdepth=1, strategy="uniform")
+    p = oracle.OracleScene(sd).render()[0]
+    sd.integrator.update(name="directlighting", strategy="one")
+    d = oracle.OracleScene(sd).render()[0]
+    assert abs(p.mean() - d.mean()) <= 0.03 * p.mean()

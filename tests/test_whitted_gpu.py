@@ -53,8 +53,7 @@ def test_whitted_image_rel_rmse_and_ray_counts(gpu, oracle, name, light, filt, m
     rc = integ.ray_counts()
     assert rc[0] == stats[0]
     assert abs(int(rc[1]) - int(stats[1])) <= 0.002 * stats[1]  # closest-hit rays: the whole specular trees
-    # shadow rays: the device also traces the (immediately missing) placeholder slots of lights without a contribution
-    assert int(rc[2]) >= int(stats[2])
+    assert abs(int(rc[2]) - int(stats[2])) <= 0.002 * max(int(stats[2]), 1)  # shadow rays (placeholder slots are not counted)
 
 
 def _many_lights_scene(wl, n_strips, maxdepth):
@@ -137,5 +136,71 @@ WorldEnd
     assert ls.to_desc().integrator.type == gpu.INTEGRATOR_WHITTED
     integ = gpu.PathIntegrator(ls)
     img = integ.render()
+    ref = oracle.OracleScene(ls).render()[0]
+    assert img.mean() > 0 and ss.rel_rmse(img, ref) <= TOL
+
+
+# ---- DirectLightingIntegrator (integrators/src/direct_lighting.rs:82-146) --------------------------------------------
+
+def _direct(wl, name, light, strategy, **kw):
+    sd = ss.one_material_scene(wl, ss.MATERIALS[name], light=light, **kw)
+    sd.integrator.update(name="directlighting", strategy=strategy)
+    return sd
+
+
+@pytest.mark.parametrize("strategy", ["all", "one"])
+@pytest.mark.parametrize("name", ["matte", "plastic", "glass", "rough_glass", "metal"])
+@pytest.mark.parametrize("light", ["infinite", "point", "area", "all"])
+def test_directlighting_li_per_sample_matches_oracle(gpu, oracle, name, light, strategy):
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = _direct(wl, name, light, strategy, res=16, spp=4, maxdepth=5)
+    integ = gpu.PathIntegrator(sd)
+    ps = _pairs(16, 4)
+    li, rays = integ.li(ps)
+    osc = oracle.OracleScene(sd)
+    oli = osc.li(ps)
+    assert rays.tobytes() == osc.camera_rays(ps).tobytes()
+    assert np.isfinite(li).all()
+    close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
+    # the MIS half samples directions with sin / cos: an ulp there can flip which triangle the MIS ray hits
+    assert close.mean() >= 0.97, "only %.4f of the samples agree" % close.mean()
+    assert abs(li.mean() - oli.mean()) <= 0.02 * max(oli.mean(), 1e-3)
+
+
+@pytest.mark.parametrize("name,light,strategy,filt,maxdepth", [("glass", "all", "all", "box", 5), ("plastic", "all", "one", "box", 5),
+                                                                 ("matte", "area", "all", "gaussian", 3), ("metal", "infinite", "one", "box", 5)])
+def test_directlighting_image_rel_rmse_and_ray_counts(gpu, oracle, name, light, strategy, filt, maxdepth):
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = _direct(wl, name, light, strategy, res=48, spp=8, maxdepth=maxdepth, nu=60, nv=30, filt=filt)
+    integ = gpu.PathIntegrator(sd)
+    img = integ.render()
+    ref, stats, _ = oracle.OracleScene(sd).render()
+    r = ss.rel_rmse(img, ref)
+    assert r <= TOL, "relative RMSE %.3e > %.0e" % (r, TOL)
+    rc = integ.ray_counts()
+    assert rc[0] == stats[0]
+    assert abs(int(rc[1]) - int(stats[1])) <= 0.005 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0.005 * max(int(stats[2]), 1)
+
+
+def test_directlighting_scene_file(gpu, oracle, tmp_path):
+    scene = tmp_path / "d.pbrt"
+    scene.write_text('''
+LookAt 0 2 -5  0 0 0  0 1 0
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [32] "integer yresolution" [32] "string filename" ["d.pfm"]
+Sampler "halton" "integer pixelsamples" [4]
+Integrator "directlighting" "integer maxdepth" [3] "string strategy" ["one"]
+WorldBegin
+LightSource "point" "rgb I" [40 40 40] "point from" [2 4 -3]
+LightSource "infinite" "rgb L" [0.5 0.5 0.6]
+Material "matte" "rgb Kd" [0.5 0.4 0.3]
+Shape "trianglemesh" "integer indices" [0 2 1 0 3 2] "point P" [-6 0 -6  6 0 -6  6 0 6  -6 0 6]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-1 0 0  1 0 0  1 1.5 0  -1 1.5 0]
+WorldEnd
+''')
+    ls = gpu.load_pbrt(str(scene))
+    d = ls.to_desc()
+    assert d.integrator.type == gpu.INTEGRATOR_DIRECT and d.integrator.direct_strategy == gpu.DIRECT_ONE
+    img = gpu.PathIntegrator(ls).render()
     ref = oracle.OracleScene(ls).render()[0]
     assert img.mean() > 0 and ss.rel_rmse(img, ref) <= TOL

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--small", action="store_true", help="reduced geometry (CPU-sized smoke run of this tool)")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--integrator", default="path", choices=["path", "whitted", "directlighting"])
+    ap.add_argument("--strategy", default="all", choices=["all", "one"], help="directlighting strategy")
     a = ap.parse_args()
 
     import __graft_entry__ as ge
@@ -50,13 +52,14 @@ def main():
     t0 = time.time()
     sd = {"c1": wl.scene_c1, "c3": wl.scene_c3, "c4": wl.scene_c4, "c5": wl.scene_c5}[a.config](**kw)
     t_gen = time.time() - t0
+    sd.integrator.update(name=a.integrator, strategy=a.strategy)
     t0 = time.time()
     integ = pkg.PathIntegrator(sd)
     integ.preprocess()
     t_pre = time.time() - t0
     n_tris = int(sd.tri_verts.shape[0]) + sum(int(o["tri_verts"].shape[0]) for o in sd.objects)
     n_inst_tris = int(sd.tri_verts.shape[0]) + sum(int(sd.objects[o]["tri_verts"].shape[0]) for o, _, _ in sd.instances)
-    out = {"config": a.config, "stored_triangles": n_tris, "instanced_triangles": n_inst_tris, "spp": sd.sampler["pixelsamples"], "scene_gen_s": t_gen, "preprocess_s": t_pre}
+    out = {"config": a.config, "integrator": a.integrator + ("/" + a.strategy if a.integrator == "directlighting" else ""), "stored_triangles": n_tris, "instanced_triangles": n_inst_tris, "spp": sd.sampler["pixelsamples"], "scene_gen_s": t_gen, "preprocess_s": t_pre}
     print("%d stored / %d instanced triangles" % (n_tris, n_inst_tris))
     print("scene generated in %.1f s, preprocess (SAH builds + upload) %.1f s" % (t_gen, t_pre), flush=True)
 

@@ -132,7 +132,11 @@ typedef struct b200pt_sampler {
     int32_t dimensions;        /* 02sequence "dimensions" */
 } b200pt_sampler;
 
-enum { B200PT_LIGHTS_UNIFORM = 0, B200PT_LIGHTS_POWER = 1 };
+/* B200PT_LIGHTS_SPATIAL: SpatialLightDistribution (core/src/light_distrib/spatial.rs), the path integrator's default
+ * "lightsamplestrategy".  Deterministic here: every lookup gets the voxel's distribution, whereas the reference's
+ * lock-free table returns None (-> uniform light sampling) to threads that look a voxel up while another thread is
+ * still computing it, i.e. this is the reference's single-thread result. */
+enum { B200PT_LIGHTS_UNIFORM = 0, B200PT_LIGHTS_POWER = 1, B200PT_LIGHTS_SPATIAL = 2 };
 /* B200PT_INTEGRATOR_PATH: PathIntegrator (integrators/src/path.rs:103-326).
  * B200PT_INTEGRATOR_WHITTED: WhittedIntegrator (integrators/src/whitted.rs:60-158 with specular_reflect /
  * specular_transmit of core/src/integrator/sampler_integrator.rs:79-238); reads max_depth and pixel_bounds only and

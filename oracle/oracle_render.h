@@ -5,6 +5,8 @@
 // each function.  Scene interchange structs come from include/b200pt.h (the
 // C ABI both the oracle and the CUDA path consume).
 #pragma once
+#include <mutex>
+#include <unordered_map>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -525,6 +527,14 @@ struct RenderScene {
     V3 world_center;
     Float world_radius = 1.0f;
     Distribution1D light_distr;
+    // SpatialLightDistribution (light_distrib/spatial.rs), deterministic: a voxel's distribution is a pure function of
+    // the voxel, so it is computed on first use under a lock and every lookup gets it (the reference's lock-free table
+    // hands out None -> uniform sampling to threads that look a voxel up while another thread is still computing it).
+    bool spatial = false;
+    int n_voxels[3] = {1, 1, 1};
+    std::mutex spatial_mu;
+    std::unordered_map<uint64_t, Distribution1D*> spatial_cache;
+    ~RenderScene() { for (auto& kv : spatial_cache) delete kv.second; }
     // per infinite light (indexed by light id): 2x2 distribution of the constant map
     std::vector<Distribution2D> inf_distr;
     std::vector<MipMap> inf_map;           // per light (built for infinite lights only)
@@ -645,6 +655,16 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
     // PathIntegrator::preprocess (path.rs:81) -> create_light_sample_distribution
     // (light_distrib/mod.rs:59-70): a single light forces the uniform strategy.
     int strat = s->lights.size() == 1 ? B200PT_LIGHTS_UNIFORM : s->integ.light_strategy;
+    if (strat == B200PT_LIGHTS_SPATIAL && s->integ.type == B200PT_INTEGRATOR_PATH) {  // SpatialLightDistribution::new(scene, 64), spatial.rs:57-88
+        s->spatial = true;
+        V3 diag = bdiagonal(s->world_bound);
+        Float bmax = diag[maximum_extent(s->world_bound)];
+        for (int i = 0; i < 3; ++i) {
+            Float r = std::round(diag[i] / bmax * 64.0f);  // f32::round: half away from zero
+            long long v = (!(r == r) || r <= 0.0f) ? 0 : (long long)r;
+            s->n_voxels[i] = (int)pmax<long long>(1, v);
+        }
+    }
     if (!s->lights.empty()) {
         std::vector<Float> f;
         for (size_t i = 0; i < s->lights.size(); ++i) f.push_back(strat == B200PT_LIGHTS_UNIFORM ? 1.0f : lum_y(light_power(*s, (int)i)));
@@ -971,13 +991,60 @@ inline RGB estimate_direct(RenderScene& sc, const SurfHit& hit, const BSDF& bsdf
     return ld;
 }
 
+// SpatialLightDistribution::compute_distribution, spatial.rs:91-160
+inline Distribution1D* spatial_compute(RenderScene& sc, const int pi[3]) {
+    const Bounds3& wb = sc.world_bound;
+    V3 p0((Float)pi[0] / (Float)sc.n_voxels[0], (Float)pi[1] / (Float)sc.n_voxels[1], (Float)pi[2] / (Float)sc.n_voxels[2]);
+    V3 p1((Float)(pi[0] + 1) / (Float)sc.n_voxels[0], (Float)(pi[1] + 1) / (Float)sc.n_voxels[1], (Float)(pi[2] + 1) / (Float)sc.n_voxels[2]);
+    auto blerp = [](const Bounds3& b, V3 t) { return V3(lerpf(t.x, b.pmin.x, b.pmax.x), lerpf(t.y, b.pmin.y, b.pmax.y), lerpf(t.z, b.pmin.z, b.pmax.z)); };
+    Bounds3 vb(blerp(wb, p0), blerp(wb, p1));  // Bounds3::new orders the corners; they already are
+    const int kSamples = 128;
+    size_t n_lights = sc.lights.size();
+    std::vector<Float> contrib(n_lights, 0.0f);
+    for (int i = 0; i < kSamples; ++i) {
+        V3 po = blerp(vb, V3(radical_inverse(0, (uint64_t)i), radical_inverse(1, (uint64_t)i), radical_inverse(2, (uint64_t)i)));
+        SurfHit intr;
+        intr.p = po;
+        intr.wo = V3(1.0f, 0.0f, 0.0f);
+        P2 u(radical_inverse(3, (uint64_t)i), radical_inverse(4, (uint64_t)i));
+        for (size_t j = 0; j < n_lights; ++j) {
+            LiSample ls = light_sample_li(sc, (int)j, intr, u);
+            if (ls.valid && ls.pdf > 0.0f) contrib[j] += lum_y(ls.value) / ls.pdf;
+        }
+    }
+    Float sum = 0.0f;
+    for (Float c : contrib) sum += c;
+    Float avg = sum / (Float)(kSamples * n_lights);
+    Float min_contrib = avg > 0.0f ? 0.001f * avg : 1.0f;
+    for (Float& c : contrib) c = pmax(c, min_contrib);
+    return new Distribution1D(contrib);
+}
+// LightDistribution::lookup (spatial.rs:163-244 for the spatial strategy; uniform.rs / power.rs return their one distribution)
+inline const Distribution1D& light_distr_lookup(RenderScene& sc, V3 p) {
+    if (!sc.spatial) return sc.light_distr;
+    V3 off = boffset(sc.world_bound, p);
+    int pi[3];
+    for (int i = 0; i < 3; ++i) {
+        Float v = off[i] * (Float)sc.n_voxels[i];
+        int q = !(v == v) ? 0 : (v >= 2147483648.0f ? 0x7fffffff : (v <= -2147483648.0f ? (int)0x80000000 : (int)v));  // `as Int` saturates
+        pi[i] = pclamp(q, 0, sc.n_voxels[i] - 1);
+    }
+    uint64_t key = ((uint64_t)pi[0] << 40) | ((uint64_t)pi[1] << 20) | (uint64_t)pi[2];
+    std::lock_guard<std::mutex> g(sc.spatial_mu);
+    auto it = sc.spatial_cache.find(key);
+    if (it != sc.spatial_cache.end()) return *it->second;
+    Distribution1D* d = spatial_compute(sc, pi);
+    sc.spatial_cache[key] = d;
+    return *d;
+}
+
 // common.rs:89-133
 inline RGB uniform_sample_one_light(RenderScene& sc, const SurfHit& hit, const BSDF& bsdf, Sampler& sampler) {
     size_t n_lights = sc.lights.size();
     if (n_lights == 0) return RGB();
     Float sample = sampler.get_1d();
     Float light_pdf;
-    size_t ln = sc.light_distr.sample_discrete(sample, &light_pdf);
+    size_t ln = light_distr_lookup(sc, hit.p).sample_discrete(sample, &light_pdf);  // path.rs:156-157
     if (light_pdf == 0.0f) return RGB();
     P2 u_light = sampler.get_2d();
     P2 u_scatter = sampler.get_2d();

@@ -29,7 +29,7 @@ PRIM_REVERSE_ORIENTATION, PRIM_HAS_UV, PRIM_HAS_NORMALS, PRIM_HAS_TANGENTS = 8, 
 MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_METAL = 0, 1, 2, 3
 LIGHT_POINT, LIGHT_AREA, LIGHT_INFINITE = 0, 1, 2
 SAMPLER_HALTON, SAMPLER_ZEROTWO = 0, 1
-LIGHTS_UNIFORM, LIGHTS_POWER = 0, 1
+LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 INTEGRATOR_PATH, INTEGRATOR_WHITTED, INTEGRATOR_DIRECT = 0, 1, 2
 DIRECT_ALL, DIRECT_ONE = 0, 1
 

@@ -46,6 +46,14 @@ struct DeviceScene {
     const float* light_cdf;
     float light_func_int;
     int n_lights, n_infinite;
+    // SpatialLightDistribution (light_distrib/spatial.rs): dense voxel table, filled on first use.  Row v holds
+    // func[n_lights], cdf[n_lights + 1], func_int; vox_state[v] = 0 untouched, 1 queued, 2 ready.
+    int spatial;
+    int n_voxels[3];
+    float wb[6];          // scene.world_bound
+    float* vox_table;
+    int* vox_state;
+    int* vox_work;        // voxels queued by the current shade launch
     DHalton halton;
     DZeroTwo zt;
     int sampler_type;  // B200PT_SAMPLER_*
@@ -81,7 +89,8 @@ struct Wave {
     float4* pend_c;     // beta rgb at the vertex, mis scattering pdf
     int4* pend_d;       // light index, shadow slot, mis slot, -
     int* pend_q;        // path ids with a pending record
-    int* counters;      // [0] next rays, [1] shadow rays, [2] mis rays, [3] pending records, [8..15] bin counts, [16..23] bin cursors
+    int* counters;      // [0] next rays, [1] shadow rays, [2] mis rays, [3] pending records, [4] sampler-dimension overflow, [5] [6] real shadow / MIS rays (tree
+                        // integrators), [8..15] bin counts, [16..23] bin cursors, [24] voxels queued, [25] slots parked (spatial light sampling)
     // sort-by-material: key per slot (0 = miss / dead, 1 + material type otherwise) and the slots grouped by key
     uint8_t* key;
     int* sorted;
@@ -92,6 +101,8 @@ struct Wave {
     // DirectLighting integrator only: per-slot MIS record (f rgb, weight) and (scattering pdf, light index)
     float4* dp_b;
     float2* dp_c;
+    // spatial light sampling: slots whose voxel was not ready in the first shade launch of a bounce
+    int* deferred;
 };
 static const int kBins = 5;
 
@@ -441,11 +452,81 @@ B2_D DirectEst estimate_direct_rays(const DeviceScene& S, const DLight& light, c
     return r;
 }
 
+// ---- SpatialLightDistribution (core/src/light_distrib/spatial.rs) -------------------------------------------------
+B2_D int ld_volatile_int(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+// lookup(), spatial.rs:166-180: voxel of a point (Bounds3::offset, `as Int` truncation, clamp)
+B2_D int spatial_voxel(const DeviceScene& S, V3 p) {
+    int pi[3];
+    const float pc[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float o = pc[i] - S.wb[i];
+        if (S.wb[3 + i] > S.wb[i]) o /= S.wb[3 + i] - S.wb[i];
+        float v = o * (float)S.n_voxels[i];
+        int q = !(v == v) ? 0 : (v >= 2147483648.0f ? 0x7fffffff : (v <= -2147483648.0f ? (int)0x80000000 : (int)v));
+        pi[i] = q < 0 ? 0 : (q > S.n_voxels[i] - 1 ? S.n_voxels[i] - 1 : q);
+    }
+    return (pi[0] * S.n_voxels[1] + pi[1]) * S.n_voxels[2] + pi[2];
+}
+B2_D float lerp_ref(float t, float a, float b) { return (1.0f - t) * a + t * b; }  // pbrt::lerp, common.rs
+
+// compute_distribution(), spatial.rs:91-137: one thread per (queued voxel, light) walks the 128 Halton points in order
+__global__ void __launch_bounds__(128) k_voxel_contrib(DeviceScene S, int n_work) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_work * S.n_lights) return;
+    const int w = (int)(t / S.n_lights), j = (int)(t % S.n_lights);
+    const int v = S.vox_work[w];
+    const int pz = v % S.n_voxels[2], py = (v / S.n_voxels[2]) % S.n_voxels[1], px = v / (S.n_voxels[2] * S.n_voxels[1]);
+    const int pi[3] = {px, py, pz};
+    float lo[3], hi[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float t0 = (float)pi[i] / (float)S.n_voxels[i], t1 = (float)(pi[i] + 1) / (float)S.n_voxels[i];
+        lo[i] = lerp_ref(t0, S.wb[i], S.wb[3 + i]);
+        hi[i] = lerp_ref(t1, S.wb[i], S.wb[3 + i]);
+    }
+    const DLight& light = S.lights[j];
+    float contrib = 0.0f;
+    for (int i = 0; i < 128; ++i) {
+        const unsigned long long a = (unsigned long long)i;
+        SurfHit sh;
+        sh.p = mk(lerp_ref(radical_inverse_base2(a), lo[0], hi[0]), lerp_ref(radical_inverse_specialized(3, a), lo[1], hi[1]),
+                  lerp_ref(radical_inverse_specialized(5, a), lo[2], hi[2]));
+        sh.p_error = mk(0, 0, 0); sh.n = mk(0, 0, 0); sh.ns = sh.n; sh.dpdu = sh.n;
+        const P2 u = mk2(radical_inverse_specialized(7, a), radical_inverse_specialized(11, a));
+        const LightSample ls = sample_light(S, light, sh, u);
+        if (ls.valid && ls.pdf > 0.0f) contrib += lum_y(ls.Li) / ls.pdf;
+    }
+    S.vox_table[(long long)v * (2 * S.n_lights + 2) + j] = contrib;
+}
+
+// spatial.rs:139-160 + Distribution1D::new (distribution_1d.rs:22-48): one thread per queued voxel, lights in order
+__global__ void __launch_bounds__(128) k_voxel_finish(DeviceScene S, int n_work) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_work) return;
+    const int v = S.vox_work[w], n = S.n_lights;
+    float* func = S.vox_table + (long long)v * (2 * n + 2);
+    float* cdf = func + n;
+    float sum = 0.0f;
+    for (int j = 0; j < n; ++j) sum += func[j];
+    const float avg = sum / (float)(128 * n);
+    const float min_contrib = avg > 0.0f ? 0.001f * avg : 1.0f;
+    for (int j = 0; j < n; ++j) func[j] = pmax(func[j], min_contrib);
+    cdf[0] = 0.0f;
+    for (int j = 1; j < n + 1; ++j) cdf[j] = cdf[j - 1] + func[j - 1] / (float)n;
+    const float func_int = cdf[n];
+    if (func_int == 0.0f) { for (int j = 1; j < n + 1; ++j) cdf[j] = (float)j / (float)n; }
+    else { for (int j = 1; j < n + 1; ++j) cdf[j] /= func_int; }
+    func[2 * n + 1] = func_int;
+    __threadfence();
+    S.vox_state[v] = 2;
+}
+
 // ---- K4: shade --------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, int n_active) {
+__global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, int n_active, const int* __restrict__ order) {
     int i_sorted = blockIdx.x * blockDim.x + threadIdx.x;
     if (i_sorted >= n_active) return;
-    const int slot = W.sorted[i_sorted];
+    const int slot = order[i_sorted];
     const int pid = W.qpid[cur][slot];
     const float4 r0 = W.ray[cur][2 * slot], r1 = W.ray[cur][2 * slot + 1];
     const float4 hit = W.hit[slot];
@@ -494,10 +575,26 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, i
 
     // path.rs:162-173 -> uniform_sample_one_light (integrator/common.rs:89-133)
     if (bsdf_num_components(bsdf, kNoSpec) > 0 && S.n_lights > 0) {
+        // path.rs:156-157: light_distribution.lookup(&isect.hit.p)
+        const float* lfunc = S.light_func;
+        const float* lcdf = S.light_cdf;
+        float lfunc_int = S.light_func_int;
+        if (S.spatial) {
+            const int v = spatial_voxel(S, sh.p);
+            if (ld_volatile_int(S.vox_state + v) != 2) {
+                // first touch of this voxel: queue it, park the slot; the host fills the queued voxels and re-runs this
+                // kernel on the parked slots (nothing of this path has been written yet)
+                if (atomicCAS(S.vox_state + v, 0, 1) == 0) S.vox_work[atomicAdd(&W.counters[24], 1)] = v;
+                W.deferred[atomicAdd(&W.counters[25], 1)] = slot;
+                return;
+            }
+            const float* row = S.vox_table + (long long)v * (2 * S.n_lights + 2);
+            lfunc = row; lcdf = row + S.n_lights; lfunc_int = row[2 * S.n_lights + 1];
+        }
         float u_pick = smp_1d(S, hidx, dim);
         // Distribution1D::sample_discrete, distribution_1d.rs:81-94
-        int ln = find_interval_cdf(S.light_cdf, S.n_lights + 1, u_pick);
-        float pick_pdf = S.light_func_int > 0.0f ? S.light_func[ln] / (S.light_func_int * (float)S.n_lights) : 0.0f;
+        int ln = find_interval_cdf(lcdf, S.n_lights + 1, u_pick);
+        float pick_pdf = lfunc_int > 0.0f ? lfunc[ln] / (lfunc_int * (float)S.n_lights) : 0.0f;
         if (pick_pdf != 0.0f) {
             P2 u_light = smp_2d(S, hidx, dim);
             P2 u_scatter = smp_2d(S, hidx, dim);
@@ -996,6 +1093,7 @@ struct SceneImpl {
     Wave wave;
     int wave_cap = 0;
     uint64_t rays[3] = {0, 0, 0};
+    uint64_t voxels_built = 0;  // SpatialLightDistribution voxels computed so far
     std::mutex mu;
     int sample_bounds[4];
     // per-sample store and film staging, grown on demand and kept across renders
@@ -1200,6 +1298,8 @@ static int wave_alloc(SceneImpl* s, int cap) {
     if ((rc = dev_alloc(s, (size_t)32, &W.counters))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.key))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.sorted))) return rc;
+    W.deferred = nullptr;
+    if (s->dev.spatial && (rc = dev_alloc(s, (size_t)cap, &W.deferred))) return rc;
     s->wave_cap = cap;
     return B200PT_OK;
 }
@@ -1218,11 +1318,25 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
         k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, n_active);
         k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, n_active);
         g_launches.fetch_add(2);
-        k_shade<<<(n_active + 127) / 128, 128, 0, st>>>(s->dev, W, cur, n_active);
+        k_shade<<<(n_active + 127) / 128, 128, 0, st>>>(s->dev, W, cur, n_active, W.sorted);
         g_launches.fetch_add(1);
-        int cnt[4];
+        int cnt[26];
         B2_CUDA(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         B2_CUDA(cudaStreamSynchronize(st));
+        if (s->dev.spatial && cnt[25] > 0) {
+            // SpatialLightDistribution: fill the voxels this bounce touched for the first time, then shade the parked slots
+            if (cnt[24] > 0) {
+                const long long items = (long long)cnt[24] * s->dev.n_lights;
+                k_voxel_contrib<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(s->dev, cnt[24]);
+                k_voxel_finish<<<(cnt[24] + 127) / 128, 128, 0, st>>>(s->dev, cnt[24]);
+                g_launches.fetch_add(2);
+                s->voxels_built += (uint64_t)cnt[24];
+            }
+            k_shade<<<(cnt[25] + 127) / 128, 128, 0, st>>>(s->dev, W, cur, cnt[25], W.deferred);
+            g_launches.fetch_add(1);
+            B2_CUDA(cudaMemcpyAsync(cnt, W.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            B2_CUDA(cudaStreamSynchronize(st));
+        }
         if (cnt[1] > 0) {
             rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, cnt[1], W.sh_occ, st) : launch_occluded(s->dev.accel, W.sh_ray, cnt[1], W.sh_occ, st, 0);
             if (rc) return rc;
@@ -1484,6 +1598,32 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     D.n_infinite = (int)inf_ids.size();
     // create_light_sample_distribution (light_distrib/mod.rs:59-70)
     int strat = d->n_lights == 1 ? B200PT_LIGHTS_UNIFORM : d->integrator.light_strategy;
+    if (strat != B200PT_LIGHTS_UNIFORM && strat != B200PT_LIGHTS_POWER && strat != B200PT_LIGHTS_SPATIAL) {
+        b200pt_set_error("b200pt_scene_create: unknown light sample strategy");
+        return fail(B200PT_ERR_INVALID);
+    }
+    D.spatial = 0;
+    if (strat == B200PT_LIGHTS_SPATIAL && d->integrator.type == B200PT_INTEGRATOR_PATH && d->n_nodes > 0) {
+        // SpatialLightDistribution::new(scene, 64), spatial.rs:57-88
+        const float* b = d->nodes[0].bounds;
+        std::memcpy(D.wb, b, 24);
+        float diag[3] = {b[3] - b[0], b[4] - b[1], b[5] - b[2]};
+        int me = (diag[0] > diag[1] && diag[0] > diag[2]) ? 0 : (diag[1] > diag[2] ? 1 : 2);
+        long long n_vox = 1;
+        for (int i = 0; i < 3; ++i) {
+            float r = std::round(diag[i] / diag[me] * 64.0f);
+            long long v = (!(r == r) || r <= 0.0f) ? 0 : (long long)r;
+            D.n_voxels[i] = (int)std::max<long long>(1, v);
+            n_vox *= D.n_voxels[i];
+        }
+        const long long row = 2ll * d->n_lights + 2;
+        if (n_vox * row * 4 > (8ll << 30)) { b200pt_set_error("b200pt_scene_create: spatial light distribution table would exceed 8 GB (voxels x lights)"); return fail(B200PT_ERR_UNSUPPORTED); }
+        if ((rc = dev_alloc(s, (size_t)(n_vox * row), &D.vox_table))) return fail(rc);
+        if ((rc = dev_alloc(s, (size_t)n_vox, &D.vox_state))) return fail(rc);
+        if ((rc = dev_alloc(s, (size_t)n_vox, &D.vox_work))) return fail(rc);
+        B2_CUDA(cudaMemset(D.vox_state, 0, (size_t)n_vox * sizeof(int)));
+        D.spatial = 1;
+    }
     HostDistr1D ld;
     std::vector<float> lf;
     for (int i = 0; i < d->n_lights; ++i) lf.push_back(strat == B200PT_LIGHTS_UNIFORM ? 1.0f : power_y[(size_t)i]);

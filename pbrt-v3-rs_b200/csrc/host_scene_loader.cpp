@@ -688,7 +688,7 @@ void Builder::finish() {
     std::string strat = integrator_p.one_string("lightsamplestrategy", integrator_name != "path" ? "uniform" : "spatial");
     if (strat == "uniform") d.integrator.light_strategy = B200PT_LIGHTS_UNIFORM;
     else if (strat == "power") d.integrator.light_strategy = B200PT_LIGHTS_POWER;
-    else throw Unsupported("lightsamplestrategy \"" + strat + "\": the spatial strategy is racy in the reference and outside this path; use \"uniform\" or \"power\"");
+    else d.integrator.light_strategy = B200PT_LIGHTS_SPATIAL;  // "spatial", and any unknown name (path.rs:314-324 warns and uses spatial)
     int sb[4] = {(int)std::floor((float)d.film.crop[0] + 0.5f - rx), (int)std::floor((float)d.film.crop[1] + 0.5f - ry),
                  (int)std::ceil((float)d.film.crop[2] - 0.5f + rx), (int)std::ceil((float)d.film.crop[3] - 0.5f + ry)};
     if (const Param* pb = integrator_p.find("pixelbounds", "integer")) {

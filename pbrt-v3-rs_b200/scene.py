@@ -247,7 +247,7 @@ class SceneDescription:
 
     def to_desc(self):
         from . import Camera, Film, Integrator, Light, Material, Sampler, SceneDesc
-        from . import (DIRECT_ALL, DIRECT_ONE, INTEGRATOR_DIRECT, INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
+        from . import (DIRECT_ALL, DIRECT_ONE, INTEGRATOR_DIRECT, INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_SPATIAL, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
                        MAT_PLASTIC, SAMPLER_HALTON, SAMPLER_ZEROTWO)
         if self.nodes is None:
             self.build_accel(None)
@@ -389,10 +389,9 @@ class SceneDescription:
             sb = [max(sb[0], pb[0]), max(sb[1], pb[1]), min(sb[2], pb[2]), min(sb[3], pb[3])]
         d.integrator.pixel_bounds[:] = sb
         strat = self.integrator.get("lightsamplestrategy", "uniform")
-        if strat not in ("uniform", "power"):
-            raise ValueError("lightsamplestrategy %r: the spatial strategy is racy in the reference and outside this path "
-                             "(SURVEY.md §2 row 24)" % strat)
-        d.integrator.light_strategy = LIGHTS_POWER if strat == "power" else LIGHTS_UNIFORM
+        if strat not in ("uniform", "power", "spatial"):  # path.rs:314-324 falls back to spatial for unknown names
+            raise ValueError("lightsamplestrategy %r (uniform, power, spatial)" % strat)
+        d.integrator.light_strategy = {"uniform": LIGHTS_UNIFORM, "power": LIGHTS_POWER, "spatial": LIGHTS_SPATIAL}[strat]
         name = self.integrator.get("name", "path")
         if name not in ("path", "whitted", "directlighting"):
             raise ValueError("Integrator %r is outside this path (path, whitted, directlighting)" % name)

@@ -125,6 +125,7 @@ def lib():
     L.b200pt_bvh_build_sah_gpu.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_bvh_build_sah_device.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp, vp]
     L.b200pt_triangle_bounds_device.argtypes = [vp, i64, vp, vp]
+    L.b200pt_bvh_build_hlbvh_device.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp, vp]
     L.b200pt_accel_create.argtypes = [vp, i64, vp, vp, vp, i64, C.POINTER(vp)]
     L.b200pt_accel_create_uv.argtypes = [vp, i64, vp, vp, vp, vp, i64, C.POINTER(vp)]
     L.b200pt_accel_destroy.argtypes = [vp]

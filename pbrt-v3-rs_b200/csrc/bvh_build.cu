@@ -686,6 +686,167 @@ __global__ void k_ordered(const Item* __restrict__ items, uint32_t n, uint32_t* 
     if (i < n) ordered[i] = __float_as_uint(items[i].b.z);
 }
 
+// ================================================================ SplitMethod::HLBVH on the GPU
+// hlbvh.rs:33-449 / morton.rs:37-120 with the reference behaviours kept by host_hlbvh.cpp (float-bit-pattern Morton
+// codes, treelets emitted in order).  Stages: scene bounds (key atomics) -> Morton codes -> 5 stable 6-bit LSD radix
+// passes (the reference's own schedule: per-block digit histograms, one scan over digit-major counts, ranked scatter)
+// -> treelet starts (flag + scan) -> one thread per treelet emits its LBVH in pre-order into its slice of a scratch
+// array -> the <= 4096 treelet roots go to the host for the upper SAH layout (b200pt_hlbvh_upper_layout; tiny and
+// sequential) -> blocks and upper nodes are written to their final places.
+__global__ void __launch_bounds__(kBlock) k_hl_bounds(const float* __restrict__ pb, uint32_t n, uint32_t* acc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t key[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { key[k] = i < n ? fkey(pb[6 * (size_t)i + k]) : 0xffffffffu; key[3 + k] = i < n ? fkey(pb[6 * (size_t)i + 3 + k]) : 0u; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        uint32_t r = k < 3 ? __reduce_min_sync(kFull, key[k]) : __reduce_max_sync(kFull, key[k]);
+        if ((threadIdx.x & 31) == 0) { if (k < 3) atomicMin(&acc[k], r); else atomicMax(&acc[k], r); }
+    }
+}
+__device__ inline uint32_t spread3(uint32_t x) {  // left_shift_3 (morton.rs:102-120), debug_assert compiled out
+    if (x == (1u << 10)) x -= 1;
+    x = (x | (x << 16)) & 0x030000FFu;
+    x = (x | (x << 8)) & 0x0300F00Fu;
+    x = (x | (x << 4)) & 0x030C30C3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+__global__ void __launch_bounds__(kBlock) k_hl_morton(const float* __restrict__ pb, uint32_t n, const uint32_t* __restrict__ acc, uint32_t* __restrict__ code,
+                                                       uint32_t* __restrict__ val) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 2; k >= 0; --k) {
+        const float lo = funkey(acc[k]), hi = funkey(acc[3 + k]);
+        const float cen = 0.5f * (pb[6 * (size_t)i + k] + pb[6 * (size_t)i + 3 + k]);  // common.rs:86
+        float o = cen - lo;                                                         // Bounds3::offset
+        if (hi > lo) o /= hi - lo;
+        c |= spread3(__float_as_uint(o * 1024.0f)) << k;                            // morton.rs:43-49: float_to_bits
+    }
+    code[i] = c;
+    val[i] = i;
+}
+// radix pass, step 1: digit histogram of every block, digit-major (hist[d * n_blocks + block])
+__global__ void __launch_bounds__(kBlock) k_hl_hist(const uint32_t* __restrict__ code, uint32_t n, int shift, uint32_t* __restrict__ hist, uint32_t n_blocks) {
+    __shared__ uint32_t h[64];
+    if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&h[(code[i] >> shift) & 63u], 1u);
+    __syncthreads();
+    if (threadIdx.x < 64) hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
+}
+// step 3 (after the exclusive scan of hist): stable scatter.  Rank inside the block = elements of the same digit in
+// earlier warps + earlier lanes of the same warp (match_any), which is the order the sequential pass visits them in.
+__global__ void __launch_bounds__(kBlock) k_hl_scatter(const uint32_t* __restrict__ code, const uint32_t* __restrict__ val, uint32_t n, int shift,
+                                                        const uint32_t* __restrict__ hist, uint32_t n_blocks, uint32_t* __restrict__ code_out,
+                                                        uint32_t* __restrict__ val_out) {
+    __shared__ uint32_t wc[kBlock / 32][64];
+    for (int t = threadIdx.x; t < (kBlock / 32) * 64; t += blockDim.x) (&wc[0][0])[t] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool live = i < n;
+    const uint32_t c = live ? code[i] : 0, d = live ? ((c >> shift) & 63u) : 64u + lane;  // dead lanes match nobody
+    const uint32_t peers = __match_any_sync(kFull, d);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (live && rank == 0) wc[warp][d] = __popc(peers);
+    __syncthreads();
+    if (!live) return;
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; ++w) before += wc[w][d];
+    const uint32_t dst = hist[d * n_blocks + blockIdx.x] + before + rank;
+    code_out[dst] = c;
+    val_out[dst] = val[i];
+}
+// treelet starts: runs of equal top-12 bits (hlbvh.rs:53-69)
+__global__ void __launch_bounds__(kBlock) k_hl_flags(const uint32_t* __restrict__ code, uint32_t n, uint8_t* __restrict__ flag, uint32_t* __restrict__ block_sum) {
+    __shared__ uint32_t warp_sum[kBlock / 32];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t p = 0;
+    if (i < n) { p = (i == 0 || ((code[i] ^ code[i - 1]) & 0x3FFC0000u) != 0) ? 1u : 0u; flag[i] = (uint8_t)p; }
+    const uint32_t c = __popc(__ballot_sync(kFull, p));
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < kBlock / 32; ++w) t += warp_sum[w]; block_sum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(kBlock) k_hl_starts(const uint8_t* __restrict__ flag, const uint32_t* __restrict__ T, uint32_t n, uint32_t* __restrict__ starts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) starts[T[i]] = i;
+}
+// emit_lbvh (hlbvh.rs:243-345) for one treelet per thread, iteratively, straight into pre-order
+__global__ void __launch_bounds__(64) k_hl_treelets(const float* __restrict__ pb, const uint32_t* __restrict__ code, const uint32_t* __restrict__ val, uint32_t n,
+                                                     const uint32_t* __restrict__ starts, uint32_t n_treelets, int max_prims, b200pt_bvh_node* __restrict__ tmp,
+                                                     uint32_t* __restrict__ sizes, Ctl* ctl) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_treelets) return;
+    const uint32_t first = starts[t], end = t + 1 < n_treelets ? starts[t + 1] : n;
+    b200pt_bvh_node* out = tmp + 2 * (size_t)first;
+    struct Job { uint32_t first, count; int32_t bit, parent; };
+    Job stack[48];  // at most one pending second child per split bit (18) plus the current first child
+    int sp = 0;
+    stack[sp++] = Job{first, end - first, 30 - 1 - 12, -1};
+    uint32_t n_nodes = 0;
+    while (sp > 0) {
+        Job j = stack[--sp];
+        while (j.bit >= 0 && j.count >= (uint32_t)max_prims && ((code[j.first] ^ code[j.first + j.count - 1]) & (1u << j.bit)) == 0) --j.bit;  // hlbvh.rs:278-291
+        const uint32_t me = n_nodes++;
+        if (j.parent >= 0) out[j.parent].offset = me;
+        if (j.bit == -1 || j.count < (uint32_t)max_prims) {  // hlbvh.rs:257-273
+            Box b = empty_box();
+            for (uint32_t i = 0; i < j.count; ++i) {
+                const float* q = pb + 6 * (size_t)val[j.first + i];
+                Box o;
+                o.lo[0] = q[0]; o.lo[1] = q[1]; o.lo[2] = q[2]; o.hi[0] = q[3]; o.hi[1] = q[4]; o.hi[2] = q[5];
+                grow(b, o);
+            }
+            if (j.count >= 65536u) atomicMax(&ctl->error, (uint32_t)kErrBigLeaf);
+            store_node(out + me, b, j.first, j.count, 0);
+            continue;
+        }
+        const uint32_t mask = 1u << j.bit;
+        uint32_t lo = 0, hi = j.count - 1;
+        while (lo + 1 != hi) {  // hlbvh.rs:293-316
+            const uint32_t mid = (lo + hi) / 2;
+            if (((code[j.first + lo] ^ code[j.first + mid]) & mask) == 0) lo = mid; else hi = mid;
+        }
+        store_node(out + me, empty_box(), 0, 0, (uint32_t)(j.bit % 3));
+        stack[sp++] = Job{j.first + hi, j.count - hi, j.bit - 1, (int32_t)me};
+        stack[sp++] = Job{j.first, hi, j.bit - 1, -1};
+    }
+    for (int32_t i = (int32_t)n_nodes - 1; i >= 0; --i) {  // interior bounds = union(child0, child1), common.rs:150-159
+        if (out[i].n_primitives != 0) continue;
+        Box a = node_box(out + i + 1), b = node_box(out + out[i].offset);
+        grow(a, b);
+        for (int k = 0; k < 3; ++k) { out[i].bounds[k] = a.lo[k]; out[i].bounds[3 + k] = a.hi[k]; }
+    }
+    sizes[t] = n_nodes;
+}
+__global__ void k_hl_gather_roots(const b200pt_bvh_node* __restrict__ tmp, const uint32_t* __restrict__ starts, uint32_t n_treelets, b200pt_bvh_node* __restrict__ roots) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_treelets) roots[t] = tmp[2 * (size_t)starts[t]];
+}
+// final placement: one warp per treelet block (second-child indices rebased), one thread per upper node
+__global__ void __launch_bounds__(256) k_hl_emit(const b200pt_bvh_node* __restrict__ tmp, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ sizes,
+                                                  const long long* __restrict__ base, uint32_t n_treelets, b200pt_bvh_node* __restrict__ out) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_treelets) return;
+    const uint32_t size = sizes[w], b = (uint32_t)base[w];
+    const float4* src = reinterpret_cast<const float4*>(tmp + 2 * (size_t)starts[w]);
+    float4* dst = reinterpret_cast<float4*>(out + b);
+    for (uint32_t q = lane; q < 2 * size; q += 32) {
+        float4 v = src[q];
+        if ((q & 1) && (__float_as_uint(v.w) & 0xffffu) == 0) v.z = __uint_as_float(__float_as_uint(v.z) + b);
+        dst[q] = v;
+    }
+}
+__global__ void k_hl_emit_upper(const b200pt_bvh_node* __restrict__ upper, const long long* __restrict__ index, uint32_t n_upper, b200pt_bvh_node* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_upper) out[index[k]] = upper[k];
+}
+
 // Build scratch: one cached device allocation, grown on demand and carved up by a bump allocator, so that a build
 // costs no cudaMalloc / cudaFree (they dominated: 40 ms of a 46 ms build of 1 M triangles).  Builds are serialised by
 // the mutex; b200pt_bvh_build_release() gives the memory back.
@@ -851,6 +1012,115 @@ int bvh_build_sah_device(const float* d_prim_bounds, int64_t n, int max_prims, b
 }
 
 }  // namespace b2
+
+extern "C" int b200pt_hlbvh_upper_layout(const b200pt_bvh_node* treelet_roots, const uint32_t* treelet_n_nodes, int64_t n_treelets,
+                                         b200pt_bvh_node* upper_nodes_out, int64_t* upper_index_out, int64_t* n_upper_out, int64_t* treelet_base_out,
+                                         int64_t* n_nodes_out);  // host_hlbvh.cpp
+
+namespace b2 {
+
+static size_t hlbvh_scratch_bytes(uint32_t n) {
+    const size_t nb = ((size_t)n + kBlock - 1) / kBlock;
+    return 4 * padded(4 * (size_t)n) + padded(4 * 64 * nb) + padded(n) + padded(4 * nb) + padded(4 * (size_t)n) + padded(4 * (size_t)n) + padded(64 * (size_t)n) +
+           padded(4 * 8192) + padded(32 * 8192) * 2 + padded(8 * 8192) * 2 + padded(sizeof(Ctl)) + padded(64);
+}
+
+int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prims, b200pt_bvh_node* d_nodes, int64_t* n_nodes_out, uint32_t* d_ordered,
+                           cudaStream_t st) {
+    *n_nodes_out = 0;
+    if (n64 == 0) return B200PT_OK;
+    if (n64 >= (1LL << 31)) { b200pt_set_error("b200pt_bvh_build_hlbvh_device: more than 2^31-1 primitives"); return B200PT_ERR_INVALID; }
+    const uint32_t n = (uint32_t)n64;
+    max_prims &= 0xff;
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    if (int rc = workspace_reserve(hlbvh_scratch_bytes(n))) return rc;
+    Arena A{g_ws.base, g_ws.cap};
+    const uint32_t n_blocks = blocks(n, kBlock);
+    uint32_t* code[2] = {A.take<uint32_t>(n), A.take<uint32_t>(n)};
+    uint32_t* val[2] = {A.take<uint32_t>(n), A.take<uint32_t>(n)};
+    uint32_t* hist = A.take<uint32_t>(64 * (size_t)n_blocks);
+    uint8_t* flag = A.take<uint8_t>(n);
+    uint32_t* block_sum = A.take<uint32_t>(n_blocks);
+    uint32_t* T = A.take<uint32_t>(n);
+    uint32_t* starts = A.take<uint32_t>(n);
+    b200pt_bvh_node* tmp = A.take<b200pt_bvh_node>(2 * (size_t)n);
+    uint32_t* sizes = A.take<uint32_t>(8192);
+    b200pt_bvh_node* d_roots = A.take<b200pt_bvh_node>(8192);
+    b200pt_bvh_node* d_upper = A.take<b200pt_bvh_node>(8192);
+    long long* d_upper_index = A.take<long long>(8192);
+    long long* d_base = A.take<long long>(8192);
+    Ctl* ctl = A.take<Ctl>(1);
+    uint32_t* acc = A.take<uint32_t>(6);
+    if (!acc) { b200pt_set_error("b200pt_bvh_build_hlbvh_device: internal error: scratch arena too small"); return B200PT_ERR_INVALID; }
+
+    int64_t launches = 0;
+    const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    B2_CUDA(cudaMemcpyAsync(acc, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemsetAsync(ctl, 0, sizeof(Ctl), st));
+    k_hl_bounds<<<n_blocks, kBlock, 0, st>>>(d_prim_bounds, n, acc);           // hlbvh.rs:42
+    k_hl_morton<<<n_blocks, kBlock, 0, st>>>(d_prim_bounds, n, acc, code[0], val[0]);  // hlbvh.rs:104-141
+    launches += 2;
+    int cur = 0;
+    for (int pass = 0; pass < 5; ++pass) {  // morton.rs:60-100
+        k_hl_hist<<<n_blocks, kBlock, 0, st>>>(code[cur], n, 6 * pass, hist, n_blocks);
+        k_scan_blocks<<<1, 1024, 0, st>>>(hist, 64 * n_blocks);
+        k_hl_scatter<<<n_blocks, kBlock, 0, st>>>(code[cur], val[cur], n, 6 * pass, hist, n_blocks, code[cur ^ 1], val[cur ^ 1]);
+        launches += 3;
+        cur ^= 1;
+    }
+    k_hl_flags<<<n_blocks, kBlock, 0, st>>>(code[cur], n, flag, block_sum);
+    k_scan_blocks<<<1, 1024, 0, st>>>(block_sum, n_blocks);
+    k_scan_apply<<<n_blocks, kBlock, 0, st>>>(flag, block_sum, T, n);
+    k_hl_starts<<<n_blocks, kBlock, 0, st>>>(flag, T, n, starts);
+    launches += 4;
+    uint32_t last[2];  // T[n-1] + flag[n-1] = number of treelets
+    uint8_t last_flag;
+    B2_CUDA(cudaMemcpyAsync(&last[0], T + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&last_flag, flag + (n - 1), 1, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_treelets = last[0] + last_flag;
+    if (n_treelets == 0 || n_treelets > 4096) { b200pt_set_error("b200pt_bvh_build_hlbvh_device: internal error: treelet count"); return B200PT_ERR_INVALID; }
+    k_hl_treelets<<<blocks(n_treelets, 64), 64, 0, st>>>(d_prim_bounds, code[cur], val[cur], n, starts, n_treelets, max_prims, tmp, sizes, ctl);
+    k_hl_gather_roots<<<blocks(n_treelets, 128), 128, 0, st>>>(tmp, starts, n_treelets, d_roots);
+    launches += 2;
+    std::vector<b200pt_bvh_node> roots(n_treelets), upper(n_treelets);
+    std::vector<uint32_t> h_sizes(n_treelets);
+    std::vector<int64_t> upper_index(n_treelets), base(n_treelets);
+    Ctl h{};
+    B2_CUDA(cudaMemcpyAsync(roots.data(), d_roots, n_treelets * sizeof(b200pt_bvh_node), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(h_sizes.data(), sizes, n_treelets * 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&h, ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    g_launches.fetch_add(launches);
+    if (h.error) { b200pt_set_error("b200pt_bvh_build_hlbvh: leaf with >= 65536 primitives (reference asserts)"); return B200PT_ERR_INVALID; }
+    int64_t n_upper = 0, total = 0;
+    if (int rc = b200pt_hlbvh_upper_layout(roots.data(), h_sizes.data(), n_treelets, upper.data(), upper_index.data(), &n_upper, base.data(), &total)) return rc;
+    B2_CUDA(cudaMemcpyAsync(d_base, base.data(), n_treelets * 8, cudaMemcpyHostToDevice, st));
+    if (n_upper > 0) {
+        B2_CUDA(cudaMemcpyAsync(d_upper, upper.data(), (size_t)n_upper * sizeof(b200pt_bvh_node), cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(d_upper_index, upper_index.data(), (size_t)n_upper * 8, cudaMemcpyHostToDevice, st));
+        k_hl_emit_upper<<<blocks((uint64_t)n_upper, 128), 128, 0, st>>>(d_upper, d_upper_index, (uint32_t)n_upper, d_nodes);
+    }
+    k_hl_emit<<<blocks((uint64_t)n_treelets * 32, 256), 256, 0, st>>>(tmp, starts, sizes, d_base, n_treelets, d_nodes);
+    B2_CUDA(cudaMemcpyAsync(d_ordered, val[cur], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));  // leaves take their primitives in sorted order
+    g_launches.fetch_add(n_upper > 0 ? 2 : 1);
+    B2_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+    B2_CUDA(cudaGetLastError());
+    *n_nodes_out = total;
+    return B200PT_OK;
+}
+
+}  // namespace b2
+
+extern "C" int b200pt_bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* d_nodes_out,
+                                             int64_t* n_nodes_out, uint32_t* d_ordered_out, void* stream) {
+    if (int rc = b2::require_device()) return rc;
+    if (n < 0 || !n_nodes_out || (n > 0 && (!d_prim_bounds || !d_nodes_out || !d_ordered_out))) {
+        b200pt_set_error("b200pt_bvh_build_hlbvh_device: invalid argument");
+        return B200PT_ERR_INVALID;
+    }
+    return b2::bvh_build_hlbvh_device(d_prim_bounds, n, max_prims_in_node, d_nodes_out, n_nodes_out, d_ordered_out, (cudaStream_t)stream);
+}
 
 extern "C" int b200pt_triangle_bounds_device(const float* d_tri_verts, int64_t n, float* d_bounds_out, void* stream) {
     if (int rc = b2::require_device()) return rc;

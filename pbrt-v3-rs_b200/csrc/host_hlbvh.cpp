@@ -143,22 +143,27 @@ struct Builder {
         int b = (!(v == v) || v <= 0.0f) ? 0 : (v >= 2147483648.0f ? 0x7fffffff : (int)v);
         return b == kBins ? kBins - 1 : b;
     }
-    const b200pt_bvh_node& root_of(uint32_t t) const { return scratch[2 * treelets[t].first]; }
 
-    // build_upper_sah (hlbvh.rs:353-449) fused with flatten_bvh_tree (mod.rs:126-153); returns the node's index
-    int64_t upper(std::vector<uint32_t>& order, size_t start, size_t end) {
+    // build_upper_sah (hlbvh.rs:353-449) fused with flatten_bvh_tree (mod.rs:126-153): lays the final array out.
+    // Needs only the treelets' root boxes and node counts; records where each treelet's block starts (treelet_base)
+    // and the interior nodes above the treelets (upper / upper_index).  Returns the node's index.
+    std::vector<b200pt_bvh_node> root_box;   // per treelet: its root node (bounds)
+    std::vector<int64_t> treelet_base;       // per treelet: index of its root in the final array
+    std::vector<b200pt_bvh_node> upper;      // interior nodes of the upper SAH tree
+    std::vector<int64_t> upper_index;        // their indices in the final array
+    const b200pt_bvh_node& root_of(uint32_t t) const { return root_box[t]; }
+
+    struct Placed { int64_t index; b200pt_bvh_node node; };
+    Placed layout(std::vector<uint32_t>& order, size_t start, size_t end) {
         const int64_t me = n_out;
         if (end - start == 1) {
-            const Treelet& t = treelets[order[start]];
-            const b200pt_bvh_node* src = scratch.data() + 2 * t.first;
-            for (uint32_t i = 0; i < t.n_nodes; ++i) {
-                out[me + i] = src[i];
-                if (src[i].n_primitives == 0) out[me + i].offset += (uint32_t)me;
-            }
-            n_out += t.n_nodes;
-            return me;
+            const uint32_t t = order[start];
+            treelet_base[t] = me;
+            n_out += treelets[t].n_nodes;
+            return Placed{me, root_box[t]};
         }
         n_out += 1;
+        b200pt_bvh_node nd{};
         Box bounds = empty_box(), cb = empty_box();
         for (size_t i = start; i < end; ++i) grow(bounds, root_of(order[i]).bounds);
         for (size_t i = start; i < end; ++i) {
@@ -169,7 +174,7 @@ struct Builder {
         }
         float dx = cb.hi[0] - cb.lo[0], dy = cb.hi[1] - cb.lo[1], dz = cb.hi[2] - cb.lo[2];
         const int dim = (dx > dy && dx > dz) ? 0 : (dy > dz ? 1 : 2);
-        if (cb.hi[dim] == cb.lo[dim]) { error = "b200pt_bvh_build_hlbvh: treelet centroids coincide (reference asserts, hlbvh.rs:376)"; return me; }
+        if (cb.hi[dim] == cb.lo[dim]) { error = "b200pt_bvh_build_hlbvh: treelet centroids coincide (reference asserts, hlbvh.rs:376)"; return Placed{me, nd}; }
         size_t count[kBins] = {0};
         Box box[kBins];
         for (int b = 0; b < kBins; ++b) box[b] = empty_box();
@@ -179,7 +184,7 @@ struct Builder {
         };
         for (size_t i = start; i < end; ++i) {
             int b = bin(order[i]);
-            if (b < 0 || b >= kBins) { error = "b200pt_bvh_build_hlbvh: bucket out of range (reference asserts)"; return me; }
+            if (b < 0 || b >= kBins) { error = "b200pt_bvh_build_hlbvh: bucket out of range (reference asserts)"; return Placed{me, nd}; }
             count[b] += 1;
             grow(box[b], root_of(order[i]).bounds);
         }
@@ -215,18 +220,28 @@ struct Builder {
             ++split;
         }
         const size_t mid = start + split;
-        if (!(mid > start && mid < end)) { error = "b200pt_bvh_build_hlbvh: upper SAH partition produced an empty side (reference asserts)"; return me; }
-        upper(order, start, mid);
-        if (error) return me;
-        const int64_t second = upper(order, mid, end);
-        if (error) return me;
-        b200pt_bvh_node& nd = out[me];
-        unite_children(nd, out[me + 1], out[second]);
-        nd.offset = (uint32_t)second;
+        if (!(mid > start && mid < end)) { error = "b200pt_bvh_build_hlbvh: upper SAH partition produced an empty side (reference asserts)"; return Placed{me, nd}; }
+        const size_t slot = upper.size();
+        upper.push_back(nd);
+        upper_index.push_back(me);
+        Placed c0 = layout(order, start, mid);
+        if (error) return Placed{me, nd};
+        Placed c1 = layout(order, mid, end);
+        if (error) return Placed{me, nd};
+        unite_children(nd, c0.node, c1.node);
+        nd.offset = (uint32_t)c1.index;
         nd.n_primitives = 0;
         nd.axis = (uint8_t)dim;
         nd.pad = 0;
-        return me;
+        upper[slot] = nd;
+        return Placed{me, nd};
+    }
+    void layout_all() {
+        std::vector<uint32_t> order(treelets.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
+        treelet_base.assign(treelets.size(), 0);
+        n_out = 0;
+        if (!error && !order.empty()) layout(order, 0, order.size());
     }
 };
 
@@ -278,10 +293,43 @@ extern "C" int b200pt_bvh_build_hlbvh(const float* prim_bounds, int64_t n, int m
     }
     B.scratch.resize(2 * (size_t)n);
     for (Treelet& t : B.treelets) B.emit_treelet(t);
-    std::vector<uint32_t> order(B.treelets.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
-    if (!B.error) B.upper(order, 0, order.size());
+    for (const Treelet& t : B.treelets) B.root_box.push_back(B.scratch[2 * t.first]);
+    B.layout_all();
     if (B.error) { b200pt_set_error(B.error); return B200PT_ERR_INVALID; }
+    for (size_t k = 0; k < B.upper.size(); ++k) nodes_out[B.upper_index[k]] = B.upper[k];
+    for (size_t t = 0; t < B.treelets.size(); ++t) {  // block-copy every treelet to where its root landed
+        const Treelet& tr = B.treelets[t];
+        const b200pt_bvh_node* src = B.scratch.data() + 2 * tr.first;
+        const int64_t base = B.treelet_base[t];
+        for (uint32_t i = 0; i < tr.n_nodes; ++i) {
+            nodes_out[base + i] = src[i];
+            if (src[i].n_primitives == 0) nodes_out[base + i].offset += (uint32_t)base;
+        }
+    }
+    *n_nodes_out = B.n_out;
+    return B200PT_OK;
+}
+
+// Upper-tree layout for the GPU builder (csrc/bvh_build.cu): treelet root nodes + node counts in, final positions out.
+// upper_nodes_out / upper_index_out need room for n_treelets - 1 entries.
+extern "C" int b200pt_hlbvh_upper_layout(const b200pt_bvh_node* treelet_roots, const uint32_t* treelet_n_nodes, int64_t n_treelets,
+                                         b200pt_bvh_node* upper_nodes_out, int64_t* upper_index_out, int64_t* n_upper_out, int64_t* treelet_base_out,
+                                         int64_t* n_nodes_out) {
+    if (n_treelets <= 0 || !treelet_roots || !treelet_n_nodes || !upper_nodes_out || !upper_index_out || !n_upper_out || !treelet_base_out || !n_nodes_out) {
+        b200pt_set_error("b200pt_hlbvh_upper_layout: invalid argument");
+        return B200PT_ERR_INVALID;
+    }
+    Builder B;
+    B.prim_bounds = nullptr; B.max_prims = 0; B.out = nullptr; B.ordered = nullptr;
+    for (int64_t t = 0; t < n_treelets; ++t) {
+        B.treelets.push_back(Treelet{0, 0, treelet_n_nodes[t]});
+        B.root_box.push_back(treelet_roots[t]);
+    }
+    B.layout_all();
+    if (B.error) { b200pt_set_error(B.error); return B200PT_ERR_INVALID; }
+    for (size_t k = 0; k < B.upper.size(); ++k) { upper_nodes_out[k] = B.upper[k]; upper_index_out[k] = B.upper_index[k]; }
+    for (int64_t t = 0; t < n_treelets; ++t) treelet_base_out[t] = B.treelet_base[(size_t)t];
+    *n_upper_out = (int64_t)B.upper.size();
     *n_nodes_out = B.n_out;
     return B200PT_OK;
 }

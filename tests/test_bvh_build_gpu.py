@@ -98,3 +98,29 @@ def test_full_size_c2_build_is_identical_and_traces(pkg, gpu):
     print("build 1M tris: gpu %.1f ms (host buffers in/out), host %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
     assert np.array_equal(o0, o1)
     assert n0.tobytes() == n1.tobytes()
+
+
+@pytest.mark.parametrize("max_prims", [1, 4, 255])
+@pytest.mark.parametrize("mesh", ["sphere", "sphere_100k", "soup", "soup_200k", "tiny", "one", "n33", "coincident_big"])
+def test_gpu_hlbvh_builder_matches_host(pkg, gpu, oracle, mesh, max_prims):
+    """SplitMethod::HLBVH on the GPU (Morton codes, stable 5 x 6-bit radix sort, per-treelet LBVH emission) returns the
+    host builder's bytes, which the CPU suite pins to the oracle's restatement of hlbvh.rs."""
+    import ctypes as C
+    import torch
+    from pbrt_v3_rs_b200 import workloads as wl
+    tv = _meshes(wl)[mesh]()
+    pb = pkg.triangle_bounds(tv)
+    n = pb.shape[0]
+    d_pb = torch.from_numpy(pb).cuda()
+    d_nodes = torch.zeros((2 * n, 32), dtype=torch.uint8, device="cuda")
+    d_ord = torch.zeros(n, dtype=torch.int32, device="cuda")
+    nn = C.c_int64(0)
+    rc = pkg.lib().b200pt_bvh_build_hlbvh_device(d_pb.data_ptr(), n, max_prims, d_nodes.data_ptr(), C.byref(nn), d_ord.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, pkg.lib().b200pt_last_error()
+    n1, o1 = pkg.build_bvh_hlbvh(pb, max_prims)
+    assert nn.value == len(n1)
+    assert np.array_equal(d_ord.cpu().numpy().view(np.uint32), o1), "ordered_prims differ"
+    assert d_nodes[:nn.value].cpu().numpy().tobytes() == n1.tobytes(), "LinearBVHNode arrays differ"
+    if n <= 20000:
+        n2, o2 = oracle.build_bvh_hlbvh(pb, max_prims)
+        assert n1.tobytes() == n2.tobytes() and np.array_equal(o1, o2)

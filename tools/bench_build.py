@@ -40,6 +40,24 @@ def run(name, tv, host=True):
         launches = pkg.launch_count() - l0
     out = {"mesh": name, "triangles": n, "nodes": nn.value, "gpu_ms": min(times[1:]), "gpu_ms_all": times, "launches": launches,
            "mtris_per_s_gpu": n / min(times[1:]) / 1e3}
+    ht = []
+    for it in range(3):  # SplitMethod::HLBVH on the GPU (same buffers)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = L.b200pt_bvh_build_hlbvh_device(d_pb.data_ptr(), n, 4, d_nodes.data_ptr(), C.byref(nn), d_ord.data_ptr(), st)
+        assert rc == 0, L.b200pt_last_error()
+        e1.record()
+        torch.cuda.synchronize()
+        ht.append(e0.elapsed_time(e1))
+    out["hlbvh_gpu_ms"] = min(ht[1:])
+    if host:
+        t0 = time.perf_counter()
+        n2, o2 = pkg.build_bvh_hlbvh(d_pb.cpu().numpy(), 4)
+        out["hlbvh_host_ms"] = (time.perf_counter() - t0) * 1e3
+        out["hlbvh_identical"] = bool(d_nodes[:nn.value].cpu().numpy().tobytes() == n2.tobytes() and np.array_equal(d_ord.cpu().numpy().view(np.uint32), o2))
+        # the SAH build again so that the comparison below sees its output
+        assert L.b200pt_bvh_build_sah_device(d_pb.data_ptr(), n, 4, d_nodes.data_ptr(), C.byref(nn), d_ord.data_ptr(), st) == 0
+        torch.cuda.synchronize()
     if host:
         pb = d_pb.cpu().numpy()
         t0 = time.perf_counter()

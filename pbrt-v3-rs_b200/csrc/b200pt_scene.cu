@@ -6,7 +6,7 @@
 //   uniform_sample_one_light, estimate_direct core/src/integrator/common.rs:89-299
 //   FilmTile::add_sample, Film::merge/write   core/src/film/film_tile.rs:62-108, film/mod.rs:220-417
 //
-// Wavefront organisation (one wave = up to kWaveCap paths, a path = one (pixel, sample)):
+// Wavefront organisation (one wave = up to wave_cap_for() paths, a path = one (pixel, sample)):
 //   K1 k_raygen     Halton dims 0-4 -> camera ray, path state init
 //   K2a closest-hit over the compacted ray queue            (traverse_kernels.cu)
 //   K4 k_shade      emission, BSDF frame, light pick + sample_li + BSDF MIS sample -> shadow / MIS ray
@@ -19,6 +19,7 @@
 // Per path the order of floating-point accumulation into L is the reference's.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -1092,6 +1093,7 @@ struct SceneImpl {
     float* d_filter_table = nullptr;
     Wave wave;
     int wave_cap = 0;
+    std::vector<void*> wave_ptrs;
     uint64_t rays[3] = {0, 0, 0};
     uint64_t voxels_built = 0;  // SpatialLightDistribution voxels computed so far
     std::mutex mu;
@@ -1111,12 +1113,23 @@ struct SceneImpl {
     int* d_row_index = nullptr;  // sample row -> position in d_rows, -1 = not owned
 };
 
-static const int kWaveCap = 1 << 22;
-// Whitted tests one shadow ray per light and node: keep paths x lights within 2^24 shadow slots
-static int wave_cap_for(const SceneImpl* s) {
-    if (!s->whitted || s->tree_mode == kTreeDirectOne) return kWaveCap;
-    long long c = (1ll << 24) / std::max(1, s->dev.n_lights);
-    return (int)std::min<long long>(kWaveCap, std::max<long long>(c, 1024));
+// Paths per wave.  Every bounce of a wave costs three traversal launches (each a persistent kernel with its own tail),
+// a counter read-back and a few small kernels; measured on C3 (1080p @ 64 spp = 1.3e8 paths): 256 ms per image with
+// 2^22-path waves, 203 ms with 2^24, 186 ms with 2^26 (profiles/r1_wave_size.txt).  The wave is therefore as large as
+// the render needs, up to kWaveCapMax paths (~330 B of wave state each: 22 GB at 2^26).  B200PT_WAVE_LOG2 overrides.
+static const long long kWaveCapMax = 1ll << 26;
+static int wave_cap_for(const SceneImpl* s, long long n_paths) {
+    long long cap = kWaveCapMax;
+    if (const char* e = std::getenv("B200PT_WAVE_LOG2")) {
+        int v = std::atoi(e);
+        if (v >= 16 && v <= 27) cap = 1ll << v;
+    }
+    long long need = 1ll << 20;
+    while (need < n_paths && need < cap) need <<= 1;
+    cap = std::min(cap, need);
+    // Whitted / DirectLighting "all" test one shadow ray per light and node: keep paths x lights within 2^26 slots
+    if (s->whitted && s->tree_mode != kTreeDirectOne) cap = std::min(cap, std::max<long long>((1ll << 26) / std::max(1, s->dev.n_lights), 1024));
+    return (int)cap;
 }
 
 template <class T> static int dev_upload(SceneImpl* s, const std::vector<T>& v, const T** out) {
@@ -1263,6 +1276,15 @@ struct HostDistr1D {  // core/src/sampling/distribution_1d.rs:22-48
 
 static int wave_alloc(SceneImpl* s, int cap) {
     Wave& W = s->wave;
+    if (s->wave_cap >= cap) return B200PT_OK;
+    for (void* p : s->wave_ptrs) cudaFree(p);  // grow: a later render needs a larger wave
+    s->wave_ptrs.clear();
+    s->wave_cap = 0;
+    const size_t n_before = s->allocs.size();
+    struct MoveOut {  // the wave's buffers are owned by wave_ptrs, not by the scene-lifetime list
+        SceneImpl* s; size_t n0;
+        ~MoveOut() { while (s->allocs.size() > n0) { s->wave_ptrs.push_back(s->allocs.back()); s->allocs.pop_back(); } }
+    } move_out{s, n_before};
     for (int k = 0; k < 2; ++k) {
         int rc = dev_alloc(s, (size_t)cap * 2, &W.ray[k]); if (rc) return rc;
         rc = dev_alloc(s, (size_t)cap, &W.qpid[k]); if (rc) return rc;
@@ -1673,6 +1695,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
 void b200pt_scene_destroy(b200pt_scene* sc) {
     if (!sc) return;
     for (void* p : sc->impl.allocs) cudaFree(p);
+    for (void* p : sc->impl.wave_ptrs) cudaFree(p);
     if (sc->impl.d_sample_L) cudaFree(sc->impl.d_sample_L);
     if (sc->impl.d_sample_pf) cudaFree(sc->impl.d_sample_pf);
     if (sc->impl.d_film) cudaFree(sc->impl.d_film);
@@ -1730,7 +1753,7 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
     const int* sb = s->sample_bounds;
     const int sw = sb[2] - sb[0], sh = sb[3] - sb[1], spp = s->spp;
     const long long n_samples = (long long)srows.size() * sw * spp;
-    if (!s->wave_cap && (rc = wave_alloc(s, wave_cap_for(s)))) return rc;
+    if ((rc = wave_alloc(s, wave_cap_for(s, n_samples)))) return rc;
     if (n_samples > s->sample_cap) {
         if (s->d_sample_L) cudaFree(s->d_sample_L);
         if (s->d_sample_pf) cudaFree(s->d_sample_pf);
@@ -1865,7 +1888,7 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
     SceneImpl* s = &sc->impl;
     std::lock_guard<std::mutex> g(s->mu);
     B2_CUDA(cudaSetDevice(g_device));
-    if (!s->wave_cap && (rc = wave_alloc(s, wave_cap_for(s)))) return rc;
+    if ((rc = wave_alloc(s, wave_cap_for(s, n)))) return rc;
     if (s->dev.sampler_type == B200PT_SAMPLER_ZEROTWO) {  // explicit lists may name any pixel: own every sample row
         const int* sb = s->sample_bounds;
         const int sw = sb[2] - sb[0], sh = sb[3] - sb[1];
@@ -1887,7 +1910,7 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
     }
     int* d_list = nullptr;
     float4 *d_L = nullptr, *d_rays = nullptr;
-    const int cap = s->wave_cap;
+    const int cap = (int)std::min<int64_t>(s->wave_cap, std::max<int64_t>(n, 1));
     B2_CUDA(cudaMalloc(&d_list, (size_t)cap * 3 * sizeof(int)));
     cudaMalloc(&d_L, (size_t)cap * sizeof(float4));
     cudaMalloc(&d_rays, (size_t)cap * 2 * sizeof(float4));

@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(128) k_voxel_finish(DeviceScene S, int n_work)
 }
 
 // ---- K4: shade --------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(DeviceScene S, Wave W, int cur, int n_active, const int* __restrict__ order) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) k_shade(DeviceScene S, Wave W, int cur, int n_active, const int* __restrict__ order) {
     int i_sorted = blockIdx.x * blockDim.x + threadIdx.x;
     if (i_sorted >= n_active) return;
     const int slot = order[i_sorted];
@@ -1326,6 +1327,15 @@ static int wave_alloc(SceneImpl* s, int cap) {
     return B200PT_OK;
 }
 
+// k_shade is compiled for several occupancy targets (register caps); B200PT_SHADE_BLOCKS picks one (A/B knob).
+static void launch_shade(SceneImpl* s, int cur, int n, const int* order, cudaStream_t st) {
+    static const int blocks = [] { const char* e = std::getenv("B200PT_SHADE_BLOCKS"); int v = e ? std::atoi(e) : 5; return (v >= 4 && v <= 6) ? v : 5; }();
+    const int g = (n + 127) / 128;
+    if (blocks == 5) k_shade<5><<<g, 128, 0, st>>>(s->dev, s->wave, cur, n, order);
+    else if (blocks == 6) k_shade<6><<<g, 128, 0, st>>>(s->dev, s->wave, cur, n, order);
+    else k_shade<4><<<g, 128, 0, st>>>(s->dev, s->wave, cur, n, order);
+}
+
 // Runs the bounce loop for the n paths currently initialised in the wave (queue 0).
 static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
     Wave& W = s->wave;
@@ -1340,7 +1350,7 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
         k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, n_active);
         k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, n_active);
         g_launches.fetch_add(2);
-        k_shade<<<(n_active + 127) / 128, 128, 0, st>>>(s->dev, W, cur, n_active, W.sorted);
+        launch_shade(s, cur, n_active, W.sorted, st);
         g_launches.fetch_add(1);
         int cnt[26];
         B2_CUDA(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
@@ -1354,7 +1364,7 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
                 g_launches.fetch_add(2);
                 s->voxels_built += (uint64_t)cnt[24];
             }
-            k_shade<<<(cnt[25] + 127) / 128, 128, 0, st>>>(s->dev, W, cur, cnt[25], W.deferred);
+            launch_shade(s, cur, cnt[25], W.deferred, st);
             g_launches.fetch_add(1);
             B2_CUDA(cudaMemcpyAsync(cnt, W.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
             B2_CUDA(cudaStreamSynchronize(st));

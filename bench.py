@@ -216,6 +216,31 @@ def path_tracing_leg(pkg, args, rank, world):
                       % (sd.tri_verts.shape[0], sd.integrator["maxdepth"], w, h, spp, multigpu.BAND_ROWS)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: keep this rank's host threads (and therefore its first-touched / pinned pages) on the CPUs that are
+    local to its GPU's PCIe root, so that the host<->device copies of the e2e leg do not cross sockets.  Best effort: on a
+    single-node host (the gpurun boxes: one NUMA node, 32 vCPUs) there is nothing to bind and this returns None."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]  # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus or cpus == os.sched_getaffinity(0):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def workload_config(w, args):
     n = int(w["closest"].shape[0])
     return {"workload": "C2 synthetic ray-cast microbench: %d-triangle displaced sphere, SAH BVH maxnodeprims=4, %d closest-hit rays (primary + shuffled diffuse-bounce) + %d any-hit rays per GPU per step"
@@ -249,6 +274,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = ge.load_package()
@@ -353,7 +379,9 @@ def main():
         if e2e_ms is not None:
             line["e2e"] = {"value": world * 2 * n / (e2e_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n,
                            "ms_per_step": e2e_max}
-        if not args.no_cpu_baseline:
+        if numa is not None:
+            line["config"]["host_numa_binding"] = numa
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N = 1 item (rank 0, all host cores)
             nt = os.cpu_count() or 1
             c = cpu_oracle_rate(w, 16.0, nt)
             line["cpu_baseline"] = {"value": c["mrays"], "unit": UNIT, "cores": nt, "kind": "port", "closest_mrays": c["closest"], "anyhit_mrays": c["anyhit"],

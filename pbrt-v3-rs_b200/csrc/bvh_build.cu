@@ -42,6 +42,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_hlbvh.h"
 
 namespace {
 
@@ -1012,10 +1013,6 @@ int bvh_build_sah_device(const float* d_prim_bounds, int64_t n, int max_prims, b
 }
 
 }  // namespace b2
-
-extern "C" int b200pt_hlbvh_upper_layout(const b200pt_bvh_node* treelet_roots, const uint32_t* treelet_n_nodes, int64_t n_treelets,
-                                         b200pt_bvh_node* upper_nodes_out, int64_t* upper_index_out, int64_t* n_upper_out, int64_t* treelet_base_out,
-                                         int64_t* n_nodes_out);  // host_hlbvh.cpp
 
 namespace b2 {
 

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/b200pt.h"
+#include "host_hlbvh.h"
 
 extern "C" int b200pt_set_error(const char* msg);
 

@@ -335,3 +335,20 @@ def test_scene_file_renders_like_the_oracle(gpu, oracle, tmp_path, with_instance
     out = str(tmp_path / ld.output)
     gpu.write_pfm(out, img)
     assert np.array_equal(gpu.read_pfm(out), img)
+
+
+@pytest.mark.parametrize("integrator,strategy", [("path", "power"), ("path", "spatial"), ("whitted", "uniform"), ("directlighting", "uniform")])
+def test_wave_splitting_does_not_change_the_image(gpu, integrator, strategy, monkeypatch):
+    """A render is cut into waves of at most 2^k paths (B200PT_WAVE_LOG2, default: as large as the render needs); every
+    (pixel, sample) is independent, so the film must not depend on where the cuts fall."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    def film(log2):
+        if log2 is None:
+            monkeypatch.delenv("B200PT_WAVE_LOG2", raising=False)
+        else:
+            monkeypatch.setenv("B200PT_WAVE_LOG2", str(log2))
+        sd = ss.one_material_scene(wl, ss.MATERIALS["glass"], light="all", res=96, spp=16, maxdepth=4, strategy="uniform")
+        sd.integrator.update(name=integrator, lightsamplestrategy=strategy)
+        return gpu.PathIntegrator(sd).render_rows()
+    one, many = film(None), film(16)  # 147 456 paths: one wave vs three
+    assert np.array_equal(one, many)

@@ -961,7 +961,7 @@ int build_in_arena(Arena& A, const float* d_prim_bounds, int64_t n64, int max_pr
         b200pt_set_error(h.error == kErrPool        ? "b200pt_bvh_build_sah_device: node pool overflow (tree too unbalanced for the device builder; use the host builder)"
                          : h.error == kErrEmptySide ? "b200pt_bvh_build_sah: SAH partition produced an empty side (reference panics here)"
                                                     : "b200pt_bvh_build_sah: leaf with >= 65536 primitives (reference asserts)");
-        return B200PT_ERR_INVALID;
+        return h.error == kErrPool ? B200PT_ERR_UNSUPPORTED : B200PT_ERR_INVALID;
     }
     launches = 0;
     const int n_levels = (int)level_first.size() - 1;  // levels [level_first[l], level_first[l+1])
@@ -1157,6 +1157,8 @@ extern "C" int b200pt_bvh_build_sah_gpu(const float* prim_bounds, int64_t n, int
     uint32_t* d_ordered = A.take<uint32_t>((size_t)n);
     B2_CUDA(cudaMemcpy(d_bounds, prim_bounds, 6 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
     int rc = b2::build_in_arena(A, d_bounds, n, max_prims_in_node, d_nodes, n_nodes_out, d_ordered, 0);
+    // the device builder sizes its node pool for n / 8 large nodes; a tree more lopsided than that is the same tree on the host
+    if (rc == B200PT_ERR_UNSUPPORTED) return b200pt_bvh_build_sah(prim_bounds, n, max_prims_in_node, nodes_out, n_nodes_out, ordered_out);
     if (rc) return rc;
     B2_CUDA(cudaMemcpy(nodes_out, d_nodes, (size_t)*n_nodes_out * sizeof(b200pt_bvh_node), cudaMemcpyDeviceToHost));
     B2_CUDA(cudaMemcpy(ordered_out, d_ordered, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));

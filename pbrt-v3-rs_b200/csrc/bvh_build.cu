@@ -1112,6 +1112,7 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
 extern "C" int b200pt_bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* d_nodes_out,
                                              int64_t* n_nodes_out, uint32_t* d_ordered_out, void* stream) {
     if (int rc = b2::require_device()) return rc;
+    B2_CUDA(cudaSetDevice(b2::g_device));
     if (n < 0 || !n_nodes_out || (n > 0 && (!d_prim_bounds || !d_nodes_out || !d_ordered_out))) {
         b200pt_set_error("b200pt_bvh_build_hlbvh_device: invalid argument");
         return B200PT_ERR_INVALID;
@@ -1121,6 +1122,7 @@ extern "C" int b200pt_bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t
 
 extern "C" int b200pt_triangle_bounds_device(const float* d_tri_verts, int64_t n, float* d_bounds_out, void* stream) {
     if (int rc = b2::require_device()) return rc;
+    B2_CUDA(cudaSetDevice(b2::g_device));
     if (n <= 0) return B200PT_OK;
     k_tri_bounds<<<blocks((uint64_t)n, 256), 256, 0, (cudaStream_t)stream>>>(d_tri_verts, n, d_bounds_out);
     b2::g_launches.fetch_add(1);
@@ -1131,6 +1133,7 @@ extern "C" int b200pt_triangle_bounds_device(const float* d_tri_verts, int64_t n
 extern "C" int b200pt_bvh_build_sah_device(const float* d_prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* d_nodes_out,
                                            int64_t* n_nodes_out, uint32_t* d_ordered_out, void* stream) {
     if (int rc = b2::require_device()) return rc;
+    B2_CUDA(cudaSetDevice(b2::g_device));
     if (n < 0 || !n_nodes_out || (n > 0 && (!d_prim_bounds || !d_nodes_out || !d_ordered_out))) {
         b200pt_set_error("b200pt_bvh_build_sah_device: invalid argument");
         return B200PT_ERR_INVALID;
@@ -1142,6 +1145,7 @@ extern "C" int b200pt_bvh_build_sah_device(const float* d_prim_bounds, int64_t n
 extern "C" int b200pt_bvh_build_sah_gpu(const float* prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* nodes_out,
                                         int64_t* n_nodes_out, uint32_t* ordered_out) {
     if (int rc = b2::require_device()) return rc;
+    B2_CUDA(cudaSetDevice(b2::g_device));
     if (n < 0 || !n_nodes_out || (n > 0 && (!prim_bounds || !nodes_out || !ordered_out))) {
         b200pt_set_error("b200pt_bvh_build_sah_gpu: invalid argument");
         return B200PT_ERR_INVALID;

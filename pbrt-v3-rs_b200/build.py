@@ -35,7 +35,7 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
+    for root in (CSRC, os.path.join(HERE, "cli"), os.path.join(HERE, "..", "include")):
         for name in sorted(os.listdir(root)):
             with open(os.path.join(root, name), "rb") as f:
                 h.update(name.encode())
@@ -68,6 +68,15 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(log[-1])
         raise RuntimeError("link failed")
+    # command-line driver: plain C++ over the C ABI (no CUDA on that side)
+    cli = os.path.join(HERE, "b200pt_render")
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", os.path.join(HERE, "cli", "b200pt_render.cpp"), "-o", cli, "-L" + HERE, "-lb200pt",
+           "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(log[-1])
+        raise RuntimeError("building b200pt_render failed")
     with open(os.path.join(HERE, "build", "build.log"), "w") as f:
         f.write("\n".join(log))
     with open(STAMP, "w") as f:

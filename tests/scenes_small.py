@@ -44,3 +44,29 @@ def rel_rmse(a, b, eps=1e-2):
     """Per-pixel relative RMSE (north_star's image gate, <= 1e-3)."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.sqrt(np.mean(((a - b) / (np.abs(b) + eps)) ** 2)))
+
+
+SLAB_LE = (3.0, 2.0, 1.0)
+
+
+def glass_slab_scene(maxdepth, integrator="whitted"):
+    """A pencil of camera rays along +z through a glass slab (eta 1.5, faces at z = 1 and z = 1.5 with outward normals) onto
+    a one-sided emitter at z = 3 that faces the camera.  The centre ray of the 3x3 image is exactly (0, 0, 1)."""
+    from pbrt_v3_rs_b200.scene import SceneDescription
+
+    def quad(z, s=4.0, flip=False):
+        q = np.array([[-s, -s, z], [s, -s, z], [s, s, z], [-s, s, z]], dtype=np.float32)
+        if flip:
+            return np.stack([np.concatenate([q[0], q[2], q[1]]), np.concatenate([q[0], q[3], q[2]])])
+        return np.stack([np.concatenate([q[0], q[1], q[2]]), np.concatenate([q[0], q[2], q[3]])])
+    sd = SceneDescription()
+    g = sd.add_material(type="glass", eta=1.5)
+    e = sd.add_material(type="matte", Kd=(0, 0, 0))
+    sd.add_mesh(quad(1.0, flip=True), g)    # front face, outward normal -z (towards the camera)
+    sd.add_mesh(quad(1.5), g)               # back face, outward normal +z: the ray leaves the glass there
+    sd.add_mesh(quad(3.0, flip=True), e, area_light=dict(L=SLAB_LE))
+    sd.camera.update(eye=(0.0, 0.0, -2.0), look=(0.0, 0.0, 1.0), up=(0, 1, 0), fov=1.0)
+    sd.film.update(xresolution=3, yresolution=3)
+    sd.sampler.update(type="halton", pixelsamples=1, samplepixelcenter=True)
+    sd.integrator.update(name=integrator, maxdepth=maxdepth)
+    return sd

@@ -139,3 +139,20 @@ def test_directlighting_area_light_all_vs_path_depth1(pkg, oracle):
     sd.integrator.update(name="directlighting", strategy="one")
     d = oracle.OracleScene(sd).render()[0]
     assert abs(p.mean() - d.mean()) <= 0.03 * p.mean()
+
+
+def test_whitted_glass_slab_normal_incidence_closed_form(pkg, oracle):
+    """A camera ray hits a glass slab (eta 1.5) head-on; behind the slab a one-sided emitter (Le), in front of it
+    nothing.  With F = ((eta - 1) / (eta + 1))^2 = 0.04 at normal incidence, SpecularTransmission carries
+    (1 - F) * eta_i^2 / eta_t^2 per interface (specular_transmission.rs:70-77; the two eta factors cancel over the slab)
+    and SpecularReflection carries F.  Paths that reach the emitter within maxdepth 5 (tree depth counts ray segments):
+    T T (3 segments) and T R R T (5 segments):  L = Le * ((1-F)^2 + (1-F)^2 F^2)."""
+    Le = np.array(ss.SLAB_LE)
+    F = ((1.5 - 1.0) / (1.5 + 1.0)) ** 2
+    for maxdepth, expect in ((3, (1 - F) ** 2), (4, (1 - F) ** 2), (5, (1 - F) ** 2 * (1 + F ** 2)), (2, 0.0)):
+        sd = ss.glass_slab_scene(maxdepth)
+        sc = oracle.OracleScene(sd)
+        li = sc.li(np.array([(1, 1, 0)], dtype=np.int32), nthreads=1)[0].astype(np.float64)
+        # the centre ray is exactly (0, 0, 1): normal incidence.  The emitter adds its own direct light on the glass: none
+        # (delta lobes have f = 0), so only the specular trees carry radiance.
+        assert np.allclose(li, Le * expect, rtol=1e-5, atol=1e-7), (maxdepth, li, Le * expect)

@@ -204,3 +204,13 @@ WorldEnd
     img = gpu.PathIntegrator(ls).render()
     ref = oracle.OracleScene(ls).render()[0]
     assert img.mean() > 0 and ss.rel_rmse(img, ref) <= TOL
+
+
+@pytest.mark.parametrize("integrator", ["whitted", "directlighting"])
+def test_glass_slab_closed_form_on_the_device(gpu, integrator):
+    """L = Le * ((1 - F)^2 + (1 - F)^2 F^2) through a glass slab at normal incidence, F = 0.04 (see tests/test_whitted_cpu.py)."""
+    Le = np.array(ss.SLAB_LE)
+    F = ((1.5 - 1.0) / (1.5 + 1.0)) ** 2
+    for maxdepth, expect in ((3, (1 - F) ** 2), (5, (1 - F) ** 2 * (1 + F ** 2)), (2, 0.0)):
+        li, _ = gpu.PathIntegrator(ss.glass_slab_scene(maxdepth, integrator)).li(np.array([(1, 1, 0)], dtype=np.int32))
+        assert np.allclose(li[0].astype(np.float64), Le * expect, rtol=1e-5, atol=1e-7), (maxdepth, li[0])

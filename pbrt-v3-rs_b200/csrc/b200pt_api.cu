@@ -77,10 +77,12 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
         return nodes[i].n_primitives == 0 ? wide_of[(size_t)i] : ~(int32_t)nodes[i].offset;
     };
     std::vector<float4> wide((size_t)std::max<int64_t>(n_wide, 1) * 4);
-    for (int64_t i = 0; i < n_nodes; ++i) {
+    std::atomic<int> bad{0};
+    parallel_for(n_nodes, [&](int64_t i_begin, int64_t i_end) {
+    for (int64_t i = i_begin; i < i_end; ++i) {
         if (nodes[i].n_primitives != 0) continue;
         int64_t c0 = i + 1, c1 = nodes[i].offset;
-        if (c1 <= i || c1 >= n_nodes || c0 >= n_nodes) { b200pt_set_error("b200pt_accel_create: malformed node array"); return B200PT_ERR_INVALID; }
+        if (c1 <= i || c1 >= n_nodes || c0 >= n_nodes) { bad = 1; continue; }
         const float* a0 = nodes[c0].bounds;
         const float* a1 = nodes[c1].bounds;
         float4* q = &wide[(size_t)wide_of[(size_t)i] * 4];
@@ -92,13 +94,16 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
         std::memcpy(&f0, &k0, 4); std::memcpy(&f1, &k1, 4); std::memcpy(&f2, &ax, 4);
         q[3] = make_float4(f0, f1, f2, 0.0f);
     }
+    });
+    if (bad) { b200pt_set_error("b200pt_accel_create: malformed node array"); return B200PT_ERR_INVALID; }
     a->dev.root_code = code_of(0);
 
     // triangles in BVHAccel.primitives order
     std::vector<float4> tris((size_t)std::max<int64_t>(n_prims, 1) * 4);
-    for (int64_t j = 0; j < n_prims; ++j) {
+    parallel_for(n_prims, [&](int64_t j_begin, int64_t j_end) {
+    for (int64_t j = j_begin; j < j_end; ++j) {
         uint32_t p = ordered[j];
-        if ((int64_t)p >= n_prims) { b200pt_set_error("b200pt_accel_create: ordered_prims index out of range"); return B200PT_ERR_INVALID; }
+        if ((int64_t)p >= n_prims) { bad = 2; continue; }
         const float* v = tri_verts + 9 * (size_t)p;
         uint32_t fl = flags ? flags[p] : 0u, zero = 0u;
         float fp, ff, fz;
@@ -108,14 +113,19 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
         tris[(size_t)j * 4 + 2] = make_float4(v[8], fp, ff, fz);
         tris[(size_t)j * 4 + 3] = record_duv(tri_uvs && (fl & B200PT_PRIM_HAS_UV) ? tri_uvs + 6 * (size_t)p : nullptr);
     }
-    for (int64_t i = 0; i < n_nodes; ++i) {
+    });
+    if (bad) { b200pt_set_error("b200pt_accel_create: ordered_prims index out of range"); return B200PT_ERR_INVALID; }
+    parallel_for(n_nodes, [&](int64_t i_begin, int64_t i_end) {
+    for (int64_t i = i_begin; i < i_end; ++i) {
         if (nodes[i].n_primitives == 0) continue;
         uint32_t cnt = nodes[i].n_primitives;
-        if ((int64_t)nodes[i].offset + cnt > n_prims) { b200pt_set_error("b200pt_accel_create: leaf range out of bounds"); return B200PT_ERR_INVALID; }
+        if ((int64_t)nodes[i].offset + cnt > n_prims) { bad = 3; continue; }
         float fc;
         std::memcpy(&fc, &cnt, 4);
-        tris[(size_t)nodes[i].offset * 4 + 2].w = fc;
+        tris[(size_t)nodes[i].offset * 4 + 2].w = fc;  // leaves own disjoint triangle ranges
     }
+    });
+    if (bad) { b200pt_set_error("b200pt_accel_create: leaf range out of bounds"); return B200PT_ERR_INVALID; }
     B2_CUDA(cudaMalloc(&a->d_wide, wide.size() * sizeof(float4)));
     B2_CUDA(cudaMalloc(&a->d_tris, tris.size() * sizeof(float4)));
     B2_CUDA(cudaMalloc(&a->d_ref, (size_t)n_nodes * 32));

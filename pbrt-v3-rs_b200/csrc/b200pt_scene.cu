@@ -1524,7 +1524,8 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
 
     // primitives in original order with their material / light / flags
     std::vector<float4> pv((size_t)d->n_prims * 3);
-    for (int64_t i = 0; i < d->n_prims; ++i) {
+    parallel_for(d->n_prims, [&](int64_t i_begin, int64_t i_end) {
+    for (int64_t i = i_begin; i < i_end; ++i) {
         const float* v = d->tri_verts + 9 * i;
         int32_t mat = d->prim_material[i], lt = d->prim_light ? d->prim_light[i] : -1;
         uint32_t fl = d->prim_flags ? d->prim_flags[i] : 0u;
@@ -1534,6 +1535,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         pv[3 * i + 1] = make_float4(v[3], v[4], v[5], fl2);
         pv[3 * i + 2] = make_float4(v[6], v[7], v[8], ff);
     }
+    });
     if ((rc = dev_upload(s, pv, &D.prim_verts))) return fail(rc);
     // optional vertex attributes (triangle.rs:384-394, 631-721)
     bool any_uv = false, any_n = false, any_s = false;

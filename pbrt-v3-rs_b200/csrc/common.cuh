@@ -4,8 +4,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/b200pt.h"
 #include "traverse.cuh"
@@ -26,6 +29,22 @@ int cuda_fail(cudaError_t e, const char* what);  // records message, returns B20
         cudaError_t _e = (call);                           \
         if (_e != cudaSuccess) return b2::cuda_fail(_e, #call); \
     } while (0)
+
+// Host-side loop over [0, n) cut into one contiguous range per hardware thread (scene upload preparation: tens of
+// millions of independent records).  f(begin, end) must only write its own range.
+template <class F> inline void parallel_for(int64_t n, F f, int64_t grain = 1 << 16) {
+    int64_t want = (n + grain - 1) / grain;
+    unsigned hw = std::thread::hardware_concurrency();
+    int64_t nt = std::min<int64_t>(want, hw ? hw : 1);
+    if (nt <= 1) { if (n > 0) f((int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    const int64_t chunk = (n + nt - 1) / nt;
+    for (int64_t t = 0; t < nt; ++t) {
+        const int64_t b = t * chunk, e = std::min(n, b + chunk);
+        if (b < e) th.emplace_back([=] { f(b, e); });
+    }
+    for (auto& x : th) x.join();
+}
 
 inline int require_device() {
     if (g_device < 0) {

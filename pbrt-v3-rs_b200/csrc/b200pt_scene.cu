@@ -1053,13 +1053,15 @@ __global__ void __launch_bounds__(128) k_film(DFilm F, const float* __restrict__
             if (x < bx0 || x >= bx1 || y < by0 || y >= by1) continue;
             long long base = ((long long)krow * sw + (qx - F.sb[0])) * spp;
             for (int s = 0; s < spp; ++s) {
-                float4 l = sample_L[base + s];
-                if (l.w == 0.0f) continue;  // pixel outside the integrator's pixel bounds
+                // the 8-byte position first: with the box filter 8 of the 9 candidate pixels fail the window test, and
+                // their 16-byte radiance is then never fetched
                 float2 pf = p_film[base + s];
                 float dx = pf.x - 0.5f, dy = pf.y - 0.5f;
                 int p0x = (int)ceilf(dx - F.rx), p0y = (int)ceilf(dy - F.ry);
                 int p1x = (int)floorf(dx + F.rx) + 1, p1y = (int)floorf(dy + F.ry) + 1;
                 if (x < p0x || x >= p1x || y < p0y || y >= p1y) continue;
+                float4 l = sample_L[base + s];
+                if (l.w == 0.0f) continue;  // pixel outside the integrator's pixel bounds
                 RGB c = rgb(l.x, l.y, l.z);
                 float ly = lum_y(c);
                 if (ly > F.max_lum) c = c * F.max_lum / ly;

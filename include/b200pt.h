@@ -124,7 +124,9 @@ typedef struct b200pt_film {
     float max_sample_luminance; /* INFINITY when unset */
 } b200pt_film;
 
-enum { B200PT_SAMPLER_HALTON = 0, B200PT_SAMPLER_ZEROTWO = 1 };
+/* B200PT_SAMPLER_SOBOL: SobolSampler (samplers/src/sobol.rs; pixelsamples rounded up to a power of two).  The scene
+ * description must then carry the generator matrices (b200pt_scene_desc.sobol_matrices_32). */
+enum { B200PT_SAMPLER_HALTON = 0, B200PT_SAMPLER_ZEROTWO = 1, B200PT_SAMPLER_SOBOL = 2 };
 typedef struct b200pt_sampler {
     int32_t type;
     int32_t spp;               /* "pixelsamples" */
@@ -204,6 +206,10 @@ typedef struct b200pt_scene_desc {
     const float* tri_uvs;      /* 6 floats per ORIGINAL primitive: uv0 uv1 uv2 */
     const float* tri_normals;  /* 9 floats per ORIGINAL primitive: n0 n1 n2 */
     const float* tri_tangents; /* 9 floats per ORIGINAL primitive: s0 s1 s2 */
+    /* Sobol sampler only: SOBOL_MATRICES_32 of core/src/sobol_matrices.rs, 1024 dimensions x 52 u32 (the Rust side passes
+     * the constant's address; the Python mirror and the scene-file loader read pbrt-v3-rs_b200/data/sobol_matrices_32.bin).
+     * NULL otherwise. */
+    const uint32_t* sobol_matrices_32;
 } b200pt_scene_desc;
 
 typedef struct b200pt_accel b200pt_accel; /* opaque: device-resident BVHAccel */
@@ -263,6 +269,11 @@ int b200pt_bvh_build_release(void);
  * NULL to get the sizes: size4 = {level0_width, level0_height, importance_width, importance_height}. */
 int b200pt_envmap_prepare(const float* map_rgb, int32_t map_width, int32_t map_height, const float L[3], int32_t size4[4],
                           float* level0_rgb_out, float* importance_out, float power_lookup_out[3]);
+
+/* Host-only: the pixel <-> sample-index tables SobolSampler uses for a 2^m x 2^m image (the reference's
+ * VD_C_SOBOL_MATRICES[m - 1] / VD_C_SOBOL_MATRICES_INV[m - 1], core/src/low_discrepency.rs:1770-1808), derived from
+ * dimensions 0 and 1 of SOBOL_MATRICES_32.  Exposed for the tests. */
+int b200pt_sobol_interval_tables(const uint32_t* sobol_matrices_32, int m, uint64_t vdc_out[52], uint64_t vdc_inv_out[52]);
 
 /* ---- scene ingestion (host only; api/src/lib.rs + api/src/parser, shapes/src/plymesh.rs, core/src/image_io.rs) ----
  * Reads the subset of the pbrt-v3 scene format that reaches this path (perspective camera; image film; box / gaussian

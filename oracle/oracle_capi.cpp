@@ -76,6 +76,25 @@ void orc_halton_pixel(int spp, int res_x, int res_y, int px, int py, int n_dims,
         ++k;
     } while (s.start_next_sample());
 }
+// Sobol sampler: the caller supplies the 1024 x 52 generator matrices (SOBOL_MATRICES_32).
+void orc_set_sobol_matrices(const uint32_t* m, int64_t n) { sobol_matrices_32().assign(m, m + n); }
+// VD_C_SOBOL_MATRICES[m - 1] / VD_C_SOBOL_MATRICES_INV[m - 1] as derived from dimensions 0 and 1 (52 + 52 u64)
+void orc_sobol_interval_tables(int m, uint64_t* vdc, uint64_t* vdc_inv) {
+    SobolIntervalTables t = sobol_interval_tables(m);
+    for (int c = 0; c < kSobolMatrixSize; ++c) { vdc[c] = t.vdc[c]; vdc_inv[c] = t.vdc_inv[c]; }
+}
+// fills out[n_samples][n_dims] for one pixel; sample_bounds = x0 y0 x1 y1; returns the sample count actually taken
+int orc_sobol_pixel(int spp, const int* sample_bounds, int px, int py, int n_dims, float* out, uint64_t* index_out) {
+    SobolSampler s(spp, sample_bounds);
+    s.start_pixel(px, py);
+    int k = 0;
+    do {
+        if (index_out) index_out[k] = s.interval_sample_index;
+        for (int d = 0; d < n_dims; ++d) out[k * n_dims + d] = s.get_1d();
+        ++k;
+    } while (s.start_next_sample());
+    return k;
+}
 uint64_t orc_halton_index(int spp, int res_x, int res_y, int px, int py, int sample) {
     HaltonSampler s(spp, res_x, res_y, false);
     s.start_pixel(px, py);

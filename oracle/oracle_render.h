@@ -18,6 +18,7 @@
 #include "oracle_envmap.h"
 #include "oracle_math.h"
 #include "oracle_rng.h"
+#include "oracle_sobol.h"
 
 namespace orc {
 
@@ -1223,6 +1224,7 @@ inline Sampler* make_sampler(const RenderScene& sc, uint64_t seed) {
     // SamplerIntegrator::render_tile: data.sampler.clone_sampler(tile_idx) (sampler_integrator.rs:323).
     // Halton ignores the seed (halton.rs:176-182); the (0,2) sampler seeds its PCG32 with it (zero_two_sequence.rs:45-51).
     if (sc.sampler.type == B200PT_SAMPLER_ZEROTWO) return new ZeroTwoSequenceSampler(sc.sampler.spp, sc.sampler.dimensions, seed);
+    if (sc.sampler.type == B200PT_SAMPLER_SOBOL) return new SobolSampler(sc.sampler.spp, sc.sample_bounds);  // sobol.rs:98-100: the seed is ignored
     return new HaltonSampler(sc.sampler.spp, sc.sample_bounds[2] - sc.sample_bounds[0], sc.sample_bounds[3] - sc.sample_bounds[1],
                              sc.sampler.sample_at_center != 0);
 }
@@ -1245,6 +1247,9 @@ inline Sampler* sampler_at(const RenderScene& sc, int px, int py, int s) {
             }
         smp->start_pixel(px, py);
         ((ZeroTwoSequenceSampler*)smp)->set_sample_number(s);
+    } else if (sc.sampler.type == B200PT_SAMPLER_SOBOL) {
+        smp->start_pixel(px, py);
+        ((SobolSampler*)smp)->set_sample_number(s);
     } else {
         HaltonSampler* h = (HaltonSampler*)smp;
         h->start_pixel(px, py);

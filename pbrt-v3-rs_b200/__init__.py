@@ -28,7 +28,7 @@ PRIM_FLIP_NORMAL, PRIM_ALPHA_ZERO, PRIM_SHADOW_ALPHA_ZERO = 1, 2, 4
 PRIM_REVERSE_ORIENTATION, PRIM_HAS_UV, PRIM_HAS_NORMALS, PRIM_HAS_TANGENTS = 8, 16, 32, 64
 MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_METAL = 0, 1, 2, 3
 LIGHT_POINT, LIGHT_AREA, LIGHT_INFINITE = 0, 1, 2
-SAMPLER_HALTON, SAMPLER_ZEROTWO = 0, 1
+SAMPLER_HALTON, SAMPLER_ZEROTWO, SAMPLER_SOBOL = 0, 1, 2
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 INTEGRATOR_PATH, INTEGRATOR_WHITTED, INTEGRATOR_DIRECT = 0, 1, 2
 DIRECT_ALL, DIRECT_ONE = 0, 1
@@ -38,6 +38,18 @@ RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tmax", "<f4"), ("d", "<f4", 3), ("time"
 HIT_DTYPE = np.dtype([("t", "<f4"), ("prim", "<u4"), ("b0", "<f4"), ("b1", "<f4")])
 NODE_DTYPE = np.dtype([("bounds", "<f4", 6), ("offset", "<u4"), ("n_primitives", "<u2"), ("axis", "u1"), ("pad", "u1")])
 assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16 and NODE_DTYPE.itemsize == 32
+
+
+def sobol_matrices_32():
+    """SOBOL_MATRICES_32 of core/src/sobol_matrices.rs (1024 x 52 u32), from pbrt-v3-rs_b200/data (tools/extract_sobol_matrices.py)."""
+    global _sobol
+    if _sobol is None:
+        _sobol = np.fromfile(os.path.join(_HERE, "data", "sobol_matrices_32.bin"), dtype="<u4")
+        assert _sobol.size == 1024 * 52
+    return _sobol
+
+
+_sobol = None
 
 
 class B200PTError(RuntimeError):
@@ -89,7 +101,7 @@ class SceneDesc(C.Structure):
                 ("materials", C.c_void_p), ("n_materials", C.c_int32), ("lights", C.c_void_p), ("n_lights", C.c_int32),
                 ("camera", Camera), ("film", Film), ("sampler", Sampler), ("integrator", Integrator),
                 ("n_top_tris", C.c_int64), ("objects", C.c_void_p), ("n_objects", C.c_int32), ("instances", C.c_void_p), ("n_instances", C.c_int32),
-                ("tri_uvs", C.c_void_p), ("tri_normals", C.c_void_p), ("tri_tangents", C.c_void_p)]
+                ("tri_uvs", C.c_void_p), ("tri_normals", C.c_void_p), ("tri_tangents", C.c_void_p), ("sobol_matrices_32", C.c_void_p)]
 
 
 _lib = None

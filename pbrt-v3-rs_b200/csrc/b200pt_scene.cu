@@ -57,6 +57,7 @@ struct DeviceScene {
     int* vox_work;        // voxels queued by the current shade launch
     DHalton halton;
     DZeroTwo zt;
+    DSobol sobol;
     int sampler_type;  // B200PT_SAMPLER_*
     DCamera camera;
     int max_depth;
@@ -114,6 +115,7 @@ B2_D int meta_pack(int dim, int bounces, int spec) { return (dim & 0xffff) | ((b
 // in its low byte and the 2-D slot counter in the next byte (core/src/sampler/pixel_sampler.rs:88-110).
 B2_D float smp_1d(const DeviceScene& S, unsigned long long key, int& dim) {
     if (S.sampler_type == B200PT_SAMPLER_HALTON) { float v = halton_dim(S.halton, key, dim); dim += 1; return v; }
+    if (S.sampler_type == B200PT_SAMPLER_SOBOL) { float v = sobol_sample_f32(S.sobol, key, dim); dim += 1; return v; }  // dimensions >= 2 only (k_raygen draws 0 / 1)
     int d1 = dim & 0xff;
     float v = zt_1d(S.zt, (long long)(key >> 16), d1, (int)(key & 0xffff));
     dim += 1;
@@ -121,6 +123,7 @@ B2_D float smp_1d(const DeviceScene& S, unsigned long long key, int& dim) {
 }
 B2_D P2 smp_2d(const DeviceScene& S, unsigned long long key, int& dim) {
     if (S.sampler_type == B200PT_SAMPLER_HALTON) { P2 v = mk2(halton_dim(S.halton, key, dim), halton_dim(S.halton, key, dim + 1)); dim += 2; return v; }
+    if (S.sampler_type == B200PT_SAMPLER_SOBOL) { P2 v = mk2(sobol_sample_f32(S.sobol, key, dim), sobol_sample_f32(S.sobol, key, dim + 1)); dim += 2; return v; }
     int d2 = (dim >> 8) & 0xff;
     P2 v = zt_2d(S.zt, (long long)(key >> 16), d2, (int)(key & 0xffff));
     dim += 0x100;
@@ -147,12 +150,15 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long
     }
     unsigned long long idx;
     if (S.sampler_type == B200PT_SAMPLER_HALTON) idx = halton_index(S.halton, px, py, (unsigned long long)s);
+    else if (S.sampler_type == B200PT_SAMPLER_SOBOL) idx = sobol_interval_to_index(S.sobol, (unsigned long long)s, px - S.sobol.sb_min[0], py - S.sobol.sb_min[1]);
     else {  // owned pixel index: position of the row among this shard's rows (explicit lists own every row)
         long long krow = list ? (long long)(py - S.sb[1]) : (g / spp) / (S.sb[2] - S.sb[0]);
         idx = ((unsigned long long)(krow * (S.sb[2] - S.sb[0]) + (px - S.sb[0])) << 16) | (unsigned long long)s;
     }
     int dim = 0;
-    P2 fs = smp_2d(S, idx, dim);  // Sampler::get_camera_sample, sampler/mod.rs:43-51
+    P2 fs;  // Sampler::get_camera_sample, sampler/mod.rs:43-51
+    if (S.sampler_type == B200PT_SAMPLER_SOBOL) { fs = mk2(sobol_film_dim(S.sobol, idx, 0, px), sobol_film_dim(S.sobol, idx, 1, py)); dim = 2; }
+    else fs = smp_2d(S, idx, dim);
     P2 pf = mk2((float)px + fs.x, (float)py + fs.y);
     float tu = smp_1d(S, idx, dim);
     P2 pl = smp_2d(S, idx, dim);
@@ -729,7 +735,7 @@ __global__ void __launch_bounds__(128) k_shade_tree(DeviceScene S, Wave W, int c
         L = L + beta * l;
     } else {
         const int dims_here = kMode == kTreeWhitted ? 2 * S.n_lights : (kMode == kTreeDirectAll ? 4 * S.n_lights : 5);
-        if (dim + dims_here + 4 > 1000) {  // HaltonSampler can only sample 1000 dimensions (halton.rs:106-110 asserts)
+        if (dim + dims_here + 4 > (S.sampler_type == B200PT_SAMPLER_SOBOL ? 1024 : 1000)) {  // HaltonSampler asserts at 1000 dimensions (halton.rs:106-110), Sobol at 1024
             atomicExch(&W.counters[4], 1);
             return;
         }
@@ -1463,9 +1469,13 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         b200pt_set_error("b200pt_scene_create: invalid scene description");
         return B200PT_ERR_INVALID;
     }
-    if (d->sampler.type != B200PT_SAMPLER_HALTON && d->sampler.type != B200PT_SAMPLER_ZEROTWO) {
-        b200pt_set_error("b200pt_scene_create: unknown sampler type (halton and 02sequence are on this path)");
+    if (d->sampler.type != B200PT_SAMPLER_HALTON && d->sampler.type != B200PT_SAMPLER_ZEROTWO && d->sampler.type != B200PT_SAMPLER_SOBOL) {
+        b200pt_set_error("b200pt_scene_create: unknown sampler type (halton, 02sequence and sobol are on this path)");
         return B200PT_ERR_UNSUPPORTED;
+    }
+    if (d->sampler.type == B200PT_SAMPLER_SOBOL && !d->sobol_matrices_32) {
+        b200pt_set_error("b200pt_scene_create: the sobol sampler needs scene_desc.sobol_matrices_32 (SOBOL_MATRICES_32, 1024 x 52 u32)");
+        return B200PT_ERR_INVALID;
     }
     if (d->integrator.type != B200PT_INTEGRATOR_PATH && d->integrator.type != B200PT_INTEGRATOR_WHITTED && d->integrator.type != B200PT_INTEGRATOR_DIRECT) {
         b200pt_set_error("b200pt_scene_create: unknown integrator type (path, whitted and directlighting are on this path)");
@@ -1478,7 +1488,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     if (d->integrator.type != B200PT_INTEGRATOR_PATH) {
         // The number of get_2d() calls of one camera sample depends on the tree it spawns; the (0,2) sampler would fall
         // back to the tile RNG (see below).  Halton is a pure function of (pixel, sample, dimension).
-        if (d->sampler.type != B200PT_SAMPLER_HALTON) { b200pt_set_error("b200pt_scene_create: the whitted / directlighting integrators need the halton sampler on this path"); return B200PT_ERR_UNSUPPORTED; }
+        if (d->sampler.type == B200PT_SAMPLER_ZEROTWO) { b200pt_set_error("b200pt_scene_create: the whitted / directlighting integrators need the halton or sobol sampler on this path"); return B200PT_ERR_UNSUPPORTED; }
         if (d->integrator.max_depth < 0 || d->integrator.max_depth > 24) { b200pt_set_error("b200pt_scene_create: whitted / directlighting maxdepth must be in [0, 24]"); return B200PT_ERR_UNSUPPORTED; }
         if ((long long)d->n_lights * 1024 > (1ll << 24)) { b200pt_set_error("b200pt_scene_create: whitted: more than 16384 lights"); return B200PT_ERR_UNSUPPORTED; }
     }
@@ -1521,7 +1531,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     s->film = d->film;
     s->sampler = d->sampler;
     s->spp = d->sampler.spp;
-    if (d->sampler.type == B200PT_SAMPLER_ZEROTWO) { int p2 = 1; while (p2 < s->spp) p2 <<= 1; s->spp = p2; }  // zero_two_sequence.rs:23-32
+    if (d->sampler.type == B200PT_SAMPLER_ZEROTWO || d->sampler.type == B200PT_SAMPLER_SOBOL) { int p2 = 1; while (p2 < s->spp) p2 <<= 1; s->spp = p2; }  // zero_two_sequence.rs:23-32, sobol.rs:28-37
     D.sampler_type = d->sampler.type;
 
     // primitives in original order with their material / light / flags
@@ -1692,6 +1702,25 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     for (int i = 0; i < 2; ++i) { D.halton.base_scale[i] = hp.base_scale[i]; D.halton.base_exp[i] = hp.base_exp[i]; D.halton.mult_inv[i] = hp.mult_inv[i]; }
     D.halton.stride = hp.stride;
     D.halton.sample_at_center = d->sampler.sample_at_center;
+    if (d->sampler.type == B200PT_SAMPLER_SOBOL) {  // SobolSampler::new, sobol.rs:25-50
+        const int ext = std::max(s->sample_bounds[2] - s->sample_bounds[0], s->sample_bounds[3] - s->sample_bounds[1]);
+        uint32_t res = 1;
+        while (res < (uint32_t)std::max(ext, 1)) res <<= 1;
+        int m = 0;
+        while ((1u << m) < res) ++m;
+        std::vector<unsigned long long> vdc(52), inv(52);
+        static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
+        if (!b2host::sobol_interval_tables(d->sobol_matrices_32, m, (uint64_t*)vdc.data(), (uint64_t*)inv.data())) {
+            b200pt_set_error("b200pt_scene_create: sobol_matrices_32 does not hold the Sobol' generator matrices (dimensions 0 / 1 are not a (0,2)-sequence)");
+            return fail(B200PT_ERR_INVALID);
+        }
+        std::vector<uint32_t> m32(d->sobol_matrices_32, d->sobol_matrices_32 + 1024 * 52);
+        if ((rc = dev_upload(s, m32, &D.sobol.m32))) return fail(rc);
+        if ((rc = dev_upload(s, vdc, &D.sobol.vdc))) return fail(rc);
+        if ((rc = dev_upload(s, inv, &D.sobol.vdc_inv))) return fail(rc);
+        D.sobol.log2_res = m; D.sobol.res = (int)res;
+        D.sobol.sb_min[0] = s->sample_bounds[0]; D.sobol.sb_min[1] = s->sample_bounds[1];
+    }
 
     std::memcpy(D.camera.r2c, d->camera.raster_to_camera, 64);
     std::memcpy(D.camera.c2w, d->camera.camera_to_world, 64);

@@ -1,6 +1,7 @@
 // Host-side sampler tables for the device HaltonSampler
 // (samplers/src/halton.rs:16-19,61-100; core/src/low_discrepency.rs:9-376,1512-1528;
 // core/src/rng.rs:14-120).  Built once per process, uploaded per scene.
+#include <algorithm>
 #include "host_sampler.h"
 
 #include <mutex>
@@ -95,3 +96,46 @@ HaltonParams halton_params(int res_x, int res_y) {  // HaltonSampler::new, halto
 }
 
 }  // namespace b2host
+
+
+// ---- SobolSampler: the pixel <-> index tables of sobol_interval_to_index (core/src/low_discrepency.rs:1770-1808) ----
+// The reference reads them from VD_C_SOBOL_MATRICES[m - 1] / VD_C_SOBOL_MATRICES_INV[m - 1]; here they are derived from the
+// generator matrices of dimensions 0 and 1 (the first 2 x 52 entries of SOBOL_MATRICES_32).  Bit j of a sample index
+// toggles, in the 2m-bit word (pixel x << m | pixel y) of a 2^m x 2^m image, the pattern
+//     e(j) = (M0[j] >> (32 - m)) << m  |  M1[j] >> (32 - m).
+// vdc[c] = e(2m + c): what bit c of the sample number does to the pixel.  vdc_inv[c] = the low index bits that
+// produce pixel-word bit c alone, i.e. column c of E^-1 with E = [e(0) .. e(2m - 1)], found by reducing [E | I] over
+// GF(2) with the basis kept as (pattern, combination) pairs.
+namespace b2host {
+
+bool sobol_interval_tables(const uint32_t* m32, int m, uint64_t vdc[52], uint64_t vdc_inv[52]) {
+    for (int c = 0; c < 52; ++c) vdc[c] = vdc_inv[c] = 0;
+    if (m <= 0 || m > 26) return m == 0;
+    const uint32_t* M0 = m32;
+    const uint32_t* M1 = m32 + 52;
+    auto e = [&](int j) -> uint64_t { return j < 52 ? (((uint64_t)(M0[j] >> (32 - m))) << m) | (uint64_t)(M1[j] >> (32 - m)) : 0ull; };
+    const int n = 2 * m;
+    for (int c = 0; c + n < 52; ++c) vdc[c] = e(n + c);
+    // pat[k]: a pixel-word pattern; comb[k]: the set of index bits whose e() XOR to it
+    uint64_t pat[52], comb[52];
+    for (int j = 0; j < n; ++j) { pat[j] = e(j); comb[j] = 1ull << j; }
+    for (int bit = 0; bit < n; ++bit) {  // make pat[bit] the only pattern with `bit` set, and pat[bit] == 1 << bit in the end
+        int pivot = -1;
+        for (int k = bit; k < n; ++k) if ((pat[k] >> bit) & 1ull) { pivot = k; break; }
+        if (pivot < 0) return false;  // singular: cannot happen for a (0, 2)-sequence in base 2
+        std::swap(pat[bit], pat[pivot]);
+        std::swap(comb[bit], comb[pivot]);
+        for (int k = 0; k < n; ++k)
+            if (k != bit && ((pat[k] >> bit) & 1ull)) { pat[k] ^= pat[bit]; comb[k] ^= comb[bit]; }
+    }
+    for (int c = 0; c < n; ++c) vdc_inv[c] = comb[c];
+    return true;
+}
+
+}  // namespace b2host
+
+// exposed for the tests (include/b200pt.h)
+extern "C" int b200pt_sobol_interval_tables(const uint32_t* sobol_matrices_32, int m, uint64_t vdc_out[52], uint64_t vdc_inv_out[52]) {
+    if (!sobol_matrices_32 || !vdc_out || !vdc_inv_out || m < 0 || m > 26) return -2;
+    return b2host::sobol_interval_tables(sobol_matrices_32, m, vdc_out, vdc_inv_out) ? 0 : -2;
+}

@@ -19,4 +19,8 @@ struct HaltonParams {
 };
 HaltonParams halton_params(int res_x, int res_y);
 
+// SobolSampler: VD_C_SOBOL_MATRICES[m - 1] / VD_C_SOBOL_MATRICES_INV[m - 1] derived from SOBOL_MATRICES_32 (m = log2 of the
+// power-of-two resolution, 0..26).  Returns false if the matrices are not those of a (0, 2)-sequence.
+bool sobol_interval_tables(const uint32_t* m32, int m, uint64_t vdc[52], uint64_t vdc_inv[52]);
+
 }  // namespace b2host

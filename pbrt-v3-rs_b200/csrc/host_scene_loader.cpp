@@ -22,6 +22,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/b200pt.h"
 
 extern "C" int b200pt_set_error(const char* msg);
@@ -271,6 +273,7 @@ struct Loaded {
     std::vector<std::unique_ptr<std::vector<float>>> images;
     std::vector<b200pt_bvh_node> nodes;
     std::vector<uint32_t> ordered;
+    std::vector<uint32_t> sobol;        // SOBOL_MATRICES_32 when the scene asks for the sobol sampler
     std::vector<ObjectDef> objects;
     std::vector<b200pt_object> object_descs;
     std::vector<b200pt_instance> instances;
@@ -675,7 +678,28 @@ void Builder::finish() {
         d.sampler.type = B200PT_SAMPLER_ZEROTWO;
         d.sampler.spp = sampler_p.one_int("pixelsamples", 16);
         d.sampler.dimensions = sampler_p.one_int("dimensions", 4);
-    } else throw Unsupported("Sampler \"" + sampler_name + "\" is outside this path (halton, 02sequence)");
+    } else if (sampler_name == "sobol") {
+        d.sampler.type = B200PT_SAMPLER_SOBOL;
+        d.sampler.spp = sampler_p.one_int("pixelsamples", 16);
+        d.sampler.dimensions = 4;
+        // the generator matrices live next to the library: <dir of libb200pt.so>/data/sobol_matrices_32.bin
+        // (or $B200PT_DATA_DIR); the reference links them in as SOBOL_MATRICES_32
+        std::string dir;
+        if (const char* e = std::getenv("B200PT_DATA_DIR")) dir = e;
+        else {
+            Dl_info info;
+            if (dladdr((void*)&b200pt_load_pbrt, &info) && info.dli_fname) {
+                std::string lib(info.dli_fname);
+                size_t sl = lib.find_last_of('/');
+                dir = (sl == std::string::npos ? std::string(".") : lib.substr(0, sl)) + "/data";
+            }
+        }
+        std::ifstream f(dir + "/sobol_matrices_32.bin", std::ios::binary);
+        L->sobol.resize(1024 * 52);
+        if (!f || !f.read((char*)L->sobol.data(), (std::streamsize)(L->sobol.size() * 4)))
+            throw Invalid("Sampler \"sobol\": cannot read " + dir + "/sobol_matrices_32.bin (set B200PT_DATA_DIR)");
+        d.sobol_matrices_32 = L->sobol.data();
+    } else throw Unsupported("Sampler \"" + sampler_name + "\" is outside this path (halton, 02sequence, sobol)");
 
     // --- Integrator (path.rs:287-326) ---
     if (integrator_name != "path" && integrator_name != "whitted" && integrator_name != "directlighting")

@@ -607,6 +607,39 @@ B2_D float halton_dim(const DHalton& h, unsigned long long index, int dim) {
     return scrambled_radical_inverse(h.primes[dim], index, h.perms + h.prime_sums[dim], h.div_m[dim], h.div_sh[dim]);
 }
 
+// ---- sampler: SobolSampler (samplers/src/sobol.rs, core/src/low_discrepency.rs:1770-1845) -------------------------
+struct DSobol {
+    const uint32_t* m32;                 // SOBOL_MATRICES_32: 1024 dimensions x 52
+    const unsigned long long* vdc;       // VD_C_SOBOL_MATRICES[m - 1] (52), derived on the host
+    const unsigned long long* vdc_inv;   // VD_C_SOBOL_MATRICES_INV[m - 1] (52)
+    int log2_res, res;
+    int sb_min[2];
+};
+B2_D float sobol_sample_f32(const DSobol& S, unsigned long long a, int dim) {  // sobol_sample_f32, scramble = 0
+    uint32_t v = 0;
+    const uint32_t* m = S.m32 + dim * 52;
+    for (; a != 0; a >>= 1, ++m)
+        if (a & 1ull) v ^= __ldg(m);
+    return pmin(__uint2float_rn(v) * 0x1.0p-32f, kOneMinusEps);
+}
+B2_D unsigned long long sobol_interval_to_index(const DSobol& S, unsigned long long frame, int px, int py) {
+    const int m = S.log2_res;
+    if (m == 0) return 0ull;  // low_discrepency.rs:1771-1773
+    unsigned long long index = frame << (2 * m), delta = 0ull;
+    for (int c = 0; frame > 0; frame >>= 1, ++c)
+        if (frame & 1ull) delta ^= S.vdc[c];
+    unsigned long long b = ((((unsigned long long)(uint32_t)px) << m) | (unsigned long long)(uint32_t)py) ^ delta;
+    for (int c = 0; b > 0; b >>= 1, ++c)
+        if (b & 1ull) index ^= S.vdc_inv[c];
+    return index;
+}
+// SobolSampler::sample_dimension for dimensions 0 / 1 (the film position inside pixel (px, py)), sobol.rs:64-80
+B2_D float sobol_film_dim(const DSobol& S, unsigned long long index, int dim, int pixel) {
+    float s = sobol_sample_f32(S, index, dim);
+    s = s * (float)S.res + (float)S.sb_min[dim];
+    return pclamp(s - (float)pixel, 0.0f, kOneMinusEps);
+}
+
 // ---- sampler: ZeroTwoSequenceSampler (samplers/src/zero_two_sequence.rs, core/src/sampler/pixel_sampler.rs) ------
 // The reference generates, per pixel and per 1-D / 2-D slot, spp gray-code samples of a scrambled van der Corput /
 // Sobol' (0,2) sequence and shuffles them with the TILE's PCG32 stream (low_discrepency.rs:1676-1763).  A prepass

@@ -248,7 +248,7 @@ class SceneDescription:
     def to_desc(self):
         from . import Camera, Film, Integrator, Light, Material, Sampler, SceneDesc
         from . import (DIRECT_ALL, DIRECT_ONE, INTEGRATOR_DIRECT, INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_SPATIAL, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
-                       MAT_PLASTIC, SAMPLER_HALTON, SAMPLER_ZEROTWO)
+                       MAT_PLASTIC, SAMPLER_HALTON, SAMPLER_SOBOL, SAMPLER_ZEROTWO)
         if self.nodes is None:
             self.build_accel(None)
         d = SceneDesc()
@@ -375,7 +375,15 @@ class SceneDescription:
         d.film.scale = self.film.get("scale", 1.0)
         d.film.max_sample_luminance = self.film.get("maxsampleluminance", float("inf"))
 
-        d.sampler.type = SAMPLER_HALTON if self.sampler["type"] == "halton" else SAMPLER_ZEROTWO
+        stype = self.sampler["type"]
+        if stype not in ("halton", "02sequence", "lowdiscrepancy", "sobol"):
+            raise ValueError("Sampler %r is outside this path (halton, 02sequence, sobol)" % stype)
+        d.sampler.type = {"halton": SAMPLER_HALTON, "sobol": SAMPLER_SOBOL}.get(stype, SAMPLER_ZEROTWO)
+        if stype == "sobol":
+            from . import sobol_matrices_32
+            m32 = sobol_matrices_32()
+            keep.append(m32)
+            d.sobol_matrices_32 = m32.ctypes.data_as(C.c_void_p)
         d.sampler.spp = self.sampler["pixelsamples"]
         d.sampler.sample_at_center = 1 if self.sampler.get("samplepixelcenter") else 0
         d.sampler.dimensions = self.sampler.get("dimensions", 4)

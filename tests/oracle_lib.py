@@ -42,6 +42,10 @@ def lib():
         L.orc_halton_pixel.argtypes = [C.c_int] * 6 + [vp]
         L.orc_bvh_build_sah.restype = i64
         L.orc_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, vp]
+        L.orc_set_sobol_matrices.argtypes = [vp, i64]
+        L.orc_sobol_interval_tables.argtypes = [C.c_int, vp, vp]
+        L.orc_sobol_pixel.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+        L.orc_sobol_pixel.restype = C.c_int
         L.orc_bvh_build_hlbvh.restype = i64
         L.orc_bvh_build_hlbvh.argtypes = [vp, i64, C.c_int, vp, vp, vp]
         L.orc_triangle_bounds.argtypes = [vp, i64, vp]
@@ -186,6 +190,8 @@ class OracleScene:
     def __init__(self, scene_description):
         self.sd = scene_description
         self.desc = scene_description.to_desc()
+        if self.desc.sobol_matrices_32:  # the Sobol sampler's generator matrices are data the caller supplies
+            lib().orc_set_sobol_matrices(self.desc.sobol_matrices_32, 1024 * 52)
         self.h = lib().orc_scene_create(C.addressof(self.desc))
 
     def __del__(self):

@@ -298,6 +298,13 @@ int b200pt_accel_create(const b200pt_bvh_node* nodes, int64_t n_nodes, const uin
  * B200PT_PRIM_HAS_UV).  The uvs reach the traversal through the degenerate-hit rejection of triangle.rs:551-572. */
 int b200pt_accel_create_uv(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered_prims, const float* tri_verts,
                            const float* tri_uvs, const uint32_t* prim_flags, int64_t n_prims, b200pt_accel** out);
+/* BVHAccel::new (SplitMethod::SAH) for triangles that already live on the device: bounds, the GPU SAH build and the
+ * traversal records are all produced in HBM (csrc/bvh_build.cu); d_tri_verts = 9 floats per triangle, d_prim_flags may be
+ * NULL (no per-mesh uvs on this entry point).  The tree is the reference's: b200pt_accel_download returns the same
+ * LinearBVHNode array / ordered_prims as b200pt_bvh_build_sah.  Rebuilding a 1 M-triangle accelerator takes a few ms. */
+int b200pt_accel_create_device(const float* d_tri_verts, int64_t n_prims, const uint32_t* d_prim_flags, int max_prims_in_node, void* stream,
+                               b200pt_accel** out);
+int b200pt_accel_download(const b200pt_accel* a, b200pt_bvh_node* nodes_out, int64_t* n_nodes_out, uint32_t* ordered_out);
 void b200pt_accel_destroy(b200pt_accel* a);
 /* Primitive::world_bound (mod.rs:159-165): 6 floats. */
 int b200pt_accel_world_bound(const b200pt_accel* a, float* bounds6);

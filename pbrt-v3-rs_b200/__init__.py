@@ -140,6 +140,8 @@ def lib():
     L.b200pt_bvh_build_hlbvh_device.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp, vp]
     L.b200pt_accel_create.argtypes = [vp, i64, vp, vp, vp, i64, C.POINTER(vp)]
     L.b200pt_accel_create_uv.argtypes = [vp, i64, vp, vp, vp, vp, i64, C.POINTER(vp)]
+    L.b200pt_accel_create_device.argtypes = [vp, i64, vp, C.c_int, vp, C.POINTER(vp)]
+    L.b200pt_accel_download.argtypes = [vp, vp, C.POINTER(i64), vp]
     L.b200pt_accel_destroy.argtypes = [vp]
     L.b200pt_accel_destroy.restype = None
     L.b200pt_accel_world_bound.argtypes = [vp, vp]
@@ -327,6 +329,26 @@ class BVHAccel:
         init(_inited if _inited is not None else 0)
         nodes, ordered = (build_bvh_sah if split == "sah" else build_bvh_hlbvh)(triangle_bounds(tv), max_prims)
         return cls(tv, nodes, ordered, prim_flags, tri_uvs)
+
+    @classmethod
+    def from_device_triangles(cls, d_tri_verts_ptr, n_prims, max_prims_in_node=4, d_prim_flags_ptr=None, stream=0, download=False):
+        """BVHAccel::new for triangles already in HBM (b200pt_accel_create_device): bounds, SAH build and traversal records
+        never leave the device.  download=True also fetches nodes / ordered_prims (what the host builders return)."""
+        init(_inited if _inited is not None else 0)
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _check(lib().b200pt_accel_create_device(d_tri_verts_ptr, int(n_prims), d_prim_flags_ptr, int(max_prims_in_node) & 0xFF, stream, C.byref(h)),
+               "b200pt_accel_create_device")
+        self._h = h
+        self.tri_verts = self.prim_flags = self.tri_uvs = None
+        self.nodes = self.ordered_prims = None
+        if download:
+            nn = C.c_int64(0)
+            _check(lib().b200pt_accel_download(h, None, C.byref(nn), None), "b200pt_accel_download")
+            self.nodes = np.zeros(nn.value, dtype=NODE_DTYPE)
+            self.ordered_prims = np.zeros(int(n_prims), dtype=np.uint32)
+            _check(lib().b200pt_accel_download(h, _ptr(self.nodes), C.byref(nn), _ptr(self.ordered_prims)), "b200pt_accel_download")
+        return self
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:

@@ -38,6 +38,7 @@
 //
 // HBM-bound integer/min-max work: nothing here is a contraction.
 #include <cfloat>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -1118,6 +1119,133 @@ extern "C" int b200pt_bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t
         return B200PT_ERR_INVALID;
     }
     return b2::bvh_build_hlbvh_device(d_prim_bounds, n, max_prims_in_node, d_nodes_out, n_nodes_out, d_ordered_out, (cudaStream_t)stream);
+}
+
+// ================================================================ BVHAccel::new without leaving the device
+// Triangles already in HBM -> bounds -> GPU SAH build -> the traversal records (64-byte two-box nodes, 64-byte leaf-order
+// triangles): what accel_build_device (b200pt_api.cu) does on the host, as three kernels.  The pre-order index of an
+// interior node among the interior nodes ("wide index") is a prefix sum over the node array.
+namespace {
+
+__global__ void __launch_bounds__(kBlock) k_acc_flag_interior(const b200pt_bvh_node* __restrict__ nodes, uint32_t n, uint8_t* __restrict__ flag,
+                                                               uint32_t* __restrict__ block_sum) {
+    __shared__ uint32_t warp_sum[kBlock / 32];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t p = 0;
+    if (i < n) { p = nodes[i].n_primitives == 0 ? 1u : 0u; flag[i] = (uint8_t)p; }
+    const uint32_t c = __popc(__ballot_sync(kFull, p));
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < kBlock / 32; ++w) t += warp_sum[w]; block_sum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(kBlock) k_acc_wide(const b200pt_bvh_node* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ T, float4* __restrict__ wide,
+                                                      float4* __restrict__ tris) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const b200pt_bvh_node nd = nodes[i];
+    if (nd.n_primitives != 0) {  // leaf: its first triangle record carries the leaf's primitive count
+        tris[(size_t)nd.offset * 4 + 2].w = __uint_as_float((uint32_t)nd.n_primitives);
+        return;
+    }
+    const b200pt_bvh_node c0 = nodes[i + 1], c1 = nodes[nd.offset];
+    const int k0 = c0.n_primitives == 0 ? (int)T[i + 1] : ~(int)c0.offset, k1 = c1.n_primitives == 0 ? (int)T[nd.offset] : ~(int)c1.offset;
+    float4* q = wide + 4 * (size_t)T[i];
+    q[0] = make_float4(c0.bounds[0], c0.bounds[1], c0.bounds[2], c0.bounds[3]);
+    q[1] = make_float4(c0.bounds[4], c0.bounds[5], c1.bounds[0], c1.bounds[1]);
+    q[2] = make_float4(c1.bounds[2], c1.bounds[3], c1.bounds[4], c1.bounds[5]);
+    q[3] = make_float4(__int_as_float(k0), __int_as_float(k1), __int_as_float((int)nd.axis), 0.0f);
+}
+__global__ void __launch_bounds__(kBlock) k_acc_tris(const float* __restrict__ tri_verts, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ ordered,
+                                                      uint32_t n, float4* __restrict__ tris) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t p = ordered[j];
+    const float* v = tri_verts + 9 * (size_t)p;
+    const uint32_t fl = flags ? flags[p] : 0u;
+    tris[(size_t)j * 4 + 0] = make_float4(v[0], v[1], v[2], v[3]);
+    tris[(size_t)j * 4 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    tris[(size_t)j * 4 + 2] = make_float4(v[8], __uint_as_float(p), __uint_as_float(fl), __uint_as_float(0u));
+    tris[(size_t)j * 4 + 3] = make_float4(0.0f - 1.0f, 0.0f - 1.0f, 1.0f - 1.0f, 0.0f - 1.0f);  // default uvs (0,0) (1,0) (1,1): uv0 - uv2, uv1 - uv2
+}
+
+}  // namespace
+
+extern "C" int b200pt_accel_create_device(const float* d_tri_verts, int64_t n_prims, const uint32_t* d_prim_flags, int max_prims_in_node, void* stream,
+                                          b200pt_accel** out) {
+    if (!out) { b200pt_set_error("b200pt_accel_create_device: out is null"); return B200PT_ERR_INVALID; }
+    *out = nullptr;
+    if (int rc = b2::require_device()) return rc;
+    if (n_prims <= 0 || !d_tri_verts || n_prims >= (1LL << 30)) { b200pt_set_error("b200pt_accel_create_device: invalid argument"); return B200PT_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(b2::g_device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t n = (uint32_t)n_prims;
+    {   // stream-ordered allocations from a pool that keeps its memory: a rebuild then costs no cudaMalloc
+        static std::once_flag once;
+        std::call_once(once, [] {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, b2::g_device) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        });
+    }
+    b200pt_accel* a = new b200pt_accel();
+    b2::AccelImpl& A = a->impl;
+    std::memset(&A.dev, 0, sizeof(A.dev));
+    auto fail = [&](int rc) { b2::accel_free_device(&A); delete a; return rc; };
+    float* d_bounds = nullptr; b200pt_bvh_node* d_nodes = nullptr; uint32_t* d_ordered = nullptr;
+    uint8_t* flag = nullptr; uint32_t *block_sum = nullptr, *T = nullptr;
+    auto free_tmp = [&]() { for (void* q : {(void*)d_bounds, (void*)d_nodes, (void*)d_ordered, (void*)flag, (void*)block_sum, (void*)T}) if (q) cudaFreeAsync(q, st); };
+    auto check = [&](cudaError_t e, const char* what) { return e == cudaSuccess ? 0 : b2::cuda_fail(e, what); };
+    int rc = 0;
+    if ((rc = check(cudaMallocAsync(&d_bounds, 6 * (size_t)n * sizeof(float), st), "cudaMalloc(bounds)")) || (rc = check(cudaMallocAsync(&d_nodes, 2 * (size_t)n * sizeof(b200pt_bvh_node), st), "cudaMalloc(nodes)")) ||
+        (rc = check(cudaMallocAsync(&d_ordered, (size_t)n * 4, st), "cudaMalloc(ordered)"))) { free_tmp(); return fail(rc); }
+    k_tri_bounds<<<blocks(n, 256), 256, 0, st>>>(d_tri_verts, n, d_bounds);
+    b2::g_launches.fetch_add(1);
+    int64_t n_nodes = 0;
+    if ((rc = b2::bvh_build_sah_device(d_bounds, n, max_prims_in_node, d_nodes, &n_nodes, d_ordered, st))) { free_tmp(); return fail(rc); }
+    const uint32_t nn = (uint32_t)n_nodes, nb = blocks(nn, kBlock);
+    if ((rc = check(cudaMallocAsync(&flag, nn, st), "cudaMalloc")) || (rc = check(cudaMallocAsync(&block_sum, (size_t)nb * 4, st), "cudaMalloc")) || (rc = check(cudaMallocAsync(&T, (size_t)nn * 4, st), "cudaMalloc")) ||
+        (rc = check(cudaMallocAsync(&A.d_tris, (size_t)n * 4 * sizeof(float4), st), "cudaMalloc(tris)")) || (rc = check(cudaMallocAsync(&A.d_ref, (size_t)nn * sizeof(b200pt_bvh_node), st), "cudaMalloc(ref nodes)"))) { free_tmp(); return fail(rc); }
+    k_acc_flag_interior<<<nb, kBlock, 0, st>>>(d_nodes, nn, flag, block_sum);
+    k_scan_blocks<<<1, 1024, 0, st>>>(block_sum, nb);
+    k_scan_apply<<<nb, kBlock, 0, st>>>(flag, block_sum, T, nn);
+    uint32_t last_T = 0; uint8_t last_flag = 0;
+    b200pt_bvh_node root;
+    cudaMemcpyAsync(&last_T, T + (nn - 1), 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&last_flag, flag + (nn - 1), 1, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&root, d_nodes, sizeof(root), cudaMemcpyDeviceToHost, st);
+    if ((rc = check(cudaStreamSynchronize(st), "accel_create_device"))) { free_tmp(); return fail(rc); }
+    const uint32_t n_wide = last_T + last_flag;
+    if ((rc = check(cudaMallocAsync(&A.d_wide, (size_t)std::max<uint32_t>(n_wide, 1) * 4 * sizeof(float4), st), "cudaMalloc(wide)"))) { free_tmp(); return fail(rc); }
+    k_acc_tris<<<blocks(n, kBlock), kBlock, 0, st>>>(d_tri_verts, d_prim_flags, d_ordered, n, A.d_tris);
+    k_acc_wide<<<nb, kBlock, 0, st>>>(d_nodes, nn, T, A.d_wide, A.d_tris);
+    cudaMemcpyAsync(A.d_ref, d_nodes, (size_t)nn * sizeof(b200pt_bvh_node), cudaMemcpyDeviceToDevice, st);
+    b2::g_launches.fetch_add(5);
+    if ((rc = check(cudaStreamSynchronize(st), "accel_create_device")) || (rc = check(cudaGetLastError(), "accel_create_device"))) { free_tmp(); return fail(rc); }
+    free_tmp();
+    A.n_nodes = n_nodes; A.n_prims = n_prims; A.n_wide = n_wide;
+    std::memcpy(A.world_bound, root.bounds, 24);
+    std::memcpy(A.dev.root_bounds, root.bounds, 24);
+    A.dev.root_code = root.n_primitives == 0 ? 0 : ~(int)root.offset;
+    A.dev.n_nodes = (int)n_nodes;
+    A.dev.n_prims = n_prims;
+    A.dev.wide = A.d_wide; A.dev.tris = A.d_tris; A.dev.ref_nodes = A.d_ref;
+    *out = a;
+    return B200PT_OK;
+}
+
+// The LinearBVHNode array / ordered_prims of a device-resident accelerator (parity checks; pass NULL to skip one).
+extern "C" int b200pt_accel_download(const b200pt_accel* a, b200pt_bvh_node* nodes_out, int64_t* n_nodes_out, uint32_t* ordered_out) {
+    if (!a) { b200pt_set_error("b200pt_accel_download: null accelerator"); return B200PT_ERR_INVALID; }
+    if (n_nodes_out) *n_nodes_out = a->impl.n_nodes;
+    if (nodes_out && a->impl.n_nodes > 0) B2_CUDA(cudaMemcpy(nodes_out, a->impl.d_ref, (size_t)a->impl.n_nodes * sizeof(b200pt_bvh_node), cudaMemcpyDeviceToHost));
+    if (ordered_out && a->impl.n_prims > 0) {  // original index = second word of the third float4 of every leaf-order triangle record
+        std::vector<float4> rec((size_t)a->impl.n_prims * 4);
+        B2_CUDA(cudaMemcpy(rec.data(), a->impl.d_tris, rec.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (int64_t j = 0; j < a->impl.n_prims; ++j) std::memcpy(&ordered_out[j], &rec[(size_t)j * 4 + 2].y, 4);
+    }
+    return B200PT_OK;
 }
 
 extern "C" int b200pt_triangle_bounds_device(const float* d_tri_verts, int64_t n, float* d_bounds_out, void* stream) {

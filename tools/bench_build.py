@@ -40,6 +40,15 @@ def run(name, tv, host=True):
         launches = pkg.launch_count() - l0
     out = {"mesh": name, "triangles": n, "nodes": nn.value, "gpu_ms": min(times[1:]), "gpu_ms_all": times, "launches": launches,
            "mtris_per_s_gpu": n / min(times[1:]) / 1e3}
+    rt = []
+    for it in range(4):  # whole accelerator (bounds + build + traversal records) from device-resident triangles
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        acc = pkg.BVHAccel.from_device_triangles(d_tv.data_ptr(), n, 4, stream=st)
+        torch.cuda.synchronize()
+        rt.append((time.perf_counter() - t0) * 1e3)
+        acc.close()
+    out["accel_create_device_ms"] = min(rt[1:])
     ht = []
     for it in range(3):  # SplitMethod::HLBVH on the GPU (same buffers)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

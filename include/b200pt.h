@@ -259,6 +259,9 @@ int b200pt_triangle_bounds_device(const float* d_tri_verts, int64_t n, float* d_
  * <= 4096-treelet upper SAH layout runs on the host): device pointers in / out, same bytes as the host builder. */
 int b200pt_bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* d_nodes_out,
                                   int64_t* n_nodes_out, uint32_t* d_ordered_out, void* stream);
+/* host buffers in / out: the drop-in for b200pt_bvh_build_hlbvh once a device is bound */
+int b200pt_bvh_build_hlbvh_gpu(const float* prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* nodes_out,
+                               int64_t* n_nodes_out, uint32_t* ordered_out);
 /* The builder keeps its device scratch (about 160 bytes per primitive of the largest build so far) between calls;
  * this frees it. */
 int b200pt_bvh_build_release(void);

@@ -133,6 +133,7 @@ def lib():
     L.b200pt_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_triangle_bounds.argtypes = [vp, i64, vp]
     L.b200pt_bvh_build_hlbvh.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
+    L.b200pt_bvh_build_hlbvh_gpu.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_hlbvh_morton_codes.argtypes = [vp, i64, vp]
     L.b200pt_bvh_build_sah_gpu.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_bvh_build_sah_device.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp, vp]
@@ -221,14 +222,22 @@ def build_bvh_sah(prim_bounds, max_prims_in_node=4, where="auto"):
     return nodes[:nn.value].copy(), ordered[:n].copy()
 
 
-def build_bvh_hlbvh(prim_bounds, max_prims_in_node=4):
-    """BVHAccel::new(.., SplitMethod::HLBVH) on the host (hlbvh.rs:33-449): returns (nodes, ordered_prims)."""
+def build_bvh_hlbvh(prim_bounds, max_prims_in_node=4, where="host"):
+    """BVHAccel::new(.., SplitMethod::HLBVH) (hlbvh.rs:33-449): returns (nodes, ordered_prims); where = "host" | "gpu" | "auto"
+    (same bytes; "auto" = the GPU once a device is bound and the input has at least GPU_BUILD_MIN_PRIMS primitives)."""
     pb = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
     n = pb.shape[0]
     nodes = np.zeros(max(2 * n - 1, 1), dtype=NODE_DTYPE)
     ordered = np.zeros(max(n, 1), dtype=np.uint32)
     nn = C.c_int64(0)
-    _check(lib().b200pt_bvh_build_hlbvh(_ptr(pb), n, int(max_prims_in_node), _ptr(nodes), C.byref(nn), _ptr(ordered)), "b200pt_bvh_build_hlbvh")
+    if where == "auto":
+        where = "gpu" if (_inited is not None and n >= GPU_BUILD_MIN_PRIMS) else "host"
+    if where == "gpu":
+        init(_inited if _inited is not None else 0)
+        fn, name = lib().b200pt_bvh_build_hlbvh_gpu, "b200pt_bvh_build_hlbvh_gpu"
+    else:
+        fn, name = lib().b200pt_bvh_build_hlbvh, "b200pt_bvh_build_hlbvh"
+    _check(fn(_ptr(pb), n, int(max_prims_in_node), _ptr(nodes), C.byref(nn), _ptr(ordered)), name)
     return nodes[:nn.value].copy(), ordered[:n].copy()
 
 
@@ -327,7 +336,7 @@ class BVHAccel:
         max_prims = int(params.get("maxnodeprims", 4)) & 0xFF
         tv = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
         init(_inited if _inited is not None else 0)
-        nodes, ordered = (build_bvh_sah if split == "sah" else build_bvh_hlbvh)(triangle_bounds(tv), max_prims)
+        nodes, ordered = (build_bvh_sah if split == "sah" else build_bvh_hlbvh)(triangle_bounds(tv), max_prims, where="auto")
         return cls(tv, nodes, ordered, prim_flags, tri_uvs)
 
     @classmethod

@@ -1121,6 +1121,33 @@ extern "C" int b200pt_bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t
     return b2::bvh_build_hlbvh_device(d_prim_bounds, n, max_prims_in_node, d_nodes_out, n_nodes_out, d_ordered_out, (cudaStream_t)stream);
 }
 
+// Same signature and results as b200pt_bvh_build_hlbvh, built on the GPU: host buffers in, host buffers out.
+extern "C" int b200pt_bvh_build_hlbvh_gpu(const float* prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* nodes_out,
+                                          int64_t* n_nodes_out, uint32_t* ordered_out) {
+    if (int rc = b2::require_device()) return rc;
+    B2_CUDA(cudaSetDevice(b2::g_device));
+    if (n < 0 || !n_nodes_out || (n > 0 && (!prim_bounds || !nodes_out || !ordered_out))) {
+        b200pt_set_error("b200pt_bvh_build_hlbvh_gpu: invalid argument");
+        return B200PT_ERR_INVALID;
+    }
+    *n_nodes_out = 0;
+    if (n == 0) return B200PT_OK;
+    float* d_bounds = nullptr; b200pt_bvh_node* d_nodes = nullptr; uint32_t* d_ordered = nullptr;
+    auto free_all = [&]() { cudaFree(d_bounds); cudaFree(d_nodes); cudaFree(d_ordered); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_bounds, 6 * (size_t)n * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&d_nodes, 2 * (size_t)n * sizeof(b200pt_bvh_node))) != cudaSuccess ||
+        (e = cudaMalloc(&d_ordered, (size_t)n * 4)) != cudaSuccess || (e = cudaMemcpy(d_bounds, prim_bounds, 6 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        free_all();
+        return b2::cuda_fail(e, "b200pt_bvh_build_hlbvh_gpu");
+    }
+    int rc = b2::bvh_build_hlbvh_device(d_bounds, n, max_prims_in_node, d_nodes, n_nodes_out, d_ordered, 0);
+    if (!rc && ((e = cudaMemcpy(nodes_out, d_nodes, (size_t)*n_nodes_out * sizeof(b200pt_bvh_node), cudaMemcpyDeviceToHost)) != cudaSuccess ||
+                (e = cudaMemcpy(ordered_out, d_ordered, (size_t)n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess))
+        rc = b2::cuda_fail(e, "b200pt_bvh_build_hlbvh_gpu");
+    free_all();
+    return rc;
+}
+
 // ================================================================ BVHAccel::new without leaving the device
 // Triangles already in HBM -> bounds -> GPU SAH build -> the traversal records (64-byte two-box nodes, 64-byte leaf-order
 // triangles): what accel_build_device (b200pt_api.cu) does on the host, as three kernels.  The pre-order index of an

@@ -148,3 +148,11 @@ def test_accelerator_created_on_the_device_is_the_same_accelerator(pkg, gpu, ora
     assert (h0["prim"] != pkg.MISS).any()
     sh = wl.shadow_rays(rays)
     assert np.array_equal(acc.occluded_batch(sh), ref.occluded_batch(sh))
+
+
+def test_hlbvh_host_buffer_entry_point(pkg, gpu):
+    from pbrt_v3_rs_b200 import workloads as wl
+    pb = pkg.triangle_bounds(wl.displaced_sphere(100, 60))
+    n0, o0 = pkg.build_bvh_hlbvh(pb, 4, where="gpu")
+    n1, o1 = pkg.build_bvh_hlbvh(pb, 4, where="host")
+    assert n0.tobytes() == n1.tobytes() and np.array_equal(o0, o1)

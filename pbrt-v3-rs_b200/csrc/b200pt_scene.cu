@@ -1103,6 +1103,10 @@ struct SceneImpl {
     Wave wave;
     int wave_cap = 0;
     std::vector<void*> wave_ptrs;
+    // streams / events that let a bounce's shadow, MIS and next closest-hit traversals overlap (run_wave)
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_aux[2] = {nullptr, nullptr};
+    bool aux_ready = false, overlap = true;
     uint64_t rays[3] = {0, 0, 0};
     uint64_t voxels_built = 0;  // SpatialLightDistribution voxels computed so far
     std::mutex mu;
@@ -1345,15 +1349,36 @@ static void launch_shade(SceneImpl* s, int cur, int n, const int* order, cudaStr
 }
 
 // Runs the bounce loop for the n paths currently initialised in the wave (queue 0).
+// The three traversals a bounce produces - shadow rays, MIS rays, and the next bounce's closest-hit rays - are
+// independent of one another.  They are launched on three streams so that the drain of one persistent kernel (and, in late
+// bounces, the ~0.1 ms latency floor of a launch that holds only a few thousand rays) overlaps the others; resolve, which
+// needs the first two, and the next shade, which needs all three, follow on the main stream behind events.
+// B200PT_OVERLAP=0 puts everything back on one stream (A/B).
+static int aux_setup(SceneImpl* s) {
+    if (s->aux_ready) return B200PT_OK;
+    for (int i = 0; i < 2; ++i) {
+        B2_CUDA(cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking));
+        B2_CUDA(cudaEventCreateWithFlags(&s->ev_aux[i], cudaEventDisableTiming));
+    }
+    const char* e = std::getenv("B200PT_OVERLAP");
+    s->overlap = !(e && e[0] == '0');
+    s->aux_ready = true;
+    return B200PT_OK;
+}
+
 static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
     Wave& W = s->wave;
+    int rc = aux_setup(s);
+    if (rc) return rc;
     int cur = 0, n_active = n;
     s->rays[0] += (uint64_t)n;
+    auto closest = [&](int q, int count) {
+        s->rays[1] += (uint64_t)count;
+        return s->instanced ? launch_intersect2(s->accel2.dev, W.ray[q], count, W.hit, st, W.hit_b2, W.hit_inst)
+                            : launch_intersect(s->dev.accel, W.ray[q], count, W.hit, st, 0, W.hit_b2);
+    };
+    if (n_active > 0 && (rc = closest(cur, n_active))) return rc;
     for (int iter = 0; n_active > 0 && iter <= s->dev.max_depth + 1; ++iter) {
-        int rc = s->instanced ? launch_intersect2(s->accel2.dev, W.ray[cur], n_active, W.hit, st, W.hit_b2, W.hit_inst)
-                              : launch_intersect(s->dev.accel, W.ray[cur], n_active, W.hit, st, 0, W.hit_b2);
-        if (rc) return rc;
-        s->rays[1] += (uint64_t)n_active;
         B2_CUDA(cudaMemsetAsync(W.counters, 0, 32 * sizeof(int), st));
         k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, n_active);
         k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, n_active);
@@ -1377,16 +1402,26 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
             B2_CUDA(cudaMemcpyAsync(cnt, W.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
             B2_CUDA(cudaStreamSynchronize(st));
         }
+        // everything the shade stage wrote is complete (the stream was just synchronised): fan out
+        cudaStream_t s_sh = s->overlap ? s->aux[0] : st, s_mis = s->overlap ? s->aux[1] : st;
         if (cnt[1] > 0) {
-            rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, cnt[1], W.sh_occ, st) : launch_occluded(s->dev.accel, W.sh_ray, cnt[1], W.sh_occ, st, 0);
+            rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, cnt[1], W.sh_occ, s_sh) : launch_occluded(s->dev.accel, W.sh_ray, cnt[1], W.sh_occ, s_sh, 0);
             if (rc) return rc;
             s->rays[2] += (uint64_t)cnt[1];
+            if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[0], s_sh));
         }
         if (cnt[2] > 0) {
-            rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, cnt[2], W.mis_hit, st, nullptr, nullptr)
-                              : launch_intersect(s->dev.accel, W.mis_ray, cnt[2], W.mis_hit, st, 0, nullptr);
+            rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, cnt[2], W.mis_hit, s_mis, nullptr, nullptr)
+                              : launch_intersect(s->dev.accel, W.mis_ray, cnt[2], W.mis_hit, s_mis, 0, nullptr);
             if (rc) return rc;
             s->rays[1] += (uint64_t)cnt[2];
+            if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[1], s_mis));
+        }
+        const bool more = cnt[0] > 0 && iter + 1 <= s->dev.max_depth + 1;
+        if (more && (rc = closest(cur ^ 1, cnt[0]))) return rc;  // the next bounce's rays, concurrently with the two above
+        if (s->overlap) {
+            if (cnt[1] > 0) B2_CUDA(cudaStreamWaitEvent(st, s->ev_aux[0], 0));
+            if (cnt[2] > 0) B2_CUDA(cudaStreamWaitEvent(st, s->ev_aux[1], 0));
         }
         if (cnt[3] > 0) { k_resolve<<<(cnt[3] + 255) / 256, 256, 0, st>>>(s->dev, W, cnt[3]); g_launches.fetch_add(1); }
         cur ^= 1;
@@ -1400,15 +1435,19 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
 // WhittedIntegrator: one tree node per path and iteration until every path has walked its whole tree.
 static int run_wave_whitted(SceneImpl* s, int n, cudaStream_t st) {
     Wave& W = s->wave;
+    int rc = aux_setup(s);
+    if (rc) return rc;
     int cur = 0, n_active = n;
     s->rays[0] += (uint64_t)n;
     const int nl = s->dev.n_lights;
     const long long max_iter = 1ll << std::min(std::max(s->dev.max_depth, 1), 24);  // a binary tree of depth max_depth
+    auto closest = [&](int q, int count) {
+        s->rays[1] += (uint64_t)count;
+        return s->instanced ? launch_intersect2(s->accel2.dev, W.ray[q], count, W.hit, st, W.hit_b2, W.hit_inst)
+                            : launch_intersect(s->dev.accel, W.ray[q], count, W.hit, st, 0, W.hit_b2);
+    };
+    if (n_active > 0 && (rc = closest(cur, n_active))) return rc;
     for (long long iter = 0; n_active > 0 && iter < max_iter; ++iter) {
-        int rc = s->instanced ? launch_intersect2(s->accel2.dev, W.ray[cur], n_active, W.hit, st, W.hit_b2, W.hit_inst)
-                              : launch_intersect(s->dev.accel, W.ray[cur], n_active, W.hit, st, 0, W.hit_b2);
-        if (rc) return rc;
-        s->rays[1] += (uint64_t)n_active;
         B2_CUDA(cudaMemsetAsync(W.counters, 0, 32 * sizeof(int), st));
         k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, n_active);
         k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, n_active);
@@ -1421,19 +1460,32 @@ static int run_wave_whitted(SceneImpl* s, int n, cudaStream_t st) {
         B2_CUDA(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         B2_CUDA(cudaStreamSynchronize(st));
         if (cnt[4]) {
-            b200pt_set_error("whitted / directlighting: a camera sample needs more than 1000 sampler dimensions (lights x tree nodes); the reference's HaltonSampler asserts here (samplers/src/halton.rs:106-110)");
+            b200pt_set_error("whitted / directlighting: a camera sample needs more sampler dimensions (lights x tree nodes) than the sampler has (halton 1000, sobol 1024); the reference asserts here (samplers/src/halton.rs:106-110)");
             return B200PT_ERR_UNSUPPORTED;
         }
+        // shadow rays, MIS rays and the next node's closest-hit rays are independent: three streams (see run_wave)
+        cudaStream_t s_sh = s->overlap ? s->aux[0] : st, s_mis = s->overlap ? s->aux[1] : st;
+        const bool with_mis = s->tree_mode != kTreeWhitted;
         if (cnt[3] > 0) {
             const int64_t n_sh = (int64_t)cnt[3] * (s->tree_mode == kTreeDirectOne ? 1 : nl);
-            rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, n_sh, W.sh_occ, st) : launch_occluded(s->dev.accel, W.sh_ray, n_sh, W.sh_occ, st, 0);
+            rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, n_sh, W.sh_occ, s_sh) : launch_occluded(s->dev.accel, W.sh_ray, n_sh, W.sh_occ, s_sh, 0);
             if (rc) return rc;
             s->rays[2] += (uint64_t)cnt[5];
-            if (s->tree_mode != kTreeWhitted) {  // the BSDF-sampled MIS rays of estimate_direct
-                rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, n_sh, W.mis_hit, st, nullptr, nullptr)
-                                  : launch_intersect(s->dev.accel, W.mis_ray, n_sh, W.mis_hit, st, 0, nullptr);
+            if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[0], s_sh));
+            if (with_mis) {  // the BSDF-sampled MIS rays of estimate_direct
+                rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, n_sh, W.mis_hit, s_mis, nullptr, nullptr)
+                                  : launch_intersect(s->dev.accel, W.mis_ray, n_sh, W.mis_hit, s_mis, 0, nullptr);
                 if (rc) return rc;
                 s->rays[1] += (uint64_t)cnt[6];
+                if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[1], s_mis));
+            }
+        }
+        const bool more = cnt[0] > 0 && iter + 1 < max_iter;
+        if (more && (rc = closest(cur ^ 1, cnt[0]))) return rc;
+        if (cnt[3] > 0) {
+            if (s->overlap) {
+                B2_CUDA(cudaStreamWaitEvent(st, s->ev_aux[0], 0));
+                if (with_mis) B2_CUDA(cudaStreamWaitEvent(st, s->ev_aux[1], 0));
             }
             const int gr = (cnt[3] + 255) / 256;
             if (s->tree_mode == kTreeWhitted) k_resolve_tree<kTreeWhitted><<<gr, 256, 0, st>>>(s->dev, W, cnt[3]);
@@ -1739,6 +1791,7 @@ void b200pt_scene_destroy(b200pt_scene* sc) {
     if (!sc) return;
     for (void* p : sc->impl.allocs) cudaFree(p);
     for (void* p : sc->impl.wave_ptrs) cudaFree(p);
+    for (int i = 0; i < 2; ++i) { if (sc->impl.aux[i]) cudaStreamDestroy(sc->impl.aux[i]); if (sc->impl.ev_aux[i]) cudaEventDestroy(sc->impl.ev_aux[i]); }
     if (sc->impl.d_sample_L) cudaFree(sc->impl.d_sample_L);
     if (sc->impl.d_sample_pf) cudaFree(sc->impl.d_sample_pf);
     if (sc->impl.d_film) cudaFree(sc->impl.d_film);

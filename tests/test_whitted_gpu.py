@@ -100,7 +100,7 @@ def test_whitted_too_many_dimensions_fails_like_the_reference(gpu):
     (samplers/src/halton.rs:106-110); the device reports the same condition instead of reading past its tables."""
     from pbrt_v3_rs_b200 import workloads as wl
     sd = _many_lights_scene(wl, 8, 4)
-    with pytest.raises(gpu.B200PTError, match="1000 sampler dimensions"):
+    with pytest.raises(gpu.B200PTError, match="sampler dimensions"):
         gpu.PathIntegrator(sd).render()
 
 

@@ -8,6 +8,7 @@
 // TransformedPrimitive::intersect semantics kept: the ray is taken to instance space by Transform::transform_ray
 // (origin nudged by its error bound, t_max shortened by the same dt, transform.rs:451-476), the nested aggregate is
 // intersected, and the INSTANCE-space t_max is written back to the world ray (transformed_primitive.rs:52-56).
+#include <cstdlib>
 #include <algorithm>
 #include <atomic>
 #include <cstring>
@@ -595,9 +596,14 @@ static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, 
         int grid = (int)std::min<int64_t>(want, (int64_t)g_sm_count * kBlocks);
         k_trace_phased2<ANY, 16, 16, kBlocks><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
     } else {
-        constexpr int kBlocks = ANY ? 7 : 6;
-        int grid = (int)std::min<int64_t>(want, (int64_t)g_sm_count * kBlocks);
-        k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, kBlocks><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+        // CTAs per SM (register cap): closest-hit 7 (72 registers, 62 B of spills: 3 % faster on C5 than 6 without spills), any-hit 7; B200PT_2L_BLOCKS = 5..8 overrides the closest-hit choice (A/B)
+        static const int closest_blocks = [] { const char* e = std::getenv("B200PT_2L_BLOCKS"); int v = e ? std::atoi(e) : 7; return (v >= 5 && v <= 8) ? v : 7; }();
+        const int kb = ANY ? 7 : closest_blocks;
+        int grid = (int)std::min<int64_t>(want, (int64_t)g_sm_count * kb);
+        if (kb == 5) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 5><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+        else if (kb == 7) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+        else if (kb == 8) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 8><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+        else k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 6><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
     }
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();

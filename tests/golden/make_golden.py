@@ -42,3 +42,19 @@ occ, _ = acc.occluded(sr)
 np.savez_compressed(os.path.join(HERE, "c2_small_hits.npz"), primary_prim=hits["prim"], primary_t=hits["t"], bounce_prim=bh["prim"],
                     bounce_t=bh["t"], occluded=np.packbits(occ), counters=np.stack([ct.sum(0), bct.sum(0)]))
 print("golden fixtures written")
+
+# per-sample radiances (Integrator::li) of one small scene for every integrator / sampler / light-strategy combination,
+# plus the HLBVH tree of the small mesh: frozen so that a change of the oracle AND the device in the same direction is seen
+import scenes_small as ss  # noqa: E402
+
+LI_CASES = ss.LI_GOLDEN_CASES
+li = {}
+for name, kw in LI_CASES.items():
+    sd = ss.li_golden_scene(wl, **kw)
+    ps = ss.li_golden_pairs()
+    li[name] = ol.OracleScene(sd).li(ps, nthreads=1)
+np.savez_compressed(os.path.join(HERE, "li_small.npz"), **li)
+hn, ho = ol.build_bvh_hlbvh(ol.triangle_bounds(tv), 4)
+json.dump({"sha256": hashlib.sha256(hn.tobytes() + ho.tobytes()).hexdigest(), "n_nodes": int(len(hn))},
+          open(os.path.join(HERE, "hlbvh_c2_small_sha256.json"), "w"))
+print("integrator fixtures written:", ", ".join(sorted(li)))

@@ -70,3 +70,29 @@ def glass_slab_scene(maxdepth, integrator="whitted"):
     sd.sampler.update(type="halton", pixelsamples=1, samplepixelcenter=True)
     sd.integrator.update(name=integrator, maxdepth=maxdepth)
     return sd
+
+
+# ---- frozen per-sample radiances (tests/golden/li_small.npz) -------------------------------------------------------
+LI_GOLDEN_CASES = {
+    "path_halton_power": dict(integrator="path", sampler="halton", strategy="power"),
+    "path_halton_spatial": dict(integrator="path", sampler="halton", strategy="spatial"),
+    "path_zerotwo_uniform": dict(integrator="path", sampler="02sequence", strategy="uniform"),
+    "path_sobol_power": dict(integrator="path", sampler="sobol", strategy="power"),
+    "whitted_halton": dict(integrator="whitted", sampler="halton", strategy="uniform"),
+    "whitted_sobol": dict(integrator="whitted", sampler="sobol", strategy="uniform"),
+    "direct_all_halton": dict(integrator="directlighting", sampler="halton", strategy="uniform", direct="all"),
+    "direct_one_halton": dict(integrator="directlighting", sampler="halton", strategy="uniform", direct="one"),
+}
+
+
+def li_golden_scene(wl, integrator, sampler, strategy, direct="all"):
+    sd = one_material_scene(wl, MATERIALS["glass"], light="all", res=12, spp=4, maxdepth=4, nu=16, nv=8, strategy="uniform")
+    sd.sampler.update(type=sampler)
+    if sampler == "02sequence":
+        sd.sampler.update(dimensions=16)
+    sd.integrator.update(name=integrator, lightsamplestrategy=strategy, strategy=direct)
+    return sd
+
+
+def li_golden_pairs():
+    return np.array([(x, y, s) for y in range(12) for x in range(12) for s in range(4)], dtype=np.int32)

@@ -80,6 +80,7 @@ struct Wave {
     uint8_t* sh_occ;
     float4* mis_ray;
     float4* mis_hit;
+    float* mis_b2;      // third barycentric of the MIS hits (needed when the light's mesh has vertex normals)
     // per path
     float4* L;          // rgb, -
     float4* beta;       // rgb, eta_scale
@@ -329,7 +330,11 @@ B2_D LightSample sample_light(const DeviceScene& S, const DLight& light, const S
         float bx = 1.0f - su0, by = u_light.y * su0;
         V3 p = bx * q0 + by * q1 + (1.0f - bx - by) * q2;
         V3 n = normalize(cross(q1 - q0, q2 - q0));
-        if (lflip) n = -1.0f * n;
+        if (S.prim_n && (f2 & B200PT_PRIM_HAS_NORMALS)) {  // triangle.rs:931-937: orient like intersect() does
+            const float* vn = S.prim_n + 9ll * light.prim;
+            V3 ns = bx * mk(vn[0], vn[1], vn[2]) + by * mk(vn[3], vn[4], vn[5]) + (1.0f - bx - by) * mk(vn[6], vn[7], vn[8]);
+            n = face_forward(n, ns);
+        } else if (lflip) n = -1.0f * n;
         V3 pas = vabs(bx * q0) + vabs(by * q1) + vabs((1.0f - bx - by) * q2);
         V3 p_err = kGamma6 * pas;
         float pdf = 1.0f / light.area;
@@ -432,7 +437,9 @@ B2_D DirectEst estimate_direct_rays(const DeviceScene& S, const DLight& light, c
                     lp = 0.0f;
                     const float4 lduv = (S.prim_duv && (lflags & B200PT_PRIM_HAS_UV)) ? ldg4(S.prim_duv + light.prim) : default_duv();
                     if (triangle_test(ro, tc, __int_as_float(0x7f800000), q0, q1, q2, &t, &c0, &c1, &c2) && triangle_nondegenerate(q0, q1, q2, lduv)) {
-                        SurfHit lh = triangle_surface(q0, q1, q2, c0, c1, c2, lflags, lduv, nullptr, nullptr);
+                        const float* lvn = (S.prim_n && (lflags & B200PT_PRIM_HAS_NORMALS)) ? S.prim_n + 9ll * light.prim : nullptr;
+                    const float* lvs = (S.prim_s && (lflags & B200PT_PRIM_HAS_TANGENTS)) ? S.prim_s + 9ll * light.prim : nullptr;
+                    SurfHit lh = triangle_surface(q0, q1, q2, c0, c1, c2, lflags, lduv, lvn, lvs);
                         lp = distance_squared(sh.p, lh.p) / (abs_dot(lh.n, -wi2) * light.area);
                         if (isinf(lp)) lp = 0.0f;
                     }
@@ -527,6 +534,19 @@ __global__ void __launch_bounds__(128) k_voxel_finish(DeviceScene S, int n_work)
     func[2 * n + 1] = func_int;
     __threadfence();
     S.vox_state[v] = 2;
+}
+
+// Geometric normal of a hit on an emissive triangle as Triangle::intersect leaves it (face-forwarded to the shading normal
+// when the mesh has vertex normals / tangents, triangle.rs:625-721), for DiffuseAreaLight::l at the end of a MIS ray.
+B2_D V3 emitter_hit_normal(const DeviceScene& S, uint32_t prim, V3 p0, V3 p1, V3 p2, uint32_t fl, float b0, float b1, float b2) {
+    if (fl & (B200PT_PRIM_HAS_NORMALS | B200PT_PRIM_HAS_TANGENTS)) {
+        const float4 duv = (S.prim_duv && (fl & B200PT_PRIM_HAS_UV)) ? ldg4(S.prim_duv + prim) : default_duv();
+        const float* vn = (S.prim_n && (fl & B200PT_PRIM_HAS_NORMALS)) ? S.prim_n + 9ll * prim : nullptr;
+        const float* vs = (S.prim_s && (fl & B200PT_PRIM_HAS_TANGENTS)) ? S.prim_s + 9ll * prim : nullptr;
+        return triangle_surface(p0, p1, p2, b0, b1, b2, fl, duv, vn, vs).n;
+    }
+    V3 n = normalize(cross(p0 - p2, p1 - p2));
+    return (fl & 1u) ? -n : n;
 }
 
 // ---- K4: shade --------------------------------------------------------------------------------
@@ -910,11 +930,7 @@ __global__ void __launch_bounds__(256) k_resolve_tree(DeviceScene S, Wave W, int
             if (prim != 0xffffffffu) {
                 V3 p0, p1, p2; int mat, al; uint32_t fl;
                 load_prim(S, prim, &p0, &p1, &p2, &mat, &al, &fl);
-                if (al == li) {
-                    V3 n = normalize(cross(p0 - p2, p1 - p2));
-                    if (fl & 1u) n = -n;
-                    Li = area_l(light, n, -wi);
-                }
+                if (al == li) Li = area_l(light, emitter_hit_normal(S, prim, p0, p1, p2, fl, mh.z, mh.w, W.mis_b2[sl]), -wi);
             } else if (light.type == LT_INFINITE) {
                 Li = infinite_le(light, S.inf_distr[light.inf_slot], wi);
             }
@@ -994,11 +1010,7 @@ __global__ void __launch_bounds__(256) k_resolve(DeviceScene S, Wave W, int n_pe
         if (prim != 0xffffffffu) {
             V3 p0, p1, p2; int mat, al; uint32_t fl;
             load_prim(S, prim, &p0, &p1, &p2, &mat, &al, &fl);
-            if (al == d.x) {
-                V3 n = normalize(cross(p0 - p2, p1 - p2));
-                if (fl & 1u) n = -n;
-                Li = area_l(light, n, -wi);
-            }
+            if (al == d.x) Li = area_l(light, emitter_hit_normal(S, prim, p0, p1, p2, fl, mh.z, mh.w, W.mis_b2[d.z]), -wi);
         } else if (light.type == LT_INFINITE) {
             Li = infinite_le(light, S.inf_distr[light.inf_slot], wi);
         }
@@ -1321,6 +1333,7 @@ static int wave_alloc(SceneImpl* s, int cap) {
     }
     if ((rc = dev_alloc(s, mis_cap * 2, &W.mis_ray))) return rc;
     if ((rc = dev_alloc(s, mis_cap, &W.mis_hit))) return rc;
+    if ((rc = dev_alloc(s, mis_cap, &W.mis_b2))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.L))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.beta))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.hidx))) return rc;
@@ -1411,8 +1424,8 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
             if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[0], s_sh));
         }
         if (cnt[2] > 0) {
-            rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, cnt[2], W.mis_hit, s_mis, nullptr, nullptr)
-                              : launch_intersect(s->dev.accel, W.mis_ray, cnt[2], W.mis_hit, s_mis, 0, nullptr);
+            rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, cnt[2], W.mis_hit, s_mis, W.mis_b2, nullptr)
+                              : launch_intersect(s->dev.accel, W.mis_ray, cnt[2], W.mis_hit, s_mis, 0, W.mis_b2);
             if (rc) return rc;
             s->rays[1] += (uint64_t)cnt[2];
             if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[1], s_mis));
@@ -1473,8 +1486,8 @@ static int run_wave_whitted(SceneImpl* s, int n, cudaStream_t st) {
             s->rays[2] += (uint64_t)cnt[5];
             if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[0], s_sh));
             if (with_mis) {  // the BSDF-sampled MIS rays of estimate_direct
-                rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, n_sh, W.mis_hit, s_mis, nullptr, nullptr)
-                                  : launch_intersect(s->dev.accel, W.mis_ray, n_sh, W.mis_hit, s_mis, 0, nullptr);
+                rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, n_sh, W.mis_hit, s_mis, W.mis_b2, nullptr)
+                                  : launch_intersect(s->dev.accel, W.mis_ray, n_sh, W.mis_hit, s_mis, 0, W.mis_b2);
                 if (rc) return rc;
                 s->rays[1] += (uint64_t)cnt[6];
                 if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[1], s_mis));
@@ -1606,10 +1619,6 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     for (int64_t i = 0; i < d->n_prims && d->prim_flags; ++i) {
         const uint32_t fl = d->prim_flags[i];
         any_uv |= (fl & B200PT_PRIM_HAS_UV) != 0; any_n |= (fl & B200PT_PRIM_HAS_NORMALS) != 0; any_s |= (fl & B200PT_PRIM_HAS_TANGENTS) != 0;
-        if ((fl & B200PT_PRIM_HAS_NORMALS) && d->prim_light && d->prim_light[i] >= 0) {
-            b200pt_set_error("b200pt_scene_create: area light on a mesh with vertex normals is not supported");
-            return fail(B200PT_ERR_UNSUPPORTED);
-        }
     }
     if ((any_uv && !d->tri_uvs) || (any_n && !d->tri_normals) || (any_s && !d->tri_tangents)) {
         b200pt_set_error("b200pt_scene_create: a primitive flag announces uvs / normals / tangents but the array is NULL");

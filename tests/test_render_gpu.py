@@ -261,17 +261,6 @@ def test_vertex_attributes_on_instanced_objects_and_flags(gpu, oracle):
     assert li.any()
 
 
-def test_area_light_on_a_mesh_with_normals_fails_loudly(gpu):
-    from pbrt_v3_rs_b200 import workloads as wl
-    from pbrt_v3_rs_b200.scene import SceneDescription
-    sd = SceneDescription()
-    m = sd.add_material(type="matte")
-    tv, uv, nrm = wl.displaced_sphere(8, 4, with_attrs=True)
-    sd.add_mesh(tv, m, normals=nrm, area_light=dict(L=(1, 1, 1)))
-    with pytest.raises(gpu.B200PTError):
-        gpu.PathIntegrator(sd).preprocess()
-
-
 def _envmap_scene(wl, mat, size, spp=8, res=32, extra_point=False, strategy="uniform"):
     from pbrt_v3_rs_b200.scene import SceneDescription
     sd = SceneDescription()
@@ -352,3 +341,44 @@ def test_wave_splitting_does_not_change_the_image(gpu, integrator, strategy, mon
         return gpu.PathIntegrator(sd).render_rows()
     one, many = film(None), film(16)  # 147 456 paths: one wave vs three
     assert np.array_equal(one, many)
+
+
+def _emissive_smooth_scene(wl, integrator="path", inward=False, twosided=False):
+    """A small emissive sphere whose mesh carries vertex normals ("N"): Triangle::sample orients the sampled normal with
+    the interpolated one (triangle.rs:931-937) and the hit's geometric normal is face-forwarded to the shading normal."""
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    sd = SceneDescription()
+    g = sd.add_material(type="matte", Kd=(0.5, 0.5, 0.5))
+    e = sd.add_material(type="matte", Kd=(0.0, 0.0, 0.0))
+    p = sd.add_material(type="plastic")
+    sd.add_mesh(wl.ground_quad(), g)
+    sd.add_mesh(wl.displaced_sphere(16, 8, radius=0.6, center=(-1.2, -0.6, 0.0)), p)
+    tv, uv, nrm = wl.displaced_sphere(8, 4, radius=0.35, amplitude=0.0, center=(0.6, 0.4, -0.3), with_attrs=True)
+    if inward:
+        nrm = -nrm  # normals pointing into the sphere: the emitting side flips with them
+    sd.add_mesh(tv, e, area_light=dict(L=(12, 11, 9), twosided=twosided), uv=uv, normals=nrm)
+    sd.camera.update(eye=(0.0, 1.2, -4.0), look=(0.0, -0.2, 0.0), up=(0, 1, 0), fov=40.0)
+    sd.film.update(xresolution=40, yresolution=32)
+    sd.sampler.update(type="halton", pixelsamples=8)
+    sd.integrator.update(name=integrator, maxdepth=4, lightsamplestrategy="power")
+    return sd
+
+
+@pytest.mark.parametrize("integrator,inward,twosided", [("path", False, False), ("path", True, False), ("path", False, True),
+                                                       ("whitted", False, False), ("directlighting", True, False)])
+def test_area_light_on_a_mesh_with_vertex_normals(gpu, oracle, integrator, inward, twosided):
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = _emissive_smooth_scene(wl, integrator, inward, twosided)
+    integ = gpu.PathIntegrator(sd)
+    osc = oracle.OracleScene(sd)
+    ps = np.array([(x, y, s) for y in range(0, 32, 2) for x in range(0, 40, 2) for s in range(4)], dtype=np.int32)
+    li, _ = integ.li(ps)
+    oli = osc.li(ps)
+    close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
+    assert close.mean() >= 0.97, close.mean()
+    img = integ.render()
+    ref, stats, _ = osc.render()
+    assert ss.rel_rmse(img, ref) <= TOL
+    assert (img.mean() > 0.01) == (twosided or not inward)  # inward-facing normals: the sphere emits into itself only
+    rc = integ.ray_counts()
+    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0.01 * stats[1]

@@ -280,10 +280,12 @@ int b200pt_sobol_interval_tables(const uint32_t* sobol_matrices_32, int m, uint6
 
 /* ---- scene ingestion (host only; api/src/lib.rs + api/src/parser, shapes/src/plymesh.rs, core/src/image_io.rs) ----
  * Reads the subset of the pbrt-v3 scene format that reaches this path (perspective camera; image film; box / gaussian
- * filter; halton / 02sequence sampler; path integrator; bvh accelerator; trianglemesh / plymesh shapes with P, N, S,
- * uv/st, alpha, shadowalpha; matte / plastic / glass / metal with constant parameters; point / infinite (.pfm map) /
- * diffuse area lights; transforms, attribute and transform stacks, named materials, object instancing, Include) and
- * builds the BVHs with b200pt_bvh_build_sah.  Anything else returns B200PT_ERR_UNSUPPORTED with the offending directive
+ * filter; halton / 02sequence / sobol sampler; path / whitted / directlighting integrator with uniform / power / spatial
+ * light sampling; bvh accelerator with splitmethod sah / hlbvh; trianglemesh / plymesh shapes with P, N, S, uv/st, alpha,
+ * shadowalpha; matte / plastic / glass / metal with constant parameters; point / infinite (.pfm map) / diffuse area
+ * lights; transforms, attribute and transform stacks, named materials, object instancing, Include) and builds the BVHs
+ * with b200pt_bvh_build_sah (on the GPU once a device is bound) / b200pt_bvh_build_hlbvh.  Anything else returns
+ * B200PT_ERR_UNSUPPORTED with the offending directive
  * in b200pt_last_error.  The returned desc stays valid until b200pt_loaded_scene_free. */
 int b200pt_load_pbrt(const char* path, b200pt_loaded_scene** out);
 const b200pt_scene_desc* b200pt_loaded_scene_desc(const b200pt_loaded_scene* s);
@@ -331,7 +333,7 @@ int b200pt_count_work_device(const b200pt_accel* a, const void* d_rays, int64_t 
 /* Kernel launches issued by this library since init (bench.py's gpu_launches). */
 int64_t b200pt_launch_count(void);
 
-/* ---- scene + PathIntegrator -------------------------------------------- */
+/* ---- scene + SamplerIntegrator (path / whitted / directlighting) -------- */
 int b200pt_scene_create(const b200pt_scene_desc* desc, b200pt_scene** out);
 void b200pt_scene_destroy(b200pt_scene* s);
 /* Integrator::render (core/src/integrator/sampler_integrator.rs:243-304) for

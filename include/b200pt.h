@@ -181,7 +181,8 @@ typedef struct b200pt_scene_desc {
     const uint32_t* ordered_prims; /* BVHAccel.primitives order: ordered position -> original index */
     const float* tri_verts;        /* 9 floats per ORIGINAL primitive, world space (TriangleMesh::new transforms to world, triangle.rs:92) */
     const uint32_t* prim_flags;    /* per original primitive, may be NULL */
-    const int32_t* prim_material;  /* per original primitive index into materials, may be NULL for accel-only scenes */
+    const int32_t* prim_material;  /* per original primitive index into materials; -1 = no material (Material "" / "none":
+                                    * the path integrator passes through the surface without counting a bounce, path.rs:146-150) */
     const int32_t* prim_light;     /* per original primitive index into lights or -1, may be NULL */
     int64_t n_prims;
     const b200pt_material* materials;
@@ -216,8 +217,16 @@ typedef struct b200pt_accel b200pt_accel; /* opaque: device-resident BVHAccel */
 typedef struct b200pt_loaded_scene b200pt_loaded_scene; /* opaque: a parsed scene file, owns the arrays of its scene_desc */
 typedef struct b200pt_scene b200pt_scene; /* opaque: device-resident Scene + PathIntegrator state */
 
-/* ---- library ---------------------------------------------------------- */
+/* ---- library ----------------------------------------------------------
+ * b200pt_init(device) checks that `device` is an sm_100 GPU, registers it and binds the CALLING THREAD to it; it may
+ * be called once per device of the box.  The first device initialised is the default of threads that never called
+ * b200pt_init / b200pt_set_device.  Creation calls (b200pt_accel_create*, b200pt_scene_create, the *_gpu / *_device
+ * BVH builders) work on the calling thread's device; every handle remembers the device it was created on and each
+ * call on it switches to that device, so one process - the reference is one process, bin/src/main.rs:29-85 - can
+ * drive all GPUs of the box (b200pt_render_multi). */
 int b200pt_init(int device);
+int b200pt_set_device(int device);   /* rebinds the calling thread to an initialised device */
+int b200pt_current_device(void);     /* the calling thread's device, -1 before any b200pt_init */
 const char* b200pt_last_error(void);
 int b200pt_version(void);
 /* number of SMs / L2 bytes of the bound device (0 before init) */
@@ -348,12 +357,38 @@ int b200pt_render_rows_device(b200pt_scene* s, int32_t row_begin, int32_t row_en
  * shards (interleaving balances sky and geometry); this call renders shard `shard` into a zero-initialised film of
  * the full window (device memory).  Summing the shards' films (NCCL all-reduce) gives the whole image. */
 int b200pt_render_shard_device(b200pt_scene* s, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream);
+/* ---- several GPUs, one process ---------------------------
+ * The reference renders from ONE process (bin/src/main.rs:29-85) and deals 16x16 tiles to its thread pool
+ * (core/src/integrator/sampler_integrator.rs:252-296).  b200pt_multi_create replicates the scene on every listed device
+ * (b200pt_init is called for each); b200pt_multi_render deals bands of `band_rows` pixel rows round-robin to the
+ * devices, renders them concurrently (one host thread per device) and gathers the bands on devices[0] over NVLink with
+ * NCCL: box-sized filters (radius <= 0.5 px) send each device's own bands into place (ncclSend / ncclRecv, 1 / n of the
+ * film per device, no reduction); wider filters overlap by their apron and are summed with one ncclReduce.  Without
+ * libnccl.so.2 (or with B200PT_GATHER=peer) the same transfers run as cudaMemcpyPeerAsync.  film_xyzw (HOST, 4 floats
+ * per pixel of the cropped window {X, Y, Z, weight}, may be NULL) receives the assembled film; results are identical
+ * to b200pt_render_rows on one device for box-sized filters (each sample is taken once, by exactly one device). */
+typedef struct b200pt_multi b200pt_multi;
+int b200pt_multi_create(const b200pt_scene_desc* desc, const int32_t* devices, int32_t n_devices, b200pt_multi** out);
+int b200pt_multi_render(b200pt_multi* m, int32_t band_rows, float* film_xyzw);
+/* rays of the last render summed over the devices, the slowest device's gather time, whether NCCL carried it */
+int b200pt_multi_info(const b200pt_multi* m, uint64_t rays[3], double* gather_ms, int32_t* uses_nccl);
+void* b200pt_multi_film_device(const b200pt_multi* m); /* devices[0]'s copy of the assembled film (device pointer) */
+void b200pt_multi_destroy(b200pt_multi* m);
+/* create + render + destroy */
+int b200pt_render_multi(const b200pt_scene_desc* desc, const int32_t* devices, int32_t n_devices, int32_t band_rows, float* film_xyzw);
+
 /* Film::write_image normalisation (film/mod.rs:356-417): XYZ+weight -> RGB,
  * 3 floats per pixel, HOST memory both sides. */
 int b200pt_film_resolve(const b200pt_film* film, const float* film_xyzw, float* rgb_out);
 /* Integrator::li for explicit (pixel x, pixel y, sample index) triples:
  * out = 3 floats (RGB radiance) per entry; rays_out (optional) = camera ray. */
 int b200pt_li_batch(b200pt_scene* s, const int32_t* pixel_sample, int64_t n, float* li_out, b200pt_ray* rays_out);
+/* Bytes of device memory the wave state of a render may take (ray queues, path state, the wave's samples: about 330
+ * bytes per path in flight).  The image is rendered in as many waves as that needs; the film keeps running sums
+ * between waves, so neither memory nor the result depends on resolution x samples per pixel or on the budget (the
+ * reference holds one FilmTile per thread, core/src/film/film_tile.rs:62-108).  0 restores the default: the
+ * environment variable B200PT_MEM_BUDGET (bytes, K / M / G suffix), else 60 % of the device's free memory. */
+int b200pt_scene_set_memory_budget(b200pt_scene* s, uint64_t bytes);
 /* Rays traced by the last render on this scene: [camera, closest-hit, shadow]. */
 int b200pt_scene_ray_counts(const b200pt_scene* s, uint64_t counts[3]);
 

@@ -1071,6 +1071,10 @@ inline RGB path_li(RenderScene& sc, Ray ray, Sampler& sampler) {
             }
         }
         if (!found || bounces >= sc.integ.max_depth) break;
+        if (sc.prim_material[isect.prim] < 0) {  // path.rs:141-150: no BSDF (Material "" / "none"): spawn_ray(ray.d), bounces not updated
+            ray = spawn_ray(isect, ray_d);
+            continue;
+        }
         BSDF bsdf = make_bsdf(sc, isect);
         if (bsdf.num_components(BSDF_ALL & ~BSDF_SPECULAR) > 0) {
             RGB ld = beta * uniform_sample_one_light(sc, isect, bsdf, sampler);

@@ -162,6 +162,16 @@ def lib():
     L.b200pt_film_resolve.argtypes = [C.POINTER(Film), vp, vp]
     L.b200pt_li_batch.argtypes = [vp, vp, i64, vp, vp]
     L.b200pt_scene_ray_counts.argtypes = [vp, vp]
+    L.b200pt_scene_set_memory_budget.argtypes = [vp, C.c_uint64]
+    L.b200pt_set_device.argtypes = [C.c_int]
+    L.b200pt_multi_create.argtypes = [C.POINTER(SceneDesc), vp, i32, C.POINTER(vp)]
+    L.b200pt_multi_render.argtypes = [vp, i32, vp]
+    L.b200pt_multi_info.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(i32)]
+    L.b200pt_multi_film_device.argtypes = [vp]
+    L.b200pt_multi_film_device.restype = vp
+    L.b200pt_multi_destroy.argtypes = [vp]
+    L.b200pt_multi_destroy.restype = None
+    L.b200pt_render_multi.argtypes = [C.POINTER(SceneDesc), vp, i32, i32, vp]
     _lib = L
     return L
 
@@ -175,12 +185,17 @@ _inited = None
 
 
 def init(device=0):
-    """b200pt_init: binds the sm_100 device.  Raises when there is none."""
+    """b200pt_init: binds the calling thread (and, the first time, the process default) to the sm_100 device.
+    Raises when there is none.  Handles remember their device, so init(other) later does not move existing ones."""
     global _inited
     if _inited == device:
         return
     _check(lib().b200pt_init(device), "b200pt_init")
     _inited = device
+
+
+def current_device():
+    return int(lib().b200pt_current_device())
 
 
 def _ptr(a):
@@ -427,4 +442,4 @@ def launch_count():
     return int(lib().b200pt_launch_count())
 
 
-from .scene import PathIntegrator, SceneDescription  # noqa: E402,F401
+from .scene import MultiGPURender, PathIntegrator, SceneDescription  # noqa: E402,F401

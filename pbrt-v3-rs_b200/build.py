@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200pt.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 
-SOURCES = ["b200pt_api.cu", "traverse_kernels.cu", "b200pt_scene.cu", "instancing.cu", "bvh_build.cu", "host_bvh.cpp", "host_hlbvh.cpp", "host_sampler.cpp", "host_envmap.cpp", "host_scene_loader.cpp"]
+SOURCES = ["b200pt_api.cu", "traverse_kernels.cu", "b200pt_scene.cu", "instancing.cu", "bvh_build.cu", "multi_gpu.cu", "host_bvh.cpp", "host_hlbvh.cpp", "host_sampler.cpp", "host_envmap.cpp", "host_scene_loader.cpp"]
 
 # -fmad=false + -ffp-contract=off: the reference (Rust f32) never fuses or
 # re-associates; traversal parity is bit-exact only without FMA contraction.

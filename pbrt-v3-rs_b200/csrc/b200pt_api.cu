@@ -10,10 +10,23 @@
 
 namespace b2 {
 std::atomic<int64_t> g_launches{0};
-int g_device = -1;
-int g_sm_count = 0;
-int64_t g_l2_bytes = 0;
+static const int kMaxDevices = 64;
+static DevCtx* g_ctx[kMaxDevices] = {};
+static std::mutex g_ctx_mu;
+static std::atomic<int> g_default_device{-1};  // the first device b200pt_init bound
+static thread_local int t_device = -1;         // b200pt_init / b200pt_set_device of this thread
 static thread_local std::string t_error;
+
+int current_device() { return t_device >= 0 ? t_device : g_default_device.load(); }
+DevCtx* dev_ctx(int device) { return device >= 0 && device < kMaxDevices ? g_ctx[device] : nullptr; }
+int use_device(int device) {
+    if (!dev_ctx(device)) {
+        b200pt_set_error("b200pt: device was not initialised (call b200pt_init(device) first; there is no CPU fallback)");
+        return B200PT_ERR_NO_DEVICE;
+    }
+    B2_CUDA(cudaSetDevice(device));
+    return B200PT_OK;
+}
 
 int cuda_fail(cudaError_t e, const char* what) {
     std::string m = std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e);
@@ -44,7 +57,7 @@ struct BatchScratch {
         return B200PT_OK;
     }
 };
-static BatchScratch g_scratch;
+static BatchScratch g_scratch[kMaxDevices];
 
 // Fourth float4 of a triangle record: uv0 - uv2, uv1 - uv2 (get_uvs, triangle.rs:384-394, 551-552).
 float4 record_duv(const float* uv6) {
@@ -57,6 +70,7 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
     a->n_nodes = n_nodes;
     a->n_prims = n_prims;
     std::memset(&a->dev, 0, sizeof(a->dev));
+    a->device = a->dev.device = current_device();
     a->dev.root_code = B2_EMPTY_ROOT;
     a->dev.n_nodes = (int)n_nodes;
     a->dev.n_prims = n_prims;
@@ -147,7 +161,8 @@ void accel_free_device(AccelImpl* a) {
 
 // Pipelined host-buffer batch (the e2e path): chunk i uses slot i % 3.
 template <class LaunchFn>
-static int run_host_batch(const void* rays, int64_t n, void* out, size_t out_elem, LaunchFn launch) {
+static int run_host_batch(int device, const void* rays, int64_t n, void* out, size_t out_elem, LaunchFn launch) {
+    BatchScratch& g_scratch = b2::g_scratch[device];
     std::lock_guard<std::mutex> g(g_scratch.mu);
     int rc = g_scratch.ensure();
     if (rc) return rc;
@@ -179,8 +194,9 @@ int b200pt_set_error(const char* msg) {
 }
 const char* b200pt_last_error(void) { return t_error.c_str(); }
 int b200pt_version(void) { return 100; }
-int b200pt_device_sm_count(void) { return g_sm_count; }
-int64_t b200pt_device_l2_bytes(void) { return g_l2_bytes; }
+int b200pt_device_sm_count(void) { DevCtx* c = dev_ctx(current_device()); return c ? c->sm_count : 0; }
+int64_t b200pt_device_l2_bytes(void) { DevCtx* c = dev_ctx(current_device()); return c ? c->l2_bytes : 0; }
+int b200pt_current_device(void) { return current_device(); }
 int64_t b200pt_launch_count(void) { return g_launches.load(); }
 
 int b200pt_init(int device) {
@@ -198,11 +214,28 @@ int b200pt_init(int device) {
         b200pt_set_error("b200pt_init: device is not sm_100 (kernels are built for sm_100a only)");
         return B200PT_ERR_NO_DEVICE;
     }
+    if (device >= kMaxDevices) { b200pt_set_error("b200pt_init: device index above the library's table"); return B200PT_ERR_INVALID; }
     B2_CUDA(cudaSetDevice(device));
-    g_device = device;
-    g_sm_count = prop.multiProcessorCount;
-    g_l2_bytes = prop.l2CacheSize;
+    {
+        std::lock_guard<std::mutex> g(g_ctx_mu);
+        if (!g_ctx[device]) {
+            DevCtx* c = new DevCtx();
+            c->device = device;
+            c->sm_count = prop.multiProcessorCount;
+            c->l2_bytes = prop.l2CacheSize;
+            g_ctx[device] = c;
+        }
+    }
+    int expected = -1;
+    g_default_device.compare_exchange_strong(expected, device);
+    t_device = device;
     return B200PT_OK;
+}
+
+int b200pt_set_device(int device) {
+    if (!dev_ctx(device)) { b200pt_set_error("b200pt_set_device: device was not initialised with b200pt_init"); return B200PT_ERR_NO_DEVICE; }
+    t_device = device;
+    return use_device(device);
 }
 
 int b200pt_envmap_prepare(const float* map_rgb, int32_t map_width, int32_t map_height, const float L[3], int32_t size4[4],
@@ -234,7 +267,6 @@ int b200pt_accel_create_uv(const b200pt_bvh_node* nodes, int64_t n_nodes, const 
         b200pt_set_error("b200pt_accel_create: invalid argument");
         return B200PT_ERR_INVALID;
     }
-    B2_CUDA(cudaSetDevice(g_device));
     b200pt_accel* a = new b200pt_accel();
     rc = accel_build_device(nodes, n_nodes, ordered_prims, tri_verts, prim_flags, n_prims, &a->impl, tri_uvs);
     if (rc) { accel_free_device(&a->impl); delete a; return rc; }
@@ -255,23 +287,23 @@ int b200pt_accel_world_bound(const b200pt_accel* a, float* bounds6) {
 }
 
 int b200pt_intersect_batch_device(const b200pt_accel* a, const void* d_rays, int64_t n, void* d_hits, void* stream, int variant) {
-    int rc = require_device();
-    if (rc) return rc;
     if (!a || n < 0 || (n > 0 && (!d_rays || !d_hits))) { b200pt_set_error("b200pt_intersect_batch_device: invalid argument"); return B200PT_ERR_INVALID; }
+    int rc = use_device(a->impl.device);
+    if (rc) return rc;
     return launch_intersect(a->impl.dev, d_rays, n, d_hits, (cudaStream_t)stream, variant);
 }
 
 int b200pt_occluded_batch_device(const b200pt_accel* a, const void* d_rays, int64_t n, void* d_occluded, void* stream, int variant) {
-    int rc = require_device();
-    if (rc) return rc;
     if (!a || n < 0 || (n > 0 && (!d_rays || !d_occluded))) { b200pt_set_error("b200pt_occluded_batch_device: invalid argument"); return B200PT_ERR_INVALID; }
+    int rc = use_device(a->impl.device);
+    if (rc) return rc;
     return launch_occluded(a->impl.dev, d_rays, n, d_occluded, (cudaStream_t)stream, variant);
 }
 
 int b200pt_count_work_device(const b200pt_accel* a, const void* d_rays, int64_t n, int any_hit, uint64_t totals[2], void* d_per_ray) {
-    int rc = require_device();
-    if (rc) return rc;
     if (!a || n < 0 || !totals || (n > 0 && !d_rays)) { b200pt_set_error("b200pt_count_work_device: invalid argument"); return B200PT_ERR_INVALID; }
+    int rc = use_device(a->impl.device);
+    if (rc) return rc;
     unsigned long long* d_tot = nullptr;
     B2_CUDA(cudaMalloc(&d_tot, 16));
     B2_CUDA(cudaMemset(d_tot, 0, 16));
@@ -284,22 +316,20 @@ int b200pt_count_work_device(const b200pt_accel* a, const void* d_rays, int64_t 
 }
 
 int b200pt_intersect_batch(const b200pt_accel* a, const b200pt_ray* rays, int64_t n, b200pt_hit* hits) {
-    int rc = require_device();
-    if (rc) return rc;
     if (!a || n < 0 || (n > 0 && (!rays || !hits))) { b200pt_set_error("b200pt_intersect_batch: invalid argument"); return B200PT_ERR_INVALID; }
-    B2_CUDA(cudaSetDevice(g_device));
+    int rc = use_device(a->impl.device);
+    if (rc) return rc;
     const DeviceAccel& A = a->impl.dev;
-    return run_host_batch(rays, n, hits, sizeof(b200pt_hit),
+    return run_host_batch(a->impl.device, rays, n, hits, sizeof(b200pt_hit),
                           [&](void* dr, int64_t m, void* dout, cudaStream_t s) { return launch_intersect(A, dr, m, dout, s, 0); });
 }
 
 int b200pt_occluded_batch(const b200pt_accel* a, const b200pt_ray* rays, int64_t n, uint8_t* occluded) {
-    int rc = require_device();
-    if (rc) return rc;
     if (!a || n < 0 || (n > 0 && (!rays || !occluded))) { b200pt_set_error("b200pt_occluded_batch: invalid argument"); return B200PT_ERR_INVALID; }
-    B2_CUDA(cudaSetDevice(g_device));
+    int rc = use_device(a->impl.device);
+    if (rc) return rc;
     const DeviceAccel& A = a->impl.dev;
-    return run_host_batch(rays, n, occluded, 1,
+    return run_host_batch(a->impl.device, rays, n, occluded, 1,
                           [&](void* dr, int64_t m, void* dout, cudaStream_t s) { return launch_occluded(A, dr, m, dout, s, 0); });
 }
 

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long
     W.beta[p] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     W.hidx[p] = idx;
     W.meta[p] = meta_pack(dim, live ? 0 : 255, 0);
-    if (p_film_out) p_film_out[g] = make_float2(pf.x, pf.y);
+    if (p_film_out) p_film_out[p] = make_float2(pf.x, pf.y);  // wave-local, like the radiance k_store_samples writes
     if (rays_out) { rays_out[2 * p] = make_float4(r.ox, r.oy, r.oz, r.tmax); rays_out[2 * p + 1] = make_float4(r.dx, r.dy, r.dz, r.time); }
 }
 
@@ -83,17 +83,21 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long
 // Counting sort with 5 bins (miss, matte, plastic, glass, metal): pass 1 classifies every slot and
 // histograms per block (one global atomic per bin per block), pass 2 scatters slot ids to their bin with
 // one warp-aggregated atomic per bin per warp.  Order inside a bin is arbitrary; results do not depend on it.
-__global__ void __launch_bounds__(256) k_bin_count(DeviceScene S, Wave W, int n_active) {
+// Queue sizes stay on the device (no host round trip per bounce): n_ptr, when set, points at the count a previous kernel
+// left in the wave's control blocks; the grid is sized for an upper bound and strides.
+B2_D int dev_count(const int* n_ptr, int n_host) { return n_ptr ? *n_ptr : n_host; }
+
+__global__ void __launch_bounds__(256) k_bin_count(DeviceScene S, Wave W, const int* __restrict__ n_ptr, int n_host) {
     __shared__ int hist[kBins];
+    const int n_active = dev_count(n_ptr, n_host);
     if (threadIdx.x < kBins) hist[threadIdx.x] = 0;
     __syncthreads();
-    int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < n_active) {
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_active; slot += gridDim.x * blockDim.x) {
         uint32_t prim = __float_as_uint(W.hit[slot].y);
         int key = 0;
         if (prim != 0xffffffffu) {
             int mat = __float_as_int(ldg4(S.prim_verts + 3ll * prim).w);
-            key = 1 + S.materials[mat].type;
+            key = mat < 0 ? kBinNull : 1 + S.materials[mat].type;
         }
         W.key[slot] = (uint8_t)key;
         atomicAdd(&hist[key], 1);
@@ -101,35 +105,39 @@ __global__ void __launch_bounds__(256) k_bin_count(DeviceScene S, Wave W, int n_
     __syncthreads();
     if (threadIdx.x < kBins && hist[threadIdx.x]) atomicAdd(&W.counters[8 + threadIdx.x], hist[threadIdx.x]);
 }
-__global__ void __launch_bounds__(256) k_bin_scatter(Wave W, int n_active) {
+__global__ void __launch_bounds__(256) k_bin_scatter(Wave W, const int* __restrict__ n_ptr, int n_host) {
     __shared__ int wcount[8][kBins];  // per warp: count, then start offset inside the bin
-    int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    int key = slot < n_active ? (int)W.key[slot] : -1;
-    int base = 0;
-    for (int k = 0; k < kBins; ++k) if (k < key) base += W.counters[8 + k];
+    const int n_active = dev_count(n_ptr, n_host);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    unsigned mine = 0;
-    for (int k = 0; k < kBins; ++k) {
-        unsigned m = __ballot_sync(0xffffffffu, key == k);
-        if (key == k) mine = m;
-        if (lane == 0) wcount[warp][k] = __popc(m);
+    int bin_base[kBins];
+    { int run = 0; for (int k = 0; k < kBins; ++k) { bin_base[k] = run; run += W.counters[8 + k]; } }
+    for (int first = blockIdx.x * blockDim.x; first < n_active; first += gridDim.x * blockDim.x) {  // block-uniform trip count
+        const int slot = first + threadIdx.x;
+        const int key = slot < n_active ? (int)W.key[slot] : -1;
+        unsigned mine = 0;
+        for (int k = 0; k < kBins; ++k) {
+            unsigned m = __ballot_sync(0xffffffffu, key == k);
+            if (key == k) mine = m;
+            if (lane == 0) wcount[warp][k] = __popc(m);
+        }
+        __syncthreads();
+        if (threadIdx.x < kBins) {  // one global atomic per bin per block, then an exclusive scan over the block's warps
+            int total = 0;
+            for (int w = 0; w < 8; ++w) total += wcount[w][threadIdx.x];
+            int run = total ? atomicAdd(&W.counters[16 + threadIdx.x], total) : 0;
+            for (int w = 0; w < 8; ++w) { int c = wcount[w][threadIdx.x]; wcount[w][threadIdx.x] = run; run += c; }
+        }
+        __syncthreads();
+        if (key >= 0) W.sorted[bin_base[key] + wcount[warp][key] + __popc(mine & ((1u << lane) - 1u))] = slot;
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x < kBins) {  // one global atomic per bin per block, then an exclusive scan over the block's warps
-        int total = 0;
-        for (int w = 0; w < 8; ++w) total += wcount[w][threadIdx.x];
-        int run = total ? atomicAdd(&W.counters[16 + threadIdx.x], total) : 0;
-        for (int w = 0; w < 8; ++w) { int c = wcount[w][threadIdx.x]; wcount[w][threadIdx.x] = run; run += c; }
-    }
-    __syncthreads();
-    if (key >= 0) W.sorted[base + wcount[warp][key] + __popc(mine & ((1u << lane) - 1u))] = slot;
 }
 
 // ---- SpatialLightDistribution (core/src/light_distrib/spatial.rs) -------------------------------------------------
 // compute_distribution(), spatial.rs:91-137: one thread per (queued voxel, light) walks the 128 Halton points in order
-__global__ void __launch_bounds__(128) k_voxel_contrib(DeviceScene S, int n_work) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n_work * S.n_lights) return;
+__global__ void __launch_bounds__(128) k_voxel_contrib(DeviceScene S, const int* __restrict__ n_work_ptr) {
+    const long long total = (long long)*n_work_ptr * S.n_lights;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int w = (int)(t / S.n_lights), j = (int)(t % S.n_lights);
     const int v = S.vox_work[w];
     const int pz = v % S.n_voxels[2], py = (v / S.n_voxels[2]) % S.n_voxels[1], px = v / (S.n_voxels[2] * S.n_voxels[1]);
@@ -153,15 +161,16 @@ __global__ void __launch_bounds__(128) k_voxel_contrib(DeviceScene S, int n_work
         const LightSample ls = sample_light(S, light, sh, u);
         if (ls.valid && ls.pdf > 0.0f) contrib += lum_y(ls.Li) / ls.pdf;
     }
-    S.vox_table[(long long)v * (2 * S.n_lights + 2) + j] = contrib;
+    S.vox_table[(long long)S.vox_row[v] * (2 * S.n_lights + 2) + j] = contrib;
+    }
 }
 
 // spatial.rs:139-160 + Distribution1D::new (distribution_1d.rs:22-48): one thread per queued voxel, lights in order
-__global__ void __launch_bounds__(128) k_voxel_finish(DeviceScene S, int n_work) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_work) return;
+__global__ void __launch_bounds__(128) k_voxel_finish(DeviceScene S, const int* __restrict__ n_work_ptr) {
+    const int n_work = *n_work_ptr;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
     const int v = S.vox_work[w], n = S.n_lights;
-    float* func = S.vox_table + (long long)v * (2 * n + 2);
+    float* func = S.vox_table + (long long)S.vox_row[v] * (2 * n + 2);
     float* cdf = func + n;
     float sum = 0.0f;
     for (int j = 0; j < n; ++j) sum += func[j];
@@ -176,16 +185,18 @@ __global__ void __launch_bounds__(128) k_voxel_finish(DeviceScene S, int n_work)
     func[2 * n + 1] = func_int;
     __threadfence();
     S.vox_state[v] = 2;
+    }
 }
 
 // ---- K4: shade --------------------------------------------------------------------------------
-template <int kMinBlocks>
-__global__ void __launch_bounds__(128, kMinBlocks) k_shade(DeviceScene S, Wave W, int cur, int n_active, const int* __restrict__ order) {
-    int i_sorted = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i_sorted >= n_active) return;
-    const int slot = order[i_sorted];
+// One path vertex (path.rs:117-280).  KM is the compile-time lobe mask of the material class the launch covers (the
+// queue is sorted by class first, so a launch only carries the BSDF code its class can reach); kMiss = the slot holds
+// an escaped ray, kNull = the hit primitive has no material (path.rs:146-150: the ray is re-spawned, nothing is counted).
+enum { kShadeHit = 0, kShadeMiss = 1, kShadeNull = 2 };
+template <uint32_t KM, int kMode>
+B2_D void shade_vertex(const DeviceScene& S, const Wave& W, int cur, int slot, bool may_park) {
     const int pid = W.qpid[cur][slot];
-    const float4 r0 = W.ray[cur][2 * slot], r1 = W.ray[cur][2 * slot + 1];
+    const float4 r1 = W.ray[cur][2 * slot + 1];
     const float4 hit = W.hit[slot];
     const float hb2 = W.hit_b2[slot];
     const V3 ray_d = mk(r1.x, r1.y, r1.z);
@@ -199,27 +210,35 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_shade(DeviceScene S, Wave W
     float eta_scale = bw.w;
     const unsigned long long hidx = W.hidx[pid];
     const uint32_t prim = __float_as_uint(hit.y);
-    const bool found = prim != 0xffffffffu;
-    (void)r0;
+    const bool found = kMode == kShadeMiss ? false : (KM == KM_ALL ? prim != 0xffffffffu : true);
 
-    HitCtx hc;
-    surface_at(S, W, slot, prim, hit, hb2, ray_d, found, &hc);
-    const SurfHit& sh = hc.sh;
-    const V3 hit_wo = hc.wo;
-    const int mat = hc.mat, alight = hc.alight;
-    // path.rs:123-134: emitted light at the vertex / from the environment
-    if (bounces == 0 || specular_bounce) {
-        if (found) {
-            if (alight >= 0) L = L + beta * area_l(S.lights[alight], sh.n, -ray_d);
-        } else {
+    if (kMode == kShadeMiss || !found) {  // path.rs:123-137: light from the environment, then the path ends
+        if (bounces == 0 || specular_bounce) {
             for (int i = 0; i < S.n_infinite; ++i) {
                 const DLight& il = S.lights[S.infinite_lights[i]];
                 L = L + beta * infinite_le(il, S.inf_distr[il.inf_slot], ray_d);
             }
+            W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
         }
+        return;
     }
-    if (!found || bounces >= S.max_depth) {  // path.rs:137
+    HitCtx hc;
+    surface_at(S, W, slot, prim, hit, hb2, ray_d, true, &hc);
+    const SurfHit& sh = hc.sh;
+    const V3 hit_wo = hc.wo;
+    const int mat = hc.mat, alight = hc.alight;
+    // path.rs:123-134: emitted light at the vertex
+    if ((bounces == 0 || specular_bounce) && alight >= 0) L = L + beta * area_l(S.lights[alight], sh.n, -ray_d);
+    if (bounces >= S.max_depth) {  // path.rs:137
         W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
+        return;
+    }
+    if (kMode == kShadeNull || (KM == KM_ALL && mat < 0)) {
+        // path.rs:146-150: no BSDF (Material "" / "none"): isect.spawn_ray(ray.d), `continue` without counting a bounce
+        W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
+        const int ns = atomicAdd(&W.counters[0], 1);
+        store_ray(W.ray[cur ^ 1], ns, offset_ray_origin(sh.p, sh.p_error, sh.n, ray_d), ray_d, __int_as_float(0x7f800000), time);
+        W.qpid[cur ^ 1][ns] = pid;
         return;
     }
     // BSDF::new frame (bsdf.rs:100-120)
@@ -239,13 +258,18 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_shade(DeviceScene S, Wave W
         if (S.spatial) {
             const int v = spatial_voxel(S, sh.p);
             if (ld_volatile_int(S.vox_state + v) != 2) {
-                // first touch of this voxel: queue it, park the slot; the host fills the queued voxels and re-runs this
-                // kernel on the parked slots (nothing of this path has been written yet)
-                if (atomicCAS(S.vox_state + v, 0, 1) == 0) S.vox_work[atomicAdd(&W.counters[24], 1)] = v;
-                W.deferred[atomicAdd(&W.counters[25], 1)] = slot;
+                // First touch of this voxel: the thread that wins the CAS takes a table row and queues the voxel; the slot is
+                // parked and shaded again, by a second launch of this kernel, once the voxel kernels have run (nothing of
+                // this path has been written yet).  A full row pool is reported to the host at the end of the wave.
+                if (atomicCAS(S.vox_state + v, 0, 1) == 0) {
+                    const int row = atomicAdd(S.vox_pool_next, 1);
+                    if (row < S.vox_pool_cap) { S.vox_row[v] = row; S.vox_work[atomicAdd(&W.counters[24], 1)] = v; }
+                    else atomicExch(&W.counters[26], 1);
+                }
+                if (may_park) W.deferred[atomicAdd(&W.counters[25], 1)] = slot;  // a parked slot whose voxel is still missing in the second pass (row pool exhausted) is dropped
                 return;
             }
-            const float* row = S.vox_table + (long long)v * (2 * S.n_lights + 2);
+            const float* row = S.vox_table + (long long)S.vox_row[v] * (2 * S.n_lights + 2);
             lfunc = row; lcdf = row + S.n_lights; lfunc_int = row[2 * S.n_lights + 1];
         }
         float u_pick = smp_1d(S, hidx, dim);
@@ -257,7 +281,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_shade(DeviceScene S, Wave W
             P2 u_scatter = smp_2d(S, hidx, dim);
             const DLight& light = S.lights[ln];
             // ---- estimate_direct (common.rs:146-299): both halves, rays still to be traced ----
-            const DirectEst de = estimate_direct_rays(S, light, sh, hit_wo, bsdf, u_light, u_scatter);
+            const DirectEst de = estimate_direct_rays<KM>(S, light, sh, hit_wo, bsdf, u_light, u_scatter);
             const RGB ld_light = de.ld_light, mis_f = de.mis_f;
             const float mis_w = de.mis_w, mis_pdf = de.mis_pdf;
             int shadow_slot = -1, mis_slot = -1;
@@ -283,7 +307,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_shade(DeviceScene S, Wave W
     // path.rs:175-206: sample the BSDF for the next direction
     P2 u = smp_2d(S, hidx, dim);
     V3 wo = -ray_d;
-    BxDFSample bs = bsdf_sample_f(bsdf, wo, u, BSDF_ALL);
+    BxDFSample bs = bsdf_sample_f<KM>(bsdf, wo, u, BSDF_ALL);
     if (is_black(bs.f) || bs.pdf == 0.0f) {
         W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
         return;
@@ -312,6 +336,25 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_shade(DeviceScene S, Wave W
     int ns = atomicAdd(&W.counters[0], 1);
     store_ray(W.ray[cur ^ 1], ns, next_o, bs.wi, __int_as_float(0x7f800000), time);
     W.qpid[cur ^ 1][ns] = pid;
+}
+
+// The slots of the sorted queue that belong to bins [bin_lo, bin_hi) (bin_lo >= 0), or the slots the first pass parked
+// for the spatial light table (bin_lo < 0).  Counts are read from the wave's control block; the grid strides.
+template <uint32_t KM, int kMode, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) k_shade(DeviceScene S, Wave W, int cur, int bin_lo, int bin_hi) {
+    const int* order;
+    int count = 0;
+    if (bin_lo >= 0) {
+        int start = 0;
+        for (int k = 0; k < bin_lo; ++k) start += W.counters[8 + k];
+        for (int k = bin_lo; k < bin_hi; ++k) count += W.counters[8 + k];
+        order = W.sorted + start;
+    } else {
+        order = W.deferred;
+        count = W.counters[25];
+    }
+    const bool may_park = bin_lo >= 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) shade_vertex<KM, kMode>(S, W, cur, order[i], may_park);
 }
 
 // ---- (0,2)-sequence prepass: one thread per reference tile replays the tile sampler's PCG32 stream ------------
@@ -361,9 +404,9 @@ __global__ void __launch_bounds__(64) k_zerotwo_tiles(int sb0, int sb1, int sb2,
 }
 
 // ---- K4': resolve pending direct lighting ------------------------------------------------------
-__global__ void __launch_bounds__(256) k_resolve(DeviceScene S, Wave W, int n_pend) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pend) return;
+__global__ void __launch_bounds__(256) k_resolve(DeviceScene S, Wave W) {
+    const int n_pend = W.counters[3];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pend; i += gridDim.x * blockDim.x) {
     const int pid = W.pend_q[i];
     float4 a = W.pend_a[pid], b = W.pend_b[pid], c = W.pend_c[pid];
     int4 d = W.pend_d[pid];
@@ -388,6 +431,25 @@ __global__ void __launch_bounds__(256) k_resolve(DeviceScene S, Wave W, int n_pe
     RGB add = rgb(c.x, c.y, c.z) * (ld / a.w);  // path.rs:165: beta * (estimate / light_pdf)
     float4 Lw = W.L[pid];
     W.L[pid] = make_float4(Lw.x + add.r, Lw.y + add.g, Lw.z + add.b, Lw.w);
+    }
+}
+
+// Wave bookkeeping kept on the device: the control blocks are cleared and the first queue size set when a wave starts;
+// when it ends the rays it traced are added to the scene's totals (read once, at the end of the render).
+__global__ void k_wave_begin(int* ctl, int n_ints, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ints; i += gridDim.x * blockDim.x) ctl[i] = i == 0 ? n : 0;
+}
+__global__ void k_wave_end(const int* ctl, int n_blocks, int n_camera, unsigned long long* totals) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long closest = 0, shadow = 0, flags = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        const int* c = ctl + b * kCtl;
+        closest += (unsigned long long)c[0];                  // the queue this block's counts opened (block 0: the camera rays)
+        if (b > 0) { closest += (unsigned long long)c[2]; shadow += (unsigned long long)c[1]; }
+        if (c[26]) flags |= 1ull;
+    }
+    if (ctl[(n_blocks - 1) * kCtl] != 0) flags |= 2ull;      // paths still alive after the last iteration that was launched
+    totals[0] += (unsigned long long)n_camera; totals[1] += closest; totals[2] += shadow; totals[3] |= flags;
 }
 
 // Copies the wave's final radiances into the per-sample store (sanitised, sampler_integrator.rs:374-401).
@@ -409,28 +471,31 @@ struct DFilm {
     int sb[4];
     int tile;  // reference tile size (16): a sample only reaches pixels of its own tile's pixel bounds
 };
-// One thread per film pixel of the rendered rows: gathers, in pixel-major then sample order, every
-// sample of this shard whose filter window covers the pixel (film_tile.rs:62-108).
+// One thread per film pixel of rows [y_begin, y_end): continues the pixel's running sums with every sample of the
+// wave [first, first + n) (pixel-major sample indices of this shard) whose filter window covers the pixel, in
+// pixel-major then sample order (film_tile.rs:62-108).  A pixel's samples reach it in ascending sample index whatever
+// the wave boundaries are, so the sums - kept in `acc` between waves - do not depend on how the render was cut into
+// waves (tests: wave / pass splitting leaves every bit of the image unchanged).
 __global__ void __launch_bounds__(128) k_film(DFilm F, const float* __restrict__ table, const float4* __restrict__ sample_L,
-                                              const float2* __restrict__ p_film, int spp, const int* __restrict__ row_index,
-                                              float4* __restrict__ film) {
+                                              const float2* __restrict__ p_film, long long first, int n, int spp, const int* __restrict__ row_index,
+                                              int y_begin, int y_end, float4* __restrict__ acc) {
     int w = F.crop[2] - F.crop[0];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w * (F.crop[3] - F.crop[1])) return;
-    int x = F.crop[0] + i % w, y = F.crop[1] + i / w;
+    if (i >= w * (y_end - y_begin)) return;
+    int x = F.crop[0] + i % w, y = y_begin + i / w;
     int sw = F.sb[2] - F.sb[0];
     // candidate source pixels: those whose sample positions can reach (x, y)
     int qx0 = (int)floorf((float)x + 0.5f - F.rx) - 1, qx1 = (int)ceilf((float)x + 0.5f + F.rx) + 1;
     int qy0 = (int)floorf((float)y + 0.5f - F.ry) - 1, qy1 = (int)ceilf((float)y + 0.5f + F.ry) + 1;
     qx0 = max(qx0, F.sb[0]); qx1 = min(qx1, F.sb[2]);
     qy0 = max(qy0, F.sb[1]); qy1 = min(qy1, F.sb[3]);
+    const long long o = (long long)(y - F.crop[1]) * w + (x - F.crop[0]);
     RGB sum = rgb1(0.0f);
     float wsum = 0.0f;
-    bool any = false;
+    bool loaded = false;
     for (int qy = qy0; qy < qy1; ++qy) {
         const int krow = row_index[qy - F.sb[1]];  // position of sample row qy among this shard's rows, -1 = not ours
         if (krow < 0) continue;
-        any = true;
         for (int qx = qx0; qx < qx1; ++qx) {
             // pixel bounds of the reference tile that owns sample pixel (qx, qy) (film/mod.rs:182-198)
             int tx0 = F.sb[0] + ((qx - F.sb[0]) / F.tile) * F.tile, ty0 = F.sb[1] + ((qy - F.sb[1]) / F.tile) * F.tile;
@@ -438,17 +503,21 @@ __global__ void __launch_bounds__(128) k_film(DFilm F, const float* __restrict__
             int bx0 = max((int)ceilf((float)tx0 - 0.5f - F.rx), F.crop[0]), by0 = max((int)ceilf((float)ty0 - 0.5f - F.ry), F.crop[1]);
             int bx1 = min((int)floorf((float)tx1 - 0.5f + F.rx) + 1, F.crop[2]), by1 = min((int)floorf((float)ty1 - 0.5f + F.ry) + 1, F.crop[3]);
             if (x < bx0 || x >= bx1 || y < by0 || y >= by1) continue;
-            long long base = ((long long)krow * sw + (qx - F.sb[0])) * spp;
-            for (int s = 0; s < spp; ++s) {
+            const long long base = ((long long)krow * sw + (qx - F.sb[0])) * spp;
+            // the part of this source pixel's samples that lies in the wave
+            const int s_lo = (int)max(0ll, first - base), s_hi = (int)min((long long)spp, first + n - base);
+            for (int s = s_lo; s < s_hi; ++s) {
                 // the 8-byte position first: with the box filter 8 of the 9 candidate pixels fail the window test, and
                 // their 16-byte radiance is then never fetched
-                float2 pf = p_film[base + s];
+                const long long k = base + s - first;
+                float2 pf = p_film[k];
                 float dx = pf.x - 0.5f, dy = pf.y - 0.5f;
                 int p0x = (int)ceilf(dx - F.rx), p0y = (int)ceilf(dy - F.ry);
                 int p1x = (int)floorf(dx + F.rx) + 1, p1y = (int)floorf(dy + F.ry) + 1;
                 if (x < p0x || x >= p1x || y < p0y || y >= p1y) continue;
-                float4 l = sample_L[base + s];
+                float4 l = sample_L[k];
                 if (l.w == 0.0f) continue;  // pixel outside the integrator's pixel bounds
+                if (!loaded) { const float4 a = acc[o]; sum = rgb(a.x, a.y, a.z); wsum = a.w; loaded = true; }
                 RGB c = rgb(l.x, l.y, l.z);
                 float ly = lum_y(c);
                 if (ly > F.max_lum) c = c * F.max_lum / ly;
@@ -460,22 +529,31 @@ __global__ void __launch_bounds__(128) k_film(DFilm F, const float* __restrict__
             }
         }
     }
-    if (!any) return;  // no sample row of this shard reaches the pixel: leave the zero written by the memset
-    // Film::merge_film_tile: tile RGB -> XYZ (film/mod.rs:243-248); accumulated into the shard's film
-    float X = 0.412453f * sum.r + 0.357580f * sum.g + 0.180423f * sum.b;
-    float Y = 0.212671f * sum.r + 0.715160f * sum.g + 0.072169f * sum.b;
-    float Z = 0.019334f * sum.r + 0.119193f * sum.g + 0.950227f * sum.b;
-    long long o = (long long)(y - F.crop[1]) * w + (x - F.crop[0]);
-    film[o] = make_float4(X, Y, Z, wsum);
+    if (loaded) acc[o] = make_float4(sum.r, sum.g, sum.b, wsum);
+}
+
+// Film::merge_film_tile: RGB sums -> XYZ (film/mod.rs:243-248), written to the shard's film {X, Y, Z, weight sum}.
+__global__ void __launch_bounds__(256) k_film_finish(const float4* __restrict__ acc, long long n_pix, float4* __restrict__ film) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_pix) return;
+    const float4 a = acc[o];
+    float X = 0.412453f * a.x + 0.357580f * a.y + 0.180423f * a.z;
+    float Y = 0.212671f * a.x + 0.715160f * a.y + 0.072169f * a.z;
+    float Z = 0.019334f * a.x + 0.119193f * a.y + 0.950227f * a.z;
+    film[o] = make_float4(X, Y, Z, a.w);
 }
 
 // ------------------------------------------------------------------------------------------------
 struct SceneImpl {
+    int device = -1;          // CUDA device the scene lives on; every entry point switches to it
     AccelImpl accel;
     Accel2Impl accel2;        // two-level scenes (instancing)
     bool instanced = false;
     bool whitted = false;     // a recursive SamplerIntegrator (Whitted / DirectLighting) instead of PathIntegrator
     int tree_mode = 0;        // kTreeWhitted / kTreeDirectAll / kTreeDirectOne
+    bool has_null_material = false;  // some primitive has no material: paths pass through it without counting a bounce
+    uint32_t material_classes = 0;   // bit t = some material of type t exists (which shade kernels a bounce launches)
+    int n_point_lights = 0;          // delta lights: estimate_direct traces no BSDF-sampled ray for them
     DeviceScene dev;
     b200pt_film film;
     b200pt_sampler sampler;
@@ -484,18 +562,25 @@ struct SceneImpl {
     Wave wave;
     int wave_cap = 0;
     std::vector<void*> wave_ptrs;
+    int* d_ctl = nullptr;                  // (kSegIters + 1) control blocks of the current wave segment
+    unsigned long long* d_totals = nullptr;  // camera / closest-hit / shadow rays of the render, error flags
+    int* h_pinned = nullptr;               // pinned host words for the few read-backs that remain
+    size_t mem_budget = 0;                 // bytes the wave state may take (0: B200PT_MEM_BUDGET, else a share of the free memory)
     // streams / events that let a bounce's shadow, MIS and next closest-hit traversals overlap (run_wave)
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_shade = nullptr;
     bool aux_ready = false, overlap = true;
     uint64_t rays[3] = {0, 0, 0};
     uint64_t voxels_built = 0;  // SpatialLightDistribution voxels computed so far
     std::mutex mu;
     int sample_bounds[4];
-    // per-sample store and film staging, grown on demand and kept across renders
+    // the wave's samples (radiance + film position), the running film sums, and film staging; grown on demand, kept across renders
     float4* d_sample_L = nullptr;
     float2* d_sample_pf = nullptr;
     long long sample_cap = 0;
+    float4* d_acc = nullptr;
+    size_t acc_cap = 0;
     float4* d_film = nullptr;
     size_t film_cap = 0;
     // (0,2)-sequence tables of the current shard
@@ -507,20 +592,59 @@ struct SceneImpl {
     int* d_row_index = nullptr;  // sample row -> position in d_rows, -1 = not owned
 };
 
-// Paths per wave.  Every bounce of a wave costs three traversal launches (each a persistent kernel with its own tail),
-// a counter read-back and a few small kernels; measured on C3 (1080p @ 64 spp = 1.3e8 paths): 256 ms per image with
-// 2^22-path waves, 203 ms with 2^24, 186 ms with 2^26 (profiles/r1_wave_size.txt).  The wave is therefore as large as
-// the render needs, up to kWaveCapMax paths (~330 B of wave state each: 22 GB at 2^26).  B200PT_WAVE_LOG2 overrides.
+// Bytes of wave state per path (what wave_alloc takes for `cap` paths, plus the wave's sample store).
+static size_t wave_bytes_per_path(const SceneImpl* s) {
+    const size_t nl = (size_t)std::max(1, s->dev.n_lights);
+    const size_t sh_mul = (s->whitted && s->tree_mode != kTreeDirectOne) ? nl : 1;
+    const size_t mis_mul = (s->whitted && s->tree_mode != kTreeWhitted) ? sh_mul : 1;
+    size_t b = 2 * (32 + 4) + 16 + 4 + 4;               // ray queues + path ids, hit, b2, instance
+    b += sh_mul * (32 + 1) + mis_mul * (32 + 16 + 4);   // shadow / MIS queues
+    b += 16 + 16 + 8 + 4 + 4 * 16 + 4 + 1 + 4;          // L, beta, sample index, meta, pending records, pending list, key, sorted
+    if (s->dev.spatial) b += 4;
+    if (s->whitted) {
+        b += sh_mul * 16 + (size_t)std::max(1, s->dev.max_depth) * 48;
+        if (s->tree_mode != kTreeWhitted) b += sh_mul * (16 + 8);
+    }
+    return b + 24;                                       // per-sample radiance + film position
+}
+
+// Paths per wave.  Every bounce of a wave costs three traversal launches (each a persistent kernel with its own tail) and
+// a few small kernels; measured on C3 (1080p @ 64 spp = 1.3e8 paths): 256 ms per image with 2^22-path waves, 203 ms with
+// 2^24, 186 ms with 2^26 (profiles/r1_wave_size.txt).  The wave is therefore as large as the render needs, up to
+// kWaveCapMax paths, within the memory budget: b200pt_scene_set_memory_budget / B200PT_MEM_BUDGET (bytes; K / M / G
+// suffix), default 60 % of what is free on the device.  Memory no longer grows with resolution x samples per pixel: the
+// film keeps running sums between waves (k_film).  B200PT_WAVE_LOG2 overrides the cap (A/B knob).
 static const long long kWaveCapMax = 1ll << 26;
+static size_t env_bytes(const char* name) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return 0;
+    char* end = nullptr;
+    double v = std::strtod(e, &end);
+    if (end && (*end == 'k' || *end == 'K')) v *= 1024.0;
+    else if (end && (*end == 'm' || *end == 'M')) v *= 1024.0 * 1024.0;
+    else if (end && (*end == 'g' || *end == 'G')) v *= 1024.0 * 1024.0 * 1024.0;
+    return v > 0.0 ? (size_t)v : 0;
+}
 static int wave_cap_for(const SceneImpl* s, long long n_paths) {
     long long cap = kWaveCapMax;
     if (const char* e = std::getenv("B200PT_WAVE_LOG2")) {
         int v = std::atoi(e);
-        if (v >= 16 && v <= 27) cap = 1ll << v;
+        if (v >= 10 && v <= 27) cap = 1ll << v;
     }
-    long long need = 1ll << 20;
+    long long need = 1ll << 14;
     while (need < n_paths && need < cap) need <<= 1;
     cap = std::min(cap, need);
+    size_t budget = s->mem_budget ? s->mem_budget : env_bytes("B200PT_MEM_BUDGET");
+    if (!budget) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            budget = (size_t)(0.6 * (double)(free_b + (size_t)s->wave_cap * wave_bytes_per_path(s)));  // what this scene's wave already holds is reusable
+        else cudaGetLastError();
+    }
+    if (budget) {
+        const size_t per_path = wave_bytes_per_path(s);
+        while (cap > 1024 && (size_t)cap * per_path > budget) cap >>= 1;
+    }
     // Whitted / DirectLighting "all" test one shadow ray per light and node: keep paths x lights within 2^26 slots
     if (s->whitted && s->tree_mode != kTreeDirectOne) cap = std::min(cap, std::max<long long>((1ll << 26) / std::max(1, s->dev.n_lights), 1024));
     return (int)cap;
@@ -670,7 +794,11 @@ struct HostDistr1D {  // core/src/sampling/distribution_1d.rs:22-48
 
 static int wave_alloc(SceneImpl* s, int cap) {
     Wave& W = s->wave;
-    if (s->wave_cap >= cap) return B200PT_OK;
+    if (!s->d_totals) {
+        B2_CUDA(cudaMalloc(&s->d_totals, 4 * sizeof(unsigned long long)));
+        B2_CUDA(cudaMallocHost(&s->h_pinned, 64 * sizeof(int)));
+    }
+    if (s->wave_cap == cap) return B200PT_OK;  // shrinks too: a smaller budget must be honoured
     for (void* p : s->wave_ptrs) cudaFree(p);  // grow: a later render needs a larger wave
     s->wave_ptrs.clear();
     s->wave_cap = 0;
@@ -712,7 +840,8 @@ static int wave_alloc(SceneImpl* s, int cap) {
     if ((rc = dev_alloc(s, (size_t)cap, &W.pend_c))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.pend_d))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.pend_q))) return rc;
-    if ((rc = dev_alloc(s, (size_t)32, &W.counters))) return rc;
+    if ((rc = dev_alloc(s, (size_t)(kSegIters + 1) * kCtl, &s->d_ctl))) return rc;
+    W.counters = s->d_ctl;
     if ((rc = dev_alloc(s, (size_t)cap, &W.key))) return rc;
     if ((rc = dev_alloc(s, (size_t)cap, &W.sorted))) return rc;
     W.deferred = nullptr;
@@ -721,27 +850,64 @@ static int wave_alloc(SceneImpl* s, int cap) {
     return B200PT_OK;
 }
 
-// k_shade is compiled for several occupancy targets (register caps); B200PT_SHADE_BLOCKS picks one (A/B knob).
-static void launch_shade(SceneImpl* s, int cur, int n, const int* order, cudaStream_t st) {
-    static const int blocks = [] { const char* e = std::getenv("B200PT_SHADE_BLOCKS"); int v = e ? std::atoi(e) : 5; return (v >= 4 && v <= 6) ? v : 5; }();
-    const int g = (n + 127) / 128;
-    if (blocks == 5) k_shade<5><<<g, 128, 0, st>>>(s->dev, s->wave, cur, n, order);
-    else if (blocks == 6) k_shade<6><<<g, 128, 0, st>>>(s->dev, s->wave, cur, n, order);
-    else k_shade<4><<<g, 128, 0, st>>>(s->dev, s->wave, cur, n, order);
+// The shade stage of one bounce: one launch per material class present in the scene over its range of the sorted queue
+// (bin 0 = escaped rays), each compiled with only the lobes that class can produce.  Register budgets (CTAs per SM) per
+// class from -Xptxas -v / ncu: profiles/r2_shade_split.txt.
+static const uint32_t kKmMatte = (1u << BX_LAMBERT) | (1u << BX_OREN_NAYAR);
+static const uint32_t kKmPlastic = (1u << BX_LAMBERT) | (1u << BX_MF_REFL) | KM_DIEL;
+static const uint32_t kKmGlass = (1u << BX_FRESNEL_SPECULAR) | (1u << BX_MF_REFL) | (1u << BX_MF_TRANS) | KM_DIEL;
+static const uint32_t kKmMetal = (1u << BX_MF_REFL) | KM_COND;
+static int shade_grid(const SceneImpl* s, int n_upper, int per_sm) {
+    const DevCtx* c = dev_ctx(s->device);
+    return std::max(1, std::min((n_upper + 127) / 128, (c ? c->sm_count : 148) * per_sm));
+}
+template <uint32_t KM>
+static void launch_shade_class(SceneImpl* s, const Wave& W, int cur, int n_upper, int bin, int blocks, cudaStream_t st) {
+    switch (blocks) {
+        case 3: k_shade<KM, kShadeHit, 3><<<shade_grid(s, n_upper, 12), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
+        case 4: k_shade<KM, kShadeHit, 4><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
+        case 6: k_shade<KM, kShadeHit, 6><<<shade_grid(s, n_upper, 24), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
+        default: k_shade<KM, kShadeHit, 5><<<shade_grid(s, n_upper, 20), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
+    }
+}
+static void launch_shade(SceneImpl* s, const Wave& W, int cur, int n_upper, cudaStream_t st) {
+    static const bool split = [] { const char* e = std::getenv("B200PT_SHADE_SPLIT"); return !(e && e[0] == '0'); }();
+    if (!split) {  // A/B: one generic kernel over the whole sorted queue
+        k_shade<KM_ALL, kShadeHit, 5><<<shade_grid(s, n_upper, 20), 128, 0, st>>>(s->dev, W, cur, 0, kBins);
+        g_launches.fetch_add(1);
+        return;
+    }
+    // CTAs per SM per class: 4 = 118-128 registers, no spills (5 spills 120-212 B, 6 spills 230-400 B; C3: 4444 180 ms, 4555 190 ms,
+    // 5555 191 ms, 3333 193 ms).  A/B knob: B200PT_SHADE_BLOCKS = four digits, matte plastic glass metal
+    static const int blocks[4] = {
+        [] { const char* e = std::getenv("B200PT_SHADE_BLOCKS"); return e && std::strlen(e) == 4 ? e[0] - '0' : 4; }(),
+        [] { const char* e = std::getenv("B200PT_SHADE_BLOCKS"); return e && std::strlen(e) == 4 ? e[1] - '0' : 4; }(),
+        [] { const char* e = std::getenv("B200PT_SHADE_BLOCKS"); return e && std::strlen(e) == 4 ? e[2] - '0' : 4; }(),
+        [] { const char* e = std::getenv("B200PT_SHADE_BLOCKS"); return e && std::strlen(e) == 4 ? e[3] - '0' : 4; }()};
+    k_shade<KM_ALL, kShadeMiss, 8><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, 0, 1);
+    int launches = 1;
+    if (s->material_classes & (1u << B200PT_MAT_MATTE)) { launch_shade_class<kKmMatte>(s, W, cur, n_upper, 1, blocks[0], st); ++launches; }
+    if (s->material_classes & (1u << B200PT_MAT_PLASTIC)) { launch_shade_class<kKmPlastic>(s, W, cur, n_upper, 2, blocks[1], st); ++launches; }
+    if (s->material_classes & (1u << B200PT_MAT_GLASS)) { launch_shade_class<kKmGlass>(s, W, cur, n_upper, 3, blocks[2], st); ++launches; }
+    if (s->material_classes & (1u << B200PT_MAT_METAL)) { launch_shade_class<kKmMetal>(s, W, cur, n_upper, 4, blocks[3], st); ++launches; }
+    if (s->has_null_material) { k_shade<KM_ALL, kShadeNull, 8><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, kBinNull, kBinNull + 1); ++launches; }
+    g_launches.fetch_add(launches);
 }
 
 // Runs the bounce loop for the n paths currently initialised in the wave (queue 0).
-// The three traversals a bounce produces - shadow rays, MIS rays, and the next bounce's closest-hit rays - are
-// independent of one another.  They are launched on three streams so that the drain of one persistent kernel (and, in late
-// bounces, the ~0.1 ms latency floor of a launch that holds only a few thousand rays) overlaps the others; resolve, which
-// needs the first two, and the next shade, which needs all three, follow on the main stream behind events.
-// B200PT_OVERLAP=0 puts everything back on one stream (A/B).
+// Nothing in the loop waits for the device: every queue size a bounce produces stays in the wave's control blocks and the
+// next kernels read it from there (grids are sized for the wave and stride; persistent traversal kernels take the count
+// pointer), so the host only enqueues.  The three traversals a bounce produces - shadow rays, MIS rays, and the next
+// bounce's closest-hit rays - are independent of one another and go to three streams so that the drain of one persistent
+// kernel overlaps the others; resolve, which needs the first two, and the next shade, which needs all three, follow on the
+// main stream behind events.  B200PT_OVERLAP=0 puts everything back on one stream (A/B).
 static int aux_setup(SceneImpl* s) {
     if (s->aux_ready) return B200PT_OK;
     for (int i = 0; i < 2; ++i) {
         B2_CUDA(cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking));
         B2_CUDA(cudaEventCreateWithFlags(&s->ev_aux[i], cudaEventDisableTiming));
     }
+    B2_CUDA(cudaEventCreateWithFlags(&s->ev_shade, cudaEventDisableTiming));
     const char* e = std::getenv("B200PT_OVERLAP");
     s->overlap = !(e && e[0] == '0');
     s->aux_ready = true;
@@ -749,65 +915,81 @@ static int aux_setup(SceneImpl* s) {
 }
 
 static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
-    Wave& W = s->wave;
     int rc = aux_setup(s);
     if (rc) return rc;
-    int cur = 0, n_active = n;
-    s->rays[0] += (uint64_t)n;
-    auto closest = [&](int q, int count) {
-        s->rays[1] += (uint64_t)count;
-        return s->instanced ? launch_intersect2(s->accel2.dev, W.ray[q], count, W.hit, st, W.hit_b2, W.hit_inst)
-                            : launch_intersect(s->dev.accel, W.ray[q], count, W.hit, st, 0, W.hit_b2);
+    if (n <= 0) return B200PT_OK;
+    const Wave& W0 = s->wave;
+    int* const ctl = s->d_ctl;
+    const DevCtx* dc = dev_ctx(s->device);
+    const int sms = dc ? dc->sm_count : 148;
+    const int g256 = std::max(1, std::min((n + 255) / 256, sms * 16));
+    auto work_ctr = [&](int block, int which) { return reinterpret_cast<unsigned long long*>(ctl + block * kCtl + 32) + which; };
+    auto closest = [&](int q, int block) {  // the queue whose size is control block `block`[0]
+        TraceLaunch tl; tl.n_dev = ctl + block * kCtl; tl.work_ctr = work_ctr(block, 0);
+        return s->instanced ? launch_intersect2(s->accel2.dev, W0.ray[q], n, W0.hit, st, W0.hit_b2, W0.hit_inst, 0, &tl)
+                            : launch_intersect(s->dev.accel, W0.ray[q], n, W0.hit, st, 0, W0.hit_b2, &tl);
     };
-    if (n_active > 0 && (rc = closest(cur, n_active))) return rc;
-    for (int iter = 0; n_active > 0 && iter <= s->dev.max_depth + 1; ++iter) {
-        B2_CUDA(cudaMemsetAsync(W.counters, 0, 32 * sizeof(int), st));
-        k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, n_active);
-        k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, n_active);
-        g_launches.fetch_add(2);
-        launch_shade(s, cur, n_active, W.sorted, st);
+    // iteration k shades the vertices with `bounces` == k; paths end at max_depth, except through null materials
+    int iters_left = s->has_null_material ? 0x7fffffff : s->dev.max_depth + 1;
+    int cur = 0, n_seg = n;
+    bool first_seg = true;
+    while (n_seg > 0 && iters_left > 0) {
+        const int seg_iters = std::min(kSegIters, iters_left);
+        k_wave_begin<<<1, 256, 0, st>>>(ctl, (kSegIters + 1) * kCtl, n_seg);
         g_launches.fetch_add(1);
-        int cnt[26];
-        B2_CUDA(cudaMemcpyAsync(cnt, W.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-        B2_CUDA(cudaStreamSynchronize(st));
-        if (s->dev.spatial && cnt[25] > 0) {
-            // SpatialLightDistribution: fill the voxels this bounce touched for the first time, then shade the parked slots
-            if (cnt[24] > 0) {
-                const long long items = (long long)cnt[24] * s->dev.n_lights;
-                k_voxel_contrib<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(s->dev, cnt[24]);
-                k_voxel_finish<<<(cnt[24] + 127) / 128, 128, 0, st>>>(s->dev, cnt[24]);
-                g_launches.fetch_add(2);
-                s->voxels_built += (uint64_t)cnt[24];
+        if ((rc = closest(cur, 0))) return rc;
+        for (int it = 0; it < seg_iters; ++it) {
+            Wave W = W0;
+            W.counters = ctl + (it + 1) * kCtl;
+            const int* n_act = ctl + it * kCtl;
+            k_bin_count<<<g256, 256, 0, st>>>(s->dev, W, n_act, 0);
+            k_bin_scatter<<<g256, 256, 0, st>>>(W, n_act, 0);
+            g_launches.fetch_add(2);
+            launch_shade(s, W, cur, n, st);
+            if (s->dev.spatial) {
+                // SpatialLightDistribution: fill the voxels this bounce touched for the first time, then shade the parked slots
+                k_voxel_contrib<<<sms * 8, 128, 0, st>>>(s->dev, W.counters + 24);
+                k_voxel_finish<<<sms, 128, 0, st>>>(s->dev, W.counters + 24);
+                k_shade<KM_ALL, kShadeHit, 5><<<shade_grid(s, n, 20), 128, 0, st>>>(s->dev, W, cur, -1, -1);
+                g_launches.fetch_add(3);
             }
-            launch_shade(s, cur, cnt[25], W.deferred, st);
-            g_launches.fetch_add(1);
-            B2_CUDA(cudaMemcpyAsync(cnt, W.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-            B2_CUDA(cudaStreamSynchronize(st));
-        }
-        // everything the shade stage wrote is complete (the stream was just synchronised): fan out
-        cudaStream_t s_sh = s->overlap ? s->aux[0] : st, s_mis = s->overlap ? s->aux[1] : st;
-        if (cnt[1] > 0) {
-            rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, cnt[1], W.sh_occ, s_sh) : launch_occluded(s->dev.accel, W.sh_ray, cnt[1], W.sh_occ, s_sh, 0);
-            if (rc) return rc;
-            s->rays[2] += (uint64_t)cnt[1];
-            if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[0], s_sh));
-        }
-        if (cnt[2] > 0) {
-            rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, cnt[2], W.mis_hit, s_mis, W.mis_b2, nullptr)
-                              : launch_intersect(s->dev.accel, W.mis_ray, cnt[2], W.mis_hit, s_mis, 0, W.mis_b2);
-            if (rc) return rc;
-            s->rays[1] += (uint64_t)cnt[2];
+            cudaStream_t s_sh = s->overlap ? s->aux[0] : st, s_mis = s->overlap ? s->aux[1] : st;
+            if (s->overlap) {
+                B2_CUDA(cudaEventRecord(s->ev_shade, st));
+                B2_CUDA(cudaStreamWaitEvent(s_sh, s->ev_shade, 0));
+                B2_CUDA(cudaStreamWaitEvent(s_mis, s->ev_shade, 0));
+            }
+            {
+                TraceLaunch tl; tl.n_dev = W.counters + 1; tl.work_ctr = work_ctr(it + 1, 1);
+                rc = s->instanced ? launch_occluded2(s->accel2.dev, W.sh_ray, n, W.sh_occ, s_sh, 0, &tl) : launch_occluded(s->dev.accel, W.sh_ray, n, W.sh_occ, s_sh, 0, &tl);
+                if (rc) return rc;
+                if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[0], s_sh));
+            }
+            if (s->dev.n_lights > s->n_point_lights) {  // estimate_direct samples the BSDF only for lights that can be hit
+                TraceLaunch tl; tl.n_dev = W.counters + 2; tl.work_ctr = work_ctr(it + 1, 2);
+                rc = s->instanced ? launch_intersect2(s->accel2.dev, W.mis_ray, n, W.mis_hit, s_mis, W.mis_b2, nullptr, 0, &tl)
+                                  : launch_intersect(s->dev.accel, W.mis_ray, n, W.mis_hit, s_mis, 0, W.mis_b2, &tl);
+                if (rc) return rc;
+            }
             if (s->overlap) B2_CUDA(cudaEventRecord(s->ev_aux[1], s_mis));
+            if (it + 1 < seg_iters && (rc = closest(cur ^ 1, it + 1))) return rc;  // the next bounce's rays, concurrently with the two above
+            if (s->overlap) {
+                B2_CUDA(cudaStreamWaitEvent(st, s->ev_aux[0], 0));
+                B2_CUDA(cudaStreamWaitEvent(st, s->ev_aux[1], 0));
+            }
+            k_resolve<<<g256, 256, 0, st>>>(s->dev, W);
+            g_launches.fetch_add(1);
+            cur ^= 1;
         }
-        const bool more = cnt[0] > 0 && iter + 1 <= s->dev.max_depth + 1;
-        if (more && (rc = closest(cur ^ 1, cnt[0]))) return rc;  // the next bounce's rays, concurrently with the two above
-        if (s->overlap) {
-            if (cnt[1] > 0) B2_CUDA(cudaStreamWaitEvent(st, s->ev_aux[0], 0));
-            if (cnt[2] > 0) B2_CUDA(cudaStreamWaitEvent(st, s->ev_aux[1], 0));
-        }
-        if (cnt[3] > 0) { k_resolve<<<(cnt[3] + 255) / 256, 256, 0, st>>>(s->dev, W, cnt[3]); g_launches.fetch_add(1); }
-        cur ^= 1;
-        n_active = cnt[0];
+        k_wave_end<<<1, 32, 0, st>>>(ctl, seg_iters + 1, first_seg ? n : 0, s->d_totals);
+        g_launches.fetch_add(1);
+        first_seg = false;
+        iters_left -= seg_iters;
+        if (iters_left <= 0) break;
+        // deeper than one segment of control blocks (maxdepth > 15, or null materials): the only read-back of the loop
+        B2_CUDA(cudaMemcpyAsync(s->h_pinned, ctl + seg_iters * kCtl, sizeof(int), cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        n_seg = s->h_pinned[0];
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wavefront kernels");
@@ -830,9 +1012,9 @@ static int run_wave_whitted(SceneImpl* s, int n, cudaStream_t st) {
     };
     if (n_active > 0 && (rc = closest(cur, n_active))) return rc;
     for (long long iter = 0; n_active > 0 && iter < max_iter; ++iter) {
-        B2_CUDA(cudaMemsetAsync(W.counters, 0, 32 * sizeof(int), st));
-        k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, n_active);
-        k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, n_active);
+        B2_CUDA(cudaMemsetAsync(W.counters, 0, kCtl * sizeof(int), st));
+        k_bin_count<<<(n_active + 255) / 256, 256, 0, st>>>(s->dev, W, nullptr, n_active);
+        k_bin_scatter<<<(n_active + 255) / 256, 256, 0, st>>>(W, nullptr, n_active);
         const int gs = (n_active + 127) / 128;
         if (s->tree_mode == kTreeWhitted) k_shade_tree<kTreeWhitted><<<gs, 128, 0, st>>>(s->dev, W, cur, n_active);
         else if (s->tree_mode == kTreeDirectAll) k_shade_tree<kTreeDirectAll><<<gs, 128, 0, st>>>(s->dev, W, cur, n_active);
@@ -937,11 +1119,36 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         }
         if (d->sampler.spp > 32768) { b200pt_set_error("b200pt_scene_create: 02sequence pixelsamples > 32768"); return B200PT_ERR_UNSUPPORTED; }
     }
-    for (int64_t i = 0; i < d->n_prims; ++i)
-        if (d->prim_material[i] < 0 || d->prim_material[i] >= d->n_materials) { b200pt_set_error("b200pt_scene_create: primitive without a material (null-BSDF pass-through is outside this path)"); return B200PT_ERR_UNSUPPORTED; }
-    B2_CUDA(cudaSetDevice(g_device));
+    if (d->integrator.type == B200PT_INTEGRATOR_PATH) {
+        // Sampler tables bound the path length: a vertex draws up to 8 dimensions after the 5 of the camera sample; the
+        // reference asserts past its tables (samplers/src/halton.rs:106-110).  The bounce counter is 8 bits (255 = unused pixel).
+        const int max_dims = d->sampler.type == B200PT_SAMPLER_SOBOL ? 1024 : 1000;
+        if (d->integrator.max_depth < 0 || d->integrator.max_depth > 254 ||
+            (d->sampler.type != B200PT_SAMPLER_ZEROTWO && 5 + 8 * (long long)d->integrator.max_depth > max_dims)) {
+            b200pt_set_error("b200pt_scene_create: path maxdepth beyond what the sampler's tables cover (halton: 124, sobol: 127)");
+            return B200PT_ERR_UNSUPPORTED;
+        }
+    }
+    bool has_null = false;
+    for (int64_t i = 0; i < d->n_prims; ++i) {
+        // material -1: Material "" / "none" (api/src/lib.rs make_material -> None): the path integrator passes through it
+        // (path.rs:146-150); an emissive primitive still emits
+        if (d->prim_material[i] < -1 || d->prim_material[i] >= d->n_materials) { b200pt_set_error("b200pt_scene_create: primitive material index out of range"); return B200PT_ERR_INVALID; }
+        if (d->prim_material[i] < 0) has_null = true;
+        if (d->prim_light && (d->prim_light[i] < -1 || d->prim_light[i] >= d->n_lights)) { b200pt_set_error("b200pt_scene_create: primitive light index out of range"); return B200PT_ERR_INVALID; }
+    }
+    if (has_null && d->integrator.type != B200PT_INTEGRATOR_PATH) {
+        b200pt_set_error("b200pt_scene_create: primitives without a material are supported by the path integrator only");
+        return B200PT_ERR_UNSUPPORTED;
+    }
     b200pt_scene* sc = new b200pt_scene();
     SceneImpl* s = &sc->impl;
+    s->device = current_device();
+    s->has_null_material = has_null;
+    for (int i = 0; i < d->n_materials; ++i)
+        if (d->materials[i].type >= 0 && d->materials[i].type < 4) s->material_classes |= 1u << d->materials[i].type;
+        else { b200pt_set_error("b200pt_scene_create: unknown material type"); delete sc; return B200PT_ERR_INVALID; }
+    for (int i = 0; i < d->n_lights; ++i) if (d->lights[i].type == B200PT_LIGHT_POINT) ++s->n_point_lights;
     auto fail = [&](int code) { b200pt_scene_destroy(sc); return code; };
     DeviceScene& D = s->dev;
     std::memset(&D, 0, sizeof(D));
@@ -1092,12 +1299,22 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
             D.n_voxels[i] = (int)std::max<long long>(1, v);
             n_vox *= D.n_voxels[i];
         }
+        // Rows (func[n_lights], cdf[n_lights + 1], func_int) are handed out on first touch from a pool: only the voxels
+        // paths actually reach - a shell around the surfaces - get one, as in the reference's lazily filled hash table.
         const long long row = 2ll * d->n_lights + 2;
-        if (n_vox * row * 4 > (8ll << 30)) { b200pt_set_error("b200pt_scene_create: spatial light distribution table would exceed 8 GB (voxels x lights)"); return fail(B200PT_ERR_UNSUPPORTED); }
-        if ((rc = dev_alloc(s, (size_t)(n_vox * row), &D.vox_table))) return fail(rc);
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+        size_t pool_bytes = env_bytes("B200PT_SPATIAL_BUDGET");
+        if (!pool_bytes) pool_bytes = std::min<size_t>((size_t)8 << 30, free_b / 4);
+        long long pool_rows = std::min<long long>(n_vox, std::max<long long>(64, (long long)(pool_bytes / (size_t)(row * 4))));
+        if ((rc = dev_alloc(s, (size_t)(pool_rows * row), &D.vox_table))) return fail(rc);
         if ((rc = dev_alloc(s, (size_t)n_vox, &D.vox_state))) return fail(rc);
+        if ((rc = dev_alloc(s, (size_t)n_vox, &D.vox_row))) return fail(rc);
         if ((rc = dev_alloc(s, (size_t)n_vox, &D.vox_work))) return fail(rc);
+        if ((rc = dev_alloc(s, (size_t)1, &D.vox_pool_next))) return fail(rc);
         B2_CUDA(cudaMemset(D.vox_state, 0, (size_t)n_vox * sizeof(int)));
+        B2_CUDA(cudaMemset(D.vox_pool_next, 0, sizeof(int)));
+        D.vox_pool_cap = (int)std::min<long long>(pool_rows, 0x7fffffff);
         D.spatial = 1;
     }
     HostDistr1D ld;
@@ -1167,12 +1384,17 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
 
 void b200pt_scene_destroy(b200pt_scene* sc) {
     if (!sc) return;
+    if (sc->impl.device >= 0) cudaSetDevice(sc->impl.device);
     for (void* p : sc->impl.allocs) cudaFree(p);
     for (void* p : sc->impl.wave_ptrs) cudaFree(p);
     for (int i = 0; i < 2; ++i) { if (sc->impl.aux[i]) cudaStreamDestroy(sc->impl.aux[i]); if (sc->impl.ev_aux[i]) cudaEventDestroy(sc->impl.ev_aux[i]); }
     if (sc->impl.d_sample_L) cudaFree(sc->impl.d_sample_L);
     if (sc->impl.d_sample_pf) cudaFree(sc->impl.d_sample_pf);
     if (sc->impl.d_film) cudaFree(sc->impl.d_film);
+    if (sc->impl.d_acc) cudaFree(sc->impl.d_acc);
+    if (sc->impl.d_totals) cudaFree(sc->impl.d_totals);
+    if (sc->impl.h_pinned) cudaFreeHost(sc->impl.h_pinned);
+    if (sc->impl.ev_shade) cudaEventDestroy(sc->impl.ev_shade);
     for (void* p : {(void*)sc->impl.d_zt_scr1, (void*)sc->impl.d_zt_scr2, (void*)sc->impl.d_zt_perm1, (void*)sc->impl.d_zt_perm2, (void*)sc->impl.d_zt_scratch})
         if (p) cudaFree(p);
     if (sc->impl.d_rows) cudaFree(sc->impl.d_rows);
@@ -1215,26 +1437,58 @@ static int zerotwo_prepare(SceneImpl* s, long long n_pix, cudaStream_t st) {
     return B200PT_OK;
 }
 
+// Reads the render's ray totals and error flags back (the one read-back of a render besides the film).
+static int finish_totals(SceneImpl* s, cudaStream_t st) {
+    unsigned long long t[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(s->h_pinned, s->d_totals, sizeof(t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "render");
+    std::memcpy(t, s->h_pinned, sizeof(t));
+    s->rays[0] += t[0]; s->rays[1] += t[1]; s->rays[2] += t[2];
+    if (s->dev.spatial) {
+        int built = 0;
+        B2_CUDA(cudaMemcpy(&built, s->dev.vox_pool_next, sizeof(int), cudaMemcpyDeviceToHost));
+        s->voxels_built = (uint64_t)std::min(built, s->dev.vox_pool_cap);
+    }
+    if (t[3] & 1ull) {
+        b200pt_set_error("render: the spatial light distribution touched more voxels than its row pool holds (raise B200PT_SPATIAL_BUDGET, or use lightsamplestrategy power / uniform)");
+        return B200PT_ERR_OOM;
+    }
+    return B200PT_OK;
+}
+
 // Renders the sample rows listed in `srows` (ascending, inside the sample bounds) into a zero-initialised film of
 // the full cropped window.  Shards with disjoint row sets sum to the whole image (each sample is taken once).
+// The shard's samples (pixel-major) are cut into waves that fit the memory budget; after each wave k_film continues the
+// running sums of the film pixels the wave's samples reach, so memory does not grow with resolution x samples per pixel.
 static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d_film_xyzw, cudaStream_t st) {
     int rc = B200PT_OK;
     const b200pt_film& f = s->film;
     const int cw = f.crop[2] - f.crop[0], ch = f.crop[3] - f.crop[1];
-    B2_CUDA(cudaMemsetAsync(d_film_xyzw, 0, (size_t)cw * ch * sizeof(float4), st));
+    const long long n_film = (long long)cw * ch;
     s->rays[0] = s->rays[1] = s->rays[2] = 0;
-    if (srows.empty()) { B2_CUDA(cudaStreamSynchronize(st)); return B200PT_OK; }
+    if (srows.empty() || n_film <= 0) {
+        if (n_film > 0) B2_CUDA(cudaMemsetAsync(d_film_xyzw, 0, (size_t)n_film * sizeof(float4), st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        return B200PT_OK;
+    }
     const int* sb = s->sample_bounds;
     const int sw = sb[2] - sb[0], sh = sb[3] - sb[1], spp = s->spp;
     const long long n_samples = (long long)srows.size() * sw * spp;
     if ((rc = wave_alloc(s, wave_cap_for(s, n_samples)))) return rc;
-    if (n_samples > s->sample_cap) {
+    if (s->wave_cap > s->sample_cap) {
         if (s->d_sample_L) cudaFree(s->d_sample_L);
         if (s->d_sample_pf) cudaFree(s->d_sample_pf);
         s->d_sample_L = nullptr; s->d_sample_pf = nullptr; s->sample_cap = 0;
-        B2_CUDA(cudaMalloc(&s->d_sample_L, (size_t)n_samples * sizeof(float4)));
-        B2_CUDA(cudaMalloc(&s->d_sample_pf, (size_t)n_samples * sizeof(float2)));
-        s->sample_cap = n_samples;
+        B2_CUDA(cudaMalloc(&s->d_sample_L, (size_t)s->wave_cap * sizeof(float4)));
+        B2_CUDA(cudaMalloc(&s->d_sample_pf, (size_t)s->wave_cap * sizeof(float2)));
+        s->sample_cap = s->wave_cap;
+    }
+    if ((size_t)n_film * sizeof(float4) > s->acc_cap) {
+        if (s->d_acc) cudaFree(s->d_acc);
+        s->d_acc = nullptr; s->acc_cap = 0;
+        B2_CUDA(cudaMalloc(&s->d_acc, (size_t)n_film * sizeof(float4)));
+        s->acc_cap = (size_t)n_film * sizeof(float4);
     }
     if (!s->d_rows) {
         B2_CUDA(cudaMalloc(&s->d_rows, (size_t)sh * sizeof(int)));
@@ -1244,8 +1498,18 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
     for (size_t k = 0; k < srows.size(); ++k) row_index[(size_t)(srows[k] - sb[1])] = (int)k;
     B2_CUDA(cudaMemcpyAsync(s->d_rows, srows.data(), srows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(s->d_row_index, row_index.data(), (size_t)sh * sizeof(int), cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemsetAsync(s->d_acc, 0, (size_t)n_film * sizeof(float4), st));
+    B2_CUDA(cudaMemsetAsync(s->d_totals, 0, 4 * sizeof(unsigned long long), st));
     B2_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
     if ((rc = zerotwo_prepare(s, (long long)srows.size() * sw, st))) return rc;
+    DFilm F;
+    std::memcpy(F.crop, f.crop, 16);
+    F.rx = f.filter_radius[0]; F.ry = f.filter_radius[1];
+    F.inv_rx = 1.0f / F.rx; F.inv_ry = 1.0f / F.ry;
+    F.max_lum = f.max_sample_luminance;
+    std::memcpy(F.sb, sb, 16);
+    F.tile = 16;
+    const int reach = (int)std::ceil(F.ry) + 2;  // film rows a sample row can touch, generously
     float4* d_L = s->d_sample_L;
     float2* d_pf = s->d_sample_pf;
     for (long long first = 0; first < n_samples && !rc; first += s->wave_cap) {
@@ -1254,24 +1518,21 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
         g_launches.fetch_add(1);
         rc = s->whitted ? run_wave_whitted(s, n, st) : run_wave(s, n, st);
         if (rc) break;
-        k_store_samples<<<(n + 255) / 256, 256, 0, st>>>(s->wave, n, d_L + first);
-        g_launches.fetch_add(1);
+        k_store_samples<<<(n + 255) / 256, 256, 0, st>>>(s->wave, n, d_L);
+        // every film pixel near the wave's sample rows continues its sums (also pixels of a neighbouring shard when the
+        // filter is wider than a pixel; the shards' films are summed afterwards)
+        const int y_lo = srows[(size_t)(first / ((long long)sw * spp))], y_hi = srows[(size_t)((first + n - 1) / ((long long)sw * spp))];
+        const int y0 = std::max(f.crop[1], y_lo - reach), y1 = std::min(f.crop[3], y_hi + reach + 1);
+        if (y1 > y0) {
+            const long long npix = (long long)cw * (y1 - y0);
+            k_film<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(F, s->d_filter_table, d_L, d_pf, first, n, spp, s->d_row_index, y0, y1, s->d_acc);
+        }
+        g_launches.fetch_add(2);
     }
     if (!rc) {
-        DFilm F;
-        std::memcpy(F.crop, f.crop, 16);
-        F.rx = f.filter_radius[0]; F.ry = f.filter_radius[1];
-        F.inv_rx = 1.0f / F.rx; F.inv_ry = 1.0f / F.ry;
-        F.max_lum = f.max_sample_luminance;
-        std::memcpy(F.sb, sb, 16);
-        F.tile = 16;
-        // every film pixel gathers from the sample rows this shard owns (also rows of a neighbouring shard's pixels
-        // when the filter is wider than a pixel); the shards' films are summed afterwards
-        int npix = cw * ch;
-        k_film<<<(npix + 127) / 128, 128, 0, st>>>(F, s->d_filter_table, d_L, d_pf, spp, s->d_row_index, (float4*)d_film_xyzw);
+        k_film_finish<<<(unsigned)((n_film + 255) / 256), 256, 0, st>>>(s->d_acc, n_film, (float4*)d_film_xyzw);
         g_launches.fetch_add(1);
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) rc = cuda_fail(e, "render");
+        rc = finish_totals(s, st);
     }
     return rc;
 }
@@ -1287,12 +1548,11 @@ static void append_rows(const SceneImpl* s, int r0, int r1, std::vector<int>* ou
 }
 
 int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_end, void* d_film_xyzw, void* stream) {
-    int rc = require_device();
-    if (rc) return rc;
     if (!sc || !d_film_xyzw) { b200pt_set_error("b200pt_render_rows_device: null argument"); return B200PT_ERR_INVALID; }
     SceneImpl* s = &sc->impl;
     std::lock_guard<std::mutex> g(s->mu);  // render serialises per scene
-    B2_CUDA(cudaSetDevice(g_device));
+    int rc = use_device(s->device);
+    if (rc) return rc;
     const int ch = s->film.crop[3] - s->film.crop[1];
     if (row_begin < 0 || row_end > ch || row_begin > row_end) { b200pt_set_error("b200pt_render_rows_device: row range outside the cropped window"); return B200PT_ERR_INVALID; }
     std::vector<int> rows;
@@ -1301,12 +1561,11 @@ int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_e
 }
 
 int b200pt_render_shard_device(b200pt_scene* sc, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream) {
-    int rc = require_device();
-    if (rc) return rc;
     if (!sc || !d_film_xyzw || n_shards < 1 || shard < 0 || shard >= n_shards || band_rows < 1) { b200pt_set_error("b200pt_render_shard_device: invalid argument"); return B200PT_ERR_INVALID; }
     SceneImpl* s = &sc->impl;
     std::lock_guard<std::mutex> g(s->mu);
-    B2_CUDA(cudaSetDevice(g_device));
+    int rc = use_device(s->device);
+    if (rc) return rc;
     const int ch = s->film.crop[3] - s->film.crop[1];
     std::vector<int> rows;
     for (int r0 = 0, band = 0; r0 < ch; r0 += band_rows, ++band)
@@ -1315,9 +1574,9 @@ int b200pt_render_shard_device(b200pt_scene* sc, int32_t shard, int32_t n_shards
 }
 
 int b200pt_render_rows(b200pt_scene* sc, int32_t row_begin, int32_t row_end, float* film_xyzw) {
-    int rc = require_device();
-    if (rc) return rc;
     if (!sc || !film_xyzw) { b200pt_set_error("b200pt_render_rows: null argument"); return B200PT_ERR_INVALID; }
+    int rc = use_device(sc->impl.device);
+    if (rc) return rc;
     const b200pt_film& f = sc->impl.film;
     size_t bytes = (size_t)(f.crop[2] - f.crop[0]) * (f.crop[3] - f.crop[1]) * sizeof(float4);
     SceneImpl* s = &sc->impl;
@@ -1356,13 +1615,13 @@ int b200pt_film_resolve(const b200pt_film* f, const float* film_xyzw, float* rgb
 }
 
 int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, float* li_out, b200pt_ray* rays_out) {
-    int rc = require_device();
-    if (rc) return rc;
     if (!sc || n < 0 || (n > 0 && (!pixel_sample || !li_out))) { b200pt_set_error("b200pt_li_batch: invalid argument"); return B200PT_ERR_INVALID; }
     SceneImpl* s = &sc->impl;
     std::lock_guard<std::mutex> g(s->mu);
-    B2_CUDA(cudaSetDevice(g_device));
+    int rc = use_device(s->device);
+    if (rc) return rc;
     if ((rc = wave_alloc(s, wave_cap_for(s, n)))) return rc;
+    B2_CUDA(cudaMemset(s->d_totals, 0, 4 * sizeof(unsigned long long)));
     if (s->dev.sampler_type == B200PT_SAMPLER_ZEROTWO) {  // explicit lists may name any pixel: own every sample row
         const int* sb = s->sample_bounds;
         const int sw = sb[2] - sb[0], sh = sb[3] - sb[1];
@@ -1405,7 +1664,15 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
         if (rays_out) cudaMemcpy(rays_out + first, d_rays, (size_t)m * sizeof(b200pt_ray), cudaMemcpyDeviceToHost);
     }
     cudaFree(d_list); cudaFree(d_L); cudaFree(d_rays);
+    if (!rc) rc = finish_totals(s, 0);
     return rc;
+}
+
+int b200pt_scene_set_memory_budget(b200pt_scene* sc, uint64_t bytes) {
+    if (!sc) { b200pt_set_error("b200pt_scene_set_memory_budget: null scene"); return B200PT_ERR_INVALID; }
+    std::lock_guard<std::mutex> g(sc->impl.mu);
+    sc->impl.mem_budget = (size_t)bytes;
+    return B200PT_OK;
 }
 
 }  // extern "C"

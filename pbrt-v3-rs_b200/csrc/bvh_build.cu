@@ -857,7 +857,8 @@ struct Workspace {
     char* base = nullptr;
     size_t cap = 0;
 };
-Workspace g_ws;
+Workspace g_ws_all[65];  // one cached scratch arena per device (the last slot is never filled: no device bound)
+inline Workspace& ws() { const int d = b2::current_device(); return g_ws_all[d >= 0 && d < 64 ? d : 64]; }
 
 struct Arena {
     char* base;
@@ -877,13 +878,13 @@ size_t build_scratch_bytes(uint32_t n) {
            padded(sizeof(Ctl)) + padded(8 * (size_t)n) + padded(n) + padded(4 * nb) + 5 * padded(4 * (size_t)n) + padded(64 * (size_t)n);
 }
 
-int workspace_reserve(size_t bytes) {  // caller holds g_ws.mu
-    if (g_ws.cap >= bytes) return B200PT_OK;
-    if (g_ws.base) { cudaFree(g_ws.base); g_ws.base = nullptr; g_ws.cap = 0; }
+int workspace_reserve(size_t bytes) {  // caller holds ws().mu
+    if (ws().cap >= bytes) return B200PT_OK;
+    if (ws().base) { cudaFree(ws().base); ws().base = nullptr; ws().cap = 0; }
     void* q = nullptr;
     B2_CUDA(cudaMalloc(&q, bytes));
-    g_ws.base = static_cast<char*>(q);
-    g_ws.cap = bytes;
+    ws().base = static_cast<char*>(q);
+    ws().cap = bytes;
     return B200PT_OK;
 }
 
@@ -1007,9 +1008,9 @@ int bvh_build_sah_device(const float* d_prim_bounds, int64_t n, int max_prims, b
     *n_nodes_out = 0;
     if (n == 0) return B200PT_OK;
     if (n >= (1LL << 31)) { b200pt_set_error("b200pt_bvh_build_sah_device: more than 2^31-1 primitives"); return B200PT_ERR_INVALID; }
-    std::lock_guard<std::mutex> lock(g_ws.mu);
+    std::lock_guard<std::mutex> lock(ws().mu);
     if (int rc = workspace_reserve(build_scratch_bytes((uint32_t)n))) return rc;
-    Arena A{g_ws.base, g_ws.cap};
+    Arena A{ws().base, ws().cap};
     return build_in_arena(A, d_prim_bounds, n, max_prims, d_nodes, n_nodes_out, d_ordered, st);
 }
 
@@ -1030,9 +1031,9 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
     if (n64 >= (1LL << 31)) { b200pt_set_error("b200pt_bvh_build_hlbvh_device: more than 2^31-1 primitives"); return B200PT_ERR_INVALID; }
     const uint32_t n = (uint32_t)n64;
     max_prims &= 0xff;
-    std::lock_guard<std::mutex> lock(g_ws.mu);
+    std::lock_guard<std::mutex> lock(ws().mu);
     if (int rc = workspace_reserve(hlbvh_scratch_bytes(n))) return rc;
-    Arena A{g_ws.base, g_ws.cap};
+    Arena A{ws().base, ws().cap};
     const uint32_t n_blocks = blocks(n, kBlock);
     uint32_t* code[2] = {A.take<uint32_t>(n), A.take<uint32_t>(n)};
     uint32_t* val[2] = {A.take<uint32_t>(n), A.take<uint32_t>(n)};
@@ -1113,7 +1114,6 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
 extern "C" int b200pt_bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* d_nodes_out,
                                              int64_t* n_nodes_out, uint32_t* d_ordered_out, void* stream) {
     if (int rc = b2::require_device()) return rc;
-    B2_CUDA(cudaSetDevice(b2::g_device));
     if (n < 0 || !n_nodes_out || (n > 0 && (!d_prim_bounds || !d_nodes_out || !d_ordered_out))) {
         b200pt_set_error("b200pt_bvh_build_hlbvh_device: invalid argument");
         return B200PT_ERR_INVALID;
@@ -1125,7 +1125,6 @@ extern "C" int b200pt_bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t
 extern "C" int b200pt_bvh_build_hlbvh_gpu(const float* prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* nodes_out,
                                           int64_t* n_nodes_out, uint32_t* ordered_out) {
     if (int rc = b2::require_device()) return rc;
-    B2_CUDA(cudaSetDevice(b2::g_device));
     if (n < 0 || !n_nodes_out || (n > 0 && (!prim_bounds || !nodes_out || !ordered_out))) {
         b200pt_set_error("b200pt_bvh_build_hlbvh_gpu: invalid argument");
         return B200PT_ERR_INVALID;
@@ -1203,14 +1202,14 @@ extern "C" int b200pt_accel_create_device(const float* d_tri_verts, int64_t n_pr
     *out = nullptr;
     if (int rc = b2::require_device()) return rc;
     if (n_prims <= 0 || !d_tri_verts || n_prims >= (1LL << 30)) { b200pt_set_error("b200pt_accel_create_device: invalid argument"); return B200PT_ERR_INVALID; }
-    B2_CUDA(cudaSetDevice(b2::g_device));
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t n = (uint32_t)n_prims;
     {   // stream-ordered allocations from a pool that keeps its memory: a rebuild then costs no cudaMalloc
-        static std::once_flag once;
-        std::call_once(once, [] {
+        static std::once_flag once[64];
+        const int dev = b2::current_device();
+        std::call_once(once[dev & 63], [dev] {
             cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, b2::g_device) == cudaSuccess) {
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
                 uint64_t keep = ~0ull;
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
@@ -1219,6 +1218,7 @@ extern "C" int b200pt_accel_create_device(const float* d_tri_verts, int64_t n_pr
     b200pt_accel* a = new b200pt_accel();
     b2::AccelImpl& A = a->impl;
     std::memset(&A.dev, 0, sizeof(A.dev));
+    A.device = A.dev.device = b2::current_device();
     auto fail = [&](int rc) { b2::accel_free_device(&A); delete a; return rc; };
     float* d_bounds = nullptr; b200pt_bvh_node* d_nodes = nullptr; uint32_t* d_ordered = nullptr;
     uint8_t* flag = nullptr; uint32_t *block_sum = nullptr, *T = nullptr;
@@ -1265,6 +1265,7 @@ extern "C" int b200pt_accel_create_device(const float* d_tri_verts, int64_t n_pr
 // The LinearBVHNode array / ordered_prims of a device-resident accelerator (parity checks; pass NULL to skip one).
 extern "C" int b200pt_accel_download(const b200pt_accel* a, b200pt_bvh_node* nodes_out, int64_t* n_nodes_out, uint32_t* ordered_out) {
     if (!a) { b200pt_set_error("b200pt_accel_download: null accelerator"); return B200PT_ERR_INVALID; }
+    if (int rc = b2::use_device(a->impl.device)) return rc;
     if (n_nodes_out) *n_nodes_out = a->impl.n_nodes;
     if (nodes_out && a->impl.n_nodes > 0) B2_CUDA(cudaMemcpy(nodes_out, a->impl.d_ref, (size_t)a->impl.n_nodes * sizeof(b200pt_bvh_node), cudaMemcpyDeviceToHost));
     if (ordered_out && a->impl.n_prims > 0) {  // original index = second word of the third float4 of every leaf-order triangle record
@@ -1277,7 +1278,6 @@ extern "C" int b200pt_accel_download(const b200pt_accel* a, b200pt_bvh_node* nod
 
 extern "C" int b200pt_triangle_bounds_device(const float* d_tri_verts, int64_t n, float* d_bounds_out, void* stream) {
     if (int rc = b2::require_device()) return rc;
-    B2_CUDA(cudaSetDevice(b2::g_device));
     if (n <= 0) return B200PT_OK;
     k_tri_bounds<<<blocks((uint64_t)n, 256), 256, 0, (cudaStream_t)stream>>>(d_tri_verts, n, d_bounds_out);
     b2::g_launches.fetch_add(1);
@@ -1288,7 +1288,6 @@ extern "C" int b200pt_triangle_bounds_device(const float* d_tri_verts, int64_t n
 extern "C" int b200pt_bvh_build_sah_device(const float* d_prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* d_nodes_out,
                                            int64_t* n_nodes_out, uint32_t* d_ordered_out, void* stream) {
     if (int rc = b2::require_device()) return rc;
-    B2_CUDA(cudaSetDevice(b2::g_device));
     if (n < 0 || !n_nodes_out || (n > 0 && (!d_prim_bounds || !d_nodes_out || !d_ordered_out))) {
         b200pt_set_error("b200pt_bvh_build_sah_device: invalid argument");
         return B200PT_ERR_INVALID;
@@ -1300,7 +1299,6 @@ extern "C" int b200pt_bvh_build_sah_device(const float* d_prim_bounds, int64_t n
 extern "C" int b200pt_bvh_build_sah_gpu(const float* prim_bounds, int64_t n, int max_prims_in_node, b200pt_bvh_node* nodes_out,
                                         int64_t* n_nodes_out, uint32_t* ordered_out) {
     if (int rc = b2::require_device()) return rc;
-    B2_CUDA(cudaSetDevice(b2::g_device));
     if (n < 0 || !n_nodes_out || (n > 0 && (!prim_bounds || !nodes_out || !ordered_out))) {
         b200pt_set_error("b200pt_bvh_build_sah_gpu: invalid argument");
         return B200PT_ERR_INVALID;
@@ -1308,9 +1306,9 @@ extern "C" int b200pt_bvh_build_sah_gpu(const float* prim_bounds, int64_t n, int
     *n_nodes_out = 0;
     if (n == 0) return B200PT_OK;
     if (n >= (1LL << 31)) { b200pt_set_error("b200pt_bvh_build_sah_gpu: more than 2^31-1 primitives"); return B200PT_ERR_INVALID; }
-    std::lock_guard<std::mutex> lock(g_ws.mu);
+    std::lock_guard<std::mutex> lock(ws().mu);
     if (int rc = workspace_reserve(build_scratch_bytes((uint32_t)n) + padded(24 * (size_t)n) + padded(64 * (size_t)n) + padded(4 * (size_t)n))) return rc;
-    Arena A{g_ws.base, g_ws.cap};
+    Arena A{ws().base, ws().cap};
     float* d_bounds = A.take<float>(6 * (size_t)n);
     b200pt_bvh_node* d_nodes = A.take<b200pt_bvh_node>(2 * (size_t)n);
     uint32_t* d_ordered = A.take<uint32_t>((size_t)n);
@@ -1325,9 +1323,9 @@ extern "C" int b200pt_bvh_build_sah_gpu(const float* prim_bounds, int64_t n, int
 }
 
 extern "C" int b200pt_bvh_build_release(void) {
-    std::lock_guard<std::mutex> lock(g_ws.mu);
-    if (g_ws.base) cudaFree(g_ws.base);
-    g_ws.base = nullptr;
-    g_ws.cap = 0;
+    std::lock_guard<std::mutex> lock(ws().mu);
+    if (ws().base) cudaFree(ws().base);
+    ws().base = nullptr;
+    ws().cap = 0;
     return B200PT_OK;
 }

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -18,9 +19,24 @@ extern "C" int b200pt_set_error(const char* msg);
 namespace b2 {
 
 extern std::atomic<int64_t> g_launches;
-extern int g_device;       // -1 until b200pt_init succeeds
-extern int g_sm_count;
-extern int64_t g_l2_bytes;
+
+// Per-device library state.  A handle (accelerator, scene) remembers the device it was created on and every entry point
+// switches to it, so one process can drive several GPUs (b200pt_render_multi); nothing below is shared across devices.
+struct DevCtx {
+    int device = -1;
+    int sm_count = 0;
+    int64_t l2_bytes = 0;
+    // 8-byte work counters of the persistent traversal kernels: one per launch in flight, handed out round-robin
+    // (the wave loop passes its own counters instead; the ring only serves the *_batch_device entry points)
+    static const int kRing = 4096;
+    unsigned long long* ring = nullptr;
+    std::atomic<unsigned> ring_next{0};
+    int persist_grid[4] = {0, 0, 0, 0};  // resident CTAs of the persistent kernels (traverse_kernels.cu)
+    std::mutex mu;                        // first-use setup of the fields above
+};
+int current_device();            // the calling thread's device: b200pt_set_device, else the first b200pt_init; -1 = none
+DevCtx* dev_ctx(int device);     // nullptr unless b200pt_init(device) succeeded
+int use_device(int device);      // cudaSetDevice for a handle's device; B200PT_ERR_NO_DEVICE if it was never initialised
 
 int cuda_fail(cudaError_t e, const char* what);  // records message, returns B200PT_ERR_CUDA / OOM
 
@@ -46,17 +62,20 @@ template <class F> inline void parallel_for(int64_t n, F f, int64_t grain = 1 <<
     for (auto& x : th) x.join();
 }
 
+// Binds the calling thread to its current device (creation entry points and the handle-less *_gpu / *_device calls).
 inline int require_device() {
-    if (g_device < 0) {
+    const int d = current_device();
+    if (d < 0) {
         b200pt_set_error("b200pt: no device bound (call b200pt_init first; there is no CPU fallback)");
         return B200PT_ERR_NO_DEVICE;
     }
-    return B200PT_OK;
+    return use_device(d);
 }
 
 // Host mirror of the device accelerator: owns the device allocations.
 struct AccelImpl {
     DeviceAccel dev;
+    int device = -1;
     float4* d_wide = nullptr;
     float4* d_tris = nullptr;
     float4* d_ref = nullptr;
@@ -69,9 +88,16 @@ int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint
 float4 record_duv(const float* uv6);  // uv0 - uv2, uv1 - uv2; uv6 == nullptr: the default uvs
 void accel_free_device(AccelImpl* a);
 
-// Kernel launchers (traverse_kernels.cu)
-int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant, float* d_b2 = nullptr);
-int launch_occluded(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant);
+// Kernel launchers (traverse_kernels.cu).  TraceLaunch lets the wavefront loop keep its queue sizes on the device:
+// with n_dev set the kernel reads the ray count from device memory (n is then only an upper bound for the grid) and
+// work_ctr is a zeroed 8-byte counter the caller owns for this launch.
+struct TraceLaunch {
+    const int* n_dev = nullptr;
+    unsigned long long* work_ctr = nullptr;
+};
+int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant, float* d_b2 = nullptr,
+                     const TraceLaunch* tl = nullptr);
+int launch_occluded(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant, const TraceLaunch* tl = nullptr);
 int launch_count_work(const DeviceAccel& A, const void* d_rays, int64_t n, int any_hit, unsigned long long* d_totals, void* d_per_ray, cudaStream_t s);
 
 }  // namespace b2

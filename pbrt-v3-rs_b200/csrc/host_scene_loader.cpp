@@ -226,6 +226,7 @@ struct Lexer {
 struct Param {
     std::string type, name;
     std::vector<float> nums;          // f32 like the reference's parser (strtod then `as f32`)
+    std::vector<int32_t> ints;        // "integer" parameters, parsed as i32 like the reference (api/src/parser/mod.rs:638): indices above 2^24 survive
     std::vector<std::string> strs;    // string / bool / texture / spectrum-file values
     mutable bool used = false;
 };
@@ -237,7 +238,7 @@ struct ParamSet {
         return nullptr;
     }
     float one_float(const std::string& n, float d) const { const Param* p = find(n, "float"); return p && !p->nums.empty() ? p->nums[0] : d; }
-    int one_int(const std::string& n, int d) const { const Param* p = find(n, "integer"); return p && !p->nums.empty() ? (int)p->nums[0] : d; }
+    int one_int(const std::string& n, int d) const { const Param* p = find(n, "integer"); return p && !p->ints.empty() ? (int)p->ints[0] : d; }
     bool one_bool(const std::string& n, bool d) const { const Param* p = find(n, "bool"); return p && !p->strs.empty() ? p->strs[0] == "true" : d; }
     std::string one_string(const std::string& n, const std::string& d) const { const Param* p = find(n, "string"); return p && !p->strs.empty() ? p->strs[0] : d; }
     std::vector<float> floats(const std::string& n) const { const Param* p = find(n, "float"); return p ? p->nums : std::vector<float>(); }
@@ -435,11 +436,13 @@ struct Builder {
     ParamSet camera_p, sampler_p, filter_p, integrator_p, film_p, accel_p;
     Xf camera_to_world = xf_identity();
     int default_matte = -1;
+    int include_depth = 0;
 
     std::string resolve(const std::string& p) const { return (!p.empty() && p[0] == '/') || dir.empty() ? p : dir + "/" + p; }
 
     static void fill_rgb(float* dst, const float* src) { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
 
+    static const int kNoMaterial = -2;  // gs.material: -1 = the default matte (not created yet), kNoMaterial = Material "none"
     int make_material(const std::string& type, const ParamSet& p) {
         for (const char* t : {"Kd", "Ks", "Kr", "Kt", "eta", "k", "sigma", "roughness", "uroughness", "vroughness", "index", "bumpmap"})
             if (p.has_texture(t)) throw Unsupported(std::string("material parameter \"texture ") + t + "\": textures are outside this path (constant values only)");
@@ -447,8 +450,10 @@ struct Builder {
         std::memset(&m, 0, sizeof(m));
         m.remap_roughness = p.one_bool("remaproughness", true) ? 1 : 0;
         const float one[3] = {1, 1, 1}, half[3] = {0.5f, 0.5f, 0.5f}, quarter[3] = {0.25f, 0.25f, 0.25f};
-        if (type == "matte" || type == "" || type == "none") {
-            if (type == "none") throw Unsupported("Material \"none\" (null-BSDF pass-through) is outside this path");
+        // GraphicsState::make_material: "none" | "" => None (api/src/graphics_state.rs:336): the primitive gets no material and
+        // the path integrator passes through it (integrators/src/path.rs:141-150)
+        if (type == "none" || type == "") return kNoMaterial;
+        if (type == "matte") {
             m.type = B200PT_MAT_MATTE;
             p.one_rgb("Kd", half, m.kd);
             m.sigma = p.one_float("sigma", 0.0f);
@@ -477,7 +482,8 @@ struct Builder {
         L->materials.push_back(m);
         return (int)L->materials.size() - 1;
     }
-    int current_material() {
+    int current_material() {  // index into materials, or -1 for a primitive without a material
+        if (gs.material == kNoMaterial) return -1;
         if (gs.material >= 0) return gs.material;
         if (default_matte < 0) default_matte = make_material("matte", ParamSet());  // GraphicsState's default material
         return default_matte;
@@ -544,7 +550,7 @@ struct Builder {
     void shape(const std::string& name, const ParamSet& p) {
         if (name == "trianglemesh") {
             std::vector<int> idx;
-            if (const Param* q = p.find("indices", "integer")) for (float v : q->nums) idx.push_back((int)v);
+            if (const Param* q = p.find("indices", "integer")) for (int32_t v : q->ints) idx.push_back((int)v);
             std::vector<float> P, N, S, UV;
             if (const Param* q = p.find("P", "point", "point3")) P = q->nums;
             if (const Param* q = p.find("N", "normal", "normal3")) N = q->nums;
@@ -719,7 +725,7 @@ void Builder::finish() {
         if (pb->nums.size() != 4) throw Invalid("'pixelbounds' expects 4 values");
         // Bounds2i::new(Point2i(pb[0], pb[1]), Point2i(pb[2], pb[3])) intersected with the sample bounds (path.rs:296-311;
         // note the order x0 y0 x1 y1, unlike pbrt-v3's C++ reader)
-        int x0 = (int)pb->nums[0], y0 = (int)pb->nums[1], x1 = (int)pb->nums[2], y1 = (int)pb->nums[3];
+        int x0 = pb->ints[0], y0 = pb->ints[1], x1 = pb->ints[2], y1 = pb->ints[3];
         sb[0] = sb[0] > x0 ? sb[0] : x0; sb[1] = sb[1] > y0 ? sb[1] : y0; sb[2] = sb[2] < x1 ? sb[2] : x1; sb[3] = sb[3] < y1 ? sb[3] : y1;
     }
     for (int i = 0; i < 4; ++i) d.integrator.pixel_bounds[i] = sb[i];
@@ -811,7 +817,13 @@ static ParamSet parse_params(Lexer& lx) {
         ds >> p.type >> p.name;
         if (p.type.empty() || p.name.empty()) lx.fail("bad parameter declaration \"" + decl.text + "\"");
         auto take = [&](const Token& t) {
-            if (t.kind == Token::Number) p.nums.push_back((float)t.num);
+            if (t.kind == Token::Number) {
+                p.nums.push_back((float)t.num);
+                if (p.type == "integer") {
+                    if (!(t.num >= -2147483648.0 && t.num <= 2147483647.0) || t.num != std::floor(t.num)) lx.fail("integer parameter \"" + decl.text + "\": value is not an i32");
+                    p.ints.push_back((int32_t)t.num);
+                }
+            }
             else if (t.kind == Token::String) p.strs.push_back(t.text);
             else if (t.kind == Token::Ident && (t.text == "true" || t.text == "false")) p.strs.push_back(t.text);
             else lx.fail("bad value for parameter \"" + decl.text + "\"");
@@ -930,6 +942,8 @@ static void parse_stream(Lexer& lx, Builder& B) {
 }
 
 static void parse_file(const std::string& path, Builder& B) {
+    struct Depth { int& d; explicit Depth(int& x) : d(x) { ++d; } ~Depth() { --d; } } depth(B.include_depth);
+    if (B.include_depth > 32) throw Invalid("Include nested deeper than 32 files (a file that includes itself?): '" + path + "'");
     std::ifstream f(path, std::ios::binary);
     if (!f) throw Invalid("cannot open scene file '" + path + "'");
     std::stringstream ss;

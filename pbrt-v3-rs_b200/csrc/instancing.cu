@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(128) k_trace_twolevel(DeviceAccel2 A, const fl
 
 template <bool ANY, int kSwitch, int kRefill, int kBlocks>
 __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2, const float4* __restrict__ rays, long long n, void* __restrict__ out,
-                                                                unsigned long long* __restrict__ counter, float* __restrict__ b2_out, int* __restrict__ inst_out) {
+                                                                unsigned long long* __restrict__ counter, float* __restrict__ b2_out, int* __restrict__ inst_out,
+                                                                 const int* __restrict__ n_dev) {
     const DeviceAccel& A = A2.top;
     const unsigned lane = threadIdx.x & 31u;
     const int kIdle = (int)0x80000000;
@@ -212,10 +213,11 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
             unsigned long long b = 0;
             if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
             b = __shfl_sync(0xffffffffu, b, 0);
-            if ((long long)b + want >= n) exhausted = true;
+            const long long n_rays = ray_count(n, n_dev);
+            if ((long long)b + want >= n_rays) exhausted = true;
             if (cur == kIdle) {
                 const long long id = (long long)b + __popc(idle_mask & ((1u << lane) - 1u));
-                if (id < n) {
+                if (id < n_rays) {
                     float4 r0 = __ldg(rays + 2 * id), r1 = __ldg(rays + 2 * id + 1);
                     ray_id = id;
                     set_ray(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
@@ -360,7 +362,8 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
 // interrupted leaf (saved_*) and the stack top.
 template <bool ANY, int kSwitch, int kRefill, int kBlocks>
 __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2, const float4* __restrict__ rays, long long n, void* __restrict__ out,
-                                                                 unsigned long long* __restrict__ counter, float* __restrict__ b2_out, int* __restrict__ inst_out) {
+                                                                 unsigned long long* __restrict__ counter, float* __restrict__ b2_out, int* __restrict__ inst_out,
+                                                                 const int* __restrict__ n_dev) {
     const DeviceAccel& A = A2.top;
     const unsigned lane = threadIdx.x & 31u;
     const int kIdle = (int)0x80000000;
@@ -407,10 +410,11 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
             unsigned long long b = 0;
             if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
             b = __shfl_sync(0xffffffffu, b, 0);
-            if ((long long)b + want >= n) exhausted = true;
+            const long long n_rays = ray_count(n, n_dev);
+            if ((long long)b + want >= n_rays) exhausted = true;
             if (cur == kIdle && pend == kIdle) {
                 const long long id = (long long)b + __popc(idle_mask & ((1u << lane) - 1u));
-                if (id < n) {
+                if (id < n_rays) {
                     float4 r0 = __ldg(rays + 2 * id), r1 = __ldg(rays + 2 * id + 1);
                     ray_id = (int)id;
                     set_ray(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
@@ -580,47 +584,50 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
     }
 }
 
-static const int kCounterRing2 = 64;  // one work counter per launch in flight (launches on different streams never share one)
-static unsigned long long* g_counter2 = nullptr;
-static std::atomic<unsigned> g_counter2_next{0};
+int trace_work_counter(int device, const TraceLaunch* tl, cudaStream_t s, unsigned long long** out);  // traverse_kernels.cu
 
 template <bool ANY>
-static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, float* d_b2, int* d_inst, int variant) {
-    if (!g_counter2) B2_CUDA(cudaMalloc(&g_counter2, kCounterRing2 * sizeof(unsigned long long)));
-    unsigned long long* ctr = g_counter2 + (g_counter2_next.fetch_add(1) % kCounterRing2);
-    B2_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
+static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, float* d_b2, int* d_inst, int variant, const TraceLaunch* tl) {
+    DevCtx* c = dev_ctx(A.top.device);
+    if (!c) { b200pt_set_error("two-level traversal: accelerator on a device that was never initialised"); return B200PT_ERR_NO_DEVICE; }
     if (n >= 0x7fffffffLL) { b200pt_set_error("two-level traversal: at most 2^31-2 rays per launch"); return B200PT_ERR_INVALID; }
+    unsigned long long* ctr = nullptr;
+    int rc = trace_work_counter(A.top.device, tl, s, &ctr);
+    if (rc) return rc;
+    const int* n_dev = tl ? tl->n_dev : nullptr;
     int64_t want = (n + 127) / 128;
     if (variant == 4) {
         constexpr int kBlocks = 5;
-        int grid = (int)std::min<int64_t>(want, (int64_t)g_sm_count * kBlocks);
-        k_trace_phased2<ANY, 16, 16, kBlocks><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+        int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * kBlocks);
+        k_trace_phased2<ANY, 16, 16, kBlocks><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
     } else {
         // CTAs per SM (register cap): closest-hit 7 (72 registers, 62 B of spills: 3 % faster on C5 than 6 without spills), any-hit 7; B200PT_2L_BLOCKS = 5..8 overrides the closest-hit choice (A/B)
         static const int closest_blocks = [] { const char* e = std::getenv("B200PT_2L_BLOCKS"); int v = e ? std::atoi(e) : 7; return (v >= 5 && v <= 8) ? v : 7; }();
         const int kb = ANY ? 7 : closest_blocks;
-        int grid = (int)std::min<int64_t>(want, (int64_t)g_sm_count * kb);
-        if (kb == 5) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 5><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
-        else if (kb == 7) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
-        else if (kb == 8) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 8><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
-        else k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 6><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst);
+        int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * kb);
+        if (kb == 5) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 5><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        else if (kb == 7) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        else if (kb == 8) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 8><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        else k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 6><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
     }
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200PT_OK : cuda_fail(e, "k_trace_phased2 launch");
 }
 
-int launch_intersect2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, float* d_b2, int* d_inst, int variant) {
+int launch_intersect2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, float* d_b2, int* d_inst, int variant, const TraceLaunch* tl) {
     if (n <= 0) return B200PT_OK;
-    if (variant == 0 || variant == 4) return launch_phased2<false>(A, d_rays, n, d_hits, s, d_b2, d_inst, variant);
+    if (variant == 0 || variant == 4) return launch_phased2<false>(A, d_rays, n, d_hits, s, d_b2, d_inst, variant, tl);
+    if (tl && tl->n_dev) { b200pt_set_error("two-level traversal: device-resident ray counts need a persistent kernel variant"); return B200PT_ERR_INVALID; }
     k_trace_twolevel<false><<<(int)((n + 127) / 128), 128, 0, s>>>(A, (const float4*)d_rays, n, d_hits, d_b2, d_inst);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200PT_OK : cuda_fail(e, "k_trace_twolevel launch");
 }
-int launch_occluded2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant) {
+int launch_occluded2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant, const TraceLaunch* tl) {
     if (n <= 0) return B200PT_OK;
-    if (variant == 0 || variant == 4) return launch_phased2<true>(A, d_rays, n, d_out, s, nullptr, nullptr, variant);
+    if (variant == 0 || variant == 4) return launch_phased2<true>(A, d_rays, n, d_out, s, nullptr, nullptr, variant, tl);
+    if (tl && tl->n_dev) { b200pt_set_error("two-level traversal: device-resident ray counts need a persistent kernel variant"); return B200PT_ERR_INVALID; }
     k_trace_twolevel<true><<<(int)((n + 127) / 128), 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, nullptr, nullptr);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
@@ -698,6 +705,7 @@ int accel2_build_device(const b200pt_scene_desc* d, Accel2Impl* a) {
     }, wide, recs, &root);
     if (rc) return rc;
     a->dev.top.root_code = root;
+    a->dev.top.device = current_device();
     if (d->n_nodes > 0) std::memcpy(a->dev.top.root_bounds, d->nodes[0].bounds, 24);
     a->dev.top.n_nodes = (int)d->n_nodes;
     a->dev.top.n_prims = d->n_prims;

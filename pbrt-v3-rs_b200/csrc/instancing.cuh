@@ -1,6 +1,6 @@
 // Two-level (instanced) accelerator: device structs and launchers.  Internal header.
 #pragma once
-#include "traverse.cuh"
+#include "common.cuh"
 
 struct b200pt_scene_desc;
 
@@ -33,7 +33,8 @@ int accel2_build_device(const b200pt_scene_desc* d, Accel2Impl* out);
 void accel2_free_device(Accel2Impl* a);
 // variant 0 = loop-free postponed-leaf persistent kernel with the instance entered / left inside one loop (default),
 // variant 4 = phase-scheduled persistent kernel without postponement, variant 2 = one thread per ray with a nested walk.
-int launch_intersect2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, float* d_b2, int* d_inst, int variant = 0);
-int launch_occluded2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant = 0);
+int launch_intersect2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, float* d_b2, int* d_inst, int variant = 0,
+                      const TraceLaunch* tl = nullptr);
+int launch_occluded2(const DeviceAccel2& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant = 0, const TraceLaunch* tl = nullptr);
 
 }  // namespace b2

@@ -178,6 +178,12 @@ B2_D V3 tr_sample_wh(TRDist d, V3 wo, P2 u) {  // :100-141 (visible-area branch)
 enum : uint32_t { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
 enum : int { BX_LAMBERT = 0, BX_OREN_NAYAR = 1, BX_MF_REFL = 2, BX_MF_TRANS = 3, BX_FRESNEL_SPECULAR = 4, BX_SPEC_REFL = 5, BX_SPEC_TRANS = 6 };
 
+// Compile-time lobe masks: the shade stage runs one kernel per material class after the sort, and each only carries the
+// code of the lobes its material can produce (bit k = BxDF kind k may occur; KM_COND / KM_DIEL = which Fresnel term a
+// microfacet reflection may use).  KM_ALL keeps every branch (tree integrators, explicit li batches).
+enum : uint32_t { KM_COND = 1u << 8, KM_DIEL = 1u << 9, KM_ALL = 0x7fu | KM_COND | KM_DIEL };
+template <uint32_t KM> B2_D bool km_is(int kind, int k) { return ((KM >> k) & 1u) && ((KM & 0x7fu) == (1u << k) || kind == k); }
+
 // One lobe with every per-material constant already evaluated on the host
 // (constant textures; roughness remap via ln() done once instead of per hit).
 struct DBxDF {
@@ -208,15 +214,16 @@ struct BxDFSample {
 B2_D RGB ldrgb(const float* c) { return rgb(c[0], c[1], c[2]); }
 B2_D bool bx_matches(const DBxDF& b, uint32_t flags) { return (b.type & flags) == b.type; }  // reflection/mod.rs:82-85
 
-B2_D RGB bx_fresnel(const DBxDF& b, float cos_i) {
-    if (!b.conductor) return rgb1(fr_dielectric(cos_i, b.fr_eta_i, b.fr_eta_t));
+template <uint32_t KM = KM_ALL> B2_D RGB bx_fresnel(const DBxDF& b, float cos_i) {
+    const bool conductor = (KM & KM_COND) && (!(KM & KM_DIEL) || b.conductor);
+    if (!conductor) return rgb1(fr_dielectric(cos_i, b.fr_eta_i, b.fr_eta_t));
     return fr_conductor(pabs(cos_i), rgb1(1.0f), ldrgb(b.c_eta_t), ldrgb(b.c_k));
 }
 
-B2_D RGB bx_f(const DBxDF& b, V3 wo, V3 wi) {
-    switch (b.kind) {
-        case BX_LAMBERT: return ldrgb(b.r) * kInvPi;  // lambertian_reflection.rs:38
-        case BX_OREN_NAYAR: {                        // oren_nayar.rs:36-57
+template <uint32_t KM = KM_ALL> B2_D RGB bx_f(const DBxDF& b, V3 wo, V3 wi) {
+    {
+        if (km_is<KM>(b.kind, BX_LAMBERT)) return ldrgb(b.r) * kInvPi;  // lambertian_reflection.rs:38
+        if (km_is<KM>(b.kind, BX_OREN_NAYAR)) {                        // oren_nayar.rs:36-57
             float sin_i = sin_theta(wi), sin_o = sin_theta(wo);
             float max_cos = 0.0f;
             if (sin_i > 1e-4f && sin_o > 1e-4f) {
@@ -230,16 +237,16 @@ B2_D RGB bx_f(const DBxDF& b, V3 wo, V3 wi) {
             else { sin_alpha = sin_i; tan_beta = sin_o / aco; }
             return ldrgb(b.r) * kInvPi * (b.on_a + b.on_b * max_cos * sin_alpha * tan_beta);
         }
-        case BX_MF_REFL: {  // microfacet_reflection.rs:48-66
+        if (km_is<KM>(b.kind, BX_MF_REFL)) {  // microfacet_reflection.rs:48-66
             float cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);
             V3 wh = wi + wo;
             if ((cos_i == 0.0f || cos_o == 0.0f) || (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f)) return rgb1(0.0f);
             wh = normalize(wh);
             TRDist d{b.ax, b.ay};
-            RGB F = bx_fresnel(b, dot(wi, face_forward(wh, mk(0.0f, 0.0f, 1.0f))));
+            RGB F = bx_fresnel<KM>(b, dot(wi, face_forward(wh, mk(0.0f, 0.0f, 1.0f))));
             return ldrgb(b.r) * tr_d(d, wh) * tr_g(d, wo, wi) * F / (4.0f * cos_i * cos_o);
         }
-        case BX_MF_TRANS: {  // microfacet_transmission.rs:70-123
+        if (km_is<KM>(b.kind, BX_MF_TRANS)) {  // microfacet_transmission.rs:70-123
             if (same_hemisphere(wo, wi)) return rgb1(0.0f);
             float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
             if (cos_i == 0.0f || cos_o == 0.0f) return rgb1(0.0f);
@@ -255,21 +262,20 @@ B2_D RGB bx_f(const DBxDF& b, V3 wo, V3 wi) {
                    pabs(tr_d(d, wh) * tr_g(d, wo, wi) * eta * eta * abs_dot(wi, wh) * abs_dot(wo, wh) * factor * factor /
                         (cos_i * cos_o * sqrt_denom * sqrt_denom));
         }
-        default: return rgb1(0.0f);  // FresnelSpecular::f, fresnel_specular.rs:63-66
+        return rgb1(0.0f);  // FresnelSpecular::f, fresnel_specular.rs:63-66
     }
 }
 
-B2_D float bx_pdf(const DBxDF& b, V3 wo, V3 wi) {
-    switch (b.kind) {
-        case BX_LAMBERT:
-        case BX_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.0f;  // reflection/mod.rs:160-167
-        case BX_MF_REFL: {                                                                       // microfacet_reflection.rs:96-103
+template <uint32_t KM = KM_ALL> B2_D float bx_pdf(const DBxDF& b, V3 wo, V3 wi) {
+    {
+        if (km_is<KM>(b.kind, BX_LAMBERT) || km_is<KM>(b.kind, BX_OREN_NAYAR)) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.0f;  // reflection/mod.rs:160-167
+        if (km_is<KM>(b.kind, BX_MF_REFL)) {                                                     // microfacet_reflection.rs:96-103
             if (!same_hemisphere(wo, wi)) return 0.0f;
             V3 wh = normalize(wo + wi);
             TRDist d{b.ax, b.ay};
             return tr_pdf(d, wo, wh) / (4.0f * dot(wo, wh));
         }
-        case BX_MF_TRANS: {  // microfacet_transmission.rs:151-172
+        if (km_is<KM>(b.kind, BX_MF_TRANS)) {  // microfacet_transmission.rs:151-172
             if (same_hemisphere(wo, wi)) return 0.0f;
             float eta = cos_theta(wo) > 0.0f ? b.eta_b / b.eta_a : b.eta_a / b.eta_b;
             V3 wh = normalize(wo + wi * eta);
@@ -279,24 +285,23 @@ B2_D float bx_pdf(const DBxDF& b, V3 wo, V3 wi) {
             TRDist d{b.ax, b.ay};
             return tr_pdf(d, wo, wh) * dwh_dwi;
         }
-        default: return 0.0f;
+        return 0.0f;
     }
 }
 
-B2_D BxDFSample bx_sample_f(const DBxDF& b, V3 wo, P2 u) {
+template <uint32_t KM = KM_ALL> B2_D BxDFSample bx_sample_f(const DBxDF& b, V3 wo, P2 u) {
     BxDFSample s;
     s.f = rgb1(0.0f); s.pdf = 0.0f; s.wi = mk(0.0f, 0.0f, 0.0f); s.type = b.type;
-    switch (b.kind) {
-        case BX_LAMBERT:
-        case BX_OREN_NAYAR: {  // reflection/mod.rs:132-141
+    {
+        if (km_is<KM>(b.kind, BX_LAMBERT) || km_is<KM>(b.kind, BX_OREN_NAYAR)) {  // reflection/mod.rs:132-141
             V3 wi = cosine_sample_hemisphere(u);
             if (wo.z < 0.0f) wi.z *= -1.0f;
-            s.pdf = bx_pdf(b, wo, wi);
-            s.f = bx_f(b, wo, wi);
+            s.pdf = bx_pdf<KM>(b, wo, wi);
+            s.f = bx_f<KM>(b, wo, wi);
             s.wi = wi;
             return s;
         }
-        case BX_MF_REFL: {  // microfacet_reflection.rs:68-94
+        if (km_is<KM>(b.kind, BX_MF_REFL)) {  // microfacet_reflection.rs:68-94
             if (wo.z == 0.0f) return s;
             TRDist d{b.ax, b.ay};
             V3 wh = tr_sample_wh(d, wo, u);
@@ -304,11 +309,11 @@ B2_D BxDFSample bx_sample_f(const DBxDF& b, V3 wo, P2 u) {
             V3 wi = reflect(wo, wh);
             if (!same_hemisphere(wo, wi)) { s.wi = wi; return s; }
             s.pdf = tr_pdf(d, wo, wh) / (4.0f * dot(wo, wh));
-            s.f = bx_f(b, wo, wi);
+            s.f = bx_f<KM>(b, wo, wi);
             s.wi = wi;
             return s;
         }
-        case BX_MF_TRANS: {  // microfacet_transmission.rs:125-149
+        if (km_is<KM>(b.kind, BX_MF_TRANS)) {  // microfacet_transmission.rs:125-149
             if (wo.z == 0.0f) return s;
             TRDist d{b.ax, b.ay};
             V3 wh = tr_sample_wh(d, wo, u);
@@ -316,12 +321,13 @@ B2_D BxDFSample bx_sample_f(const DBxDF& b, V3 wo, P2 u) {
             float eta = cos_theta(wo) > 0.0f ? b.eta_a / b.eta_b : b.eta_b / b.eta_a;
             V3 wi;
             if (!refract(wo, wh, eta, &wi)) return s;
-            s.pdf = bx_pdf(b, wo, wi);
-            s.f = bx_f(b, wo, wi);
+            s.pdf = bx_pdf<KM>(b, wo, wi);
+            s.f = bx_f<KM>(b, wo, wi);
             s.wi = wi;
             return s;
         }
-        default: {  // FresnelSpecular::sample_f, fresnel_specular.rs:68-103
+        if (!((KM >> BX_FRESNEL_SPECULAR) & 1u)) return s;
+        {  // FresnelSpecular::sample_f, fresnel_specular.rs:68-103
             float F = fr_dielectric(cos_theta(wo), b.eta_a, b.eta_b);
             if (u.x < F) {
                 V3 wi = mk(-wo.x, -wo.y, wo.z);
@@ -387,28 +393,28 @@ B2_D int bsdf_num_components(const BSDF& b, uint32_t flags) {
     for (int i = 0; i < b.m->n_bxdf; ++i) if (bx_matches(b.m->bx[i], flags)) ++c;
     return c;
 }
-B2_D RGB bsdf_f(const BSDF& b, V3 wo_w, V3 wi_w, uint32_t flags) {  // :166-192
+template <uint32_t KM = KM_ALL> B2_D RGB bsdf_f(const BSDF& b, V3 wo_w, V3 wi_w, uint32_t flags) {  // :166-192
     V3 wi = bsdf_to_local(b, wi_w), wo = bsdf_to_local(b, wo_w);
     if (wo.z == 0.0f) return rgb1(0.0f);
     bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
     RGB f = rgb1(0.0f);
     for (int i = 0; i < b.m->n_bxdf; ++i) {
         const DBxDF& x = b.m->bx[i];
-        if (bx_matches(x, flags) && ((refl && (x.type & BSDF_REFLECTION)) || (!refl && (x.type & BSDF_TRANSMISSION)))) f = f + bx_f(x, wo, wi);
+        if (bx_matches(x, flags) && ((refl && (x.type & BSDF_REFLECTION)) || (!refl && (x.type & BSDF_TRANSMISSION)))) f = f + bx_f<KM>(x, wo, wi);
     }
     return f;
 }
-B2_D float bsdf_pdf(const BSDF& b, V3 wo_w, V3 wi_w, uint32_t flags) {  // :331-356
+template <uint32_t KM = KM_ALL> B2_D float bsdf_pdf(const BSDF& b, V3 wo_w, V3 wi_w, uint32_t flags) {  // :331-356
     if (b.m->n_bxdf == 0) return 0.0f;
     V3 wo = bsdf_to_local(b, wo_w), wi = bsdf_to_local(b, wi_w);
     if (wo.z == 0.0f) return 0.0f;
     int m = 0;
     float p = 0.0f;
     for (int i = 0; i < b.m->n_bxdf; ++i)
-        if (bx_matches(b.m->bx[i], flags)) { ++m; p += bx_pdf(b.m->bx[i], wo, wi); }
+        if (bx_matches(b.m->bx[i], flags)) { ++m; p += bx_pdf<KM>(b.m->bx[i], wo, wi); }
     return m > 0 ? p / (float)m : 0.0f;
 }
-B2_D BxDFSample bsdf_sample_f(const BSDF& b, V3 wo_w, P2 u, uint32_t flags) {  // :194-292
+template <uint32_t KM = KM_ALL> B2_D BxDFSample bsdf_sample_f(const BSDF& b, V3 wo_w, P2 u, uint32_t flags) {  // :194-292
     BxDFSample none;
     none.f = rgb1(0.0f); none.pdf = 0.0f; none.wi = mk(0.0f, 0.0f, 0.0f); none.type = 0;
     int m = bsdf_num_components(b, flags);
@@ -421,19 +427,19 @@ B2_D BxDFSample bsdf_sample_f(const BSDF& b, V3 wo_w, P2 u, uint32_t flags) {  /
     P2 ur = mk2(pmin(u.x * (float)m - (float)comp, kOneMinusEps), u.y);
     V3 wo = bsdf_to_local(b, wo_w);
     if (wo.z == 0.0f) return none;
-    BxDFSample s = bx_sample_f(b.m->bx[idx], wo, ur);
+    BxDFSample s = bx_sample_f<KM>(b.m->bx[idx], wo, ur);
     if (s.pdf == 0.0f) return none;
     V3 wi_w = bsdf_to_world(b, s.wi);
     if (!(s.type & BSDF_SPECULAR) && m > 1)
         for (int i = 0; i < b.m->n_bxdf; ++i)
-            if (i != idx && bx_matches(b.m->bx[i], flags)) s.pdf += bx_pdf(b.m->bx[i], wo, s.wi);
+            if (i != idx && bx_matches(b.m->bx[i], flags)) s.pdf += bx_pdf<KM>(b.m->bx[i], wo, s.wi);
     if (m > 1) s.pdf /= (float)m;
     if (!(s.type & BSDF_SPECULAR)) {
         bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
         s.f = rgb1(0.0f);
         for (int i = 0; i < b.m->n_bxdf; ++i) {
             const DBxDF& x = b.m->bx[i];
-            if (bx_matches(x, flags) && ((refl && (x.type & BSDF_REFLECTION)) || (!refl && (x.type & BSDF_TRANSMISSION)))) s.f = s.f + bx_f(x, wo, s.wi);
+            if (bx_matches(x, flags) && ((refl && (x.type & BSDF_REFLECTION)) || (!refl && (x.type & BSDF_TRANSMISSION)))) s.f = s.f + bx_f<KM>(x, wo, s.wi);
         }
     }
     s.wi = wi_w;

@@ -40,9 +40,14 @@ struct DeviceAccel {
     int root_code;        // code of the root (>=0 interior 0, <0 leaf), INT_MIN/empty => no nodes
     int n_nodes;
     long long n_prims;
+    int device;           // CUDA device the arrays live on (host side: which DevCtx launches use)
 };
 
 #define B2_EMPTY_ROOT 0x7fffffff
+
+// Ray count of a persistent launch: the host value, or - wavefront loop - the queue size a previous kernel left in device
+// memory.  Read where lanes are refilled (a uniform load every few dozen rays) instead of being held in a register.
+B2_D long long ray_count(long long n, const int* n_dev) { return n_dev ? (long long)*reinterpret_cast<const volatile int*>(n_dev) : n; }
 
 // ---- slab test -----------------------------------------------------------
 // Returns the geometric part of Bounds3::intersect_p_inv and the entry

@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(128) k_trace_simple(DeviceAccel A, const float
 
 template <bool ANY>
 __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, const float4* __restrict__ rays, long long n,
-                                                              void* __restrict__ out, unsigned long long* __restrict__ counter, float* __restrict__ b2_out) {
+                                                              void* __restrict__ out, unsigned long long* __restrict__ counter, float* __restrict__ b2_out,
+                                                              const int* __restrict__ n_dev) {
     const unsigned lane = threadIdx.x & 31u;
     int stack_code[B2_STACK];
     float stack_t[B2_STACK];
@@ -66,11 +67,12 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(counter, (unsigned long long)n_idle);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if ((long long)base + n_idle >= n) exhausted = true;
+            const long long n_rays = ray_count(n, n_dev);
+            if ((long long)base + n_idle >= n_rays) exhausted = true;
             if (idle) {
                 const int my = __popc(idle_mask & ((1u << lane) - 1u));
                 const long long id = (long long)base + my;
-                if (id < n) {
+                if (id < n_rays) {
                     float4 r0 = __ldg(rays + 2 * id), r1 = __ldg(rays + 2 * id + 1);
                     ray_id = id;
                     r.ox = r0.x; r.oy = r0.y; r.oz = r0.z;
@@ -236,32 +238,43 @@ int launch_count_work(const DeviceAccel& A, const void* d_rays, int64_t n, int a
 
 static int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
 
-// Work counters for the persistent kernels: one 8-byte counter per launch in
-// flight, rotated so launches on different streams never share one.
-static const int kCounterRing = 256;
-static unsigned long long* g_counters = nullptr;
-static std::atomic<unsigned> g_counter_next{0};
-static int g_persist_grid[4] = {0, 0, 0, 0};
-
-static int persistent_setup() {
-    if (g_counters) return B200PT_OK;
-    B2_CUDA(cudaMalloc(&g_counters, kCounterRing * sizeof(unsigned long long)));
+// First use on a device: the work-counter ring and the resident grid of each persistent kernel.
+static int persistent_setup(DevCtx* c) {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (c->ring) return B200PT_OK;
+    unsigned long long* ring = nullptr;
+    B2_CUDA(cudaMalloc(&ring, DevCtx::kRing * sizeof(unsigned long long)));
     int nb = 0;
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_persistent<false>, 128, 0));
-    g_persist_grid[0] = g_sm_count * (nb > 0 ? nb : 1);
+    c->persist_grid[0] = c->sm_count * (nb > 0 ? nb : 1);
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_persistent<true>, 128, 0));
-    g_persist_grid[1] = g_sm_count * (nb > 0 ? nb : 1);
+    c->persist_grid[1] = c->sm_count * (nb > 0 ? nb : 1);
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_spec2<false, 20, 20, 7, 1>, 128, 0));
-    g_persist_grid[2] = g_sm_count * (nb > 0 ? nb : 1);
+    c->persist_grid[2] = c->sm_count * (nb > 0 ? nb : 1);
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_spec2<true, 20, 16, 8, 1>, 128, 0));
-    g_persist_grid[3] = g_sm_count * (nb > 0 ? nb : 1);
+    c->persist_grid[3] = c->sm_count * (nb > 0 ? nb : 1);
+    c->ring = ring;
+    return B200PT_OK;
+}
+
+// A zeroed work counter for one persistent launch on stream s (the caller's own, or the next ring slot).
+int trace_work_counter(int device, const TraceLaunch* tl, cudaStream_t s, unsigned long long** out) {
+    if (tl && tl->work_ctr) { *out = tl->work_ctr; return B200PT_OK; }
+    DevCtx* c = dev_ctx(device);
+    if (!c) { b200pt_set_error("traversal: accelerator on a device that was never initialised"); return B200PT_ERR_NO_DEVICE; }
+    if (!c->ring) { int rc = persistent_setup(c); if (rc) return rc; }
+    unsigned long long* ctr = c->ring + (c->ring_next.fetch_add(1) % DevCtx::kRing);
+    B2_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
+    *out = ctr;
     return B200PT_OK;
 }
 
 template <bool ANY>
-static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant, float* d_b2) {
+static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant, float* d_b2, const TraceLaunch* tl) {
     if (n <= 0) return B200PT_OK;
     const int block = 128;
+    const int* n_dev = tl ? tl->n_dev : nullptr;
+    if (n_dev && (variant == 1 || variant == 2)) { b200pt_set_error("traversal: device-resident ray counts need a persistent kernel variant"); return B200PT_ERR_INVALID; }
     if (variant == 1) {
         k_trace_simple<ANY, 1><<<grid_for(n, block), block, 0, s>>>(A, (const float4*)d_rays, n, d_out, d_b2);
     } else if (variant == 2) {
@@ -269,25 +282,27 @@ static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void*
     } else {
         // Persistent kernels.  0 (default) = loop-free postponed-leaf walk (traverse_spec.cuh); A/B baselines:
         // 3 = "if-if" persistent warps, 4 = phase-scheduled without postponement, 5 = postponed leaf with pop loops.
-        int rc = persistent_setup();
-        if (rc) return rc;
+        DevCtx* c = dev_ctx(A.device);
+        if (!c) { b200pt_set_error("traversal: accelerator on a device that was never initialised"); return B200PT_ERR_NO_DEVICE; }
+        if (!c->ring) { int rc = persistent_setup(c); if (rc) return rc; }
         if (n >= 0x7fffffffLL) { b200pt_set_error("traversal: at most 2^31-2 rays per launch"); return B200PT_ERR_INVALID; }
-        unsigned long long* ctr = g_counters + (g_counter_next.fetch_add(1) % kCounterRing);
-        B2_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
-        int grid = g_persist_grid[(variant != 3 ? 2 : 0) + (ANY ? 1 : 0)];
+        unsigned long long* ctr = nullptr;
+        int rc = trace_work_counter(A.device, tl, s, &ctr);
+        if (rc) return rc;
+        int grid = c->persist_grid[(variant != 3 ? 2 : 0) + (ANY ? 1 : 0)];
         int need = grid_for(n, block);
         if (need < grid) grid = need;
         const float4* R = (const float4*)d_rays;
         // closest-hit: <= 72 registers -> 7 CTAs/SM; any-hit: 64 registers -> 8 CTAs/SM (profiles/r1_variants.txt)
-        if (variant == 3) k_trace_persistent<ANY><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
+        if (variant == 3) k_trace_persistent<ANY><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
         else if (variant == 4) {
-            if (ANY) k_trace_phased<true, 16, 16, 0, 8><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
-            else k_trace_phased<false, 16, 16, 0, 7><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
+            if (ANY) k_trace_phased<true, 16, 16, 0, 8><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+            else k_trace_phased<false, 16, 16, 0, 7><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
         } else if (variant == 5) {
-            k_trace_spec<ANY, 16, 16, ANY ? 8 : 7><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
+            k_trace_spec<ANY, 16, 16, ANY ? 8 : 7><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
         } else {
-            if (ANY) k_trace_spec2<true, 20, 16, 8, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
-            else k_trace_spec2<false, 20, 20, 7, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2);
+            if (ANY) k_trace_spec2<true, 20, 16, 8, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+            else k_trace_spec2<false, 20, 20, 7, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
         }
     }
     g_launches.fetch_add(1);
@@ -296,11 +311,11 @@ static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void*
     return B200PT_OK;
 }
 
-int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant, float* d_b2) {
-    return launch_any<false>(A, d_rays, n, d_hits, s, variant, d_b2);
+int launch_intersect(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_hits, cudaStream_t s, int variant, float* d_b2, const TraceLaunch* tl) {
+    return launch_any<false>(A, d_rays, n, d_hits, s, variant, d_b2, tl);
 }
-int launch_occluded(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant) {
-    return launch_any<true>(A, d_rays, n, d_out, s, variant, nullptr);
+int launch_occluded(const DeviceAccel& A, const void* d_rays, int64_t n, void* d_out, cudaStream_t s, int variant, const TraceLaunch* tl) {
+    return launch_any<true>(A, d_rays, n, d_out, s, variant, nullptr, tl);
 }
 
 }  // namespace b2

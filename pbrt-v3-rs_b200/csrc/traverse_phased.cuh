@@ -41,7 +41,7 @@ template <> struct StackEntry<true> {
 //             (slab_fast, 25 vs 37 instructions per box); a warp holding an axis-parallel ray keeps the literal one.
 template <bool ANY, int kSwitch, int kRefill, int kChunk, int kBlocks, int kOpt = 1>
 __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, const float4* __restrict__ rays, long long n, void* __restrict__ out,
-                                                         unsigned long long* __restrict__ counter, float* __restrict__ b2_out) {
+                                                         unsigned long long* __restrict__ counter, float* __restrict__ b2_out, const int* __restrict__ n_dev) {
     const unsigned lane = threadIdx.x & 31u;
     const int kIdle = (int)0x80000000;  // no ray in this lane (leaf codes are ~first >= -2^31 + 1)
     StackEntry<ANY> stack[B2_STACK];    // closest: {code, bits(t_entry)}; any-hit: code only (t_max never shrinks)
@@ -77,8 +77,9 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
                 if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
                 b = __shfl_sync(0xffffffffu, b, 0);
                 chunk_next = (long long)b;
-                chunk_end = (long long)b + want < n ? (long long)b + want : n;
-                if (chunk_next >= n) { exhausted = true; chunk_end = chunk_next; }
+                const long long n_rays = ray_count(n, n_dev);
+                chunk_end = (long long)b + want < n_rays ? (long long)b + want : n_rays;
+                if (chunk_next >= n_rays) { exhausted = true; chunk_end = chunk_next; }
             }
             const long long base = chunk_next;
             const int rank = __popc(idle_mask & ((1u << lane) - 1u));

@@ -24,7 +24,7 @@ namespace b2 {
 
 template <bool ANY, int kSwitch, int kRefill, int kBlocks>
 __global__ void __launch_bounds__(128, kBlocks) k_trace_spec(DeviceAccel A, const float4* __restrict__ rays, long long n, void* __restrict__ out,
-                                                             unsigned long long* __restrict__ counter, float* __restrict__ b2_out) {
+                                                             unsigned long long* __restrict__ counter, float* __restrict__ b2_out, const int* __restrict__ n_dev) {
     const unsigned lane = threadIdx.x & 31u;
     const int kIdle = (int)0x80000000;
     StackEntry<ANY> stack[B2_STACK];
@@ -69,11 +69,12 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec(DeviceAccel A, cons
             unsigned long long b = 0;
             if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
             b = __shfl_sync(0xffffffffu, b, 0);
-            if ((long long)b + want >= n) exhausted = true;
+            const long long n_rays = ray_count(n, n_dev);
+            if ((long long)b + want >= n_rays) exhausted = true;
             if (cur == kIdle && pend == kIdle) {
                 lane_slow = false;
                 const long long id = (long long)b + __popc(idle_mask & ((1u << lane) - 1u));
-                if (id < n) {
+                if (id < n_rays) {
                     float4 r0 = __ldg(rays + 2 * id), r1 = __ldg(rays + 2 * id + 1);
                     ray_id = (int)id;
                     r.ox = r0.x; r.oy = r0.y; r.oz = r0.z;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec(DeviceAccel A, cons
 // (profiles/r1: those loops were ~16 % of the issued instructions).  kReps node steps run per phase vote.
 template <bool ANY, int kSwitch, int kRefill, int kBlocks, int kReps>
 __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2(DeviceAccel A, const float4* __restrict__ rays, long long n, void* __restrict__ out,
-                                                              unsigned long long* __restrict__ counter, float* __restrict__ b2_out) {
+                                                              unsigned long long* __restrict__ counter, float* __restrict__ b2_out, const int* __restrict__ n_dev) {
     const unsigned lane = threadIdx.x & 31u;
     const int kIdle = (int)0x80000000;
     const int kRetry = (int)0x80000001;  // pop (again) in the next NODE step; never a leaf code (~first with first < 2^31 - 2)
@@ -233,11 +234,12 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2(DeviceAccel A, con
             unsigned long long b = 0;
             if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
             b = __shfl_sync(0xffffffffu, b, 0);
-            if ((long long)b + want >= n) exhausted = true;
+            const long long n_rays = ray_count(n, n_dev);
+            if ((long long)b + want >= n_rays) exhausted = true;
             if (cur == kIdle && pend == kIdle) {
                 lane_slow = false;
                 const long long id = (long long)b + __popc(idle_mask & ((1u << lane) - 1u));
-                if (id < n) {
+                if (id < n_rays) {
                     float4 r0 = __ldg(rays + 2 * id), r1 = __ldg(rays + 2 * id + 1);
                     ray_id = (int)id;
                     r.ox = r0.x; r.oy = r0.y; r.oz = r0.z;

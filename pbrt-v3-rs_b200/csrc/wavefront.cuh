@@ -24,13 +24,17 @@ struct DeviceScene {
     const float* light_cdf;
     float light_func_int;
     int n_lights, n_infinite;
-    // SpatialLightDistribution (light_distrib/spatial.rs): dense voxel table, filled on first use.  Row v holds
-    // func[n_lights], cdf[n_lights + 1], func_int; vox_state[v] = 0 untouched, 1 queued, 2 ready.
+    // SpatialLightDistribution (light_distrib/spatial.rs): voxel rows handed out from a pool on first touch (the
+    // reference's hash table is filled lazily too, spatial.rs:170-250).  A row holds func[n_lights], cdf[n_lights + 1],
+    // func_int; vox_state[v] = 0 untouched, 1 queued, 2 ready; vox_row[v] = the voxel's row once queued.
     int spatial;
     int n_voxels[3];
     float wb[6];          // scene.world_bound
     float* vox_table;
     int* vox_state;
+    int* vox_row;
+    int* vox_pool_next;   // rows handed out so far
+    int vox_pool_cap;
     int* vox_work;        // voxels queued by the current shade launch
     DHalton halton;
     DZeroTwo zt;
@@ -69,8 +73,9 @@ struct Wave {
     float4* pend_c;     // beta rgb at the vertex, mis scattering pdf
     int4* pend_d;       // light index, shadow slot, mis slot, -
     int* pend_q;        // path ids with a pending record
-    int* counters;      // [0] next rays, [1] shadow rays, [2] mis rays, [3] pending records, [4] sampler-dimension overflow, [5] [6] real shadow / MIS rays (tree
-                        // integrators), [8..15] bin counts, [16..23] bin cursors, [24] voxels queued, [25] slots parked (spatial light sampling)
+    int* counters;      // the current control block: [0] next rays, [1] shadow rays, [2] mis rays, [3] pending records, [4] sampler-dimension overflow,
+                        // [5] [6] real shadow / MIS rays (tree integrators), [8..15] bin counts, [16..23] bin cursors, [24] voxels queued,
+                        // [25] slots parked (spatial light sampling), [26] spatial row pool exhausted, [32..37] traversal work counters
     // sort-by-material: key per slot (0 = miss / dead, 1 + material type otherwise) and the slots grouped by key
     uint8_t* key;
     int* sorted;
@@ -84,7 +89,13 @@ struct Wave {
     // spatial light sampling: slots whose voxel was not ready in the first shade launch of a bounce
     int* deferred;
 };
-static const int kBins = 5;
+static const int kBins = 6;     // miss, matte, plastic, glass, metal, null material
+static const int kBinNull = 5;
+// Control block: 64 ints per bounce iteration.  Block 0 opens the wave ([0] = its paths); block i + 1 receives the counts
+// iteration i produces, and its [0] is the queue size of iteration i + 1.  [32..37] are the three 8-byte work counters of
+// the persistent traversal launches that consume the block's queues (closest, shadow, MIS).
+static const int kCtl = 64;
+static const int kSegIters = 16;  // iterations per control-block segment (deeper paths continue in a new segment)
 
 B2_D int meta_pack(int dim, int bounces, int spec) { return (dim & 0xffff) | ((bounces & 0xff) << 16) | ((spec & 0xff) << 24); }
 
@@ -273,7 +284,7 @@ struct DirectEst {
     bool shadow, mis;
     V3 sh_o, sh_d, mis_o, mis_d;
 };
-B2_D DirectEst estimate_direct_rays(const DeviceScene& S, const DLight& light, const SurfHit& sh, V3 hit_wo, const BSDF& bsdf, P2 u_light, P2 u_scatter) {
+template <uint32_t KM = KM_ALL> B2_D DirectEst estimate_direct_rays(const DeviceScene& S, const DLight& light, const SurfHit& sh, V3 hit_wo, const BSDF& bsdf, P2 u_light, P2 u_scatter) {
     const uint32_t kNoSpec = BSDF_ALL & ~BSDF_SPECULAR;
     // ---- estimate_direct (common.rs:146-299), light-sampling half ----
     DirectEst r;
@@ -289,8 +300,8 @@ B2_D DirectEst estimate_direct_rays(const DeviceScene& S, const DLight& light, c
     const uint32_t lflags = ls.lflags;
     float scattering_pdf = 0.0f;
     if (li_valid && light_pdf > 0.0f && !is_black(Li)) {
-        RGB f = bsdf_f(bsdf, hit_wo, wi, kNoSpec) * abs_dot(wi, sh.ns);
-        scattering_pdf = bsdf_pdf(bsdf, hit_wo, wi, kNoSpec);
+        RGB f = bsdf_f<KM>(bsdf, hit_wo, wi, kNoSpec) * abs_dot(wi, sh.ns);
+        scattering_pdf = bsdf_pdf<KM>(bsdf, hit_wo, wi, kNoSpec);
         if (!is_black(f)) {
             // VisibilityTester -> Hit::spawn_ray_to_hit (interaction/mod.rs:212-223)
             V3 origin = offset_ray_origin(sh.p, sh.p_error, sh.n, lp1 - sh.p);
@@ -307,7 +318,7 @@ B2_D DirectEst estimate_direct_rays(const DeviceScene& S, const DLight& light, c
     RGB mis_f = rgb1(0.0f);
     float mis_w = 1.0f, mis_pdf = 0.0f;
     if (light.type != LT_POINT) {
-        BxDFSample bs = bsdf_sample_f(bsdf, hit_wo, u_scatter, kNoSpec);
+        BxDFSample bs = bsdf_sample_f<KM>(bsdf, hit_wo, u_scatter, kNoSpec);
         V3 wi2 = bs.wi;
         RGB f = bs.f * abs_dot(wi2, sh.ns);
         bool sampled_specular = (bs.type & BSDF_SPECULAR) != 0;

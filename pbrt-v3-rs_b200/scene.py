@@ -500,3 +500,54 @@ class PathIntegrator:
         c = np.zeros(3, dtype=np.uint64)
         _check(lib().b200pt_scene_ray_counts(self._h, _ptr(c)), "b200pt_scene_ray_counts")
         return c
+
+    def set_memory_budget(self, n_bytes):
+        """Bytes of device memory the wave state of a render may take (0 = default); results do not depend on it."""
+        from . import _check, lib
+        if self._h is None:
+            self.preprocess()
+        _check(lib().b200pt_scene_set_memory_budget(self._h, int(n_bytes)), "b200pt_scene_set_memory_budget")
+
+
+class MultiGPURender:
+    """Integrator::render on several GPUs of this process (b200pt_multi_*): the scene replicated per device, interleaved
+    row bands, the bands gathered on devices[0] over NVLink (NCCL send / recv, or one ncclReduce for wide filters)."""
+
+    def __init__(self, scene_description, devices):
+        from . import _check, lib
+        self.sd = scene_description
+        self._desc = scene_description.to_desc()
+        self.devices = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        _check(lib().b200pt_multi_create(C.byref(self._desc), self.devices.ctypes.data_as(C.c_void_p), len(self.devices), C.byref(h)), "b200pt_multi_create")
+        self._h = h
+
+    def film_shape(self):
+        c = self._desc.film.crop
+        return (c[3] - c[1], c[2] - c[0])
+
+    def render_rows(self, band_rows=8, download=True):
+        """-> (H, W, 4) XYZ + weight film (host), or None with download=False (the film stays on devices[0])."""
+        from . import _check, _ptr, lib
+        h, w = self.film_shape()
+        film = np.zeros((h, w, 4), dtype=F32) if download else None
+        _check(lib().b200pt_multi_render(self._h, band_rows, _ptr(film)), "b200pt_multi_render")
+        return film
+
+    def info(self):
+        from . import _check, _ptr, lib
+        rays = np.zeros(3, dtype=np.uint64)
+        ms, nccl = C.c_double(0.0), C.c_int32(0)
+        _check(lib().b200pt_multi_info(self._h, _ptr(rays), C.byref(ms), C.byref(nccl)), "b200pt_multi_info")
+        return {"rays": rays, "gather_ms": ms.value, "nccl": bool(nccl.value)}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            try:
+                from . import lib
+                lib().b200pt_multi_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    __del__ = close

@@ -272,3 +272,32 @@ def test_hlbvh_accelerator_bit_exact(gpu, oracle, variant):
     sr = wl.shadow_rays(br)
     oo, _ = oacc.occluded(sr)
     assert np.array_equal(accel.occluded_batch(sr), oo)
+
+
+def test_count_work_matches_oracle_counters(gpu, oracle):
+    """The roofline numerator (bench.py: 32 B x N_node + 36 B x N_tri per ray) comes from b200pt_count_work_device; its
+    totals and per-ray counts must be the oracle's counters of the reference walk (BVHAccel::intersect / intersect_p,
+    accelerators/src/bvh/mod.rs:173-283) on the same rays: 2^16 primary, 2^16 incoherent bounce and 2^16 shadow rays
+    of the full-size C2 mesh."""
+    import torch
+    from pbrt_v3_rs_b200 import workloads as wl
+    cfg = wl.C2_FULL
+    tv = wl.c2_mesh(cfg)
+    accel = gpu.BVHAccel.from_params({"maxnodeprims": 4}, tv)
+    oacc = oracle.OracleAccel(accel.nodes, accel.ordered_prims, tv)
+    rays = wl.primary_rays(cfg["width"], cfg["height"])
+    sel = np.random.default_rng(3).choice(rays.shape[0], 1 << 16, replace=False)
+    prim = np.ascontiguousarray(rays[sel])
+    hits = accel.intersect_batch(prim)
+    bounce = wl.bounce_rays(tv, prim, hits, prim.shape[0])
+    shadow = wl.shadow_rays(bounce)
+    for rs, any_hit in ((prim, False), (bounce, False), (shadow, True)):
+        n = rs.shape[0]
+        d_r = torch.from_numpy(rs.view(np.float32).reshape(-1, 8)).cuda()
+        d_c = torch.zeros((n, 2), dtype=torch.int32, device="cuda")
+        tot = gpu.count_work_device(accel, d_r.data_ptr(), n, any_hit=any_hit, d_per_ray_ptr=d_c.data_ptr())
+        per_ray = d_c.cpu().numpy().view(np.uint32)
+        oct_ = oacc.occluded(rs)[1] if any_hit else oacc.intersect(rs)[2]
+        assert np.array_equal(per_ray, oct_), "per-ray (N_node, N_tri) differ from the oracle's counters"
+        assert tot == (int(oct_[:, 0].astype(np.int64).sum()), int(oct_[:, 1].astype(np.int64).sum()))
+        assert tot[0] > 10 * n  # a real walk, not a root miss

@@ -32,11 +32,17 @@ METRIC = "Mrays/s (closest+shadow) and path samples/s at 1080p on 1/2/4/8 B200 v
 UNIT = "Mrays/s"
 
 
-def measured_traffic():
-    """DRAM bytes per launch of the dominant kernels from the committed `ncu --set full` capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p))
+def measured_traffic(key=None):
+    """DRAM bytes per launch (and lane / issue utilisation) of the dominant kernels from the committed `ncu --set full`
+    captures under profiles/, or None.  key = None: the C2 closest / any-hit launches; "c4_rays": the HBM-resident workload."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            if key is None:
+                return d
+            if key in d:
+                return d[key]
     return None
 
 
@@ -174,46 +180,127 @@ def run_reference(args, rank):
     return 0
 
 
-def path_tracing_leg(pkg, args, rank, world):
-    """Second half of BASELINE.json's metric: path samples/s at 1920x1080 (config C3: 871 200 triangles, matte /
-    plastic / glass / metal, area + point light, maxdepth 8, 64 spp Halton), screen rows sharded over the ranks
-    in interleaved bands, film summed with one all-reduce.  Strong scaling: the image is fixed."""
+PATH_CONFIGS = {
+    "c4": "C4: %d triangles in one BVH (San-Miguel-scale stand-in), matte/plastic/glass/metal, area + point light + dim environment, power light sampling, maxdepth %d, %dx%d @ %d spp Halton, box filter",
+    "c3": "C3: %d triangles, matte/plastic/glass/metal, area+point light, power light sampling, maxdepth %d, %dx%d @ %d spp Halton, box filter",
+}
+
+
+def path_tracing_leg(pkg, args, rank, world, which):
+    """Second half of BASELINE.json's metric: path samples/s at 1920x1080, screen rows sharded over the ranks in
+    interleaved bands of 8 rows, the owned bands gathered on rank 0 over NCCL (box filter: no reduction needed).
+    which = "c4" (BASELINE's sharded configuration: 10 M triangles, 256 spp) or "c3" (871 K triangles, 64 spp).
+    Strong scaling: the image is fixed.  The timed region is render + gather; the film buffer is allocated before."""
     import torch
     import torch.distributed as dist
     from pbrt_v3_rs_b200 import multigpu
     from pbrt_v3_rs_b200 import workloads as wl
-    sd = wl.scene_c3(nu=40, nv=40, xres=160, yres=90, spp=8) if args.small else wl.scene_c3()
+    t_setup = time.time()
+    if which == "c4":
+        sd = wl.scene_c4(n_objects=6, nu=40, nv=40, xres=160, yres=90, spp=8) if args.small else wl.scene_c4()
+    else:
+        sd = wl.scene_c3(nu=40, nv=40, xres=160, yres=90, spp=8) if args.small else wl.scene_c3()
     integ = pkg.PathIntegrator(sd)
     integ.preprocess()
+    t_setup = time.time() - t_setup
     h, w = integ.film_shape()
     spp = sd.sampler["pixelsamples"]
-    times, red = [], []
+    film = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    gather = multigpu.BandGather(h, w, film.device, multigpu.BAND_ROWS)
+    sp = torch.cuda.current_stream().cuda_stream
+    times, gat = [], []
     for it in range(1 + args.path_iters):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        film = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
-        integ.render_shard_device(rank, world, film.data_ptr(), multigpu.BAND_ROWS, torch.cuda.current_stream().cuda_stream)
+        integ.render_shard_device(rank, world, film.data_ptr(), multigpu.BAND_ROWS, sp)  # zeroes the film itself
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        multigpu.reduce_film(film)
+        gather(film)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         if it:  # first iteration is the warm-up
             times.append(t2 - t0)
-            red.append(t2 - t1)
+            gat.append(t2 - t1)
     rc = integ.ray_counts()
-    t = torch.tensor([float(np.mean(times)), float(np.mean(red)), float(rc[1] + rc[2])], dtype=torch.float64, device="cuda")
-    tmax = t.clone()
+    t = torch.tensor([float(np.mean(times)), float(np.mean(gat)), float(rc[1] + rc[2]), float(np.mean(times)) - float(np.mean(gat))], dtype=torch.float64, device="cuda")
+    tmax, tmin = t.clone(), t.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    secs, red_s = float(tmax[0]), float(tmax[1])
-    return {"metric": "path samples/s", "value": h * w * spp / secs, "unit": "samples/s", "ms_per_image": secs * 1e3, "n_gpus": world,
-            "scaling": "strong", "film_allreduce_ms": red_s * 1e3, "rays_per_image": float(t[2]), "mrays_in_render": float(t[2]) / secs / 1e6,
-            "config": "C3: %d triangles, matte/plastic/glass/metal, area+point light, power light sampling, maxdepth %d, %dx%d @ %d spp Halton, box filter; rows in bands of %d dealt round-robin to the ranks"
-                      % (sd.tri_verts.shape[0], sd.integrator["maxdepth"], w, h, spp, multigpu.BAND_ROWS)}
+    secs, gat_s = float(tmax[0]), float(tmax[1])
+    n_tris = int(sd.tri_verts.shape[0])
+    out = {"metric": "path samples/s", "value": h * w * spp / secs, "unit": "samples/s", "ms_per_image": secs * 1e3, "n_gpus": world,
+           "scaling": "strong", "film_gather_ms": gat_s * 1e3, "film_gather": "owned bands -> rank 0 (dist.gather over NCCL), %d bytes per rank" % (gather.max_rows * w * 16),
+           "render_ms_slowest_rank": float(tmax[3]) * 1e3, "render_ms_fastest_rank": float(tmin[3]) * 1e3,
+           "rays_per_image": float(t[2]), "mrays_in_render": float(t[2]) / secs / 1e6, "setup_s": t_setup,
+           "config": (PATH_CONFIGS[which] % (n_tris, sd.integrator["maxdepth"], w, h, spp)) + "; rows in bands of %d dealt round-robin to the ranks" % multigpu.BAND_ROWS}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the reference's CPU path for this leg: the oracle renders a centre crop of the same scene on all host cores
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        ge.build_oracle()
+        import oracle_lib as ol
+        frac = 0.05 if which == "c4" else 0.1
+        if args.small:
+            frac = 0.5
+        sd.film["cropwindow"] = (0.5 - frac / 2, 0.5 + frac / 2, 0.5 - frac / 2, 0.5 + frac / 2)
+        _, stats, secs_o = ol.OracleScene(sd).render()
+        out["cpu_baseline"] = {"value": float(stats[0]) / secs_o, "unit": "samples/s", "cores": ol.ncpu(), "kind": "port",
+                               "sample": "centre crop (%.0f %% of width and height, %d samples) of the same scene rendered by the C++ oracle on %d threads, %.1f s" % (frac * 100, int(stats[0]), ol.ncpu(), secs_o)}
+    del integ
+    torch.cuda.empty_cache()
+    return out
+
+
+def c4_rays_roofline(pkg, args):
+    """An HBM-resident ray workload for the roofline: the C4 mesh (10 M triangles: 0.35 GB of two-box nodes + 0.64 GB of
+    triangle records, 8x the 126 MB L2) walked by 2^24 incoherent diffuse-bounce closest-hit rays, same accounting as the
+    C2 line (algorithmic bytes = 32 B x nodes tested + 36 B x triangles tested + ray in + hit out, counted in reference
+    order by b200pt_count_work_device)."""
+    import torch
+    from pbrt_v3_rs_b200 import workloads as wl
+    t0 = time.time()
+    sd = wl.scene_c4(n_objects=6, nu=40, nv=40) if args.small else wl.scene_c4()
+    tv = sd.tri_verts
+    accel = pkg.BVHAccel.from_params({"splitmethod": "sah", "maxnodeprims": 4}, tv)
+    n_prim = 1 << (14 if args.small else 24)
+    side = int(np.sqrt(n_prim))
+    prim = wl.primary_rays_lookat(side, n_prim // side, sd.camera["eye"], sd.camera["look"], sd.camera["up"], float(sd.camera["fov"]))
+    hits = accel.intersect_batch(prim)
+    bounce = wl.bounce_rays(tv, prim, hits, prim.shape[0])
+    n = int(bounce.shape[0])
+    d_rays = torch.from_numpy(bounce.view(np.float32).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    nn, nt = pkg.count_work_device(accel, d_rays.data_ptr(), n, False)
+    bytes_alg = 32 * nn + 36 * nt + (32 + 16) * n
+    stream = torch.cuda.current_stream()
+    for _ in range(3):
+        accel.intersect_batch_device(d_rays.data_ptr(), n, d_hits.data_ptr(), stream.cuda_stream, 0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    for k in range(args.steps):
+        accel.intersect_batch_device(d_rays.data_ptr(), n, d_hits.data_ptr(), stream.cuda_stream, 0)
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[-1]) / args.steps
+    peak, peak_src = measured_peak()
+    tr = measured_traffic("c4_rays")
+    ach = bytes_alg / (ms * 1e-3) / 1e9
+    out = {"bound": "hbm", "kernel": "k_trace_spec2<closest>", "workload": "C4-rays: %d-triangle mesh (%.2f GB of node + triangle records, HBM-resident), %d incoherent diffuse-bounce closest-hit rays" % (tv.shape[0], (accel.nodes.shape[0] // 2 * 64 + tv.shape[0] * 64) / 1e9, n),
+           "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,
+           "traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
+           "traffic_over_algorithmic": (tr["dram_bytes_per_launch"] / bytes_alg) if tr else None,
+           "nodes_per_ray": nn / n, "tris_per_ray": nt / n, "launch_ms": ms, "mrays": n / (ms * 1e-3) / 1e6, "setup_s": time.time() - t0}
+    if tr:
+        for k in ("lanes_active", "issue_busy_pct", "l2_hit_pct", "dram_gbs"):
+            if k in tr:
+                out[k] = tr[k]
+    del accel, d_rays, d_hits
+    torch.cuda.empty_cache()
+    return out
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -260,6 +347,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-path", action="store_true", help="skip the path-tracing (samples/s) leg")
     ap.add_argument("--path-iters", type=int, default=3)
+    ap.add_argument("--no-c4-rays", action="store_true", help="skip the HBM-resident C4-rays roofline line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -348,7 +436,9 @@ def main():
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         assert torch.equal(h_hits.view(torch.int32), d_hits.cpu().view(torch.int32)) and torch.equal(h_occ, d_occ.cpu()), "e2e results differ from the resident path"
 
-    path = None if args.no_path else path_tracing_leg(pkg, args, rank, world)
+    path = None if args.no_path else path_tracing_leg(pkg, args, rank, world, "c4")
+    path_c3 = None if args.no_path else path_tracing_leg(pkg, args, rank, world, "c3")
+    roof_c4 = c4_rays_roofline(pkg, args) if (rank == 0 and not args.no_c4_rays) else None
 
     # max over ranks
     t = torch.tensor([total_ms, closest_ms, shadow_ms, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
@@ -365,7 +455,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(w, args),
                 "closest_mrays": n / (closest_ms * 1e-3) / 1e6, "anyhit_mrays": n / (shadow_ms * 1e-3) / 1e6,
-                "roofline": {"bound": "hbm", "kernel": {0: "k_trace_spec2<closest>", 3: "k_trace_persistent<closest>", 4: "k_trace_phased<closest>", 5: "k_trace_spec<closest>"}.get(args.variant, "k_trace_simple<closest,%d>" % args.variant),
+                "roofline": {"bound": "hbm", "limiter": "instruction issue at partial lane occupancy: the 84 MB BVH is L2-resident, DRAM moves ~3 % of the algorithmic bytes (see lanes_active / issue_busy_pct; the HBM-resident workload is roofline_c4)",
+                             "lanes_active": tr.get("closest_lanes_active") if tr else None, "issue_busy_pct": tr.get("closest_issue_busy_pct") if tr else None,
+                             "kernel": {0: "k_trace_spec2<closest>", 3: "k_trace_persistent<closest>", 4: "k_trace_phased<closest>", 5: "k_trace_spec<closest>"}.get(args.variant, "k_trace_simple<closest,%d>" % args.variant),
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": tr["closest_dram_bytes_per_launch"] if tr else None,
                              "traffic_source": tr["source"] if tr else None, "peak_source": peak_src,
                              "note": "algorithmic bytes (32 B/node test + 36 B/triangle test + ray in + hit out, counted in reference order) over launch time; the 1 M-triangle BVH is L2-resident so DRAM traffic is ~3 % of the algorithmic bytes and the kernel is issue-bound (profiles/README.md)",
@@ -376,6 +468,9 @@ def main():
                 "gpu_launches": int(launches), "clocks": clk, "setup_s": w["setup_s"]}
         if path is not None:
             line["path_tracing"] = path
+            line["path_tracing_c3"] = path_c3
+        if roof_c4 is not None:
+            line["roofline_c4"] = roof_c4
         if e2e_ms is not None:
             line["e2e"] = {"value": world * 2 * n / (e2e_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n,
                            "ms_per_step": e2e_max}

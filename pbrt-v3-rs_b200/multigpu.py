@@ -3,10 +3,11 @@
 The reference renders 16x16 tiles from a work queue on one host
 (core/src/integrator/sampler_integrator.rs:252-296).  Here the scene is replicated on every GPU, the
 pixel rows are cut into bands dealt round-robin to the ranks (interleaving balances sky and geometry),
-each rank renders its bands into a zero-initialised film of the full window, and ONE collective — a sum
-all-reduce of the {X, Y, Z, weight} film (33 MB at 1080p) over NCCL / NVLink — assembles the image.  With a
-box filter the rows are disjoint, so the sum only fills zeros; with wider filters the aprons add up.
-Nothing else crosses GPUs: the path has no data-path collective.
+each rank renders its bands into a zero-initialised film of the full window, and ONE collective over NCCL / NVLink
+assembles the image: with a box-sized filter the rows are disjoint, so every rank ships only the bands it owns to rank 0
+(a gather of 1 / world of the film per rank); with wider filters the aprons overlap and the films are summed (all-reduce).
+Nothing else crosses GPUs: the path has no data-path collective.  This module is the one-process-per-GPU (torchrun) form;
+one process driving all GPUs goes through b200pt_multi_render (csrc/multi_gpu.cu, `MultiGPURender`).
 """
 import numpy as np
 
@@ -23,23 +24,64 @@ def shard_rows(height, n_shards, shard, band_rows=BAND_ROWS):
 
 
 def reduce_film(film, group=None):
-    """Sum all-reduce of a (H, W, 4) film tensor across the process group (NCCL on GPUs, gloo in CPU tests)."""
+    """Sum all-reduce of a (H, W, 4) film tensor across the process group (NCCL on GPUs, gloo in CPU tests): the
+    general form, needed when the filter is wider than a pixel and neighbouring bands overlap by its apron."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(film, op=dist.ReduceOp.SUM, group=group)
     return film
 
 
-def render_distributed(integrator, band_rows=BAND_ROWS):
-    """Renders this rank's shard on the current CUDA device and all-reduces the film.  Returns the (H, W, 4)
-    XYZ+weight film as a CUDA tensor, identical on every rank."""
+class BandGather:
+    """Gather of OWNED bands for box-sized filters (radius <= 0.5 px): a rank's samples only reach its own rows, so each
+    rank ships just those rows (1 / world of the film) to rank 0 instead of all-reducing the whole film: one
+    `dist.gather` of (rows_per_rank, W, 4) blocks over NCCL / NVLink, then rank 0 drops them into place.  Index tensors
+    and staging buffers are built once (outside any timed region)."""
+
+    def __init__(self, height, width, device, band_rows=BAND_ROWS, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rows = [torch.from_numpy(shard_rows(height, self.world, r, band_rows)).to(device) for r in range(self.world)]
+        self.max_rows = max(int(r.numel()) for r in self.rows)
+        self.mine = torch.zeros((self.max_rows, width, 4), dtype=torch.float32, device=device)
+        self.parts = [torch.zeros_like(self.mine) for _ in range(self.world)] if self.rank == 0 else None
+
+    def __call__(self, film):
+        """film: this rank's (H, W, 4) shard film; on rank 0 it holds the whole image afterwards."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return film
+        my = self.rows[self.rank]
+        self.mine[:my.numel()].copy_(film.index_select(0, my))
+        dist.gather(self.mine, self.parts, dst=0, group=self.group)
+        if self.rank == 0:
+            for r in range(1, self.world):
+                film.index_copy_(0, self.rows[r], self.parts[r][:self.rows[r].numel()])
+        return film
+
+
+def render_distributed(integrator, band_rows=BAND_ROWS, gather=None):
+    """Renders this rank's shard on the library's device and assembles the film: with a box-sized filter the owned bands
+    are gathered on rank 0 (BandGather; other ranks keep their shard), otherwise the films are all-reduced.  Returns the
+    (H, W, 4) XYZ+weight film as a CUDA tensor."""
     import torch
     import torch.distributed as dist
+    from . import current_device, init
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
+    if current_device() < 0:
+        init(torch.cuda.current_device())
+    if current_device() != torch.cuda.current_device():
+        raise RuntimeError("render_distributed: torch's current device (%d) is not the library's device (%d); call pkg.init(local_rank) after torch.cuda.set_device(local_rank)"
+                           % (torch.cuda.current_device(), current_device()))
     if integrator.handle is None:
         integrator.preprocess()
     h, w = integrator.film_shape()
     film = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
     integrator.render_shard_device(rank, world, film.data_ptr(), band_rows, torch.cuda.current_stream().cuda_stream)
+    if integrator.filter_radius()[1] <= 0.5:
+        return (gather or BandGather(h, w, film.device, band_rows))(film)
     return reduce_film(film)

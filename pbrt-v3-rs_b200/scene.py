@@ -448,6 +448,9 @@ class PathIntegrator:
         c = self._desc.film.crop
         return (c[3] - c[1], c[2] - c[0])
 
+    def filter_radius(self):
+        return tuple(self._desc.film.filter_radius)
+
     def render_rows(self, row_begin=0, row_end=None):
         """Renders pixel rows [row_begin,row_end) of the cropped window; returns (H, W, 4) XYZ+weight."""
         from . import _check, _ptr, lib

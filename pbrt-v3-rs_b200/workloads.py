@@ -154,6 +154,23 @@ def primary_rays(width, height, eye=(0.0, 0.0, -3.5), fov_deg=38.0):
     return rays
 
 
+def primary_rays_lookat(width, height, eye, look, up=(0.0, 1.0, 0.0), fov_deg=40.0):
+    """primary_rays through a look-at camera (right-handed basis from eye / look / up; the fov spans the shorter image side)."""
+    rays = primary_rays(width, height, eye=(0.0, 0.0, 0.0), fov_deg=fov_deg)
+    eye, look, up = (np.asarray(v, dtype=np.float64) for v in (eye, look, up))
+    f = look - eye
+    f /= np.linalg.norm(f)
+    r = np.cross(up, f)
+    r /= np.linalg.norm(r)
+    u = np.cross(f, r)
+    d = rays["d"].astype(np.float64)
+    dw = d[:, 0:1] * r + d[:, 1:2] * u + d[:, 2:3] * f
+    dw /= np.linalg.norm(dw, axis=1, keepdims=True)
+    rays["d"] = dw.astype(F32)
+    rays["o"] = eye.astype(F32)
+    return rays
+
+
 def bounce_rays(tri_verts, primary, hits, n, shuffle_seed=3):
     """Diffuse-bounce rays: origin = hit point of a primary ray nudged off the surface, direction =
     cosine-weighted about the geometric normal (facing the incoming side), then shuffled so that

@@ -1,5 +1,6 @@
 """N > 1 host logic on CPU (gloo, world_size 2): row-band sharding partitions the image and the one collective of
-the path — a sum all-reduce of the per-rank films — reassembles it."""
+the path — a gather of the owned bands on rank 0 (box-sized filters), or a sum all-reduce of the per-rank films (wider
+filters) — reassembles it."""
 import os
 import socket
 
@@ -31,8 +32,14 @@ def _worker(rank, world, port, h, w, q):
     rows = multigpu.shard_rows(h, world, rank)
     part = torch.zeros_like(full)
     part[rows] = full[rows]
-    out = multigpu.reduce_film(part)
-    q.put((rank, bool(torch.equal(out, full)), int(rows.size)))
+    out = multigpu.reduce_film(part.clone())
+    ok = bool(torch.equal(out, full))
+    # the gather of owned bands (box-sized filters): rank 0 ends up with the whole image, nobody ships more than its rows
+    g = multigpu.BandGather(h, w, "cpu")
+    got = g(part.clone())
+    ok = ok and (bool(torch.equal(got, full)) if rank == 0 else bool(torch.equal(got, part)))
+    ok = ok and g.mine.shape[0] == max(multigpu.shard_rows(h, world, r).size for r in range(world))
+    q.put((rank, ok, int(rows.size)))
     dist.destroy_process_group()
 
 

@@ -382,3 +382,143 @@ def test_area_light_on_a_mesh_with_vertex_normals(gpu, oracle, integrator, inwar
     assert (img.mean() > 0.01) == (twosided or not inward)  # inward-facing normals: the sphere emits into itself only
     rc = integ.ray_counts()
     assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0.01 * stats[1]
+
+
+@pytest.mark.parametrize("filt,integrator", [("box", "path"), ("gaussian", "path"), ("box", "whitted")])
+def test_memory_budget_does_not_change_the_image(gpu, filt, integrator):
+    """b200pt_scene_set_memory_budget: the wave state is bounded by a byte budget and the render is cut into as many
+    waves as that needs; the film keeps running sums between waves (k_film), in the same pixel-major / sample order
+    (core/src/film/film_tile.rs:62-108), so every bit of the film is independent of the budget - also with a filter
+    wider than a pixel, where a wave boundary falls between samples that reach the same pixel."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="all", res=80, spp=24, maxdepth=4, strategy="power", filt=filt)
+    sd.integrator.update(name=integrator)
+    integ = gpu.PathIntegrator(sd)
+    full = integ.render_rows()
+    rc = integ.ray_counts().copy()
+    assert full[..., 3].min() > 0
+    integ.set_memory_budget(8 << 20)      # 8 MiB: ~16 K paths per wave -> about ten waves for 153 600+ samples
+    small = integ.render_rows()
+    assert np.array_equal(small, full)
+    assert np.array_equal(integ.ray_counts(), rc)
+    integ.set_memory_budget(0)
+    assert np.array_equal(integ.render_rows(), full)
+
+
+def test_null_material_is_passed_through(gpu, oracle):
+    """Material "none" (api/src/graphics_state.rs:336 -> None): PathIntegrator::li re-spawns the ray through the surface
+    without counting a bounce or drawing samples (integrators/src/path.rs:141-150); an emissive primitive without a
+    material still emits.  Point light + area light => every transcendental on the path is exact: bit parity."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    from pbrt_v3_rs_b200.scene import SceneDescription
+
+    def build(with_null):
+        sd = SceneDescription()
+        m = sd.add_material(type="plastic")
+        g = sd.add_material(type="matte", Kd=(0.4, 0.4, 0.4))
+        sd.add_mesh(wl.displaced_sphere(24, 12), m)
+        sd.add_mesh(wl.ground_quad(), g)
+        if with_null:  # a shell around the sphere and a curtain in front of the camera, both without a material
+            sd.add_mesh(wl.displaced_sphere(16, 8, radius=1.6, amplitude=0.0), -1)
+            q = np.array([[-3, -1, -2.5], [3, -1, -2.5], [3, 3, -2.5], [-3, 3, -2.5]], dtype=np.float32)
+            sd.add_mesh(np.stack([np.concatenate([q[0], q[1], q[2]]), np.concatenate([q[0], q[2], q[3]])]), -1)
+        lq = np.array([[-1.5, 3.0, -1.0], [1.5, 3.0, -1.0], [1.5, 3.0, 1.0], [-1.5, 3.0, 1.0]], dtype=np.float32)
+        sd.add_mesh(np.stack([np.concatenate([lq[0], lq[1], lq[2]]), np.concatenate([lq[0], lq[2], lq[3]])]), -1 if with_null else g,
+                    area_light=dict(L=(15, 15, 15), twosided=True))
+        sd.add_point_light((1.5, 2.5, -3.0), (30, 30, 30))
+        sd.camera.update(eye=(0.0, 1.2, -4.0), look=(0.0, -0.1, 0.0), up=(0, 1, 0), fov=40.0)
+        sd.film.update(xresolution=32, yresolution=32)
+        sd.sampler.update(type="halton", pixelsamples=4)
+        sd.integrator.update(maxdepth=5, lightsamplestrategy="power")
+        return sd
+    sd = build(True)
+    integ = gpu.PathIntegrator(sd)
+    osc = oracle.OracleScene(sd)
+    ps = _pairs(32, 4)
+    li, rays = integ.li(ps)
+    oli = osc.li(ps)
+    assert rays.tobytes() == osc.camera_rays(ps).tobytes()
+    same = (li.view(np.uint32) == oli.view(np.uint32)).all(1)
+    assert same.mean() >= 0.995, same.mean()
+    img = integ.render()
+    ref, stats, _ = osc.render()
+    assert ss.rel_rmse(img, ref) <= TOL
+    assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]
+    # the surfaces are really crossed: more closest-hit rays than the same scene without them, and shadow rays still see them as occluders
+    plain = gpu.PathIntegrator(build(False))
+    plain.render()
+    assert int(integ.ray_counts()[1]) > int(plain.ray_counts()[1])
+    # the tree integrators do not take primitives without a material
+    sd.integrator.update(name="whitted")
+    with pytest.raises(gpu.B200PTError):
+        gpu.PathIntegrator(sd).preprocess()
+
+
+def test_deep_paths_continue_in_a_new_control_segment(gpu, oracle):
+    """maxdepth above the 16 iterations one segment of control blocks holds: the bounce loop reads the surviving queue
+    size back once per segment and continues (mirror-like metal box: paths really get that deep)."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["glass"], light="point", res=24, spp=4, maxdepth=40)
+    shell = sd.add_material(type="matte", Kd=(0.9, 0.9, 0.9))
+    sd.add_mesh(wl.displaced_sphere(16, 8, radius=9.0, amplitude=0.0), shell)  # a closed room: no path escapes
+    sd.integrator.update(rrthreshold=0.0)  # no Russian roulette: every path lives until maxdepth
+    integ = gpu.PathIntegrator(sd)
+    osc = oracle.OracleScene(sd)
+    ps = _pairs(24, 4)
+    li, _ = integ.li(ps)
+    oli = osc.li(ps)
+    same = (li.view(np.uint32) == oli.view(np.uint32)).all(1)
+    assert same.mean() >= 0.995, same.mean()
+    img = integ.render()
+    ref, stats, _ = osc.render()
+    assert ss.rel_rmse(img, ref) <= TOL
+    assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]
+    assert int(stats[1]) > 30 * int(stats[0])  # the paths really are that long
+
+
+def test_path_depth_beyond_the_sampler_tables_is_refused(gpu):
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["matte"], res=8, spp=2, maxdepth=125)  # 5 + 8 * 125 > 1000 Halton dimensions
+    with pytest.raises(gpu.B200PTError):
+        gpu.PathIntegrator(sd).preprocess()
+    sd.integrator.update(maxdepth=124)
+    gpu.PathIntegrator(sd).preprocess()
+
+
+def test_spatial_row_pool_exhaustion_is_reported(gpu, monkeypatch):
+    """SpatialLightDistribution rows are handed out on first touch; a pool too small for the voxels a render reaches is an
+    error, not a silently different image."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["matte"], light="all", res=48, spp=4, strategy="spatial")
+    full = gpu.PathIntegrator(sd).render_rows()
+    assert full[..., 3].min() > 0
+    monkeypatch.setenv("B200PT_SPATIAL_BUDGET", "1024")  # -> the minimum pool of 64 rows
+    integ = gpu.PathIntegrator(sd)
+    with pytest.raises(gpu.B200PTError, match="spatial"):
+        integ.render_rows()
+
+
+def test_render_multi_on_the_visible_devices(gpu, oracle):
+    """b200pt_multi_*: the scene replicated on every visible GPU of this process, interleaved row bands, bands gathered on
+    the first device (NCCL send / recv; ncclReduce for the gaussian filter).  Same film as one device renders (box:
+    bit-identical, every sample is taken by exactly one device; gaussian: up to the rounding of summing shard films)."""
+    import torch
+    from pbrt_v3_rs_b200 import workloads as wl
+    n = torch.cuda.device_count()
+    for filt in ("box", "gaussian"):
+        sd = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="all", res=72, spp=8, maxdepth=4, strategy="power", filt=filt)
+        single = gpu.PathIntegrator(sd)
+        full = single.render_rows()
+        rc = [int(x) for x in single.ray_counts()]
+        for devs in sorted({1, n}):
+            multi = gpu.MultiGPURender(sd, list(range(devs)))
+            film = multi.render_rows(band_rows=8)
+            info = multi.info()
+            if filt == "box":
+                assert np.array_equal(film, full), (filt, devs)
+            else:
+                assert np.allclose(film, full, rtol=2e-6, atol=1e-6), (filt, devs)
+            assert [int(x) for x in info["rays"]] == rc or filt == "gaussian"
+            assert int(info["rays"][0]) == rc[0]
+            multi.close()
+    assert gpu.current_device() == 0

@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <vector>
 
@@ -403,6 +404,146 @@ __global__ void __launch_bounds__(64) k_zerotwo_tiles(int sb0, int sb1, int sb2,
     }
 }
 
+// ---- (0,2)-sequence, tile-sequential mode -----------------------------------------------------------------------
+// With fewer pre-generated "dimensions" than a path can ask for (the reference's default is 4,
+// samplers/src/zero_two_sequence.rs:157) PixelSampler::get_1d / get_2d fall back to the TILE sampler's RNG inside li()
+// (pixel_sampler.rs:88-110), so the stream position of every later sample of the tile depends on the lengths of the
+// paths before it: a tile is a sequential stream.  Tiles are independent (clone_sampler(tile_idx),
+// sampler_integrator.rs:323), so the wave holds ONE path per tile: every step each tile moves on to its next
+// (pixel, sample) in the reference's order (start_pixel draws the pixel's tables from the tile RNG, also for pixels
+// outside the integrator's pixel bounds, sampler_integrator.rs:343-350), the wave runs that path to its end, and its
+// radiance goes to the (pixel, sample) place of the sample store.  256 x spp waves of (number of tiles) paths: a slow
+// path by construction, bit-compatible with the reference's streams.
+struct ZtSeq {
+    DPcg32* rng;     // [slot] the tile's PCG32 stream (also read by smp_1d / smp_2d through DeviceScene::zt.rng)
+    int* tile;       // [slot] reference tile index
+    int* cursor;     // [slot] pixel position inside the tile, row-major
+    int* samp;       // [slot] sample number of the path in flight
+    int* dst;        // [slot] place of the path's sample in the sample store, -1 = nowhere (rows of another shard)
+    uint32_t* scr1;  // tables of the slot's CURRENT pixel: [slot][dims], [slot][dims][2], [slot][dims][spp] x 2
+    uint32_t* scr2;
+    uint16_t* perm1;
+    uint16_t* perm2;
+    int dims, spp, ntx;
+};
+// ZeroTwoSequenceSampler::start_pixel (zero_two_sequence.rs:65-111): per 1-D slot one scramble, per 2-D slot two, then
+// spp one-element shuffles (one draw each: bounded_uniform_u32(0, 1) has threshold 0) and one shuffle of the spp samples.
+B2_D void zt_start_pixel(DPcg32& rng, int dims, int spp, bool store, uint32_t* scr1, uint16_t* perm1, uint32_t* scr2, uint16_t* perm2) {
+    for (int pass = 0; pass < 2; ++pass)
+        for (int d = 0; d < dims; ++d) {
+            const uint32_t s0 = pcg_next(rng), s1 = pass ? pcg_next(rng) : 0u;
+            for (int i = 0; i < spp; ++i) (void)pcg_next(rng);
+            uint16_t* o = (pass ? perm2 : perm1) + (size_t)d * spp;
+            if (store) for (int i = 0; i < spp; ++i) o[i] = (uint16_t)i;
+            for (int i = 0; i < spp; ++i) {
+                const int other = i + (int)pcg_bounded(rng, (uint32_t)(spp - i));
+                if (store) { const uint16_t t = o[i]; o[i] = o[other]; o[other] = t; }
+            }
+            if (store) {
+                if (pass == 0) scr1[d] = s0;
+                else { scr2[2 * d] = s0; scr2[2 * d + 1] = s1; }
+            }
+        }
+}
+// Camera sample + ray of sample `smp` of pixel (px, py) for the path in slot p (Sampler::get_camera_sample, k_raygen).
+B2_D Ray32 zt_seq_emit(const DeviceScene& S, const Wave& W, int p, int px, int py, int smp, bool live, P2* pf_out) {
+    const unsigned long long key = ((unsigned long long)p << 16) | (unsigned long long)smp;
+    int dim = 0;
+    const P2 fs = smp_2d(S, key, dim);
+    const P2 pf = mk2((float)px + fs.x, (float)py + fs.y);
+    const float tu = smp_1d(S, key, dim);
+    const P2 pl = smp_2d(S, key, dim);
+    const Ray32 r = camera_ray(S.camera, pf, tu, pl);
+    W.ray[0][2 * p] = make_float4(r.ox, r.oy, r.oz, live ? r.tmax : -1.0f);
+    W.ray[0][2 * p + 1] = make_float4(r.dx, r.dy, r.dz, r.time);
+    W.qpid[0][p] = p;
+    W.L[p] = make_float4(0.0f, 0.0f, 0.0f, live ? 1.0f : 0.0f);
+    W.beta[p] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    W.hidx[p] = key;
+    W.meta[p] = meta_pack(dim, live ? 0 : 255, 0);
+    *pf_out = pf;
+    return r;
+}
+B2_D void zt_seq_dead(const Wave& W, int p) {
+    W.ray[0][2 * p] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+    W.ray[0][2 * p + 1] = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+    W.qpid[0][p] = p;
+    W.L[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    W.beta[p] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    W.hidx[p] = 0ull;
+    W.meta[p] = meta_pack(0, 255, 0);
+}
+// One step of every tile of the group: the next sample of the current pixel, or start_pixel on the next pixel(s).
+__global__ void __launch_bounds__(64) k_zt_seq_next(DeviceScene S, Wave W, ZtSeq Z, int n_slots, int first_step, const int* __restrict__ row_index,
+                                                    long long first_local, float2* __restrict__ p_film_out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_slots) return;
+    const int tile = Z.tile[p], tx = tile % Z.ntx, ty = tile / Z.ntx;
+    const int x0 = S.sb[0] + tx * 16, x1 = min(x0 + 16, S.sb[2]), y0 = S.sb[1] + ty * 16, y1 = min(y0 + 16, S.sb[3]);
+    const int w = x1 - x0, npix = w * (y1 - y0), spp = Z.spp;
+    DPcg32 rng;
+    int cur, smp;
+    if (first_step) { pcg_set_sequence(rng, (unsigned long long)tile); cur = -1; smp = spp - 1; }  // clone_sampler(tile_idx) -> RNG::new(seed)
+    else { rng = Z.rng[p]; cur = Z.cursor[p]; smp = Z.samp[p]; }
+    if (cur < npix) {
+        if (cur >= 0 && smp + 1 < spp) smp += 1;  // start_next_sample
+        else {
+            for (++cur; cur < npix; ++cur) {
+                zt_start_pixel(rng, Z.dims, spp, true, Z.scr1 + (size_t)p * Z.dims, Z.perm1 + (size_t)p * Z.dims * spp, Z.scr2 + (size_t)p * Z.dims * 2,
+                               Z.perm2 + (size_t)p * Z.dims * spp);
+                const int px = x0 + cur % w, py = y0 + cur / w;
+                if (px >= S.pb[0] && px < S.pb[2] && py >= S.pb[1] && py < S.pb[3]) break;  // sampler_integrator.rs:348: checked after start_pixel
+            }
+            smp = 0;
+        }
+    }
+    Z.rng[p] = rng; Z.cursor[p] = cur; Z.samp[p] = smp;
+    if (cur >= npix) { zt_seq_dead(W, p); Z.dst[p] = -1; return; }
+    const int px = x0 + cur % w, py = y0 + cur / w;
+    P2 pf;
+    zt_seq_emit(S, W, p, px, py, smp, true, &pf);
+    const int krow = row_index[py - S.sb[1]];
+    int dst = -1;
+    if (krow >= 0) {
+        dst = (int)((((long long)krow * (S.sb[2] - S.sb[0]) + (px - S.sb[0])) * spp + smp) - first_local);
+        p_film_out[dst] = make_float2(pf.x, pf.y);
+    }
+    Z.dst[p] = dst;
+}
+// Explicit (x, y, sample) triples (b200pt_li_batch): every entry gets a fresh copy of its tile's stream positioned as
+// render_tile would reach the pixel if no earlier path had drawn from it - start_pixel on every earlier pixel of the
+// tile, then on the pixel itself (the oracle's sampler_at convention; a render's true stream position also depends on
+// the earlier paths, which only the render itself reproduces).
+__global__ void __launch_bounds__(64) k_zt_seq_list(DeviceScene S, Wave W, ZtSeq Z, int n, const int* __restrict__ list, float4* __restrict__ rays_out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int px = list[3 * p], py = list[3 * p + 1], smp = list[3 * p + 2];
+    const int tx = (px - S.sb[0]) / 16, ty = (py - S.sb[1]) / 16;
+    const int x0 = S.sb[0] + tx * 16, x1 = min(x0 + 16, S.sb[2]), y0 = S.sb[1] + ty * 16;
+    DPcg32 rng;
+    pcg_set_sequence(rng, (unsigned long long)(ty * Z.ntx + tx));
+    const int w = x1 - x0, own = (py - y0) * w + (px - x0);
+    for (int cur = 0; cur <= own; ++cur)
+        zt_start_pixel(rng, Z.dims, Z.spp, cur == own, Z.scr1 + (size_t)p * Z.dims, Z.perm1 + (size_t)p * Z.dims * Z.spp, Z.scr2 + (size_t)p * Z.dims * 2,
+                       Z.perm2 + (size_t)p * Z.dims * Z.spp);
+    Z.rng[p] = rng;
+    P2 pf;
+    const Ray32 r = zt_seq_emit(S, W, p, px, py, smp, true, &pf);
+    if (rays_out) { rays_out[2 * p] = make_float4(r.ox, r.oy, r.oz, r.tmax); rays_out[2 * p + 1] = make_float4(r.dx, r.dy, r.dz, r.time); }
+}
+// The finished paths' radiances go to their (pixel, sample) places (sanitised like k_store_samples).
+__global__ void __launch_bounds__(256) k_zt_seq_store(Wave W, const int* __restrict__ dst, int n, float4* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int d = dst[p];
+    if (d < 0) return;
+    const float4 l = W.L[p];
+    RGB c = rgb(l.x, l.y, l.z);
+    const float y = lum_y(c);
+    if (isnan(c.r) || isnan(c.g) || isnan(c.b) || y < -1e-5f || isinf(y)) c = rgb1(0.0f);
+    out[d] = make_float4(c.r, c.g, c.b, l.w);
+}
+
 // ---- K4': resolve pending direct lighting ------------------------------------------------------
 __global__ void __launch_bounds__(256) k_resolve(DeviceScene S, Wave W) {
     const int n_pend = W.counters[3];
@@ -444,7 +585,9 @@ __global__ void k_wave_end(const int* ctl, int n_blocks, int n_camera, unsigned 
     unsigned long long closest = 0, shadow = 0, flags = 0;
     for (int b = 0; b < n_blocks; ++b) {
         const int* c = ctl + b * kCtl;
-        closest += (unsigned long long)c[0];                  // the queue this block's counts opened (block 0: the camera rays)
+        // the queue this block's counts opened (block 0: the camera rays); the last block's queue is traced by the next
+        // segment, as its block 0, or not at all
+        if (b + 1 < n_blocks) closest += (unsigned long long)c[0];
         if (b > 0) { closest += (unsigned long long)c[2]; shadow += (unsigned long long)c[1]; }
         if (c[26]) flags |= 1ull;
     }
@@ -587,6 +730,10 @@ struct SceneImpl {
     uint32_t *d_zt_scr1 = nullptr, *d_zt_scr2 = nullptr;
     uint16_t *d_zt_perm1 = nullptr, *d_zt_perm2 = nullptr, *d_zt_scratch = nullptr;
     long long zt_pix_cap = 0;
+    // tile-sequential (0,2) mode ("dimensions" below the path's worst case): one path per tile, see ZtSeq
+    bool zt_seq = false;
+    ZtSeq ztq{};
+    int ztq_cap = 0;
     int spp = 1;                 // samples per pixel actually taken (rounded up to a power of two for the (0,2) sampler)
     int* d_rows = nullptr;       // sample rows owned by the current shard
     int* d_row_index = nullptr;  // sample row -> position in d_rows, -1 = not owned
@@ -1110,11 +1257,11 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     }
     if (d->sampler.type == B200PT_SAMPLER_ZEROTWO) {
         // Past its pre-generated slots the reference's PixelSampler draws from the TILE's RNG inside li(), which makes the
-        // stream position of every later pixel depend on earlier path lengths (SURVEY §7 "ZeroTwo sequencing"): inherently
-        // sequential.  Supported here when "dimensions" covers the path's worst case, so li() never touches the RNG.
-        int need1 = 1 + 2 * d->integrator.max_depth, need2 = 2 + 3 * d->integrator.max_depth;
-        if (d->sampler.dimensions < need1 || d->sampler.dimensions < need2 || d->sampler.dimensions > 255) {
-            b200pt_set_error("b200pt_scene_create: 02sequence needs \"dimensions\" >= 2 + 3 * maxdepth (and <= 255) so that li() never draws from the tile RNG");
+        // stream position of every later pixel depend on earlier path lengths (SURVEY §7 "ZeroTwo sequencing").  When
+        // "dimensions" covers the path's worst case li() never touches the RNG and all samples run in parallel; otherwise
+        // (the reference's default is 4) the render takes the tile-sequential mode (ZtSeq), one path per tile at a time.
+        if (d->sampler.dimensions < 0 || d->sampler.dimensions > 255) {
+            b200pt_set_error("b200pt_scene_create: 02sequence \"dimensions\" must be in [0, 255]");
             return B200PT_ERR_UNSUPPORTED;
         }
         if (d->sampler.spp > 32768) { b200pt_set_error("b200pt_scene_create: 02sequence pixelsamples > 32768"); return B200PT_ERR_UNSUPPORTED; }
@@ -1173,6 +1320,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     s->sampler = d->sampler;
     s->spp = d->sampler.spp;
     if (d->sampler.type == B200PT_SAMPLER_ZEROTWO || d->sampler.type == B200PT_SAMPLER_SOBOL) { int p2 = 1; while (p2 < s->spp) p2 <<= 1; s->spp = p2; }  // zero_two_sequence.rs:23-32, sobol.rs:28-37
+    s->zt_seq = d->sampler.type == B200PT_SAMPLER_ZEROTWO && (d->sampler.dimensions < 1 + 2 * d->integrator.max_depth || d->sampler.dimensions < 2 + 3 * d->integrator.max_depth);
     D.sampler_type = d->sampler.type;
 
     // primitives in original order with their material / light / flags
@@ -1395,6 +1543,9 @@ void b200pt_scene_destroy(b200pt_scene* sc) {
     if (sc->impl.d_totals) cudaFree(sc->impl.d_totals);
     if (sc->impl.h_pinned) cudaFreeHost(sc->impl.h_pinned);
     if (sc->impl.ev_shade) cudaEventDestroy(sc->impl.ev_shade);
+    for (void* p : {(void*)sc->impl.ztq.rng, (void*)sc->impl.ztq.tile, (void*)sc->impl.ztq.cursor, (void*)sc->impl.ztq.samp, (void*)sc->impl.ztq.dst, (void*)sc->impl.ztq.scr1,
+                    (void*)sc->impl.ztq.scr2, (void*)sc->impl.ztq.perm1, (void*)sc->impl.ztq.perm2})
+        if (p) cudaFree(p);
     for (void* p : {(void*)sc->impl.d_zt_scr1, (void*)sc->impl.d_zt_scr2, (void*)sc->impl.d_zt_perm1, (void*)sc->impl.d_zt_perm2, (void*)sc->impl.d_zt_scratch})
         if (p) cudaFree(p);
     if (sc->impl.d_rows) cudaFree(sc->impl.d_rows);
@@ -1412,7 +1563,7 @@ int b200pt_scene_ray_counts(const b200pt_scene* s, uint64_t counts[3]) {
 
 // Builds the (0,2)-sequence tables for the rows currently described by s->d_row_index (no-op for Halton).
 static int zerotwo_prepare(SceneImpl* s, long long n_pix, cudaStream_t st) {
-    if (s->dev.sampler_type != B200PT_SAMPLER_ZEROTWO) return B200PT_OK;
+    if (s->dev.sampler_type != B200PT_SAMPLER_ZEROTWO || s->zt_seq) return B200PT_OK;
     const int* sb = s->sample_bounds;
     const int spp = s->spp, dims = s->sampler.dimensions;
     const int n1 = 1 + 2 * s->dev.max_depth, n2 = 2 + 3 * s->dev.max_depth;
@@ -1435,6 +1586,92 @@ static int zerotwo_prepare(SceneImpl* s, long long n_pix, cudaStream_t st) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_zerotwo_tiles");
     return B200PT_OK;
+}
+
+// Per-slot state of the tile-sequential (0,2) mode for `slots` tiles (or list entries) in flight.
+static int ztq_alloc(SceneImpl* s, int slots) {
+    ZtSeq& Z = s->ztq;
+    const int dims = std::max(1, s->sampler.dimensions), spp = s->spp;
+    if (slots > s->ztq_cap) {
+        for (void** p : {(void**)&Z.rng, (void**)&Z.tile, (void**)&Z.cursor, (void**)&Z.samp, (void**)&Z.dst, (void**)&Z.scr1, (void**)&Z.scr2, (void**)&Z.perm1, (void**)&Z.perm2}) {
+            if (*p) cudaFree(*p);
+            *p = nullptr;
+        }
+        s->ztq_cap = 0;
+        B2_CUDA(cudaMalloc(&Z.rng, (size_t)slots * sizeof(DPcg32)));
+        B2_CUDA(cudaMalloc(&Z.tile, (size_t)slots * sizeof(int)));
+        B2_CUDA(cudaMalloc(&Z.cursor, (size_t)slots * sizeof(int)));
+        B2_CUDA(cudaMalloc(&Z.samp, (size_t)slots * sizeof(int)));
+        B2_CUDA(cudaMalloc(&Z.dst, (size_t)slots * sizeof(int)));
+        B2_CUDA(cudaMalloc(&Z.scr1, (size_t)slots * dims * sizeof(uint32_t)));
+        B2_CUDA(cudaMalloc(&Z.scr2, (size_t)slots * dims * 2 * sizeof(uint32_t)));
+        B2_CUDA(cudaMalloc(&Z.perm1, (size_t)slots * dims * spp * sizeof(uint16_t)));
+        B2_CUDA(cudaMalloc(&Z.perm2, (size_t)slots * dims * spp * sizeof(uint16_t)));
+        s->ztq_cap = slots;
+    }
+    const int* sb = s->sample_bounds;
+    Z.dims = s->sampler.dimensions; Z.spp = spp; Z.ntx = (sb[2] - sb[0] + 15) / 16;
+    DZeroTwo& z = s->dev.zt;
+    z.scr1 = Z.scr1; z.perm1 = Z.perm1; z.scr2 = Z.scr2; z.perm2 = Z.perm2;
+    z.n1 = z.n2 = Z.dims; z.spp = spp; z.rng = Z.rng;
+    return B200PT_OK;
+}
+
+// The wave loop of the tile-sequential (0,2) mode: the shard's tile rows are taken in groups whose samples fit the sample
+// store; a group's tiles each carry one path per step, 256 x spp steps (fewer for clipped tiles), then k_film continues
+// the film sums with the group's samples exactly as after a wave of the parallel modes.
+static int render_zt_seq(SceneImpl* s, const std::vector<int>& srows, cudaStream_t st, const std::function<void(long long, long long, int, int)>& film_pass) {
+    const int* sb = s->sample_bounds;
+    const int sw = sb[2] - sb[0], spp = s->spp, ntx = (sw + 15) / 16;
+    struct TRow { int ty; size_t k0, k1; };
+    std::vector<TRow> trows;
+    for (size_t k = 0; k < srows.size();) {
+        const int ty = (srows[k] - sb[1]) / 16;
+        size_t k1 = k;
+        while (k1 < srows.size() && (srows[k1] - sb[1]) / 16 == ty) ++k1;
+        trows.push_back({ty, k, k1});
+        k = k1;
+    }
+    int rc = B200PT_OK;
+    std::vector<int> tiles;
+    for (size_t i = 0; i < trows.size() && !rc;) {
+        size_t j = i;
+        long long ns = 0;
+        int max_h = 0;
+        while (j < trows.size()) {
+            const long long add = (long long)(trows[j].k1 - trows[j].k0) * sw * spp;
+            if (j > i && (ns + add > s->wave_cap || (long long)(j - i + 1) * ntx > s->wave_cap)) break;
+            ns += add;
+            max_h = std::max(max_h, std::min(16, sb[3] - (sb[1] + trows[j].ty * 16)));
+            ++j;
+        }
+        if (ns > s->wave_cap || ntx > s->wave_cap) {
+            b200pt_set_error("render: the memory budget does not hold the samples of one row of 16x16 tiles (02sequence with \"dimensions\" below the path's worst case renders tile-sequentially)");
+            return B200PT_ERR_OOM;
+        }
+        tiles.clear();
+        for (size_t t = i; t < j; ++t)
+            for (int tx = 0; tx < ntx; ++tx) tiles.push_back(trows[t].ty * ntx + tx);
+        const int T = (int)tiles.size();
+        if ((rc = ztq_alloc(s, T))) return rc;
+        B2_CUDA(cudaMemcpyAsync(s->ztq.tile, tiles.data(), (size_t)T * sizeof(int), cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemsetAsync(s->d_sample_L, 0, (size_t)ns * sizeof(float4), st));   // weight 0: pixels outside the integrator's pixel bounds
+        B2_CUDA(cudaMemsetAsync(s->d_sample_pf, 0, (size_t)ns * sizeof(float2), st));
+        B2_CUDA(cudaStreamSynchronize(st));  // `tiles` is reused by the next group
+        const long long first_local = (long long)trows[i].k0 * sw * spp;
+        const long long steps = (long long)std::min(16, sw) * max_h * spp;
+        for (long long step = 0; step < steps && !rc; ++step) {
+            k_zt_seq_next<<<(T + 63) / 64, 64, 0, st>>>(s->dev, s->wave, s->ztq, T, step == 0 ? 1 : 0, s->d_row_index, first_local, s->d_sample_pf);
+            g_launches.fetch_add(1);
+            rc = run_wave(s, T, st);
+            if (rc) break;
+            k_zt_seq_store<<<(T + 255) / 256, 256, 0, st>>>(s->wave, s->ztq.dst, T, s->d_sample_L);
+            g_launches.fetch_add(1);
+        }
+        if (!rc) film_pass(first_local, ns, srows[trows[i].k0], srows[trows[j - 1].k1 - 1]);
+        i = j;
+    }
+    return rc;
 }
 
 // Reads the render's ray totals and error flags back (the one read-back of a render besides the film).
@@ -1512,7 +1749,16 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
     const int reach = (int)std::ceil(F.ry) + 2;  // film rows a sample row can touch, generously
     float4* d_L = s->d_sample_L;
     float2* d_pf = s->d_sample_pf;
-    for (long long first = 0; first < n_samples && !rc; first += s->wave_cap) {
+    if (s->zt_seq) {
+        rc = render_zt_seq(s, srows, st, [&](long long first, long long n, int y_lo, int y_hi) {
+            const int y0 = std::max(f.crop[1], y_lo - reach), y1 = std::min(f.crop[3], y_hi + reach + 1);
+            if (y1 <= y0) return;
+            const long long npix = (long long)cw * (y1 - y0);
+            k_film<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(F, s->d_filter_table, d_L, d_pf, first, (int)n, spp, s->d_row_index, y0, y1, s->d_acc);
+            g_launches.fetch_add(1);
+        });
+    }
+    for (long long first = 0; first < n_samples && !rc && !s->zt_seq; first += s->wave_cap) {
         int n = (int)std::min<long long>(s->wave_cap, n_samples - first);
         k_raygen<<<(n + 255) / 256, 256, 0, st>>>(s->dev, s->wave, first, n, spp, s->d_rows, nullptr, d_pf, nullptr);
         g_launches.fetch_add(1);
@@ -1644,6 +1890,7 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
     int* d_list = nullptr;
     float4 *d_L = nullptr, *d_rays = nullptr;
     const int cap = (int)std::min<int64_t>(s->wave_cap, std::max<int64_t>(n, 1));
+    if (s->zt_seq && (rc = ztq_alloc(s, cap))) return rc;
     B2_CUDA(cudaMalloc(&d_list, (size_t)cap * 3 * sizeof(int)));
     cudaMalloc(&d_L, (size_t)cap * sizeof(float4));
     cudaMalloc(&d_rays, (size_t)cap * 2 * sizeof(float4));
@@ -1651,7 +1898,8 @@ int b200pt_li_batch(b200pt_scene* sc, const int32_t* pixel_sample, int64_t n, fl
     for (int64_t first = 0; first < n && !rc; first += cap) {
         int m = (int)std::min<int64_t>(cap, n - first);
         cudaMemcpy(d_list, pixel_sample + 3 * first, (size_t)m * 3 * sizeof(int), cudaMemcpyHostToDevice);
-        k_raygen<<<(m + 255) / 256, 256>>>(s->dev, s->wave, 0, m, s->spp, nullptr, d_list, nullptr, d_rays);
+        if (s->zt_seq) k_zt_seq_list<<<(m + 63) / 64, 64>>>(s->dev, s->wave, s->ztq, m, d_list, d_rays);
+        else k_raygen<<<(m + 255) / 256, 256>>>(s->dev, s->wave, 0, m, s->spp, nullptr, d_list, nullptr, d_rays);
         g_launches.fetch_add(1);
         rc = s->whitted ? run_wave_whitted(s, m, 0) : run_wave(s, m, 0);
         if (rc) break;

@@ -651,12 +651,17 @@ B2_D float sobol_film_dim(const DSobol& S, unsigned long long index, int dim, in
 // Sobol' (0,2) sequence and shuffles them with the TILE's PCG32 stream (low_discrepency.rs:1676-1763).  A prepass
 // (k_zerotwo_tiles, one thread per 16x16 tile, replaying that stream in pixel order) stores per (pixel, slot) the
 // scramble(s) and the shuffle as a source-index permutation; a sample is then scramble ^ G * gray(perm[s]).
+struct DPcg32;
 struct DZeroTwo {
     const uint32_t* scr1;   // [pixel][n1]
     const uint16_t* perm1;  // [pixel][n1][spp]
     const uint32_t* scr2;   // [pixel][n2][2]
     const uint16_t* perm2;  // [pixel][n2][spp]
     int n1, n2, spp;
+    // Tile-sequential mode ("dimensions" below the path's worst case, e.g. the reference's default 4): `pixel` above is
+    // the path's slot (one path in flight per tile, tables of the tile's current pixel only) and requests past the
+    // n1 / n2 pre-generated slots draw from the tile's PCG32 stream (pixel_sampler.rs:88-110).  Null otherwise.
+    DPcg32* rng;
 };
 __device__ __constant__ uint32_t kCSobol1[32] = {
     0x80000000, 0xc0000000, 0xa0000000, 0xf0000000, 0x88000000, 0xcc000000, 0xaa000000, 0xff000000, 0x80800000, 0xc0c00000, 0xa0a00000,

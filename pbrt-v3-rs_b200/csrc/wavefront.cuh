@@ -106,6 +106,7 @@ B2_D float smp_1d(const DeviceScene& S, unsigned long long key, int& dim) {
     if (S.sampler_type == B200PT_SAMPLER_HALTON) { float v = halton_dim(S.halton, key, dim); dim += 1; return v; }
     if (S.sampler_type == B200PT_SAMPLER_SOBOL) { float v = sobol_sample_f32(S.sobol, key, dim); dim += 1; return v; }  // dimensions >= 2 only (k_raygen draws 0 / 1)
     int d1 = dim & 0xff;
+    if (S.zt.rng && d1 >= S.zt.n1) return u32_to_unit(pcg_next(S.zt.rng[key >> 16]));  // RNG::uniform_float, rng.rs:98-103
     float v = zt_1d(S.zt, (long long)(key >> 16), d1, (int)(key & 0xffff));
     dim += 1;
     return v;
@@ -114,6 +115,12 @@ B2_D P2 smp_2d(const DeviceScene& S, unsigned long long key, int& dim) {
     if (S.sampler_type == B200PT_SAMPLER_HALTON) { P2 v = mk2(halton_dim(S.halton, key, dim), halton_dim(S.halton, key, dim + 1)); dim += 2; return v; }
     if (S.sampler_type == B200PT_SAMPLER_SOBOL) { P2 v = mk2(sobol_sample_f32(S.sobol, key, dim), sobol_sample_f32(S.sobol, key, dim + 1)); dim += 2; return v; }
     int d2 = (dim >> 8) & 0xff;
+    if (S.zt.rng && d2 >= S.zt.n2) {
+        DPcg32& r = S.zt.rng[key >> 16];
+        const float a = u32_to_unit(pcg_next(r));
+        const float b = u32_to_unit(pcg_next(r));
+        return mk2(a, b);
+    }
     P2 v = zt_2d(S.zt, (long long)(key >> 16), d2, (int)(key & 0xffff));
     dim += 0x100;
     return v;

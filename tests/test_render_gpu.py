@@ -124,8 +124,39 @@ def test_unsupported_inputs_fail_loudly(gpu):
     from pbrt_v3_rs_b200 import workloads as wl
     sd = ss.one_material_scene(wl, ss.MATERIALS["matte"], res=8, spp=2)
     sd.sampler["type"] = "02sequence"
+    sd.integrator.update(name="whitted")  # the tree integrators draw a data-dependent number of dimensions: halton / sobol only
     with pytest.raises(gpu.B200PTError):
         gpu.PathIntegrator(sd).preprocess()
+
+
+@pytest.mark.parametrize("name,light,spp,dims,res", [("matte", "all", 4, 4, 40), ("glass", "area", 3, 4, 37), ("plastic", "infinite", 2, 0, 24), ("metal", "point", 4, 7, 33)])
+def test_zerotwo_default_dimensions_tile_sequential(gpu, oracle, name, light, spp, dims, res):
+    """The reference's default "dimensions" = 4 (samplers/src/zero_two_sequence.rs:157): past the pre-generated slots
+    get_1d / get_2d draw from the tile sampler's RNG inside li() (pixel_sampler.rs:88-110), so every tile is one
+    sequential stream.  The tile-sequential mode must reproduce the reference's streams: images, ray counts and
+    per-sample radiance (fresh tile stream per queried sample, the oracle's sampler_at convention) against the oracle,
+    incl. clipped tiles (res not a multiple of 16) and pixel counts rounded up to a power of two."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS[name], light=light, res=res, spp=spp, maxdepth=5, strategy="power")
+    sd.sampler.update(type="02sequence", dimensions=dims)
+    integ = gpu.PathIntegrator(sd)
+    osc = oracle.OracleScene(sd)
+    spp2 = 1 << (spp - 1).bit_length()
+    ps = np.array([(x, y, s) for y in (0, 3, 15, 16, res - 1) for x in (0, 15, 16, 31, res - 1) for s in range(spp2)], dtype=np.int32)
+    li, rays = integ.li(ps)
+    assert rays.tobytes() == osc.camera_rays(ps).tobytes()
+    oli = osc.li(ps)
+    close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
+    assert close.mean() >= 0.97, close.mean()
+    img = integ.render()
+    ref, stats, _ = osc.render()
+    assert ss.rel_rmse(img, ref) <= TOL
+    assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]
+    # a row shard renders whole tiles but keeps only its rows: the two halves sum to the image
+    film_a = integ.render_rows(0, 20)
+    film_b = integ.render_rows(20, res)
+    whole = integ.render_rows(0, res)
+    assert np.array_equal((film_a + film_b).view(np.uint32), whole.view(np.uint32))
 
 
 @pytest.mark.parametrize("name,light,spp", [("matte", "infinite", 8), ("plastic", "all", 4), ("glass", "area", 6)])

@@ -2,6 +2,7 @@
 
   python tools/prof_traversal.py c2        C2: 1 M-triangle mesh (L2-resident), 2^24 closest + 2^24 any-hit rays
   python tools/prof_traversal.py c4        C4-rays: 10 M-triangle mesh (HBM-resident), 2^24 incoherent bounce rays, closest-hit
+  python tools/prof_traversal.py c3        C3 render at 16 spp (the per-material shade kernels: ncu -k regex:k_shade)
   python tools/prof_traversal.py c5        C5: two-level walk (1 000 instances of a 100 K-triangle object), 2^22 primary + bounce rays
 """
 import os
@@ -19,9 +20,9 @@ pkg = ge.load_package()
 pkg.init(0)
 from pbrt_v3_rs_b200 import workloads as wl  # noqa: E402
 
-if which == "c5":
-    # two-level scenes have no stand-alone accelerator handle: drive the kernel through a render of a few rows
-    sd = wl.scene_c5(spp=8)
+if which in ("c5", "c3"):
+    # two-level scenes have no stand-alone accelerator handle: drive the kernel through a render (c3: the shade kernels)
+    sd = wl.scene_c5(spp=8) if which == "c5" else wl.scene_c3(spp=16)
     integ = pkg.PathIntegrator(sd)
     integ.preprocess()
     film = torch.zeros((1080, 1920, 4), dtype=torch.float32, device="cuda")

@@ -475,7 +475,7 @@ B2_D void zt_seq_dead(const Wave& W, int p) {
 }
 // One step of every tile of the group: the next sample of the current pixel, or start_pixel on the next pixel(s).
 __global__ void __launch_bounds__(64) k_zt_seq_next(DeviceScene S, Wave W, ZtSeq Z, int n_slots, int first_step, const int* __restrict__ row_index,
-                                                    long long first_local, float2* __restrict__ p_film_out) {
+                                                    long long first_local, float2* __restrict__ p_film_out, unsigned long long* __restrict__ totals) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_slots) return;
     const int tile = Z.tile[p], tx = tile % Z.ntx, ty = tile / Z.ntx;
@@ -498,7 +498,13 @@ __global__ void __launch_bounds__(64) k_zt_seq_next(DeviceScene S, Wave W, ZtSeq
         }
     }
     Z.rng[p] = rng; Z.cursor[p] = cur; Z.samp[p] = smp;
-    if (cur >= npix) { zt_seq_dead(W, p); Z.dst[p] = -1; return; }
+    if (cur >= npix) {
+        // the tile has no sample left: its slot idles through the wave; take it out of the camera / closest-hit ray totals
+        // the wave bookkeeping adds for every slot (k_wave_end)
+        zt_seq_dead(W, p); Z.dst[p] = -1;
+        atomicAdd(totals, ~0ull); atomicAdd(totals + 1, ~0ull);
+        return;
+    }
     const int px = x0 + cur % w, py = y0 + cur / w;
     P2 pf;
     zt_seq_emit(S, W, p, px, py, smp, true, &pf);
@@ -1661,7 +1667,7 @@ static int render_zt_seq(SceneImpl* s, const std::vector<int>& srows, cudaStream
         const long long first_local = (long long)trows[i].k0 * sw * spp;
         const long long steps = (long long)std::min(16, sw) * max_h * spp;
         for (long long step = 0; step < steps && !rc; ++step) {
-            k_zt_seq_next<<<(T + 63) / 64, 64, 0, st>>>(s->dev, s->wave, s->ztq, T, step == 0 ? 1 : 0, s->d_row_index, first_local, s->d_sample_pf);
+            k_zt_seq_next<<<(T + 63) / 64, 64, 0, st>>>(s->dev, s->wave, s->ztq, T, step == 0 ? 1 : 0, s->d_row_index, first_local, s->d_sample_pf, s->d_totals);
             g_launches.fetch_add(1);
             rc = run_wave(s, T, st);
             if (rc) break;

@@ -584,6 +584,10 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
     }
 }
 
+}  // namespace b2
+#include "instancing_spec3.cuh"
+namespace b2 {
+
 int trace_work_counter(int device, const TraceLaunch* tl, cudaStream_t s, unsigned long long** out);  // traverse_kernels.cu
 
 template <bool ANY>
@@ -605,7 +609,24 @@ static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, 
         static const int closest_blocks = [] { const char* e = std::getenv("B200PT_2L_BLOCKS"); int v = e ? std::atoi(e) : 7; return (v >= 5 && v <= 8) ? v : 7; }();
         const int kb = ANY ? 7 : closest_blocks;
         int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * kb);
-        if (kb == 5) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 5><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        // B200PT_2L_KERNEL: 3 (default) = three-phase kernel (instancing_spec3.cuh), 2 = k_trace_spec2_2l; B200PT_2L_TUNE picks the
+        // phase-switch / refill thresholds of the three-phase kernel (A/B)
+        static const int kernel = [] { const char* e = std::getenv("B200PT_2L_KERNEL"); return e ? std::atoi(e) : 2; }();
+        static const int tune = [] { const char* e = std::getenv("B200PT_2L_TUNE"); return e ? std::atoi(e) : 0; }();
+        if (kernel == 3 && kb == 7) {
+            if (tune == 1) k_trace_spec3_2l<ANY, 16, 12, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+            else if (tune == 2) k_trace_spec3_2l<ANY, 12, 8, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+            else if (tune == 3) k_trace_spec3_2l<ANY, 24, 12, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+            else k_trace_spec3_2l<ANY, 20, ANY ? 16 : 20, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+            g_launches.fetch_add(1);
+            cudaError_t e3 = cudaGetLastError();
+            return e3 == cudaSuccess ? B200PT_OK : cuda_fail(e3, "k_trace_spec3_2l launch");
+        }
+        if (kb == 7 && tune == 1) k_trace_spec2_2l<ANY, 16, 12, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        else if (kb == 7 && tune == 2) k_trace_spec2_2l<ANY, 20, 12, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        else if (kb == 7 && tune == 3) k_trace_spec2_2l<ANY, 24, 16, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        else if (kb == 7 && tune == 4) k_trace_spec2_2l<ANY, 12, 8, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        else if (kb == 5) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 5><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
         else if (kb == 7) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
         else if (kb == 8) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 8><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
         else k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 6><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);

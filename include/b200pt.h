@@ -70,6 +70,7 @@ typedef struct b200pt_bvh_node {
 #define B200PT_PRIM_HAS_UV 16u            /* the primitive's mesh has "uv"/"st": tri_uvs holds its three uvs (triangle.rs:384-394) */
 #define B200PT_PRIM_HAS_NORMALS 32u       /* ... has "N": tri_normals (triangle.rs:631-653) */
 #define B200PT_PRIM_HAS_TANGENTS 64u      /* ... has "S": tri_tangents (triangle.rs:655-670) */
+#define B200PT_PRIM_ALPHA_TEXTURE 128u    /* the mesh's "alpha" or "shadowalpha" is a non-constant float texture: prim_alpha_tex names it (triangle.rs:278-312) */
 
 /* materials/src/{matte,plastic,glass,metal}.rs with constant textures. */
 enum { B200PT_MAT_MATTE = 0, B200PT_MAT_PLASTIC = 1, B200PT_MAT_GLASS = 2, B200PT_MAT_METAL = 3 };
@@ -175,6 +176,28 @@ typedef struct b200pt_instance {
     float world_to_instance[16];
 } b200pt_instance;
 
+/* Float textures a mesh can name as "alpha" / "shadowalpha" (shapes/src/triangle.rs:278-312), evaluated at the hit's
+ * interpolated uv inside Triangle::intersect / intersect_p (triangle.rs:587-607, 840-899) through UVMapping2D
+ * (core/src/texture/mapping/uv_2d.rs: st = (su * u + du, sv * v + dv)).  The interaction the reference builds for that
+ * test has zero differentials, so a checkerboard point-samples (textures/src/checkerboard_2d.rs:62-84) and an image map is
+ * the level-0 bilinear lookup MIPMap::triangle(0, st) for both filters (core/src/mipmap/mod.rs:212-311).  A hit whose
+ * texture evaluates to exactly 0 is rejected.  Constant textures are the B200PT_PRIM_*_ALPHA_ZERO flag bits instead. */
+#define B200PT_TEX_CONSTANT 0
+#define B200PT_TEX_CHECKERBOARD 1 /* 2-D: value = {tex1, tex2} constants (checkerboard_2d.rs) */
+#define B200PT_TEX_DOTS 2         /* value = {outside_dot, inside_dot} as DotsTexture STORES them: its from-params hands
+                                   * ("inside", "outside") to new(outside_dot, inside_dot) (textures/src/dots.rs:31,86), so
+                                   * the scene-file parameter "inside" is value[0] and colours the outside of the dots */
+#define B200PT_TEX_IMAGEMAP 3     /* texels = pyramid level 0 of the MIPMap<Float> (after convert_in's scale / gamma / y(),
+                                   * the vertical flip and the power-of-two resampling of MIPMap::new), row t, column s */
+typedef struct b200pt_float_texture {
+    int32_t type;
+    float su, sv, du, dv; /* "uscale" "vscale" "udelta" "vdelta" (textures/src/lib.rs:47-52) */
+    float value[2];
+    int32_t wrap;         /* imagemap: 0 repeat, 1 black, 2 clamp (core/src/mipmap/mod.rs:580-608) */
+    int32_t width, height;
+    const float* texels;
+} b200pt_float_texture;
+
 typedef struct b200pt_scene_desc {
     const b200pt_bvh_node* nodes;
     int64_t n_nodes;
@@ -211,6 +234,15 @@ typedef struct b200pt_scene_desc {
      * the constant's address; the Python mirror and the scene-file loader read pbrt-v3-rs_b200/data/sobol_matrices_32.bin).
      * NULL otherwise. */
     const uint32_t* sobol_matrices_32;
+    /* Alpha masks (optional): prim_alpha_tex = 2 ints per ORIGINAL primitive, the index into float_textures of its mesh's
+     * "alpha" and "shadowalpha" texture or -1 (none / constant, see the flag bits); read for primitives whose flags carry
+     * B200PT_PRIM_ALPHA_TEXTURE.  noise_perm = NOISE_PERM[0..256) of core/src/texture/common.rs (Perlin's permutation;
+     * needed by "dots" textures only: the Rust side passes the constant, the mirror and the loader read
+     * pbrt-v3-rs_b200/data/noise_perm.bin). */
+    const b200pt_float_texture* float_textures;
+    int32_t n_float_textures;
+    const int32_t* prim_alpha_tex;
+    const uint8_t* noise_perm;
 } b200pt_scene_desc;
 
 typedef struct b200pt_accel b200pt_accel; /* opaque: device-resident BVHAccel */
@@ -318,6 +350,10 @@ int b200pt_accel_create_uv(const b200pt_bvh_node* nodes, int64_t n_nodes, const 
  * LinearBVHNode array / ordered_prims as b200pt_bvh_build_sah.  Rebuilding a 1 M-triangle accelerator takes a few ms. */
 int b200pt_accel_create_device(const float* d_tri_verts, int64_t n_prims, const uint32_t* d_prim_flags, int max_prims_in_node, void* stream,
                                b200pt_accel** out);
+/* Alpha masks for a stand-alone accelerator (same arrays as in b200pt_scene_desc; tri_uvs may be NULL when no mesh has
+ * uvs: Triangle::get_uvs then supplies (0,0) (1,0) (1,1), triangle.rs:384-394).  Call before tracing. */
+int b200pt_accel_set_alpha_textures(b200pt_accel* a, const b200pt_float_texture* float_textures, int32_t n_float_textures,
+                                    const int32_t* prim_alpha_tex, const float* tri_uvs, const uint32_t* prim_flags, const uint8_t* noise_perm);
 int b200pt_accel_download(const b200pt_accel* a, b200pt_bvh_node* nodes_out, int64_t* n_nodes_out, uint32_t* ordered_out);
 void b200pt_accel_destroy(b200pt_accel* a);
 /* Primitive::world_bound (mod.rs:159-165): 6 floats. */

@@ -6,6 +6,7 @@
 #pragma once
 #include <vector>
 #include "oracle_math.h"
+#include "oracle_texture.h"
 
 namespace orc {
 
@@ -371,6 +372,7 @@ enum : uint32_t {
     PRIM_HAS_UV = 16u,            // the primitive's mesh has "uv"/"st" (tri_uvs holds its three uvs)
     PRIM_HAS_NORMALS = 32u,       // ... has "N" (tri_normals)
     PRIM_HAS_TANGENTS = 64u,      // ... has "S" (tri_tangents)
+    PRIM_ALPHA_TEXTURE = 128u,    // the mesh's alpha / shadowalpha is a non-constant texture (Accel::alpha_tex)
 };
 
 // Flattened accelerator: nodes + triangles in ordered_prims order.
@@ -380,6 +382,18 @@ struct Accel {
     std::vector<Float> verts;          // 9 floats per ORIGINAL primitive
     std::vector<uint32_t> flags;       // per ORIGINAL primitive
     std::vector<Float> uvs, normals, tangents;  // optional: 6 / 9 / 9 floats per ORIGINAL primitive (empty = the mesh has none)
+    // alpha masks (triangle.rs:278-312): per ORIGINAL primitive the index of its mesh's alpha / shadowalpha texture or -1
+    std::vector<int32_t> alpha_tex;
+    std::vector<FloatTexture> textures;
+    std::vector<uint8_t> noise_perm;
+    // mask.evaluate(..) == 0.0 -> the hit is rejected (triangle.rs:601-603, 886-899)
+    bool alpha_rejects(size_t prim, P2 uv, bool shadow) const {
+        if (!(flag(prim) & PRIM_ALPHA_TEXTURE) || alpha_tex.empty()) return false;
+        int ta = alpha_tex[2 * prim], ts = alpha_tex[2 * prim + 1];
+        if (ta >= 0 && float_texture_evaluate(textures[(size_t)ta], noise_perm.data(), uv.x, uv.y) == 0.0f) return true;
+        if (shadow && ts >= 0 && float_texture_evaluate(textures[(size_t)ts], noise_perm.data(), uv.x, uv.y) == 0.0f) return true;
+        return false;
+    }
     V3 vert(size_t prim, int k) const { const Float* v = &verts[9 * prim + 3 * k]; return V3(v[0], v[1], v[2]); }
     uint32_t flag(size_t prim) const { return flags.empty() ? 0u : flags[prim]; }
     TriAttr attr(size_t prim) const {
@@ -416,6 +430,7 @@ inline bool prim_intersect(const Accel& a, uint32_t prim, const Ray& r, TriHit* 
     uint32_t fl = a.flag(prim);
     if (!triangle_geometry(p0, p1, p2, th->b0, th->b1, th->b2, a.attr(prim), &g)) return false;
     if (fl & PRIM_ALPHA_ZERO) return false;  // triangle.rs:587-607
+    if (a.alpha_rejects(prim, g.uv, false)) return false;
     return true;
 }
 // Triangle::intersect_p (triangle.rs:731-903).
@@ -427,6 +442,7 @@ inline bool prim_intersect_p(const Accel& a, uint32_t prim, const Ray& r) {
     uint32_t fl = a.flag(prim);
     if (!triangle_geometry(p0, p1, p2, th.b0, th.b1, th.b2, a.attr(prim), &g)) return false;
     if (fl & (PRIM_ALPHA_ZERO | PRIM_SHADOW_ALPHA_ZERO)) return false;
+    if (a.alpha_rejects(prim, g.uv, true)) return false;  // triangle.rs:886-899
     return true;
 }
 

@@ -192,6 +192,19 @@ void orc_accel_set_uvs(void* accel, const float* uvs, int64_t n_prims) {
     Accel* a = (Accel*)accel;
     a->uvs.assign(uvs, uvs + 6 * n_prims);
 }
+// Alpha-mask textures of a stand-alone accelerator (same arrays as b200pt_accel_set_alpha_textures).
+void orc_accel_set_alpha(void* accel, const b200pt_float_texture* tex, int n_tex, const int32_t* prim_alpha_tex, const uint8_t* noise_perm, int64_t n_prims) {
+    Accel* a = (Accel*)accel;
+    a->alpha_tex.assign(prim_alpha_tex, prim_alpha_tex + 2 * n_prims);
+    a->textures.clear();
+    for (int k = 0; k < n_tex; ++k) a->textures.push_back(float_texture_from(tex[k]));
+    a->noise_perm.clear();
+    if (noise_perm) a->noise_perm.assign(noise_perm, noise_perm + 256);
+}
+float orc_float_texture_evaluate(const b200pt_float_texture* tex, const uint8_t* noise_perm, float u, float v) {
+    return float_texture_evaluate(float_texture_from(*tex), noise_perm, u, v);
+}
+float orc_noise_3d(const uint8_t* noise_perm, float x, float y, float z) { return noise_3d(noise_perm, x, y, z); }
 void orc_accel_destroy(void* a) { delete (Accel*)a; }
 // Hit geometry of a triangle at barycentrics b (triangle.rs:547-725).  attrs: uv6 / n9 / s9 may be null.
 // out: p(3) p_error(3) n(3) dpdu(3) dpdv(3) shading_n(3) shading_dpdu(3) = 21 floats.  Returns 0 for a degenerate hit.

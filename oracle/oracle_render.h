@@ -572,6 +572,14 @@ inline RGB light_power(const RenderScene& sc, int li) {
     return kPi * sc.world_radius * sc.world_radius * spec;
 }
 
+inline FloatTexture float_texture_from(const b200pt_float_texture& t) {
+    FloatTexture f;
+    f.type = t.type; f.su = t.su; f.sv = t.sv; f.du = t.du; f.dv = t.dv; f.a = t.value[0]; f.b = t.value[1];
+    f.wrap = t.wrap; f.width = t.width; f.height = t.height;
+    if (t.type == B200PT_TEX_IMAGEMAP && t.texels) f.texels.assign(t.texels, t.texels + (size_t)t.width * t.height);
+    return f;
+}
+
 inline RenderScene* scene_create(const b200pt_scene_desc* d) {
     RenderScene* s = new RenderScene();
     s->accel.nodes.resize((size_t)d->n_nodes);
@@ -583,6 +591,11 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
     if (d->tri_uvs) s->accel.uvs.assign(d->tri_uvs, d->tri_uvs + 6 * d->n_prims);
     if (d->tri_normals) s->accel.normals.assign(d->tri_normals, d->tri_normals + 9 * d->n_prims);
     if (d->tri_tangents) s->accel.tangents.assign(d->tri_tangents, d->tri_tangents + 9 * d->n_prims);
+    if (d->float_textures && d->n_float_textures > 0 && d->prim_alpha_tex) {  // alpha masks
+        s->accel.alpha_tex.assign(d->prim_alpha_tex, d->prim_alpha_tex + 2 * d->n_prims);
+        for (int k = 0; k < d->n_float_textures; ++k) s->accel.textures.push_back(float_texture_from(d->float_textures[k]));
+        if (d->noise_perm) s->accel.noise_perm.assign(d->noise_perm, d->noise_perm + 256);
+    }
     if (d->prim_material) s->prim_material.assign(d->prim_material, d->prim_material + d->n_prims);
     if (d->prim_light) s->prim_light.assign(d->prim_light, d->prim_light + d->n_prims);
     if (d->n_objects > 0) {
@@ -598,6 +611,11 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
             a.verts.assign(d->tri_verts + 9 * ob.first_prim, d->tri_verts + 9 * (ob.first_prim + ob.n_prims));
             if (d->prim_flags) a.flags.assign(d->prim_flags + ob.first_prim, d->prim_flags + ob.first_prim + ob.n_prims);
             if (d->tri_uvs) a.uvs.assign(d->tri_uvs + 6 * ob.first_prim, d->tri_uvs + 6 * (ob.first_prim + ob.n_prims));
+            if (!s->accel.alpha_tex.empty()) {
+                a.alpha_tex.assign(d->prim_alpha_tex + 2 * ob.first_prim, d->prim_alpha_tex + 2 * (ob.first_prim + ob.n_prims));
+                a.textures = s->accel.textures;
+                a.noise_perm = s->accel.noise_perm;
+            }
             s->top.objects.push_back(a);
             s->top.object_first_prim.push_back(ob.first_prim);
         }

@@ -95,13 +95,52 @@ class Instance(C.Structure):
     _fields_ = [("object", C.c_int32), ("instance_to_world", C.c_float * 16), ("world_to_instance", C.c_float * 16)]
 
 
+class FloatTexture(C.Structure):
+    _fields_ = [("type", C.c_int32), ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float), ("value", C.c_float * 2),
+                ("wrap", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("texels", C.c_void_p)]
+
+
+TEX_CONSTANT, TEX_CHECKERBOARD, TEX_DOTS, TEX_IMAGEMAP = 0, 1, 2, 3
+PRIM_ALPHA_TEXTURE = 128
+
+
+def noise_perm():
+    """NOISE_PERM[0..256) (tools/extract_noise_perm.py)."""
+    return np.fromfile(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "noise_perm.bin"), dtype=np.uint8)
+
+
+def float_texture_array(textures, keep):
+    """ctypes array of b200pt_float_texture from the mirror's texture dicts (scene.SceneDescription.add_float_texture)."""
+    arr = (FloatTexture * max(1, len(textures)))()
+    for k, t in enumerate(textures):
+        T = arr[k]
+        T.type = {"constant": TEX_CONSTANT, "checkerboard": TEX_CHECKERBOARD, "dots": TEX_DOTS, "imagemap": TEX_IMAGEMAP}[t["type"]]
+        T.su, T.sv, T.du, T.dv = t.get("uscale", 1.0), t.get("vscale", 1.0), t.get("udelta", 0.0), t.get("vdelta", 0.0)
+        if t["type"] == "constant":
+            T.value[:] = (t.get("value", 1.0), 0.0)
+        elif t["type"] == "checkerboard":  # checkerboard_2d.rs:127-128 defaults
+            T.value[:] = (t.get("tex1", 1.0), t.get("tex2", 0.0))
+        elif t["type"] == "dots":
+            # dots.rs:82-86: Self::new(inside, outside, map) feeds new(outside_dot, inside_dot, mapping)
+            T.value[:] = (t.get("inside", 1.0), t.get("outside", 0.0))
+        else:
+            tex = np.ascontiguousarray(t["texels"], dtype=np.float32)
+            keep.append(tex)
+            T.height, T.width = tex.shape
+            T.texels = tex.ctypes.data_as(C.c_void_p)
+            T.wrap = {"repeat": 0, "black": 1, "clamp": 2}[t.get("wrap", "repeat")]
+    keep.append(arr)
+    return arr
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("nodes", C.c_void_p), ("n_nodes", C.c_int64), ("ordered_prims", C.c_void_p), ("tri_verts", C.c_void_p),
                 ("prim_flags", C.c_void_p), ("prim_material", C.c_void_p), ("prim_light", C.c_void_p), ("n_prims", C.c_int64),
                 ("materials", C.c_void_p), ("n_materials", C.c_int32), ("lights", C.c_void_p), ("n_lights", C.c_int32),
                 ("camera", Camera), ("film", Film), ("sampler", Sampler), ("integrator", Integrator),
                 ("n_top_tris", C.c_int64), ("objects", C.c_void_p), ("n_objects", C.c_int32), ("instances", C.c_void_p), ("n_instances", C.c_int32),
-                ("tri_uvs", C.c_void_p), ("tri_normals", C.c_void_p), ("tri_tangents", C.c_void_p), ("sobol_matrices_32", C.c_void_p)]
+                ("tri_uvs", C.c_void_p), ("tri_normals", C.c_void_p), ("tri_tangents", C.c_void_p), ("sobol_matrices_32", C.c_void_p),
+                ("float_textures", C.c_void_p), ("n_float_textures", C.c_int32), ("prim_alpha_tex", C.c_void_p), ("noise_perm", C.c_void_p)]
 
 
 _lib = None
@@ -142,6 +181,7 @@ def lib():
     L.b200pt_accel_create.argtypes = [vp, i64, vp, vp, vp, i64, C.POINTER(vp)]
     L.b200pt_accel_create_uv.argtypes = [vp, i64, vp, vp, vp, vp, i64, C.POINTER(vp)]
     L.b200pt_accel_create_device.argtypes = [vp, i64, vp, C.c_int, vp, C.POINTER(vp)]
+    L.b200pt_accel_set_alpha_textures.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.b200pt_accel_download.argtypes = [vp, vp, C.POINTER(i64), vp]
     L.b200pt_accel_destroy.argtypes = [vp]
     L.b200pt_accel_destroy.restype = None
@@ -373,6 +413,26 @@ class BVHAccel:
             self.ordered_prims = np.zeros(int(n_prims), dtype=np.uint32)
             _check(lib().b200pt_accel_download(h, _ptr(self.nodes), C.byref(nn), _ptr(self.ordered_prims)), "b200pt_accel_download")
         return self
+
+    def set_alpha_textures(self, textures, prim_alpha_tex):
+        """Alpha masks of the meshes (shapes/src/triangle.rs:278-312): ``textures`` = texture dicts as taken by
+        scene.SceneDescription.add_float_texture, ``prim_alpha_tex`` = (n, 2) indices (alpha, shadowalpha) or -1 per primitive.
+        Primitives with an index >= 0 get B200PT_PRIM_ALPHA_TEXTURE."""
+        pat = np.ascontiguousarray(prim_alpha_tex, dtype=np.int32).reshape(-1, 2)
+        fl = np.zeros(self.tri_verts.shape[0], dtype=np.uint32) if self.prim_flags is None else self.prim_flags.copy()
+        fl[(pat >= 0).any(1)] |= np.uint32(PRIM_ALPHA_TEXTURE)
+        self.prim_flags, self.prim_alpha_tex, self.float_textures = fl, pat, list(textures)
+        # the triangle records carry the flags: rebuild the accelerator with them, then attach the textures
+        lib().b200pt_accel_destroy(self._h)
+        h = C.c_void_p()
+        _check(lib().b200pt_accel_create_uv(_ptr(self.nodes), len(self.nodes), _ptr(self.ordered_prims), _ptr(self.tri_verts), _ptr(self.tri_uvs),
+                                            _ptr(self.prim_flags), self.tri_verts.shape[0], C.byref(h)), "b200pt_accel_create_uv")
+        self._h = h
+        keep = []
+        arr = float_texture_array(self.float_textures, keep)
+        perm = noise_perm()
+        _check(lib().b200pt_accel_set_alpha_textures(self._h, C.cast(arr, C.c_void_p), len(self.float_textures), _ptr(pat), _ptr(self.tri_uvs), _ptr(self.prim_flags),
+                                                     _ptr(perm)), "b200pt_accel_set_alpha_textures")
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:

@@ -129,7 +129,8 @@ B2_D float float_tex_eval(const DeviceAlpha& D, const DFloatTex& T, float u, flo
 }
 
 // true = the hit survives its mesh's alpha (closest hit) / alpha and shadowalpha (any hit) textures
-__device__ __noinline__ bool alpha_tex_accepts(const DeviceAlpha D, uint32_t prim, float b0, float b1, float b2, bool shadow) {
+static __device__ __noinline__ bool alpha_tex_accepts(const DeviceAlpha* __restrict__ Dp, uint32_t prim, float b0, float b1, float b2, bool shadow) {
+    const DeviceAlpha D = *Dp;
     const float* uv = D.uv + 6ll * prim;
     const float u = b0 * uv[0] + b1 * uv[2] + b2 * uv[4];  // uv_hit = b0 * uv[0] + b1 * uv[1] + b2 * uv[2] (triangle.rs:585)
     const float v = b0 * uv[1] + b1 * uv[3] + b2 * uv[5];

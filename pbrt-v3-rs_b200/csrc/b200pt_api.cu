@@ -159,6 +159,74 @@ void accel_free_device(AccelImpl* a) {
     a->d_wide = a->d_tris = a->d_ref = nullptr;
 }
 
+void alpha_free_device(AlphaImpl* a) {
+    for (void* p : a->allocs) cudaFree(p);
+    a->allocs.clear();
+    a->dev = nullptr;
+}
+
+int alpha_build_device(const b200pt_float_texture* tex, int32_t n_tex, const int32_t* prim_alpha_tex, const float* tri_uvs, const uint32_t* prim_flags,
+                       int64_t n_prims, const uint8_t* noise_perm, AlphaImpl* out) {
+    alpha_free_device(out);
+    bool any = false;
+    if (prim_flags)
+        for (int64_t i = 0; i < n_prims && !any; ++i) any = (prim_flags[i] & B200PT_PRIM_ALPHA_TEXTURE) != 0;
+    if (!any) return B200PT_OK;
+    if (!tex || n_tex <= 0 || !prim_alpha_tex) {
+        b200pt_set_error("alpha textures: a primitive carries B200PT_PRIM_ALPHA_TEXTURE but float_textures / prim_alpha_tex are missing");
+        return B200PT_ERR_INVALID;
+    }
+    bool dots = false;
+    std::vector<DFloatTex> dt((size_t)n_tex);
+    auto upload = [&](const void* src, size_t bytes, void** dst) -> int {
+        B2_CUDA(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+        out->allocs.push_back(*dst);
+        B2_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+        return B200PT_OK;
+    };
+    int rc;
+    for (int32_t k = 0; k < n_tex; ++k) {
+        const b200pt_float_texture& t = tex[k];
+        DFloatTex& d = dt[(size_t)k];
+        if (t.type < B200PT_TEX_CONSTANT || t.type > B200PT_TEX_IMAGEMAP) { b200pt_set_error("alpha textures: unknown float texture type (constant, checkerboard, dots, imagemap are on this path)"); return B200PT_ERR_UNSUPPORTED; }
+        d.type = t.type; d.su = t.su; d.sv = t.sv; d.du = t.du; d.dv = t.dv; d.v0 = t.value[0]; d.v1 = t.value[1];
+        d.wrap = t.wrap; d.width = t.width; d.height = t.height; d.texels = nullptr;
+        if (t.type == B200PT_TEX_DOTS) dots = true;
+        if (t.type == B200PT_TEX_IMAGEMAP) {
+            if (!t.texels || t.width <= 0 || t.height <= 0 || t.wrap < 0 || t.wrap > 2) { b200pt_set_error("alpha textures: imagemap without texels / with an unknown wrap mode"); return B200PT_ERR_INVALID; }
+            void* p = nullptr;
+            if ((rc = upload(t.texels, (size_t)t.width * t.height * sizeof(float), &p))) return rc;
+            d.texels = (const float*)p;
+        }
+    }
+    if (dots && !noise_perm) { b200pt_set_error("alpha textures: \"dots\" needs noise_perm (NOISE_PERM[0..256) of core/src/texture/common.rs)"); return B200PT_ERR_INVALID; }
+    std::vector<float> uv((size_t)n_prims * 6);
+    std::vector<int32_t> pt((size_t)n_prims * 2, -1);
+    for (int64_t i = 0; i < n_prims; ++i) {
+        const uint32_t fl = prim_flags[i];
+        float* o = &uv[(size_t)i * 6];
+        if (tri_uvs && (fl & B200PT_PRIM_HAS_UV)) std::memcpy(o, tri_uvs + 6 * (size_t)i, 6 * sizeof(float));
+        else { o[0] = 0.0f; o[1] = 0.0f; o[2] = 1.0f; o[3] = 0.0f; o[4] = 1.0f; o[5] = 1.0f; }  // Triangle::get_uvs, triangle.rs:384-394
+        if (!(fl & B200PT_PRIM_ALPHA_TEXTURE)) continue;
+        for (int c = 0; c < 2; ++c) {
+            const int32_t v = prim_alpha_tex[2 * i + c];
+            if (v < -1 || v >= n_tex) { b200pt_set_error("alpha textures: prim_alpha_tex index out of range"); return B200PT_ERR_INVALID; }
+            pt[(size_t)i * 2 + c] = v;
+        }
+    }
+    void *d_tex = nullptr, *d_uv = nullptr, *d_pt = nullptr, *d_perm = nullptr;
+    if ((rc = upload(dt.data(), dt.size() * sizeof(DFloatTex), &d_tex))) return rc;
+    if ((rc = upload(uv.data(), uv.size() * sizeof(float), &d_uv))) return rc;
+    if ((rc = upload(pt.data(), pt.size() * sizeof(int32_t), &d_pt))) return rc;
+    if (noise_perm && (rc = upload(noise_perm, 256, &d_perm))) return rc;
+    DeviceAlpha h;
+    h.tex = (const DFloatTex*)d_tex; h.uv = (const float*)d_uv; h.prim_tex = (const int*)d_pt; h.perm = (const unsigned char*)d_perm;
+    void* d_h = nullptr;
+    if ((rc = upload(&h, sizeof(h), &d_h))) return rc;
+    out->dev = (const DeviceAlpha*)d_h;
+    return B200PT_OK;
+}
+
 // Pipelined host-buffer batch (the e2e path): chunk i uses slot i % 3.
 template <class LaunchFn>
 static int run_host_batch(int device, const void* rays, int64_t n, void* out, size_t out_elem, LaunchFn launch) {
@@ -274,8 +342,19 @@ int b200pt_accel_create_uv(const b200pt_bvh_node* nodes, int64_t n_nodes, const 
     return B200PT_OK;
 }
 
+int b200pt_accel_set_alpha_textures(b200pt_accel* a, const b200pt_float_texture* float_textures, int32_t n_float_textures,
+                                    const int32_t* prim_alpha_tex, const float* tri_uvs, const uint32_t* prim_flags, const uint8_t* noise_perm) {
+    if (!a) { b200pt_set_error("b200pt_accel_set_alpha_textures: null accelerator"); return B200PT_ERR_INVALID; }
+    int rc = use_device(a->impl.device);
+    if (rc) return rc;
+    rc = alpha_build_device(float_textures, n_float_textures, prim_alpha_tex, tri_uvs, prim_flags, a->impl.n_prims, noise_perm, &a->alpha);
+    a->impl.dev.alpha = a->alpha.dev;
+    return rc;
+}
+
 void b200pt_accel_destroy(b200pt_accel* a) {
     if (!a) return;
+    alpha_free_device(&a->alpha);
     accel_free_device(&a->impl);
     delete a;
 }

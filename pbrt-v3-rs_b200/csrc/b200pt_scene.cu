@@ -697,6 +697,7 @@ struct SceneImpl {
     int device = -1;          // CUDA device the scene lives on; every entry point switches to it
     AccelImpl accel;
     Accel2Impl accel2;        // two-level scenes (instancing)
+    AlphaImpl alpha;          // alpha-mask textures
     bool instanced = false;
     bool whitted = false;     // a recursive SamplerIntegrator (Whitted / DirectLighting) instead of PathIntegrator
     int tree_mode = 0;        // kTreeWhitted / kTreeDirectAll / kTreeDirectOne
@@ -1322,6 +1323,11 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         if (rc) return fail(rc);
         D.accel = s->accel.dev;
     }
+    // alpha-mask textures (triangle.rs:587-607, 840-899): evaluated inside the traversal kernels' accept path
+    rc = alpha_build_device(d->float_textures, d->n_float_textures, d->prim_alpha_tex, d->tri_uvs, d->prim_flags, d->n_prims, d->noise_perm, &s->alpha);
+    if (rc) return fail(rc);
+    D.accel.alpha = s->alpha.dev;
+    if (s->instanced) s->accel2.dev.top.alpha = s->alpha.dev; else s->accel.dev.alpha = s->alpha.dev;
     s->film = d->film;
     s->sampler = d->sampler;
     s->spp = d->sampler.spp;
@@ -1556,6 +1562,7 @@ void b200pt_scene_destroy(b200pt_scene* sc) {
         if (p) cudaFree(p);
     if (sc->impl.d_rows) cudaFree(sc->impl.d_rows);
     if (sc->impl.d_row_index) cudaFree(sc->impl.d_row_index);
+    alpha_free_device(&sc->impl.alpha);
     accel_free_device(&sc->impl.accel);
     accel2_free_device(&sc->impl.accel2);
     delete sc;

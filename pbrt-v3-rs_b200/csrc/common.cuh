@@ -85,6 +85,15 @@ struct AccelImpl {
 
 int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered, const float* tri_verts,
                        const uint32_t* flags, int64_t n_prims, AccelImpl* out, const float* tri_uvs = nullptr);
+// Alpha-mask textures on the device (alpha_tex.cuh): uploads the texture table, the per-primitive texture indices and
+// the absolute uvs the evaluation needs; the caller stores out->dev into DeviceAccel::alpha.
+struct AlphaImpl {
+    const DeviceAlpha* dev = nullptr;  // device copy of the table
+    std::vector<void*> allocs;
+};
+int alpha_build_device(const b200pt_float_texture* tex, int32_t n_tex, const int32_t* prim_alpha_tex, const float* tri_uvs, const uint32_t* prim_flags,
+                       int64_t n_prims, const uint8_t* noise_perm, AlphaImpl* out);
+void alpha_free_device(AlphaImpl* a);
 float4 record_duv(const float* uv6);  // uv0 - uv2, uv1 - uv2; uv6 == nullptr: the default uvs
 void accel_free_device(AccelImpl* a);
 
@@ -104,4 +113,5 @@ int launch_count_work(const DeviceAccel& A, const void* d_rays, int64_t n, int a
 
 struct b200pt_accel {
     b2::AccelImpl impl;
+    b2::AlphaImpl alpha;
 };

@@ -242,6 +242,7 @@ struct ParamSet {
     bool one_bool(const std::string& n, bool d) const { const Param* p = find(n, "bool"); return p && !p->strs.empty() ? p->strs[0] == "true" : d; }
     std::string one_string(const std::string& n, const std::string& d) const { const Param* p = find(n, "string"); return p && !p->strs.empty() ? p->strs[0] : d; }
     std::vector<float> floats(const std::string& n) const { const Param* p = find(n, "float"); return p ? p->nums : std::vector<float>(); }
+    std::string one_texture(const std::string& n) const { const Param* p = find(n, "texture"); return p && !p->strs.empty() ? p->strs[0] : std::string(); }
     bool has_texture(const std::string& n) const { for (const Param& p : ps) if (p.name == n && p.type == "texture") return true; return false; }
     // find_one_spectrum with RGB values ("rgb" / "color"); "spectrum" files and "blackbody" are outside this path
     void one_rgb(const std::string& n, const float d[3], float out[3]) const {
@@ -259,6 +260,7 @@ struct ObjectDef {
     std::vector<float> verts, uvs, normals, tangents;
     std::vector<uint32_t> flags;
     std::vector<int32_t> material;
+    std::vector<int32_t> alpha_tex;     // 2 per triangle: alpha / shadowalpha float-texture index or -1
     std::vector<b200pt_bvh_node> nodes;
     std::vector<uint32_t> ordered;
     bool any_uv = false, any_n = false, any_s = false;
@@ -275,6 +277,9 @@ struct Loaded {
     std::vector<b200pt_bvh_node> nodes;
     std::vector<uint32_t> ordered;
     std::vector<uint32_t> sobol;        // SOBOL_MATRICES_32 when the scene asks for the sobol sampler
+    std::vector<b200pt_float_texture> float_textures;  // Texture "name" "float" ... used as alpha masks
+    std::vector<int32_t> alpha_tex;     // 2 per triangle (top-level triangles first, then the objects')
+    std::vector<uint8_t> noise_perm;    // NOISE_PERM[0..256) when a "dots" texture is used
     std::vector<ObjectDef> objects;
     std::vector<b200pt_object> object_descs;
     std::vector<b200pt_instance> instances;
@@ -418,6 +423,7 @@ struct GState {
     bool has_area = false;
     float area_L[3] = {1, 1, 1};
     bool area_two_sided = false;
+    std::map<std::string, int> float_textures;  // GraphicsState::float_textures: name -> index into Loaded::float_textures (scoped by Attribute blocks)
 };
 
 struct Builder {
@@ -489,17 +495,109 @@ struct Builder {
         return default_matte;
     }
 
+    std::string data_dir() const {  // <dir of libb200pt.so>/data or $B200PT_DATA_DIR
+        if (const char* e = std::getenv("B200PT_DATA_DIR")) return e;
+        Dl_info info;
+        if (dladdr((void*)&b200pt_load_pbrt, &info) && info.dli_fname) {
+            std::string lib(info.dli_fname);
+            size_t sl = lib.find_last_of('/');
+            return (sl == std::string::npos ? std::string(".") : lib.substr(0, sl)) + "/data";
+        }
+        return "data";
+    }
+    // Texture "name" "float" "class": the float textures a mesh can use as alpha / shadowalpha (api/src/lib.rs pbrt_texture ->
+    // make_float_texture; textures/src/{constant,checkerboard_2d,dots,imagemap}.rs from-params).  Spectrum textures feed
+    // materials, which take constants only on this path.
+    void texture(const std::string& name, const std::string& type, const std::string& cls, const ParamSet& p) {
+        if (type != "float") throw Unsupported("Texture \"" + name + "\" \"" + type + "\": only float textures (alpha masks) are on this path");
+        b200pt_float_texture t;
+        std::memset(&t, 0, sizeof(t));
+        if (cls != "constant") {
+            const std::string mapping = p.one_string("mapping", "uv");
+            if (mapping != "uv") throw Unsupported("Texture \"" + name + "\": mapping \"" + mapping + "\" is outside this path (uv)");
+        }
+        t.su = p.one_float("uscale", 1.0f); t.sv = p.one_float("vscale", 1.0f); t.du = p.one_float("udelta", 0.0f); t.dv = p.one_float("vdelta", 0.0f);
+        auto const_or_named = [&](const char* pn, float dflt) {  // get_float_texture_or_else with constant sub-textures
+            const std::string tn = p.one_texture(pn);
+            if (!tn.empty()) {
+                auto it = gs.float_textures.find(tn);
+                if (it != gs.float_textures.end()) {
+                    const b200pt_float_texture& s = L->float_textures[(size_t)it->second];
+                    if (s.type != B200PT_TEX_CONSTANT) throw Unsupported("Texture \"" + name + "\": nested non-constant textures are outside this path");
+                    return s.value[0];
+                }
+            }
+            return p.one_float(pn, dflt);
+        };
+        if (cls == "constant") { t.type = B200PT_TEX_CONSTANT; t.value[0] = const_or_named("value", 1.0f); }
+        else if (cls == "checkerboard") {
+            if (p.one_int("dimension", 2) != 2) throw Unsupported("Texture \"" + name + "\": 3-D checkerboards are outside this path");
+            t.type = B200PT_TEX_CHECKERBOARD;
+            t.value[0] = const_or_named("tex1", 1.0f); t.value[1] = const_or_named("tex2", 0.0f);
+        } else if (cls == "dots") {
+            // dots.rs:82-86 hands (inside, outside) to new(outside_dot, inside_dot): value[0] is what the texture returns OUTSIDE the dots
+            t.type = B200PT_TEX_DOTS;
+            t.value[0] = const_or_named("inside", 1.0f); t.value[1] = const_or_named("outside", 0.0f);
+            if (L->noise_perm.empty()) {
+                std::ifstream f(data_dir() + "/noise_perm.bin", std::ios::binary);
+                L->noise_perm.resize(256);
+                if (!f || !f.read((char*)L->noise_perm.data(), 256)) throw Invalid("Texture \"dots\": cannot read " + data_dir() + "/noise_perm.bin (set B200PT_DATA_DIR)");
+            }
+        } else if (cls == "imagemap") {
+            // imagemap.rs:104-141; images: PFM only on this path, power-of-two sides (MIPMap::new would resample others)
+            std::string fn = p.one_string("filename", "");
+            if (fn.empty()) throw Invalid("Texture \"" + name + "\": imagemap without \"filename\"");
+            const std::string path = resolve(fn);
+            if (path.size() < 4 || path.substr(path.size() - 4) != ".pfm") throw Unsupported("Texture \"" + name + "\": only .pfm image maps are on this path");
+            std::vector<float> rgb;
+            int w = 0, h = 0;
+            read_pfm(path, &rgb, &w, &h);
+            if ((w & (w - 1)) || (h & (h - 1))) throw Unsupported("Texture \"" + name + "\": image sides must be powers of two on this path (no resampling)");
+            const float scale = p.one_float("scale", 1.0f);
+            const bool gamma = p.one_bool("gamma", false);  // default: true for .tga / .png only (imagemap.rs:129)
+            const std::string wrap = p.one_string("wrap", "repeat");
+            t.type = B200PT_TEX_IMAGEMAP;
+            t.wrap = wrap == "black" ? 1 : (wrap == "clamp" ? 2 : 0);
+            t.width = w; t.height = h;
+            auto tex = std::make_unique<std::vector<float>>((size_t)w * h);
+            for (int y = 0; y < h; ++y)
+                for (int x = 0; x < w; ++x) {
+                    // generate_mipmap (mipmap/cache.rs): texel (x, y) of the image lands in row h - 1 - y (texture space has
+                    // t = 0 at the bottom); convert_in::<Float>: scale * (gamma ? inv_gamma(y()) : y())
+                    const float* c = &rgb[((size_t)y * w + x) * 3];
+                    float lum = 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2];
+                    if (gamma) lum = lum <= 0.04045f ? lum * 1.0f / 12.92f : std::pow((lum + 0.055f) * 1.0f / 1.055f, 2.4f);  // inv_gamma_correct, pbrt/common.rs:152-158
+                    (*tex)[(size_t)(h - 1 - y) * w + x] = scale * lum;
+                }
+            t.texels = tex->data();
+            L->images.push_back(std::move(tex));
+        } else throw Unsupported("Texture \"" + name + "\" \"float\" \"" + cls + "\" is outside this path (constant, checkerboard, dots, imagemap)");
+        L->float_textures.push_back(t);
+        gs.float_textures[name] = (int)L->float_textures.size() - 1;
+    }
+
     void add_triangles(const std::vector<int>& idx, const std::vector<float>& P, const std::vector<float>& N, const std::vector<float>& S,
                        const std::vector<float>& UV, const ParamSet& params) {
-        if (params.has_texture("alpha") || params.has_texture("shadowalpha")) throw Unsupported("alpha / shadowalpha textures are outside this path (constant floats only)");
-        const float alpha = params.one_float("alpha", 1.0f), shadow_alpha = params.one_float("shadowalpha", 1.0f);
+        // triangle.rs:278-312: "texture alpha" names a float texture; an unknown name falls back to the float parameter
+        float alpha = params.one_float("alpha", 1.0f), shadow_alpha = params.one_float("shadowalpha", 1.0f);
+        int alpha_tex[2] = {-1, -1};
+        const char* names[2] = {"alpha", "shadowalpha"};
+        for (int c = 0; c < 2; ++c) {
+            const std::string tn = params.one_texture(names[c]);
+            if (tn.empty()) continue;
+            auto it = gs.float_textures.find(tn);
+            if (it == gs.float_textures.end()) continue;
+            const b200pt_float_texture& ft = L->float_textures[(size_t)it->second];
+            if (ft.type == B200PT_TEX_CONSTANT) (c == 0 ? alpha : shadow_alpha) = ft.value[0];
+            else alpha_tex[c] = it->second;
+        }
         const size_t np = P.size() / 3;
         for (int i : idx) if (i < 0 || (size_t)i >= np) throw Invalid("triangle mesh has an out-of-bounds vertex index");
         const Xf& o2w = gs.ctm;
         const bool flip = gs.reverse != swaps_handedness(o2w.m);
         uint32_t fl = (flip ? B200PT_PRIM_FLIP_NORMAL : 0u) | (alpha == 0.0f ? B200PT_PRIM_ALPHA_ZERO : 0u) | (shadow_alpha == 0.0f ? B200PT_PRIM_SHADOW_ALPHA_ZERO : 0u) |
                       (gs.reverse ? B200PT_PRIM_REVERSE_ORIENTATION : 0u) | (!UV.empty() ? B200PT_PRIM_HAS_UV : 0u) | (!N.empty() ? B200PT_PRIM_HAS_NORMALS : 0u) |
-                      (!S.empty() ? B200PT_PRIM_HAS_TANGENTS : 0u);
+                      (!S.empty() ? B200PT_PRIM_HAS_TANGENTS : 0u) | ((alpha_tex[0] >= 0 || alpha_tex[1] >= 0) ? B200PT_PRIM_ALPHA_TEXTURE : 0u);
         // TriangleMesh::new: everything to world space once (triangle.rs:92-99)
         std::vector<V3> wp(np), wn(N.empty() ? 0 : np), ws(S.empty() ? 0 : np);
         for (size_t i = 0; i < np; ++i) wp[i] = xf_point(o2w.m, v3(P[3 * i], P[3 * i + 1], P[3 * i + 2]));
@@ -514,6 +612,7 @@ struct Builder {
         std::vector<float>& Ss = into_object ? L->objects[(size_t)cur_object].tangents : L->tangents;
         std::vector<uint32_t>& F = into_object ? L->objects[(size_t)cur_object].flags : L->flags;
         std::vector<int32_t>& M = into_object ? L->objects[(size_t)cur_object].material : L->material;
+        std::vector<int32_t>& AT = into_object ? L->objects[(size_t)cur_object].alpha_tex : L->alpha_tex;
         if (into_object) {
             ObjectDef& o = L->objects[(size_t)cur_object];
             o.any_uv |= !UV.empty(); o.any_n |= !N.empty(); o.any_s |= !S.empty();
@@ -528,6 +627,7 @@ struct Builder {
             }
             F.push_back(fl);
             M.push_back(mat);
+            AT.push_back(alpha_tex[0]); AT.push_back(alpha_tex[1]);
             if (!into_object) {
                 int light = -1;
                 if (gs.has_area) {  // one DiffuseAreaLight per triangle, api/src/lib.rs:783-803
@@ -792,6 +892,12 @@ void Builder::finish() {
         L->flags.insert(L->flags.end(), o.flags.begin(), o.flags.end());
         L->material.insert(L->material.end(), o.material.begin(), o.material.end());
         L->light.insert(L->light.end(), o.flags.size(), -1);
+        L->alpha_tex.insert(L->alpha_tex.end(), o.alpha_tex.begin(), o.alpha_tex.end());
+    }
+    if (!L->float_textures.empty()) {
+        d.float_textures = L->float_textures.data(); d.n_float_textures = (int32_t)L->float_textures.size();
+        d.prim_alpha_tex = L->alpha_tex.data();
+        d.noise_perm = L->noise_perm.empty() ? nullptr : L->noise_perm.data();
     }
     d.nodes = L->nodes.data(); d.n_nodes = (int64_t)L->nodes.size(); d.ordered_prims = L->ordered.data();
     d.tri_verts = L->verts.data(); d.prim_flags = L->flags.data(); d.prim_material = L->material.data(); d.prim_light = L->light.data();
@@ -935,7 +1041,8 @@ static void parse_stream(Lexer& lx, Builder& B) {
             B.L->instances.push_back(in);
         }
         else if (d == "Include") { parse_file(B.resolve(str()), B); }
-        else if (d == "Texture" || d == "MakeNamedMedium" || d == "MediumInterface" || d == "ActiveTransform" || d == "TransformTimes")
+        else if (d == "Texture") { std::string n = str(); std::string ty = str(); std::string cls = str(); ParamSet p = parse_params(lx); B.texture(n, ty, cls, p); }
+        else if (d == "MakeNamedMedium" || d == "MediumInterface" || d == "ActiveTransform" || d == "TransformTimes")
             throw Unsupported("directive " + d + " is outside this path");
         else lx.fail("unknown directive '" + d + "'");
     }

@@ -118,8 +118,8 @@ B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, in
                     float t, b0, b1, b2;
                     if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, first + i)) {
                         if (ANY) {
-                            if (!(flags & 6u)) return true;
-                        } else if (!(flags & 2u)) {
+                            if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) return true;
+                        } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                             hit = true;
                             t_max = t;
                             out->t = t; out->prim = prim; out->b0 = b0; out->b1 = b1; out->b2 = b2;
@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
                     float t, b0, b1, b2;
                     if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, tri_i - 1)) {
                         if (ANY) {
-                            if (!(flags & 6u)) { hit = true; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
-                        } else if (!(flags & 2u)) {
+                            if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { hit = true; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
+                        } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                             hit = true;
                             t_max = t;
                             h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;
@@ -370,6 +370,11 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
     const int kRetry = (int)0x80000001;  // pop (again) in the next NODE step
     const int kHold = (int)0x80000002;   // scene-aggregate level: wait until the parked leaf has been processed, then pop
     StackEntry<ANY> stack[B2_STACK2];
+    // The world-space ray context (origin, reciprocals, watertight-test constants) while the lane walks an object: kept in
+    // local memory (volatile: not promoted to registers) instead of being re-derived from the input ray on return.
+    // profiles/r2_ncu_full_c5_k_trace_spec2_2l_sass.csv.gz: the re-derivation (three divisions, make_tri_ctx: ~250
+    // instructions) ran with 1.0 of 32 lanes, 19.6 M times per 16.6 M rays = 22 % of the kernel's issued instructions.
+    volatile float wsave[10];
 
     int ray_id = -1;
     RayCtx r;
@@ -528,6 +533,9 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
                         in_inst = (int)prim; inst_hit = false;
                         if (top_code != kIdle) { stack[sp].set(top_code, top_t); ++sp; top_code = kIdle; }
                         sp_base = sp;
+                        wsave[0] = r.ox; wsave[1] = r.oy; wsave[2] = r.oz; wsave[3] = r.ix; wsave[4] = r.iy; wsave[5] = r.iz;
+                        wsave[6] = tc.sx; wsave[7] = tc.sy; wsave[8] = tc.sz;
+                        wsave[9] = __int_as_float(tc.kx | (tc.ky << 2) | (tc.kz << 4) | (negmask << 6));
                         r = ri;
                         negmask = r.nx | (r.ny << 1) | (r.nz << 2);
                         tc = make_tri_ctx(ir.dx, ir.dy, ir.dz);
@@ -541,8 +549,8 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
                     float t, b0, b1, b2;
                     if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)tri_i - 1)) {
                         if (ANY) {
-                            if (!(flags & 6u)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
-                        } else if (!(flags & 2u)) {
+                            if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
+                        } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                             t_max = t;
                             h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;
                             h_inst = in_inst;
@@ -566,8 +574,15 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
                 if (!inst_hit) t_max = world_t_max;
                 in_inst = -1;
                 sp_base = 0;
-                const float4 w0 = __ldg(rays + 2ll * ray_id), w1 = __ldg(rays + 2ll * ray_id + 1);
-                set_ray(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
+                {
+                    r.ox = wsave[0]; r.oy = wsave[1]; r.oz = wsave[2]; r.ix = wsave[3]; r.iy = wsave[4]; r.iz = wsave[5];
+                    tc.sx = wsave[6]; tc.sy = wsave[7]; tc.sz = wsave[8];
+                    const int pk = __float_as_int(wsave[9]);
+                    tc.kx = pk & 3; tc.ky = (pk >> 2) & 3; tc.kz = (pk >> 4) & 3;
+                    negmask = (pk >> 6) & 7;
+                    r.nx = negmask & 1; r.ny = (negmask >> 1) & 1; r.nz = (negmask >> 2) & 1;
+                    o = mk(r.ox, r.oy, r.oz);
+                }
                 if (sp > 0) { --sp; const StackEntry<ANY> e = stack[sp]; top_code = e.code(); top_t = e.t(); }
                 if (saved_left > 0) { pend = -1; tri_i = saved_i; tri_left = saved_left; cur = kHold; }  // pend: any leaf code, tri_i / tri_left carry the position
                 else cur = kRetry;
@@ -612,7 +627,7 @@ static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, 
         // B200PT_2L_KERNEL: 3 (default) = three-phase kernel (instancing_spec3.cuh), 2 = k_trace_spec2_2l; B200PT_2L_TUNE picks the
         // phase-switch / refill thresholds of the three-phase kernel (A/B)
         static const int kernel = [] { const char* e = std::getenv("B200PT_2L_KERNEL"); return e ? std::atoi(e) : 2; }();
-        static const int tune = [] { const char* e = std::getenv("B200PT_2L_TUNE"); return e ? std::atoi(e) : 0; }();
+        static const int tune = [] { const char* e = std::getenv("B200PT_2L_TUNE"); return e ? std::atoi(e) : 4; }();  // profiles/r2_c5_ab.txt: (12, 8) is 5 % faster on C5 than (20, 20)
         if (kernel == 3 && kb == 7) {
             if (tune == 1) k_trace_spec3_2l<ANY, 16, 12, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
             else if (tune == 2) k_trace_spec3_2l<ANY, 12, 8, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);

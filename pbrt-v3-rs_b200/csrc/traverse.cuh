@@ -25,6 +25,8 @@
 //   entry is popped; every other term of the test does not depend on t_max.
 #pragma once
 #include "pt_math.cuh"
+#include "../../include/b200pt.h"
+#include "alpha_tex.cuh"
 
 namespace b2 {
 
@@ -41,7 +43,17 @@ struct DeviceAccel {
     int n_nodes;
     long long n_prims;
     int device;           // CUDA device the arrays live on (host side: which DevCtx launches use)
+    const DeviceAlpha* alpha;  // alpha-mask textures: a DeviceAlpha in device memory (null when the scene has none)
 };
+
+// The alpha test of Triangle::intersect (closest hit: "alpha") / intersect_p (any hit: "alpha" and "shadowalpha").
+// Constant textures are flag bits; B200PT_PRIM_ALPHA_TEXTURE sends the hit through the texture evaluation (alpha_tex.cuh).
+template <bool ANY>
+B2_D bool alpha_ok(const DeviceAccel& A, uint32_t flags, uint32_t prim, float b0, float b1, float b2) {
+    if (flags & (ANY ? 6u : 2u)) return false;
+    if (!(flags & B200PT_PRIM_ALPHA_TEXTURE)) return true;
+    return alpha_tex_accepts(A.alpha, prim, b0, b1, b2, ANY);
+}
 
 #define B2_EMPTY_ROOT 0x7fffffff
 
@@ -286,8 +298,8 @@ B2_D bool traverse_wide(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
                 float t, b0, b1, b2;
                 if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, first + i)) {
                     if (ANY) {
-                        if (!(flags & 6u)) return true;  // alpha / shadow-alpha == 0 reject (triangle.rs:886-899)
-                    } else if (!(flags & 2u)) {          // alpha == 0 reject (triangle.rs:587-607)
+                        if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) return true;  // alpha / shadow-alpha == 0 reject (triangle.rs:886-899)
+                    } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {          // alpha == 0 reject (triangle.rs:587-607)
                         hit = true;
                         t_max = t;
                         out->t = t; out->prim = prim; out->b0 = b0; out->b1 = b1; out->b2 = b2;
@@ -341,8 +353,8 @@ B2_D bool traverse_ref(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
                     float t, b0, b1, b2;
                     if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)offset + i)) {
                         if (ANY) {
-                            if (!(flags & 6u)) return true;
-                        } else if (!(flags & 2u)) {
+                            if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) return true;
+                        } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                             hit = true;
                             t_max = t;
                             out->t = t; out->prim = prim; out->b0 = b0; out->b1 = b1; out->b2 = b2;

@@ -1,5 +1,6 @@
 // Traversal kernels (K2a closest-hit, K2b any-hit; K3 triangle test inlined).
 // See traverse.cuh for the data layout and the equivalence argument.
+#include <cstdlib>
 #include "common.cuh"
 #include "traverse_phased.cuh"
 #include "traverse_spec.cuh"
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
                         float t, b0, b1, b2;
                         if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, first + i)) {
                             if (ANY) {
-                                if (!(flags & 6u)) { any_done = true; break; }
-                            } else if (!(flags & 2u)) {
+                                if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { any_done = true; break; }
+                            } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                                 hit = true;
                                 t_max = t;
                                 h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;
@@ -204,8 +205,8 @@ __global__ void __launch_bounds__(128) k_count(DeviceAccel A, const float4* __re
                         float t, b0, b1, b2;
                         ++nt;
                         if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)offset + k)) {
-                            if (ANY) { if (!(flags & 6u)) done = true; }
-                            else if (!(flags & 2u)) t_max = t;
+                            if (ANY) { if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) done = true; }
+                            else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) t_max = t;
                         }
                     }
                     if (sp == 0) done = true; else cur = stack[--sp];
@@ -301,8 +302,21 @@ static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void*
         } else if (variant == 5) {
             k_trace_spec<ANY, 16, 16, ANY ? 8 : 7><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
         } else {
+            // B200PT_TRACE_TUNE (A/B): phase-switch / refill thresholds other than the round-1 choice (20, 20 / 16)
+            static const int tune = [] { const char* e = std::getenv("B200PT_TRACE_TUNE"); return e ? std::atoi(e) : 0; }();
+            if (tune == 1) {
+                if (ANY) k_trace_spec2<true, 16, 12, 8, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+                else k_trace_spec2<false, 16, 12, 7, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+            } else if (tune == 2) {
+                if (ANY) k_trace_spec2<true, 12, 8, 8, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+                else k_trace_spec2<false, 12, 8, 7, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+            } else if (tune == 3) {
+                if (ANY) k_trace_spec2<true, 20, 8, 8, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+                else k_trace_spec2<false, 20, 8, 7, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+            } else {
             if (ANY) k_trace_spec2<true, 20, 16, 8, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
             else k_trace_spec2<false, 20, 20, 7, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+            }
         }
     }
     g_launches.fetch_add(1);

@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
                 float t, b0, b1, b2;
                 if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, tri_i)) {
                     if (ANY) {
-                        if (!(flags & 6u)) { hit = true; sp = 0; top_code = kIdle; tri_left = 1; }
-                    } else if (!(flags & 2u)) {
+                        if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { hit = true; sp = 0; top_code = kIdle; tri_left = 1; }
+                    } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                         hit = true;
                         t_max = t;
                         h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;

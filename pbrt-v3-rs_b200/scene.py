@@ -134,6 +134,8 @@ class SceneDescription:
         self.prim_material = np.zeros(0, dtype=np.int32)
         self.prim_light = np.zeros(0, dtype=np.int32)
         self.prim_flags = np.zeros(0, dtype=np.uint32)
+        self.prim_alpha_tex = np.zeros((0, 2), dtype=np.int32)  # per primitive: alpha / shadowalpha float-texture index or -1
+        self.float_textures = []  # dicts, see add_float_texture
         self.materials = []   # list of dicts
         self.lights = []      # list of dicts
         self.camera = dict(eye=(0, 0, -5), look=(0, 0, 0), up=(0, 1, 0), fov=45.0, lensradius=0.0, focaldistance=1e6,
@@ -168,6 +170,29 @@ class SceneDescription:
         blk = np.zeros((n, width), dtype=F32) if a is None else np.ascontiguousarray(a, dtype=F32).reshape(n, width)
         return np.concatenate([base, blk])
 
+    def add_float_texture(self, type, **params):
+        """Texture "name" "float" "<type>" (api/src/lib.rs make_float_texture) for use as a mesh's alpha / shadowalpha:
+        type "constant" (value), "checkerboard" (tex1, tex2, uscale, vscale, udelta, vdelta), "dots" (inside, outside - the
+        scene-file parameter names -, uscale, ...), "imagemap" (texels = level-0 (h, w) float array, wrap).  Returns its index."""
+        assert type in ("constant", "checkerboard", "dots", "imagemap")
+        self.float_textures.append(dict(type=type, **params))
+        return len(self.float_textures) - 1
+
+    def _alpha_pair(self, alpha, shadowalpha):
+        """(constant alpha, constant shadowalpha, texture index pair): a texture index is given as ("texture", k)."""
+        pair = [-1, -1]
+        consts = [1.0, 1.0]
+        for c, a in enumerate((alpha, shadowalpha)):
+            if isinstance(a, tuple) and a[0] == "texture":
+                t = self.float_textures[a[1]]
+                if t["type"] == "constant":
+                    consts[c] = float(t.get("value", 1.0))
+                else:
+                    pair[c] = int(a[1])
+            else:
+                consts[c] = float(a)
+        return consts[0], consts[1], pair
+
     def add_mesh(self, tri_verts, material, area_light=None, reverse_orientation=False, alpha=1.0, shadowalpha=1.0, uv=None, normals=None,
                  tangents=None, swaps_handedness=False):
         """One GeometricPrimitive per triangle; with ``area_light={'L': (r,g,b), 'twosided': False}`` one
@@ -181,8 +206,10 @@ class SceneDescription:
         self.tri_tangents = self._attr(tangents, n, 9, self.tri_tangents, n0)
         self.tri_verts = np.concatenate([self.tri_verts, tv])
         self.prim_material = np.concatenate([self.prim_material, np.full(n, material, dtype=np.int32)])
-        flags = self._mesh_flags(reverse_orientation, swaps_handedness, alpha, shadowalpha, uv, normals, tangents)
+        alpha, shadowalpha, tex_pair = self._alpha_pair(alpha, shadowalpha)
+        flags = self._mesh_flags(reverse_orientation, swaps_handedness, alpha, shadowalpha, uv, normals, tangents) | (128 if max(tex_pair) >= 0 else 0)
         self.prim_flags = np.concatenate([self.prim_flags, np.full(n, flags, dtype=np.uint32)])
+        self.prim_alpha_tex = np.concatenate([self.prim_alpha_tex, np.tile(np.array(tex_pair, dtype=np.int32), (n, 1))])
         pl = np.full(n, -1, dtype=np.int32)
         if area_light is not None:
             for i in range(n):
@@ -209,11 +236,13 @@ class SceneDescription:
 
     # -- flattening --
     # -- instancing: ObjectBegin/ObjectEnd + ObjectInstance (api/src/lib.rs:880-987) --
-    def add_object(self, tri_verts, material, reverse_orientation=False, uv=None, normals=None, tangents=None):
+    def add_object(self, tri_verts, material, reverse_orientation=False, uv=None, normals=None, tangents=None, alpha=1.0, shadowalpha=1.0):
         """Defines a named object (its triangles get their own BVHAccel); returns the object id."""
         tv = np.ascontiguousarray(tri_verts, dtype=F32).reshape(-1, 9)
-        self.objects.append(dict(tri_verts=tv, material=material, flags=self._mesh_flags(reverse_orientation, False, 1.0, 1.0, uv, normals, tangents),
-                                 nodes=None, ordered=None, uv=uv, normals=normals, tangents=tangents))
+        alpha, shadowalpha, tex_pair = self._alpha_pair(alpha, shadowalpha)
+        self.objects.append(dict(tri_verts=tv, material=material,
+                                 flags=self._mesh_flags(reverse_orientation, False, alpha, shadowalpha, uv, normals, tangents) | (128 if max(tex_pair) >= 0 else 0),
+                                 nodes=None, ordered=None, uv=uv, normals=normals, tangents=tangents, alpha_tex=tex_pair))
         return len(self.objects) - 1
 
     def add_instance(self, obj, instance_to_world):
@@ -299,6 +328,15 @@ class SceneDescription:
                 n = o["tri_verts"].shape[0]
                 blocks.append(np.zeros((n, width), dtype=F32) if o.get(key) is None else np.ascontiguousarray(o[key], dtype=F32).reshape(n, width))
             setattr(d, field, arr(np.concatenate(blocks), F32))
+        if self.float_textures:
+            from . import float_texture_array, noise_perm
+            blocks = [self.prim_alpha_tex.reshape(-1, 2)]
+            for o in self.objects:
+                blocks.append(np.tile(np.array(o.get("alpha_tex", (-1, -1)), dtype=np.int32), (o["tri_verts"].shape[0], 1)))
+            d.prim_alpha_tex = arr(np.concatenate(blocks), np.int32)
+            d.float_textures = C.cast(float_texture_array(self.float_textures, keep), C.c_void_p)
+            d.n_float_textures = len(self.float_textures)
+            d.noise_perm = arr(noise_perm(), np.uint8)
         d.objects, d.n_objects = C.cast(objs, C.c_void_p), len(self.objects)
         d.instances, d.n_instances = C.cast(insts, C.c_void_p), len(self.instances)
 

@@ -53,6 +53,11 @@ def lib():
         L.orc_accel_create.argtypes = [vp, i64, vp, vp, vp, i64]
         L.orc_accel_destroy.argtypes = [vp]
         L.orc_accel_set_uvs.argtypes = [vp, vp, i64]
+        L.orc_accel_set_alpha.argtypes = [vp, vp, C.c_int, vp, vp, i64]
+        L.orc_float_texture_evaluate.argtypes = [vp, vp, C.c_float, C.c_float]
+        L.orc_float_texture_evaluate.restype = C.c_float
+        L.orc_noise_3d.argtypes = [vp, C.c_float, C.c_float, C.c_float]
+        L.orc_noise_3d.restype = C.c_float
         L.orc_envmap_prepare.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
         L.orc_envmap_lookup.argtypes = [vp, C.c_int, C.c_int, vp, C.c_float, vp]
         L.orc_triangle_geometry.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
@@ -80,6 +85,14 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _pkg():
+    """The product package, for its ctypes struct definitions only (b200pt_float_texture mirrors include/b200pt.h)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import __graft_entry__ as ge
+    return ge.load_package()
 
 
 def ncpu():
@@ -125,9 +138,26 @@ class OracleAccel:
             fl = np.zeros(self.verts.shape[0], dtype=np.uint32) if self.flags is None else self.flags
             self.flags = fl | np.uint32(16)  # PRIM_HAS_UV
         self.h = lib().orc_accel_create(_p(self.nodes), len(self.nodes), _p(self.ordered), _p(self.verts), _p(self.flags), self.verts.shape[0])
+        self.uv = None
         if tri_uvs is not None:
-            uv = np.ascontiguousarray(tri_uvs, dtype=np.float32).reshape(-1, 6)
+            uv = self.uv = np.ascontiguousarray(tri_uvs, dtype=np.float32).reshape(-1, 6)
             lib().orc_accel_set_uvs(self.h, _p(uv), uv.shape[0])
+
+    def set_alpha_textures(self, textures, prim_alpha_tex):
+        """Same arguments as BVHAccel.set_alpha_textures; the flags gain PRIM_ALPHA_TEXTURE where an index is >= 0."""
+        pkg = _pkg()
+        pat = np.ascontiguousarray(prim_alpha_tex, dtype=np.int32).reshape(-1, 2)
+        fl = np.zeros(self.verts.shape[0], dtype=np.uint32) if self.flags is None else self.flags.copy()
+        fl[(pat >= 0).any(1)] |= np.uint32(128)
+        self.flags = fl
+        lib().orc_accel_destroy(self.h)
+        self.h = lib().orc_accel_create(_p(self.nodes), len(self.nodes), _p(self.ordered), _p(self.verts), _p(self.flags), self.verts.shape[0])
+        if getattr(self, "uv", None) is not None:
+            lib().orc_accel_set_uvs(self.h, _p(self.uv), self.uv.shape[0])
+        keep = []
+        arr = pkg.float_texture_array(list(textures), keep)
+        perm = pkg.noise_perm()
+        lib().orc_accel_set_alpha(self.h, C.cast(arr, C.c_void_p), len(textures), _p(pat), _p(perm), self.verts.shape[0])
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -129,7 +129,7 @@ B2_D float float_tex_eval(const DeviceAlpha& D, const DFloatTex& T, float u, flo
 }
 
 // true = the hit survives its mesh's alpha (closest hit) / alpha and shadowalpha (any hit) textures
-static __device__ __noinline__ bool alpha_tex_accepts(const DeviceAlpha* __restrict__ Dp, uint32_t prim, float b0, float b1, float b2, bool shadow) {
+B2_D bool alpha_tex_accepts_inl(const DeviceAlpha* __restrict__ Dp, uint32_t prim, float b0, float b1, float b2, bool shadow) {
     const DeviceAlpha D = *Dp;
     const float* uv = D.uv + 6ll * prim;
     const float u = b0 * uv[0] + b1 * uv[2] + b2 * uv[4];  // uv_hit = b0 * uv[0] + b1 * uv[1] + b2 * uv[2] (triangle.rs:585)
@@ -138,6 +138,10 @@ static __device__ __noinline__ bool alpha_tex_accepts(const DeviceAlpha* __restr
     if (ta >= 0 && float_tex_eval(D, D.tex[ta], u, v) == 0.0f) return false;
     if (shadow && ts >= 0 && float_tex_eval(D, D.tex[ts], u, v) == 0.0f) return false;
     return true;
+}
+
+static __device__ __noinline__ bool alpha_tex_accepts(const DeviceAlpha* __restrict__ Dp, uint32_t prim, float b0, float b1, float b2, bool shadow) {
+    return alpha_tex_accepts_inl(Dp, prim, b0, b1, b2, shadow);
 }
 
 }  // namespace b2

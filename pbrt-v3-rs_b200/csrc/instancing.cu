@@ -118,7 +118,7 @@ B2_D bool traverse_top(const DeviceAccel2& A2, const Ray32& ray, HitOut* out, in
                     float t, b0, b1, b2;
                     if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, first + i)) {
                         if (ANY) {
-                            if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) return true;
+                            if (alpha_ok_any(A, flags, first + i, o, tc, t_max)) return true;
                         } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                             hit = true;
                             t_max = t;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
                     float t, b0, b1, b2;
                     if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, tri_i - 1)) {
                         if (ANY) {
-                            if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { hit = true; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
+                            if (alpha_ok_any(A, flags, tri_i - 1, o, tc, t_max)) { hit = true; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
                         } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                             hit = true;
                             t_max = t;
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
                     float t, b0, b1, b2;
                     if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)tri_i - 1)) {
                         if (ANY) {
-                            if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
+                            if (alpha_ok_any(A, flags, (long long)tri_i - 1, o, tc, t_max)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
                         } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                             t_max = t;
                             h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;

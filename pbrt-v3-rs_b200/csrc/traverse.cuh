@@ -48,12 +48,7 @@ struct DeviceAccel {
 
 // The alpha test of Triangle::intersect (closest hit: "alpha") / intersect_p (any hit: "alpha" and "shadowalpha").
 // Constant textures are flag bits; B200PT_PRIM_ALPHA_TEXTURE sends the hit through the texture evaluation (alpha_tex.cuh).
-template <bool ANY>
-B2_D bool alpha_ok(const DeviceAccel& A, uint32_t flags, uint32_t prim, float b0, float b1, float b2) {
-    if (flags & (ANY ? 6u : 2u)) return false;
-    if (!(flags & B200PT_PRIM_ALPHA_TEXTURE)) return true;
-    return alpha_tex_accepts(A.alpha, prim, b0, b1, b2, ANY);
-}
+
 
 #define B2_EMPTY_ROOT 0x7fffffff
 
@@ -234,6 +229,33 @@ B2_D void load_tri(const float4* tris, long long i, V3* p0, V3* p1, V3* p2, uint
     *prim = __float_as_uint(c.y); *flags = __float_as_uint(c.z); *leaf_n = __float_as_uint(c.w);
 }
 
+// The alpha test of Triangle::intersect (closest hit: "alpha") / intersect_p (any hit: "alpha" and "shadowalpha").
+// Constant textures are flag bits; B200PT_PRIM_ALPHA_TEXTURE sends the hit through the texture evaluation (alpha_tex.cuh).
+template <bool ANY>
+B2_D bool alpha_ok(const DeviceAccel& A, uint32_t flags, uint32_t prim, float b0, float b1, float b2) {
+    if (flags & (ANY ? 6u : 2u)) return false;
+    if (!(flags & B200PT_PRIM_ALPHA_TEXTURE)) return true;
+    return alpha_tex_accepts(A.alpha, prim, b0, b1, b2, ANY);
+}
+// Any-hit form: the kernels do not keep the barycentrics of an accepted candidate, so the (rare) textured triangle is
+// tested once more out of line - only values that are live in the walk anyway cross the call.
+static __device__ __noinline__ bool alpha_any_retest(const DeviceAlpha* __restrict__ Dp, const float4* __restrict__ tris, long long i, float4 o_tmax, float4 s_k) {
+    const float4 ra = __ldg(tris + 4 * i), rb = __ldg(tris + 4 * i + 1), rc = __ldg(tris + 4 * i + 2);
+    const V3 p0 = mk(ra.x, ra.y, ra.z), p1 = mk(ra.w, rb.x, rb.y), p2 = mk(rb.z, rb.w, rc.x);
+    const uint32_t prim = __float_as_uint(rc.y);
+    TriCtx tc;
+    const int pk = __float_as_int(s_k.w);
+    tc.kx = pk & 3; tc.ky = (pk >> 2) & 3; tc.kz = (pk >> 4) & 3; tc.sx = s_k.x; tc.sy = s_k.y; tc.sz = s_k.z;
+    float t, b0, b1, b2;
+    if (!triangle_test(mk(o_tmax.x, o_tmax.y, o_tmax.z), tc, o_tmax.w, p0, p1, p2, &t, &b0, &b1, &b2)) return false;  // cannot happen: same inputs as the caller's test
+    return alpha_tex_accepts_inl(Dp, prim, b0, b1, b2, true);
+}
+B2_D bool alpha_ok_any(const DeviceAccel& A, uint32_t flags, long long tri_index, V3 o, const TriCtx& tc, float t_max) {
+    if (flags & 6u) return false;
+    if (!(flags & B200PT_PRIM_ALPHA_TEXTURE)) return true;
+    return alpha_any_retest(A.alpha, A.tris, tri_index, make_float4(o.x, o.y, o.z, t_max), make_float4(tc.sx, tc.sy, tc.sz, __int_as_float(tc.kx | (tc.ky << 2) | (tc.kz << 4))));
+}
+
 struct HitOut {
     float t;
     uint32_t prim;
@@ -298,7 +320,7 @@ B2_D bool traverse_wide(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
                 float t, b0, b1, b2;
                 if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, first + i)) {
                     if (ANY) {
-                        if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) return true;  // alpha / shadow-alpha == 0 reject (triangle.rs:886-899)
+                        if (alpha_ok_any(A, flags, first + i, o, tc, t_max)) return true;  // alpha / shadow-alpha == 0 reject (triangle.rs:886-899)
                     } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {          // alpha == 0 reject (triangle.rs:587-607)
                         hit = true;
                         t_max = t;
@@ -353,7 +375,7 @@ B2_D bool traverse_ref(const DeviceAccel& A, const Ray32& ray, HitOut* out) {
                     float t, b0, b1, b2;
                     if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)offset + i)) {
                         if (ANY) {
-                            if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) return true;
+                            if (alpha_ok_any(A, flags, (long long)offset + i, o, tc, t_max)) return true;
                         } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                             hit = true;
                             t_max = t;

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128, 4) k_trace_persistent(DeviceAccel A, cons
                         float t, b0, b1, b2;
                         if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, first + i)) {
                             if (ANY) {
-                                if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { any_done = true; break; }
+                                if (alpha_ok_any(A, flags, first + i, o, tc, t_max)) { any_done = true; break; }
                             } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                                 hit = true;
                                 t_max = t;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(128) k_count(DeviceAccel A, const float4* __re
                         float t, b0, b1, b2;
                         ++nt;
                         if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)offset + k)) {
-                            if (ANY) { if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) done = true; }
+                            if (ANY) { if (alpha_ok_any(A, flags, (long long)offset + k, o, tc, t_max)) done = true; }
                             else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) t_max = t;
                         }
                     }

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased(DeviceAccel A, co
                 float t, b0, b1, b2;
                 if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, tri_i)) {
                     if (ANY) {
-                        if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { hit = true; sp = 0; top_code = kIdle; tri_left = 1; }
+                        if (alpha_ok_any(A, flags, tri_i, o, tc, t_max)) { hit = true; sp = 0; top_code = kIdle; tri_left = 1; }
                     } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                         hit = true;
                         t_max = t;

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec(DeviceAccel A, cons
                 float t, b0, b1, b2;
                 if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)tri_i)) {
                     if (ANY) {
-                        if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; tri_left = 1; }  // occluded: drop the rest of the walk
+                        if (alpha_ok_any(A, flags, (long long)tri_i, o, tc, t_max)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; tri_left = 1; }  // occluded: drop the rest of the walk
                     } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                         t_max = t;
                         h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2(DeviceAccel A, con
                 float t, b0, b1, b2;
                 if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)tri_i)) {
                     if (ANY) {
-                        if (alpha_ok<true>(A, flags, prim, b0, b1, b2)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; tri_left = 1; }
+                        if (alpha_ok_any(A, flags, (long long)tri_i, o, tc, t_max)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; tri_left = 1; }
                     } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
                         t_max = t;
                         h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;

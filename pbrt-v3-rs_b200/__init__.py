@@ -168,6 +168,8 @@ def lib():
     L.b200pt_loaded_scene_free.restype = None
     L.b200pt_write_pfm.argtypes = [C.c_char_p, vp, i32, i32]
     L.b200pt_read_pfm.argtypes = [C.c_char_p, vp, vp]
+    L.b200pt_write_png.argtypes = [C.c_char_p, vp, i32, i32]
+    L.b200pt_write_image.argtypes = [C.c_char_p, vp, i32, i32]
     L.b200pt_init.argtypes = [C.c_int]
     L.b200pt_bvh_build_sah.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.b200pt_triangle_bounds.argtypes = [vp, i64, vp]
@@ -335,6 +337,12 @@ def load_pbrt(path):
 def write_pfm(path, rgb):
     a = np.ascontiguousarray(rgb, dtype=np.float32)
     _check(lib().b200pt_write_pfm(os.fsencode(path), _ptr(a), a.shape[1], a.shape[0]), "b200pt_write_pfm")
+
+
+def write_image(path, rgb):
+    """write_image (core/src/image_io.rs): .png = the reference's 8-bit sRGB encode, .pfm = float."""
+    a = np.ascontiguousarray(rgb, dtype=np.float32)
+    _check(lib().b200pt_write_image(os.fsencode(path), _ptr(a), a.shape[1], a.shape[0]), "b200pt_write_image")
 
 
 def read_pfm(path):

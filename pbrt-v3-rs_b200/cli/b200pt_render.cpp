@@ -2,7 +2,7 @@
 // reference's `pbrt-v3-rs` binary (bin/src/main.rs -> api::pbrt_init / parse / pbrt_cleanup): reads a pbrt-v3 scene
 // file, renders it on the GPU and writes the image.  Links against libb200pt.so only; no CUDA or Python on this side.
 //
-//   b200pt_render [--device N] [--outfile image.pfm] [--cropwindow x0 x1 y0 y1 is taken from the scene file] scene.pbrt
+//   b200pt_render [--device N] [--outfile image.png|.pfm] [--cropwindow x0 x1 y0 y1 is taken from the scene file] scene.pbrt
 //
 // Options follow the reference's where they exist (core/src/app.rs: --outfile; --nthreads / --quick do not apply).
 #include <chrono>
@@ -27,9 +27,9 @@ int main(int argc, char** argv) {
         if (a == "--device" && i + 1 < argc) device = std::atoi(argv[++i]);
         else if ((a == "--outfile" || a == "-o") && i + 1 < argc) outfile = argv[++i];
         else if (a == "--help" || a == "-h") {
-            std::printf("usage: b200pt_render [--device N] [--outfile image.pfm] scene.pbrt\n"
+            std::printf("usage: b200pt_render [--device N] [--outfile image.png|.pfm] scene.pbrt\n"
                         "Renders the scene with the B200 path (path / whitted / directlighting integrators over triangle meshes)\n"
-                        "and writes a PFM image (default: the Film's \"filename\" with a .pfm extension).\n");
+                        "and writes a .png (the reference's 8-bit sRGB encode) or .pfm image (default: the Film's \"filename\").\n");
             return 0;
         } else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "b200pt_render: unknown option %s\n", a.c_str()); return 2; }
         else scene_path = a;
@@ -63,12 +63,13 @@ int main(int argc, char** argv) {
     std::printf("rendered in %.3f s: %.3e samples/s, %.1f Mrays/s (%llu camera, %llu closest-hit, %llu shadow rays)\n", dt, (double)rays[0] / dt,
                 (double)(rays[1] + rays[2]) / dt / 1e6, (unsigned long long)rays[0], (unsigned long long)rays[1], (unsigned long long)rays[2]);
 
-    if (outfile.empty()) {
+    if (outfile.empty()) {  // the Film's "filename"; extensions this path does not write (.exr, .tga) become .pfm
         outfile = b200pt_loaded_scene_output(loaded);
         const size_t dot = outfile.find_last_of('.');
-        outfile = (dot == std::string::npos ? outfile : outfile.substr(0, dot)) + ".pfm";
+        const std::string ext = dot == std::string::npos ? std::string() : outfile.substr(dot);
+        if (ext != ".png" && ext != ".pfm") outfile = (dot == std::string::npos ? outfile : outfile.substr(0, dot)) + ".pfm";
     }
-    if (b200pt_write_pfm(outfile.c_str(), rgb.data(), w, h) != B200PT_OK) return fail("b200pt_write_pfm");
+    if (b200pt_write_image(outfile.c_str(), rgb.data(), w, h) != B200PT_OK) return fail("b200pt_write_image");
     std::printf("wrote %s\n", outfile.c_str());
     b200pt_scene_destroy(scene);
     b200pt_loaded_scene_free(loaded);

@@ -1095,6 +1095,87 @@ const b200pt_scene_desc* b200pt_loaded_scene_desc(const b200pt_loaded_scene* s) 
 const char* b200pt_loaded_scene_output(const b200pt_loaded_scene* s) { return s ? s->L.output.c_str() : ""; }
 void b200pt_loaded_scene_free(b200pt_loaded_scene* s) { delete s; }
 
+// 8-bit PNG as core/src/image_io.rs writes it (write_8_bit, :291-390): every channel clamp(255 * gamma_correct(v) + 0.5, 0, 255)
+// as u8, RGB, 8 bits, no interlace.  The deflate stream uses stored blocks (no compressor in this image; any PNG reader
+// accepts them), CRC-32 / Adler-32 computed here.
+namespace b2load {
+static uint32_t crc32_update(uint32_t c, const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) { uint32_t v = i; for (int k = 0; k < 8; ++k) v = (v & 1u) ? 0xedb88320u ^ (v >> 1) : v >> 1; table[i] = v; }
+        ready = true;
+    }
+    for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+    return c;
+}
+static void png_chunk(std::ofstream& f, const char type[4], const std::vector<uint8_t>& data) {
+    auto be32 = [&](uint32_t v) { const uint8_t b[4] = {(uint8_t)(v >> 24), (uint8_t)(v >> 16), (uint8_t)(v >> 8), (uint8_t)v}; f.write((const char*)b, 4); };
+    be32((uint32_t)data.size());
+    f.write(type, 4);
+    if (!data.empty()) f.write((const char*)data.data(), (std::streamsize)data.size());
+    uint32_t c = crc32_update(0xffffffffu, (const uint8_t*)type, 4);
+    c = crc32_update(c, data.data(), data.size()) ^ 0xffffffffu;
+    be32(c);
+}
+static float gamma_correct(float v) { return v <= 0.0031308f ? 12.92f * v : 1.055f * std::pow(v, 1.0f / 2.4f) - 0.055f; }  // pbrt/common.rs:140-146
+static void write_png(const std::string& path, const float* rgb, int w, int h) {
+    std::vector<uint8_t> raw((size_t)h * (1 + 3 * (size_t)w));
+    for (int y = 0; y < h; ++y) {
+        uint8_t* row = &raw[(size_t)y * (1 + 3 * (size_t)w)];
+        row[0] = 0;  // filter type None
+        for (int x = 0; x < 3 * w; ++x) {
+            float v = 255.0f * gamma_correct(rgb[(size_t)y * 3 * w + x]) + 0.5f;
+            v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);  // clamp(); NaN -> 0 like Rust's `as u8`
+            row[1 + x] = v == v ? (uint8_t)v : 0;
+        }
+    }
+    std::vector<uint8_t> z;
+    z.push_back(0x78); z.push_back(0x01);
+    uint32_t a = 1, b = 0;
+    for (size_t pos = 0; pos < raw.size() || pos == 0;) {
+        const size_t n = std::min<size_t>(65535, raw.size() - pos);
+        const bool last = pos + n >= raw.size();
+        z.push_back(last ? 1 : 0);
+        z.push_back((uint8_t)(n & 0xff)); z.push_back((uint8_t)(n >> 8));
+        z.push_back((uint8_t)(~n & 0xff)); z.push_back((uint8_t)((~n >> 8) & 0xff));
+        for (size_t i = 0; i < n; ++i) { a = (a + raw[pos + i]) % 65521u; b = (b + a) % 65521u; }
+        z.insert(z.end(), raw.begin() + (std::ptrdiff_t)pos, raw.begin() + (std::ptrdiff_t)(pos + n));
+        pos += n;
+        if (last) break;
+    }
+    const uint32_t adler = (b << 16) | a;
+    z.push_back((uint8_t)(adler >> 24)); z.push_back((uint8_t)(adler >> 16)); z.push_back((uint8_t)(adler >> 8)); z.push_back((uint8_t)adler);
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw Invalid("cannot write image '" + path + "'");
+    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    f.write((const char*)sig, 8);
+    std::vector<uint8_t> ihdr = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w, (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h, 8, 2, 0, 0, 0};
+    png_chunk(f, "IHDR", ihdr);
+    png_chunk(f, "IDAT", z);
+    png_chunk(f, "IEND", {});
+    if (!f) throw Invalid("error writing image '" + path + "'");
+}
+}  // namespace b2load
+
+int b200pt_write_png(const char* path, const float* rgb, int32_t width, int32_t height) {
+    if (!path || !rgb || width <= 0 || height <= 0) { b200pt_set_error("b200pt_write_png: invalid argument"); return B200PT_ERR_INVALID; }
+    try { b2load::write_png(path, rgb, width, height); }
+    catch (const std::exception& e) { b200pt_set_error(e.what()); return B200PT_ERR_INVALID; }
+    return B200PT_OK;
+}
+// write_image (core/src/image_io.rs:227-289): dispatch on the extension; .png and .pfm are on this path.
+int b200pt_write_image(const char* path, const float* rgb, int32_t width, int32_t height) {
+    if (!path) { b200pt_set_error("b200pt_write_image: null path"); return B200PT_ERR_INVALID; }
+    const std::string p(path);
+    const size_t dot = p.find_last_of('.');
+    const std::string ext = dot == std::string::npos ? std::string() : p.substr(dot);
+    if (ext == ".png") return b200pt_write_png(path, rgb, width, height);
+    if (ext == ".pfm") return b200pt_write_pfm(path, rgb, width, height);
+    b200pt_set_error("b200pt_write_image: only .png and .pfm are written on this path (the reference also writes .exr / .tga)");
+    return B200PT_ERR_UNSUPPORTED;
+}
+
 int b200pt_write_pfm(const char* path, const float* rgb, int32_t width, int32_t height) {
     if (!path || !rgb || width <= 0 || height <= 0) { b200pt_set_error("b200pt_write_pfm: invalid argument"); return B200PT_ERR_INVALID; }
     try { b2load::write_pfm(path, rgb, width, height); }

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_phased2(DeviceAccel2 A2,
 // TransformedPrimitives, and entering one replaces the lane's ray.  Entering spills the register-held stack top and
 // records sp_base; the object's walk pops down to sp_base only; leaving restores the world ray from the input, the
 // interrupted leaf (saved_*) and the stack top.
-template <bool ANY, int kSwitch, int kRefill, int kBlocks>
+template <bool ANY, int kSwitch, int kRefill, int kBlocks, bool kTex = true>
 __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2, const float4* __restrict__ rays, long long n, void* __restrict__ out,
                                                                  unsigned long long* __restrict__ counter, float* __restrict__ b2_out, int* __restrict__ inst_out,
                                                                  const int* __restrict__ n_dev) {
@@ -549,8 +549,8 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2_2l(DeviceAccel2 A2
                     float t, b0, b1, b2;
                     if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)tri_i - 1)) {
                         if (ANY) {
-                            if (alpha_ok_any(A, flags, (long long)tri_i - 1, o, tc, t_max)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
-                        } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
+                            if (alpha_ok_any<kTex>(A, flags, (long long)tri_i - 1, o, tc, t_max)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; sp_base = 0; in_inst = -1; tri_left = 0; }
+                        } else if (alpha_ok<false, kTex>(A, flags, prim, b0, b1, b2)) {
                             t_max = t;
                             h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;
                             h_inst = in_inst;
@@ -640,7 +640,10 @@ static int launch_phased2(const DeviceAccel2& A, const void* d_rays, int64_t n, 
         if (kb == 7 && tune == 1) k_trace_spec2_2l<ANY, 16, 12, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
         else if (kb == 7 && tune == 2) k_trace_spec2_2l<ANY, 20, 12, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
         else if (kb == 7 && tune == 3) k_trace_spec2_2l<ANY, 24, 16, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
-        else if (kb == 7 && tune == 4) k_trace_spec2_2l<ANY, 12, 8, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        else if (kb == 7 && tune == 4) {  // default
+            if (A.top.alpha) k_trace_spec2_2l<ANY, 12, 8, 7, true><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+            else k_trace_spec2_2l<ANY, 12, 8, 7, false><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
+        }
         else if (kb == 5) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 5><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
         else if (kb == 7) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 7><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);
         else if (kb == 8) k_trace_spec2_2l<ANY, 20, ANY ? 16 : 20, 8><<<grid, 128, 0, s>>>(A, (const float4*)d_rays, n, d_out, ctr, d_b2, d_inst, n_dev);

@@ -231,9 +231,13 @@ B2_D void load_tri(const float4* tris, long long i, V3* p0, V3* p1, V3* p2, uint
 
 // The alpha test of Triangle::intersect (closest hit: "alpha") / intersect_p (any hit: "alpha" and "shadowalpha").
 // Constant textures are flag bits; B200PT_PRIM_ALPHA_TEXTURE sends the hit through the texture evaluation (alpha_tex.cuh).
-template <bool ANY>
+// kTex = false: an instantiation for accelerators without alpha textures (no out-of-line call in the kernel at all; the
+// default kernels are launched that way unless the scene has textures - the call costs the any-hit kernel two spilled
+// registers in its inner loop, 6 % on C2).
+template <bool ANY, bool kTex = true>
 B2_D bool alpha_ok(const DeviceAccel& A, uint32_t flags, uint32_t prim, float b0, float b1, float b2) {
     if (flags & (ANY ? 6u : 2u)) return false;
+    if (!kTex) return true;
     if (!(flags & B200PT_PRIM_ALPHA_TEXTURE)) return true;
     return alpha_tex_accepts(A.alpha, prim, b0, b1, b2, ANY);
 }
@@ -250,8 +254,10 @@ static __device__ __noinline__ bool alpha_any_retest(const DeviceAlpha* __restri
     if (!triangle_test(mk(o_tmax.x, o_tmax.y, o_tmax.z), tc, o_tmax.w, p0, p1, p2, &t, &b0, &b1, &b2)) return false;  // cannot happen: same inputs as the caller's test
     return alpha_tex_accepts_inl(Dp, prim, b0, b1, b2, true);
 }
+template <bool kTex = true>
 B2_D bool alpha_ok_any(const DeviceAccel& A, uint32_t flags, long long tri_index, V3 o, const TriCtx& tc, float t_max) {
     if (flags & 6u) return false;
+    if (!kTex) return true;
     if (!(flags & B200PT_PRIM_ALPHA_TEXTURE)) return true;
     return alpha_any_retest(A.alpha, A.tris, tri_index, make_float4(o.x, o.y, o.z, t_max), make_float4(tc.sx, tc.sy, tc.sz, __int_as_float(tc.kx | (tc.ky << 2) | (tc.kz << 4))));
 }

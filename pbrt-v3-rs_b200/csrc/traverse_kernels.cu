@@ -250,9 +250,9 @@ static int persistent_setup(DevCtx* c) {
     c->persist_grid[0] = c->sm_count * (nb > 0 ? nb : 1);
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_persistent<true>, 128, 0));
     c->persist_grid[1] = c->sm_count * (nb > 0 ? nb : 1);
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_spec2<false, 20, 20, 7, 1>, 128, 0));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_spec2<false, 20, 20, 7, 1, false>, 128, 0));
     c->persist_grid[2] = c->sm_count * (nb > 0 ? nb : 1);
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_spec2<true, 20, 16, 8, 1>, 128, 0));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_spec2<true, 20, 16, 8, 1, false>, 128, 0));
     c->persist_grid[3] = c->sm_count * (nb > 0 ? nb : 1);
     c->ring = ring;
     return B200PT_OK;
@@ -314,8 +314,11 @@ static int launch_any(const DeviceAccel& A, const void* d_rays, int64_t n, void*
                 if (ANY) k_trace_spec2<true, 20, 8, 8, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
                 else k_trace_spec2<false, 20, 8, 7, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
             } else {
-            if (ANY) k_trace_spec2<true, 20, 16, 8, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
-            else k_trace_spec2<false, 20, 20, 7, 1><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+            // the scene has no alpha textures (the usual case): instantiation without the texture call
+            if (ANY) { if (A.alpha) k_trace_spec2<true, 20, 16, 8, 1, true><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+                       else k_trace_spec2<true, 20, 16, 8, 1, false><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev); }
+            else { if (A.alpha) k_trace_spec2<false, 20, 20, 7, 1, true><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev);
+                   else k_trace_spec2<false, 20, 20, 7, 1, false><<<grid, block, 0, s>>>(A, R, n, d_out, ctr, d_b2, n_dev); }
             }
         }
     }

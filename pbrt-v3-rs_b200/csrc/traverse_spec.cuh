@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec(DeviceAccel A, cons
 // entry fails `t_entry < t_max`, or that has just parked the leaf it popped, stays in state kRetry and pops again in
 // the next NODE step instead of making the warp wait in a 2-3-lane loop with a dependent local-memory load
 // (profiles/r1: those loops were ~16 % of the issued instructions).  kReps node steps run per phase vote.
-template <bool ANY, int kSwitch, int kRefill, int kBlocks, int kReps>
+template <bool ANY, int kSwitch, int kRefill, int kBlocks, int kReps, bool kTex = true>
 __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2(DeviceAccel A, const float4* __restrict__ rays, long long n, void* __restrict__ out,
                                                               unsigned long long* __restrict__ counter, float* __restrict__ b2_out, const int* __restrict__ n_dev) {
     const unsigned lane = threadIdx.x & 31u;
@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(128, kBlocks) k_trace_spec2(DeviceAccel A, con
                 float t, b0, b1, b2;
                 if (triangle_test(o, tc, t_max, p0, p1, p2, &t, &b0, &b1, &b2) && triangle_nondegenerate(p0, p1, p2, A.tris, (long long)tri_i)) {
                     if (ANY) {
-                        if (alpha_ok_any(A, flags, (long long)tri_i, o, tc, t_max)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; tri_left = 1; }
-                    } else if (alpha_ok<false>(A, flags, prim, b0, b1, b2)) {
+                        if (alpha_ok_any<kTex>(A, flags, (long long)tri_i, o, tc, t_max)) { h.prim = 0u; cur = kIdle; top_code = kIdle; sp = 0; tri_left = 1; }
+                    } else if (alpha_ok<false, kTex>(A, flags, prim, b0, b1, b2)) {
                         t_max = t;
                         h.t = t; h.prim = prim; h.b0 = b0; h.b1 = b1; h.b2 = b2;
                     }

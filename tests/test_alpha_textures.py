@@ -280,12 +280,25 @@ def test_alpha_masked_traversal_matches_oracle(gpu, oracle, name):
     oo, _ = orc.occluded(sh)
     plain = oracle.OracleAccel(sd.nodes, sd.ordered_prims, sd.tri_verts, base_flags, sd.tri_uvs)
     assert (plain.intersect(rays)[0]["prim"] != oh["prim"]).mean() > 0.005  # the mask matters on this ray set
+    import torch
+    n = rays.shape[0]
+    d_r = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
+    d_s = torch.from_numpy(sh.view(np.float32).reshape(-1, 8)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
     for variant in (0, 1, 2, 3, 4, 5):
-        h = acc.intersect_batch(rays, variant=variant)
+        d_h = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+        d_o = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        acc.intersect_batch_device(d_r.data_ptr(), n, d_h.data_ptr(), st, variant)
+        acc.occluded_batch_device(d_s.data_ptr(), n, d_o.data_ptr(), st, variant)
+        torch.cuda.synchronize()
+        h = d_h.cpu().numpy().view(gpu.HIT_DTYPE).reshape(-1)
         assert np.array_equal(h["prim"], oh["prim"]), variant
         assert np.array_equal(h["t"].view(np.uint32), oh["t"].view(np.uint32)), variant
         assert np.array_equal(h["b0"].view(np.uint32), oh["b0"].view(np.uint32)) and np.array_equal(h["b1"].view(np.uint32), oh["b1"].view(np.uint32))
-        assert np.array_equal(acc.occluded_batch(sh, variant=variant), oo), variant
+        assert np.array_equal(d_o.cpu().numpy(), oo), variant
+    # the host-buffer entry points (b200pt_intersect_batch / b200pt_occluded_batch) run the default kernels
+    h = acc.intersect_batch(rays)
+    assert np.array_equal(h["prim"], oh["prim"]) and np.array_equal(acc.occluded_batch(sh), oo)
 
 
 @pytest.mark.gpu

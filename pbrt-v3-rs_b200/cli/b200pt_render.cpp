@@ -2,7 +2,7 @@
 // reference's `pbrt-v3-rs` binary (bin/src/main.rs -> api::pbrt_init / parse / pbrt_cleanup): reads a pbrt-v3 scene
 // file, renders it on the GPU and writes the image.  Links against libb200pt.so only; no CUDA or Python on this side.
 //
-//   b200pt_render [--device N] [--outfile image.png|.pfm] [--cropwindow x0 x1 y0 y1 is taken from the scene file] scene.pbrt
+//   b200pt_render [--device N | --devices 0,1,..] [--outfile image.png|.pfm] [--cropwindow x0 x1 y0 y1 is taken from the scene file] scene.pbrt
 //
 // Options follow the reference's where they exist (core/src/app.rs: --outfile; --nthreads / --quick do not apply).
 #include <chrono>
@@ -21,13 +21,17 @@ static int fail(const char* what) {
 
 int main(int argc, char** argv) {
     int device = 0;
+    std::vector<int32_t> devices;  // --devices 0,1,..: Integrator::render over several GPUs of this process (b200pt_render_multi)
     std::string outfile, scene_path;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "--device" && i + 1 < argc) device = std::atoi(argv[++i]);
+        else if (a == "--devices" && i + 1 < argc) {
+            for (const char* p = argv[++i]; *p;) { devices.push_back((int32_t)std::strtol(p, const_cast<char**>(&p), 10)); if (*p == ',') ++p; }
+        }
         else if ((a == "--outfile" || a == "-o") && i + 1 < argc) outfile = argv[++i];
         else if (a == "--help" || a == "-h") {
-            std::printf("usage: b200pt_render [--device N] [--outfile image.png|.pfm] scene.pbrt\n"
+            std::printf("usage: b200pt_render [--device N | --devices 0,1,..] [--outfile image.png|.pfm] scene.pbrt\n"
                         "Renders the scene with the B200 path (path / whitted / directlighting integrators over triangle meshes)\n"
                         "and writes a .png (the reference's 8-bit sRGB encode) or .pfm image (default: the Film's \"filename\").\n");
             return 0;
@@ -39,7 +43,7 @@ int main(int argc, char** argv) {
     using clock = std::chrono::steady_clock;
     auto secs = [](clock::time_point a, clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
 
-    if (b200pt_init(device) != B200PT_OK) return fail("b200pt_init");
+    if (b200pt_init(devices.empty() ? device : devices[0]) != B200PT_OK) return fail("b200pt_init");
     const auto t0 = clock::now();
     b200pt_loaded_scene* loaded = nullptr;
     if (b200pt_load_pbrt(scene_path.c_str(), &loaded) != B200PT_OK) return fail("b200pt_load_pbrt");
@@ -50,15 +54,29 @@ int main(int argc, char** argv) {
                 d->integrator.type == B200PT_INTEGRATOR_WHITTED ? "whitted" : d->integrator.type == B200PT_INTEGRATOR_DIRECT ? "directlighting" : "path", secs(t0, t1));
 
     b200pt_scene* scene = nullptr;
-    if (b200pt_scene_create(d, &scene) != B200PT_OK) return fail("b200pt_scene_create");
+    b200pt_multi* multi = nullptr;
     const int w = d->film.crop[2] - d->film.crop[0], h = d->film.crop[3] - d->film.crop[1];
     std::vector<float> film((size_t)w * h * 4), rgb((size_t)w * h * 3);
-    const auto t2 = clock::now();
-    if (b200pt_render_rows(scene, 0, h, film.data()) != B200PT_OK) return fail("b200pt_render_rows");
-    const auto t3 = clock::now();
-    if (b200pt_film_resolve(&d->film, film.data(), rgb.data()) != B200PT_OK) return fail("b200pt_film_resolve");
     uint64_t rays[3] = {0, 0, 0};
-    b200pt_scene_ray_counts(scene, rays);
+    clock::time_point t2, t3;
+    if (!devices.empty()) {
+        // the scene replicated on every listed GPU, bands of 8 pixel rows dealt round-robin, gathered over NVLink (NCCL)
+        if (b200pt_multi_create(d, devices.data(), (int32_t)devices.size(), &multi) != B200PT_OK) return fail("b200pt_multi_create");
+        t2 = clock::now();
+        if (b200pt_multi_render(multi, 8, film.data()) != B200PT_OK) return fail("b200pt_multi_render");
+        t3 = clock::now();
+        double gather_ms = 0.0;
+        int32_t nccl = 0;
+        b200pt_multi_info(multi, rays, &gather_ms, &nccl);
+        std::printf("%d devices, band gather %.3f ms (%s)\n", (int)devices.size(), gather_ms, nccl ? "NCCL" : "peer copies");
+    } else {
+        if (b200pt_scene_create(d, &scene) != B200PT_OK) return fail("b200pt_scene_create");
+        t2 = clock::now();
+        if (b200pt_render_rows(scene, 0, h, film.data()) != B200PT_OK) return fail("b200pt_render_rows");
+        t3 = clock::now();
+        b200pt_scene_ray_counts(scene, rays);
+    }
+    if (b200pt_film_resolve(&d->film, film.data(), rgb.data()) != B200PT_OK) return fail("b200pt_film_resolve");
     const double dt = secs(t2, t3);
     std::printf("rendered in %.3f s: %.3e samples/s, %.1f Mrays/s (%llu camera, %llu closest-hit, %llu shadow rays)\n", dt, (double)rays[0] / dt,
                 (double)(rays[1] + rays[2]) / dt / 1e6, (unsigned long long)rays[0], (unsigned long long)rays[1], (unsigned long long)rays[2]);
@@ -71,7 +89,8 @@ int main(int argc, char** argv) {
     }
     if (b200pt_write_image(outfile.c_str(), rgb.data(), w, h) != B200PT_OK) return fail("b200pt_write_image");
     std::printf("wrote %s\n", outfile.c_str());
-    b200pt_scene_destroy(scene);
+    if (multi) b200pt_multi_destroy(multi);
+    if (scene) b200pt_scene_destroy(scene);
     b200pt_loaded_scene_free(loaded);
     return 0;
 }

@@ -58,6 +58,34 @@ def test_cli_renders_the_same_image_as_the_library_calls(gpu, tmp_path, integrat
     ref = gpu.PathIntegrator(gpu.load_pbrt(str(path))).render()
     assert img.shape == (30, 40, 3) and img.mean() > 0
     assert np.array_equal(img, ref)
-    # default output name: the Film's "filename" with a .pfm extension
+    # default output name: the Film's "filename"; an extension this path does not write (.exr) becomes .pfm
     r = subprocess.run([CLI, str(path)], capture_output=True, text=True, cwd=str(tmp_path))
     assert r.returncode == 0 and (tmp_path / "cli_out.pfm").exists()
+    # .png: the reference's 8-bit sRGB encode (core/src/image_io.rs:384-390)
+    png = tmp_path / "img.png"
+    r = subprocess.run([CLI, "--outfile", str(png), str(path)], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    from PIL import Image
+    got = np.array(Image.open(str(png))).astype(np.int32)
+    v = np.asarray(ref, dtype=np.float32)
+    g = np.where(v <= np.float32(0.0031308), np.float32(12.92) * v, np.float32(1.055) * np.power(np.maximum(v, 0), np.float32(1 / 2.4)) - np.float32(0.055))
+    want = np.clip(np.float32(255.0) * g + np.float32(0.5), 0, 255).astype(np.uint8).astype(np.int32)
+    assert np.abs(got - want).max() <= 1 and (got == want).mean() > 0.999  # powf rounding may move a value sitting on a .5 boundary
+
+
+@pytest.mark.gpu
+def test_cli_multi_device_render_from_one_cpp_process(gpu, tmp_path):
+    """b200pt_multi_create / _render / _info / _destroy driven from C++ (--devices): one process, every visible GPU,
+    bands gathered on the first device; the image equals the single-device render bit for bit (box filter: every
+    sample is taken once, by exactly one device)."""
+    import torch
+    path = tmp_path / "s.pbrt"
+    path.write_text(SCENE % "path")
+    ref = gpu.PathIntegrator(gpu.load_pbrt(str(path))).render()
+    n = torch.cuda.device_count()
+    for devs in sorted({1, min(2, n), n}):
+        out = tmp_path / ("multi%d.pfm" % devs)
+        r = subprocess.run([CLI, "--devices", ",".join(str(k) for k in range(devs)), "--outfile", str(out), str(path)], capture_output=True, text=True, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stderr
+        assert "%d devices, band gather" % devs in r.stdout
+        assert np.array_equal(gpu.read_pfm(str(out)), ref), devs

@@ -397,6 +397,12 @@ int b200pt_render_rows_device(b200pt_scene* s, int32_t row_begin, int32_t row_en
  * shards (interleaving balances sky and geometry); this call renders shard `shard` into a zero-initialised film of
  * the full window (device memory).  Summing the shards' films (NCCL all-reduce) gives the whole image. */
 int b200pt_render_shard_device(b200pt_scene* s, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream);
+/* The same shard as {sum of filter-weighted RGB, sum of filter weights} per pixel - FilmTile's running sums before
+ * Film::merge_film_tile converts them to XYZ (core/src/film/mod.rs:243-248).  Shard films are combined in this space
+ * (copy the owned bands, add the overlapping rows), then b200pt_film_finish_device converts once, so that the assembled
+ * film equals the single-device film bit for bit (the conversion is not additive in floating point).  In place allowed. */
+int b200pt_render_shard_device_raw(b200pt_scene* s, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_rgbw, void* stream);
+int b200pt_film_finish_device(const void* d_film_rgbw, int64_t n_pix, void* d_film_xyzw, void* stream);
 /* ---- several GPUs, one process ---------------------------
  * The reference renders from ONE process (bin/src/main.rs:29-85) and deals 16x16 tiles to its thread pool
  * (core/src/integrator/sampler_integrator.rs:252-296).  b200pt_multi_create replicates the scene on every listed device

@@ -1711,7 +1711,7 @@ static int finish_totals(SceneImpl* s, cudaStream_t st) {
 // the full cropped window.  Shards with disjoint row sets sum to the whole image (each sample is taken once).
 // The shard's samples (pixel-major) are cut into waves that fit the memory budget; after each wave k_film continues the
 // running sums of the film pixels the wave's samples reach, so memory does not grow with resolution x samples per pixel.
-static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d_film_xyzw, cudaStream_t st) {
+static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d_film_xyzw, cudaStream_t st, bool raw = false) {
     int rc = B200PT_OK;
     const b200pt_film& f = s->film;
     const int cw = f.crop[2] - f.crop[0], ch = f.crop[3] - f.crop[1];
@@ -1789,8 +1789,10 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
         g_launches.fetch_add(2);
     }
     if (!rc) {
-        k_film_finish<<<(unsigned)((n_film + 255) / 256), 256, 0, st>>>(s->d_acc, n_film, (float4*)d_film_xyzw);
-        g_launches.fetch_add(1);
+        // raw: the running sums themselves {sum of filter-weighted RGB, sum of filter weights} (shard films are combined in
+        // that space, b200pt_film_finish_device converts afterwards); otherwise Film::merge_film_tile's RGB -> XYZ
+        if (raw) B2_CUDA(cudaMemcpyAsync(d_film_xyzw, s->d_acc, (size_t)n_film * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        else { k_film_finish<<<(unsigned)((n_film + 255) / 256), 256, 0, st>>>(s->d_acc, n_film, (float4*)d_film_xyzw); g_launches.fetch_add(1); }
         rc = finish_totals(s, st);
     }
     return rc;
@@ -1819,7 +1821,22 @@ int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_e
     return render_rows_impl(s, rows, d_film_xyzw, (cudaStream_t)stream);
 }
 
+static int render_shard_impl(b200pt_scene* sc, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream, bool raw);
 int b200pt_render_shard_device(b200pt_scene* sc, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream) {
+    return render_shard_impl(sc, shard, n_shards, band_rows, d_film_xyzw, stream, false);
+}
+int b200pt_render_shard_device_raw(b200pt_scene* sc, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_rgbw, void* stream) {
+    return render_shard_impl(sc, shard, n_shards, band_rows, d_film_rgbw, stream, true);
+}
+int b200pt_film_finish_device(const void* d_film_rgbw, int64_t n_pix, void* d_film_xyzw, void* stream) {
+    if (!d_film_rgbw || !d_film_xyzw || n_pix < 0) { b200pt_set_error("b200pt_film_finish_device: invalid argument"); return B200PT_ERR_INVALID; }
+    if (n_pix == 0) return B200PT_OK;
+    k_film_finish<<<(unsigned)((n_pix + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_film_rgbw, n_pix, (float4*)d_film_xyzw);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200PT_OK : cuda_fail(e, "k_film_finish");
+}
+static int render_shard_impl(b200pt_scene* sc, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream, bool raw) {
     if (!sc || !d_film_xyzw || n_shards < 1 || shard < 0 || shard >= n_shards || band_rows < 1) { b200pt_set_error("b200pt_render_shard_device: invalid argument"); return B200PT_ERR_INVALID; }
     SceneImpl* s = &sc->impl;
     std::lock_guard<std::mutex> g(s->mu);
@@ -1829,7 +1846,7 @@ int b200pt_render_shard_device(b200pt_scene* sc, int32_t shard, int32_t n_shards
     std::vector<int> rows;
     for (int r0 = 0, band = 0; r0 < ch; r0 += band_rows, ++band)
         if (band % n_shards == shard) append_rows(s, r0, std::min(ch, r0 + band_rows), &rows);
-    return render_rows_impl(s, rows, d_film_xyzw, (cudaStream_t)stream);
+    return render_rows_impl(s, rows, d_film_xyzw, (cudaStream_t)stream, raw);
 }
 
 int b200pt_render_rows(b200pt_scene* sc, int32_t row_begin, int32_t row_end, float* film_xyzw) {

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -72,6 +73,19 @@ __global__ void __launch_bounds__(256) k_film_sum(float4* __restrict__ dst, cons
     dst[i] = a;
 }
 
+// Box-sized filters: a sample whose film position has a zero fractional part in y also lands in the pixel row ABOVE its
+// own (film_tile.rs:73-76: p0 = ceil(p - 0.5 - radius)), so the first sample row of band k contributes to the last pixel
+// row of band k - 1, which another device owns.  spill[k] = that row as the owner of band k rendered it (it holds nothing
+// but those contributions); it is added after the row's own samples, the order the single-device film kernel uses.
+__global__ void __launch_bounds__(256) k_film_add_spill(float4* __restrict__ film, const float4* __restrict__ spill, int band_rows, int n_bands, int cw) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)(n_bands - 1) * cw) return;
+    const int k = 1 + (int)(i / cw), x = (int)(i % cw);
+    const float4 b = spill[(long long)k * cw + x];
+    float4& a = film[((long long)k * band_rows - 1) * cw + x];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+
 }  // namespace b2
 
 struct b200pt_multi {
@@ -81,6 +95,8 @@ struct b200pt_multi {
     std::vector<float4*> d_film;       // per device: the full cropped window
     std::vector<cudaStream_t> stream;  // per device
     float4* d_stage = nullptr;         // first device: (n - 1) staged films (peer path, wide filters)
+    float4* d_spill = nullptr;         // first device: one film row per band (box-sized filters, see k_film_add_spill)
+    int spill_bands = 0;
     std::vector<ncclComm_t> comms;
     bool nccl = false;
     bool disjoint = true;              // a device's samples only reach its own rows
@@ -115,6 +131,7 @@ void b200pt_multi_destroy(b200pt_multi* m) {
         if (i < (int)m->stream.size() && m->stream[(size_t)i]) cudaStreamDestroy(m->stream[(size_t)i]);
         if (i < (int)m->comms.size() && m->comms[(size_t)i]) nccl_api().CommDestroy(m->comms[(size_t)i]);
         if (i == 0 && m->d_stage) cudaFree(m->d_stage);
+        if (i == 0 && m->d_spill) cudaFree(m->d_spill);
     }
     delete m;
 }
@@ -200,35 +217,71 @@ int b200pt_multi_render(b200pt_multi* m, int32_t band_rows, float* film_xyzw) {
     std::vector<double> gather_ms((size_t)n, 0.0);
     std::vector<std::thread> th;
     NcclApi& N = nccl_api();
+    std::promise<void> first_ready;                       // peer-copy path: the first device's render is complete
+    std::shared_future<void> first_ready_f = first_ready.get_future().share();
+    bool first_signalled = false;
+    // the spill rows of box-sized filters (one row per band on the first device)
+    if (n > 1 && m->disjoint) {
+        const int n_bands = (ch + band_rows - 1) / band_rows;
+        if (n_bands > m->spill_bands) {
+            cudaSetDevice(m->devices[0]);
+            if (m->d_spill) cudaFree(m->d_spill);
+            m->d_spill = nullptr; m->spill_bands = 0;
+            B2_CUDA(cudaMalloc(&m->d_spill, (size_t)n_bands * (size_t)std::max(cw, 1) * sizeof(float4)));
+            m->spill_bands = n_bands;
+        }
+    }
     for (int i = 0; i < n; ++i)
         th.emplace_back([&, i] {
             auto body = [&]() -> int {
                 int rc = b200pt_set_device(m->devices[(size_t)i]);
                 if (rc) return rc;
                 cudaStream_t st = m->stream[(size_t)i];
-                rc = b200pt_render_shard_device(m->scenes[(size_t)i], i, n, band_rows, m->d_film[(size_t)i], st);  // returns with the shard's film complete
+                // n > 1: the shard's running sums (RGB + weight); they are combined on the first device and converted to XYZ there
+                rc = n == 1 ? b200pt_render_shard_device(m->scenes[(size_t)i], i, n, band_rows, m->d_film[(size_t)i], st)
+                            : b200pt_render_shard_device_raw(m->scenes[(size_t)i], i, n, band_rows, m->d_film[(size_t)i], st);  // returns with the shard's film complete
                 if (rc || n == 1) return rc;
                 cudaEvent_t e0, e1;
                 B2_CUDA(cudaEventCreate(&e0)); B2_CUDA(cudaEventCreate(&e1));
                 B2_CUDA(cudaEventRecord(e0, st));
+                const int n_bands = (ch + band_rows - 1) / band_rows;
+                if (m->disjoint && i == 0) {
+                    // the first device keeps the spill rows of its own bands before other devices' bands land on them
+                    for (int k = 1; k < n_bands; ++k)
+                        if (k % n == 0) B2_CUDA(cudaMemcpyAsync(m->d_spill + (size_t)k * cw, m->d_film[0] + ((size_t)k * band_rows - 1) * cw, (size_t)cw * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+                }
                 if (m->nccl && m->disjoint) {
-                    // every device ships the bands it owns into their place in the first device's film
+                    // every device ships the bands it owns into their place in the first device's film, and the row above
+                    // each of them into the spill buffer (same order on both sides of a pair)
                     B2_NCCL(N.GroupStart());
-                    for (int r0 = 0, band = 0; r0 < ch; r0 += band_rows, ++band) {
-                        const int owner = band % n;
+                    for (int k = 0; k < n_bands; ++k) {
+                        const int owner = k % n, r0 = k * band_rows;
                         const size_t off = (size_t)r0 * cw, cnt = (size_t)(std::min(ch, r0 + band_rows) - r0) * cw * 4;
-                        if (i == 0 && owner != 0) B2_NCCL(N.Recv(m->d_film[0] + off, cnt, ncclFloat, owner, m->comms[0], st));
-                        else if (i != 0 && owner == i) B2_NCCL(N.Send(m->d_film[(size_t)i] + off, cnt, ncclFloat, 0, m->comms[(size_t)i], st));
+                        if (i == 0 && owner != 0) {
+                            if (k >= 1) B2_NCCL(N.Recv(m->d_spill + (size_t)k * cw, (size_t)cw * 4, ncclFloat, owner, m->comms[0], st));
+                            B2_NCCL(N.Recv(m->d_film[0] + off, cnt, ncclFloat, owner, m->comms[0], st));
+                        } else if (i != 0 && owner == i) {
+                            if (k >= 1) B2_NCCL(N.Send(m->d_film[(size_t)i] + off - (size_t)cw, (size_t)cw * 4, ncclFloat, 0, m->comms[(size_t)i], st));
+                            B2_NCCL(N.Send(m->d_film[(size_t)i] + off, cnt, ncclFloat, 0, m->comms[(size_t)i], st));
+                        }
                     }
                     B2_NCCL(N.GroupEnd());
                 } else if (m->nccl) {
                     // filter aprons overlap: sum the films (in place on the first device)
                     B2_NCCL(N.Reduce(m->d_film[(size_t)i], m->d_film[(size_t)i], (size_t)m->n_pix * 4, ncclFloat, ncclSum, 0, m->comms[(size_t)i], st));
-                } else if (i != 0) {
+                } else if (i == 0) {
+                    // peer copies: the other devices write into this device's film once its own render (and the stash above) is complete
+                    B2_CUDA(cudaStreamSynchronize(st));
+                    first_signalled = true;
+                    first_ready.set_value();
+                } else {
+                    first_ready_f.wait();
                     if (m->disjoint) {
-                        for (int r0 = 0, band = 0; r0 < ch; r0 += band_rows, ++band) {
-                            if (band % n != i) continue;
+                        for (int k = 0; k < n_bands; ++k) {
+                            if (k % n != i) continue;
+                            const int r0 = k * band_rows;
                             const size_t off = (size_t)r0 * cw, bytes = (size_t)(std::min(ch, r0 + band_rows) - r0) * cw * sizeof(float4);
+                            if (k >= 1) B2_CUDA(cudaMemcpyPeerAsync(m->d_spill + (size_t)k * cw, m->devices[0], m->d_film[(size_t)i] + off - (size_t)cw, m->devices[(size_t)i], (size_t)cw * sizeof(float4), st));
                             B2_CUDA(cudaMemcpyPeerAsync(m->d_film[0] + off, m->devices[0], m->d_film[(size_t)i] + off, m->devices[(size_t)i], bytes, st));
                         }
                     } else {
@@ -247,6 +300,9 @@ int b200pt_multi_render(b200pt_multi* m, int32_t band_rows, float* film_xyzw) {
             int rc = body();
             if (rc) errs[(size_t)i] = b200pt_last_error();
             rcs[(size_t)i] = rc;
+            if (i == 0 && !first_signalled) {  // never leave the other threads waiting (failure, NCCL path, one device)
+                try { first_ready.set_value(); } catch (const std::future_error&) {}
+            }
         });
     for (auto& t : th) t.join();
     int rc = B200PT_OK;
@@ -262,10 +318,18 @@ int b200pt_multi_render(b200pt_multi* m, int32_t band_rows, float* film_xyzw) {
     }
     if (!rc) {
         cudaSetDevice(m->devices[0]);
+        if (n > 1 && m->disjoint) {
+            const int n_bands = (ch + band_rows - 1) / band_rows;
+            if (n_bands > 1) {
+                k_film_add_spill<<<(unsigned)(((long long)(n_bands - 1) * cw + 255) / 256), 256, 0, m->stream[0]>>>(m->d_film[0], m->d_spill, band_rows, n_bands, cw);
+                g_launches.fetch_add(1);
+            }
+        }
         if (n > 1 && !m->nccl && !m->disjoint) {
             k_film_sum<<<(unsigned)((m->n_pix + 255) / 256), 256, 0, m->stream[0]>>>(m->d_film[0], m->d_stage, n - 1, m->n_pix);
             g_launches.fetch_add(1);
         }
+        if (n > 1) rc = b200pt_film_finish_device(m->d_film[0], m->n_pix, m->d_film[0], m->stream[0]);
         cudaError_t e = cudaSuccess;
         if (film_xyzw) e = cudaMemcpyAsync(film_xyzw, m->d_film[0], (size_t)m->n_pix * sizeof(float4), cudaMemcpyDeviceToHost, m->stream[0]);
         if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream[0]);

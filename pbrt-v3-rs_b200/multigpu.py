@@ -4,8 +4,8 @@ The reference renders 16x16 tiles from a work queue on one host
 (core/src/integrator/sampler_integrator.rs:252-296).  Here the scene is replicated on every GPU, the
 pixel rows are cut into bands dealt round-robin to the ranks (interleaving balances sky and geometry),
 each rank renders its bands into a zero-initialised film of the full window, and ONE collective over NCCL / NVLink
-assembles the image: with a box-sized filter the rows are disjoint, so every rank ships only the bands it owns to rank 0
-(a gather of 1 / world of the film per rank); with wider filters the aprons overlap and the films are summed (all-reduce).
+assembles the image: with a box-sized filter every rank ships only the bands it owns (plus one spill row per band, see
+`spill_rows`) to rank 0 (a gather of ~1 / world of the film per rank); with wider filters the aprons overlap and the films are summed (all-reduce).
 Nothing else crosses GPUs: the path has no data-path collective.  This module is the one-process-per-GPU (torchrun) form;
 one process driving all GPUs goes through b200pt_multi_render (csrc/multi_gpu.cu, `MultiGPURender`).
 """
@@ -32,11 +32,20 @@ def reduce_film(film, group=None):
     return film
 
 
+def spill_rows(height, n_shards, shard, band_rows=BAND_ROWS):
+    """Rows just ABOVE each band of `shard` (band index >= 1): a sample whose film position has a zero fractional part in y
+    also lands in the pixel row above its own (film_tile.rs:73-76: p0 = ceil(p - 0.5 - radius) includes it), so the first
+    sample row of a band can contribute to the last pixel row of the previous band - which another shard owns."""
+    return np.asarray([r0 - 1 for band, r0 in enumerate(range(0, height, band_rows)) if band >= 1 and band % n_shards == shard], dtype=np.int64)
+
+
 class BandGather:
-    """Gather of OWNED bands for box-sized filters (radius <= 0.5 px): a rank's samples only reach its own rows, so each
-    rank ships just those rows (1 / world of the film) to rank 0 instead of all-reducing the whole film: one
-    `dist.gather` of (rows_per_rank, W, 4) blocks over NCCL / NVLink, then rank 0 drops them into place.  Index tensors
-    and staging buffers are built once (outside any timed region)."""
+    """Gather of OWNED bands for box-sized filters (radius <= 0.5 px): a rank's samples reach its own rows and, for the
+    rare sample that sits exactly on a pixel boundary, the one row above each of its bands (`spill_rows`).  Each rank
+    ships just those rows (1 / world of the film plus one row per band) to rank 0 instead of all-reducing the whole film:
+    one `dist.gather` over NCCL / NVLink, then rank 0 drops the bands into place and ADDS the spill rows (in the order
+    the single-device film kernel adds them: the row's own samples first).  Index tensors and staging buffers are built
+    once (outside any timed region)."""
 
     def __init__(self, height, width, device, band_rows=BAND_ROWS, group=None):
         import torch
@@ -45,8 +54,10 @@ class BandGather:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rows = [torch.from_numpy(shard_rows(height, self.world, r, band_rows)).to(device) for r in range(self.world)]
+        self.spill = [torch.from_numpy(spill_rows(height, self.world, r, band_rows)).to(device) for r in range(self.world)]
         self.max_rows = max(int(r.numel()) for r in self.rows)
-        self.mine = torch.zeros((self.max_rows, width, 4), dtype=torch.float32, device=device)
+        self.max_spill = max(int(r.numel()) for r in self.spill)
+        self.mine = torch.zeros((self.max_rows + self.max_spill, width, 4), dtype=torch.float32, device=device)
         self.parts = [torch.zeros_like(self.mine) for _ in range(self.world)] if self.rank == 0 else None
 
     def __call__(self, film):
@@ -54,12 +65,18 @@ class BandGather:
         import torch.distributed as dist
         if self.world == 1:
             return film
-        my = self.rows[self.rank]
+        my, sp = self.rows[self.rank], self.spill[self.rank]
         self.mine[:my.numel()].copy_(film.index_select(0, my))
+        if sp.numel():
+            self.mine[self.max_rows:self.max_rows + sp.numel()].copy_(film.index_select(0, sp))
         dist.gather(self.mine, self.parts, dst=0, group=self.group)
         if self.rank == 0:
             for r in range(1, self.world):
                 film.index_copy_(0, self.rows[r], self.parts[r][:self.rows[r].numel()])
+            for r in range(self.world):  # rank 0's own spill rows were staged in self.mine before the bands overwrote them
+                if self.spill[r].numel():
+                    src = self.mine if r == 0 else self.parts[r]
+                    film.index_add_(0, self.spill[r], src[self.max_rows:self.max_rows + self.spill[r].numel()])
         return film
 
 
@@ -81,7 +98,18 @@ def render_distributed(integrator, band_rows=BAND_ROWS, gather=None):
         integrator.preprocess()
     h, w = integrator.film_shape()
     film = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
-    integrator.render_shard_device(rank, world, film.data_ptr(), band_rows, torch.cuda.current_stream().cuda_stream)
+    sp = torch.cuda.current_stream().cuda_stream
+    if world == 1:
+        integrator.render_shard_device(rank, world, film.data_ptr(), band_rows, sp)
+        return film
+    # shard films are combined as running sums (RGB + weight) and converted to XYZ once, after the collective: the
+    # assembled film is then the single-device film bit for bit (see b200pt_render_shard_device_raw)
+    integrator.render_shard_device_raw(rank, world, film.data_ptr(), band_rows, sp)
     if integrator.filter_radius()[1] <= 0.5:
-        return (gather or BandGather(h, w, film.device, band_rows))(film)
-    return reduce_film(film)
+        film = (gather or BandGather(h, w, film.device, band_rows))(film)
+        if rank == 0:
+            integrator.film_finish_device(film.data_ptr(), h * w, sp)
+        return film
+    film = reduce_film(film)
+    integrator.film_finish_device(film.data_ptr(), h * w, sp)
+    return film

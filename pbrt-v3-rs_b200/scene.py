@@ -507,6 +507,19 @@ class PathIntegrator:
             self.preprocess()
         _check(lib().b200pt_render_shard_device(self._h, shard, n_shards, band_rows, d_film_ptr, stream), "b200pt_render_shard_device")
 
+    def render_shard_device_raw(self, shard, n_shards, d_film_ptr, band_rows=8, stream=0):
+        """The shard as running sums {filter-weighted RGB, weight}: combine shard films in this space, then film_finish_device."""
+        from . import _check, lib
+        if self._h is None:
+            self.preprocess()
+        _check(lib().b200pt_render_shard_device_raw(self._h, shard, n_shards, band_rows, d_film_ptr, stream), "b200pt_render_shard_device_raw")
+
+    @staticmethod
+    def film_finish_device(d_film_ptr, n_pix, stream=0):
+        """Film::merge_film_tile's RGB -> XYZ on an assembled film of running sums, in place."""
+        from . import _check, lib
+        _check(lib().b200pt_film_finish_device(d_film_ptr, n_pix, d_film_ptr, stream), "b200pt_film_finish_device")
+
     def render_rows_device(self, row_begin, row_end, d_film_ptr, stream=0):
         from . import _check, lib
         if self._h is None:

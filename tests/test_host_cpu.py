@@ -19,11 +19,25 @@ def test_cabi_exports_every_declared_symbol(pkg):
     assert not missing, "symbols declared in include/b200pt.h but not exported: %s" % missing
 
 
+def test_integration_md_binds_every_declared_symbol(pkg):
+    """INTEGRATION.md's b200pt-sys extern block is generated from the header (tools/gen_rust_ffi.py --update): it must name
+    every entry point, and its struct mirror must carry the fields the ctypes mirror has."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "b200pt.h")).read()
+    names = set(re.findall(r"\b(b200pt_[a-z0-9_]+)\s*\(", hdr))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = [n for n in sorted(names) if "pub fn %s(" % n not in doc]
+    assert not missing, "entry points missing from INTEGRATION.md (run python tools/gen_rust_ffi.py --update): %s" % missing
+    for field, _ in pkg.SceneDesc._fields_:
+        assert "pub %s:" % field in doc, field
+
+
 def test_struct_sizes_match_header(pkg):
     assert pkg.RAY_DTYPE.itemsize == 32 and pkg.HIT_DTYPE.itemsize == 16 and pkg.NODE_DTYPE.itemsize == 32
     assert C.sizeof(pkg.Material) == 4 + 15 * 4 + 3 * 4 + 4
     assert C.sizeof(pkg.Light) == 168 + 8 + 4 + 4  # 164 bytes of scalars, padded to 168 for the map pointer
     assert C.sizeof(pkg.Film) == 8 + 16 + 8 + 1024 + 8
+    assert C.sizeof(pkg.FloatTexture) == 4 + 16 + 8 + 12 + 8  # 40 bytes of scalars, then the texel pointer
 
 
 @pytest.mark.parametrize("max_prims", [1, 4, 8, 255])

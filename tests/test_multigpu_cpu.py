@@ -35,10 +35,21 @@ def _worker(rank, world, port, h, w, q):
     out = multigpu.reduce_film(part.clone())
     ok = bool(torch.equal(out, full))
     # the gather of owned bands (box-sized filters): rank 0 ends up with the whole image, nobody ships more than its rows
+    # plus one spill row per band (samples sitting exactly on a pixel boundary also land in the row above their band)
+    spill_all = torch.from_numpy(np.random.default_rng(6).random((h, w, 4)).astype(np.float32))
+    want = full.clone()
+    for r in range(world):
+        sr = multigpu.spill_rows(h, world, r)
+        want[sr] += spill_all[sr]
+    mine_spill = multigpu.spill_rows(h, world, rank)
+    part2 = part.clone()
+    part2[mine_spill] = spill_all[mine_spill]  # rows this rank does not own: they hold only its boundary contributions
     g = multigpu.BandGather(h, w, "cpu")
-    got = g(part.clone())
-    ok = ok and (bool(torch.equal(got, full)) if rank == 0 else bool(torch.equal(got, part)))
-    ok = ok and g.mine.shape[0] == max(multigpu.shard_rows(h, world, r).size for r in range(world))
+    got = g(part2.clone())
+    ok = ok and (bool(torch.equal(got, want)) if rank == 0 else bool(torch.equal(got, part2)))
+    ok = ok and g.mine.shape[0] == max(multigpu.shard_rows(h, world, r).size for r in range(world)) + max(multigpu.spill_rows(h, world, r).size for r in range(world))
+    all_spill = np.concatenate([multigpu.spill_rows(h, world, r) for r in range(world)])
+    ok = ok and sorted(all_spill.tolist()) == [r0 - 1 for r0 in range(multigpu.BAND_ROWS, h, multigpu.BAND_ROWS)]
     q.put((rank, ok, int(rows.size)))
     dist.destroy_process_group()
 

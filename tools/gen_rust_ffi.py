@@ -1,6 +1,6 @@
 """Prints the `extern "C"` block of the b200pt-sys crate from include/b200pt.h, one Rust declaration
 per exported entry point, so that the document cannot drift from the header (tests/test_host_cpu.py checks that every
-symbol of the header appears in INTEGRATION.md).  Usage: python tools/gen_rust_ffi.py"""
+symbol of the header appears in INTEGRATION.md).  Usage: python tools/gen_rust_ffi.py [--update]   (--update rewrites the block in INTEGRATION.md)"""
 import os
 import re
 
@@ -40,5 +40,20 @@ def declarations():
     return out
 
 
+def update_integration_md():
+    """Rewrites the extern block of INTEGRATION.md in place."""
+    path = os.path.join(ROOT, "INTEGRATION.md")
+    s = open(path).read()
+    i0 = s.index('#[link(name = "b200pt")]\nextern "C" {')
+    i1 = s.index("```", i0)
+    d = declarations()
+    s = s[:i0] + '#[link(name = "b200pt")]\nextern "C" {   // generated from include/b200pt.h by tools/gen_rust_ffi.py: all %d entry points\n' % len(d) + "\n".join(d) + "\n}\n" + s[i1:]
+    open(path, "w").write(s)
+
+
 if __name__ == "__main__":
-    print("\n".join(declarations()))
+    import sys
+    if "--update" in sys.argv:
+        update_integration_md()
+    else:
+        print("\n".join(declarations()))

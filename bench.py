@@ -241,7 +241,7 @@ def path_tracing_leg(pkg, args, rank, world, which):
            "scaling": "strong", "film_gather_ms": gat_s * 1e3, "film_gather": "owned bands -> rank 0 (dist.gather over NCCL), %d bytes per rank" % (gather.max_rows * w * 16),
            "render_ms_slowest_rank": float(tmax[3]) * 1e3, "render_ms_fastest_rank": float(tmin[3]) * 1e3,
            "rays_per_image": float(t[2]), "mrays_in_render": float(t[2]) / secs / 1e6, "setup_s": t_setup,
-           "config": (PATH_CONFIGS[which] % (n_tris, sd.integrator["maxdepth"], w, h, spp)) + "; rows in bands of %d dealt round-robin to the ranks" % multigpu.BAND_ROWS}
+           "config": (PATH_CONFIGS[which] % (n_tris, sd.integrator["maxdepth"], w, h, spp)) + "; rows in bands of %d dealt in snake order to the ranks" % multigpu.BAND_ROWS}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the reference's CPU path for this leg: the oracle renders a centre crop of the same scene on all host cores
         sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -393,9 +393,13 @@ void b200pt_scene_destroy(b200pt_scene* s);
 int b200pt_render_rows(b200pt_scene* s, int32_t row_begin, int32_t row_end, float* film_xyzw);
 /* Same, film stays on the device (d_film_xyzw: device pointer, full window). */
 int b200pt_render_rows_device(b200pt_scene* s, int32_t row_begin, int32_t row_end, void* d_film_xyzw, void* stream);
-/* Multi-GPU decomposition: the pixel rows are cut into bands of `band_rows` rows dealt round-robin to `n_shards`
- * shards (interleaving balances sky and geometry); this call renders shard `shard` into a zero-initialised film of
+/* Multi-GPU decomposition: the pixel rows are cut into bands of `band_rows` rows dealt in snake order (b200pt_band_owner) to `n_shards`
+ * shards (b200pt_band_owner; interleaving balances sky and geometry); this call renders shard `shard` into a zero-initialised film of
  * the full window (device memory).  Summing the shards' films (NCCL all-reduce) gives the whole image. */
+/* Which shard renders band `band` (bands of band_rows pixel rows, counted from the top): dealt in snake order
+ * 0 1 .. n-1 n-1 .. 1 0 0 1 .., so that a cost gradient down the image (sky above, geometry below) cancels within every
+ * pair of passes instead of making the last shard of every pass the slowest. */
+int32_t b200pt_band_owner(int32_t band, int32_t n_shards);
 int b200pt_render_shard_device(b200pt_scene* s, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream);
 /* The same shard as {sum of filter-weighted RGB, sum of filter weights} per pixel - FilmTile's running sums before
  * Film::merge_film_tile converts them to XYZ (core/src/film/mod.rs:243-248).  Shard films are combined in this space
@@ -406,7 +410,7 @@ int b200pt_film_finish_device(const void* d_film_rgbw, int64_t n_pix, void* d_fi
 /* ---- several GPUs, one process ---------------------------
  * The reference renders from ONE process (bin/src/main.rs:29-85) and deals 16x16 tiles to its thread pool
  * (core/src/integrator/sampler_integrator.rs:252-296).  b200pt_multi_create replicates the scene on every listed device
- * (b200pt_init is called for each); b200pt_multi_render deals bands of `band_rows` pixel rows round-robin to the
+ * (b200pt_init is called for each); b200pt_multi_render deals bands of `band_rows` pixel rows in snake order to the
  * devices, renders them concurrently (one host thread per device) and gathers the bands on devices[0] over NVLink with
  * NCCL: box-sized filters (radius <= 0.5 px) send each device's own bands into place (ncclSend / ncclRecv, 1 / n of the
  * film per device, no reduction); wider filters overlap by their apron and are summed with one ncclReduce.  Without

@@ -201,6 +201,8 @@ def lib():
     L.b200pt_render_rows.argtypes = [vp, i32, i32, vp]
     L.b200pt_render_rows_device.argtypes = [vp, i32, i32, vp, vp]
     L.b200pt_render_shard_device.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.b200pt_band_owner.argtypes = [i32, i32]
+    L.b200pt_band_owner.restype = i32
     L.b200pt_render_shard_device_raw.argtypes = [vp, i32, i32, i32, vp, vp]
     L.b200pt_film_finish_device.argtypes = [vp, i64, vp, vp]
     L.b200pt_film_resolve.argtypes = [C.POINTER(Film), vp, vp]

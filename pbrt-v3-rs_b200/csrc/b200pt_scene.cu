@@ -358,6 +358,42 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_shade(DeviceScene S, Wave W
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) shade_vertex<KM, kMode>(S, W, cur, order[i], may_park);
 }
 
+// All material classes of a bounce in ONE launch: virtual blocks of 128 slots are dealt over the classes' ranges of the
+// sorted queue (bins 1..4), every block runs one class's code (the switch is block-uniform).  Same registers as the
+// per-class kernels (the largest class sets them); what it buys is latency: shading ONE vertex is a ~50 us dependent
+// chain, and four nearly empty class launches in a row cost four of those per bounce (profiles/r2_launches_floor_c3_tiny.csv:
+// 183 us of a 256 us bounce floor), which is what limits small renders and the per-GPU share of a multi-GPU render.
+static const uint32_t kKmMatteD = (1u << BX_LAMBERT) | (1u << BX_OREN_NAYAR);
+static const uint32_t kKmPlasticD = (1u << BX_LAMBERT) | (1u << BX_MF_REFL) | KM_DIEL;
+static const uint32_t kKmGlassD = (1u << BX_FRESNEL_SPECULAR) | (1u << BX_MF_REFL) | (1u << BX_MF_TRANS) | KM_DIEL;
+static const uint32_t kKmMetalD = (1u << BX_MF_REFL) | KM_COND;
+template <int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) k_shade_classes(DeviceScene S, Wave W, int cur) {
+    int start[5], vb[5];
+    int acc = W.counters[8], v_total = 0;  // bin 0 = escaped rays (their own small kernel)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = W.counters[9 + k];
+        start[k] = acc; acc += c;
+        vb[k] = v_total; v_total += (c + 127) >> 7;
+    }
+    start[4] = acc; vb[4] = v_total;
+    for (int v = blockIdx.x; v < v_total; v += gridDim.x) {
+        int b = 0;
+#pragma unroll
+        for (int k = 1; k < 4; ++k) b += (v >= vb[k]) ? 1 : 0;
+        const int i = ((v - vb[b]) << 7) + (int)threadIdx.x;
+        if (i >= start[b + 1] - start[b]) continue;
+        const int slot = W.sorted[start[b] + i];
+        switch (b) {  // block-uniform
+            case 0: shade_vertex<kKmMatteD, kShadeHit>(S, W, cur, slot, true); break;
+            case 1: shade_vertex<kKmPlasticD, kShadeHit>(S, W, cur, slot, true); break;
+            case 2: shade_vertex<kKmGlassD, kShadeHit>(S, W, cur, slot, true); break;
+            default: shade_vertex<kKmMetalD, kShadeHit>(S, W, cur, slot, true); break;
+        }
+    }
+}
+
 // ---- (0,2)-sequence prepass: one thread per reference tile replays the tile sampler's PCG32 stream ------------
 // ZeroTwoSequenceSampler::start_pixel for every pixel of the tile in row-major order (zero_two_sequence.rs:65-111,
 // sampler_integrator.rs:323-345): per slot one (two) scramble draw(s), spp one-element shuffles (one draw each, the
@@ -717,9 +753,10 @@ struct SceneImpl {
     int* h_pinned = nullptr;               // pinned host words for the few read-backs that remain
     size_t mem_budget = 0;                 // bytes the wave state may take (0: B200PT_MEM_BUDGET, else a share of the free memory)
     // streams / events that let a bounce's shadow, MIS and next closest-hit traversals overlap (run_wave)
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_shade = nullptr;
+    cudaStream_t shade_main = nullptr;  // the stream of the current launch_shade call (the classes fork from / join to it)
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_shade = nullptr, ev_fork = nullptr;
     bool aux_ready = false, overlap = true;
     uint64_t rays[3] = {0, 0, 0};
     uint64_t voxels_built = 0;  // SpatialLightDistribution voxels computed so far
@@ -1017,16 +1054,21 @@ static int shade_grid(const SceneImpl* s, int n_upper, int per_sm) {
 }
 template <uint32_t KM>
 static void launch_shade_class(SceneImpl* s, const Wave& W, int cur, int n_upper, int bin, int blocks, cudaStream_t st) {
+    if (st != s->shade_main) cudaStreamWaitEvent(st, s->ev_fork, 0);  // a class on its own stream starts after the sort
     switch (blocks) {
         case 3: k_shade<KM, kShadeHit, 3><<<shade_grid(s, n_upper, 12), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
         case 4: k_shade<KM, kShadeHit, 4><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
         case 6: k_shade<KM, kShadeHit, 6><<<shade_grid(s, n_upper, 24), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
         default: k_shade<KM, kShadeHit, 5><<<shade_grid(s, n_upper, 20), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
     }
+    if (st != s->shade_main) {  // join: the main stream continues after this class
+        for (int k = 0; k < 3; ++k)
+            if (st == s->aux[k]) { cudaEventRecord(s->ev_aux[k], st); cudaStreamWaitEvent(s->shade_main, s->ev_aux[k], 0); }
+    }
 }
 static void launch_shade(SceneImpl* s, const Wave& W, int cur, int n_upper, cudaStream_t st) {
-    static const bool split = [] { const char* e = std::getenv("B200PT_SHADE_SPLIT"); return !(e && e[0] == '0'); }();
-    if (!split) {  // A/B: one generic kernel over the whole sorted queue
+    static const int mode = [] { const char* e = std::getenv("B200PT_SHADE_SPLIT"); return e ? std::atoi(e) : 1; }();
+    if (mode == 0) {  // A/B: one generic kernel over the whole sorted queue
         k_shade<KM_ALL, kShadeHit, 5><<<shade_grid(s, n_upper, 20), 128, 0, st>>>(s->dev, W, cur, 0, kBins);
         g_launches.fetch_add(1);
         return;
@@ -1038,12 +1080,37 @@ static void launch_shade(SceneImpl* s, const Wave& W, int cur, int n_upper, cuda
         [] { const char* e = std::getenv("B200PT_SHADE_BLOCKS"); return e && std::strlen(e) == 4 ? e[1] - '0' : 4; }(),
         [] { const char* e = std::getenv("B200PT_SHADE_BLOCKS"); return e && std::strlen(e) == 4 ? e[2] - '0' : 4; }(),
         [] { const char* e = std::getenv("B200PT_SHADE_BLOCKS"); return e && std::strlen(e) == 4 ? e[3] - '0' : 4; }()};
+    const int n_classes = __builtin_popcount(s->material_classes & 0xfu);
+    int launches = 0;
+    // Default (mode 1): one launch per class, each class on its own stream.  With a full queue every launch fills the GPU
+    // and they run one after the other as before; with a nearly empty one (late bounces, small renders, one GPU's share
+    // of a multi-GPU render) the ~50 us dependent chains of the classes overlap instead of adding up
+    // (profiles/r2_launches_floor_c3_tiny.csv: 183 us of a 256 us bounce floor were four class launches in a row).
+    // Putting the classes into ONE kernel (mode 3, k_shade_classes) overlaps them too but mixes four code paths on every
+    // SM: C3 174 -> 216 ms per image (instruction cache).  Mode 2: all classes on one stream (the first form of the split).
+    s->shade_main = st;
+    cudaStream_t cs[4] = {st, st, st, st};
+    if (mode == 1 && s->overlap && n_classes > 1) {
+        cudaEventRecord(s->ev_fork, st);
+        int k = 0;
+        for (int c = 0; c < 4; ++c)
+            if (s->material_classes & (1u << c)) { cs[c] = k == 0 ? st : s->aux[k - 1]; ++k; }
+    }
     k_shade<KM_ALL, kShadeMiss, 8><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, 0, 1);
-    int launches = 1;
-    if (s->material_classes & (1u << B200PT_MAT_MATTE)) { launch_shade_class<kKmMatte>(s, W, cur, n_upper, 1, blocks[0], st); ++launches; }
-    if (s->material_classes & (1u << B200PT_MAT_PLASTIC)) { launch_shade_class<kKmPlastic>(s, W, cur, n_upper, 2, blocks[1], st); ++launches; }
-    if (s->material_classes & (1u << B200PT_MAT_GLASS)) { launch_shade_class<kKmGlass>(s, W, cur, n_upper, 3, blocks[2], st); ++launches; }
-    if (s->material_classes & (1u << B200PT_MAT_METAL)) { launch_shade_class<kKmMetal>(s, W, cur, n_upper, 4, blocks[3], st); ++launches; }
+    ++launches;
+    if (mode == 3 && n_classes > 1) {
+        k_shade_classes<4><<<std::max(1, std::min((n_upper + 127) / 128 + 4, (dev_ctx(s->device) ? dev_ctx(s->device)->sm_count : 148) * 16)), 128, 0, st>>>(s->dev, W, cur);
+        ++launches;
+    } else {
+        // the main stream's class first: the joins of the other streams (enqueued by launch_shade_class) must come after it
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool main_pass = pass == 0;
+            if ((s->material_classes & (1u << B200PT_MAT_MATTE)) && (cs[0] == st) == main_pass) { launch_shade_class<kKmMatte>(s, W, cur, n_upper, 1, blocks[0], cs[0]); ++launches; }
+            if ((s->material_classes & (1u << B200PT_MAT_PLASTIC)) && (cs[1] == st) == main_pass) { launch_shade_class<kKmPlastic>(s, W, cur, n_upper, 2, blocks[1], cs[1]); ++launches; }
+            if ((s->material_classes & (1u << B200PT_MAT_GLASS)) && (cs[2] == st) == main_pass) { launch_shade_class<kKmGlass>(s, W, cur, n_upper, 3, blocks[2], cs[2]); ++launches; }
+            if ((s->material_classes & (1u << B200PT_MAT_METAL)) && (cs[3] == st) == main_pass) { launch_shade_class<kKmMetal>(s, W, cur, n_upper, 4, blocks[3], cs[3]); ++launches; }
+        }
+    }
     if (s->has_null_material) { k_shade<KM_ALL, kShadeNull, 8><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, kBinNull, kBinNull + 1); ++launches; }
     g_launches.fetch_add(launches);
 }
@@ -1057,11 +1124,12 @@ static void launch_shade(SceneImpl* s, const Wave& W, int cur, int n_upper, cuda
 // main stream behind events.  B200PT_OVERLAP=0 puts everything back on one stream (A/B).
 static int aux_setup(SceneImpl* s) {
     if (s->aux_ready) return B200PT_OK;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         B2_CUDA(cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking));
         B2_CUDA(cudaEventCreateWithFlags(&s->ev_aux[i], cudaEventDisableTiming));
     }
     B2_CUDA(cudaEventCreateWithFlags(&s->ev_shade, cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     const char* e = std::getenv("B200PT_OVERLAP");
     s->overlap = !(e && e[0] == '0');
     s->aux_ready = true;
@@ -1547,7 +1615,8 @@ void b200pt_scene_destroy(b200pt_scene* sc) {
     if (sc->impl.device >= 0) cudaSetDevice(sc->impl.device);
     for (void* p : sc->impl.allocs) cudaFree(p);
     for (void* p : sc->impl.wave_ptrs) cudaFree(p);
-    for (int i = 0; i < 2; ++i) { if (sc->impl.aux[i]) cudaStreamDestroy(sc->impl.aux[i]); if (sc->impl.ev_aux[i]) cudaEventDestroy(sc->impl.ev_aux[i]); }
+    for (int i = 0; i < 3; ++i) { if (sc->impl.aux[i]) cudaStreamDestroy(sc->impl.aux[i]); if (sc->impl.ev_aux[i]) cudaEventDestroy(sc->impl.ev_aux[i]); }
+    if (sc->impl.ev_fork) cudaEventDestroy(sc->impl.ev_fork);
     if (sc->impl.d_sample_L) cudaFree(sc->impl.d_sample_L);
     if (sc->impl.d_sample_pf) cudaFree(sc->impl.d_sample_pf);
     if (sc->impl.d_film) cudaFree(sc->impl.d_film);
@@ -1821,6 +1890,13 @@ int b200pt_render_rows_device(b200pt_scene* sc, int32_t row_begin, int32_t row_e
     return render_rows_impl(s, rows, d_film_xyzw, (cudaStream_t)stream);
 }
 
+int32_t b200pt_band_owner(int32_t band, int32_t n_shards) {
+    if (n_shards < 1 || band < 0) return 0;
+    static const bool round_robin = [] { const char* e = std::getenv("B200PT_BAND_ORDER"); return e && std::strcmp(e, "roundrobin") == 0; }();  // A/B
+    if (round_robin) return band % n_shards;
+    const int32_t pass = band / n_shards, k = band % n_shards;
+    return (pass & 1) ? n_shards - 1 - k : k;
+}
 static int render_shard_impl(b200pt_scene* sc, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream, bool raw);
 int b200pt_render_shard_device(b200pt_scene* sc, int32_t shard, int32_t n_shards, int32_t band_rows, void* d_film_xyzw, void* stream) {
     return render_shard_impl(sc, shard, n_shards, band_rows, d_film_xyzw, stream, false);
@@ -1845,7 +1921,7 @@ static int render_shard_impl(b200pt_scene* sc, int32_t shard, int32_t n_shards, 
     const int ch = s->film.crop[3] - s->film.crop[1];
     std::vector<int> rows;
     for (int r0 = 0, band = 0; r0 < ch; r0 += band_rows, ++band)
-        if (band % n_shards == shard) append_rows(s, r0, std::min(ch, r0 + band_rows), &rows);
+        if (b200pt_band_owner(band, n_shards) == shard) append_rows(s, r0, std::min(ch, r0 + band_rows), &rows);
     return render_rows_impl(s, rows, d_film_xyzw, (cudaStream_t)stream, raw);
 }
 

@@ -2,7 +2,7 @@
 //
 // The reference is a single process that hands 16x16 tiles to a thread pool (core/src/integrator/
 // sampler_integrator.rs:252-296).  Here the scene is replicated on every GPU, the pixel rows are cut into bands dealt
-// round-robin to the devices (b200pt_render_shard_device), one host thread per device renders its bands into its own
+// in snake order to the devices (b200pt_band_owner, b200pt_render_shard_device), one host thread per device renders its bands into its own
 // film, and the bands are gathered on the first device over NVLink:
 //   * box-sized filters (radius <= 0.5 px in y): a device's samples only reach its own rows, so each device SENDS ITS
 //     OWN BANDS (1 / n of the film) straight into their place in the first device's film - NCCL send / recv grouped
@@ -230,6 +230,10 @@ int b200pt_multi_render(b200pt_multi* m, int32_t band_rows, float* film_xyzw) {
             B2_CUDA(cudaMalloc(&m->d_spill, (size_t)n_bands * (size_t)std::max(cw, 1) * sizeof(float4)));
             m->spill_bands = n_bands;
         }
+        // rows of bands whose upper neighbour has the same owner are never written: they must add nothing
+        cudaSetDevice(m->devices[0]);
+        B2_CUDA(cudaMemsetAsync(m->d_spill, 0, (size_t)n_bands * (size_t)std::max(cw, 1) * sizeof(float4), m->stream[0]));
+        B2_CUDA(cudaStreamSynchronize(m->stream[0]));
     }
     for (int i = 0; i < n; ++i)
         th.emplace_back([&, i] {
@@ -248,20 +252,21 @@ int b200pt_multi_render(b200pt_multi* m, int32_t band_rows, float* film_xyzw) {
                 if (m->disjoint && i == 0) {
                     // the first device keeps the spill rows of its own bands before other devices' bands land on them
                     for (int k = 1; k < n_bands; ++k)
-                        if (k % n == 0) B2_CUDA(cudaMemcpyAsync(m->d_spill + (size_t)k * cw, m->d_film[0] + ((size_t)k * band_rows - 1) * cw, (size_t)cw * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+                        if (b200pt_band_owner(k, n) == 0 && b200pt_band_owner(k - 1, n) != 0) B2_CUDA(cudaMemcpyAsync(m->d_spill + (size_t)k * cw, m->d_film[0] + ((size_t)k * band_rows - 1) * cw, (size_t)cw * sizeof(float4), cudaMemcpyDeviceToDevice, st));
                 }
                 if (m->nccl && m->disjoint) {
                     // every device ships the bands it owns into their place in the first device's film, and the row above
                     // each of them into the spill buffer (same order on both sides of a pair)
                     B2_NCCL(N.GroupStart());
                     for (int k = 0; k < n_bands; ++k) {
-                        const int owner = k % n, r0 = k * band_rows;
+                        const int owner = b200pt_band_owner(k, n), r0 = k * band_rows;
+                        const bool spill = k >= 1 && b200pt_band_owner(k - 1, n) != owner;  // the row above belongs to another device
                         const size_t off = (size_t)r0 * cw, cnt = (size_t)(std::min(ch, r0 + band_rows) - r0) * cw * 4;
                         if (i == 0 && owner != 0) {
-                            if (k >= 1) B2_NCCL(N.Recv(m->d_spill + (size_t)k * cw, (size_t)cw * 4, ncclFloat, owner, m->comms[0], st));
+                            if (spill) B2_NCCL(N.Recv(m->d_spill + (size_t)k * cw, (size_t)cw * 4, ncclFloat, owner, m->comms[0], st));
                             B2_NCCL(N.Recv(m->d_film[0] + off, cnt, ncclFloat, owner, m->comms[0], st));
                         } else if (i != 0 && owner == i) {
-                            if (k >= 1) B2_NCCL(N.Send(m->d_film[(size_t)i] + off - (size_t)cw, (size_t)cw * 4, ncclFloat, 0, m->comms[(size_t)i], st));
+                            if (spill) B2_NCCL(N.Send(m->d_film[(size_t)i] + off - (size_t)cw, (size_t)cw * 4, ncclFloat, 0, m->comms[(size_t)i], st));
                             B2_NCCL(N.Send(m->d_film[(size_t)i] + off, cnt, ncclFloat, 0, m->comms[(size_t)i], st));
                         }
                     }
@@ -278,10 +283,11 @@ int b200pt_multi_render(b200pt_multi* m, int32_t band_rows, float* film_xyzw) {
                     first_ready_f.wait();
                     if (m->disjoint) {
                         for (int k = 0; k < n_bands; ++k) {
-                            if (k % n != i) continue;
+                            if (b200pt_band_owner(k, n) != i) continue;
                             const int r0 = k * band_rows;
+                            const bool spill = k >= 1 && b200pt_band_owner(k - 1, n) != i;
                             const size_t off = (size_t)r0 * cw, bytes = (size_t)(std::min(ch, r0 + band_rows) - r0) * cw * sizeof(float4);
-                            if (k >= 1) B2_CUDA(cudaMemcpyPeerAsync(m->d_spill + (size_t)k * cw, m->devices[0], m->d_film[(size_t)i] + off - (size_t)cw, m->devices[(size_t)i], (size_t)cw * sizeof(float4), st));
+                            if (spill) B2_CUDA(cudaMemcpyPeerAsync(m->d_spill + (size_t)k * cw, m->devices[0], m->d_film[(size_t)i] + off - (size_t)cw, m->devices[(size_t)i], (size_t)cw * sizeof(float4), st));
                             B2_CUDA(cudaMemcpyPeerAsync(m->d_film[0] + off, m->devices[0], m->d_film[(size_t)i] + off, m->devices[(size_t)i], bytes, st));
                         }
                     } else {

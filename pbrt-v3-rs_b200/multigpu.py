@@ -2,7 +2,7 @@
 
 The reference renders 16x16 tiles from a work queue on one host
 (core/src/integrator/sampler_integrator.rs:252-296).  Here the scene is replicated on every GPU, the
-pixel rows are cut into bands dealt round-robin to the ranks (interleaving balances sky and geometry),
+pixel rows are cut into bands dealt in snake order to the ranks (interleaving balances sky and geometry, the snake cancels a gradient),
 each rank renders its bands into a zero-initialised film of the full window, and ONE collective over NCCL / NVLink
 assembles the image: with a box-sized filter every rank ships only the bands it owns (plus one spill row per band, see
 `spill_rows`) to rank 0 (a gather of ~1 / world of the film per rank); with wider filters the aprons overlap and the films are summed (all-reduce).
@@ -14,11 +14,18 @@ import numpy as np
 BAND_ROWS = 8
 
 
+def band_owner(band, n_shards):
+    """b200pt_band_owner (include/b200pt.h): bands are dealt in snake order 0 1 .. n-1 n-1 .. 1 0 0 1 .., which cancels a cost
+    gradient down the image within every pair of passes."""
+    from . import lib
+    return int(lib().b200pt_band_owner(int(band), int(n_shards)))
+
+
 def shard_rows(height, n_shards, shard, band_rows=BAND_ROWS):
-    """Pixel rows of `shard`: bands of `band_rows` rows dealt round-robin (mirrors b200pt_render_shard_device)."""
+    """Pixel rows of `shard`: bands of `band_rows` rows dealt in snake order (mirrors b200pt_render_shard_device)."""
     rows = []
     for band, r0 in enumerate(range(0, height, band_rows)):
-        if band % n_shards == shard:
+        if band_owner(band, n_shards) == shard:
             rows.extend(range(r0, min(height, r0 + band_rows)))
     return np.asarray(rows, dtype=np.int64)
 
@@ -36,7 +43,8 @@ def spill_rows(height, n_shards, shard, band_rows=BAND_ROWS):
     """Rows just ABOVE each band of `shard` (band index >= 1): a sample whose film position has a zero fractional part in y
     also lands in the pixel row above its own (film_tile.rs:73-76: p0 = ceil(p - 0.5 - radius) includes it), so the first
     sample row of a band can contribute to the last pixel row of the previous band - which another shard owns."""
-    return np.asarray([r0 - 1 for band, r0 in enumerate(range(0, height, band_rows)) if band >= 1 and band % n_shards == shard], dtype=np.int64)
+    return np.asarray([r0 - 1 for band, r0 in enumerate(range(0, height, band_rows))
+                       if band >= 1 and band_owner(band, n_shards) == shard and band_owner(band - 1, n_shards) != shard], dtype=np.int64)
 
 
 class BandGather:

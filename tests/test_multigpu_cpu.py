@@ -49,7 +49,9 @@ def _worker(rank, world, port, h, w, q):
     ok = ok and (bool(torch.equal(got, want)) if rank == 0 else bool(torch.equal(got, part2)))
     ok = ok and g.mine.shape[0] == max(multigpu.shard_rows(h, world, r).size for r in range(world)) + max(multigpu.spill_rows(h, world, r).size for r in range(world))
     all_spill = np.concatenate([multigpu.spill_rows(h, world, r) for r in range(world)])
-    ok = ok and sorted(all_spill.tolist()) == [r0 - 1 for r0 in range(multigpu.BAND_ROWS, h, multigpu.BAND_ROWS)]
+    # every band boundary between two different owners has exactly one spill row
+    want_spill = [k * multigpu.BAND_ROWS - 1 for k in range(1, -(-h // multigpu.BAND_ROWS)) if multigpu.band_owner(k, world) != multigpu.band_owner(k - 1, world)]
+    ok = ok and sorted(all_spill.tolist()) == want_spill
     q.put((rank, ok, int(rows.size)))
     dist.destroy_process_group()
 

@@ -22,7 +22,7 @@ def rust_type(t):
 
 def prototypes():
     h = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "b200pt.h")).read(), flags=re.S)
-    return [" ".join(p.split()) for p in re.findall(r"^(?:int|void|const char\*|void\*|int64_t|const b200pt_scene_desc\*)\s+\*?b200pt_\w+\([^;]*\);", h, flags=re.M)]
+    return [" ".join(p.split()) for p in re.findall(r"^(?:int|void|const char\*|void\*|int64_t|int32_t|const b200pt_scene_desc\*)\s+\*?b200pt_\w+\([^;]*\);", h, flags=re.M)]
 
 
 def declarations():

@@ -43,7 +43,7 @@ def test_li_per_sample_matches_oracle(gpu, oracle, name, light):
     assert np.isfinite(li).all()
     close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
     # an ulp of difference in a sampled direction can flip which triangle a later bounce hits: allow a few paths
-    assert close.mean() >= 0.97, "only %.4f of the paths agree" % close.mean()
+    assert close.mean() >= 0.999, "only %.4f of the paths agree" % close.mean()
     assert abs(li.mean() - oli.mean()) <= 0.02 * max(oli.mean(), 1e-3)
 
 
@@ -61,7 +61,7 @@ def test_image_rel_rmse(gpu, oracle, name, light, strategy, filt):
     assert r <= TOL, "relative RMSE %.3e > %.0e" % (r, TOL)
     rc = integ.ray_counts()
     assert rc[0] == stats[0]  # same number of camera rays
-    assert abs(int(rc[1]) - int(stats[1])) <= 0.01 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0.01 * stats[2]
+    assert abs(int(rc[1]) - int(stats[1])) <= 0 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0 * stats[2]
 
 
 def test_c1_config_small_and_row_shards(gpu, oracle):
@@ -147,7 +147,7 @@ def test_zerotwo_default_dimensions_tile_sequential(gpu, oracle, name, light, sp
     assert rays.tobytes() == osc.camera_rays(ps).tobytes()
     oli = osc.li(ps)
     close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
-    assert close.mean() >= 0.97, close.mean()
+    assert close.mean() >= 0.999, close.mean()
     img = integ.render()
     ref, stats, _ = osc.render()
     assert ss.rel_rmse(img, ref) <= TOL
@@ -175,7 +175,7 @@ def test_zerotwo_sampler_matches_oracle(gpu, oracle, name, light, spp):
     assert rays.tobytes() == osc.camera_rays(ps).tobytes()
     oli = osc.li(ps)
     close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
-    assert close.mean() >= 0.97
+    assert close.mean() >= 0.999
     img = integ.render()
     ref, stats, _ = osc.render()
     assert ss.rel_rmse(img, ref) <= TOL
@@ -219,12 +219,12 @@ def test_instancing_two_level_bvh_matches_oracle(gpu, oracle, name):
     assert rays.tobytes() == osc.camera_rays(ps).tobytes()
     oli = osc.li(ps)
     close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
-    assert close.mean() >= 0.97, close.mean()
+    assert close.mean() >= 0.999, close.mean()
     img = integ.render()
     ref, stats, _ = osc.render()
     assert ss.rel_rmse(img, ref) <= TOL
     rc = integ.ray_counts()
-    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0.01 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0.01 * stats[2]
+    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0 * stats[2]
 
 
 def test_instancing_point_light_only_is_bit_exact(gpu, oracle):
@@ -327,12 +327,12 @@ def test_image_mapped_infinite_light_matches_oracle(gpu, oracle, name, size, ext
     oli = osc.li(ps)
     assert rays.tobytes() == osc.camera_rays(ps).tobytes()
     close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
-    assert close.mean() >= 0.97, close.mean()
+    assert close.mean() >= 0.999, close.mean()
     img = integ.render()
     ref, stats, _ = osc.render()
     assert np.isfinite(img).all() and ss.rel_rmse(img, ref) <= TOL
     rc = integ.ray_counts()
-    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0.01 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0.01 * stats[2]
+    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0 * stats[2]
     # the map matters: the same scene lit by the constant light is a different image
     sd.lights[0].pop("image")
     assert ss.rel_rmse(gpu.PathIntegrator(sd).render(), img) > 10 * TOL
@@ -406,13 +406,13 @@ def test_area_light_on_a_mesh_with_vertex_normals(gpu, oracle, integrator, inwar
     li, _ = integ.li(ps)
     oli = osc.li(ps)
     close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
-    assert close.mean() >= 0.97, close.mean()
+    assert close.mean() >= 0.999, close.mean()
     img = integ.render()
     ref, stats, _ = osc.render()
     assert ss.rel_rmse(img, ref) <= TOL
     assert (img.mean() > 0.01) == (twosided or not inward)  # inward-facing normals: the sphere emits into itself only
     rc = integ.ray_counts()
-    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0.01 * stats[1]
+    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0 * stats[1]
 
 
 @pytest.mark.parametrize("filt,integrator", [("box", "path"), ("gaussian", "path"), ("box", "whitted")])

@@ -73,7 +73,7 @@ def test_spatial_gpu_li_matches_oracle(gpu, oracle, name):
     li, _ = integ.li(ps)
     oli = oracle.OracleScene(sd).li(ps)
     close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
-    assert close.mean() >= 0.97, close.mean()
+    assert close.mean() >= 0.999, close.mean()
     li2, _ = integ.li(ps)  # second call: every voxel is already in the table
     assert np.array_equal(li, li2)
 
@@ -90,7 +90,7 @@ def test_spatial_gpu_image_rel_rmse(gpu, oracle, name, filt):
     r = ss.rel_rmse(img, ref)
     assert r <= 1e-3, r
     rc = integ.ray_counts()
-    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0.01 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0.01 * stats[2]
+    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0 * stats[2]
 
 
 @pytest.mark.gpu

@@ -52,8 +52,8 @@ def test_whitted_image_rel_rmse_and_ray_counts(gpu, oracle, name, light, filt, m
     assert r <= TOL, "relative RMSE %.3e > %.0e" % (r, TOL)
     rc = integ.ray_counts()
     assert rc[0] == stats[0]
-    assert abs(int(rc[1]) - int(stats[1])) <= 0.002 * stats[1]  # closest-hit rays: the whole specular trees
-    assert abs(int(rc[2]) - int(stats[2])) <= 0.002 * max(int(stats[2]), 1)  # shadow rays (placeholder slots are not counted)
+    assert abs(int(rc[1]) - int(stats[1])) <= 0 * stats[1]  # closest-hit rays: the whole specular trees
+    assert abs(int(rc[2]) - int(stats[2])) <= 0  # shadow rays (placeholder slots are not counted)
 
 
 def _many_lights_scene(wl, n_strips, maxdepth):
@@ -92,7 +92,7 @@ def test_whitted_many_lights_and_instances(gpu, oracle):
     img = integ.render()
     ref, stats, _ = oracle.OracleScene(sd).render()
     assert ss.rel_rmse(img, ref) <= TOL
-    assert integ.ray_counts()[0] == stats[0] and abs(int(integ.ray_counts()[1]) - int(stats[1])) <= 0.002 * stats[1]
+    assert integ.ray_counts()[0] == stats[0] and abs(int(integ.ray_counts()[1]) - int(stats[1])) <= 0 * stats[1]
 
 
 def test_whitted_too_many_dimensions_fails_like_the_reference(gpu):
@@ -163,7 +163,7 @@ def test_directlighting_li_per_sample_matches_oracle(gpu, oracle, name, light, s
     assert np.isfinite(li).all()
     close = np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1)
     # the MIS half samples directions with sin / cos: an ulp there can flip which triangle the MIS ray hits
-    assert close.mean() >= 0.97, "only %.4f of the samples agree" % close.mean()
+    assert close.mean() >= 0.999, "only %.4f of the samples agree" % close.mean()
     assert abs(li.mean() - oli.mean()) <= 0.02 * max(oli.mean(), 1e-3)
 
 
@@ -179,7 +179,7 @@ def test_directlighting_image_rel_rmse_and_ray_counts(gpu, oracle, name, light, 
     assert r <= TOL, "relative RMSE %.3e > %.0e" % (r, TOL)
     rc = integ.ray_counts()
     assert rc[0] == stats[0]
-    assert abs(int(rc[1]) - int(stats[1])) <= 0.005 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0.005 * max(int(stats[2]), 1)
+    assert abs(int(rc[1]) - int(stats[1])) <= 0 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0
 
 
 def test_directlighting_scene_file(gpu, oracle, tmp_path):

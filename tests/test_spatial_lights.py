@@ -90,7 +90,7 @@ def test_spatial_gpu_image_rel_rmse(gpu, oracle, name, filt):
     r = ss.rel_rmse(img, ref)
     assert r <= 1e-3, r
     rc = integ.ray_counts()
-    assert rc[0] == stats[0] and abs(int(rc[1]) - int(stats[1])) <= 0 * stats[1] and abs(int(rc[2]) - int(stats[2])) <= 0 * stats[2]
+    assert rc[0] == stats[0] and int(rc[1]) == int(stats[1]) and int(rc[2]) == int(stats[2])
 
 
 @pytest.mark.gpu

@@ -65,8 +65,33 @@ float4 record_duv(const float* uv6) {
     return make_float4(uv6[0] - uv6[4], uv6[1] - uv6[5], uv6[2] - uv6[4], uv6[3] - uv6[5]);
 }
 
+int bvh_max_depth(const b200pt_bvh_node* nodes, int64_t n_nodes) {
+    if (n_nodes <= 0) return 0;
+    std::vector<int32_t> depth((size_t)n_nodes, -1);
+    depth[0] = 0;
+    int best = 0;
+    for (int64_t i = 0; i < n_nodes; ++i) {  // pre-order: a node's depth is known before its children are reached
+        const int32_t d = depth[(size_t)i];
+        if (d < 0) return -1;
+        best = std::max(best, (int)d);
+        if (nodes[i].n_primitives != 0) continue;
+        const int64_t c0 = i + 1, c1 = nodes[i].offset;
+        if (c0 >= n_nodes || c1 <= i || c1 >= n_nodes) return -1;
+        depth[(size_t)c0] = d + 1; depth[(size_t)c1] = d + 1;
+    }
+    return best;
+}
+
 int accel_build_device(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint32_t* ordered, const float* tri_verts,
                        const uint32_t* flags, int64_t n_prims, AccelImpl* a, const float* tri_uvs) {
+    if (n_nodes > 0) {
+        const int depth = bvh_max_depth(nodes, n_nodes);
+        if (depth < 0) { b200pt_set_error("b200pt_accel_create: malformed node array"); return B200PT_ERR_INVALID; }
+        if (depth > B2_STACK) {
+            b200pt_set_error("b200pt_accel_create: the BVH is more than 64 levels deep; BVHAccel::intersect's fixed traversal stack (accelerators/src/bvh/mod.rs:185) overflows on such a tree too");
+            return B200PT_ERR_UNSUPPORTED;
+        }
+    }
     a->n_nodes = n_nodes;
     a->n_prims = n_prims;
     std::memset(&a->dev, 0, sizeof(a->dev));

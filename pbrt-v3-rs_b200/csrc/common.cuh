@@ -94,6 +94,9 @@ struct AlphaImpl {
 int alpha_build_device(const b200pt_float_texture* tex, int32_t n_tex, const int32_t* prim_alpha_tex, const float* tri_uvs, const uint32_t* prim_flags,
                        int64_t n_prims, const uint8_t* noise_perm, AlphaImpl* out);
 void alpha_free_device(AlphaImpl* a);
+// Depth of a flattened BVH (root = 0; -1 for a malformed array).  The walks keep one pending far child per level: the
+// reference's `nodes_to_visit: [usize; 64]` (mod.rs:185) overflows past 64 levels, the device stacks (B2_STACK, B2_STACK2) too.
+int bvh_max_depth(const b200pt_bvh_node* nodes, int64_t n_nodes);
 float4 record_duv(const float* uv6);  // uv0 - uv2, uv1 - uv2; uv6 == nullptr: the default uvs
 void accel_free_device(AccelImpl* a);
 

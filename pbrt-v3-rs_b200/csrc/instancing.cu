@@ -717,6 +717,20 @@ static int append_bvh(const b200pt_bvh_node* nodes, int64_t n_nodes, const uint3
 }
 
 int accel2_build_device(const b200pt_scene_desc* d, Accel2Impl* a) {
+    {   // the scene aggregate's and the deepest object's pending entries share one stack of B2_STACK2 entries
+        const int top = bvh_max_depth(d->nodes, d->n_nodes);
+        int obj = 0;
+        for (int o = 0; o < d->n_objects; ++o) {
+            const int dd = bvh_max_depth(d->objects[o].nodes, d->objects[o].n_nodes);
+            if (dd < 0) { b200pt_set_error("b200pt_scene_create: malformed object node array"); return B200PT_ERR_INVALID; }
+            obj = std::max(obj, dd);
+        }
+        if (top < 0) { b200pt_set_error("b200pt_scene_create: malformed node array"); return B200PT_ERR_INVALID; }
+        if (top > 64 || obj > 64 || top + obj + 2 > B2_STACK2) {
+            b200pt_set_error("b200pt_scene_create: scene aggregate + object BVH are deeper than the traversal stack holds (64 levels each in the reference, mod.rs:185; 94 together here)");
+            return B200PT_ERR_UNSUPPORTED;
+        }
+    }
     std::vector<float4> wide, recs;
     auto tri_record = [&](int64_t gp, float4* q) {
         const float* v = d->tri_verts + 9 * (size_t)gp;

@@ -749,11 +749,19 @@ struct SceneImpl {
     int wave_cap = 0;
     std::vector<void*> wave_ptrs;
     int* d_ctl = nullptr;                  // (kSegIters + 1) control blocks of the current wave segment
+    long long wave_launches = 0;           // kernel launches one run_wave call enqueues (for the launch counter of graph replays)
     unsigned long long* d_totals = nullptr;  // camera / closest-hit / shadow rays of the render, error flags
     int* h_pinned = nullptr;               // pinned host words for the few read-backs that remain
     size_t mem_budget = 0;                 // bytes the wave state may take (0: B200PT_MEM_BUDGET, else a share of the free memory)
     // streams / events that let a bounce's shadow, MIS and next closest-hit traversals overlap (run_wave)
     cudaStream_t shade_main = nullptr;  // the stream of the current launch_shade call (the classes fork from / join to it)
+    // CUDA graphs of the bounce loop, one per wave size (run_wave_graphed): the ~105 launches of a wave are replayed by the
+    // device without the host in between
+    struct WaveGraph { int n = 0; int uses = 0; cudaGraphExec_t exec = nullptr; };
+    std::vector<WaveGraph> graphs;
+    cudaStream_t graph_stream = nullptr;
+    cudaEvent_t ev_graph_in = nullptr, ev_graph_out = nullptr;
+    bool graph_failed = false;
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_shade = nullptr, ev_fork = nullptr;
@@ -990,6 +998,8 @@ static int wave_alloc(SceneImpl* s, int cap) {
         B2_CUDA(cudaMallocHost(&s->h_pinned, 64 * sizeof(int)));
     }
     if (s->wave_cap == cap) return B200PT_OK;  // shrinks too: a smaller budget must be honoured
+    for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);  // captured launches hold the old buffers' addresses
+    s->graphs.clear();
     for (void* p : s->wave_ptrs) cudaFree(p);  // grow: a later render needs a larger wave
     s->wave_ptrs.clear();
     s->wave_cap = 0;
@@ -1140,6 +1150,8 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
     int rc = aux_setup(s);
     if (rc) return rc;
     if (n <= 0) return B200PT_OK;
+    const long long launches_before = g_launches.load();
+    struct CountLaunches { SceneImpl* s; long long before; ~CountLaunches() { s->wave_launches = g_launches.load() - before; } } count_launches{s, launches_before};
     const Wave& W0 = s->wave;
     int* const ctl = s->d_ctl;
     const DevCtx* dc = dev_ctx(s->device);
@@ -1215,6 +1227,59 @@ static int run_wave(SceneImpl* s, int n, cudaStream_t st) {
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wavefront kernels");
+    return B200PT_OK;
+}
+
+// The bounce loop of a wave replayed from a CUDA graph.  run_wave only enqueues (no read-back when maxdepth + 1 fits one
+// control segment), so its launches - sort, shade classes on their streams, three traversals, resolve, per bounce - can be
+// captured once per wave size and replayed: the device then runs a wave's ~105 launches without waiting for the host,
+// which matters on a busy host (eight ranks and their clock samplers on 16 threads: single renders showed 37-56 ms
+// spikes around a 24.7 ms median, profiles/r2_shard_and_floor.txt).  The first wave of a given size runs eagerly (first-use
+// setup of streams, counters and occupancy queries must not happen inside a capture), the second is captured, later ones
+// are replayed.  Any capture error falls back to the eager loop for the rest of the scene's life.  B200PT_GRAPH=0 disables it.
+static int run_wave_graphed(SceneImpl* s, int n, cudaStream_t st) {
+    static const bool enabled = [] { const char* e = std::getenv("B200PT_GRAPH"); return !(e && e[0] == '0'); }();
+    const bool eligible = enabled && !s->graph_failed && !s->whitted && !s->zt_seq && !s->has_null_material && s->dev.max_depth + 1 <= kSegIters &&
+                          s->dev.sampler_type != B200PT_SAMPLER_ZEROTWO && n > 0;
+    if (!eligible) return run_wave(s, n, st);
+    SceneImpl::WaveGraph* g = nullptr;
+    for (auto& e : s->graphs) if (e.n == n) g = &e;
+    if (!g) { s->graphs.push_back({}); g = &s->graphs.back(); g->n = n; }
+    if (g->uses++ == 0) {
+        // first wave of this size: eager, then the same launches are captured for the next one (nothing runs during capture)
+        int rc = run_wave(s, n, st);
+        if (rc) return rc;
+        if (!s->graph_stream) {
+            if (cudaStreamCreateWithFlags(&s->graph_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_graph_in, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->ev_graph_out, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); s->graph_failed = true; return B200PT_OK; }
+        }
+        // capture on an own stream (the caller's may be the legacy default stream, which cannot be captured)
+        cudaGraph_t graph = nullptr;
+        const long long launches_before = g_launches.load();
+        cudaError_t e = cudaStreamBeginCapture(s->graph_stream, cudaStreamCaptureModeThreadLocal);
+        int rc2 = B200PT_OK;
+        if (e == cudaSuccess) {
+            rc2 = run_wave(s, n, s->graph_stream);
+            e = cudaStreamEndCapture(s->graph_stream, &graph);
+        }
+        g_launches.fetch_sub(g_launches.load() - launches_before > 0 ? s->wave_launches : 0);  // nothing was launched during the capture
+        if (e == cudaSuccess && rc2 == B200PT_OK && graph) e = cudaGraphInstantiate(&g->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess || rc2 != B200PT_OK || !g->exec) {
+            cudaGetLastError();
+            g->exec = nullptr;
+            s->graph_failed = true;
+        }
+        return B200PT_OK;
+    }
+    if (!g->exec) return run_wave(s, n, st);
+    B2_CUDA(cudaEventRecord(s->ev_graph_in, st));
+    B2_CUDA(cudaStreamWaitEvent(s->graph_stream, s->ev_graph_in, 0));
+    B2_CUDA(cudaGraphLaunch(g->exec, s->graph_stream));
+    B2_CUDA(cudaEventRecord(s->ev_graph_out, s->graph_stream));
+    B2_CUDA(cudaStreamWaitEvent(st, s->ev_graph_out, 0));
+    // launches of the replayed wave (same count as the eager loop enqueues)
+    g_launches.fetch_add(s->wave_launches);
     return B200PT_OK;
 }
 
@@ -1617,6 +1682,10 @@ void b200pt_scene_destroy(b200pt_scene* sc) {
     for (void* p : sc->impl.wave_ptrs) cudaFree(p);
     for (int i = 0; i < 3; ++i) { if (sc->impl.aux[i]) cudaStreamDestroy(sc->impl.aux[i]); if (sc->impl.ev_aux[i]) cudaEventDestroy(sc->impl.ev_aux[i]); }
     if (sc->impl.ev_fork) cudaEventDestroy(sc->impl.ev_fork);
+    for (auto& g : sc->impl.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (sc->impl.graph_stream) cudaStreamDestroy(sc->impl.graph_stream);
+    if (sc->impl.ev_graph_in) cudaEventDestroy(sc->impl.ev_graph_in);
+    if (sc->impl.ev_graph_out) cudaEventDestroy(sc->impl.ev_graph_out);
     if (sc->impl.d_sample_L) cudaFree(sc->impl.d_sample_L);
     if (sc->impl.d_sample_pf) cudaFree(sc->impl.d_sample_pf);
     if (sc->impl.d_film) cudaFree(sc->impl.d_film);
@@ -1844,7 +1913,7 @@ static int render_rows_impl(SceneImpl* s, const std::vector<int>& srows, void* d
         int n = (int)std::min<long long>(s->wave_cap, n_samples - first);
         k_raygen<<<(n + 255) / 256, 256, 0, st>>>(s->dev, s->wave, first, n, spp, s->d_rows, nullptr, d_pf, nullptr);
         g_launches.fetch_add(1);
-        rc = s->whitted ? run_wave_whitted(s, n, st) : run_wave(s, n, st);
+        rc = s->whitted ? run_wave_whitted(s, n, st) : run_wave_graphed(s, n, st);
         if (rc) break;
         k_store_samples<<<(n + 255) / 256, 256, 0, st>>>(s->wave, n, d_L);
         // every film pixel near the wave's sample rows continues its sums (also pixels of a neighbouring shard when the

@@ -209,25 +209,33 @@ def path_tracing_leg(pkg, args, rank, world, which):
     gather = multigpu.BandGather(h, w, film.device, multigpu.BAND_ROWS)
     sp = torch.cuda.current_stream().cuda_stream
     times, gat = [], []
+    stream = torch.cuda.current_stream()
     for it in range(1 + args.path_iters):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        # timed on the device (CUDA events on the launching stream): render + band gather (+ the XYZ conversion on rank 0)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
         if world == 1:
             integ.render_shard_device(rank, world, film.data_ptr(), multigpu.BAND_ROWS, sp)  # zeroes the film itself
         else:
             integ.render_shard_device_raw(rank, world, film.data_ptr(), multigpu.BAND_ROWS, sp)  # running sums; XYZ after the gather
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
+        e1.record(stream)
         gather(film)
         if world > 1 and rank == 0:
             integ.film_finish_device(film.data_ptr(), h * w, sp)
+        e2.record(stream)
         torch.cuda.synchronize()
-        t2 = time.perf_counter()
-        if it:  # first iteration is the warm-up
-            times.append(t2 - t0)
-            gat.append(t2 - t1)
+        if it:  # first iteration is the warm-up (it also captures the CUDA graph of the bounce loop)
+            times.append(e0.elapsed_time(e2) * 1e-3)
+            gat.append(e1.elapsed_time(e2) * 1e-3)
+    # These shared hosts are busy (N ranks + clock samplers on 16 threads): a render whose host thread is descheduled
+    # between two enqueues leaves the GPU idle for tens of ms once in ~10 runs.  The figure is the MEDIAN of the timed
+    # iterations; every sample is in `samples_ms`.
+    samples_ms = [t * 1e3 for t in times]
+    k_med = int(np.argsort(times)[len(times) // 2])
+    times, gat = [times[k_med]], [gat[k_med]]
     rc = integ.ray_counts()
     t = torch.tensor([float(np.mean(times)), float(np.mean(gat)), float(rc[1] + rc[2]), float(np.mean(times)) - float(np.mean(gat))], dtype=torch.float64, device="cuda")
     tmax, tmin = t.clone(), t.clone()
@@ -237,7 +245,8 @@ def path_tracing_leg(pkg, args, rank, world, which):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     secs, gat_s = float(tmax[0]), float(tmax[1])
     n_tris = int(sd.tri_verts.shape[0])
-    out = {"metric": "path samples/s", "value": h * w * spp / secs, "unit": "samples/s", "ms_per_image": secs * 1e3, "n_gpus": world,
+    out = {"metric": "path samples/s", "value": h * w * spp / secs, "unit": "samples/s", "ms_per_image": secs * 1e3, "stat": "median of %d device-timed iterations (max over ranks)" % args.path_iters,
+           "samples_ms": samples_ms, "n_gpus": world,
            "scaling": "strong", "film_gather_ms": gat_s * 1e3, "film_gather": "owned bands -> rank 0 (dist.gather over NCCL), %d bytes per rank" % (gather.max_rows * w * 16),
            "render_ms_slowest_rank": float(tmax[3]) * 1e3, "render_ms_fastest_rank": float(tmin[3]) * 1e3,
            "rays_per_image": float(t[2]), "mrays_in_render": float(t[2]) / secs / 1e6, "setup_s": t_setup,
@@ -352,7 +361,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-path", action="store_true", help="skip the path-tracing (samples/s) leg")
-    ap.add_argument("--path-iters", type=int, default=3)
+    ap.add_argument("--path-iters", type=int, default=5)
     ap.add_argument("--no-c4-rays", action="store_true", help="skip the HBM-resident C4-rays roofline line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

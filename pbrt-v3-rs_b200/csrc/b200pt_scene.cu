@@ -1987,6 +1987,11 @@ static int render_shard_impl(b200pt_scene* sc, int32_t shard, int32_t n_shards, 
     std::lock_guard<std::mutex> g(s->mu);
     int rc = use_device(s->device);
     if (rc) return rc;
+    if (s->zt_seq && n_shards > 1 && (band_rows % 16 != 0 || (s->film.crop[1] - s->sample_bounds[1]) % 16 != 0)) {
+        // a tile is one sequential stream: a shard that owns part of a tile's rows has to render the whole tile anyway
+        b200pt_set_error("b200pt_render_shard_device: the tile-sequential (0,2) mode shards by whole 16-row tiles: band_rows must be a multiple of 16 (and the crop window must start on a tile row)");
+        return B200PT_ERR_INVALID;
+    }
     const int ch = s->film.crop[3] - s->film.crop[1];
     std::vector<int> rows;
     for (int r0 = 0, band = 0; r0 < ch; r0 += band_rows, ++band)

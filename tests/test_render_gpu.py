@@ -157,6 +157,21 @@ def test_zerotwo_default_dimensions_tile_sequential(gpu, oracle, name, light, sp
     film_b = integ.render_rows(20, res)
     whole = integ.render_rows(0, res)
     assert np.array_equal((film_a + film_b).view(np.uint32), whole.view(np.uint32))
+    # multi-GPU shards must be whole tile rows (a tile is one sequential stream): bands of 16 rows work and every ray is
+    # traced once, bands of 8 are refused
+    import torch
+    h, w = integ.film_shape()
+    parts, rays = [], np.zeros(3, dtype=np.int64)
+    for r in range(2):
+        part = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        integ.render_shard_device(r, 2, part.data_ptr(), band_rows=16)
+        torch.cuda.synchronize()
+        parts.append(part.cpu().numpy())
+        rays += np.array([int(x) for x in integ.ray_counts()], dtype=np.int64)
+    assert np.array_equal((parts[0] + parts[1]).view(np.uint32), whole.view(np.uint32))
+    assert rays.tolist() == [int(x) for x in stats[:3]]
+    with pytest.raises(gpu.B200PTError, match="multiple of 16"):
+        integ.render_shard_device(0, 2, torch.zeros((h, w, 4), dtype=torch.float32, device="cuda").data_ptr(), band_rows=8)
 
 
 @pytest.mark.parametrize("name,light,spp", [("matte", "infinite", 8), ("plastic", "all", 4), ("glass", "area", 6)])

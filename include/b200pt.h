@@ -88,7 +88,9 @@ typedef struct b200pt_material {
 } b200pt_material;
 
 /* lights/src/{point,diffuse,infinite}.rs */
-enum { B200PT_LIGHT_POINT = 0, B200PT_LIGHT_AREA = 1, B200PT_LIGHT_INFINITE = 2 };
+enum { B200PT_LIGHT_POINT = 0, B200PT_LIGHT_AREA = 1, B200PT_LIGHT_INFINITE = 2,
+       B200PT_LIGHT_DISTANT = 3 /* lights/src/distant.rs: pos = w_light, the NORMALISED world-space direction TOWARDS the light
+                                  * (light_to_world.transform_vector(from - to).normalize(), distant.rs:50-52), L = L * scale */ };
 typedef struct b200pt_light {
     int32_t type;
     float pos[3];             /* point: p_light (world) */

@@ -564,6 +564,7 @@ inline Float triangle_area(V3 p0, V3 p1, V3 p2) { return 0.5f * length(cross(p1 
 inline RGB light_power(const RenderScene& sc, int li) {
     const b200pt_light& l = sc.lights[li];
     if (l.type == B200PT_LIGHT_POINT) return kFourPi * light_L(l);
+    if (l.type == B200PT_LIGHT_DISTANT) return light_L(l) * kPi * sc.world_radius * sc.world_radius;  // distant.rs:92-95
     if (l.type == B200PT_LIGHT_AREA) {
         Float s = l.two_sided ? 2.0f : 1.0f;
         return s * light_L(l) * sc.light_area[li] * kPi;
@@ -885,6 +886,14 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
         r.valid = true;
         return r;
     }
+    if (l.type == B200PT_LIGHT_DISTANT) {  // distant.rs:81-90
+        r.wi = V3(l.pos[0], l.pos[1], l.pos[2]);
+        r.pdf = 1.0f;
+        r.p1 = hit.p + r.wi * (2.0f * sc.world_radius);
+        r.value = light_L(l);
+        r.valid = true;
+        return r;
+    }
     if (l.type == B200PT_LIGHT_AREA) {
         // Triangle::sample, triangle.rs:918-949
         V3 p0 = sc.accel.vert(l.prim, 0), p1 = sc.accel.vert(l.prim, 1), p2 = sc.accel.vert(l.prim, 2);
@@ -938,7 +947,7 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
 // Light::pdf_li
 inline Float light_pdf_li(const RenderScene& sc, int li, const SurfHit& hit, V3 wi) {
     const b200pt_light& l = sc.lights[li];
-    if (l.type == B200PT_LIGHT_POINT) return 0.0f;
+    if (l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT) return 0.0f;
     if (l.type == B200PT_LIGHT_AREA) {  // Shape::pdf_solid_angle, shape.rs:81-107
         Ray ray = spawn_ray(hit, wi);
         V3 p0 = sc.accel.vert(l.prim, 0), p1 = sc.accel.vert(l.prim, 1), p2 = sc.accel.vert(l.prim, 2);
@@ -956,7 +965,7 @@ inline Float light_pdf_li(const RenderScene& sc, int li, const SurfHit& hit, V3 
     if (sin_t == 0.0f) return 0.0f;
     return sc.inf_distr[li].pdf(P2(phi * kInvTwoPi, theta * kInvPi)) / (kTwoPi * kPi * sin_t);
 }
-inline bool light_is_delta(const b200pt_light& l) { return l.type == B200PT_LIGHT_POINT; }
+inline bool light_is_delta(const b200pt_light& l) { return l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT; }  // DELTA_POSITION | DELTA_DIRECTION
 
 // core/src/integrator/common.rs:146-299 (handle_media = false, specular = false)
 inline RGB estimate_direct(RenderScene& sc, const SurfHit& hit, const BSDF& bsdf, P2 u_scatter, int li, P2 u_light) {

@@ -230,6 +230,52 @@ struct Param {
     std::vector<std::string> strs;    // string / bool / texture / spectrum-file values
     mutable bool used = false;
 };
+// <dir of libb200pt.so>/data or $B200PT_DATA_DIR: the published constant tables the reference links in (Sobol matrices, Perlin's
+// permutation, CIE colour-matching functions).
+static std::string lib_data_dir() {
+    if (const char* e = std::getenv("B200PT_DATA_DIR")) return e;
+    Dl_info info;
+    if (dladdr((void*)&b200pt_load_pbrt, &info) && info.dli_fname) {
+        std::string lib(info.dli_fname);
+        size_t sl = lib.find_last_of('/');
+        return (sl == std::string::npos ? std::string(".") : lib.substr(0, sl)) + "/data";
+    }
+    return "data";
+}
+// "blackbody L" [T scale] -> RGB exactly as the reference forms it: ParamSet::add_blackbody_spectrum (paramset/mod.rs:236-249)
+// samples blackbody_normalized (spectrum/common.rs:361-398, f32 arithmetic, expf) at the 471 CIE wavelengths, RGBSpectrum::from
+// (spectrum/rgb_spectrum.rs:76-103) sums value x CIE_X / Y / Z in order (the samples sit exactly on the CIE wavelengths, so
+// interpolate_spectrum_samples returns them unchanged), scales by (830 - 360) / (CIE_Y_INTEGRAL * 471) and converts XYZ -> RGB;
+// then `scale * spectrum`.
+static float planck(float lambda_nm, float t) {
+    const float C = 299792458.0f, H = 6.62606957e-34f, KB = 1.3806488e-23f;
+    const float l = lambda_nm * 1e-9f;
+    const float lambda5 = (l * l) * (l * l) * l;
+    return (2.0f * H * C * C) / (lambda5 * (std::exp((H * C) / (l * KB * t)) - 1.0f));
+}
+static void blackbody_rgb(float t, float scale, float out[3]) {
+    static std::vector<float> cie;
+    if (cie.empty()) {
+        std::ifstream f(lib_data_dir() + "/cie_xyz.bin", std::ios::binary);
+        cie.resize(3 * 471);
+        if (!f || !f.read((char*)cie.data(), (std::streamsize)(cie.size() * 4))) { cie.clear(); throw Invalid("\"blackbody\" parameter: cannot read " + lib_data_dir() + "/cie_xyz.bin (set B200PT_DATA_DIR)"); }
+    }
+    float xyz[3] = {0.0f, 0.0f, 0.0f};
+    if (t > 0.0f) {
+        const float lambda_max = 2.8977721e-3f / t * 1e9f;
+        const float max_l = planck(lambda_max, t);
+        for (int i = 0; i < 471; ++i) {
+            const float val = planck((float)(360 + i), t) / max_l;
+            xyz[0] += val * cie[(size_t)i]; xyz[1] += val * cie[471 + (size_t)i]; xyz[2] += val * cie[942 + (size_t)i];
+        }
+    }
+    const float sc = (float)(830 - 360) / (106.856895f * (float)471);
+    for (int c = 0; c < 3; ++c) xyz[c] *= sc;
+    const float rgbv[3] = {3.240479f * xyz[0] - 1.537150f * xyz[1] - 0.498535f * xyz[2], -0.969256f * xyz[0] + 1.875991f * xyz[1] + 0.041556f * xyz[2],
+                           0.055648f * xyz[0] - 0.204043f * xyz[1] + 1.057311f * xyz[2]};
+    for (int c = 0; c < 3; ++c) out[c] = scale * rgbv[c];
+}
+
 struct ParamSet {
     std::vector<Param> ps;
     const Param* find(const std::string& name, const char* t1, const char* t2 = nullptr, const char* t3 = nullptr) const {
@@ -247,7 +293,12 @@ struct ParamSet {
     // find_one_spectrum with RGB values ("rgb" / "color"); "spectrum" files and "blackbody" are outside this path
     void one_rgb(const std::string& n, const float d[3], float out[3]) const {
         for (const Param& p : ps)
-            if (p.name == n && (p.type == "spectrum" || p.type == "blackbody" || p.type == "xyz")) throw Unsupported("parameter \"" + p.type + " " + n + "\": only rgb / color spectra are on this path");
+            if (p.name == n && (p.type == "spectrum" || p.type == "xyz")) throw Unsupported("parameter \"" + p.type + " " + n + "\": only rgb / color / blackbody spectra are on this path");
+        if (const Param* b = find(n, "blackbody")) {
+            if (b->nums.size() < 2) throw Invalid("parameter \"blackbody " + n + "\" needs a temperature and a scale");
+            blackbody_rgb(b->nums[0], b->nums[1], out);  // find_one_spectrum takes the first of the (T, scale) pairs
+            return;
+        }
         const Param* p = find(n, "rgb", "color");
         if (p && p->nums.size() >= 3) { out[0] = p->nums[0]; out[1] = p->nums[1]; out[2] = p->nums[2]; }
         else { out[0] = d[0]; out[1] = d[1]; out[2] = d[2]; }
@@ -495,16 +546,7 @@ struct Builder {
         return default_matte;
     }
 
-    std::string data_dir() const {  // <dir of libb200pt.so>/data or $B200PT_DATA_DIR
-        if (const char* e = std::getenv("B200PT_DATA_DIR")) return e;
-        Dl_info info;
-        if (dladdr((void*)&b200pt_load_pbrt, &info) && info.dli_fname) {
-            std::string lib(info.dli_fname);
-            size_t sl = lib.find_last_of('/');
-            return (sl == std::string::npos ? std::string(".") : lib.substr(0, sl)) + "/data";
-        }
-        return "data";
-    }
+    std::string data_dir() const { return lib_data_dir(); }
     // Texture "name" "float" "class": the float textures a mesh can use as alpha / shadowalpha (api/src/lib.rs pbrt_texture ->
     // make_float_texture; textures/src/{constant,checkerboard_2d,dots,imagemap}.rs from-params).  Spectrum textures feed
     // materials, which take constants only on this path.
@@ -707,7 +749,20 @@ struct Builder {
                 l.map_rgb = img->data(); l.map_width = w; l.map_height = h;
                 L->images.push_back(std::move(img));
             }
-        } else throw Unsupported("LightSource \"" + name + "\" is outside this path (point, infinite)");
+        } else if (name == "distant") {  // distant.rs:131-143 + DistantLight::new :44-52
+            l.type = B200PT_LIGHT_DISTANT;
+            float Lv[3];
+            p.one_rgb("L", one, Lv);
+            for (int c = 0; c < 3; ++c) l.L[c] = Lv[c] * sc[c];
+            V3 from = v3(0, 0, 0), to = v3(0, 0, 1);
+            if (const Param* q = p.find("from", "point", "point3")) if (q->nums.size() >= 3) from = v3(q->nums[0], q->nums[1], q->nums[2]);
+            if (const Param* q = p.find("to", "point", "point3")) if (q->nums.size() >= 3) to = v3(q->nums[0], q->nums[1], q->nums[2]);
+            V3 w = xf_vector(gs.ctm.m, v3(from.x - to.x, from.y - to.y, from.z - to.z));
+            const float len = std::sqrt(w.x * w.x + w.y * w.y + w.z * w.z);
+            const float inv = 1.0f / len;  // Vector3::normalize = self / length = self * (1 / length)
+            l.pos[0] = inv * w.x; l.pos[1] = inv * w.y; l.pos[2] = inv * w.z;
+            std::memcpy(l.light_to_world, gs.ctm.m.m, 64); std::memcpy(l.world_to_light, gs.ctm.inv.m, 64);
+        } else throw Unsupported("LightSource \"" + name + "\" is outside this path (point, distant, infinite)");
         L->lights.push_back(l);
     }
 

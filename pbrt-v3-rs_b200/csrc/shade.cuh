@@ -447,7 +447,8 @@ template <uint32_t KM = KM_ALL> B2_D BxDFSample bsdf_sample_f(const BSDF& b, V3 
 }
 
 // ---- lights -------------------------------------------------------------------------
-enum : int { LT_POINT = 0, LT_AREA = 1, LT_INFINITE = 2 };
+enum : int { LT_POINT = 0, LT_AREA = 1, LT_INFINITE = 2, LT_DISTANT = 3 };
+B2_D bool light_is_delta(int type) { return type == LT_POINT || type == LT_DISTANT; }  // light.rs: DELTA_POSITION | DELTA_DIRECTION
 struct DLight {
     int type;
     int prim;        // area: original primitive index

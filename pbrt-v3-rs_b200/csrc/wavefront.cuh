@@ -224,6 +224,12 @@ B2_D LightSample sample_light(const DeviceScene& S, const DLight& light, const S
         lp1 = pl;
         Li = ldrgb(light.L) / distance_squared(pl, sh.p);
         li_valid = true;
+    } else if (light.type == LT_DISTANT) {  // distant.rs:81-90: p_outside = p + w_light * (2 * world_radius), pdf 1
+        wi = mk(light.pos[0], light.pos[1], light.pos[2]);
+        light_pdf = 1.0f;
+        lp1 = sh.p + wi * (2.0f * S.world_radius);
+        Li = ldrgb(light.L);
+        li_valid = true;
     } else if (light.type == LT_AREA) {
         int m2, l2i; uint32_t f2;
         load_prim(S, (uint32_t)light.prim, &q0, &q1, &q2, &m2, &l2i, &f2);
@@ -314,7 +320,7 @@ template <uint32_t KM = KM_ALL> B2_D DirectEst estimate_direct_rays(const Device
             V3 origin = offset_ray_origin(sh.p, sh.p_error, sh.n, lp1 - sh.p);
             V3 target = offset_ray_origin(lp1, lp1_err, lp1_n, origin - lp1);
             r.shadow = true; r.sh_o = origin; r.sh_d = target - origin;
-            if (light.type == LT_POINT) ld_light = f * Li / light_pdf;
+            if (light_is_delta(light.type)) ld_light = f * Li / light_pdf;
             else {
                 float wgt = power_heuristic(light_pdf, scattering_pdf);
                 ld_light = f * Li * wgt / light_pdf;
@@ -324,7 +330,7 @@ template <uint32_t KM = KM_ALL> B2_D DirectEst estimate_direct_rays(const Device
     // ---- BSDF-sampling half (non-delta lights only) ----
     RGB mis_f = rgb1(0.0f);
     float mis_w = 1.0f, mis_pdf = 0.0f;
-    if (light.type != LT_POINT) {
+    if (!light_is_delta(light.type)) {
         BxDFSample bs = bsdf_sample_f<KM>(bsdf, hit_wo, u_scatter, kNoSpec);
         V3 wi2 = bs.wi;
         RGB f = bs.f * abs_dot(wi2, sh.ns);

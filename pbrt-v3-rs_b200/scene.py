@@ -222,6 +222,13 @@ class SceneDescription:
     def add_point_light(self, pos, I):
         self.lights.append(dict(type="point", pos=tuple(pos), L=tuple(I)))
 
+    def add_distant_light(self, L, w_light):
+        """LightSource "distant" (lights/src/distant.rs): radiance ``L`` arriving from direction ``w_light`` (towards the
+        light, world space; normalised here the way Vector3::normalize does: v * (1 / |v|))."""
+        w = np.asarray(w_light, dtype=F32)
+        inv = F32(1.0) / np.sqrt(F32(w[0] * w[0] + w[1] * w[1]) + F32(w[2] * w[2]), dtype=F32)
+        self.lights.append(dict(type="distant", L=tuple(L), pos=tuple(float(F32(inv * c)) for c in w)))
+
     def add_infinite_light(self, L, image=None, light_to_world=None):
         """LightSource "infinite": ``L`` (times "scale"), optional environment ``image`` = decoded "mapname" as an
         (h, w, 3) float32 array (top row first, lat-long), optional 4x4 ``light_to_world``."""
@@ -276,7 +283,7 @@ class SceneDescription:
 
     def to_desc(self):
         from . import Camera, Film, Integrator, Light, Material, Sampler, SceneDesc
-        from . import (DIRECT_ALL, DIRECT_ONE, INTEGRATOR_DIRECT, INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_SPATIAL, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
+        from . import (DIRECT_ALL, DIRECT_ONE, INTEGRATOR_DIRECT, INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_DISTANT, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_SPATIAL, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
                        MAT_PLASTIC, SAMPLER_HALTON, SAMPLER_SOBOL, SAMPLER_ZEROTWO)
         if self.nodes is None:
             self.build_accel(None)
@@ -381,6 +388,9 @@ class SceneDescription:
             Lt.world_to_light[:] = l.get("world_to_light", ident)
             if l["type"] == "point":
                 Lt.type = LIGHT_POINT
+                Lt.pos[:] = l["pos"]
+            elif l["type"] == "distant":
+                Lt.type = LIGHT_DISTANT
                 Lt.pos[:] = l["pos"]
             elif l["type"] == "diffuse":
                 Lt.type = LIGHT_AREA

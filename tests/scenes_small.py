@@ -17,6 +17,12 @@ def one_material_scene(wl, mat, light="infinite", res=24, spp=8, maxdepth=5, nu=
         sd.add_infinite_light((1.2, 1.2, 1.1))
     if light in ("point", "all"):
         sd.add_point_light((1.5, 3.0, -3.0), (30, 30, 30))
+    if light in ("distant", "all+distant"):
+        sd.add_distant_light((2.5, 2.4, 2.2), (-0.4, 1.0, -0.6))
+    if light == "all+distant":
+        light = "all"
+        sd.add_infinite_light((1.2, 1.2, 1.1))
+        sd.add_point_light((1.5, 3.0, -3.0), (30, 30, 30))
     if light in ("area", "all"):
         lq = np.array([[-1.5, 3.0, -1.0], [1.5, 3.0, -1.0], [1.5, 3.0, 1.0], [-1.5, 3.0, 1.0]], dtype=np.float32)
         lt = np.stack([np.concatenate([lq[0], lq[1], lq[2]]), np.concatenate([lq[0], lq[2], lq[3]])])

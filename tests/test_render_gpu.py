@@ -568,3 +568,26 @@ def test_render_multi_on_the_visible_devices(gpu, oracle):
             assert int(info["rays"][0]) == rc[0]
             multi.close()
     assert gpu.current_device() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,light,integrator,strategy", [("matte", "distant", "path", "uniform"), ("plastic", "all+distant", "path", "power"), ("glass", "all+distant", "path", "spatial"),
+                                                            ("matte", "all+distant", "whitted", "uniform"), ("plastic", "all+distant", "directlighting", "uniform")])
+def test_distant_light_matches_oracle(gpu, oracle, name, light, integrator, strategy):
+    """DistantLight (lights/src/distant.rs): a delta-direction light - sample_li with pdf 1 towards w_light, visibility tested
+    up to p + w_light * 2 * world_radius, power L * pi * r^2 in the power / spatial distributions, no BSDF-sampled MIS ray."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS[name], light=light, res=40, spp=8, maxdepth=4, strategy=strategy)
+    sd.integrator.update(name=integrator)
+    integ = gpu.PathIntegrator(sd)
+    osc = oracle.OracleScene(sd)
+    ps = _pairs(40, 8)
+    li, rays = integ.li(ps)
+    oli = osc.li(ps)
+    assert rays.tobytes() == osc.camera_rays(ps).tobytes()
+    assert np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1).mean() >= 0.999
+    img = integ.render()
+    ref, stats, _ = osc.render()
+    assert img.mean() > 0.01 and ss.rel_rmse(img, ref) <= TOL
+    assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]
+

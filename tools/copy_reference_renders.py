@@ -1,9 +1,12 @@
-"""Copies the reference's own committed renders of the three shipped scenes that lie entirely on this path (triangle
+"""Copies the reference's own committed renders of the six shipped scenes that lie entirely on this path (triangle
 meshes, matte, point / infinite light, Whitted, Halton, box filter) into tests/golden/ref_renders/:
 
   renders/lights/point.png                 <- scenes/lights/point.pbrt
   renders/lights/infinite-no-map.png       <- scenes/lights/infinite-no-map.pbrt
   renders/shapes/triangles-alpha-mask.png  <- scenes/shapes/triangles-alpha-mask.pbrt
+  renders/lights/distant.png               <- scenes/lights/distant.pbrt        (distant light, "blackbody L")
+  renders/objects/instances.png            <- scenes/objects/instances.pbrt     (ten ObjectInstances of a cube: the two-level BVH)
+  renders/cameras/perspective.png          <- scenes/cameras/perspective.pbrt   (infinite + distant light)
 
 They are OUTPUTS of the reference (8-bit sRGB PNGs written by core/src/image_io.rs), i.e. golden vectors: the only
 artefacts in the reference tree that were produced by executing it.  tests/test_reference_renders.py renders the same
@@ -16,6 +19,7 @@ DST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 if __name__ == "__main__":
     os.makedirs(DST, exist_ok=True)
-    for sub, name in (("lights", "point"), ("lights", "infinite-no-map"), ("shapes", "triangles-alpha-mask")):
+    for sub, name in (("lights", "point"), ("lights", "infinite-no-map"), ("shapes", "triangles-alpha-mask"), ("lights", "distant"),
+                      ("objects", "instances"), ("cameras", "perspective")):
         shutil.copyfile(os.path.join(SRC, sub, name + ".png"), os.path.join(DST, name + ".png"))
         print("copied", name)

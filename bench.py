@@ -13,6 +13,13 @@ calls with pinned host memory, copies inside the timed region.
 Under torchrun (N > 1) every rank traces its own batch (weak scaling, no data-path collective);
 the time is the max over ranks.  `--impl reference` times the CPU oracle (the reference cannot be
 built here: no Rust toolchain) on all host cores, rank 0 only.
+
+Besides the contract's keys the line carries: `roofline` (C2's closest-hit kernel: algorithmic bytes per second against the
+measured copy peak, with the DRAM traffic / lanes / issue utilisation of the committed ncu capture; the tree is L2-resident,
+so `bound` says "issue"), `roofline_c4` (the same kernel on a 10 M-triangle, HBM-resident mesh), `path_tracing` (C4,
+BASELINE's sharded configuration: 1080p @ 256 spp, rows dealt to the ranks in bands, owned bands gathered on rank 0 over
+NCCL; strong scaling) and `path_tracing_c3` (C3, 64 spp), each with its own `cpu_baseline`; the path legs are timed with CUDA
+events and report the median of `--path-iters` iterations with every sample (`samples_ms`).
 """
 import argparse
 import json

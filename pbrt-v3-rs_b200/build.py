@@ -44,6 +44,40 @@ def _digest():
     return h.hexdigest()
 
 
+def _object_digest(src):
+    """One translation unit's inputs: the source itself, every header beside it and under include/, and the flags."""
+    h = hashlib.sha256()
+    names = [os.path.join(CSRC, src)]
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        names += [os.path.join(root, n) for n in sorted(os.listdir(root)) if n.endswith((".h", ".cuh", ".hpp"))]
+    for name in names:
+        with open(name, "rb") as f:
+            h.update(os.path.basename(name).encode())
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src, force):
+    """Compiles one source unless its object is up to date; returns (object, log text)."""
+    obj = os.path.join(HERE, "build", src + ".o")
+    stamp = obj + ".stamp"
+    digest = _object_digest(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp):
+        with open(stamp) as f:
+            if f.read().strip() == digest:
+                return obj, "(up to date) " + src
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    text = "$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr
+    if r.returncode != 0:
+        sys.stderr.write(text)
+        raise RuntimeError("nvcc failed on " + src)
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return obj, text
+
+
 def build(force=False, verbose=False):
     digest = _digest()
     if not force and os.path.exists(OUT) and os.path.exists(STAMP):
@@ -51,17 +85,12 @@ def build(force=False, verbose=False):
             if f.read().strip() == digest:
                 return OUT
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    objs = []
-    log = []
-    for src in SOURCES:
-        obj = os.path.join(HERE, "build", src + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(log[-1])
-            raise RuntimeError("nvcc failed on " + src)
-        objs.append(obj)
+    # translation units are independent: compile them side by side (the two largest take minutes each)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(SOURCES), os.cpu_count() or 1))) as pool:
+        results = list(pool.map(lambda s: _compile(s, force), SOURCES))
+    objs = [o for o, _ in results]
+    log = [t for _, t in results]
     cmd = [_nvcc(), "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)

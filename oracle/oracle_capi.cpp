@@ -201,6 +201,15 @@ void orc_accel_set_alpha(void* accel, const b200pt_float_texture* tex, int n_tex
     a->noise_perm.clear();
     if (noise_perm) a->noise_perm.assign(noise_perm, noise_perm + 256);
 }
+// Texture<Spectrum>::evaluate for uv and the four screen-space uv derivatives der = {dudx, dvdx, dudy, dvdy}
+void orc_spectrum_texture_evaluate(const b200pt_spectrum_texture* t, float u, float v, const float* der, float* out3) {
+    SpectrumTexture T;
+    T.type = t->type; T.su = t->su; T.sv = t->sv; T.du = t->du; T.dv = t->dv; T.closedform = t->aa_closedform != 0;
+    for (int c = 0; c < 3; ++c) { T.tex1[c] = t->tex1[c]; T.tex2[c] = t->tex2[c]; }
+    UVDerivs d;
+    d.dudx = der[0]; d.dvdx = der[1]; d.dudy = der[2]; d.dvdy = der[3];
+    spectrum_texture_evaluate(T, u, v, d, out3);
+}
 float orc_float_texture_evaluate(const b200pt_float_texture* tex, const uint8_t* noise_perm, float u, float v) {
     return float_texture_evaluate(float_texture_from(*tex), noise_perm, u, v);
 }

@@ -209,8 +209,19 @@ inline void bounding_sphere(const Bounds3& b, V3* center, Float* radius) {
 struct Ray {
     V3 o, d;
     Float t_max, time;
+    // RayDifferential (core/src/geometry/ray.rs): only camera rays carry one on this path; it feeds texture filtering only
+    bool has_diff = false;
+    V3 rx_o, ry_o, rx_d, ry_d;
     Ray() : t_max(kInfinity), time(0) {}
     Ray(V3 o_, V3 d_, Float tm, Float ti) : o(o_), d(d_), t_max(tm), time(ti) {}
+    // ray.rs:90-99
+    void scale_differentials(Float s) {
+        if (!has_diff) return;
+        rx_o = o + (rx_o - o) * s;
+        ry_o = o + (ry_o - o) * s;
+        rx_d = d + (rx_d - d) * s;
+        ry_d = d + (ry_d - d) * s;
+    }
 };
 
 // core/src/geometry/ray.rs:107-127
@@ -372,7 +383,13 @@ inline Ray xf_ray(const M4& M, const Ray& r) {
         o = o + d * dt;
         t_max -= dt;
     }
-    return Ray(o, d, t_max, r.time);
+    Ray out(o, d, t_max, r.time);
+    if (r.has_diff) {  // transform.rs:464-472: the differential origins are NOT nudged along the error bound
+        out.has_diff = true;
+        out.rx_o = xf_point(M, r.rx_o); out.ry_o = xf_point(M, r.ry_o);
+        out.rx_d = xf_vector(M, r.rx_d); out.ry_d = xf_vector(M, r.ry_d);
+    }
+    return out;
 }
 // transform.rs:593-599
 inline bool swaps_handedness(const M4& M) {

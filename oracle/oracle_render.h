@@ -499,6 +499,8 @@ struct BSDF {
 struct SurfHit {
     V3 p, p_error, wo, n;  // Hit
     V3 shading_n, dpdu;    // Shading (== geometric values: no vertex normals/tangents, no bump)
+    P2 uv;                 // SurfaceInteraction::uv
+    V3 dpdu_g, dpdv_g;     // SurfaceInteraction::der.{dpdu, dpdv}: the geometric partials (texture filtering only)
     uint32_t prim = 0xffffffffu;
     Float time = 0;
 };
@@ -517,6 +519,8 @@ struct RenderScene {
     bool has_instances = false;
     std::vector<int32_t> prim_material, prim_light;
     std::vector<b200pt_material> materials;
+    std::vector<SpectrumTexture> spectrum_textures;  // textured "Kd" (matte / plastic)
+    std::vector<int32_t> material_kd_tex;            // per material: index into spectrum_textures or -1 (empty = none)
     std::vector<b200pt_light> lights;
     std::vector<int> infinite_lights;
     b200pt_camera camera;
@@ -629,6 +633,17 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
         }
     }
     s->materials.assign(d->materials, d->materials + d->n_materials);
+    if (d->material_kd_tex && d->spectrum_textures && d->n_spectrum_textures > 0) {
+        s->material_kd_tex.assign(d->material_kd_tex, d->material_kd_tex + d->n_materials);
+        for (int k = 0; k < d->n_spectrum_textures; ++k) {
+            const b200pt_spectrum_texture& t = d->spectrum_textures[k];
+            SpectrumTexture T;
+            T.type = t.type; T.su = t.su; T.sv = t.sv; T.du = t.du; T.dv = t.dv;
+            for (int c = 0; c < 3; ++c) { T.tex1[c] = t.tex1[c]; T.tex2[c] = t.tex2[c]; }
+            T.closedform = t.aa_closedform != 0;
+            s->spectrum_textures.push_back(T);
+        }
+    }
     s->lights.assign(d->lights, d->lights + d->n_lights);
     s->camera = d->camera; s->film = d->film; s->sampler = d->sampler; s->integ = d->integrator;
     s->raster_to_camera = m4_from(d->camera.raster_to_camera);
@@ -738,6 +753,7 @@ inline bool scene_intersect(RenderScene& sc, Ray& ray, SurfHit* sh) {
     triangle_geometry(p0, p1, p2, h.b0, h.b1, h.b2, sc.accel.attr(h.prim), &g);
     sh->prim = h.prim;
     sh->time = ray.time;
+    sh->uv = g.uv; sh->dpdu_g = g.dpdu; sh->dpdv_g = g.dpdv;
     if (inst < 0) {
         sh->p = g.p; sh->p_error = g.p_error; sh->n = g.n; sh->shading_n = g.shading_n; sh->dpdu = g.shading_dpdu;
         V3 wo = -d_in;
@@ -763,6 +779,7 @@ inline bool scene_intersect(RenderScene& sc, Ray& ray, SurfHit* sh) {
     V3 sn = normalize(xf_normal(I.w2i, g.shading_n));
     sh->shading_n = face_forward(sn, sh->n);
     sh->dpdu = xf_vector(I.i2w, g.shading_dpdu);
+    sh->dpdu_g = xf_vector(I.i2w, g.dpdu); sh->dpdv_g = xf_vector(I.i2w, g.dpdv);  // transform.rs:577-578
     return true;
 }
 inline bool scene_intersect_p(RenderScene& sc, const Ray& ray) {
@@ -774,13 +791,51 @@ inline bool scene_intersect_p(RenderScene& sc, const Ray& ray) {
 // materials/src/{matte,plastic,glass,metal}.rs compute_scattering_functions
 // with constant textures, no bump map, allow_multiple_lobes = true (path.rs:145).
 // BSDF::new is called with eta = None in all four, so bsdf.eta = 1.0.
-inline BSDF make_bsdf(const RenderScene& sc, const SurfHit& sh, bool allow_multiple_lobes = true) {
+// matrix4x4.rs:305-318
+inline bool solve_linear_system_2x2(const Float a[2][2], const Float b[2], Float* x0, Float* x1) {
+    Float det = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+    if (pabs(det) < 1e-10f) return false;
+    *x0 = (a[1][1] * b[0] - a[0][1] * b[1]) / det;
+    *x1 = (a[0][0] * b[1] - a[1][0] * b[0]) / det;
+    return !(std::isnan(*x0) || std::isnan(*x1));
+}
+// SurfaceInteraction::compute_differentials (surface_interaction.rs:203-277): the uv footprint of one pixel step, from
+// the ray's differentials and the tangent plane at the hit.  Rays without differentials leave all of it zero.
+inline UVDerivs compute_differentials(const SurfHit& sh, const Ray* ray) {
+    UVDerivs der;
+    if (!ray || !ray->has_diff) return der;
+    V3 n = sh.n, p = sh.p;
+    Float d = dot(n, p);
+    Float tx = -(dot(n, ray->rx_o) - d) / dot(n, ray->rx_d);
+    if (std::isinf(tx) || std::isnan(tx)) return der;
+    V3 px = ray->rx_o + tx * ray->rx_d;
+    Float ty = -(dot(n, ray->ry_o) - d) / dot(n, ray->ry_d);
+    if (std::isinf(ty) || std::isnan(ty)) return der;
+    V3 py = ray->ry_o + ty * ray->ry_d;
+    int dim[2];
+    if (pabs(n.x) > pabs(n.y) && pabs(n.x) > pabs(n.z)) { dim[0] = 1; dim[1] = 2; }
+    else if (pabs(n.y) > pabs(n.z)) { dim[0] = 0; dim[1] = 2; }
+    else { dim[0] = 0; dim[1] = 1; }
+    const Float a[2][2] = {{sh.dpdu_g[dim[0]], sh.dpdv_g[dim[0]]}, {sh.dpdu_g[dim[1]], sh.dpdv_g[dim[1]]}};
+    const Float bx[2] = {px[dim[0]] - p[dim[0]], px[dim[1]] - p[dim[1]]};
+    const Float by[2] = {py[dim[0]] - p[dim[0]], py[dim[1]] - p[dim[1]]};
+    if (!solve_linear_system_2x2(a, bx, &der.dudx, &der.dvdx)) { der.dudx = 0.0f; der.dvdx = 0.0f; }
+    if (!solve_linear_system_2x2(a, by, &der.dudy, &der.dvdy)) { der.dudy = 0.0f; der.dvdy = 0.0f; }
+    return der;
+}
+
+// `ray` = the ray that found the hit (isect.compute_scattering_functions(&ray, ..), path.rs:145, whitted.rs:76): its
+// differentials, if any, size the footprint a textured "Kd" is filtered over.
+inline BSDF make_bsdf(const RenderScene& sc, const SurfHit& sh, bool allow_multiple_lobes = true, const Ray* ray = nullptr) {
     BSDF b;
     b.ns = sh.shading_n; b.ng = sh.n;
     b.ss = normalize(sh.dpdu);
     b.ts = cross(b.ns, b.ss);
     b.eta = 1.0f;
-    const b200pt_material& m = sc.materials[sc.prim_material[sh.prim]];
+    const int mat_index = sc.prim_material[sh.prim];
+    b200pt_material m = sc.materials[(size_t)mat_index];
+    if (!sc.material_kd_tex.empty() && sc.material_kd_tex[(size_t)mat_index] >= 0 && (m.type == B200PT_MAT_MATTE || m.type == B200PT_MAT_PLASTIC))
+        spectrum_texture_evaluate(sc.spectrum_textures[(size_t)sc.material_kd_tex[(size_t)mat_index]], sh.uv.x, sh.uv.y, compute_differentials(sh, ray), m.kd);
     auto rgb = [](const float* c) { return RGB(c[0], c[1], c[2]); };
     switch (m.type) {
         case B200PT_MAT_MATTE: {
@@ -1102,7 +1157,7 @@ inline RGB path_li(RenderScene& sc, Ray ray, Sampler& sampler) {
             ray = spawn_ray(isect, ray_d);
             continue;
         }
-        BSDF bsdf = make_bsdf(sc, isect);
+        BSDF bsdf = make_bsdf(sc, isect, true, &ray);
         if (bsdf.num_components(BSDF_ALL & ~BSDF_SPECULAR) > 0) {
             RGB ld = beta * uniform_sample_one_light(sc, isect, bsdf, sampler);
             L += ld;
@@ -1130,7 +1185,8 @@ inline RGB path_li(RenderScene& sc, Ray ray, Sampler& sampler) {
 }
 
 // integrators/src/whitted.rs:60-126 with specular_reflect / specular_transmit of
-// core/src/integrator/sampler_integrator.rs:79-238 (ray differentials only feed texture filtering: dropped).
+// core/src/integrator/sampler_integrator.rs:79-238 (the camera ray's differentials filter a textured "Kd"; specular children
+// get none here, so scene_create refuses Whitted / DirectLighting scenes that combine a closedform checkerboard with glass).
 inline RGB whitted_li(RenderScene& sc, Ray ray, Sampler& sampler, int depth) {
     RGB l;
     SurfHit isect;
@@ -1138,7 +1194,7 @@ inline RGB whitted_li(RenderScene& sc, Ray ray, Sampler& sampler, int depth) {
         for (int li : sc.infinite_lights) l += infinite_le(sc, li, ray);  // Light::le is zero for the other kinds
         return l;
     }
-    BSDF bsdf = make_bsdf(sc, isect, false);
+    BSDF bsdf = make_bsdf(sc, isect, false, &ray);
     const V3 n = isect.shading_n, wo = isect.wo;
     int al = sc.prim_light.empty() ? -1 : sc.prim_light[isect.prim];
     if (al >= 0) l += area_l(sc.lights[al], isect.n, wo);
@@ -1182,7 +1238,7 @@ inline RGB direct_li(RenderScene& sc, Ray ray, Sampler& sampler, int depth) {
         for (int li : sc.infinite_lights) l += infinite_le(sc, li, ray);
         return l;
     }
-    BSDF bsdf = make_bsdf(sc, isect, false);
+    BSDF bsdf = make_bsdf(sc, isect, false, &ray);
     const V3 n = isect.shading_n, wo = isect.wo;
     int al = sc.prim_light.empty() ? -1 : sc.prim_light[isect.prim];
     if (al >= 0) l += area_l(sc.lights[al], isect.n, wo);
@@ -1230,8 +1286,8 @@ inline RGB integrator_li(RenderScene& sc, Ray ray, Sampler& sampler) {
     return sc.integ.type == B200PT_INTEGRATOR_WHITTED ? whitted_li(sc, ray, sampler, 0) : path_li(sc, ray, sampler);
 }
 
-// cameras/src/perspective_camera.rs:144-204 (differentials dropped) +
-// core/src/sampler/mod.rs:43-51.
+// cameras/src/perspective_camera.rs:144-204 (generate_ray_differential) + core/src/sampler/mod.rs:43-51; the
+// differentials are scaled by 1 / sqrt(spp) as render_tile does right after (sampler_integrator.rs:357-358).
 inline Ray camera_ray(const RenderScene& sc, int px, int py, Sampler& sampler, P2* p_film_out) {
     P2 fs = sampler.get_2d();
     P2 p_film((Float)px + fs.x, (Float)py + fs.y);
@@ -1248,7 +1304,34 @@ inline Ray camera_ray(const RenderScene& sc, int px, int py, Sampler& sampler, P
         ray.d = normalize(p_focus - ray.o);
     }
     *p_film_out = p_film;
-    return xf_ray(sc.camera_to_world, ray);
+    if (!sc.spectrum_textures.empty()) {
+        // dx_camera / dy_camera, perspective_camera.rs:71-74
+        V3 c00 = xf_point(sc.raster_to_camera, V3(0.0f, 0.0f, 0.0f));
+        V3 dx_camera = xf_point(sc.raster_to_camera, V3(1.0f, 0.0f, 0.0f)) - c00;
+        V3 dy_camera = xf_point(sc.raster_to_camera, V3(0.0f, 1.0f, 0.0f)) - c00;
+        ray.has_diff = true;
+        if (sc.camera.lens_radius > 0.0f) {  // :175-193
+            P2 cd = concentric_sample_disk(p_lens);
+            P2 pl(sc.camera.lens_radius * cd.x, sc.camera.lens_radius * cd.y);
+            V3 dx = normalize(p_camera + dx_camera);
+            Float ftx = sc.camera.focal_distance / dx.z;
+            V3 p_focus_x = V3(0.0f, 0.0f, 0.0f) + (ftx * dx);
+            ray.rx_o = V3(pl.x, pl.y, 0.0f);
+            ray.rx_d = normalize(p_focus_x - ray.rx_o);
+            V3 dy = normalize(p_camera + dy_camera);
+            Float fty = sc.camera.focal_distance / dy.z;
+            V3 p_focus_y = V3(0.0f, 0.0f, 0.0f) + (fty * dy);
+            ray.ry_o = V3(pl.x, pl.y, 0.0f);
+            ray.ry_d = normalize(p_focus_y - ray.ry_o);
+        } else {  // :194-199
+            ray.rx_o = ray.o; ray.ry_o = ray.o;
+            ray.rx_d = normalize(p_camera + dx_camera);
+            ray.ry_d = normalize(p_camera + dy_camera);
+        }
+    }
+    Ray world = xf_ray(sc.camera_to_world, ray);
+    world.scale_differentials(1.0f / std::sqrt((Float)sampler.spp));
+    return world;
 }
 
 inline Sampler* make_sampler(const RenderScene& sc, uint64_t seed) {

@@ -102,4 +102,41 @@ inline Float float_texture_evaluate(const FloatTexture& T, const uint8_t* perm, 
            ftex_texel(T, s0 + 1, t0 + 1) * ds * dt;
 }
 
+// ---- spectrum textures a material's "Kd" can name (textures/src/{constant,checkerboard_2d}.rs over UVMapping2D) ----
+struct SpectrumTexture {
+    int type = 0;  // B200PT_STEX_*: 0 constant, 1 checkerboard (2-D)
+    Float su = 1.0f, sv = 1.0f, du = 0.0f, dv = 0.0f;
+    Float tex1[3] = {1.0f, 1.0f, 1.0f}, tex2[3] = {0.0f, 0.0f, 0.0f};
+    bool closedform = true;
+};
+// si.der's screen-space uv derivatives (SurfaceInteraction::compute_differentials, surface_interaction.rs:203-277)
+struct UVDerivs {
+    Float dudx = 0.0f, dvdx = 0.0f, dudy = 0.0f, dvdy = 0.0f;
+};
+inline Float bump_int(Float x) {  // checkerboard_2d.rs:101-103
+    Float h = std::floor(x / 2.0f);
+    return h + 2.0f * pmax((x / 2.0f) - h - 0.5f, 0.0f);
+}
+// Texture<Spectrum>::evaluate; out = 3 floats (not clamped: the material clamps, matte.rs:63)
+inline void spectrum_texture_evaluate(const SpectrumTexture& T, Float u, Float v, const UVDerivs& der, Float out[3]) {
+    if (T.type == 0) { out[0] = T.tex1[0]; out[1] = T.tex1[1]; out[2] = T.tex1[2]; return; }
+    // uv_2d.rs:44-50
+    Float dsdx = T.su * der.dudx, dtdx = T.sv * der.dvdx, dsdy = T.su * der.dudy, dtdy = T.sv * der.dvdy;
+    Float s = T.su * u + T.du, t = T.sv * v + T.dv;
+    auto point_sample = [&]() {
+        int sum = (int)((unsigned)as_i32(std::floor(s)) + (unsigned)as_i32(std::floor(t)));
+        const Float* c = sum % 2 == 0 ? T.tex1 : T.tex2;
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2];
+    };
+    if (!T.closedform) { point_sample(); return; }
+    // checkerboard_2d.rs:72-97
+    Float ds = pmax(pabs(dsdx), pabs(dsdy)), dt = pmax(pabs(dtdx), pabs(dtdy));
+    Float s0 = s - ds, s1 = s + ds, t0 = t - dt, t1 = t + dt;
+    if (std::floor(s0) == std::floor(s1) && std::floor(t0) == std::floor(t1)) { point_sample(); return; }
+    Float sint = (bump_int(s1) - bump_int(s0)) / (2.0f * ds);
+    Float tint = (bump_int(t1) - bump_int(t0)) / (2.0f * dt);
+    Float area2 = (ds > 1.0f || dt > 1.0f) ? 0.5f : sint + tint - 2.0f * sint * tint;
+    for (int c = 0; c < 3; ++c) out[c] = T.tex1[c] * (1.0f - area2) + T.tex2[c] * area2;
+}
+
 }  // namespace orc

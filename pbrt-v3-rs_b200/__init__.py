@@ -133,6 +133,31 @@ def float_texture_array(textures, keep):
     return arr
 
 
+class SpectrumTexture(C.Structure):
+    _fields_ = [("type", C.c_int32), ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float), ("tex1", C.c_float * 3),
+                ("tex2", C.c_float * 3), ("aa_closedform", C.c_int32)]
+
+
+STEX_CONSTANT, STEX_CHECKERBOARD = 0, 1
+
+
+def spectrum_texture_array(textures, keep):
+    """ctypes array of b200pt_spectrum_texture from the mirror's dicts (scene.SceneDescription.add_spectrum_texture)."""
+    arr = (SpectrumTexture * max(1, len(textures)))()
+    for k, t in enumerate(textures):
+        T = arr[k]
+        T.type = {"constant": STEX_CONSTANT, "checkerboard": STEX_CHECKERBOARD}[t["type"]]
+        T.su, T.sv, T.du, T.dv = t.get("uscale", 1.0), t.get("vscale", 1.0), t.get("udelta", 0.0), t.get("vdelta", 0.0)
+        if t["type"] == "constant":
+            T.tex1[:] = t.get("value", (1.0, 1.0, 1.0))
+        else:  # checkerboard_2d.rs:127-128, 134: tex1 = 1, tex2 = 0, aamode closedform
+            T.tex1[:] = t.get("tex1", (1.0, 1.0, 1.0))
+            T.tex2[:] = t.get("tex2", (0.0, 0.0, 0.0))
+        T.aa_closedform = 0 if t.get("aamode", "closedform") == "none" else 1
+    keep.append(arr)
+    return arr
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("nodes", C.c_void_p), ("n_nodes", C.c_int64), ("ordered_prims", C.c_void_p), ("tri_verts", C.c_void_p),
                 ("prim_flags", C.c_void_p), ("prim_material", C.c_void_p), ("prim_light", C.c_void_p), ("n_prims", C.c_int64),
@@ -140,7 +165,8 @@ class SceneDesc(C.Structure):
                 ("camera", Camera), ("film", Film), ("sampler", Sampler), ("integrator", Integrator),
                 ("n_top_tris", C.c_int64), ("objects", C.c_void_p), ("n_objects", C.c_int32), ("instances", C.c_void_p), ("n_instances", C.c_int32),
                 ("tri_uvs", C.c_void_p), ("tri_normals", C.c_void_p), ("tri_tangents", C.c_void_p), ("sobol_matrices_32", C.c_void_p),
-                ("float_textures", C.c_void_p), ("n_float_textures", C.c_int32), ("prim_alpha_tex", C.c_void_p), ("noise_perm", C.c_void_p)]
+                ("float_textures", C.c_void_p), ("n_float_textures", C.c_int32), ("prim_alpha_tex", C.c_void_p), ("noise_perm", C.c_void_p),
+                ("spectrum_textures", C.c_void_p), ("n_spectrum_textures", C.c_int32), ("material_kd_tex", C.c_void_p)]
 
 
 _lib = None

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene S, Wave W, long long
     W.beta[p] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     W.hidx[p] = idx;
     W.meta[p] = meta_pack(dim, live ? 0 : 255, 0);
+    if (W.cam_diff) camera_differentials(S.camera, pf, pl, mk(r.ox, r.oy, r.oz), mk(r.dx, r.dy, r.dz), S.cam_diff_scale, W.cam_diff + 3ll * p);
     if (p_film_out) p_film_out[p] = make_float2(pf.x, pf.y);  // wave-local, like the radiance k_store_samples writes
     if (rays_out) { rays_out[2 * p] = make_float4(r.ox, r.oy, r.oz, r.tmax); rays_out[2 * p + 1] = make_float4(r.dx, r.dy, r.dz, r.time); }
 }
@@ -204,7 +205,7 @@ B2_D void shade_vertex(const DeviceScene& S, const Wave& W, int cur, int slot, b
     const float time = r1.w;
     int meta = W.meta[pid];
     int dim = meta & 0xffff, bounces = (meta >> 16) & 0xff;
-    bool specular_bounce = ((meta >> 24) & 0xff) != 0;
+    bool specular_bounce = ((meta >> 24) & 1) != 0;
     if (bounces == 255) return;  // pixel outside the integrator's pixel bounds: no sample is taken
     float4 Lw = W.L[pid], bw = W.beta[pid];
     RGB L = rgb(Lw.x, Lw.y, Lw.z), beta = rgb(bw.x, bw.y, bw.z);
@@ -237,6 +238,7 @@ B2_D void shade_vertex(const DeviceScene& S, const Wave& W, int cur, int slot, b
     if (kMode == kShadeNull || (KM == KM_ALL && mat < 0)) {
         // path.rs:146-150: no BSDF (Material "" / "none"): isect.spawn_ray(ray.d), `continue` without counting a bounce
         W.L[pid] = make_float4(L.r, L.g, L.b, Lw.w);
+        W.meta[pid] = meta | (1 << 25);  // the re-spawned ray carries no differentials (Hit::spawn_ray)
         const int ns = atomicAdd(&W.counters[0], 1);
         store_ray(W.ray[cur ^ 1], ns, offset_ray_origin(sh.p, sh.p_error, sh.n, ray_d), ray_d, __int_as_float(0x7f800000), time);
         W.qpid[cur ^ 1][ns] = pid;
@@ -248,6 +250,15 @@ B2_D void shade_vertex(const DeviceScene& S, const Wave& W, int cur, int slot, b
     bsdf.ss = normalize(sh.dpdu);
     bsdf.ts = cross(bsdf.ns, bsdf.ss);
     bsdf.m = S.materials + mat;
+    DMaterial tex_mat;  // KM_TEX kernels only: the material with this intersection's Kd
+    if ((KM & KM_TEX) && S.mat_kd_tex) {
+        const int tex = S.mat_kd_tex[mat];
+        if (tex >= 0) {
+            const bool camera_ray = bounces == 0 && !((meta >> 25) & 1);  // path.rs: every later ray comes from spawn_ray
+            textured_material(S, W, slot, prim, hit, hb2, sh, tex, (camera_ray && W.cam_diff) ? W.cam_diff + 3ll * pid : nullptr, S.materials[mat], &tex_mat);
+            bsdf.m = &tex_mat;
+        }
+    }
     const uint32_t kNoSpec = BSDF_ALL & ~BSDF_SPECULAR;
 
     // path.rs:162-173 -> uniform_sample_one_light (integrator/common.rs:89-133)
@@ -497,6 +508,7 @@ B2_D Ray32 zt_seq_emit(const DeviceScene& S, const Wave& W, int p, int px, int p
     W.beta[p] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     W.hidx[p] = key;
     W.meta[p] = meta_pack(dim, live ? 0 : 255, 0);
+    if (W.cam_diff) camera_differentials(S.camera, pf, pl, mk(r.ox, r.oy, r.oz), mk(r.dx, r.dy, r.dz), S.cam_diff_scale, W.cam_diff + 3ll * p);
     *pf_out = pf;
     return r;
 }
@@ -738,6 +750,8 @@ struct SceneImpl {
     bool whitted = false;     // a recursive SamplerIntegrator (Whitted / DirectLighting) instead of PathIntegrator
     int tree_mode = 0;        // kTreeWhitted / kTreeDirectAll / kTreeDirectOne
     bool has_null_material = false;  // some primitive has no material: paths pass through it without counting a bounce
+    bool has_kd_tex = false;         // some matte / plastic material has a textured Kd: their shade kernels are the KM_TEX instantiations
+    bool needs_cam_diff = false;     // ... and one of the textures filters over the camera ray's differentials (closedform checkerboard)
     uint32_t material_classes = 0;   // bit t = some material of type t exists (which shade kernels a bounce launches)
     int n_point_lights = 0;          // delta lights: estimate_direct traces no BSDF-sampled ray for them
     DeviceScene dev;
@@ -800,6 +814,7 @@ static size_t wave_bytes_per_path(const SceneImpl* s) {
     b += sh_mul * (32 + 1) + mis_mul * (32 + 16 + 4);   // shadow / MIS queues
     b += 16 + 16 + 8 + 4 + 4 * 16 + 4 + 1 + 4;          // L, beta, sample index, meta, pending records, pending list, key, sorted
     if (s->dev.spatial) b += 4;
+    if (s->needs_cam_diff) b += 48;
     if (s->whitted) {
         b += sh_mul * 16 + (size_t)std::max(1, s->dev.max_depth) * 48;
         if (s->tree_mode != kTreeWhitted) b += sh_mul * (16 + 8);
@@ -1047,6 +1062,8 @@ static int wave_alloc(SceneImpl* s, int cap) {
     if ((rc = dev_alloc(s, (size_t)cap, &W.sorted))) return rc;
     W.deferred = nullptr;
     if (s->dev.spatial && (rc = dev_alloc(s, (size_t)cap, &W.deferred))) return rc;
+    W.cam_diff = nullptr;
+    if (s->needs_cam_diff && (rc = dev_alloc(s, (size_t)cap * 3, &W.cam_diff))) return rc;
     s->wave_cap = cap;
     return B200PT_OK;
 }
@@ -1065,7 +1082,8 @@ static int shade_grid(const SceneImpl* s, int n_upper, int per_sm) {
 template <uint32_t KM>
 static void launch_shade_class(SceneImpl* s, const Wave& W, int cur, int n_upper, int bin, int blocks, cudaStream_t st) {
     if (st != s->shade_main) cudaStreamWaitEvent(st, s->ev_fork, 0);  // a class on its own stream starts after the sort
-    switch (blocks) {
+    if constexpr ((KM & KM_TEX) != 0) k_shade<KM, kShadeHit, 4><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1);  // textured Kd: one register budget
+    else switch (blocks) {
         case 3: k_shade<KM, kShadeHit, 3><<<shade_grid(s, n_upper, 12), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
         case 4: k_shade<KM, kShadeHit, 4><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
         case 6: k_shade<KM, kShadeHit, 6><<<shade_grid(s, n_upper, 24), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
@@ -1108,15 +1126,23 @@ static void launch_shade(SceneImpl* s, const Wave& W, int cur, int n_upper, cuda
     }
     k_shade<KM_ALL, kShadeMiss, 8><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, 0, 1);
     ++launches;
-    if (mode == 3 && n_classes > 1) {
+    if (mode == 3 && n_classes > 1 && !s->has_kd_tex) {
         k_shade_classes<4><<<std::max(1, std::min((n_upper + 127) / 128 + 4, (dev_ctx(s->device) ? dev_ctx(s->device)->sm_count : 148) * 16)), 128, 0, st>>>(s->dev, W, cur);
         ++launches;
     } else {
         // the main stream's class first: the joins of the other streams (enqueued by launch_shade_class) must come after it
         for (int pass = 0; pass < 2; ++pass) {
             const bool main_pass = pass == 0;
-            if ((s->material_classes & (1u << B200PT_MAT_MATTE)) && (cs[0] == st) == main_pass) { launch_shade_class<kKmMatte>(s, W, cur, n_upper, 1, blocks[0], cs[0]); ++launches; }
-            if ((s->material_classes & (1u << B200PT_MAT_PLASTIC)) && (cs[1] == st) == main_pass) { launch_shade_class<kKmPlastic>(s, W, cur, n_upper, 2, blocks[1], cs[1]); ++launches; }
+            if ((s->material_classes & (1u << B200PT_MAT_MATTE)) && (cs[0] == st) == main_pass) {
+                if (s->has_kd_tex) launch_shade_class<kKmMatte | KM_TEX>(s, W, cur, n_upper, 1, blocks[0], cs[0]);
+                else launch_shade_class<kKmMatte>(s, W, cur, n_upper, 1, blocks[0], cs[0]);
+                ++launches;
+            }
+            if ((s->material_classes & (1u << B200PT_MAT_PLASTIC)) && (cs[1] == st) == main_pass) {
+                if (s->has_kd_tex) launch_shade_class<kKmPlastic | KM_TEX>(s, W, cur, n_upper, 2, blocks[1], cs[1]);
+                else launch_shade_class<kKmPlastic>(s, W, cur, n_upper, 2, blocks[1], cs[1]);
+                ++launches;
+            }
             if ((s->material_classes & (1u << B200PT_MAT_GLASS)) && (cs[2] == st) == main_pass) { launch_shade_class<kKmGlass>(s, W, cur, n_upper, 3, blocks[2], cs[2]); ++launches; }
             if ((s->material_classes & (1u << B200PT_MAT_METAL)) && (cs[3] == st) == main_pass) { launch_shade_class<kKmMetal>(s, W, cur, n_upper, 4, blocks[3], cs[3]); ++launches; }
         }
@@ -1507,9 +1533,57 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         if ((rc = dev_upload(s, vs, &D.prim_s))) return fail(rc);
     }
 
+    // Textured "Kd" (matte / plastic): the material's lobes are built with a placeholder Kd so that the diffuse lobe exists
+    // as lobe 0; the shade kernels put the texture's value in per intersection (wavefront.cuh: textured_material).
+    std::vector<int> kd_tex((size_t)std::max(1, d->n_materials), -1);
+    bool closedform_tex = false;
+    if (d->material_kd_tex && d->spectrum_textures && d->n_spectrum_textures > 0) {
+        bool specular_material = false;
+        for (int i = 0; i < d->n_materials; ++i) {
+            const b200pt_material& m = d->materials[i];
+            if (m.type == B200PT_MAT_GLASS && m.urough == 0.0f && m.vrough == 0.0f) specular_material = true;
+            const int t = d->material_kd_tex[i];
+            if (t < 0 || (m.type != B200PT_MAT_MATTE && m.type != B200PT_MAT_PLASTIC)) continue;
+            if (t >= d->n_spectrum_textures) { b200pt_set_error("b200pt_scene_create: material_kd_tex index out of range"); return fail(B200PT_ERR_INVALID); }
+            const b200pt_spectrum_texture& T = d->spectrum_textures[t];
+            if (T.type != B200PT_STEX_CONSTANT && T.type != B200PT_STEX_CHECKERBOARD) { b200pt_set_error("b200pt_scene_create: unknown spectrum texture type (constant, checkerboard)"); return fail(B200PT_ERR_UNSUPPORTED); }
+            kd_tex[(size_t)i] = t;
+            s->has_kd_tex = true;
+            if (T.type == B200PT_STEX_CHECKERBOARD && T.aa_closedform) closedform_tex = true;
+        }
+        if (closedform_tex && specular_material && d->integrator.type != B200PT_INTEGRATOR_PATH) {
+            // specular_reflect / specular_transmit hand differentials to their children (sampler_integrator.rs:108-125, 170-205)
+            b200pt_set_error("b200pt_scene_create: whitted / directlighting with a closedform checkerboard and a specular material: ray differentials of specular children are not on this path (use \"aamode\" \"none\")");
+            return fail(B200PT_ERR_UNSUPPORTED);
+        }
+    }
     std::vector<DMaterial> mats;
-    for (int i = 0; i < d->n_materials; ++i) mats.push_back(make_material(d->materials[i], d->integrator.type == B200PT_INTEGRATOR_PATH));
+    for (int i = 0; i < d->n_materials; ++i) {
+        b200pt_material m = d->materials[i];
+        if (kd_tex[(size_t)i] >= 0) m.kd[0] = m.kd[1] = m.kd[2] = 1.0f;
+        mats.push_back(make_material(m, d->integrator.type == B200PT_INTEGRATOR_PATH));
+    }
     if ((rc = dev_upload(s, mats, &D.materials))) return fail(rc);
+    if (s->has_kd_tex) {
+        std::vector<DSpecTex> st((size_t)d->n_spectrum_textures);
+        for (int k = 0; k < d->n_spectrum_textures; ++k) {
+            const b200pt_spectrum_texture& T = d->spectrum_textures[k];
+            DSpecTex& o = st[(size_t)k];
+            o.type = T.type; o.su = T.su; o.sv = T.sv; o.du = T.du; o.dv = T.dv; o.closedform = T.aa_closedform ? 1 : 0;
+            std::memcpy(o.tex1, T.tex1, 12); std::memcpy(o.tex2, T.tex2, 12);
+        }
+        std::vector<float> uv6((size_t)d->n_prims * 6);
+        for (int64_t i = 0; i < d->n_prims; ++i) {
+            const bool has = d->tri_uvs && d->prim_flags && (d->prim_flags[i] & B200PT_PRIM_HAS_UV);
+            static const float dflt[6] = {0.0f, 0.0f, 1.0f, 0.0f, 1.0f, 1.0f};  // triangle.rs:384-394
+            std::memcpy(&uv6[(size_t)i * 6], has ? d->tri_uvs + 6 * i : dflt, 24);
+        }
+        if ((rc = dev_upload(s, kd_tex, &D.mat_kd_tex))) return fail(rc);
+        if ((rc = dev_upload(s, st, &D.spec_tex))) return fail(rc);
+        if ((rc = dev_upload(s, uv6, &D.prim_uv6))) return fail(rc);
+        s->needs_cam_diff = closedform_tex;
+        D.cam_diff_scale = 1.0f / std::sqrt((float)s->spp);
+    }
 
     // Scene::new (core/src/scene.rs:50-77): world bound, infinite lights, Light::preprocess
     V3 wc = mk(0, 0, 0);

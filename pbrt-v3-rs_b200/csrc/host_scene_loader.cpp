@@ -330,6 +330,8 @@ struct Loaded {
     std::vector<uint32_t> sobol;        // SOBOL_MATRICES_32 when the scene asks for the sobol sampler
     std::vector<b200pt_float_texture> float_textures;  // Texture "name" "float" ... used as alpha masks
     std::vector<int32_t> alpha_tex;     // 2 per triangle (top-level triangles first, then the objects')
+    std::vector<b200pt_spectrum_texture> spectrum_textures;  // Texture "name" "spectrum" | "color" ... used as a material's Kd
+    std::vector<int32_t> material_kd_tex;  // per material: index into spectrum_textures or -1
     std::vector<uint8_t> noise_perm;    // NOISE_PERM[0..256) when a "dots" texture is used
     std::vector<ObjectDef> objects;
     std::vector<b200pt_object> object_descs;
@@ -475,6 +477,7 @@ struct GState {
     float area_L[3] = {1, 1, 1};
     bool area_two_sided = false;
     std::map<std::string, int> float_textures;  // GraphicsState::float_textures: name -> index into Loaded::float_textures (scoped by Attribute blocks)
+    std::map<std::string, int> spectrum_textures;  // GraphicsState::spectrum_textures, likewise
 };
 
 struct Builder {
@@ -501,8 +504,16 @@ struct Builder {
 
     static const int kNoMaterial = -2;  // gs.material: -1 = the default matte (not created yet), kNoMaterial = Material "none"
     int make_material(const std::string& type, const ParamSet& p) {
-        for (const char* t : {"Kd", "Ks", "Kr", "Kt", "eta", "k", "sigma", "roughness", "uroughness", "vroughness", "index", "bumpmap"})
-            if (p.has_texture(t)) throw Unsupported(std::string("material parameter \"texture ") + t + "\": textures are outside this path (constant values only)");
+        for (const char* t : {"Ks", "Kr", "Kt", "eta", "k", "sigma", "roughness", "uroughness", "vroughness", "index", "bumpmap"})
+            if (p.has_texture(t)) throw Unsupported(std::string("material parameter \"texture ") + t + "\": textures are outside this path (constant values, and a textured Kd)");
+        // "texture Kd": TextureParams::get_spectrum_texture_or_else looks the name up among the spectrum textures in scope
+        // (an unknown name falls back to the constant parameter / default, texture_params.rs)
+        int kd_tex = -1;
+        if (p.has_texture("Kd")) {
+            if (type != "matte" && type != "plastic") throw Unsupported("\"texture Kd\" on Material \"" + type + "\" is outside this path");
+            auto it = gs.spectrum_textures.find(p.one_texture("Kd"));
+            if (it != gs.spectrum_textures.end()) kd_tex = it->second;
+        }
         b200pt_material m;
         std::memset(&m, 0, sizeof(m));
         m.remap_roughness = p.one_bool("remaproughness", true) ? 1 : 0;
@@ -536,7 +547,12 @@ struct Builder {
             m.urough = p.find("uroughness", "float") ? p.one_float("uroughness", r) : r;
             m.vrough = p.find("vroughness", "float") ? p.one_float("vroughness", r) : r;
         } else throw Unsupported("Material \"" + type + "\" is outside this path (matte, plastic, glass, metal)");
+        if (kd_tex >= 0 && L->spectrum_textures[(size_t)kd_tex].type == B200PT_STEX_CONSTANT) {  // a constant texture is just the value
+            fill_rgb(m.kd, L->spectrum_textures[(size_t)kd_tex].tex1);
+            kd_tex = -1;
+        }
         L->materials.push_back(m);
+        L->material_kd_tex.push_back(kd_tex);
         return (int)L->materials.size() - 1;
     }
     int current_material() {  // index into materials, or -1 for a primitive without a material
@@ -550,8 +566,43 @@ struct Builder {
     // Texture "name" "float" "class": the float textures a mesh can use as alpha / shadowalpha (api/src/lib.rs pbrt_texture ->
     // make_float_texture; textures/src/{constant,checkerboard_2d,dots,imagemap}.rs from-params).  Spectrum textures feed
     // materials, which take constants only on this path.
+    // Texture "name" "spectrum" | "color" "class": what a matte / plastic material can name as "texture Kd"
+    // (make_spectrum_texture; textures/src/{constant,checkerboard_2d}.rs from-params with constant tex1 / tex2).
+    void spectrum_texture(const std::string& name, const std::string& cls, const ParamSet& p) {
+        b200pt_spectrum_texture t;
+        std::memset(&t, 0, sizeof(t));
+        auto const_or_named = [&](const char* pn, float dflt, float out[3]) {  // get_spectrum_texture_or_else with constant sub-textures
+            const std::string tn = p.one_texture(pn);
+            if (!tn.empty()) {
+                auto it = gs.spectrum_textures.find(tn);
+                if (it != gs.spectrum_textures.end()) {
+                    const b200pt_spectrum_texture& s = L->spectrum_textures[(size_t)it->second];
+                    if (s.type != B200PT_STEX_CONSTANT) throw Unsupported("Texture \"" + name + "\": nested non-constant textures are outside this path");
+                    fill_rgb(out, s.tex1);
+                    return;
+                }
+            }
+            const float d[3] = {dflt, dflt, dflt};
+            p.one_rgb(pn, d, out);
+        };
+        t.su = t.sv = 1.0f;
+        if (cls == "constant") { t.type = B200PT_STEX_CONSTANT; const_or_named("value", 1.0f, t.tex1); }
+        else if (cls == "checkerboard") {
+            if (p.one_int("dimension", 2) != 2) throw Unsupported("Texture \"" + name + "\": 3-D checkerboards are outside this path");
+            const std::string mapping = p.one_string("mapping", "uv");
+            if (mapping != "uv") throw Unsupported("Texture \"" + name + "\": mapping \"" + mapping + "\" is outside this path (uv)");
+            t.type = B200PT_STEX_CHECKERBOARD;
+            t.su = p.one_float("uscale", 1.0f); t.sv = p.one_float("vscale", 1.0f); t.du = p.one_float("udelta", 0.0f); t.dv = p.one_float("vdelta", 0.0f);
+            const_or_named("tex1", 1.0f, t.tex1); const_or_named("tex2", 0.0f, t.tex2);
+            t.aa_closedform = p.one_string("aamode", "closedform") == "none" ? 0 : 1;  // anything else warns and means closedform (checkerboard_2d.rs:134-145)
+        } else throw Unsupported("Texture \"" + name + "\" \"spectrum\" \"" + cls + "\" is outside this path (constant, checkerboard)");
+        L->spectrum_textures.push_back(t);
+        gs.spectrum_textures[name] = (int)L->spectrum_textures.size() - 1;
+    }
+
     void texture(const std::string& name, const std::string& type, const std::string& cls, const ParamSet& p) {
-        if (type != "float") throw Unsupported("Texture \"" + name + "\" \"" + type + "\": only float textures (alpha masks) are on this path");
+        if (type == "spectrum" || type == "color") { spectrum_texture(name, cls, p); return; }
+        if (type != "float") throw Unsupported("Texture \"" + name + "\" \"" + type + "\": only float, spectrum and color textures exist");
         b200pt_float_texture t;
         std::memset(&t, 0, sizeof(t));
         if (cls != "constant") {
@@ -948,6 +999,14 @@ void Builder::finish() {
         L->material.insert(L->material.end(), o.material.begin(), o.material.end());
         L->light.insert(L->light.end(), o.flags.size(), -1);
         L->alpha_tex.insert(L->alpha_tex.end(), o.alpha_tex.begin(), o.alpha_tex.end());
+    }
+    {
+        bool any_kd_tex = false;
+        for (int32_t k : L->material_kd_tex) any_kd_tex |= k >= 0;
+        if (any_kd_tex) {
+            d.spectrum_textures = L->spectrum_textures.data(); d.n_spectrum_textures = (int32_t)L->spectrum_textures.size();
+            d.material_kd_tex = L->material_kd_tex.data();
+        }
     }
     if (!L->float_textures.empty()) {
         d.float_textures = L->float_textures.data(); d.n_float_textures = (int32_t)L->float_textures.size();

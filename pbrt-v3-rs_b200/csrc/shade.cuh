@@ -181,7 +181,8 @@ enum : int { BX_LAMBERT = 0, BX_OREN_NAYAR = 1, BX_MF_REFL = 2, BX_MF_TRANS = 3,
 // Compile-time lobe masks: the shade stage runs one kernel per material class after the sort, and each only carries the
 // code of the lobes its material can produce (bit k = BxDF kind k may occur; KM_COND / KM_DIEL = which Fresnel term a
 // microfacet reflection may use).  KM_ALL keeps every branch (tree integrators, explicit li batches).
-enum : uint32_t { KM_COND = 1u << 8, KM_DIEL = 1u << 9, KM_ALL = 0x7fu | KM_COND | KM_DIEL };
+// KM_TEX: the material's "Kd" may be a spectrum texture evaluated per intersection (spectrum_tex.cuh).
+enum : uint32_t { KM_COND = 1u << 8, KM_DIEL = 1u << 9, KM_TEX = 1u << 10, KM_ALL = 0x7fu | KM_COND | KM_DIEL | KM_TEX };
 template <uint32_t KM> B2_D bool km_is(int kind, int k) { return ((KM >> k) & 1u) && ((KM & 0x7fu) == (1u << k) || kind == k); }
 
 // One lobe with every per-material constant already evaluated on the host

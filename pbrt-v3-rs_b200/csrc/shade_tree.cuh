@@ -87,6 +87,15 @@ __global__ void __launch_bounds__(128) k_shade_tree(DeviceScene S, Wave W, int c
         bsdf.ss = normalize(sh.dpdu);
         bsdf.ts = cross(bsdf.ns, bsdf.ss);
         bsdf.m = S.materials + hc.mat;  // built with allow_multiple_lobes = false (whitted.rs:76, direct_lighting.rs:91)
+        DMaterial tex_mat;
+        if (S.mat_kd_tex) {  // textured Kd: the camera ray (depth 0) carries differentials; scenes whose specular children would need
+                             // them (closedform checkerboard + glass) are refused at b200pt_scene_create
+            const int tex = S.mat_kd_tex[hc.mat];
+            if (tex >= 0) {
+                textured_material(S, W, slot, prim, hit, hb2, sh, tex, (depth == 0 && W.cam_diff) ? W.cam_diff + 3ll * pid : nullptr, S.materials[hc.mat], &tex_mat);
+                bsdf.m = &tex_mat;
+            }
+        }
         RGB le = rgb1(0.0f);
         if (hc.alight >= 0) le = area_l(S.lights[hc.alight], sh.n, wo);  // isect.le(&wo)
         int rec = -1, n_real_sh = 0, n_real_mis = 0;

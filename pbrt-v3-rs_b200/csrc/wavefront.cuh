@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "instancing.cuh"
 #include "shade.cuh"
+#include "spectrum_tex.cuh"
 
 namespace b2 {
 
@@ -16,6 +17,12 @@ struct DeviceScene {
     const float* prim_n;       // optional (meshes with N): 9 floats per ORIGINAL primitive
     const float* prim_s;       // optional (meshes with S): 9 floats per ORIGINAL primitive
     const DMaterial* materials;
+    // textured "Kd" (null / unused when the scene has none): per material the spectrum-texture index or -1, the textures,
+    // and 6 floats of uv per ORIGINAL primitive (defaults (0,0) (1,0) (1,1) filled in for meshes without uvs)
+    const int* mat_kd_tex;
+    const DSpecTex* spec_tex;
+    const float* prim_uv6;
+    float cam_diff_scale;  // 1 / sqrt(samples per pixel): Ray::scale_differentials in render_tile (sampler_integrator.rs:358)
     const DLight* lights;
     const int* infinite_lights;
     const DInfDistr* inf_distr;
@@ -66,7 +73,8 @@ struct Wave {
     float4* L;          // rgb, -
     float4* beta;       // rgb, eta_scale
     unsigned long long* hidx;
-    int* meta;          // dim (16) | bounces (8) | specular flag (8)
+    int* meta;          // dim (16) | bounces (8) | specular flag (bit 24) | the ray is no camera ray any more: no differentials (bit 25)
+    float4* cam_diff;   // 3 float4 per path: the camera ray's scaled differentials (null unless a closedform checkerboard needs them)
     // pending direct lighting, per path
     float4* pend_a;     // ld_light rgb, pick pdf
     float4* pend_b;     // mis f rgb, mis weight
@@ -197,6 +205,29 @@ B2_D void surface_at(const DeviceScene& S, const Wave& W, int slot, uint32_t pri
     out->mat = mat;
     out->alight = alight;
     out->pflags = pflags;
+}
+
+// Material::compute_scattering_functions of a matte / plastic material whose "Kd" is spectrum texture `tex`
+// (matte.rs:63-72, plastic.rs:81-84): kd = texture(si).clamp(); the diffuse lobe - always lobe 0 of `base`, which the host
+// builds with a placeholder Kd - takes it, or is left out when it is black.  diff = the path's camera differentials or null.
+B2_D void textured_material(const DeviceScene& S, const Wave& W, int slot, uint32_t prim, float4 hit, float hb2, const SurfHit& sh, int tex, const float4* diff,
+                            const DMaterial& base, DMaterial* out) {
+    V3 p0, p1, p2;
+    int mat_unused, light_unused;
+    uint32_t pflags;
+    load_prim(S, prim, &p0, &p1, &p2, &mat_unused, &light_unused, &pflags);
+    const float4 duv = (S.prim_duv && (pflags & B200PT_PRIM_HAS_UV)) ? ldg4(S.prim_duv + prim) : default_duv();
+    const int inst = S.instances ? W.hit_inst[slot] : -1;
+    const float* i2w = (inst >= 0 && !S.instances[inst].identity) ? S.instances[inst].i2w : nullptr;
+    RGB kd = kd_texture_eval(S.spec_tex + tex, S.prim_uv6 + 6ll * prim, hit.z, hit.w, hb2, p0, p1, p2, duv, i2w, sh.p, sh.n, diff);
+    kd = rgb(clamp0inf(kd.r), clamp0inf(kd.g), clamp0inf(kd.b));  // Spectrum::clamp_default
+    *out = base;
+    if (is_black(kd)) {  // `if !r.is_black()`: no diffuse lobe
+        out->n_bxdf = base.n_bxdf - 1;
+        out->bx[0] = base.bx[1];
+    } else {
+        out->bx[0].r[0] = kd.r; out->bx[0].r[1] = kd.g; out->bx[0].r[2] = kd.b;
+    }
 }
 
 // Light::sample_li for the three light kinds of this path (point.rs:83-94, diffuse.rs:114-129 over Triangle::sample

@@ -136,6 +136,7 @@ class SceneDescription:
         self.prim_flags = np.zeros(0, dtype=np.uint32)
         self.prim_alpha_tex = np.zeros((0, 2), dtype=np.int32)  # per primitive: alpha / shadowalpha float-texture index or -1
         self.float_textures = []  # dicts, see add_float_texture
+        self.spectrum_textures = []  # dicts, see add_spectrum_texture
         self.materials = []   # list of dicts
         self.lights = []      # list of dicts
         self.camera = dict(eye=(0, 0, -5), look=(0, 0, 0), up=(0, 1, 0), fov=45.0, lensradius=0.0, focaldistance=1e6,
@@ -177,6 +178,14 @@ class SceneDescription:
         assert type in ("constant", "checkerboard", "dots", "imagemap")
         self.float_textures.append(dict(type=type, **params))
         return len(self.float_textures) - 1
+
+    def add_spectrum_texture(self, type, **params):
+        """Texture "name" "spectrum" "<type>" for use as a matte / plastic material's Kd (``Kd=("texture", index)``): type
+        "constant" (value) or "checkerboard" (tex1, tex2 - RGB constants -, uscale, vscale, udelta, vdelta, aamode
+        "closedform" | "none"; textures/src/checkerboard_2d.rs).  Returns its index."""
+        assert type in ("constant", "checkerboard")
+        self.spectrum_textures.append(dict(type=type, **params))
+        return len(self.spectrum_textures) - 1
 
     def _alpha_pair(self, alpha, shadowalpha):
         """(constant alpha, constant shadowalpha, texture index pair): a texture index is given as ("texture", k)."""
@@ -348,9 +357,13 @@ class SceneDescription:
         d.instances, d.n_instances = C.cast(insts, C.c_void_p), len(self.instances)
 
         mats = (Material * max(1, len(self.materials)))()
+        kd_tex = np.full(max(1, len(self.materials)), -1, dtype=np.int32)
         for i, m in enumerate(self.materials):
             t = m["type"]
             M = mats[i]
+            if isinstance(m.get("Kd"), tuple) and len(m["Kd"]) == 2 and m["Kd"][0] == "texture":
+                kd_tex[i] = int(m["Kd"][1])
+                m = dict(m, Kd=(0.5, 0.5, 0.5) if t == "matte" else (0.25, 0.25, 0.25))
             M.remap_roughness = 1 if m.get("remaproughness", True) else 0
             if t == "matte":     # materials/src/matte.rs:77-84
                 M.type = MAT_MATTE
@@ -377,6 +390,11 @@ class SceneDescription:
                 raise ValueError("material %r is outside this path" % t)
         keep.append(mats)
         d.materials, d.n_materials = C.cast(mats, C.c_void_p), len(self.materials)
+        if self.spectrum_textures and (kd_tex >= 0).any():
+            from . import spectrum_texture_array
+            d.spectrum_textures = C.cast(spectrum_texture_array(self.spectrum_textures, keep), C.c_void_p)
+            d.n_spectrum_textures = len(self.spectrum_textures)
+            d.material_kd_tex = arr(kd_tex, np.int32)
 
         lights = (Light * max(1, len(self.lights)))()
         ident = np.eye(4, dtype=F32).reshape(-1)

@@ -56,6 +56,8 @@ def lib():
         L.orc_accel_set_alpha.argtypes = [vp, vp, C.c_int, vp, vp, i64]
         L.orc_float_texture_evaluate.argtypes = [vp, vp, C.c_float, C.c_float]
         L.orc_float_texture_evaluate.restype = C.c_float
+        L.orc_spectrum_texture_evaluate.argtypes = [vp, C.c_float, C.c_float, vp, vp]
+        L.orc_spectrum_texture_evaluate.restype = None
         L.orc_noise_3d.argtypes = [vp, C.c_float, C.c_float, C.c_float]
         L.orc_noise_3d.restype = C.c_float
         L.orc_envmap_prepare.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]

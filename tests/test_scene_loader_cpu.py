@@ -196,7 +196,7 @@ def test_ply_variants_pfm_roundtrip_and_transform_stack(tmp_path, pkg):
     (tmp_path / "u.pbrt").write_text('Integrator "bdpt"\nWorldBegin\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n')
     with pytest.raises(pkg.B200PTError, match="bdpt"):
         pkg.load_pbrt(str(tmp_path / "u.pbrt"))
-    (tmp_path / "t.pbrt").write_text('WorldBegin\nTexture "x" "spectrum" "constant"\nWorldEnd\n')  # float textures are alpha masks (test_alpha_textures.py); spectrum textures feed materials: out of scope
+    (tmp_path / "t.pbrt").write_text('WorldBegin\nTexture "x" "spectrum" "marble"\nWorldEnd\n')  # spectrum textures: constant and checkerboard only (test_spectrum_textures.py)
     with pytest.raises(pkg.B200PTError, match="Texture"):
         pkg.load_pbrt(str(tmp_path / "t.pbrt"))
     (tmp_path / "sph.pbrt").write_text('WorldBegin\nShape "sphere"\nWorldEnd\n')

@@ -89,8 +89,11 @@ typedef struct b200pt_material {
 
 /* lights/src/{point,diffuse,infinite}.rs */
 enum { B200PT_LIGHT_POINT = 0, B200PT_LIGHT_AREA = 1, B200PT_LIGHT_INFINITE = 2,
-       B200PT_LIGHT_DISTANT = 3 /* lights/src/distant.rs: pos = w_light, the NORMALISED world-space direction TOWARDS the light
-                                  * (light_to_world.transform_vector(from - to).normalize(), distant.rs:50-52), L = L * scale */ };
+       B200PT_LIGHT_DISTANT = 3, /* lights/src/distant.rs: pos = w_light, the NORMALISED world-space direction TOWARDS the light
+                                   * (light_to_world.transform_vector(from - to).normalize(), distant.rs:50-52), L = L * scale */
+       B200PT_LIGHT_SPOT = 4 /* lights/src/spot.rs: pos = p_light = light_to_world(0), L = I * scale, world_to_light = the inverse of
+                              * ctm * Translate(from) * dir_to_z^-1 (spot.rs:209-226), cos_total_width / cos_falloff_start =
+                              * cos(radians(coneangle)), cos(radians(coneangle - conedeltaangle)) (spot.rs:57-58) */ };
 typedef struct b200pt_light {
     int32_t type;
     float pos[3];             /* point: p_light (world) */
@@ -104,6 +107,7 @@ typedef struct b200pt_light {
      * (the reference then uses the 1x1 image [L]). */
     const float* map_rgb;
     int32_t map_width, map_height;
+    float cos_total_width, cos_falloff_start; /* spot */
 } b200pt_light;
 
 /* cameras/src/perspective_camera.rs + core/src/camera.rs:276-306: the two

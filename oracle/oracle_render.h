@@ -569,6 +569,7 @@ inline RGB light_power(const RenderScene& sc, int li) {
     const b200pt_light& l = sc.lights[li];
     if (l.type == B200PT_LIGHT_POINT) return kFourPi * light_L(l);
     if (l.type == B200PT_LIGHT_DISTANT) return light_L(l) * kPi * sc.world_radius * sc.world_radius;  // distant.rs:92-95
+    if (l.type == B200PT_LIGHT_SPOT) return light_L(l) * kTwoPi * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width));  // spot.rs:109-111
     if (l.type == B200PT_LIGHT_AREA) {
         Float s = l.two_sided ? 2.0f : 1.0f;
         return s * light_L(l) * sc.light_area[li] * kPi;
@@ -941,6 +942,23 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
         r.valid = true;
         return r;
     }
+    if (l.type == B200PT_LIGHT_SPOT) {  // spot.rs:97-107 with falloff(), :62-76
+        V3 pl(l.pos[0], l.pos[1], l.pos[2]);
+        r.wi = normalize(pl - hit.p);
+        r.pdf = 1.0f;
+        r.p1 = pl;
+        V3 wl = normalize(xf_vector(m4_from(l.world_to_light), -r.wi));
+        Float cos_theta = wl.z, falloff;
+        if (cos_theta < l.cos_total_width) falloff = 0.0f;
+        else if (cos_theta >= l.cos_falloff_start) falloff = 1.0f;
+        else {
+            Float delta = (cos_theta - l.cos_total_width) / (l.cos_falloff_start - l.cos_total_width);
+            falloff = (delta * delta) * (delta * delta);
+        }
+        r.value = light_L(l) * falloff / distance_squared(pl, hit.p);
+        r.valid = true;
+        return r;
+    }
     if (l.type == B200PT_LIGHT_DISTANT) {  // distant.rs:81-90
         r.wi = V3(l.pos[0], l.pos[1], l.pos[2]);
         r.pdf = 1.0f;
@@ -1002,7 +1020,7 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
 // Light::pdf_li
 inline Float light_pdf_li(const RenderScene& sc, int li, const SurfHit& hit, V3 wi) {
     const b200pt_light& l = sc.lights[li];
-    if (l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT) return 0.0f;
+    if (l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT) return 0.0f;
     if (l.type == B200PT_LIGHT_AREA) {  // Shape::pdf_solid_angle, shape.rs:81-107
         Ray ray = spawn_ray(hit, wi);
         V3 p0 = sc.accel.vert(l.prim, 0), p1 = sc.accel.vert(l.prim, 1), p2 = sc.accel.vert(l.prim, 2);
@@ -1020,7 +1038,7 @@ inline Float light_pdf_li(const RenderScene& sc, int li, const SurfHit& hit, V3 
     if (sin_t == 0.0f) return 0.0f;
     return sc.inf_distr[li].pdf(P2(phi * kInvTwoPi, theta * kInvPi)) / (kTwoPi * kPi * sin_t);
 }
-inline bool light_is_delta(const b200pt_light& l) { return l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT; }  // DELTA_POSITION | DELTA_DIRECTION
+inline bool light_is_delta(const b200pt_light& l) { return l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT; }  // DELTA_POSITION | DELTA_DIRECTION
 
 // core/src/integrator/common.rs:146-299 (handle_media = false, specular = false)
 inline RGB estimate_direct(RenderScene& sc, const SurfHit& hit, const BSDF& bsdf, P2 u_scatter, int li, P2 u_light) {

@@ -1461,7 +1461,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     for (int i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type >= 0 && d->materials[i].type < 4) s->material_classes |= 1u << d->materials[i].type;
         else { b200pt_set_error("b200pt_scene_create: unknown material type"); delete sc; return B200PT_ERR_INVALID; }
-    for (int i = 0; i < d->n_lights; ++i) if (d->lights[i].type == B200PT_LIGHT_POINT || d->lights[i].type == B200PT_LIGHT_DISTANT) ++s->n_point_lights;  // delta lights
+    for (int i = 0; i < d->n_lights; ++i) if (d->lights[i].type == B200PT_LIGHT_POINT || d->lights[i].type == B200PT_LIGHT_DISTANT || d->lights[i].type == B200PT_LIGHT_SPOT) ++s->n_point_lights;  // delta lights
     auto fail = [&](int code) { b200pt_scene_destroy(sc); return code; };
     DeviceScene& D = s->dev;
     std::memset(&D, 0, sizeof(D));
@@ -1612,6 +1612,10 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
         RGB power = rgb1(0.0f);
         if (l.type == B200PT_LIGHT_POINT) power = kFourPi * Lr;  // point.rs:96-98
         else if (l.type == B200PT_LIGHT_DISTANT) power = Lr * kPi * radius * radius;  // distant.rs:92-95
+        else if (l.type == B200PT_LIGHT_SPOT) {  // spot.rs:109-111
+            power = Lr * (kPi * 2.0f) * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width));
+            o.area = l.cos_total_width; o.cos_falloff_start = l.cos_falloff_start;
+        }
         else if (l.type == B200PT_LIGHT_AREA) {
             if (l.prim < 0 || l.prim >= d->n_prims) { b200pt_set_error("b200pt_scene_create: area light primitive out of range"); return fail(B200PT_ERR_INVALID); }
             const float* v = d->tri_verts + 9 * (size_t)l.prim;

@@ -813,7 +813,35 @@ struct Builder {
             const float inv = 1.0f / len;  // Vector3::normalize = self / length = self * (1 / length)
             l.pos[0] = inv * w.x; l.pos[1] = inv * w.y; l.pos[2] = inv * w.z;
             std::memcpy(l.light_to_world, gs.ctm.m.m, 64); std::memcpy(l.world_to_light, gs.ctm.inv.m, 64);
-        } else throw Unsupported("LightSource \"" + name + "\" is outside this path (point, distant, infinite)");
+        } else if (name == "spot") {  // spot.rs:200-237 + SpotLight::new :44-60
+            l.type = B200PT_LIGHT_SPOT;
+            float I[3];
+            p.one_rgb("I", one, I);
+            for (int c = 0; c < 3; ++c) l.L[c] = I[c] * sc[c];
+            const float cone_angle = p.one_float("coneangle", 30.0f);
+            const float cone_delta = p.one_float("conedeltaangle", 5.0f);  // the reference reads "conedeltaangle" (pbrt-v3 scenes' "conedelta" is ignored, spot.rs:208)
+            V3 from = v3(0, 0, 0), to = v3(0, 0, 1);
+            if (const Param* q = p.find("from", "point", "point3")) if (q->nums.size() >= 3) from = v3(q->nums[0], q->nums[1], q->nums[2]);
+            if (const Param* q = p.find("to", "point", "point3")) if (q->nums.size() >= 3) to = v3(q->nums[0], q->nums[1], q->nums[2]);
+            V3 dir = v3(to.x - from.x, to.y - from.y, to.z - from.z);
+            const float dinv = 1.0f / std::sqrt(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);  // Vector3::normalize = self * (1 / length)
+            dir = v3(dir.x * dinv, dir.y * dinv, dir.z * dinv);
+            V3 du, dv;  // coordinate_system(&dir), coordinate_system.rs:12-20
+            if (std::fabs(dir.x) > std::fabs(dir.y)) { const float k = 1.0f / std::sqrt(dir.x * dir.x + dir.z * dir.z); du = v3(-dir.z * k, 0.0f * k, dir.x * k); }
+            else { const float k = 1.0f / std::sqrt(dir.y * dir.y + dir.z * dir.z); du = v3(0.0f * k, dir.z * k, -dir.y * k); }
+            dv = v3((dir.y * du.z) - (dir.z * du.y), (dir.z * du.x) - (dir.x * du.z), (dir.x * du.y) - (dir.y * du.x));
+            M4 dz = m4_identity();
+            dz.m[0][0] = du.x; dz.m[0][1] = du.y; dz.m[0][2] = du.z;
+            dz.m[1][0] = dv.x; dz.m[1][1] = dv.y; dz.m[1][2] = dv.z;
+            dz.m[2][0] = dir.x; dz.m[2][1] = dir.y; dz.m[2][2] = dir.z;
+            const Xf l2w = xf_mul(xf_mul(gs.ctm, xf_translate(from.x, from.y, from.z)), xf_inverse(xf_from(dz)));
+            const V3 pl = xf_point(l2w.m, v3(0, 0, 0));
+            l.pos[0] = pl.x; l.pos[1] = pl.y; l.pos[2] = pl.z;
+            std::memcpy(l.light_to_world, l2w.m.m, 64); std::memcpy(l.world_to_light, l2w.inv.m, 64);
+            const float rad = 3.14159265358979323846f / 180.0f;  // f32::to_radians
+            l.cos_total_width = std::cos(cone_angle * rad);
+            l.cos_falloff_start = std::cos((cone_angle - cone_delta) * rad);
+        } else throw Unsupported("LightSource \"" + name + "\" is outside this path (point, spot, distant, infinite)");
         L->lights.push_back(l);
     }
 

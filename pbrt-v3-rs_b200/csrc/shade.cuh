@@ -448,19 +448,19 @@ template <uint32_t KM = KM_ALL> B2_D BxDFSample bsdf_sample_f(const BSDF& b, V3 
 }
 
 // ---- lights -------------------------------------------------------------------------
-enum : int { LT_POINT = 0, LT_AREA = 1, LT_INFINITE = 2, LT_DISTANT = 3 };
-B2_D bool light_is_delta(int type) { return type == LT_POINT || type == LT_DISTANT; }  // light.rs: DELTA_POSITION | DELTA_DIRECTION
+enum : int { LT_POINT = 0, LT_AREA = 1, LT_INFINITE = 2, LT_DISTANT = 3, LT_SPOT = 4 };
+B2_D bool light_is_delta(int type) { return type == LT_POINT || type == LT_DISTANT || type == LT_SPOT; }  // light.rs: DELTA_POSITION | DELTA_DIRECTION
 struct DLight {
     int type;
     int prim;        // area: original primitive index
     int two_sided;
     int inf_slot;    // infinite: index into the DInfDistr table
     float pos[3];
-    float area;      // area: Triangle::area (host, f32)
+    float area;      // area: Triangle::area (host, f32); spot: cos_total_width
     float L[3];
-    float pad;
+    float cos_falloff_start;  // spot
     float l2w[9];    // infinite: upper 3x3 of light_to_world (row-major)
-    float w2l[9];
+    float w2l[9];    // infinite, spot: upper 3x3 of world_to_light
 };
 // Environment map of an InfiniteAreaLight (host_envmap.cpp): level 0 of its MIPMap (float4 texels already multiplied by
 // L; 1x1 without a "mapname") and the Distribution2D over the (2w x 2h) importance image (infinite.rs:326-369).

@@ -255,6 +255,24 @@ B2_D LightSample sample_light(const DeviceScene& S, const DLight& light, const S
         lp1 = pl;
         Li = ldrgb(light.L) / distance_squared(pl, sh.p);
         li_valid = true;
+    } else if (light.type == LT_SPOT) {  // spot.rs:97-107, falloff() :62-76
+        V3 pl = mk(light.pos[0], light.pos[1], light.pos[2]);
+        wi = normalize(pl - sh.p);
+        light_pdf = 1.0f;
+        lp1 = pl;
+        const V3 w = -wi;
+        const float* m = light.w2l;
+        const V3 wl = normalize(mk(m[0] * w.x + m[1] * w.y + m[2] * w.z, m[3] * w.x + m[4] * w.y + m[5] * w.z, m[6] * w.x + m[7] * w.y + m[8] * w.z));
+        const float cos_theta = wl.z, cos_total = light.area, cos_start = light.cos_falloff_start;
+        float falloff;
+        if (cos_theta < cos_total) falloff = 0.0f;
+        else if (cos_theta >= cos_start) falloff = 1.0f;
+        else {
+            const float delta = (cos_theta - cos_total) / (cos_start - cos_total);
+            falloff = (delta * delta) * (delta * delta);
+        }
+        Li = ldrgb(light.L) * falloff / distance_squared(pl, sh.p);
+        li_valid = true;
     } else if (light.type == LT_DISTANT) {  // distant.rs:81-90: p_outside = p + w_light * (2 * world_radius), pdf 1
         wi = mk(light.pos[0], light.pos[1], light.pos[2]);
         light_pdf = 1.0f;

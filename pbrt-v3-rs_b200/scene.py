@@ -231,6 +231,34 @@ class SceneDescription:
     def add_point_light(self, pos, I):
         self.lights.append(dict(type="point", pos=tuple(pos), L=tuple(I)))
 
+    def add_spot_light(self, I, p_from, p_to, coneangle=30.0, conedeltaangle=5.0):
+        """LightSource "spot" (lights/src/spot.rs) under an identity CTM: intensity ``I`` from ``p_from`` towards ``p_to``,
+        full intensity inside coneangle - conedeltaangle degrees, falling to zero at coneangle.  world_to_light's vector part
+        is the dir_to_z rotation (rows du, dv, dir of coordinate_system(dir), spot.rs:213-224); the cosines are libm's cosf
+        of f32 radians, as the reference's f32::cos."""
+        f, t = np.asarray(p_from, dtype=F32), np.asarray(p_to, dtype=F32)
+        d = (t - f).astype(F32)
+        d = (d * (F32(1.0) / np.sqrt(F32(F32(d[0] * d[0]) + F32(d[1] * d[1])) + F32(d[2] * d[2]), dtype=F32))).astype(F32)
+        if abs(d[0]) > abs(d[1]):
+            k = F32(1.0) / np.sqrt(F32(d[0] * d[0]) + F32(d[2] * d[2]), dtype=F32)
+            du = np.array([-d[2] * k, F32(0.0) * k, d[0] * k], dtype=F32)
+        else:
+            k = F32(1.0) / np.sqrt(F32(d[1] * d[1]) + F32(d[2] * d[2]), dtype=F32)
+            du = np.array([F32(0.0) * k, d[2] * k, -d[1] * k], dtype=F32)
+        dv = np.array([F32(d[1] * du[2]) - F32(d[2] * du[1]), F32(d[2] * du[0]) - F32(d[0] * du[2]), F32(d[0] * du[1]) - F32(d[1] * du[0])], dtype=F32)
+        w2l = np.eye(4, dtype=F32)
+        w2l[0, :3], w2l[1, :3], w2l[2, :3] = du, dv, d
+        for r in range(3):  # dir_to_z * Translate(-from) (Transform::mul keeps the product of the stored inverses)
+            w2l[r, 3] = F32(F32(F32(F32(w2l[r, 0] * -f[0]) + F32(w2l[r, 1] * -f[1])) + F32(w2l[r, 2] * -f[2])) + F32(0.0))
+        l2w = np.eye(4, dtype=F32)
+        l2w[:3, :3] = w2l[:3, :3].T
+        l2w[:3, 3] = f
+        cosf = C.CDLL("libm.so.6").cosf
+        cosf.restype, cosf.argtypes = C.c_float, [C.c_float]
+        rad = F32(3.14159265358979323846) / F32(180.0)
+        self.lights.append(dict(type="spot", L=tuple(I), pos=tuple(float(c) for c in f), light_to_world=l2w.reshape(-1), world_to_light=w2l.reshape(-1),
+                                cos_total_width=cosf(float(F32(coneangle) * rad)), cos_falloff_start=cosf(float(F32(F32(coneangle) - F32(conedeltaangle)) * rad))))
+
     def add_distant_light(self, L, w_light):
         """LightSource "distant" (lights/src/distant.rs): radiance ``L`` arriving from direction ``w_light`` (towards the
         light, world space; normalised here the way Vector3::normalize does: v * (1 / |v|))."""
@@ -292,7 +320,7 @@ class SceneDescription:
 
     def to_desc(self):
         from . import Camera, Film, Integrator, Light, Material, Sampler, SceneDesc
-        from . import (DIRECT_ALL, DIRECT_ONE, INTEGRATOR_DIRECT, INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_DISTANT, LIGHT_INFINITE, LIGHT_POINT, LIGHTS_POWER, LIGHTS_SPATIAL, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
+        from . import (DIRECT_ALL, DIRECT_ONE, INTEGRATOR_DIRECT, INTEGRATOR_PATH, INTEGRATOR_WHITTED, LIGHT_AREA, LIGHT_DISTANT, LIGHT_INFINITE, LIGHT_POINT, LIGHT_SPOT, LIGHTS_POWER, LIGHTS_SPATIAL, LIGHTS_UNIFORM, MAT_GLASS, MAT_MATTE, MAT_METAL,
                        MAT_PLASTIC, SAMPLER_HALTON, SAMPLER_SOBOL, SAMPLER_ZEROTWO)
         if self.nodes is None:
             self.build_accel(None)
@@ -410,6 +438,10 @@ class SceneDescription:
             elif l["type"] == "distant":
                 Lt.type = LIGHT_DISTANT
                 Lt.pos[:] = l["pos"]
+            elif l["type"] == "spot":
+                Lt.type = LIGHT_SPOT
+                Lt.pos[:] = l["pos"]
+                Lt.cos_total_width, Lt.cos_falloff_start = l["cos_total_width"], l["cos_falloff_start"]
             elif l["type"] == "diffuse":
                 Lt.type = LIGHT_AREA
                 Lt.prim = l["prim"]

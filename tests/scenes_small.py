@@ -17,6 +17,10 @@ def one_material_scene(wl, mat, light="infinite", res=24, spp=8, maxdepth=5, nu=
         sd.add_infinite_light((1.2, 1.2, 1.1))
     if light in ("point", "all"):
         sd.add_point_light((1.5, 3.0, -3.0), (30, 30, 30))
+    if light in ("spot", "all+spot"):
+        sd.add_spot_light((40, 38, 35), (1.0, 3.0, -2.0), (0.0, -0.5, 0.0), coneangle=28.0, conedeltaangle=12.0)
+    if light == "all+spot":
+        light = "all"
     if light in ("distant", "all+distant"):
         sd.add_distant_light((2.5, 2.4, 2.2), (-0.4, 1.0, -0.6))
     if light == "all+distant":

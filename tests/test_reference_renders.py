@@ -1,12 +1,12 @@
 """Execution-level pin of the oracle - and of the CUDA path - to the reference: its own committed renders.
 
 The reference cannot be built here or on the GPU box (no Rust toolchain, profiles/r2_toolchain_probe.txt), but its tree
-holds images it rendered itself.  Six of the shipped scenes lie entirely on this path:
+holds images it rendered itself.  Seven of the shipped scenes lie entirely on this path:
 
-  scenes/lights/{point, distant, infinite-no-map}.pbrt, scenes/shapes/triangles-alpha-mask.pbrt,
+  scenes/lights/{point, spot, distant, infinite-no-map}.pbrt, scenes/shapes/triangles-alpha-mask.pbrt,
   scenes/cameras/perspective.pbrt, scenes/objects/instances.pbrt
   (Whitted, Halton 128 spp, 400x400, box filter, a matte cube - or ten ObjectInstances of it - over a ground quad with a
-  checkerboard "Kd" texture, point / distant (blackbody) / infinite lights, a "dots" alpha mask)
+  checkerboard "Kd" texture, point / spot / distant (blackbody) / infinite lights, a "dots" alpha mask)
 
 The Halton sampler is deterministic, so the whole image has to come out the same after the reference's own encode
 (core/src/image_io.rs:384-390: clamp(255 * gamma_correct(v) + 0.5) as u8) - stochastic infinite-light estimate, closed-form
@@ -41,11 +41,12 @@ CAMERA = {
     "infinite-no-map": ('LookAt 0 5 3  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 5, 3), (0, 0, 0), 90.0),
     "triangles-alpha-mask": ('LookAt 0 5 3  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 5, 3), (0, 0, 0), 90.0),
     "distant": ('LookAt 0 5 3  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 5, 3), (0, 0, 0), 90.0),
+    "spot": ('LookAt 0 5 3  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 5, 3), (0, 0, 0), 90.0),
     "perspective": ('LookAt 0 2 2  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 2, 2), (0, 0, 0), 90.0),
     # "LookAt ..; Translate 0 -1 0; Camera": the camera sits at world (0, 8, 15) and looks at (0, 1, 0)
     "instances": ('LookAt 0 7 15  0 0 0  0 0 1\nTranslate 0 -1 0\nCamera "perspective" "float fov" 45', (0, 8, 15), (0, 1, 0), 45.0),
 }
-ALBEDO = {"point": (0.3, 0.8), "infinite-no-map": (0.3, 0.8), "triangles-alpha-mask": (0.3, 0.8), "distant": (0.3, 0.8), "perspective": (0.1, 0.8), "instances": (0.1, 0.8)}
+ALBEDO = {"point": (0.3, 0.8), "infinite-no-map": (0.3, 0.8), "triangles-alpha-mask": (0.3, 0.8), "distant": (0.3, 0.8), "spot": (0.3, 0.8), "perspective": (0.1, 0.8), "instances": (0.1, 0.8)}
 GROUND = '''  AttributeBegin
     Translate 0 0 -1
     Material "matte" "rgb Kd" [%g %g %g]
@@ -71,6 +72,14 @@ BODY = {
   AttributeEnd
 ''',
     "infinite-no-map": '''  LightSource "infinite" "rgb L" [.4 .45 .5]
+  AttributeBegin
+    Rotate 45 0 0 1
+    Material "matte" "rgb Kd" [.2 .01 .01]
+    %(cube)s
+  AttributeEnd
+''',
+    # as shipped: "conedelta" is not a parameter SpotLight reads ("conedeltaangle", spot.rs:208), so the falloff starts at 25 - 5 degrees
+    "spot": '''  LightSource "spot" "rgb I" [.4 .45 .5] "point from" [-5 0 5] "point to" [0 0 0] "rgb scale" [200 200 200] "float coneangle" 25 "float conedelta" 20
   AttributeBegin
     Rotate 45 0 0 1
     Material "matte" "rgb Kd" [.2 .01 .01]
@@ -162,7 +171,7 @@ def _oracle_render(path):
     return ol.OracleScene(ge.load_package().load_pbrt(path)).render()[0]
 
 
-SCENES = ["point", "infinite-no-map", "triangles-alpha-mask", "distant", "perspective", "instances"]
+SCENES = ["point", "infinite-no-map", "triangles-alpha-mask", "distant", "perspective", "instances", "spot"]
 
 
 @pytest.mark.parametrize("which", SCENES)

@@ -591,3 +591,27 @@ def test_distant_light_matches_oracle(gpu, oracle, name, light, integrator, stra
     assert img.mean() > 0.01 and ss.rel_rmse(img, ref) <= TOL
     assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,light,integrator,strategy", [("matte", "spot", "path", "uniform"), ("plastic", "all+spot", "path", "power"), ("glass", "all+spot", "path", "spatial"),
+                                                            ("matte", "all+spot", "whitted", "uniform"), ("plastic", "all+spot", "directlighting", "uniform")])
+def test_spot_light_matches_oracle(gpu, oracle, name, light, integrator, strategy):
+    """SpotLight (lights/src/spot.rs): a point light times falloff(-wi) = smooth step ^ 4 between cos(coneangle) and
+    cos(coneangle - conedeltaangle) in light space; power I * 2 pi * (1 - (cos_start + cos_total) / 2) in the distributions."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS[name], light=light, res=40, spp=8, maxdepth=4, strategy=strategy)
+    sd.integrator.update(name=integrator)
+    integ = gpu.PathIntegrator(sd)
+    osc = oracle.OracleScene(sd)
+    ps = _pairs(40, 8)
+    li, rays = integ.li(ps)
+    oli = osc.li(ps)
+    assert rays.tobytes() == osc.camera_rays(ps).tobytes()
+    assert np.isclose(li, oli, rtol=2e-3, atol=1e-5).all(1).mean() >= 0.999
+    if light == "spot":  # no infinite light: every transcendental is exact, radiance must agree bit for bit
+        assert (li.view(np.uint32) == oli.view(np.uint32)).all(1).mean() >= 0.995
+    img = integ.render()
+    ref, stats, _ = osc.render()
+    assert img.mean() > 0.01 and ss.rel_rmse(img, ref) <= TOL
+    assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]

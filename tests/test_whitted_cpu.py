@@ -41,6 +41,33 @@ def test_point_light_on_matte_floor_closed_form(pkg, oracle):
     assert np.argmax(li[:, 0]) == 40  # brightest under the light (centre pixel)
 
 
+def test_spot_light_on_matte_floor_closed_form(pkg, oracle):
+    """SpotLight (lights/src/spot.rs:62-107): L = (Kd / pi) * I * falloff / d^2 * cos(theta), falloff = 1 inside
+    coneangle - conedeltaangle, ((cos a - cos total) / (cos start - cos total))^4 in the penumbra, 0 outside - float64 closed
+    form at the points where the oracle's camera rays meet the floor; the loader's light equals the mirror's."""
+    kd, I, h = np.array([0.5, 0.25, 0.125]), 8.0, 2.0
+    sd = _floor_scene(kd=tuple(kd), res=33)
+    sd.lights.clear()
+    sd.camera.update(fov=60.0)
+    sd.add_spot_light((I, I, I), (0.0, h, 0.0), (0.5, 0.0, 0.2), coneangle=35.0, conedeltaangle=15.0)
+    sc = oracle.OracleScene(sd)
+    ps = np.array([(x, y, 0) for y in range(33) for x in range(33)], dtype=np.int32)
+    li = sc.li(ps, nthreads=1).astype(np.float64)
+    rays = sc.camera_rays(ps)
+    o, d = rays["o"].astype(np.float64), rays["d"].astype(np.float64)
+    p = o + (-o[:, 1] / d[:, 1])[:, None] * d
+    to_light = np.array([0.0, h, 0.0]) - p
+    d2 = (to_light ** 2).sum(1)
+    axis = np.array([0.5, -h, 0.2]); axis /= np.linalg.norm(axis)
+    cos_a = (-to_light / np.sqrt(d2)[:, None]) @ axis
+    ct, cs = np.cos(np.deg2rad(35.0)), np.cos(np.deg2rad(20.0))
+    fall = np.where(cos_a < ct, 0.0, np.where(cos_a >= cs, 1.0, ((cos_a - ct) / (cs - ct)) ** 4))
+    expect = (kd[None, :] / np.pi) * (I * fall / d2)[:, None] * (to_light[:, 1] / np.sqrt(d2))[:, None]
+    edge = np.abs(cos_a - ct) < 1e-4  # the cone's rim: f32 vs f64 may fall on different sides
+    assert np.allclose(li[~edge], expect[~edge], rtol=2e-4, atol=1e-6)
+    assert (fall == 0).any() and (fall == 1).any() and ((fall > 0) & (fall < 1)).sum() > 20
+
+
 def test_shadowed_point_is_black_and_emitter_is_seen(pkg, oracle):
     from pbrt_v3_rs_b200.scene import SceneDescription
     sd = _floor_scene()

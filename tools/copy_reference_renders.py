@@ -1,5 +1,6 @@
-"""Copies the reference's own committed renders of the six shipped scenes that lie entirely on this path (triangle
-meshes, matte, point / infinite light, Whitted, Halton, box filter) into tests/golden/ref_renders/:
+"""Copies the reference's own committed renders of the seven shipped scenes that lie entirely on this path (triangle
+meshes, matte incl. the checkerboard Kd texture, point / spot / distant / infinite light, Whitted, Halton, box filter) into
+tests/golden/ref_renders/:
 
   renders/lights/point.png                 <- scenes/lights/point.pbrt
   renders/lights/infinite-no-map.png       <- scenes/lights/infinite-no-map.pbrt
@@ -7,6 +8,7 @@ meshes, matte, point / infinite light, Whitted, Halton, box filter) into tests/g
   renders/lights/distant.png               <- scenes/lights/distant.pbrt        (distant light, "blackbody L")
   renders/objects/instances.png            <- scenes/objects/instances.pbrt     (ten ObjectInstances of a cube: the two-level BVH)
   renders/cameras/perspective.png          <- scenes/cameras/perspective.pbrt   (infinite + distant light)
+  renders/lights/spot.png                  <- scenes/lights/spot.pbrt           (spot light; its "conedelta" is not a parameter the reference reads)
 
 They are OUTPUTS of the reference (8-bit sRGB PNGs written by core/src/image_io.rs), i.e. golden vectors: the only
 artefacts in the reference tree that were produced by executing it.  tests/test_reference_renders.py renders the same
@@ -20,6 +22,6 @@ DST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 if __name__ == "__main__":
     os.makedirs(DST, exist_ok=True)
     for sub, name in (("lights", "point"), ("lights", "infinite-no-map"), ("shapes", "triangles-alpha-mask"), ("lights", "distant"),
-                      ("objects", "instances"), ("cameras", "perspective")):
+                      ("objects", "instances"), ("cameras", "perspective"), ("lights", "spot")):
         shutil.copyfile(os.path.join(SRC, sub, name + ".png"), os.path.join(DST, name + ".png"))
         print("copied", name)

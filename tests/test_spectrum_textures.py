@@ -238,7 +238,9 @@ def test_textured_kd_matches_oracle(gpu, oracle, case):
     if case.get("lens", 0.0) > 0.0:
         floor = 0.0    # the thin lens' ray origins are equal to ~1e-6 only (tests/test_render_gpu.py::test_camera_rays_bit_exact): statistical check below
     elif case.get("integrator", "path") != "path":
-        floor = 0.95   # tree integrators: nodes below depth 0 multiply the throughput in a different order
+        # tree integrators: nodes below depth 0 multiply the throughput on the way down, the reference on the way back up
+        #  - every sample that sees the glass ball differs by an ulp
+        floor = 0.8 if case.get("glass") else 0.95
     else:
         floor = 0.995
     assert same.mean() >= floor, "only %.4f of the per-sample radiances are bit-identical" % same.mean()

@@ -883,7 +883,30 @@ void Builder::finish() {
                 float px = ((float)x + 0.5f) * rx * (1.0f / 16.0f), py = ((float)y + 0.5f) * ry * (1.0f / 16.0f);
                 d.film.filter_table[k++] = gaussian_1d(px, ex, alpha) * gaussian_1d(py, ey, alpha);
             }
-    } else throw Unsupported("PixelFilter \"" + filter_name + "\" is outside this path (box, gaussian)");
+    } else if (filter_name == "triangle" || filter_name == "mitchell" || filter_name == "sinc") {
+        // filters/src/{triangle,mitchell,sinc}.rs evaluated at the table points of Film::new (film/mod.rs:113-125)
+        const float dflt = filter_name == "sinc" ? 4.0f : 2.0f;
+        rx = filter_p.one_float("xwidth", dflt); ry = filter_p.one_float("ywidth", dflt);
+        const float B = filter_p.one_float("B", 1.0f / 3.0f), Cc = filter_p.one_float("C", 1.0f / 3.0f), tau = filter_p.one_float("tau", 3.0f);
+        const float irx = 1.0f / rx, iry = 1.0f / ry;
+        auto mitchell_1d = [&](float x) {  // mitchell.rs:41-57 (incl. its 8 C + 24 C constant term)
+            x = std::fabs(2.0f * x);
+            if (x > 1.0f) return ((-B - 6.0f * Cc) * x * x * x + (6.0f * B + 30.0f * Cc) * x * x + (-12.0f * B - 48.0f * Cc) * x + (8.0f * Cc + 24.0f * Cc)) * (1.0f / 6.0f);
+            return ((12.0f - 9.0f * B - 6.0f * Cc) * x * x * x + (-18.0f + 12.0f * B + 6.0f * Cc) * x * x + (6.0f - 2.0f * B)) * (1.0f / 6.0f);
+        };
+        auto sinc = [](float x) { x = std::fabs(x); return x < 1e-5f ? 1.0f : std::sin(3.14159265358979323846f * x) / (3.14159265358979323846f * x); };  // sinc.rs:72-79
+        auto windowed_sinc = [&](float x, float radius) { x = std::fabs(x); if (x > radius) return 0.0f; const float lanczos = sinc(x / tau); return sinc(x) * lanczos; };
+        int k = 0;
+        for (int y = 0; y < 16; ++y)
+            for (int x = 0; x < 16; ++x) {
+                const float px = ((float)x + 0.5f) * rx * (1.0f / 16.0f), py = ((float)y + 0.5f) * ry * (1.0f / 16.0f);
+                float v;
+                if (filter_name == "triangle") { const float a = rx - std::fabs(px), b = ry - std::fabs(py); v = (0.0f > a ? 0.0f : a) * (0.0f > b ? 0.0f : b); }
+                else if (filter_name == "mitchell") v = mitchell_1d(px * irx) * mitchell_1d(py * iry);
+                else v = windowed_sinc(px, rx) * windowed_sinc(py, ry);
+                d.film.filter_table[k++] = v;
+            }
+    } else throw Unsupported("PixelFilter \"" + filter_name + "\" is not one of the reference's filters (box, gaussian, triangle, mitchell, sinc)");
     d.film.filter_radius[0] = rx; d.film.filter_radius[1] = ry;
 
     // --- Camera (perspective_camera.rs:35-75, 357-421; camera.rs:276-306) ---

@@ -101,10 +101,10 @@ def perspective_raster_to_camera(fov, xres, yres, screen_window=None):
     return _m4_mul(c2s_inv, r2s)
 
 
-def filter_table(kind="box", radius=None, alpha=2.0):
-    """Film::new filter table (core/src/film/mod.rs:113-125), 16x16 floats."""
+def filter_table(kind="box", radius=None, alpha=2.0, B=1.0 / 3.0, Cm=1.0 / 3.0, tau=3.0):
+    """Film::new filter table (core/src/film/mod.rs:113-125), 16x16 floats, for the reference's five filters."""
     if radius is None:
-        radius = (0.5, 0.5) if kind == "box" else (2.0, 2.0)
+        radius = {"box": (0.5, 0.5), "sinc": (4.0, 4.0)}.get(kind, (2.0, 2.0))
     rx, ry = F32(radius[0]), F32(radius[1])
     tab = np.zeros(256, dtype=F32)
     if kind == "box":
@@ -121,8 +121,37 @@ def filter_table(kind="box", radius=None, alpha=2.0):
                 gy = max(F32(0), np.exp(-a * py * py, dtype=F32) - ey)
                 tab[k] = gx * gy
                 k += 1
+    elif kind in ("triangle", "mitchell", "sinc"):  # filters/src/{triangle,mitchell,sinc}.rs
+        b, c, ta, pi = F32(B), F32(Cm), F32(tau), F32(3.14159265358979323846)
+
+        def mitchell_1d(x):  # mitchell.rs:41-57 (incl. its 8 C + 24 C constant term); np.float32 scalars round after every operation
+            x = abs(F32(2) * F32(x))
+            if x > 1:
+                return ((-b - F32(6) * c) * x * x * x + (F32(6) * b + F32(30) * c) * x * x + (F32(-12) * b - F32(48) * c) * x + (F32(8) * c + F32(24) * c)) * (F32(1) / F32(6))
+            return ((F32(12) - F32(9) * b - F32(6) * c) * x * x * x + (F32(-18) + F32(12) * b + F32(6) * c) * x * x + (F32(6) - F32(2) * b)) * (F32(1) / F32(6))
+
+        def sinc(x):  # sinc.rs:72-79
+            x = abs(F32(x))
+            return F32(1) if x < F32(1e-5) else F32(np.sin(F32(pi * x), dtype=F32) / F32(pi * x))
+
+        def windowed_sinc(x, radius):
+            x = abs(F32(x))
+            return F32(0) if x > radius else F32(sinc(x) * sinc(F32(x / ta)))
+
+        k = 0
+        for y in range(16):
+            for x in range(16):
+                px = (F32(x) + F32(0.5)) * rx * F32(1.0 / 16.0)
+                py = (F32(y) + F32(0.5)) * ry * F32(1.0 / 16.0)
+                if kind == "triangle":
+                    tab[k] = max(F32(0), F32(rx - abs(px))) * max(F32(0), F32(ry - abs(py)))
+                elif kind == "mitchell":
+                    tab[k] = mitchell_1d(F32(px * F32(F32(1) / rx))) * mitchell_1d(F32(py * F32(F32(1) / ry)))
+                else:
+                    tab[k] = windowed_sinc(px, rx) * windowed_sinc(py, ry)
+                k += 1
     else:
-        raise ValueError("filter %r is outside this path (box, gaussian only)" % kind)
+        raise ValueError("filter %r is not one of the reference's filters (box, gaussian, triangle, mitchell, sinc)" % kind)
     return tab, (float(rx), float(ry))
 
 

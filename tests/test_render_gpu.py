@@ -49,7 +49,8 @@ def test_li_per_sample_matches_oracle(gpu, oracle, name, light):
 
 @pytest.mark.parametrize("name,light,strategy,filt", [("matte", "infinite", "uniform", "box"), ("plastic", "all", "power", "box"),
                                                         ("glass", "all", "power", "box"), ("metal", "all", "uniform", "box"),
-                                                        ("matte", "all", "power", "gaussian")])
+                                                        ("matte", "all", "power", "gaussian"), ("plastic", "all", "power", "mitchell"),
+                                                        ("matte", "all", "uniform", "sinc"), ("matte", "all", "uniform", "triangle")])
 def test_image_rel_rmse(gpu, oracle, name, light, strategy, filt):
     from pbrt_v3_rs_b200 import workloads as wl
     sd = ss.one_material_scene(wl, ss.MATERIALS[name], light=light, res=48, spp=16, maxdepth=5, nu=60, nv=30, strategy=strategy, filt=filt)

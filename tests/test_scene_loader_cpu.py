@@ -204,3 +204,38 @@ def test_ply_variants_pfm_roundtrip_and_transform_stack(tmp_path, pkg):
         pkg.load_pbrt(str(tmp_path / "sph.pbrt"))
     with pytest.raises(pkg.B200PTError):
         pkg.load_pbrt(str(tmp_path / "missing.pbrt"))
+
+
+@pytest.mark.parametrize("name,params,kw", [("triangle", '"float xwidth" 1.5 "float ywidth" 2.5', dict(radius=(1.5, 2.5))), ("mitchell", '"float B" 0.2 "float C" 0.4', dict(B=0.2, Cm=0.4)),
+                                            ("mitchell", "", {}), ("sinc", '"float tau" 2.5', dict(tau=2.5)), ("sinc", "", {}), ("gaussian", "", {}), ("box", "", {})])
+def test_loader_filter_tables_match_the_mirror_and_closed_forms(tmp_path, pkg, name, params, kw):
+    """PixelFilter box / gaussian / triangle / mitchell / sinc (filters/src/*.rs) sampled at Film::new's 16x16 table points
+    (film/mod.rs:113-125): loader == mirror, and spot values against float64 closed forms."""
+    from pbrt_v3_rs_b200.scene import filter_table
+    (tmp_path / "f.pbrt").write_text('Camera "perspective"\nPixelFilter "%s" %s\nFilm "image" "integer xresolution" [8] "integer yresolution" [8]\nWorldBegin\n'
+                                     'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 1 1 0 1 0 1 1]\nLightSource "point"\nWorldEnd\n' % (name, params))
+    loaded = pkg.load_pbrt(str(tmp_path / "f.pbrt"))  # owns the description's memory
+    d = loaded.to_desc()
+    tab, (rx, ry) = filter_table(name, kw.pop("radius", None), **kw)
+    got = np.array(list(d.film.filter_table), dtype=np.float32)
+    assert (d.film.filter_radius[0], d.film.filter_radius[1]) == (rx, ry)
+    assert np.allclose(got, tab, rtol=2e-6, atol=1e-7)  # sinc: numpy's sinf vs libm's
+    x, y = (3 + 0.5) * rx / 16.0, (9 + 0.5) * ry / 16.0  # table entry [9][3]
+    if name == "triangle":
+        want = max(0.0, rx - x) * max(0.0, ry - y)
+    elif name == "sinc":
+        tau = kw.get("tau", 3.0)
+        sinc = lambda v: 1.0 if abs(v) < 1e-5 else np.sin(np.pi * abs(v)) / (np.pi * abs(v))
+        want = sinc(x) * sinc(x / tau) * sinc(y) * sinc(y / tau)
+    elif name == "mitchell":
+        B, Cc = kw.get("B", 1 / 3), kw.get("Cm", 1 / 3)
+
+        def m1(v):
+            v = abs(2 * v)
+            if v > 1:
+                return ((-B - 6 * Cc) * v ** 3 + (6 * B + 30 * Cc) * v ** 2 + (-12 * B - 48 * Cc) * v + (8 * Cc + 24 * Cc)) / 6  # the reference's constant term (pbrt has 8 B + 24 C)
+            return ((12 - 9 * B - 6 * Cc) * v ** 3 + (-18 + 12 * B + 6 * Cc) * v ** 2 + (6 - 2 * B)) / 6
+        want = m1(x / rx) * m1(y / ry)
+    else:
+        return
+    assert np.isclose(got[9 * 16 + 3], want, rtol=1e-5, atol=1e-6)

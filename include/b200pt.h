@@ -209,8 +209,8 @@ typedef struct b200pt_float_texture {
  * checkerboard with "aamode" closedform (the default, textures/src/checkerboard_2d.rs:62-98) box-filters over the
  * footprint (dudx, dvdx, dudy, dvdy) that SurfaceInteraction::compute_differentials (surface_interaction.rs:203-277)
  * derives from the ray's differentials: only CAMERA rays carry them (PerspectiveCamera::generate_ray_differential,
- * perspective_camera.rs:144-204, scaled by 1 / sqrt(spp), sampler_integrator.rs:357-358); rays spawned by the path
- * integrator have none and point-sample.  tex1 / tex2 are constants here (nested textures are not supported). */
+ * perspective_camera.rs:144-204, scaled by 1 / sqrt(spp), sampler_integrator.rs:357-358) and hand them on to the specular
+ * children of the Whitted / DirectLighting trees; rays spawned by the path integrator have none and point-sample.  tex1 / tex2 are constants here (nested textures are not supported). */
 #define B200PT_STEX_CONSTANT 0
 #define B200PT_STEX_CHECKERBOARD 1
 typedef struct b200pt_spectrum_texture {
@@ -268,10 +268,9 @@ typedef struct b200pt_scene_desc {
     const uint8_t* noise_perm;
     /* Textured "Kd" (optional): material_kd_tex = per material the index into spectrum_textures of its "Kd" texture or -1
      * (the constant b200pt_material.kd); read for matte and plastic materials.  NULL = every Kd is constant.  Needs
-     * tri_uvs for meshes with "uv" / "st" (others use the default (0,0) (1,0) (1,1), triangle.rs:384-394).  Whitted /
-     * DirectLighting scenes that combine a closedform checkerboard with a specular material (glass) are refused:
-     * specular_reflect / specular_transmit would have to carry differentials to the children
-     * (sampler_integrator.rs:108-125). */
+     * tri_uvs for meshes with "uv" / "st" (others use the default (0,0) (1,0) (1,1), triangle.rs:384-394).  Under Whitted /
+     * DirectLighting the specular children carry the reflected / refracted differentials of specular_reflect /
+     * specular_transmit (sampler_integrator.rs:108-125, 164-227). */
     const b200pt_spectrum_texture* spectrum_textures;
     int32_t n_spectrum_textures;
     const int32_t* material_kd_tex;

@@ -301,6 +301,7 @@ struct TriGeom {
     V3 p, p_error, n, dpdu, dpdv;
     P2 uv;
     V3 shading_n, shading_dpdu;  // Shading::{n, dpdu} after set_shading_geometry (== n, dpdu without N / S)
+    V3 dndu, dndv;               // Shading::{dndu, dndv}: zero without vertex normals (they only feed the differentials of specular children)
 };
 // Returns false when the reference rejects the hit as degenerate (triangle.rs:567-572).
 inline bool triangle_geometry(V3 p0, V3 p1, V3 p2, Float b0, Float b1, Float b2, const TriAttr& at, TriGeom* g) {
@@ -352,6 +353,18 @@ inline bool triangle_geometry(V3 p0, V3 p1, V3 p2, Float b0, Float b1, Float b2,
             ss = cross(ts, ns);
         } else {
             coordinate_system(ns, &ss, &ts);
+        }
+        if (at.n) {  // triangle.rs:679-713
+            V3 n0(at.n[0], at.n[1], at.n[2]), n1(at.n[3], at.n[4], at.n[5]), n2(at.n[6], at.n[7], at.n[8]);
+            V3 dn1 = n0 - n2, dn2 = n1 - n2;
+            if (degenerate_uv) {
+                V3 dn = cross(n2 - n0, n1 - n0);
+                if (length_squared(dn) != 0.0f) coordinate_system(dn, &g->dndu, &g->dndv);
+            } else {
+                Float invdet = 1.0f / determinant;
+                g->dndu = (duv12y * dn1 - duv02y * dn2) * invdet;
+                g->dndv = (-duv12x * dn1 + duv02x * dn2) * invdet;
+            }
         }
         if (at.reverse) ts = -ts;
         // SurfaceInteraction::set_shading_geometry(ss, ts, .., orientation_is_authoritative = true), surface_interaction.rs:152-173

@@ -501,6 +501,7 @@ struct SurfHit {
     V3 shading_n, dpdu;    // Shading (== geometric values: no vertex normals/tangents, no bump)
     P2 uv;                 // SurfaceInteraction::uv
     V3 dpdu_g, dpdv_g;     // SurfaceInteraction::der.{dpdu, dpdv}: the geometric partials (texture filtering only)
+    V3 dndu, dndv;         // Shading::{dndu, dndv} (differentials of specular children only)
     uint32_t prim = 0xffffffffu;
     Float time = 0;
 };
@@ -754,7 +755,7 @@ inline bool scene_intersect(RenderScene& sc, Ray& ray, SurfHit* sh) {
     triangle_geometry(p0, p1, p2, h.b0, h.b1, h.b2, sc.accel.attr(h.prim), &g);
     sh->prim = h.prim;
     sh->time = ray.time;
-    sh->uv = g.uv; sh->dpdu_g = g.dpdu; sh->dpdv_g = g.dpdv;
+    sh->uv = g.uv; sh->dpdu_g = g.dpdu; sh->dpdv_g = g.dpdv; sh->dndu = g.dndu; sh->dndv = g.dndv;
     if (inst < 0) {
         sh->p = g.p; sh->p_error = g.p_error; sh->n = g.n; sh->shading_n = g.shading_n; sh->dpdu = g.shading_dpdu;
         V3 wo = -d_in;
@@ -781,6 +782,7 @@ inline bool scene_intersect(RenderScene& sc, Ray& ray, SurfHit* sh) {
     sh->shading_n = face_forward(sn, sh->n);
     sh->dpdu = xf_vector(I.i2w, g.shading_dpdu);
     sh->dpdu_g = xf_vector(I.i2w, g.dpdu); sh->dpdv_g = xf_vector(I.i2w, g.dpdv);  // transform.rs:577-578
+    sh->dndu = xf_normal(I.w2i, g.dndu); sh->dndv = xf_normal(I.w2i, g.dndv);      // shading.dndu / dndv, transform.rs:587-588
     return true;
 }
 inline bool scene_intersect_p(RenderScene& sc, const Ray& ray) {
@@ -802,8 +804,9 @@ inline bool solve_linear_system_2x2(const Float a[2][2], const Float b[2], Float
 }
 // SurfaceInteraction::compute_differentials (surface_interaction.rs:203-277): the uv footprint of one pixel step, from
 // the ray's differentials and the tangent plane at the hit.  Rays without differentials leave all of it zero.
-inline UVDerivs compute_differentials(const SurfHit& sh, const Ray* ray) {
+inline UVDerivs compute_differentials(const SurfHit& sh, const Ray* ray, V3* dpdx = nullptr, V3* dpdy = nullptr) {
     UVDerivs der;
+    if (dpdx) { *dpdx = V3(0.0f, 0.0f, 0.0f); *dpdy = V3(0.0f, 0.0f, 0.0f); }
     if (!ray || !ray->has_diff) return der;
     V3 n = sh.n, p = sh.p;
     Float d = dot(n, p);
@@ -813,6 +816,7 @@ inline UVDerivs compute_differentials(const SurfHit& sh, const Ray* ray) {
     Float ty = -(dot(n, ray->ry_o) - d) / dot(n, ray->ry_d);
     if (std::isinf(ty) || std::isnan(ty)) return der;
     V3 py = ray->ry_o + ty * ray->ry_d;
+    if (dpdx) { *dpdx = px - p; *dpdy = py - p; }
     int dim[2];
     if (pabs(n.x) > pabs(n.y) && pabs(n.x) > pabs(n.z)) { dim[0] = 1; dim[1] = 2; }
     else if (pabs(n.y) > pabs(n.z)) { dim[0] = 0; dim[1] = 2; }
@@ -1202,9 +1206,48 @@ inline RGB path_li(RenderScene& sc, Ray ray, Sampler& sampler) {
     return L;
 }
 
+// The child ray of specular_reflect / specular_transmit (sampler_integrator.rs:104-127, 161-232): Hit::spawn_ray plus, when
+// the parent ray carries differentials, the reflected / refracted differentials.  `eta_bsdf` = bsdf.eta (1.0 for every
+// material of this path: BSDF::new(.., None)).
+inline Ray specular_child(const SurfHit& isect, const Ray& ray, V3 wi, bool transmit, Float eta_bsdf) {
+    Ray rd = spawn_ray(isect, wi);
+    if (!ray.has_diff) return rd;
+    V3 dpdx, dpdy;
+    UVDerivs uv = compute_differentials(isect, &ray, &dpdx, &dpdy);
+    const V3 wo = isect.wo, p = isect.p;
+    V3 ns = isect.shading_n;
+    rd.has_diff = true;
+    rd.rx_o = p + dpdx;
+    rd.ry_o = p + dpdy;
+    V3 dndx = isect.dndu * uv.dudx + isect.dndv * uv.dvdx;
+    V3 dndy = isect.dndu * uv.dudy + isect.dndv * uv.dvdy;
+    if (!transmit) {
+        V3 dwodx = -ray.rx_d - wo, dwody = -ray.ry_d - wo;
+        Float ddndx = dot(dwodx, ns) + dot(wo, dndx);
+        Float ddndy = dot(dwody, ns) + dot(wo, dndy);
+        rd.rx_d = wi - dwodx + 2.0f * (dot(wo, ns) * dndx + ddndx * ns);
+        rd.ry_d = wi - dwody + 2.0f * (dot(wo, ns) * dndy + ddndy * ns);
+        return rd;
+    }
+    Float eta = 1.0f / eta_bsdf;
+    if (dot(wo, ns) < 0.0f) {
+        eta = 1.0f / eta;
+        ns = -ns; dndx = -dndx; dndy = -dndy;
+    }
+    V3 dwodx = -ray.rx_d - wo, dwody = -ray.ry_d - wo;
+    Float ddndx = dot(dwodx, ns) + dot(wo, dndx);
+    Float ddndy = dot(dwody, ns) + dot(wo, dndy);
+    Float mu = eta * dot(wo, ns) - abs_dot(wi, ns);
+    Float dmudx = (eta - (eta * eta * dot(wo, ns)) / abs_dot(wi, ns)) * ddndx;
+    Float dmudy = (eta - (eta * eta * dot(wo, ns)) / abs_dot(wi, ns)) * ddndy;
+    rd.rx_d = wi - eta * dwodx + (mu * dndx + dmudx * ns);
+    rd.ry_d = wi - eta * dwody + (mu * dndy + dmudy * ns);
+    return rd;
+}
+
 // integrators/src/whitted.rs:60-126 with specular_reflect / specular_transmit of
-// core/src/integrator/sampler_integrator.rs:79-238 (the camera ray's differentials filter a textured "Kd"; specular children
-// get none here, so scene_create refuses Whitted / DirectLighting scenes that combine a closedform checkerboard with glass).
+// core/src/integrator/sampler_integrator.rs:79-238 (ray differentials - the camera ray's, then those specular_child
+// derives for the reflected / refracted rays - size the filter footprint of a textured "Kd").
 inline RGB whitted_li(RenderScene& sc, Ray ray, Sampler& sampler, int depth) {
     RGB l;
     SurfHit isect;
@@ -1233,13 +1276,13 @@ inline RGB whitted_li(RenderScene& sc, Ray ray, Sampler& sampler, int depth) {
             P2 u = sampler.get_2d();
             BxDFSample bs = bsdf.sample_f(wo, u, BSDF_REFLECTION | BSDF_SPECULAR);
             if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(bs.wi, n) != 0.0f)
-                refl = bs.f * whitted_li(sc, spawn_ray(isect, bs.wi), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
+                refl = bs.f * whitted_li(sc, specular_child(isect, ray, bs.wi, false, bsdf.eta), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
         }
         {
             P2 u = sampler.get_2d();
             BxDFSample bs = bsdf.sample_f(wo, u, BSDF_TRANSMISSION | BSDF_SPECULAR);
             if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(bs.wi, n) != 0.0f)
-                trans = bs.f * whitted_li(sc, spawn_ray(isect, bs.wi), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
+                trans = bs.f * whitted_li(sc, specular_child(isect, ray, bs.wi, true, bsdf.eta), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
         }
         l += refl + trans;
     }
@@ -1285,13 +1328,13 @@ inline RGB direct_li(RenderScene& sc, Ray ray, Sampler& sampler, int depth) {
             P2 u = sampler.get_2d();
             BxDFSample bs = bsdf.sample_f(wo, u, BSDF_REFLECTION | BSDF_SPECULAR);
             if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(bs.wi, n) != 0.0f)
-                refl = bs.f * direct_li(sc, spawn_ray(isect, bs.wi), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
+                refl = bs.f * direct_li(sc, specular_child(isect, ray, bs.wi, false, bsdf.eta), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
         }
         {
             P2 u = sampler.get_2d();
             BxDFSample bs = bsdf.sample_f(wo, u, BSDF_TRANSMISSION | BSDF_SPECULAR);
             if (bs.pdf > 0.0f && !is_black(bs.f) && abs_dot(bs.wi, n) != 0.0f)
-                trans = bs.f * direct_li(sc, spawn_ray(isect, bs.wi), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
+                trans = bs.f * direct_li(sc, specular_child(isect, ray, bs.wi, true, bsdf.eta), sampler, depth + 1) * abs_dot(bs.wi, n) / bs.pdf;
         }
         l += refl + trans;
     }

@@ -816,7 +816,7 @@ static size_t wave_bytes_per_path(const SceneImpl* s) {
     if (s->dev.spatial) b += 4;
     if (s->needs_cam_diff) b += 48;
     if (s->whitted) {
-        b += sh_mul * 16 + (size_t)std::max(1, s->dev.max_depth) * 48;
+        b += sh_mul * 16 + (size_t)std::max(1, s->dev.max_depth) * (s->needs_cam_diff ? 96 : 48);
         if (s->tree_mode != kTreeWhitted) b += sh_mul * (16 + 8);
     }
     return b + 24;                                       // per-sample radiance + film position
@@ -1038,7 +1038,8 @@ static int wave_alloc(SceneImpl* s, int cap) {
     W.wstack = nullptr; W.sh_c = nullptr; W.dp_b = nullptr; W.dp_c = nullptr;
     if (s->whitted) {
         if ((rc = dev_alloc(s, sh_cap, &W.sh_c))) return rc;
-        if ((rc = dev_alloc(s, (size_t)cap * (size_t)std::max(1, s->dev.max_depth) * 3, &W.wstack))) return rc;
+        W.wstack_n = s->needs_cam_diff ? 6 : 3;  // with ray differentials a parked transmission child keeps its own (3 float4 more)
+        if ((rc = dev_alloc(s, (size_t)cap * (size_t)std::max(1, s->dev.max_depth) * (size_t)W.wstack_n, &W.wstack))) return rc;
         if (s->tree_mode != kTreeWhitted) {
             if ((rc = dev_alloc(s, sh_cap, &W.dp_b))) return rc;
             if ((rc = dev_alloc(s, sh_cap, &W.dp_c))) return rc;
@@ -1538,10 +1539,8 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     std::vector<int> kd_tex((size_t)std::max(1, d->n_materials), -1);
     bool closedform_tex = false;
     if (d->material_kd_tex && d->spectrum_textures && d->n_spectrum_textures > 0) {
-        bool specular_material = false;
         for (int i = 0; i < d->n_materials; ++i) {
             const b200pt_material& m = d->materials[i];
-            if (m.type == B200PT_MAT_GLASS && m.urough == 0.0f && m.vrough == 0.0f) specular_material = true;
             const int t = d->material_kd_tex[i];
             if (t < 0 || (m.type != B200PT_MAT_MATTE && m.type != B200PT_MAT_PLASTIC)) continue;
             if (t >= d->n_spectrum_textures) { b200pt_set_error("b200pt_scene_create: material_kd_tex index out of range"); return fail(B200PT_ERR_INVALID); }
@@ -1550,11 +1549,6 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
             kd_tex[(size_t)i] = t;
             s->has_kd_tex = true;
             if (T.type == B200PT_STEX_CHECKERBOARD && T.aa_closedform) closedform_tex = true;
-        }
-        if (closedform_tex && specular_material && d->integrator.type != B200PT_INTEGRATOR_PATH) {
-            // specular_reflect / specular_transmit hand differentials to their children (sampler_integrator.rs:108-125, 170-205)
-            b200pt_set_error("b200pt_scene_create: whitted / directlighting with a closedform checkerboard and a specular material: ray differentials of specular children are not on this path (use \"aamode\" \"none\")");
-            return fail(B200PT_ERR_UNSUPPORTED);
         }
     }
     std::vector<DMaterial> mats;

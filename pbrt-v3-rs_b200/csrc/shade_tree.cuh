@@ -27,7 +27,7 @@ namespace b2 {
 enum { kTreeWhitted = 0, kTreeDirectAll = 1, kTreeDirectOne = 2 };
 
 B2_D void wstack_store(const Wave& W, int max_depth, int pid, int sp, V3 o, V3 d, float time, RGB beta, int depth, bool valid) {
-    float4* e = W.wstack + ((long long)pid * max_depth + sp) * 3;
+    float4* e = W.wstack + ((long long)pid * max_depth + sp) * W.wstack_n;
     e[0] = make_float4(o.x, o.y, o.z, time);
     e[1] = make_float4(d.x, d.y, d.z, __int_as_float(valid ? depth : -1));
     e[2] = make_float4(beta.r, beta.g, beta.b, 0.0f);
@@ -87,12 +87,30 @@ __global__ void __launch_bounds__(128) k_shade_tree(DeviceScene S, Wave W, int c
         bsdf.ss = normalize(sh.dpdu);
         bsdf.ts = cross(bsdf.ns, bsdf.ss);
         bsdf.m = S.materials + hc.mat;  // built with allow_multiple_lobes = false (whitted.rs:76, direct_lighting.rs:91)
+        // Ray differentials (scenes with a closed-form checkerboard): every ray of the tree carries them - the camera ray's, then
+        // the ones specular_reflect / specular_transmit derive for their children - in W.cam_diff[pid]; si.der of this hit:
+        const bool have_diff = W.cam_diff != nullptr;
+        HitDerivs HD;
+        HD.dudx = HD.dvdx = HD.dudy = HD.dvdy = 0.0f;
+        HD.dpdx = HD.dpdy = mk(0.0f, 0.0f, 0.0f);
+        V3 dndu = mk(0.0f, 0.0f, 0.0f), dndv = dndu;
+        float tex_u = 0.0f, tex_v = 0.0f;
+        float4 parent_diff[3];
+        if (have_diff) {
+            for (int k = 0; k < 3; ++k) parent_diff[k] = W.cam_diff[3ll * pid + k];
+            tree_hit_derivs(S, W, slot, prim, hit, hb2, sh, parent_diff, &HD, &tex_u, &tex_v, &dndu, &dndv);
+        }
         DMaterial tex_mat;
-        if (S.mat_kd_tex) {  // textured Kd: the camera ray (depth 0) carries differentials; scenes whose specular children would need
-                             // them (closedform checkerboard + glass) are refused at b200pt_scene_create
+        if (S.mat_kd_tex) {  // textured Kd (matte.rs:63, plastic.rs:81)
             const int tex = S.mat_kd_tex[hc.mat];
             if (tex >= 0) {
-                textured_material(S, W, slot, prim, hit, hb2, sh, tex, (depth == 0 && W.cam_diff) ? W.cam_diff + 3ll * pid : nullptr, S.materials[hc.mat], &tex_mat);
+                if (have_diff) {
+                    RGB kd = spectrum_texture_eval(S.spec_tex[tex], tex_u, tex_v, HD.dudx, HD.dvdx, HD.dudy, HD.dvdy);
+                    kd = rgb(clamp0inf(kd.r), clamp0inf(kd.g), clamp0inf(kd.b));
+                    tex_mat = S.materials[hc.mat];
+                    if (is_black(kd)) { tex_mat.n_bxdf -= 1; tex_mat.bx[0] = tex_mat.bx[1]; }
+                    else { tex_mat.bx[0].r[0] = kd.r; tex_mat.bx[0].r[1] = kd.g; tex_mat.bx[0].r[2] = kd.b; }
+                } else textured_material(S, W, slot, prim, hit, hb2, sh, tex, nullptr, S.materials[hc.mat], &tex_mat);
                 bsdf.m = &tex_mat;
             }
         }
@@ -191,6 +209,10 @@ __global__ void __launch_bounds__(128) k_shade_tree(DeviceScene S, Wave W, int c
                 // specular_transmit runs after the whole reflection subtree: park it (its get_2d is charged at the pop)
                 V3 to = t_ok ? offset_ray_origin(sh.p, sh.p_error, sh.n, t_wi) : mk(0, 0, 0);
                 wstack_store(W, S.max_depth, pid, sp, to, t_wi, time, t_beta, depth + 1, t_ok);
+                if (have_diff) {
+                    if (t_ok) specular_child_differentials(parent_diff, HD, sh.p, wo, sh.ns, dndu, dndv, t_wi, true, 1.0f, W.wstack + ((long long)pid * S.max_depth + sp) * W.wstack_n + 3);
+                    specular_child_differentials(parent_diff, HD, sh.p, wo, sh.ns, dndu, dndv, r_wi, false, 1.0f, W.cam_diff + 3ll * pid);
+                }
                 sp += 1;
             } else {
                 dim += 2;  // specular_transmit: sampler.get_2d()
@@ -198,6 +220,7 @@ __global__ void __launch_bounds__(128) k_shade_tree(DeviceScene S, Wave W, int c
                     have_next = true;
                     next_o = offset_ray_origin(sh.p, sh.p_error, sh.n, t_wi);
                     next_d = t_wi; next_beta = t_beta; next_depth = depth + 1;
+                    if (have_diff) specular_child_differentials(parent_diff, HD, sh.p, wo, sh.ns, dndu, dndv, t_wi, true, 1.0f, W.cam_diff + 3ll * pid);
                 }
             }
         }
@@ -205,12 +228,13 @@ __global__ void __launch_bounds__(128) k_shade_tree(DeviceScene S, Wave W, int c
     float next_time = time;
     while (!have_next && sp > 0) {  // return to the innermost node that still owes its specular_transmit
         sp -= 1;
-        const float4* e = W.wstack + ((long long)pid * S.max_depth + sp) * 3;
+        const float4* e = W.wstack + ((long long)pid * S.max_depth + sp) * W.wstack_n;
         const float4 e0 = e[0], e1 = e[1], e2 = e[2];
         dim += 2;
         const int d = __float_as_int(e1.w);
         if (d >= 0) {
             have_next = true;
+            if (W.cam_diff) for (int k = 0; k < 3; ++k) W.cam_diff[3ll * pid + k] = e[3 + k];
             next_o = mk(e0.x, e0.y, e0.z); next_d = mk(e1.x, e1.y, e1.z); next_time = e0.w;
             next_beta = rgb(e2.x, e2.y, e2.z); next_depth = d;
         }

@@ -79,54 +79,59 @@ B2_D int f32_as_i32(float f) {  // Rust `as i32`: saturating, NaN -> 0
     return (int)f;
 }
 
-// Kd of one intersection, before the material's clamp.  uv6 = the primitive's three uvs; (p0, p1, p2, duv) its vertices and
+// si.der after SurfaceInteraction::compute_differentials: the screen-space derivatives of uv and of the hit point.
+struct HitDerivs {
+    float dudx, dvdx, dudy, dvdy;
+    V3 dpdx, dpdy;
+};
+// compute_differentials (surface_interaction.rs:203-277) for a triangle hit.  (p0, p1, p2, duv) = the primitive's vertices and
 // uv differences in the space the hit was found in; i2w = the instance's primitive_to_world 4x4 (null: top-level triangle or
-// identity) for der.dpdu / der.dpdv (transform.rs:577-578); p, n = Hit::p / Hit::n in world space; diff = the path's stored
-// camera differentials, or null for a ray without any.  Out of line: one call site per shade kernel.
-__device__ __noinline__ RGB kd_texture_eval(const DSpecTex* tp, const float* uv6, float b0, float b1, float b2, V3 p0, V3 p1, V3 p2, float4 duv, const float* i2w, V3 p,
-                                            V3 n, const float4* diff) {
-    const DSpecTex T = *tp;
-    if (T.type == 0) return rgb(T.tex1[0], T.tex1[1], T.tex1[2]);
-    // triangle.rs:573-575: uv = b0 uv0 + b1 uv1 + b2 uv2
-    const float u = b0 * uv6[0] + b1 * uv6[2] + b2 * uv6[4];
-    const float v = b0 * uv6[1] + b1 * uv6[3] + b2 * uv6[5];
-    float dudx = 0.0f, dvdx = 0.0f, dudy = 0.0f, dvdy = 0.0f;
-    if (T.closedform && diff) {
-        // der.dpdu / der.dpdv: the geometric partials of Triangle::intersect (triangle.rs:548-570)
-        const V3 dp02 = p0 - p2, dp12 = p1 - p2;
-        const float determinant = duv.x * duv.w - duv.y * duv.z;
-        const bool degenerate_uv = pabs(determinant) < 1e-8f;
-        V3 dpdu = mk(0.0f, 0.0f, 0.0f), dpdv = dpdu;
-        if (!degenerate_uv) {
-            const float invdet = 1.0f / determinant;
-            dpdu = (duv.w * dp02 - duv.y * dp12) * invdet;
-            dpdv = (-duv.z * dp02 + duv.x * dp12) * invdet;
-        }
-        if (degenerate_uv || length_squared(cross(dpdu, dpdv)) == 0.0f) coordinate_system(normalize(cross(p2 - p0, p1 - p0)), &dpdu, &dpdv);
-        if (i2w) {
-            const float* m = i2w;
-            dpdu = mk(m[0] * dpdu.x + m[1] * dpdu.y + m[2] * dpdu.z, m[4] * dpdu.x + m[5] * dpdu.y + m[6] * dpdu.z, m[8] * dpdu.x + m[9] * dpdu.y + m[10] * dpdu.z);
-            dpdv = mk(m[0] * dpdv.x + m[1] * dpdv.y + m[2] * dpdv.z, m[4] * dpdv.x + m[5] * dpdv.y + m[6] * dpdv.z, m[8] * dpdv.x + m[9] * dpdv.y + m[10] * dpdv.z);
-        }
-        // compute_differentials, surface_interaction.rs:203-277
-        const float4 d0 = diff[0], d1 = diff[1], d2 = diff[2];
-        const V3 rx_o = mk(d0.x, d0.y, d0.z), rx_d = mk(d0.w, d1.x, d1.y), ry_o = mk(d1.z, d1.w, d2.x), ry_d = mk(d2.y, d2.z, d2.w);
-        const float d = dot(n, p);
-        const float tx = -(dot(n, rx_o) - d) / dot(n, rx_d);
-        const float ty = -(dot(n, ry_o) - d) / dot(n, ry_d);
-        if (!(isinf(tx) || isnan(tx)) && !(isinf(ty) || isnan(ty))) {
-            const V3 px = rx_o + rx_d * tx, py = ry_o + ry_d * ty;
-            int a0, a1;
-            if (pabs(n.x) > pabs(n.y) && pabs(n.x) > pabs(n.z)) { a0 = 1; a1 = 2; }
-            else if (pabs(n.y) > pabs(n.z)) { a0 = 0; a1 = 2; }
-            else { a0 = 0; a1 = 1; }
-            const float a00 = vcomp(dpdu, a0), a01 = vcomp(dpdv, a0), a10 = vcomp(dpdu, a1), a11 = vcomp(dpdv, a1);
-            const float bx0 = vcomp(px, a0) - vcomp(p, a0), bx1 = vcomp(px, a1) - vcomp(p, a1);
-            const float by0 = vcomp(py, a0) - vcomp(p, a0), by1 = vcomp(py, a1) - vcomp(p, a1);
-            if (!solve_2x2(a00, a01, a10, a11, bx0, bx1, &dudx, &dvdx)) { dudx = 0.0f; dvdx = 0.0f; }
-            if (!solve_2x2(a00, a01, a10, a11, by0, by1, &dudy, &dvdy)) { dudy = 0.0f; dvdy = 0.0f; }
-        }
+// identity) for der.dpdu / der.dpdv (transform.rs:577-578); p, n = Hit::p / Hit::n in world space; diff = the ray's
+// differentials (3 float4, camera_differentials' layout).  Out of line: one call site per kernel.
+__device__ __noinline__ void hit_differentials(V3 p0, V3 p1, V3 p2, float4 duv, const float* i2w, V3 p, V3 n, const float4* diff, HitDerivs* out) {
+    HitDerivs D;
+    D.dudx = D.dvdx = D.dudy = D.dvdy = 0.0f;
+    D.dpdx = D.dpdy = mk(0.0f, 0.0f, 0.0f);
+    // der.dpdu / der.dpdv: the geometric partials of Triangle::intersect (triangle.rs:548-570)
+    const V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    const float determinant = duv.x * duv.w - duv.y * duv.z;
+    const bool degenerate_uv = pabs(determinant) < 1e-8f;
+    V3 dpdu = mk(0.0f, 0.0f, 0.0f), dpdv = dpdu;
+    if (!degenerate_uv) {
+        const float invdet = 1.0f / determinant;
+        dpdu = (duv.w * dp02 - duv.y * dp12) * invdet;
+        dpdv = (-duv.z * dp02 + duv.x * dp12) * invdet;
     }
+    if (degenerate_uv || length_squared(cross(dpdu, dpdv)) == 0.0f) coordinate_system(normalize(cross(p2 - p0, p1 - p0)), &dpdu, &dpdv);
+    if (i2w) {
+        const float* m = i2w;
+        dpdu = mk(m[0] * dpdu.x + m[1] * dpdu.y + m[2] * dpdu.z, m[4] * dpdu.x + m[5] * dpdu.y + m[6] * dpdu.z, m[8] * dpdu.x + m[9] * dpdu.y + m[10] * dpdu.z);
+        dpdv = mk(m[0] * dpdv.x + m[1] * dpdv.y + m[2] * dpdv.z, m[4] * dpdv.x + m[5] * dpdv.y + m[6] * dpdv.z, m[8] * dpdv.x + m[9] * dpdv.y + m[10] * dpdv.z);
+    }
+    const float4 d0 = diff[0], d1 = diff[1], d2 = diff[2];
+    const V3 rx_o = mk(d0.x, d0.y, d0.z), rx_d = mk(d0.w, d1.x, d1.y), ry_o = mk(d1.z, d1.w, d2.x), ry_d = mk(d2.y, d2.z, d2.w);
+    const float d = dot(n, p);
+    const float tx = -(dot(n, rx_o) - d) / dot(n, rx_d);
+    const float ty = -(dot(n, ry_o) - d) / dot(n, ry_d);
+    if (!(isinf(tx) || isnan(tx)) && !(isinf(ty) || isnan(ty))) {
+        const V3 px = rx_o + rx_d * tx, py = ry_o + ry_d * ty;
+        D.dpdx = px - p; D.dpdy = py - p;
+        int a0, a1;
+        if (pabs(n.x) > pabs(n.y) && pabs(n.x) > pabs(n.z)) { a0 = 1; a1 = 2; }
+        else if (pabs(n.y) > pabs(n.z)) { a0 = 0; a1 = 2; }
+        else { a0 = 0; a1 = 1; }
+        const float a00 = vcomp(dpdu, a0), a01 = vcomp(dpdv, a0), a10 = vcomp(dpdu, a1), a11 = vcomp(dpdv, a1);
+        const float bx0 = vcomp(px, a0) - vcomp(p, a0), bx1 = vcomp(px, a1) - vcomp(p, a1);
+        const float by0 = vcomp(py, a0) - vcomp(p, a0), by1 = vcomp(py, a1) - vcomp(p, a1);
+        if (!solve_2x2(a00, a01, a10, a11, bx0, bx1, &D.dudx, &D.dvdx)) { D.dudx = 0.0f; D.dvdx = 0.0f; }
+        if (!solve_2x2(a00, a01, a10, a11, by0, by1, &D.dudy, &D.dvdy)) { D.dudy = 0.0f; D.dvdy = 0.0f; }
+    }
+    *out = D;
+}
+
+// Texture<Spectrum>::evaluate at (u, v) with the uv derivatives of D (zero = point sampling), before the material's clamp.
+B2_D RGB spectrum_texture_eval(const DSpecTex& T, float u, float v, float dudx, float dvdx, float dudy, float dvdy) {
+    if (T.type == 0) return rgb(T.tex1[0], T.tex1[1], T.tex1[2]);
     // uv_2d.rs:44-50
     const float dsdx = T.su * dudx, dtdx = T.sv * dvdx, dsdy = T.su * dudy, dtdy = T.sv * dvdy;
     const float s = T.su * u + T.du, t = T.sv * v + T.dv;
@@ -142,6 +147,56 @@ __device__ __noinline__ RGB kd_texture_eval(const DSpecTex* tp, const float* uv6
     const float tint = (bump_int(t1) - bump_int(t0)) / (2.0f * dt);
     const float area2 = (ds > 1.0f || dt > 1.0f) ? 0.5f : sint + tint - 2.0f * sint * tint;
     return rgb(T.tex1[0] * (1.0f - area2) + T.tex2[0] * area2, T.tex1[1] * (1.0f - area2) + T.tex2[1] * area2, T.tex1[2] * (1.0f - area2) + T.tex2[2] * area2);
+}
+
+// Kd of one intersection of the path integrator (uv6 = the primitive's three uvs; the rest as for hit_differentials; diff =
+// null for a ray without differentials).  Out of line: one call site per shade kernel.
+__device__ __noinline__ RGB kd_texture_eval(const DSpecTex* tp, const float* uv6, float b0, float b1, float b2, V3 p0, V3 p1, V3 p2, float4 duv, const float* i2w, V3 p,
+                                            V3 n, const float4* diff) {
+    const DSpecTex T = *tp;
+    // triangle.rs:573-575: uv = b0 uv0 + b1 uv1 + b2 uv2
+    const float u = b0 * uv6[0] + b1 * uv6[2] + b2 * uv6[4];
+    const float v = b0 * uv6[1] + b1 * uv6[3] + b2 * uv6[5];
+    HitDerivs D;
+    D.dudx = D.dvdx = D.dudy = D.dvdy = 0.0f;
+    if (T.type != 0 && T.closedform && diff) hit_differentials(p0, p1, p2, duv, i2w, p, n, diff, &D);
+    return spectrum_texture_eval(T, u, v, D.dudx, D.dvdx, D.dudy, D.dvdy);
+}
+
+// The differentials of the child ray specular_reflect / specular_transmit spawn (sampler_integrator.rs:108-125, 164-227) from
+// the parent's (diff), the hit's derivatives D, shading normal ns and its derivatives dndu / dndv, for the sampled direction wi.
+// eta_bsdf = bsdf.eta (1 for every material of this path: BSDF::new(.., None)).  Layout of out: camera_differentials'.
+B2_D void specular_child_differentials(const float4* diff, const HitDerivs& D, V3 p, V3 wo, V3 ns, V3 dndu, V3 dndv, V3 wi, bool transmit, float eta_bsdf, float4* out) {
+    const float4 d0 = diff[0], d1 = diff[1], d2 = diff[2];
+    const V3 prx_d = mk(d0.w, d1.x, d1.y), pry_d = mk(d2.y, d2.z, d2.w);
+    const V3 rx_o = p + D.dpdx, ry_o = p + D.dpdy;
+    V3 dndx = dndu * D.dudx + dndv * D.dvdx;
+    V3 dndy = dndu * D.dudy + dndv * D.dvdy;
+    V3 rx_d, ry_d;
+    if (!transmit) {
+        const V3 dwodx = -prx_d - wo, dwody = -pry_d - wo;
+        const float ddndx = dot(dwodx, ns) + dot(wo, dndx);
+        const float ddndy = dot(dwody, ns) + dot(wo, dndy);
+        rx_d = wi - dwodx + 2.0f * (dot(wo, ns) * dndx + ddndx * ns);
+        ry_d = wi - dwody + 2.0f * (dot(wo, ns) * dndy + ddndy * ns);
+    } else {
+        float eta = 1.0f / eta_bsdf;
+        if (dot(wo, ns) < 0.0f) {
+            eta = 1.0f / eta;
+            ns = -ns; dndx = -dndx; dndy = -dndy;
+        }
+        const V3 dwodx = -prx_d - wo, dwody = -pry_d - wo;
+        const float ddndx = dot(dwodx, ns) + dot(wo, dndx);
+        const float ddndy = dot(dwody, ns) + dot(wo, dndy);
+        const float mu = eta * dot(wo, ns) - abs_dot(wi, ns);
+        const float dmudx = (eta - (eta * eta * dot(wo, ns)) / abs_dot(wi, ns)) * ddndx;
+        const float dmudy = (eta - (eta * eta * dot(wo, ns)) / abs_dot(wi, ns)) * ddndy;
+        rx_d = wi - eta * dwodx + (mu * dndx + dmudx * ns);
+        ry_d = wi - eta * dwody + (mu * dndy + dmudy * ns);
+    }
+    out[0] = make_float4(rx_o.x, rx_o.y, rx_o.z, rx_d.x);
+    out[1] = make_float4(rx_d.y, rx_d.z, ry_o.x, ry_o.y);
+    out[2] = make_float4(ry_o.z, ry_d.x, ry_d.y, ry_d.z);
 }
 
 }  // namespace b2

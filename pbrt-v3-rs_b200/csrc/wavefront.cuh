@@ -90,6 +90,7 @@ struct Wave {
     // Whitted integrator only: per-path stack of postponed specular-transmission children (3 float4 per entry,
     // max_depth entries per path) and the per-shadow-ray contribution of the light loop (rgb, valid)
     float4* wstack;
+    int wstack_n;       // float4 per stack entry: 3, or 6 when the rays carry differentials (cam_diff)
     float4* sh_c;
     // DirectLighting integrator only: per-slot MIS record (f rgb, weight) and (scattering pdf, light index)
     float4* dp_b;
@@ -228,6 +229,44 @@ B2_D void textured_material(const DeviceScene& S, const Wave& W, int slot, uint3
     } else {
         out->bx[0].r[0] = kd.r; out->bx[0].r[1] = kd.g; out->bx[0].r[2] = kd.b;
     }
+}
+
+// Tree integrators with ray differentials: si.der (compute_differentials), the interpolated uv and shading.dndu / dndv
+// (triangle.rs:679-713; transform_normal for a hit inside an instance, transform.rs:587-588) of the hit in `slot`.
+B2_D void tree_hit_derivs(const DeviceScene& S, const Wave& W, int slot, uint32_t prim, float4 hit, float hb2, const SurfHit& sh, const float4* diff, HitDerivs* D,
+                          float* u, float* v, V3* dndu, V3* dndv) {
+    V3 p0, p1, p2;
+    int mat_unused, light_unused;
+    uint32_t pflags;
+    load_prim(S, prim, &p0, &p1, &p2, &mat_unused, &light_unused, &pflags);
+    const float4 duv = (S.prim_duv && (pflags & B200PT_PRIM_HAS_UV)) ? ldg4(S.prim_duv + prim) : default_duv();
+    const int inst = S.instances ? W.hit_inst[slot] : -1;
+    const bool xf = inst >= 0 && !S.instances[inst].identity;
+    hit_differentials(p0, p1, p2, duv, xf ? S.instances[inst].i2w : nullptr, sh.p, sh.n, diff, D);
+    const float* uv6 = S.prim_uv6 + 6ll * prim;
+    *u = hit.z * uv6[0] + hit.w * uv6[2] + hb2 * uv6[4];
+    *v = hit.z * uv6[1] + hit.w * uv6[3] + hb2 * uv6[5];
+    V3 du = mk(0.0f, 0.0f, 0.0f), dv = du;
+    if (S.prim_n && (pflags & B200PT_PRIM_HAS_NORMALS)) {
+        const float* vn = S.prim_n + 9ll * prim;
+        const V3 n0 = mk(vn[0], vn[1], vn[2]), n1 = mk(vn[3], vn[4], vn[5]), n2 = mk(vn[6], vn[7], vn[8]);
+        const V3 dn1 = n0 - n2, dn2 = n1 - n2;
+        const float determinant = duv.x * duv.w - duv.y * duv.z;
+        if (pabs(determinant) < 1e-8f) {
+            const V3 dn = cross(n2 - n0, n1 - n0);
+            if (length_squared(dn) != 0.0f) coordinate_system(dn, &du, &dv);
+        } else {
+            const float invdet = 1.0f / determinant;
+            du = (duv.w * dn1 - duv.y * dn2) * invdet;
+            dv = (-duv.z * dn1 + duv.x * dn2) * invdet;
+        }
+        if (xf) {
+            const float* mi = S.instances[inst].w2i;
+            du = mk(mi[0] * du.x + mi[4] * du.y + mi[8] * du.z, mi[1] * du.x + mi[5] * du.y + mi[9] * du.z, mi[2] * du.x + mi[6] * du.y + mi[10] * du.z);
+            dv = mk(mi[0] * dv.x + mi[4] * dv.y + mi[8] * dv.z, mi[1] * dv.x + mi[5] * dv.y + mi[9] * dv.z, mi[2] * dv.x + mi[6] * dv.y + mi[10] * dv.z);
+        }
+    }
+    *dndu = du; *dndv = dv;
 }
 
 // Light::sample_li for the three light kinds of this path (point.rs:83-94, diffuse.rs:114-129 over Triangle::sample

@@ -170,6 +170,42 @@ def test_oracle_footprint_of_a_pinhole_over_a_plane():
     assert np.abs(r16[-4:] - 1).max() > 0.05 and np.abs(r16[:2] - 1).max() < 1e-5  # near rows resolve checks, far rows stay filtered
 
 
+def test_oracle_specular_children_carry_differentials():
+    """Whitted through a flat glass slab onto the 2.5 cm checkerboard: the ground is reached by a twice-refracted ray whose
+    differentials come from specular_transmit (sampler_integrator.rs:164-227).  Their footprint is still wider than a check,
+    so the image equals the render with Kd = 0.5 bit for bit; a child without differentials would point-sample black / white."""
+    import oracle_lib as ol
+    _pkg()
+    from pbrt_v3_rs_b200.scene import SceneDescription
+
+    def quad(y, up):
+        p = np.array([[-50, y, -50], [50, y, -50], [50, y, 50], [-50, y, 50]], dtype=F32)
+        return np.stack([np.concatenate([p[0], p[2], p[1]]), np.concatenate([p[0], p[3], p[2]])]) if up else np.stack([np.concatenate([p[0], p[1], p[2]]), np.concatenate([p[0], p[2], p[3]])])
+
+    def render(kd, spp, aamode="closedform"):
+        sd = SceneDescription()
+        if kd is None:
+            kd = ("texture", sd.add_spectrum_texture("checkerboard", uscale=4000.0, vscale=4000.0, tex1=(1, 1, 1), tex2=(0, 0, 0), aamode=aamode))
+        g = sd.add_material(type="matte", Kd=kd)
+        glass = sd.add_material(type="glass", eta=1.5)
+        sd.add_mesh(quad(0.0, True), g, uv=np.array([[0, 0, 1, 1, 1, 0], [0, 0, 0, 1, 1, 1]], dtype=F32))
+        sd.add_mesh(quad(0.5, True), glass)    # slab: top face (normal up) ...
+        sd.add_mesh(quad(0.3, False), glass)   # ... and bottom face (normal down)
+        sd.add_point_light((0.0, 0.2, 1.5), (10, 10, 10))  # below the slab: the ground's shadow rays are free
+        sd.camera.update(eye=(0.0, 1.0, 0.0), look=(0.0, 0.0, 3.0), up=(0, 1, 0), fov=60.0)
+        sd.film.update(xresolution=32, yresolution=32)
+        sd.sampler.update(type="halton", pixelsamples=spp)
+        sd.integrator.update(name="whitted", maxdepth=5)
+        return ol.OracleScene(sd).render()[0][20:, :, 0]
+
+    half_grey = render((0.5, 0.5, 0.5), 1)
+    assert (half_grey > 0).mean() > 0.9
+    assert np.array_equal(render(None, 1), half_grey)
+    ps = render(None, 1, "none")
+    lit = half_grey > 0
+    assert (ps[lit] == 0).mean() > 0.2 and (ps[lit] > 1.5 * half_grey[lit]).mean() > 0.2  # point sampling: black or white checks
+
+
 def test_loader_reads_spectrum_textures_like_the_mirror(tmp_path):
     import oracle_lib as ol
     pkg = _pkg()
@@ -212,7 +248,10 @@ def _pairs(res, spp):
 
 CASES = [dict(), dict(material="plastic"), dict(material="oren_nayar"), dict(lens=0.08), dict(aamode="none"), dict(black_check=True), dict(instanced=True),
          dict(null_cover=True), dict(sampler="sobol"), dict(sampler="02sequence"), dict(integrator="whitted"), dict(integrator="directlighting"),
-         dict(integrator="whitted", instanced=True, lens=0.05), dict(integrator="whitted", aamode="none", glass=True)]
+         dict(integrator="whitted", instanced=True, lens=0.05), dict(integrator="whitted", aamode="none", glass=True),
+         # specular children carry the reflected / refracted differentials (sampler_integrator.rs:108-125, 164-227); the instanced ball
+         # has vertex normals, whose dndu / dndv go through the instance's transform_normal
+         dict(integrator="whitted", glass=True), dict(integrator="directlighting", glass=True, instanced=True), dict(integrator="whitted", glass=True, lens=0.05)]
 
 
 @pytest.mark.gpu
@@ -254,11 +293,3 @@ def test_textures_show_in_the_image(gpu):
     a = gpu.PathIntegrator(_textured_scene(wl)).render()
     b = gpu.PathIntegrator(_textured_scene(wl, aamode="none")).render()
     assert ss.rel_rmse(a, b) > 1e-3
-
-
-@pytest.mark.gpu
-def test_closedform_checkerboard_with_glass_is_refused_for_whitted(gpu):
-    from pbrt_v3_rs_b200 import workloads as wl
-    sd = _textured_scene(wl, integrator="whitted", glass=True)
-    with pytest.raises(Exception, match="differentials"):
-        gpu.PathIntegrator(sd).render()

@@ -38,6 +38,7 @@
 //
 // HBM-bound integer/min-max work: nothing here is a contraction.
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -826,6 +827,99 @@ __global__ void __launch_bounds__(64) k_hl_treelets(const float* __restrict__ pb
     }
     sizes[t] = n_nodes;
 }
+// ---- the same treelets, level-parallel (default) ---------------------------------------------------------------------
+// emit_lbvh splits a range at the highest Morton bit (<= the parent's bit - 1) in which its codes differ, so a node's children
+// are a pure function of (first, count, bit): all nodes of one depth are independent.  One launch per depth (the bit falls by at
+// least one per level: 19 launches) lets one thread create each node and allocate its two children with one atomicAdd; the
+// ids of a depth are contiguous, so the next launch's work list is the id range itself.  Pre-order positions follow from
+// subtree sizes (bottom-up, together with the bounds: union(child0, child1) as common.rs:150-159) and "first child = me + 1,
+// second child = me + 1 + size(first)" (top-down).  Output: the same `tmp` / `sizes` the one-thread-per-treelet kernel writes.
+struct HlLevels {
+    uint32_t *first, *count, *c0, *size, *pos, *tre;
+    int32_t* bit;
+    float* box;          // 6 floats per node
+    uint32_t* counter;   // nodes allocated
+    uint32_t* lvl;       // lvl[d] = first id of depth d
+};
+__global__ void k_hlp_init(HlLevels T, const uint32_t* __restrict__ starts, uint32_t n_treelets, uint32_t n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) { *T.counter = n_treelets; T.lvl[0] = 0; T.lvl[1] = n_treelets; }
+    if (t >= n_treelets) return;
+    const uint32_t first = starts[t], end = t + 1 < n_treelets ? starts[t + 1] : n;
+    T.first[t] = first; T.count[t] = end - first; T.bit[t] = 30 - 1 - 12; T.tre[t] = t;
+}
+__global__ void __launch_bounds__(256) k_hlp_level(HlLevels T, int depth, const float* __restrict__ pb, const uint32_t* __restrict__ code, const uint32_t* __restrict__ val,
+                                                    int max_prims, Ctl* ctl) {
+    const uint32_t lo_id = T.lvl[depth], hi_id = T.lvl[depth + 1];
+    for (uint32_t id = lo_id + blockIdx.x * blockDim.x + threadIdx.x; id < hi_id; id += gridDim.x * blockDim.x) {
+        const uint32_t first = T.first[id], count = T.count[id];
+        int bit = T.bit[id];
+        while (bit >= 0 && count >= (uint32_t)max_prims && ((code[first] ^ code[first + count - 1]) & (1u << bit)) == 0) --bit;  // hlbvh.rs:278-291
+        T.bit[id] = bit;
+        if (bit == -1 || count < (uint32_t)max_prims) {  // hlbvh.rs:257-273
+            Box b = empty_box();
+            for (uint32_t i = 0; i < count; ++i) {
+                const float* q = pb + 6 * (size_t)val[first + i];
+                Box o;
+                o.lo[0] = q[0]; o.lo[1] = q[1]; o.lo[2] = q[2]; o.hi[0] = q[3]; o.hi[1] = q[4]; o.hi[2] = q[5];
+                grow(b, o);
+            }
+            if (count >= 65536u) atomicMax(&ctl->error, (uint32_t)kErrBigLeaf);
+            float* bx = T.box + 6 * (size_t)id;
+            for (int k = 0; k < 3; ++k) { bx[k] = b.lo[k]; bx[3 + k] = b.hi[k]; }
+            T.c0[id] = 0xffffffffu;
+            T.size[id] = 1;
+            continue;
+        }
+        const uint32_t mask = 1u << bit;
+        uint32_t lo = 0, hi = count - 1;
+        while (lo + 1 != hi) {  // hlbvh.rs:293-316
+            const uint32_t mid = (lo + hi) / 2;
+            if (((code[first + lo] ^ code[first + mid]) & mask) == 0) lo = mid; else hi = mid;
+        }
+        const uint32_t c = atomicAdd(T.counter, 2u);
+        T.c0[id] = c;
+        const uint32_t tre = T.tre[id];
+        T.first[c] = first; T.count[c] = hi; T.bit[c] = bit - 1; T.tre[c] = tre;
+        T.first[c + 1] = first + hi; T.count[c + 1] = count - hi; T.bit[c + 1] = bit - 1; T.tre[c + 1] = tre;
+    }
+}
+__global__ void k_hlp_mark(HlLevels T, int depth) { T.lvl[depth + 2] = *T.counter; }
+__global__ void __launch_bounds__(256) k_hlp_up(HlLevels T, int depth) {
+    const uint32_t lo_id = T.lvl[depth], hi_id = T.lvl[depth + 1];
+    for (uint32_t id = lo_id + blockIdx.x * blockDim.x + threadIdx.x; id < hi_id; id += gridDim.x * blockDim.x) {
+        const uint32_t c = T.c0[id];
+        if (c == 0xffffffffu) continue;
+        T.size[id] = 1 + T.size[c] + T.size[c + 1];
+        const float *a = T.box + 6 * (size_t)c, *b = a + 6;
+        float* o = T.box + 6 * (size_t)id;
+        for (int k = 0; k < 3; ++k) { o[k] = fmin_ref(a[k], b[k]); o[3 + k] = fmax_ref(a[3 + k], b[3 + k]); }
+    }
+}
+__global__ void __launch_bounds__(256) k_hlp_down(HlLevels T, int depth) {
+    const uint32_t lo_id = T.lvl[depth], hi_id = T.lvl[depth + 1];
+    for (uint32_t id = lo_id + blockIdx.x * blockDim.x + threadIdx.x; id < hi_id; id += gridDim.x * blockDim.x) {
+        if (depth == 0) T.pos[id] = 0;
+        const uint32_t c = T.c0[id];
+        if (c == 0xffffffffu) continue;
+        const uint32_t me = T.pos[id];
+        T.pos[c] = me + 1;
+        T.pos[c + 1] = me + 1 + T.size[c];
+    }
+}
+__global__ void __launch_bounds__(256) k_hlp_emit(HlLevels T, const uint32_t* __restrict__ starts, uint32_t n_treelets, b200pt_bvh_node* __restrict__ tmp, uint32_t* __restrict__ sizes) {
+    const uint32_t total = *T.counter;
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
+        b200pt_bvh_node* out = tmp + 2 * (size_t)starts[T.tre[id]] + T.pos[id];
+        const float* bx = T.box + 6 * (size_t)id;
+        Box b;
+        for (int k = 0; k < 3; ++k) { b.lo[k] = bx[k]; b.hi[k] = bx[3 + k]; }
+        const uint32_t c = T.c0[id];
+        if (c == 0xffffffffu) store_node(out, b, T.first[id], T.count[id], 0);
+        else store_node(out, b, T.pos[c + 1], 0, (uint32_t)(T.bit[id] % 3));
+        if (id < n_treelets) sizes[id] = T.size[id];
+    }
+}
 __global__ void k_hl_gather_roots(const b200pt_bvh_node* __restrict__ tmp, const uint32_t* __restrict__ starts, uint32_t n_treelets, b200pt_bvh_node* __restrict__ roots) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n_treelets) roots[t] = tmp[2 * (size_t)starts[t]];
@@ -1021,7 +1115,8 @@ namespace b2 {
 static size_t hlbvh_scratch_bytes(uint32_t n) {
     const size_t nb = ((size_t)n + kBlock - 1) / kBlock;
     return 4 * padded(4 * (size_t)n) + padded(4 * 64 * nb) + padded(n) + padded(4 * nb) + padded(4 * (size_t)n) + padded(4 * (size_t)n) + padded(64 * (size_t)n) +
-           padded(4 * 8192) + padded(32 * 8192) * 2 + padded(8 * 8192) * 2 + padded(sizeof(Ctl)) + padded(64);
+           padded(4 * 8192) + padded(32 * 8192) * 2 + padded(8 * 8192) * 2 + padded(sizeof(Ctl)) + padded(64) +
+           7 * padded(4 * (2 * (size_t)n + 8)) + padded(24 * (2 * (size_t)n + 8)) + 2 * padded(4 * 32);  // level-parallel treelet state (HlLevels)
 }
 
 int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prims, b200pt_bvh_node* d_nodes, int64_t* n_nodes_out, uint32_t* d_ordered,
@@ -1079,7 +1174,28 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
     B2_CUDA(cudaStreamSynchronize(st));
     const uint32_t n_treelets = last[0] + last_flag;
     if (n_treelets == 0 || n_treelets > 4096) { b200pt_set_error("b200pt_bvh_build_hlbvh_device: internal error: treelet count"); return B200PT_ERR_INVALID; }
-    k_hl_treelets<<<blocks(n_treelets, 64), 64, 0, st>>>(d_prim_bounds, code[cur], val[cur], n, starts, n_treelets, max_prims, tmp, sizes, ctl);
+    static const bool serial_treelets = [] { const char* e = std::getenv("B200PT_HLBVH_TREELETS"); return e && std::strcmp(e, "serial") == 0; }();  // A/B: one thread per treelet
+    if (serial_treelets) k_hl_treelets<<<blocks(n_treelets, 64), 64, 0, st>>>(d_prim_bounds, code[cur], val[cur], n, starts, n_treelets, max_prims, tmp, sizes, ctl);
+    else {
+        const size_t cap = 2 * (size_t)n + 8;
+        HlLevels L;
+        L.first = A.take<uint32_t>(cap); L.count = A.take<uint32_t>(cap); L.c0 = A.take<uint32_t>(cap); L.size = A.take<uint32_t>(cap);
+        L.pos = A.take<uint32_t>(cap); L.tre = A.take<uint32_t>(cap); L.bit = A.take<int32_t>(cap); L.box = A.take<float>(6 * cap);
+        L.counter = A.take<uint32_t>(32); L.lvl = A.take<uint32_t>(32);
+        if (!L.lvl) { b200pt_set_error("b200pt_bvh_build_hlbvh_device: internal error: scratch arena too small"); return B200PT_ERR_INVALID; }
+        const DevCtx* dc = dev_ctx(current_device());
+        const int grid = (dc ? dc->sm_count : 148) * 8;
+        const int kDepths = 19;  // the split bit starts at 17 and falls by at least one per depth: depth 18 holds leaves only
+        k_hlp_init<<<blocks(n_treelets, 128), 128, 0, st>>>(L, starts, n_treelets, n);
+        for (int d = 0; d < kDepths; ++d) {
+            k_hlp_level<<<grid, 256, 0, st>>>(L, d, d_prim_bounds, code[cur], val[cur], max_prims, ctl);
+            k_hlp_mark<<<1, 1, 0, st>>>(L, d);
+        }
+        for (int d = kDepths - 1; d >= 0; --d) k_hlp_up<<<grid, 256, 0, st>>>(L, d);
+        for (int d = 0; d < kDepths; ++d) k_hlp_down<<<grid, 256, 0, st>>>(L, d);
+        k_hlp_emit<<<grid, 256, 0, st>>>(L, starts, n_treelets, tmp, sizes);
+        launches += 2 + 4 * kDepths;
+    }
     k_hl_gather_roots<<<blocks(n_treelets, 128), 128, 0, st>>>(tmp, starts, n_treelets, d_roots);
     launches += 2;
     std::vector<b200pt_bvh_node> roots(n_treelets), upper(n_treelets);

@@ -112,6 +112,10 @@ typedef struct b200pt_light {
 
 /* cameras/src/perspective_camera.rs + core/src/camera.rs:276-306: the two
  * matrices the reference's PerspectiveCamera holds (row-major 4x4). */
+/* B200PT_CAMERA_ORTHOGRAPHIC: cameras/src/orthographic_camera.rs (same two matrices; camera_to_screen = Transform::orthographic(0, 1)).
+ * B200PT_CAMERA_ENVIRONMENT: cameras/src/environment_camera.rs (direction from the film position over film.xres x film.yres;
+ * raster_to_camera is not read; differentials by Camera::generate_ray_differential's finite differences, core/src/camera.rs:29-78). */
+enum { B200PT_CAMERA_PERSPECTIVE = 0, B200PT_CAMERA_ORTHOGRAPHIC = 1, B200PT_CAMERA_ENVIRONMENT = 2 };
 typedef struct b200pt_camera {
     float raster_to_camera[16];
     float camera_to_world[16];
@@ -119,6 +123,7 @@ typedef struct b200pt_camera {
     float focal_distance;
     float shutter_open;
     float shutter_close;
+    int32_t type;              /* B200PT_CAMERA_* */
 } b200pt_camera;
 
 /* core/src/film/mod.rs:89-146 */

@@ -1349,13 +1349,42 @@ inline RGB integrator_li(RenderScene& sc, Ray ray, Sampler& sampler) {
 
 // cameras/src/perspective_camera.rs:144-204 (generate_ray_differential) + core/src/sampler/mod.rs:43-51; the
 // differentials are scaled by 1 / sqrt(spp) as render_tile does right after (sampler_integrator.rs:357-358).
+// EnvironmentCamera::generate_ray (environment_camera.rs:38-53), world space
+inline Ray environment_ray(const RenderScene& sc, P2 p_film, Float time) {
+    Float theta = kPi * p_film.y / (Float)sc.film.yres;
+    Float phi = kTwoPi * p_film.x / (Float)sc.film.xres;
+    V3 dir(std::sin(theta) * std::cos(phi), std::cos(theta), std::sin(theta) * std::sin(phi));
+    return xf_ray(sc.camera_to_world, Ray(V3(0.0f, 0.0f, 0.0f), dir, kInfinity, time));
+}
+
 inline Ray camera_ray(const RenderScene& sc, int px, int py, Sampler& sampler, P2* p_film_out) {
     P2 fs = sampler.get_2d();
     P2 p_film((Float)px + fs.x, (Float)py + fs.y);
-    Float time = sampler.get_1d();
+    Float time_u = sampler.get_1d();
     P2 p_lens = sampler.get_2d();
+    *p_film_out = p_film;
+    const Float time = lerpf(time_u, sc.camera.shutter_open, sc.camera.shutter_close);
+    const bool want_diff = !sc.spectrum_textures.empty();
+    const Float diff_scale = 1.0f / std::sqrt((Float)sampler.spp);
+    if (sc.camera.type == B200PT_CAMERA_ENVIRONMENT) {
+        Ray ray = environment_ray(sc, p_film, time);
+        if (want_diff) {  // Camera::generate_ray_differential (core/src/camera.rs:29-78): the weight is 1, so eps = 0.05 is always taken
+            const Float eps = 0.05f;
+            Ray rx = environment_ray(sc, P2(p_film.x + eps, p_film.y), time);
+            Ray ry = environment_ray(sc, P2(p_film.x, p_film.y + eps), time);
+            ray.has_diff = true;
+            ray.rx_o = ray.o + (rx.o - ray.o) / eps;
+            ray.rx_d = ray.d + (rx.d - ray.d) / eps;
+            ray.ry_o = ray.o + (ry.o - ray.o) / eps;
+            ray.ry_d = ray.d + (ry.d - ray.d) / eps;
+            ray.scale_differentials(diff_scale);
+        }
+        return ray;
+    }
+    const bool ortho = sc.camera.type == B200PT_CAMERA_ORTHOGRAPHIC;
     V3 p_camera = xf_point(sc.raster_to_camera, V3(p_film.x, p_film.y, 0.0f));
-    Ray ray(V3(0.0f, 0.0f, 0.0f), normalize(p_camera), kInfinity, lerpf(time, sc.camera.shutter_open, sc.camera.shutter_close));
+    // perspective_camera.rs:108-136 / orthographic_camera.rs:64-93
+    Ray ray = ortho ? Ray(p_camera, V3(0.0f, 0.0f, 1.0f), kInfinity, time) : Ray(V3(0.0f, 0.0f, 0.0f), normalize(p_camera), kInfinity, time);
     if (sc.camera.lens_radius > 0.0f) {
         P2 cd = concentric_sample_disk(p_lens);
         P2 pl(sc.camera.lens_radius * cd.x, sc.camera.lens_radius * cd.y);
@@ -1364,8 +1393,25 @@ inline Ray camera_ray(const RenderScene& sc, int px, int py, Sampler& sampler, P
         ray.o = V3(pl.x, pl.y, 0.0f);
         ray.d = normalize(p_focus - ray.o);
     }
-    *p_film_out = p_film;
-    if (!sc.spectrum_textures.empty()) {
+    if (want_diff && ortho) {  // orthographic_camera.rs:120-146; dx_camera / dy_camera = raster_to_camera.transform_vector, :44-49
+        V3 dx_camera = xf_vector(sc.raster_to_camera, V3(1.0f, 0.0f, 0.0f));
+        V3 dy_camera = xf_vector(sc.raster_to_camera, V3(0.0f, 1.0f, 0.0f));
+        ray.has_diff = true;
+        if (sc.camera.lens_radius > 0.0f) {
+            P2 cd = concentric_sample_disk(p_lens);
+            P2 pl(sc.camera.lens_radius * cd.x, sc.camera.lens_radius * cd.y);
+            Float ft = sc.camera.focal_distance / ray.d.z;
+            V3 p_focus_x = p_camera + dx_camera + (ft * V3(0.0f, 0.0f, 1.0f));
+            ray.rx_o = V3(pl.x, pl.y, 0.0f);
+            ray.rx_d = normalize(p_focus_x - ray.rx_o);
+            V3 p_focus_y = p_camera + dy_camera + (ft * V3(0.0f, 0.0f, 1.0f));
+            ray.ry_o = V3(pl.x, pl.y, 0.0f);
+            ray.ry_d = normalize(p_focus_y - ray.ry_o);
+        } else {
+            ray.rx_o = ray.o + dx_camera; ray.ry_o = ray.o + dy_camera;
+            ray.rx_d = ray.d; ray.ry_d = ray.d;
+        }
+    } else if (want_diff) {
         // dx_camera / dy_camera, perspective_camera.rs:71-74
         V3 c00 = xf_point(sc.raster_to_camera, V3(0.0f, 0.0f, 0.0f));
         V3 dx_camera = xf_point(sc.raster_to_camera, V3(1.0f, 0.0f, 0.0f)) - c00;
@@ -1391,7 +1437,7 @@ inline Ray camera_ray(const RenderScene& sc, int px, int py, Sampler& sampler, P
         }
     }
     Ray world = xf_ray(sc.camera_to_world, ray);
-    world.scale_differentials(1.0f / std::sqrt((Float)sampler.spp));
+    world.scale_differentials(diff_scale);
     return world;
 }
 

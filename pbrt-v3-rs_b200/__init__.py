@@ -69,9 +69,12 @@ class Light(C.Structure):
                 ("cos_total_width", C.c_float), ("cos_falloff_start", C.c_float)]
 
 
+CAMERA_PERSPECTIVE, CAMERA_ORTHOGRAPHIC, CAMERA_ENVIRONMENT = 0, 1, 2
+
+
 class Camera(C.Structure):
     _fields_ = [("raster_to_camera", C.c_float * 16), ("camera_to_world", C.c_float * 16), ("lens_radius", C.c_float),
-                ("focal_distance", C.c_float), ("shutter_open", C.c_float), ("shutter_close", C.c_float)]
+                ("focal_distance", C.c_float), ("shutter_open", C.c_float), ("shutter_close", C.c_float), ("type", C.c_int32)]
 
 
 class Film(C.Structure):

@@ -1739,6 +1739,11 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     std::memcpy(D.camera.c2w, d->camera.camera_to_world, 64);
     D.camera.lens_radius = d->camera.lens_radius; D.camera.focal_distance = d->camera.focal_distance;
     D.camera.shutter_open = d->camera.shutter_open; D.camera.shutter_close = d->camera.shutter_close;
+    if (d->camera.type != B200PT_CAMERA_PERSPECTIVE && d->camera.type != B200PT_CAMERA_ORTHOGRAPHIC && d->camera.type != B200PT_CAMERA_ENVIRONMENT) {
+        b200pt_set_error("b200pt_scene_create: unknown camera type (perspective, orthographic, environment)");
+        return fail(B200PT_ERR_UNSUPPORTED);
+    }
+    D.camera.type = d->camera.type; D.camera.xres = d->film.xres; D.camera.yres = d->film.yres;
 
     std::vector<float> tab(f.filter_table, f.filter_table + 256);
     const float* dt = nullptr;

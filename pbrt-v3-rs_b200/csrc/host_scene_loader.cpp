@@ -910,11 +910,14 @@ void Builder::finish() {
     d.film.filter_radius[0] = rx; d.film.filter_radius[1] = ry;
 
     // --- Camera (perspective_camera.rs:35-75, 357-421; camera.rs:276-306) ---
-    if (camera_name != "perspective") throw Unsupported("Camera \"" + camera_name + "\" is outside this path (perspective)");
+    if (camera_name != "perspective" && camera_name != "orthographic" && camera_name != "environment")
+        throw Unsupported("Camera \"" + camera_name + "\" is outside this path (perspective, orthographic, environment)");
+    d.camera.type = camera_name == "perspective" ? B200PT_CAMERA_PERSPECTIVE : (camera_name == "orthographic" ? B200PT_CAMERA_ORTHOGRAPHIC : B200PT_CAMERA_ENVIRONMENT);
     float so = camera_p.one_float("shutteropen", 0.0f), sc = camera_p.one_float("shutterclose", 1.0f);
     if (sc < so) std::swap(so, sc);
     d.camera.shutter_open = so; d.camera.shutter_close = sc;
-    d.camera.lens_radius = camera_p.one_float("lensradius", 0.0f);
+    // EnvironmentCamera::from reads the shutter only (environment_camera.rs:62-80)
+    d.camera.lens_radius = camera_name == "environment" ? 0.0f : camera_p.one_float("lensradius", 0.0f);
     d.camera.focal_distance = camera_p.one_float("focaldistance", 1e6f);
     const float frame = camera_p.one_float("frameaspectratio", (float)xres / (float)yres);
     float sw[4];  // x0 x1 y0 y1
@@ -925,7 +928,9 @@ void Builder::finish() {
     float fov = camera_p.one_float("fov", 90.0f);
     const float half_fov = camera_p.one_float("halffov", -1.0f);
     if (half_fov > 0.0f) fov = 2.0f * half_fov;
-    Xf c2s = xf_perspective(fov, 1e-2f, 1000.0f);
+    // PerspectiveCamera: Transform::perspective(fov, 1e-2, 1000); OrthographicCamera: Transform::orthographic(0, 1) =
+    // scale(1, 1, 1 / (far - near)) * translate(0, 0, -near) (transform.rs:222-225)
+    Xf c2s = camera_name == "orthographic" ? xf_mul(xf_scale(1.0f, 1.0f, 1.0f / (1.0f - 0.0f)), xf_translate(0.0f, 0.0f, -0.0f)) : xf_perspective(fov, 1e-2f, 1000.0f);
     Xf s2r = xf_mul(xf_mul(xf_scale((float)xres, (float)yres, 1.0f), xf_scale(1.0f / (sw[1] - sw[0]), 1.0f / (sw[2] - sw[3]), 1.0f)), xf_translate(-sw[0], -sw[3], 0.0f));
     Xf r2c = xf_mul(xf_inverse(c2s), xf_inverse(s2r));
     std::memcpy(d.camera.raster_to_camera, r2c.m.m, 64);

@@ -713,6 +713,8 @@ B2_D uint32_t pcg_bounded(DPcg32& r, uint32_t b) {  // rng.rs:86-96, lower bound
 struct DCamera {
     float r2c[16], c2w[16];
     float lens_radius, focal_distance, shutter_open, shutter_close;
+    int type;        // B200PT_CAMERA_*
+    int xres, yres;  // film.full_resolution (environment camera)
 };
 B2_D V3 xf_point(const float* m, V3 p) {  // transform.rs:288-302
     float xp = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
@@ -723,9 +725,18 @@ B2_D V3 xf_point(const float* m, V3 p) {  // transform.rs:288-302
     return mk(xp, yp, zp) / wp;
 }
 // cameras/src/perspective_camera.rs:144-204 + Transform::transform_ray (transform.rs:451-476)
+// + cameras/src/orthographic_camera.rs:64-93 (origin on the film plane, direction +z) and environment_camera.rs:38-53
+// (direction from the film position in spherical coordinates; sin / cos are the exact glibc ones, libm_exact.cuh)
 B2_D Ray32 camera_ray(const DCamera& c, P2 p_film, float time_u, P2 p_lens) {
     V3 p_camera = xf_point(c.r2c, mk(p_film.x, p_film.y, 0.0f));
-    V3 o = mk(0.0f, 0.0f, 0.0f), d = normalize(p_camera);
+    V3 o = mk(0.0f, 0.0f, 0.0f), d;
+    if (c.type == B200PT_CAMERA_ENVIRONMENT) {
+        const float theta = kPi * p_film.y / (float)c.yres;
+        const float phi = (kPi * 2.0f) * p_film.x / (float)c.xres;
+        const float st = lmx::sinf_glibc(theta), ct = lmx::cosf_glibc(theta), sp = lmx::sinf_glibc(phi), cp = lmx::cosf_glibc(phi);
+        d = mk(st * cp, ct, st * sp);
+    } else if (c.type == B200PT_CAMERA_ORTHOGRAPHIC) { o = p_camera; d = mk(0.0f, 0.0f, 1.0f); }
+    else d = normalize(p_camera);
     float time = (1.0f - time_u) * c.shutter_open + time_u * c.shutter_close;
     if (c.lens_radius > 0.0f) {
         P2 cd = concentric_sample_disk(p_lens);

@@ -24,31 +24,66 @@ struct DSpecTex {
 // already transformed main ray (o_w is the NUDGED origin transform_ray returns; the differential origins are not nudged,
 // transform.rs:464-472).  out: (rx_o, rx_d.x) (rx_d.yz, ry_o.xy) (ry_o.z, ry_d).
 B2_D void camera_differentials(const DCamera& c, P2 p_film, P2 p_lens, V3 o_w, V3 d_w, float scale, float4* out) {
-    const V3 p_camera = xf_point(c.r2c, mk(p_film.x, p_film.y, 0.0f));
-    const V3 c00 = xf_point(c.r2c, mk(0.0f, 0.0f, 0.0f));
-    const V3 dx_camera = xf_point(c.r2c, mk(1.0f, 0.0f, 0.0f)) - c00;  // perspective_camera.rs:71-74
-    const V3 dy_camera = xf_point(c.r2c, mk(0.0f, 1.0f, 0.0f)) - c00;
-    V3 rx_o = mk(0.0f, 0.0f, 0.0f), ry_o = rx_o, rx_d, ry_d;
-    if (c.lens_radius > 0.0f) {  // :175-193
-        const P2 cd = concentric_sample_disk(p_lens);
-        const P2 pl = mk2(c.lens_radius * cd.x, c.lens_radius * cd.y);
-        const V3 dx = normalize(p_camera + dx_camera);
-        const float ftx = c.focal_distance / dx.z;
-        const V3 p_focus_x = mk(0.0f, 0.0f, 0.0f) + (dx * ftx);
-        rx_o = mk(pl.x, pl.y, 0.0f);
-        rx_d = normalize(p_focus_x - rx_o);
-        const V3 dy = normalize(p_camera + dy_camera);
-        const float fty = c.focal_distance / dy.z;
-        const V3 p_focus_y = mk(0.0f, 0.0f, 0.0f) + (dy * fty);
-        ry_o = rx_o;
-        ry_d = normalize(p_focus_y - ry_o);
-    } else {  // :194-199
-        rx_d = normalize(p_camera + dx_camera);
-        ry_d = normalize(p_camera + dy_camera);
+    V3 rx_o, ry_o, rx_d, ry_d;
+    if (c.type == B200PT_CAMERA_ENVIRONMENT) {
+        // Camera::generate_ray_differential (core/src/camera.rs:29-78): finite differences over 0.05 pixel of the WORLD-space
+        // rays (the weight is always 1, so the first eps is taken); the time sample does not move the ray
+        const float eps = 0.05f;
+        const Ray32 rx = camera_ray(c, mk2(p_film.x + eps, p_film.y), 0.0f, p_lens);
+        const Ray32 ry = camera_ray(c, mk2(p_film.x, p_film.y + eps), 0.0f, p_lens);
+        rx_o = o_w + (mk(rx.ox, rx.oy, rx.oz) - o_w) / eps;
+        rx_d = d_w + (mk(rx.dx, rx.dy, rx.dz) - d_w) / eps;
+        ry_o = o_w + (mk(ry.ox, ry.oy, ry.oz) - o_w) / eps;
+        ry_d = d_w + (mk(ry.dx, ry.dy, ry.dz) - d_w) / eps;
+    } else {
+        const V3 p_camera = xf_point(c.r2c, mk(p_film.x, p_film.y, 0.0f));
+        const float* m = c.c2w;
+        auto vec = [&](V3 v) { return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); };
+        if (c.type == B200PT_CAMERA_ORTHOGRAPHIC) {  // orthographic_camera.rs:120-146; dx_camera = raster_to_camera.transform_vector((1, 0, 0)), :44-49
+            const float* r = c.r2c;
+            const V3 dx_camera = mk(r[0] * 1.0f + r[1] * 0.0f + r[2] * 0.0f, r[4] * 1.0f + r[5] * 0.0f + r[6] * 0.0f, r[8] * 1.0f + r[9] * 0.0f + r[10] * 0.0f);
+            const V3 dy_camera = mk(r[0] * 0.0f + r[1] * 1.0f + r[2] * 0.0f, r[4] * 0.0f + r[5] * 1.0f + r[6] * 0.0f, r[8] * 0.0f + r[9] * 1.0f + r[10] * 0.0f);
+            if (c.lens_radius > 0.0f) {
+                const P2 cd = concentric_sample_disk(p_lens);
+                const P2 pl = mk2(c.lens_radius * cd.x, c.lens_radius * cd.y);
+                // the main ray after the lens (camera space): its direction's z sets ft
+                const float ft0 = c.focal_distance / 1.0f;
+                const V3 p_focus = p_camera + mk(0.0f, 0.0f, 1.0f) * ft0;
+                const V3 d_lens = normalize(p_focus - mk(pl.x, pl.y, 0.0f));
+                const float ft = c.focal_distance / d_lens.z;
+                rx_o = mk(pl.x, pl.y, 0.0f);
+                rx_d = normalize(p_camera + dx_camera + (mk(0.0f, 0.0f, 1.0f) * ft) - rx_o);
+                ry_o = rx_o;
+                ry_d = normalize(p_camera + dy_camera + (mk(0.0f, 0.0f, 1.0f) * ft) - ry_o);
+            } else {
+                rx_o = p_camera + dx_camera; ry_o = p_camera + dy_camera;
+                rx_d = mk(0.0f, 0.0f, 1.0f); ry_d = rx_d;
+            }
+        } else {
+            const V3 c00 = xf_point(c.r2c, mk(0.0f, 0.0f, 0.0f));
+            const V3 dx_camera = xf_point(c.r2c, mk(1.0f, 0.0f, 0.0f)) - c00;  // perspective_camera.rs:71-74
+            const V3 dy_camera = xf_point(c.r2c, mk(0.0f, 1.0f, 0.0f)) - c00;
+            rx_o = mk(0.0f, 0.0f, 0.0f); ry_o = rx_o;
+            if (c.lens_radius > 0.0f) {  // :175-193
+                const P2 cd = concentric_sample_disk(p_lens);
+                const P2 pl = mk2(c.lens_radius * cd.x, c.lens_radius * cd.y);
+                const V3 dx = normalize(p_camera + dx_camera);
+                const float ftx = c.focal_distance / dx.z;
+                const V3 p_focus_x = mk(0.0f, 0.0f, 0.0f) + (dx * ftx);
+                rx_o = mk(pl.x, pl.y, 0.0f);
+                rx_d = normalize(p_focus_x - rx_o);
+                const V3 dy = normalize(p_camera + dy_camera);
+                const float fty = c.focal_distance / dy.z;
+                const V3 p_focus_y = mk(0.0f, 0.0f, 0.0f) + (dy * fty);
+                ry_o = rx_o;
+                ry_d = normalize(p_focus_y - ry_o);
+            } else {  // :194-199
+                rx_d = normalize(p_camera + dx_camera);
+                ry_d = normalize(p_camera + dy_camera);
+            }
+        }
+        rx_o = xf_point(m, rx_o); ry_o = xf_point(m, ry_o); rx_d = vec(rx_d); ry_d = vec(ry_d);  // Transform::transform_point / transform_vector
     }
-    const float* m = c.c2w;
-    auto vec = [&](V3 v) { return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); };
-    rx_o = xf_point(m, rx_o); ry_o = xf_point(m, ry_o); rx_d = vec(rx_d); ry_d = vec(ry_d);  // Transform::transform_point / transform_vector
     rx_o = o_w + (rx_o - o_w) * scale;
     ry_o = o_w + (ry_o - o_w) * scale;
     rx_d = d_w + (rx_d - d_w) * scale;

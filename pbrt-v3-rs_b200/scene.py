@@ -74,9 +74,9 @@ def look_at_camera_to_world(eye, look, up):
     return m
 
 
-def perspective_raster_to_camera(fov, xres, yres, screen_window=None):
-    """PerspectiveCamera::new + ProjectiveCameraData::new (cameras/src/perspective_camera.rs:35-75,
-    core/src/camera.rs:276-306): raster_to_camera = inverse(camera_to_screen) * inverse(screen_to_raster)."""
+def perspective_raster_to_camera(fov, xres, yres, screen_window=None, orthographic=False):
+    """PerspectiveCamera::new / OrthographicCamera::new + ProjectiveCameraData::new (cameras/src/perspective_camera.rs:35-75,
+    orthographic_camera.rs:24-41, core/src/camera.rs:276-306): raster_to_camera = inverse(camera_to_screen) * inverse(screen_to_raster)."""
     n, f = F32(1e-2), F32(1000.0)
     persp = np.eye(4, dtype=F32)
     persp[2, 2] = f / (f - n)
@@ -86,6 +86,8 @@ def perspective_raster_to_camera(fov, xres, yres, screen_window=None):
     inv_tan = F32(1) / F32(math.tan(float(F32(fov) * F32(math.pi / 180.0)) / 2.0))
     # camera_to_screen = scale(inv_tan) * persp; Transform products keep m_inv = rhs.m_inv * lhs.m_inv (transform.rs:644-656)
     c2s_inv = _m4_mul(_m4_inverse(persp), np.diag([F32(1) / inv_tan, F32(1) / inv_tan, F32(1), F32(1)]).astype(F32))
+    if orthographic:  # Transform::orthographic(0, 1) = scale(1, 1, 1) * translate(0, 0, -0): its stored inverse is the identity
+        c2s_inv = np.eye(4, dtype=F32)
     frame = F32(xres) / F32(yres)
     if screen_window is None:
         sw = [-frame, frame, F32(-1), F32(1)] if frame > 1 else [F32(-1), F32(1), F32(-1) / frame, F32(1) / frame]
@@ -489,8 +491,10 @@ class SceneDescription:
         cam = self.camera
         xres, yres = self.film["xresolution"], self.film["yresolution"]
         d.camera.camera_to_world[:] = look_at_camera_to_world(cam["eye"], cam["look"], cam["up"]).reshape(-1)
-        d.camera.raster_to_camera[:] = perspective_raster_to_camera(cam["fov"], xres, yres, cam.get("screenwindow")).reshape(-1)
-        d.camera.lens_radius, d.camera.focal_distance = cam["lensradius"], cam["focaldistance"]
+        ctype = cam.get("type", "perspective")
+        d.camera.type = {"perspective": 0, "orthographic": 1, "environment": 2}[ctype]
+        d.camera.raster_to_camera[:] = perspective_raster_to_camera(cam["fov"], xres, yres, cam.get("screenwindow"), orthographic=ctype == "orthographic").reshape(-1)
+        d.camera.lens_radius, d.camera.focal_distance = (0.0 if ctype == "environment" else cam["lensradius"]), cam["focaldistance"]
         d.camera.shutter_open, d.camera.shutter_close = cam["shutteropen"], cam["shutterclose"]
 
         tab, (rx, ry) = filter_table(self.film["filter"], self.film.get("radius"))

@@ -1,17 +1,17 @@
 """Execution-level pin of the oracle - and of the CUDA path - to the reference: its own committed renders.
 
 The reference cannot be built here or on the GPU box (no Rust toolchain, profiles/r2_toolchain_probe.txt), but its tree
-holds images it rendered itself.  Seven of the shipped scenes lie entirely on this path:
+holds images it rendered itself.  Nine of the shipped scenes lie entirely on this path:
 
   scenes/lights/{point, spot, distant, infinite-no-map}.pbrt, scenes/shapes/triangles-alpha-mask.pbrt,
-  scenes/cameras/perspective.pbrt, scenes/objects/instances.pbrt
+  scenes/cameras/{perspective, orthographic, environment}.pbrt, scenes/objects/instances.pbrt
   (Whitted, Halton 128 spp, 400x400, box filter, a matte cube - or ten ObjectInstances of it - over a ground quad with a
   checkerboard "Kd" texture, point / spot / distant (blackbody) / infinite lights, a "dots" alpha mask)
 
 The Halton sampler is deterministic, so the whole image has to come out the same after the reference's own encode
 (core/src/image_io.rs:384-390: clamp(255 * gamma_correct(v) + 0.5) as u8) - stochastic infinite-light estimate, closed-form
-filtered checkerboard (camera ray differentials, compute_differentials) and all.  It does: three scenes equal the
-reference's PNG on all 160 000 pixels, the other three on all but <= 5 pixels that are one level off.
+filtered checkerboard (camera ray differentials, compute_differentials) and all.  It does: four scenes equal the
+reference's PNG on all 160 000 pixels, the other five on all but <= 6 pixels.
 
 tests/golden/ref_renders/*.png are copies of the reference's renders (tools/copy_reference_renders.py)."""
 import os
@@ -31,7 +31,7 @@ CUBE = '''Shape "trianglemesh"
 HEAD = '''%(camera)s
 Sampler "halton" "integer pixelsamples" %(spp)d
 Integrator "whitted"
-Film "image" "string filename" "x.pfm" "integer xresolution" [400] "integer yresolution" [400]
+Film "image" "string filename" "x.pfm" "integer xresolution" [%(xres)d] "integer yresolution" [%(yres)d]
 WorldBegin
 '''
 # per scene: the camera lines of the scene file, the equivalent (eye, look, fov) for the ground-parity computation, the two
@@ -45,8 +45,11 @@ CAMERA = {
     "perspective": ('LookAt 0 2 2  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 2, 2), (0, 0, 0), 90.0),
     # "LookAt ..; Translate 0 -1 0; Camera": the camera sits at world (0, 8, 15) and looks at (0, 1, 0)
     "instances": ('LookAt 0 7 15  0 0 0  0 0 1\nTranslate 0 -1 0\nCamera "perspective" "float fov" 45', (0, 8, 15), (0, 1, 0), 45.0),
+    "orthographic": ('LookAt 0 10 10  0 0 0  0 0 1\nCamera "orthographic"', None, None, None),
+    "environment": ('LookAt 0 0 1  0 1 0  0 0 1\nCamera "environment"', None, None, None),
 }
-ALBEDO = {"point": (0.3, 0.8), "infinite-no-map": (0.3, 0.8), "triangles-alpha-mask": (0.3, 0.8), "distant": (0.3, 0.8), "spot": (0.3, 0.8), "perspective": (0.1, 0.8), "instances": (0.1, 0.8)}
+RESOLUTION = {"environment": (800, 400)}  # the others: 400 x 400
+ALBEDO = {"point": (0.3, 0.8), "infinite-no-map": (0.3, 0.8), "triangles-alpha-mask": (0.3, 0.8), "distant": (0.3, 0.8), "spot": (0.3, 0.8), "perspective": (0.1, 0.8), "instances": (0.1, 0.8), "orthographic": (0.1, 0.8), "environment": (0.1, 0.8)}
 GROUND = '''  AttributeBegin
     Translate 0 0 -1
     Material "matte" "rgb Kd" [%g %g %g]
@@ -114,6 +117,27 @@ BODY = {
     ObjectInstance "cube"
   AttributeEnd
 ''' % (36 * k) for k in range(10)),
+    # the whole world under "Scale 0.25 0.25 0.25" (the CTM the lights were declared in is not scaled)
+    "orthographic": '''  LightSource "infinite" "rgb L" [.4 .45 .5]
+  LightSource "distant" "point from" [ -30 40  100 ] "blackbody L" [3000 1.5]
+  Scale 0.25 0.25 0.25
+  AttributeBegin
+    Rotate 45 0 0 1
+    Material "matte" "rgb Kd" [.2 .01 .01]
+    %(cube)s
+  AttributeEnd
+''',
+    # ten cubes on a circle around the camera (plain shapes, no instancing)
+    "environment": '''  LightSource "infinite" "rgb L" [.4 .45 .5]
+  LightSource "distant" "point from" [ -30 40  100 ] "blackbody L" [3000 1.5]
+  Material "matte" "rgb Kd" [.8 .1 .01]
+''' + "".join('''  AttributeBegin
+    %s
+    Translate 0 5 0
+    Rotate 45 0 0 1
+    %%(cube)s
+  AttributeEnd
+''' % ("Rotate %d 0 0 1" % (36 * k) if k else "") for k in range(10)),
     "triangles-alpha-mask": '''  LightSource "point" "rgb I" [.4 .45 .5] "point from" [-5 0 5] "rgb scale" [200 200 200]
   AttributeBegin
     Texture "alpha" "float" "dots" "float inside" %(inside)g "float outside" %(outside)g "float uscale" 10 "float vscale" 10
@@ -130,7 +154,8 @@ def scene_file(tmp_path, which, ground_kd=None, spp=128, inside=1.0, outside=0.0
     """ground_kd None: the checkerboard texture of the scene file; a number: a constant albedo instead (counterfactuals)."""
     p = tmp_path / ("%s_%s_%d_%g_%d.pbrt" % (which, ground_kd, spp, inside, len(texture_extra)))
     ground = GROUND % (ground_kd, ground_kd, ground_kd) if ground_kd is not None else GROUND_CHECKS % dict(a=ALBEDO[which][0], b=ALBEDO[which][1], extra=texture_extra)
-    p.write_text(HEAD % dict(camera=CAMERA[which][0], spp=spp) + BODY[which] % dict(cube=CUBE, inside=inside, outside=outside) + ground)
+    xres, yres = RESOLUTION.get(which, (400, 400))
+    p.write_text(HEAD % dict(camera=CAMERA[which][0], spp=spp, xres=xres, yres=yres) + BODY[which] % dict(cube=CUBE, inside=inside, outside=outside) + ground)
     return str(p)
 
 
@@ -144,7 +169,7 @@ def encode_8bit(rgb):
 def reference_png(which):
     from PIL import Image
     a = np.array(Image.open(os.path.join(HERE, "golden", "ref_renders", which + ".png")).convert("RGB")).astype(np.int32)
-    assert a.shape == (400, 400, 3)
+    assert a.shape == RESOLUTION.get(which, (400, 400))[::-1] + (3,)
     return a
 
 
@@ -152,7 +177,8 @@ RESULTS = {}
 
 
 def _check_scene(render, tmp_path, which, tag):
-    """The whole 400x400 image against the reference's PNG: no pixel further than one 8-bit level, >= 99.99 % equal."""
+    """The whole image against the reference's PNG: >= 99.99 % of the pixels equal, none further than one 8-bit level (the
+    orthographic / environment scenes: a few edge pixels by the weight of one sample)."""
     img = encode_8bit(render(scene_file(tmp_path, which)))
     ref = reference_png(which)
     d = np.abs(img - ref).max(2)
@@ -160,8 +186,12 @@ def _check_scene(render, tmp_path, which, tag):
                  psnr_db=float(10 * np.log10(255.0 ** 2 / max(((img - ref) ** 2).mean(), 1e-12))))
     RESULTS[(tag, which)] = stats
     print(tag, which, stats)
-    assert stats["max_diff"] <= 1, stats
-    assert stats["differing"] <= 16, stats  # measured: 0 (point, distant, triangles-alpha-mask), 1-5 (the scenes with an infinite light)
+    # Measured (oracle and CUDA path alike): point / spot / distant / triangles-alpha-mask 0 differing pixels; infinite-no-map 5,
+    # perspective 1, instances 5, all one level off.  The two other cameras: orthographic 2 pixels, environment 6 of 320 000,
+    # most of them one level off, three on cube edges by 2-5 levels = ONE of the pixel's 128 samples deciding differently.
+    loose = which in ("orthographic", "environment")
+    assert stats["max_diff"] <= (6 if loose else 1), stats
+    assert stats["differing"] <= 16 * stats["pixels"] // 160000, stats
     return img, ref
 
 
@@ -171,7 +201,7 @@ def _oracle_render(path):
     return ol.OracleScene(ge.load_package().load_pbrt(path)).render()[0]
 
 
-SCENES = ["point", "infinite-no-map", "triangles-alpha-mask", "distant", "perspective", "instances", "spot"]
+SCENES = ["point", "infinite-no-map", "triangles-alpha-mask", "distant", "perspective", "instances", "spot", "orthographic", "environment"]
 
 
 @pytest.mark.parametrize("which", SCENES)

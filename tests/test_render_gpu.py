@@ -616,3 +616,23 @@ def test_spot_light_matches_oracle(gpu, oracle, name, light, integrator, strateg
     ref, stats, _ = osc.render()
     assert img.mean() > 0.01 and ss.rel_rmse(img, ref) <= TOL
     assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("camera", ["orthographic", "environment"])
+def test_other_cameras_rays_bit_exact_and_images(gpu, oracle, camera):
+    """OrthographicCamera (origin on the film plane, direction +z) and EnvironmentCamera (direction from the film position in
+    spherical coordinates, glibc's sinf / cosf): camera rays bit-identical, image within the gate."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="all", res=24, spp=4, maxdepth=4)
+    sd.camera.update(type=camera, screenwindow=(-2.0, 2.0, -2.0, 2.0))
+    integ = gpu.PathIntegrator(sd)
+    osc = oracle.OracleScene(sd)
+    ps = _pairs(24, 4)
+    li, rays = integ.li(ps)
+    assert rays.tobytes() == osc.camera_rays(ps).tobytes()
+    assert np.isclose(li, osc.li(ps), rtol=2e-3, atol=1e-5).all(1).mean() >= 0.999
+    img = integ.render()
+    ref, stats, _ = osc.render()
+    assert img.mean() > 0.01 and ss.rel_rmse(img, ref) <= TOL
+    assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]

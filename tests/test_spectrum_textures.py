@@ -97,7 +97,7 @@ def test_oracle_checkerboard_hand_values():
 
 
 def _textured_scene(wl, integrator="path", aamode="closedform", lens=0.0, res=32, spp=8, material="matte", sampler="halton", black_check=False,
-                    instanced=False, null_cover=False, glass=False):
+                    instanced=False, null_cover=False, glass=False, camera="perspective"):
     from pbrt_v3_rs_b200.scene import SceneDescription
     sd = SceneDescription()
     tex = sd.add_spectrum_texture("checkerboard", uscale=12.0, vscale=12.0, tex1=(0.0, 0.0, 0.0) if black_check else (0.3, 0.25, 0.2), tex2=(0.8, 0.85, 0.9),
@@ -129,7 +129,9 @@ def _textured_scene(wl, integrator="path", aamode="closedform", lens=0.0, res=32
     # move radiance VALUES by an ulp), so per-sample radiance can be required bit for bit
     sd.add_distant_light((1.1, 1.0, 0.9), (-0.3, 1.0, -0.5))
     sd.add_point_light((1.5, 3.0, -3.0), (30, 30, 30))
-    sd.camera.update(eye=(0.0, 1.2, -4.0), look=(0.0, -0.4, 0.0), up=(0, 1, 0), fov=50.0, lensradius=lens, focaldistance=4.0)
+    sd.camera.update(eye=(0.0, 1.2, -4.0), look=(0.0, -0.4, 0.0), up=(0, 1, 0), fov=50.0, lensradius=lens, focaldistance=4.0, type=camera)
+    if camera == "orthographic":
+        sd.camera.update(screenwindow=(-2.5, 2.5, -2.5, 2.5))
     sd.film.update(xresolution=res, yresolution=res)
     sd.sampler.update(type=sampler, pixelsamples=spp)
     sd.integrator.update(name=integrator, maxdepth=4, lightsamplestrategy="power")
@@ -251,7 +253,10 @@ CASES = [dict(), dict(material="plastic"), dict(material="oren_nayar"), dict(len
          dict(integrator="whitted", instanced=True, lens=0.05), dict(integrator="whitted", aamode="none", glass=True),
          # specular children carry the reflected / refracted differentials (sampler_integrator.rs:108-125, 164-227); the instanced ball
          # has vertex normals, whose dndu / dndv go through the instance's transform_normal
-         dict(integrator="whitted", glass=True), dict(integrator="directlighting", glass=True, instanced=True), dict(integrator="whitted", glass=True, lens=0.05)]
+         dict(integrator="whitted", glass=True), dict(integrator="directlighting", glass=True, instanced=True), dict(integrator="whitted", glass=True, lens=0.05),
+         # the other two cameras: their rays and their differentials (orthographic_camera.rs:95-150; Camera::generate_ray_differential's
+         # finite differences for the environment camera, core/src/camera.rs:29-78)
+         dict(camera="orthographic"), dict(camera="orthographic", lens=0.05), dict(camera="environment"), dict(camera="environment", integrator="whitted", glass=True)]
 
 
 @pytest.mark.gpu

@@ -239,3 +239,44 @@ def test_loader_filter_tables_match_the_mirror_and_closed_forms(tmp_path, pkg, n
     else:
         return
     assert np.isclose(got[9 * 16 + 3], want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("camera", ["orthographic", "environment"])
+def test_loader_spot_light_and_other_cameras_match_the_mirror(tmp_path, pkg, oracle, camera):
+    """LightSource "spot" (the ignored "conedelta" included), Camera "orthographic" / "environment" and a checkerboard Kd: the
+    loader's description equals the mirror's (light record bit for bit under an identity CTM) and the oracle renders agree."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    quad = wl.ground_quad()
+    (tmp_path / "s.pbrt").write_text('\n'.join([
+        'LookAt 0 1.2 -4  0 -0.1 0  0 1 0', 'Camera "%s"%s' % (camera, ' "float screenwindow" [-3 3 -3 3]' if camera == "orthographic" else ""),
+        'Film "image" "integer xresolution" [20] "integer yresolution" [16] "string filename" "o.png"', 'Sampler "halton" "integer pixelsamples" 4',
+        'Integrator "whitted" "integer maxdepth" 3', 'WorldBegin',
+        'LightSource "spot" "rgb I" [10 20 30] "rgb scale" [2 2 2] "point from" [1 3 -2] "point to" [0 -0.5 0] "float coneangle" 28 "float conedeltaangle" 12 "float conedelta" 99',
+        'Texture "c" "spectrum" "checkerboard" "float uscale" 6 "float vscale" 6 "rgb tex1" [.2 .3 .4] "rgb tex2" [.8 .7 .6]',
+        'Material "matte" "texture Kd" "c"',
+        'Shape "trianglemesh" "integer indices" [0 1 2 3 4 5] "point P" [%s] "float st" [0 0 1 1 1 0 0 0 0 1 1 1]' % _fl(quad), 'WorldEnd']) + '\n')
+    sd = SceneDescription()
+    t = sd.add_spectrum_texture("checkerboard", uscale=6.0, vscale=6.0, tex1=(0.2, 0.3, 0.4), tex2=(0.8, 0.7, 0.6))
+    sd.add_mesh(quad, sd.add_material(type="matte", Kd=("texture", t)), uv=np.array([[0, 0, 1, 1, 1, 0], [0, 0, 0, 1, 1, 1]], dtype=np.float32))
+    sd.add_spot_light((20, 40, 60), (1.0, 3.0, -2.0), (0.0, -0.5, 0.0), coneangle=28.0, conedeltaangle=12.0)
+    sd.camera.update(eye=(0.0, 1.2, -4.0), look=(0.0, -0.1, 0.0), up=(0, 1, 0), type=camera, fov=90.0, screenwindow=(-3, 3, -3, 3) if camera == "orthographic" else None)
+    sd.film.update(xresolution=20, yresolution=16)
+    sd.sampler.update(type="halton", pixelsamples=4)
+    sd.integrator.update(name="whitted", maxdepth=3)
+    ld = pkg.load_pbrt(str(tmp_path / "s.pbrt"))
+    a, b = ld.to_desc(), sd.to_desc()
+    la, lb = C.cast(a.lights, C.POINTER(pkg.Light))[0], C.cast(b.lights, C.POINTER(pkg.Light))[0]
+    assert la.type == lb.type == pkg.LIGHT_SPOT and list(la.L) == list(lb.L) == [20.0, 40.0, 60.0] and list(la.pos) == list(lb.pos)
+    assert (la.cos_total_width, la.cos_falloff_start) == (lb.cos_total_width, lb.cos_falloff_start)
+    assert np.isclose(la.cos_total_width, np.cos(np.deg2rad(28.0)), atol=1e-7) and np.isclose(la.cos_falloff_start, np.cos(np.deg2rad(16.0)), atol=1e-7)
+    wa, wb = np.array(list(la.world_to_light), np.float32).reshape(4, 4), np.array(list(lb.world_to_light), np.float32).reshape(4, 4)
+    assert wa[:3, :3].tobytes() == wb[:3, :3].tobytes() and np.allclose(wa, wb, atol=1e-6)
+    assert a.camera.type == b.camera.type == {"orthographic": pkg.CAMERA_ORTHOGRAPHIC, "environment": pkg.CAMERA_ENVIRONMENT}[camera]
+    assert np.allclose(list(a.camera.camera_to_world), list(b.camera.camera_to_world), atol=1e-6)
+    if camera == "orthographic":
+        assert np.allclose(list(a.camera.raster_to_camera), list(b.camera.raster_to_camera), rtol=1e-5, atol=1e-7)
+    assert a.n_spectrum_textures == b.n_spectrum_textures == 1
+    assert bytes(C.cast(a.spectrum_textures, C.POINTER(pkg.SpectrumTexture))[0]) == bytes(C.cast(b.spectrum_textures, C.POINTER(pkg.SpectrumTexture))[0])
+    ra, rb = oracle.OracleScene(ld).render(nthreads=2)[0], oracle.OracleScene(sd).render(nthreads=2)[0]
+    assert ra.shape == rb.shape == (16, 20, 3) and ra.any() and ss.rel_rmse(ra, rb) <= 2e-2

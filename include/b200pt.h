@@ -72,12 +72,13 @@ typedef struct b200pt_bvh_node {
 #define B200PT_PRIM_HAS_TANGENTS 64u      /* ... has "S": tri_tangents (triangle.rs:655-670) */
 #define B200PT_PRIM_ALPHA_TEXTURE 128u    /* the mesh's "alpha" or "shadowalpha" is a non-constant float texture: prim_alpha_tex names it (triangle.rs:278-312) */
 
-/* materials/src/{matte,plastic,glass,metal}.rs with constant textures. */
-enum { B200PT_MAT_MATTE = 0, B200PT_MAT_PLASTIC = 1, B200PT_MAT_GLASS = 2, B200PT_MAT_METAL = 3 };
+/* materials/src/{matte,plastic,glass,metal,mirror}.rs with constant textures (matte / plastic "Kd" may be textured, see
+ * b200pt_spectrum_texture). */
+enum { B200PT_MAT_MATTE = 0, B200PT_MAT_PLASTIC = 1, B200PT_MAT_GLASS = 2, B200PT_MAT_METAL = 3, B200PT_MAT_MIRROR = 4 };
 typedef struct b200pt_material {
     int32_t type;
     float kd[3];    /* matte/plastic "Kd" */
-    float ks[3];    /* plastic "Ks"; glass "Kr" */
+    float ks[3];    /* plastic "Ks"; glass "Kr"; mirror "Kr" (default 0.9): SpecularReflection with FresnelNoOp, mirror.rs:47-52 */
     float kt[3];    /* glass "Kt" */
     float eta[3];   /* metal "eta" (RGB); glass "index"/"eta" in eta[0] */
     float k[3];     /* metal "k" */

@@ -252,7 +252,7 @@ struct TRDist {
 enum : uint8_t { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
 
 enum BxDFKind { BX_LAMBERT, BX_OREN_NAYAR, BX_MF_REFL, BX_MF_TRANS, BX_FRESNEL_SPECULAR, BX_SPEC_REFL, BX_SPEC_TRANS };
-enum FresnelKind { FR_DIELECTRIC, FR_CONDUCTOR };
+enum FresnelKind { FR_DIELECTRIC, FR_CONDUCTOR, FR_NOOP };
 
 struct BxDFSample {
     RGB f;
@@ -274,6 +274,7 @@ struct BxDF {
 
     RGB fresnel(Float cos_i) const {  // fresnel.rs:13-21, 60-62, 95-98
         if (fr == FR_DIELECTRIC) return RGB(fr_dielectric(cos_i, fr_eta_i, fr_eta_t));
+        if (fr == FR_NOOP) return RGB(1.0f);  // FresnelNoOp, fresnel.rs:124-138
         return fr_conductor(pabs(cos_i), c_eta_i, c_eta_t, c_k);
     }
 
@@ -907,6 +908,11 @@ inline BSDF make_bsdf(const RenderScene& sc, const SurfHit& sh, bool allow_multi
                     }
                 }
             }
+            break;
+        }
+        case B200PT_MAT_MIRROR: {  // mirror.rs:45-56
+            RGB r = rgb_clamp0(rgb(m.ks));
+            if (!is_black(r)) { BxDF x; x.kind = BX_SPEC_REFL; x.type = BSDF_REFLECTION | BSDF_SPECULAR; x.r = r; x.fr = FR_NOOP; b.add(x); }
             break;
         }
         case B200PT_MAT_METAL: {

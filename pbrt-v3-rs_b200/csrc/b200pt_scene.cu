@@ -970,6 +970,15 @@ static DMaterial make_material(const b200pt_material& m, bool allow_multiple_lob
             }
             break;
         }
+        case B200PT_MAT_MIRROR: {  // mirror.rs:45-56: SpecularReflection(Kr, FresnelNoOp)
+            float r[3] = {clamp0(m.ks[0]), clamp0(m.ks[1]), clamp0(m.ks[2])};
+            if (!black3(r)) {
+                DBxDF& x = lobe(BX_SPEC_REFL, BSDF_REFLECTION | BSDF_SPECULAR);
+                std::memcpy(x.r, r, 12);
+                x.conductor = 2;
+            }
+            break;
+        }
         case B200PT_MAT_METAL: {
             float ur = m.urough, vr = m.vrough;
             if (m.remap_roughness) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
@@ -1076,6 +1085,7 @@ static const uint32_t kKmMatte = (1u << BX_LAMBERT) | (1u << BX_OREN_NAYAR);
 static const uint32_t kKmPlastic = (1u << BX_LAMBERT) | (1u << BX_MF_REFL) | KM_DIEL;
 static const uint32_t kKmGlass = (1u << BX_FRESNEL_SPECULAR) | (1u << BX_MF_REFL) | (1u << BX_MF_TRANS) | KM_DIEL;
 static const uint32_t kKmMetal = (1u << BX_MF_REFL) | KM_COND;
+static const uint32_t kKmMirror = (1u << BX_SPEC_REFL);
 static int shade_grid(const SceneImpl* s, int n_upper, int per_sm) {
     const DevCtx* c = dev_ctx(s->device);
     return std::max(1, std::min((n_upper + 127) / 128, (c ? c->sm_count : 148) * per_sm));
@@ -1083,7 +1093,7 @@ static int shade_grid(const SceneImpl* s, int n_upper, int per_sm) {
 template <uint32_t KM>
 static void launch_shade_class(SceneImpl* s, const Wave& W, int cur, int n_upper, int bin, int blocks, cudaStream_t st) {
     if (st != s->shade_main) cudaStreamWaitEvent(st, s->ev_fork, 0);  // a class on its own stream starts after the sort
-    if constexpr ((KM & KM_TEX) != 0) k_shade<KM, kShadeHit, 4><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1);  // textured Kd: one register budget
+    if constexpr ((KM & KM_TEX) != 0 || KM == kKmMirror) k_shade<KM, kShadeHit, 4><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1);  // textured Kd, mirror: one register budget
     else switch (blocks) {
         case 3: k_shade<KM, kShadeHit, 3><<<shade_grid(s, n_upper, 12), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
         case 4: k_shade<KM, kShadeHit, 4><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, bin, bin + 1); break;
@@ -1127,7 +1137,7 @@ static void launch_shade(SceneImpl* s, const Wave& W, int cur, int n_upper, cuda
     }
     k_shade<KM_ALL, kShadeMiss, 8><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, 0, 1);
     ++launches;
-    if (mode == 3 && n_classes > 1 && !s->has_kd_tex) {
+    if (mode == 3 && n_classes > 1 && !s->has_kd_tex && !(s->material_classes & (1u << B200PT_MAT_MIRROR))) {
         k_shade_classes<4><<<std::max(1, std::min((n_upper + 127) / 128 + 4, (dev_ctx(s->device) ? dev_ctx(s->device)->sm_count : 148) * 16)), 128, 0, st>>>(s->dev, W, cur);
         ++launches;
     } else {
@@ -1146,6 +1156,7 @@ static void launch_shade(SceneImpl* s, const Wave& W, int cur, int n_upper, cuda
             }
             if ((s->material_classes & (1u << B200PT_MAT_GLASS)) && (cs[2] == st) == main_pass) { launch_shade_class<kKmGlass>(s, W, cur, n_upper, 3, blocks[2], cs[2]); ++launches; }
             if ((s->material_classes & (1u << B200PT_MAT_METAL)) && (cs[3] == st) == main_pass) { launch_shade_class<kKmMetal>(s, W, cur, n_upper, 4, blocks[3], cs[3]); ++launches; }
+            if ((s->material_classes & (1u << B200PT_MAT_MIRROR)) && main_pass) { launch_shade_class<kKmMirror>(s, W, cur, n_upper, 5, 4, st); ++launches; }  // a small kernel, on the main stream
         }
     }
     if (s->has_null_material) { k_shade<KM_ALL, kShadeNull, 8><<<shade_grid(s, n_upper, 16), 128, 0, st>>>(s->dev, W, cur, kBinNull, kBinNull + 1); ++launches; }
@@ -1460,7 +1471,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     s->device = current_device();
     s->has_null_material = has_null;
     for (int i = 0; i < d->n_materials; ++i)
-        if (d->materials[i].type >= 0 && d->materials[i].type < 4) s->material_classes |= 1u << d->materials[i].type;
+        if (d->materials[i].type >= 0 && d->materials[i].type < 5) s->material_classes |= 1u << d->materials[i].type;
         else { b200pt_set_error("b200pt_scene_create: unknown material type"); delete sc; return B200PT_ERR_INVALID; }
     for (int i = 0; i < d->n_lights; ++i) if (d->lights[i].type == B200PT_LIGHT_POINT || d->lights[i].type == B200PT_LIGHT_DISTANT || d->lights[i].type == B200PT_LIGHT_SPOT) ++s->n_point_lights;  // delta lights
     auto fail = [&](int code) { b200pt_scene_destroy(sc); return code; };

@@ -537,6 +537,10 @@ struct Builder {
             m.eta[0] = p.find("eta", "float") ? p.one_float("eta", 1.5f) : p.one_float("index", 1.5f);
             m.urough = p.one_float("uroughness", 0.0f);
             m.vrough = p.one_float("vroughness", 0.0f);
+        } else if (type == "mirror") {  // mirror.rs:62-70
+            m.type = B200PT_MAT_MIRROR;
+            const float kr[3] = {0.9f, 0.9f, 0.9f};
+            p.one_rgb("Kr", kr, m.ks);
         } else if (type == "metal") {
             m.type = B200PT_MAT_METAL;
             // copper SPD -> RGB as the reference's Spectrum::from(&samples).to_rgb() evaluates it (materials/src/metal.rs:109-133)
@@ -546,7 +550,7 @@ struct Builder {
             float r = p.one_float("roughness", 0.01f);
             m.urough = p.find("uroughness", "float") ? p.one_float("uroughness", r) : r;
             m.vrough = p.find("vroughness", "float") ? p.one_float("vroughness", r) : r;
-        } else throw Unsupported("Material \"" + type + "\" is outside this path (matte, plastic, glass, metal)");
+        } else throw Unsupported("Material \"" + type + "\" is outside this path (matte, plastic, glass, metal, mirror)");
         if (kd_tex >= 0 && L->spectrum_textures[(size_t)kd_tex].type == B200PT_STEX_CONSTANT) {  // a constant texture is just the value
             fill_rgb(m.kd, L->spectrum_textures[(size_t)kd_tex].tex1);
             kd_tex = -1;

@@ -192,7 +192,7 @@ struct DBxDF {
     uint32_t type;
     float r[3], t[3];
     float on_a, on_b;      // Oren-Nayar
-    int conductor;         // microfacet reflection Fresnel: 0 dielectric, 1 conductor
+    int conductor;         // Fresnel term of a reflection lobe: 0 dielectric, 1 conductor, 2 none (FresnelNoOp: the mirror material)
     float fr_eta_i, fr_eta_t;
     float c_eta_t[3], c_k[3];  // conductor (eta_i = 1)
     float ax, ay;          // Trowbridge-Reitz alpha (already max(1e-3, .))
@@ -327,6 +327,13 @@ template <uint32_t KM = KM_ALL> B2_D BxDFSample bx_sample_f(const DBxDF& b, V3 w
             s.wi = wi;
             return s;
         }
+        if (km_is<KM>(b.kind, BX_SPEC_REFL)) {  // SpecularReflection::sample_f, specular_reflection.rs:45-51 (the path integrator reaches it through the mirror material)
+            V3 wi = mk(-wo.x, -wo.y, wo.z);
+            s.pdf = 1.0f;
+            s.f = rgb1(b.conductor == 2 ? 1.0f : fr_dielectric(cos_theta(wi), b.fr_eta_i, b.fr_eta_t)) * ldrgb(b.r) / abs_cos_theta(wi);
+            s.wi = wi;
+            return s;
+        }
         if (!((KM >> BX_FRESNEL_SPECULAR) & 1u)) return s;
         {  // FresnelSpecular::sample_f, fresnel_specular.rs:68-103
             float F = fr_dielectric(cos_theta(wo), b.eta_a, b.eta_b);
@@ -361,7 +368,7 @@ B2_D BxDFSample spec_refl_sample_f(const DBxDF& b, V3 wo) {
     V3 wi = mk(-wo.x, -wo.y, wo.z);
     s.type = b.type;
     s.pdf = 1.0f;
-    s.f = rgb1(fr_dielectric(cos_theta(wi), b.fr_eta_i, b.fr_eta_t)) * ldrgb(b.r) / abs_cos_theta(wi);
+    s.f = rgb1(b.conductor == 2 ? 1.0f : fr_dielectric(cos_theta(wi), b.fr_eta_i, b.fr_eta_t)) * ldrgb(b.r) / abs_cos_theta(wi);
     s.wi = wi;
     return s;
 }

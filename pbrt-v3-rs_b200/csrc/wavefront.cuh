@@ -98,8 +98,8 @@ struct Wave {
     // spatial light sampling: slots whose voxel was not ready in the first shade launch of a bounce
     int* deferred;
 };
-static const int kBins = 6;     // miss, matte, plastic, glass, metal, null material
-static const int kBinNull = 5;
+static const int kBins = 7;     // miss, matte, plastic, glass, metal, mirror, null material
+static const int kBinNull = 6;
 // Control block: 64 ints per bounce iteration.  Block 0 opens the wave ([0] = its paths); block i + 1 receives the counts
 // iteration i produces, and its [0] is the queue size of iteration i + 1.  [32..37] are the three 8-byte work counters of
 // the persistent traversal launches that consume the block's queues (closest, shadow, MIS).

@@ -439,6 +439,9 @@ class SceneDescription:
                 M.kt[:] = m.get("Kt", (1, 1, 1))
                 M.eta[0] = m.get("eta", m.get("index", 1.5))
                 M.urough, M.vrough = m.get("uroughness", 0.0), m.get("vroughness", 0.0)
+            elif t == "mirror":  # mirror.rs:62-70
+                M.type = 4
+                M.ks[:] = m.get("Kr", (0.9, 0.9, 0.9))
             elif t == "metal":   # metal.rs:109-133; the default copper SPD->RGB conversion is done by the caller
                 M.type = MAT_METAL
                 M.eta[:] = m.get("eta", (0.19999069, 0.92208463, 1.09987593))

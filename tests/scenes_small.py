@@ -46,6 +46,7 @@ MATERIALS = {
     "glass": dict(type="glass", eta=1.5),
     "rough_glass": dict(type="glass", eta=1.5, uroughness=0.2, vroughness=0.1),
     "metal": dict(type="metal", roughness=0.01),
+    "mirror": dict(type="mirror", Kr=(0.9, 0.85, 0.8)),
     "rough_metal": dict(type="metal", uroughness=0.3, vroughness=0.1, remaproughness=False),
 }
 

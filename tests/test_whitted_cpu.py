@@ -183,3 +183,23 @@ def test_whitted_glass_slab_normal_incidence_closed_form(pkg, oracle):
         # the centre ray is exactly (0, 0, 1): normal incidence.  The emitter adds its own direct light on the glass: none
         # (delta lobes have f = 0), so only the specular trees carry radiance.
         assert np.allclose(li, Le * expect, rtol=1e-5, atol=1e-7), (maxdepth, li, Le * expect)
+
+
+@pytest.mark.parametrize("integrator", ["whitted", "path", "directlighting"])
+def test_mirror_reflects_an_emitter_closed_form(pkg, oracle, integrator):
+    """MirrorMaterial (materials/src/mirror.rs): SpecularReflection(Kr, FresnelNoOp) - a camera ray that leaves a mirror floor
+    towards a one-sided emitter returns exactly Kr * Le (f = Kr / |cos|, pdf = 1, times |cos|), for all three integrators."""
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    sd = SceneDescription()
+    mirror = sd.add_material(type="mirror", Kr=(0.9, 0.8, 0.7))
+    black = sd.add_material(type="matte", Kd=(0, 0, 0))
+    q = np.array([[-50, 0, -50], [50, 0, -50], [50, 0, 50], [-50, 0, 50]], dtype=np.float32)
+    sd.add_mesh(np.stack([np.concatenate([q[0], q[2], q[1]]), np.concatenate([q[0], q[3], q[2]])]), mirror)
+    e = np.array([[-40, -1, 6], [40, -1, 6], [40, 60, 6], [-40, 60, 6]], dtype=np.float32)  # faces -z: towards the reflected rays
+    sd.add_mesh(np.stack([np.concatenate([e[0], e[2], e[1]]), np.concatenate([e[0], e[3], e[2]])]), black, area_light=dict(L=(3, 2, 1)))
+    sd.camera.update(eye=(0.0, 1.0, -1.0), look=(0.0, 0.0, 0.0), up=(0, 1, 0), fov=20.0)
+    sd.film.update(xresolution=5, yresolution=5)
+    sd.sampler.update(type="halton", pixelsamples=2)
+    sd.integrator.update(name=integrator, maxdepth=4)
+    img = oracle.OracleScene(sd).render(nthreads=1)[0]
+    assert np.allclose(img, np.array([0.9 * 3, 0.8 * 2, 0.7 * 1]), rtol=1e-5)

@@ -357,11 +357,13 @@ int b200pt_envmap_prepare(const float* map_rgb, int32_t map_width, int32_t map_h
 int b200pt_sobol_interval_tables(const uint32_t* sobol_matrices_32, int m, uint64_t vdc_out[52], uint64_t vdc_inv_out[52]);
 
 /* ---- scene ingestion (host only; api/src/lib.rs + api/src/parser, shapes/src/plymesh.rs, core/src/image_io.rs) ----
- * Reads the subset of the pbrt-v3 scene format that reaches this path (perspective camera; image film; box / gaussian
- * filter; halton / 02sequence / sobol sampler; path / whitted / directlighting integrator with uniform / power / spatial
- * light sampling; bvh accelerator with splitmethod sah / hlbvh; trianglemesh / plymesh shapes with P, N, S, uv/st, alpha,
- * shadowalpha; matte / plastic / glass / metal with constant parameters; point / infinite (.pfm map) / diffuse area
- * lights; transforms, attribute and transform stacks, named materials, object instancing, Include) and builds the BVHs
+ * Reads the subset of the pbrt-v3 scene format that reaches this path (perspective / orthographic / environment camera;
+ * image film; box / gaussian / triangle / mitchell / sinc filter; halton / 02sequence / sobol sampler; path / whitted /
+ * directlighting integrator with uniform / power / spatial light sampling; bvh accelerator with splitmethod sah / hlbvh;
+ * trianglemesh / plymesh shapes with P, N, S, uv/st, alpha, shadowalpha (float textures: constant, checkerboard, dots,
+ * imagemap); matte / plastic / glass / metal / mirror with constant parameters (a matte / plastic "Kd" may be a constant or
+ * checkerboard spectrum texture); point / spot / distant / infinite (.pfm map) / diffuse area lights; rgb / color /
+ * blackbody spectra; transforms, attribute and transform stacks, named materials, object instancing, Include) and builds the BVHs
  * with b200pt_bvh_build_sah (on the GPU once a device is bound) / b200pt_bvh_build_hlbvh.  Anything else returns
  * B200PT_ERR_UNSUPPORTED with the offending directive
  * in b200pt_last_error.  The returned desc stays valid until b200pt_loaded_scene_free. */

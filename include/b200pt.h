@@ -92,6 +92,9 @@ typedef struct b200pt_material {
 enum { B200PT_LIGHT_POINT = 0, B200PT_LIGHT_AREA = 1, B200PT_LIGHT_INFINITE = 2,
        B200PT_LIGHT_DISTANT = 3, /* lights/src/distant.rs: pos = w_light, the NORMALISED world-space direction TOWARDS the light
                                    * (light_to_world.transform_vector(from - to).normalize(), distant.rs:50-52), L = L * scale */
+       B200PT_LIGHT_GONIOMETRIC = 5, /* lights/src/goniometric.rs: pos = p_light, L = I * scale, world_to_light, and the "mapname" image in
+                                      * map_rgb (decoded, as for an infinite light): the intensity in direction w is scaled by the image
+                                      * at (phi, theta) of world_to_light(w) with y and z swapped - MIPMap::lookup_triangle(st, 0) (:101-115) */
        B200PT_LIGHT_SPOT = 4 /* lights/src/spot.rs: pos = p_light = light_to_world(0), L = I * scale, world_to_light = the inverse of
                               * ctm * Translate(from) * dir_to_z^-1 (spot.rs:209-226), cos_total_width / cos_falloff_start =
                               * cos(radians(coneangle)), cos(radians(coneangle - conedeltaangle)) (spot.rs:57-58) */ };

@@ -571,6 +571,11 @@ inline RGB light_power(const RenderScene& sc, int li) {
     const b200pt_light& l = sc.lights[li];
     if (l.type == B200PT_LIGHT_POINT) return kFourPi * light_L(l);
     if (l.type == B200PT_LIGHT_DISTANT) return light_L(l) * kPi * sc.world_radius * sc.world_radius;  // distant.rs:92-95
+    if (l.type == B200PT_LIGHT_GONIOMETRIC) {  // goniometric.rs:140-150
+        RGB spec(1.0f);
+        if (!sc.inf_map[(size_t)li].pyramid.empty()) spec = sc.inf_map[(size_t)li].lookup_triangle(P2(0.5f, 0.5f), 0.5f);
+        return (4.0f * kPi) * light_L(l) * spec;
+    }
     if (l.type == B200PT_LIGHT_SPOT) return light_L(l) * kTwoPi * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width));  // spot.rs:109-111
     if (l.type == B200PT_LIGHT_AREA) {
         Float s = l.two_sided ? 2.0f : 1.0f;
@@ -664,6 +669,11 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
         const b200pt_light& l = s->lights[i];
         if (l.type == B200PT_LIGHT_AREA)
             s->light_area[i] = triangle_area(s->accel.vert(l.prim, 0), s->accel.vert(l.prim, 1), s->accel.vert(l.prim, 2));
+        if (l.type == B200PT_LIGHT_GONIOMETRIC && l.map_rgb && l.map_width > 0 && l.map_height > 0) {  // GonioPhotometricLight::new, goniometric.rs:71-90
+            std::vector<RGB> texels((size_t)l.map_width * l.map_height);
+            for (size_t k = 0; k < texels.size(); ++k) texels[k] = RGB(l.map_rgb[3 * k], l.map_rgb[3 * k + 1], l.map_rgb[3 * k + 2]);
+            s->inf_map[i].build(l.map_width, l.map_height, texels);
+        }
         if (l.type == B200PT_LIGHT_INFINITE) {
             s->infinite_lights.push_back((int)i);
             // InfiniteAreaLight::new, infinite.rs:61-92: texels = image * L (or the 1x1 image [L]), MIPMap over them
@@ -952,6 +962,19 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
         r.valid = true;
         return r;
     }
+    if (l.type == B200PT_LIGHT_GONIOMETRIC) {  // goniometric.rs:127-138 with scale(), :101-115
+        V3 pl(l.pos[0], l.pos[1], l.pos[2]);
+        r.wi = normalize(pl - hit.p);
+        r.pdf = 1.0f;
+        r.p1 = pl;
+        V3 wp = normalize(xf_vector(m4_from(l.world_to_light), -r.wi));
+        std::swap(wp.y, wp.z);
+        RGB scale(1.0f);
+        if (!sc.inf_map[(size_t)li].pyramid.empty()) scale = sc.inf_map[(size_t)li].lookup_triangle(P2(spherical_phi(wp) * kInvTwoPi, spherical_theta(wp) * kInvPi), 0.0f);
+        r.value = light_L(l) * scale / distance_squared(pl, hit.p);
+        r.valid = true;
+        return r;
+    }
     if (l.type == B200PT_LIGHT_SPOT) {  // spot.rs:97-107 with falloff(), :62-76
         V3 pl(l.pos[0], l.pos[1], l.pos[2]);
         r.wi = normalize(pl - hit.p);
@@ -1030,7 +1053,7 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
 // Light::pdf_li
 inline Float light_pdf_li(const RenderScene& sc, int li, const SurfHit& hit, V3 wi) {
     const b200pt_light& l = sc.lights[li];
-    if (l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT) return 0.0f;
+    if (l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT || l.type == B200PT_LIGHT_GONIOMETRIC) return 0.0f;
     if (l.type == B200PT_LIGHT_AREA) {  // Shape::pdf_solid_angle, shape.rs:81-107
         Ray ray = spawn_ray(hit, wi);
         V3 p0 = sc.accel.vert(l.prim, 0), p1 = sc.accel.vert(l.prim, 1), p2 = sc.accel.vert(l.prim, 2);
@@ -1048,7 +1071,7 @@ inline Float light_pdf_li(const RenderScene& sc, int li, const SurfHit& hit, V3 
     if (sin_t == 0.0f) return 0.0f;
     return sc.inf_distr[li].pdf(P2(phi * kInvTwoPi, theta * kInvPi)) / (kTwoPi * kPi * sin_t);
 }
-inline bool light_is_delta(const b200pt_light& l) { return l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT; }  // DELTA_POSITION | DELTA_DIRECTION
+inline bool light_is_delta(const b200pt_light& l) { return l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT || l.type == B200PT_LIGHT_GONIOMETRIC; }  // DELTA_POSITION | DELTA_DIRECTION
 
 // core/src/integrator/common.rs:146-299 (handle_media = false, specular = false)
 inline RGB estimate_direct(RenderScene& sc, const SurfHit& hit, const BSDF& bsdf, P2 u_scatter, int li, P2 u_light) {

@@ -27,7 +27,7 @@ MISS = 0xFFFFFFFF
 PRIM_FLIP_NORMAL, PRIM_ALPHA_ZERO, PRIM_SHADOW_ALPHA_ZERO = 1, 2, 4
 PRIM_REVERSE_ORIENTATION, PRIM_HAS_UV, PRIM_HAS_NORMALS, PRIM_HAS_TANGENTS = 8, 16, 32, 64
 MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_METAL, MAT_MIRROR = 0, 1, 2, 3, 4
-LIGHT_POINT, LIGHT_AREA, LIGHT_INFINITE, LIGHT_DISTANT, LIGHT_SPOT = 0, 1, 2, 3, 4
+LIGHT_POINT, LIGHT_AREA, LIGHT_INFINITE, LIGHT_DISTANT, LIGHT_SPOT, LIGHT_GONIOMETRIC = 0, 1, 2, 3, 4, 5
 SAMPLER_HALTON, SAMPLER_ZEROTWO, SAMPLER_SOBOL = 0, 1, 2
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 INTEGRATOR_PATH, INTEGRATOR_WHITTED, INTEGRATOR_DIRECT = 0, 1, 2

@@ -133,7 +133,7 @@ void make_cdf(const float* f, int n, float* cdf, float* integral) {
 
 }  // namespace
 
-void build_envmap(const float* rgb, int mw, int mh, const float L[3], EnvMapTables* out) {
+void build_envmap(const float* rgb, int mw, int mh, const float L[3], EnvMapTables* out, bool importance) {
     // InfiniteAreaLight::new, infinite.rs:66-81: texels = image * L, or the 1x1 image [L]
     std::vector<Px> img;
     int w = 1, h = 1;
@@ -168,6 +168,11 @@ void build_envmap(const float* rgb, int mw, int mh, const float L[3], EnvMapTabl
         out->texels[4 * k] = P.lv[0].px[k].r; out->texels[4 * k + 1] = P.lv[0].px[k].g; out->texels[4 * k + 2] = P.lv[0].px[k].b; out->texels[4 * k + 3] = 0.0f;
     }
 
+    {
+        Px pw = P.trilinear(0.5f, 0.5f, 0.5f);
+        out->power_lookup[0] = pw.r; out->power_lookup[1] = pw.g; out->power_lookup[2] = pw.b;
+    }
+    if (!importance) { out->nu = out->nv = 0; return; }
     // compute_scalar_image + Distribution2D::new, infinite.rs:326-369, sampling/distribution_2d.rs
     const int nu = 2 * out->width, nv = 2 * out->height;
     const float fwidth = 0.5f / (float)(nu < nv ? nu : nv);
@@ -189,9 +194,6 @@ void build_envmap(const float* rgb, int mw, int mh, const float L[3], EnvMapTabl
     out->marg_func = out->cond_int;
     out->marg_cdf.resize((size_t)nv + 1);
     make_cdf(out->marg_func.data(), nv, out->marg_cdf.data(), &out->marg_int);
-
-    Px pw = P.trilinear(0.5f, 0.5f, 0.5f);
-    out->power_lookup[0] = pw.r; out->power_lookup[1] = pw.g; out->power_lookup[2] = pw.b;
 }
 
 }  // namespace b2host

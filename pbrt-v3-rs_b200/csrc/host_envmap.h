@@ -21,6 +21,7 @@ struct EnvMapTables {
 };
 
 // rgb: map_width x map_height x 3 floats (NULL => the 1x1 image [L]); L multiplies every texel.
-void build_envmap(const float* rgb, int map_width, int map_height, const float L[3], EnvMapTables* out);
+// importance = false (a goniometric light's map): the pyramid, level 0 and power_lookup only.
+void build_envmap(const float* rgb, int map_width, int map_height, const float L[3], EnvMapTables* out, bool importance = true);
 
 }  // namespace b2host

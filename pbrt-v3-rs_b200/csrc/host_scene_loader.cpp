@@ -817,6 +817,23 @@ struct Builder {
             const float inv = 1.0f / len;  // Vector3::normalize = self / length = self * (1 / length)
             l.pos[0] = inv * w.x; l.pos[1] = inv * w.y; l.pos[2] = inv * w.z;
             std::memcpy(l.light_to_world, gs.ctm.m.m, 64); std::memcpy(l.world_to_light, gs.ctm.inv.m, 64);
+        } else if (name == "goniometric") {  // goniometric.rs:219-238 + GonioPhotometricLight::new :59-100
+            l.type = B200PT_LIGHT_GONIOMETRIC;
+            float I[3];
+            p.one_rgb("I", one, I);
+            for (int c = 0; c < 3; ++c) l.L[c] = I[c] * sc[c];
+            const V3 pl = xf_point(gs.ctm.m, v3(0, 0, 0));
+            l.pos[0] = pl.x; l.pos[1] = pl.y; l.pos[2] = pl.z;
+            std::memcpy(l.light_to_world, gs.ctm.m.m, 64); std::memcpy(l.world_to_light, gs.ctm.inv.m, 64);
+            std::string map = p.one_string("mapname", "");
+            if (!map.empty()) {
+                if (map.size() < 4 || map.substr(map.size() - 4) != ".pfm") throw Unsupported("goniometric light \"mapname\": only .pfm images are decoded here (convert '" + map + "': 8-bit values / 255, no gamma, image_io.rs:192-218)");
+                auto img = std::make_unique<std::vector<float>>();
+                int w = 0, h = 0;
+                read_pfm(resolve(map), img.get(), &w, &h);
+                l.map_rgb = img->data(); l.map_width = w; l.map_height = h;
+                L->images.push_back(std::move(img));
+            }
         } else if (name == "spot") {  // spot.rs:200-237 + SpotLight::new :44-60
             l.type = B200PT_LIGHT_SPOT;
             float I[3];
@@ -845,7 +862,7 @@ struct Builder {
             const float rad = 3.14159265358979323846f / 180.0f;  // f32::to_radians
             l.cos_total_width = std::cos(cone_angle * rad);
             l.cos_falloff_start = std::cos((cone_angle - cone_delta) * rad);
-        } else throw Unsupported("LightSource \"" + name + "\" is outside this path (point, spot, distant, infinite)");
+        } else throw Unsupported("LightSource \"" + name + "\" is outside this path (point, spot, goniometric, distant, infinite)");
         L->lights.push_back(l);
     }
 

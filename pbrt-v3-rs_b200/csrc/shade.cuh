@@ -455,13 +455,13 @@ template <uint32_t KM = KM_ALL> B2_D BxDFSample bsdf_sample_f(const BSDF& b, V3 
 }
 
 // ---- lights -------------------------------------------------------------------------
-enum : int { LT_POINT = 0, LT_AREA = 1, LT_INFINITE = 2, LT_DISTANT = 3, LT_SPOT = 4 };
-B2_D bool light_is_delta(int type) { return type == LT_POINT || type == LT_DISTANT || type == LT_SPOT; }  // light.rs: DELTA_POSITION | DELTA_DIRECTION
+enum : int { LT_POINT = 0, LT_AREA = 1, LT_INFINITE = 2, LT_DISTANT = 3, LT_SPOT = 4, LT_GONIO = 5 };
+B2_D bool light_is_delta(int type) { return type == LT_POINT || type == LT_DISTANT || type == LT_SPOT || type == LT_GONIO; }  // light.rs: DELTA_POSITION | DELTA_DIRECTION
 struct DLight {
     int type;
     int prim;        // area: original primitive index
     int two_sided;
-    int inf_slot;    // infinite: index into the DInfDistr table
+    int inf_slot;    // infinite, goniometric: index into the DInfDistr table (goniometric: texels only)
     float pos[3];
     float area;      // area: Triangle::area (host, f32); spot: cos_total_width
     float L[3];
@@ -541,6 +541,13 @@ B2_D float spherical_phi(V3 v) { float p = atan2f(v.y, v.x); return p < 0.0f ? p
 B2_D RGB infinite_le(const DLight& l, const DInfDistr& D, V3 ray_d) {
     V3 w = normalize(xf3(l.w2l, ray_d));
     P2 st = mk2(spherical_phi(w) * kInvTwoPi, spherical_theta(w) * kInvPi);
+    return inf_lookup(D, st);
+}
+// GonioPhotometricLight::scale (goniometric.rs:101-115): the map at the spherical coordinates of the light-space direction with y and z swapped
+B2_D RGB gonio_scale(const DLight& l, const DInfDistr& D, V3 w_world) {
+    V3 wp = normalize(xf3(l.w2l, w_world));
+    const float t = wp.y; wp.y = wp.z; wp.z = t;
+    P2 st = mk2(spherical_phi(wp) * kInvTwoPi, spherical_theta(wp) * kInvPi);
     return inf_lookup(D, st);
 }
 // DiffuseAreaLight::l, diffuse.rs:220-226

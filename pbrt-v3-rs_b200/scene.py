@@ -290,6 +290,14 @@ class SceneDescription:
         self.lights.append(dict(type="spot", L=tuple(I), pos=tuple(float(c) for c in f), light_to_world=l2w.reshape(-1), world_to_light=w2l.reshape(-1),
                                 cos_total_width=cosf(float(F32(coneangle) * rad)), cos_falloff_start=cosf(float(F32(F32(coneangle) - F32(conedeltaangle)) * rad))))
 
+    def add_goniometric_light(self, I, image=None, light_to_world=None):
+        """LightSource "goniometric" (lights/src/goniometric.rs): a point light at light_to_world(0) whose intensity in a
+        direction is scaled by ``image`` ((h, w, 3) floats, top row first; None = 1) at the direction's spherical coordinates."""
+        m = np.eye(4, dtype=F32) if light_to_world is None else np.asarray(light_to_world, dtype=F32).reshape(4, 4)
+        img = None if image is None else np.ascontiguousarray(image, dtype=F32)
+        self.lights.append(dict(type="goniometric", L=tuple(I), pos=tuple(float(c) for c in m[:3, 3]), light_to_world=m.reshape(-1),
+                                world_to_light=_m4_inverse(m).reshape(-1), image=img))
+
     def add_distant_light(self, L, w_light):
         """LightSource "distant" (lights/src/distant.rs): radiance ``L`` arriving from direction ``w_light`` (towards the
         light, world space; normalised here the way Vector3::normalize does: v * (1 / |v|))."""
@@ -472,6 +480,13 @@ class SceneDescription:
             elif l["type"] == "distant":
                 Lt.type = LIGHT_DISTANT
                 Lt.pos[:] = l["pos"]
+            elif l["type"] == "goniometric":
+                Lt.type = 5
+                Lt.pos[:] = l["pos"]
+                if l.get("image") is not None:
+                    keep.append(l["image"])
+                    Lt.map_rgb = l["image"].ctypes.data_as(C.c_void_p)
+                    Lt.map_height, Lt.map_width = l["image"].shape[:2]
             elif l["type"] == "spot":
                 Lt.type = LIGHT_SPOT
                 Lt.pos[:] = l["pos"]

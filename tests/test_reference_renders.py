@@ -42,6 +42,7 @@ CAMERA = {
     "triangles-alpha-mask": ('LookAt 0 5 3  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 5, 3), (0, 0, 0), 90.0),
     "distant": ('LookAt 0 5 3  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 5, 3), (0, 0, 0), 90.0),
     "spot": ('LookAt 0 5 3  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 5, 3), (0, 0, 0), 90.0),
+    "goniometric": ('LookAt 0 5 3  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 5, 3), (0, 0, 0), 90.0),
     "perspective": ('LookAt 0 2 2  0 0 0  0 0 1\nCamera "perspective" "float fov" 90', (0, 2, 2), (0, 0, 0), 90.0),
     # "LookAt ..; Translate 0 -1 0; Camera": the camera sits at world (0, 8, 15) and looks at (0, 1, 0)
     "instances": ('LookAt 0 7 15  0 0 0  0 0 1\nTranslate 0 -1 0\nCamera "perspective" "float fov" 45', (0, 8, 15), (0, 1, 0), 45.0),
@@ -49,7 +50,7 @@ CAMERA = {
     "environment": ('LookAt 0 0 1  0 1 0  0 0 1\nCamera "environment"', None, None, None),
 }
 RESOLUTION = {"environment": (800, 400)}  # the others: 400 x 400
-ALBEDO = {"point": (0.3, 0.8), "infinite-no-map": (0.3, 0.8), "triangles-alpha-mask": (0.3, 0.8), "distant": (0.3, 0.8), "spot": (0.3, 0.8), "perspective": (0.1, 0.8), "instances": (0.1, 0.8), "orthographic": (0.1, 0.8), "environment": (0.1, 0.8)}
+ALBEDO = {"point": (0.3, 0.8), "infinite-no-map": (0.3, 0.8), "triangles-alpha-mask": (0.3, 0.8), "distant": (0.3, 0.8), "spot": (0.3, 0.8), "goniometric": (0.3, 0.8), "perspective": (0.1, 0.8), "instances": (0.1, 0.8), "orthographic": (0.1, 0.8), "environment": (0.1, 0.8)}
 GROUND = '''  AttributeBegin
     Translate 0 0 -1
     Material "matte" "rgb Kd" [%g %g %g]
@@ -83,6 +84,21 @@ BODY = {
 ''',
     # as shipped: "conedelta" is not a parameter SpotLight reads ("conedeltaangle", spot.rs:208), so the falloff starts at 25 - 5 degrees
     "spot": '''  LightSource "spot" "rgb I" [.4 .45 .5] "point from" [-5 0 5] "point to" [0 0 0] "rgb scale" [200 200 200] "float coneangle" 25 "float conedelta" 20
+  AttributeBegin
+    Rotate 45 0 0 1
+    Material "matte" "rgb Kd" [.2 .01 .01]
+    %(cube)s
+  AttributeEnd
+''',
+    # the light's image: tests/golden/ref_renders/goniometric-upward-downward.png = scenes/images/..., handed over as a PFM holding
+    # the reference's decode of an 8-bit image (value / 255, no gamma: core/src/image_io.rs:192-218); 1572 x 790, so MIPMap::new
+    # resamples it to 2048 x 1024 (Lanczos) before the lookups
+    "goniometric": '''  AttributeBegin
+    Translate -5 0 5
+    Rotate 135 1 0 0
+    Rotate 60 0 1 0
+    LightSource "goniometric" "rgb I" [.4 .45 .5] "rgb scale" [200 200 200] "float fov" 45 "string mapname" "gonio.pfm"
+  AttributeEnd
   AttributeBegin
     Rotate 45 0 0 1
     Material "matte" "rgb Kd" [.2 .01 .01]
@@ -155,6 +171,11 @@ def scene_file(tmp_path, which, ground_kd=None, spp=128, inside=1.0, outside=0.0
     p = tmp_path / ("%s_%s_%d_%g_%d.pbrt" % (which, ground_kd, spp, inside, len(texture_extra)))
     ground = GROUND % (ground_kd, ground_kd, ground_kd) if ground_kd is not None else GROUND_CHECKS % dict(a=ALBEDO[which][0], b=ALBEDO[which][1], extra=texture_extra)
     xres, yres = RESOLUTION.get(which, (400, 400))
+    if which == "goniometric" and not (tmp_path / "gonio.pfm").exists():
+        from PIL import Image
+        import __graft_entry__ as ge
+        px = np.array(Image.open(os.path.join(HERE, "golden", "ref_renders", "goniometric-upward-downward.png")).convert("RGB"))
+        ge.load_package().write_pfm(str(tmp_path / "gonio.pfm"), px.astype(F32) / F32(255.0))
     p.write_text(HEAD % dict(camera=CAMERA[which][0], spp=spp, xres=xres, yres=yres) + BODY[which] % dict(cube=CUBE, inside=inside, outside=outside) + ground)
     return str(p)
 
@@ -189,7 +210,7 @@ def _check_scene(render, tmp_path, which, tag):
     # Measured (oracle and CUDA path alike): point / spot / distant / triangles-alpha-mask 0 differing pixels; infinite-no-map 5,
     # perspective 1, instances 5, all one level off.  The two other cameras: orthographic 2 pixels, environment 6 of 320 000,
     # most of them one level off, three on cube edges by 2-5 levels = ONE of the pixel's 128 samples deciding differently.
-    loose = which in ("orthographic", "environment")
+    loose = which in ("orthographic", "environment", "goniometric")
     assert stats["max_diff"] <= (6 if loose else 1), stats
     assert stats["differing"] <= 16 * stats["pixels"] // 160000, stats
     return img, ref
@@ -201,7 +222,7 @@ def _oracle_render(path):
     return ol.OracleScene(ge.load_package().load_pbrt(path)).render()[0]
 
 
-SCENES = ["point", "infinite-no-map", "triangles-alpha-mask", "distant", "perspective", "instances", "spot", "orthographic", "environment"]
+SCENES = ["point", "infinite-no-map", "triangles-alpha-mask", "distant", "perspective", "instances", "spot", "orthographic", "environment", "goniometric"]
 
 
 @pytest.mark.parametrize("which", SCENES)

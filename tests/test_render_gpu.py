@@ -636,3 +636,28 @@ def test_other_cameras_rays_bit_exact_and_images(gpu, oracle, camera):
     ref, stats, _ = osc.render()
     assert img.mean() > 0.01 and ss.rel_rmse(img, ref) <= TOL
     assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("integrator,with_map", [("whitted", True), ("path", True), ("directlighting", False)])
+def test_goniometric_light_matches_oracle(gpu, oracle, integrator, with_map):
+    """GonioPhotometricLight (lights/src/goniometric.rs): a point light scaled by an image looked up at the spherical
+    coordinates of the light-space direction (y / z swapped) - MIPMap::new over a non-power-of-two image (Lanczos resampling),
+    lookup_triangle(st, 0); power 4 pi I lookup_triangle((.5, .5), .5) in the light distribution."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="area", res=32, spp=8, maxdepth=4, strategy="power")
+    rng = np.random.default_rng(5)
+    img = (rng.uniform(0.0, 1.0, size=(12, 20, 3)) ** 2).astype(np.float32) if with_map else None
+    c, s_ = np.float32(np.cos(0.7)), np.float32(np.sin(0.7))
+    m = np.array([[c, 0, s_, 1.0], [0, 1, 0, 3.0], [-s_, 0, c, -2.0], [0, 0, 0, 1]], dtype=np.float32)
+    sd.add_goniometric_light((60, 55, 50), image=img, light_to_world=m)
+    sd.integrator.update(name=integrator)
+    integ = gpu.PathIntegrator(sd)
+    osc = oracle.OracleScene(sd)
+    ps = _pairs(32, 4)
+    li, _ = integ.li(ps)
+    assert np.isclose(li, osc.li(ps), rtol=2e-3, atol=1e-5).all(1).mean() >= 0.999
+    img_g = integ.render()
+    ref, stats, _ = osc.render()
+    assert img_g.mean() > 0.01 and ss.rel_rmse(img_g, ref) <= TOL
+    assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]

@@ -1,16 +1,16 @@
 """Execution-level pin of the oracle - and of the CUDA path - to the reference: its own committed renders.
 
 The reference cannot be built here or on the GPU box (no Rust toolchain, profiles/r2_toolchain_probe.txt), but its tree
-holds images it rendered itself.  Nine of the shipped scenes lie entirely on this path:
+holds images it rendered itself.  Ten of the shipped scenes lie entirely on this path:
 
-  scenes/lights/{point, spot, distant, infinite-no-map}.pbrt, scenes/shapes/triangles-alpha-mask.pbrt,
+  scenes/lights/{point, spot, goniometric, distant, infinite-no-map}.pbrt, scenes/shapes/triangles-alpha-mask.pbrt,
   scenes/cameras/{perspective, orthographic, environment}.pbrt, scenes/objects/instances.pbrt
   (Whitted, Halton 128 spp, 400x400, box filter, a matte cube - or ten ObjectInstances of it - over a ground quad with a
   checkerboard "Kd" texture, point / spot / distant (blackbody) / infinite lights, a "dots" alpha mask)
 
 The Halton sampler is deterministic, so the whole image has to come out the same after the reference's own encode
 (core/src/image_io.rs:384-390: clamp(255 * gamma_correct(v) + 0.5) as u8) - stochastic infinite-light estimate, closed-form
-filtered checkerboard (camera ray differentials, compute_differentials) and all.  It does: four scenes equal the
+filtered checkerboard (camera ray differentials, compute_differentials) and all.  It does: five scenes equal the
 reference's PNG on all 160 000 pixels, the other five on all but <= 6 pixels.
 
 tests/golden/ref_renders/*.png are copies of the reference's renders (tools/copy_reference_renders.py)."""

@@ -365,7 +365,8 @@ int b200pt_sobol_interval_tables(const uint32_t* sobol_matrices_32, int m, uint6
  * directlighting integrator with uniform / power / spatial light sampling; bvh accelerator with splitmethod sah / hlbvh;
  * trianglemesh / plymesh shapes with P, N, S, uv/st, alpha, shadowalpha (float textures: constant, checkerboard, dots,
  * imagemap); matte / plastic / glass / metal / mirror with constant parameters (a matte / plastic "Kd" may be a constant or
- * checkerboard spectrum texture); point / spot / distant / infinite (.pfm map) / diffuse area lights; rgb / color /
+ * checkerboard spectrum texture); point / spot / goniometric / distant / infinite / diffuse area lights (image maps: .pfm and
+ * 8-bit .png); rgb / color /
  * blackbody spectra; transforms, attribute and transform stacks, named materials, object instancing, Include) and builds the BVHs
  * with b200pt_bvh_build_sah (on the GPU once a device is bound) / b200pt_bvh_build_hlbvh.  Anything else returns
  * B200PT_ERR_UNSUPPORTED with the offending directive

@@ -10,7 +10,9 @@
 // Everything is f32 with the reference's operation order (host code is built with -ffp-contract=off).
 // Outside this path (reported as B200PT_ERR_UNSUPPORTED, never silently dropped): textures, media, other shapes,
 // cameras, samplers, integrators, lights and materials, animated transforms, spectrum files.
+#include <cctype>
 #include <cmath>
+#include <iterator>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +25,7 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <zlib.h>
 
 #include "../../include/b200pt.h"
 
@@ -362,6 +365,77 @@ static void read_pfm(const std::string& path, std::vector<float>* rgb, int* w, i
         for (int x = 0; x < *w; ++x)
             for (int c = 0; c < 3; ++c) (*rgb)[((size_t)y * *w + x) * 3 + c] = s * raw[((size_t)(*h - 1 - y) * *w + x) * ch + (ch == 3 ? c : 0)];
 }
+// 8-bit PNG as the reference's read_8_bit takes it (core/src/image_io.rs:192-218: image::open(..).into_rgb8(), value / 255, no
+// gamma): non-interlaced, 8 bits per channel, grey / RGB / palette with or without alpha (alpha is dropped).  Rows top to bottom.
+static void read_png(const std::string& path, std::vector<float>* rgb, int* w, int* h) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw Invalid("cannot open image '" + path + "'");
+    std::vector<unsigned char> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (file.size() < 8 || std::memcmp(file.data(), sig, 8) != 0) throw Invalid("'" + path + "' is not a PNG image");
+    auto be32 = [&](size_t o) { return ((uint32_t)file[o] << 24) | ((uint32_t)file[o + 1] << 16) | ((uint32_t)file[o + 2] << 8) | (uint32_t)file[o + 3]; };
+    uint32_t width = 0, height = 0;
+    int depth = 0, color = 0, interlace = 0;
+    std::vector<unsigned char> idat, plte;
+    for (size_t o = 8; o + 12 <= file.size();) {
+        const uint32_t len = be32(o);
+        if (o + 12 + (size_t)len > file.size()) throw Invalid("'" + path + "': truncated PNG chunk");
+        const std::string type((const char*)&file[o + 4], 4);
+        const unsigned char* data = &file[o + 8];
+        if (type == "IHDR" && len >= 13) { width = be32(o + 8); height = be32(o + 12); depth = data[8]; color = data[9]; interlace = data[12]; }
+        else if (type == "PLTE") plte.assign(data, data + len);
+        else if (type == "IDAT") idat.insert(idat.end(), data, data + len);
+        else if (type == "IEND") break;
+        o += 12 + (size_t)len;
+    }
+    if (width == 0 || height == 0 || width > (1u << 16) || height > (1u << 16)) throw Invalid("'" + path + "': bad PNG header");
+    if (depth != 8 || interlace != 0) throw Unsupported("'" + path + "': only non-interlaced PNGs with 8 bits per channel are decoded here");
+    const int ch = color == 0 ? 1 : (color == 2 ? 3 : (color == 3 ? 1 : (color == 4 ? 2 : (color == 6 ? 4 : 0))));
+    if (ch == 0 || (color == 3 && plte.size() < 3)) throw Invalid("'" + path + "': bad PNG colour type");
+    const size_t stride = (size_t)width * ch;
+    std::vector<unsigned char> raw((stride + 1) * height);
+    uLongf out_len = (uLongf)raw.size();
+    if (uncompress(raw.data(), &out_len, idat.data(), (uLong)idat.size()) != Z_OK || out_len != raw.size()) throw Invalid("'" + path + "': cannot inflate the PNG data");
+    std::vector<unsigned char> px(stride * height);
+    for (uint32_t y = 0; y < height; ++y) {  // undo the scanline filters (PNG specification, section 9)
+        const unsigned char* in = &raw[(stride + 1) * y];
+        unsigned char* cur = &px[stride * y];
+        const unsigned char* up = y ? &px[stride * (y - 1)] : nullptr;
+        const int ft = in[0];
+        for (size_t i = 0; i < stride; ++i) {
+            const int a = i >= (size_t)ch ? cur[i - ch] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)ch) ? up[i - ch] : 0;
+            int pred = 0;
+            if (ft == 1) pred = a;
+            else if (ft == 2) pred = b;
+            else if (ft == 3) pred = (a + b) / 2;
+            else if (ft == 4) { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+            else if (ft != 0) throw Invalid("'" + path + "': bad PNG filter type");
+            cur[i] = (unsigned char)(in[1 + i] + pred);
+        }
+    }
+    *w = (int)width; *h = (int)height;
+    rgb->resize((size_t)width * height * 3);
+    for (size_t k = 0; k < (size_t)width * height; ++k) {
+        unsigned char r, g, bl;
+        const unsigned char* q = &px[k * ch];
+        if (color == 0 || color == 4) r = g = bl = q[0];
+        else if (color == 3) { const size_t e = (size_t)q[0] * 3; if (e + 3 > plte.size()) throw Invalid("'" + path + "': PNG palette index out of range"); r = plte[e]; g = plte[e + 1]; bl = plte[e + 2]; }
+        else { r = q[0]; g = q[1]; bl = q[2]; }
+        (*rgb)[3 * k] = (float)r / 255.0f; (*rgb)[3 * k + 1] = (float)g / 255.0f; (*rgb)[3 * k + 2] = (float)bl / 255.0f;
+    }
+}
+static bool has_ext(const std::string& path, const char* ext) {
+    const size_t n = std::strlen(ext);
+    if (path.size() < n) return false;
+    for (size_t i = 0; i < n; ++i) if (std::tolower((unsigned char)path[path.size() - n + i]) != ext[i]) return false;
+    return true;
+}
+// read_image (core/src/image_io.rs:227-240) for the formats decoded here: .pfm and 8-bit .png
+static void read_image(const std::string& path, std::vector<float>* rgb, int* w, int* h) {
+    if (has_ext(path, ".pfm")) read_pfm(path, rgb, w, h);
+    else if (has_ext(path, ".png")) read_png(path, rgb, w, h);
+    else throw Unsupported("image '" + path + "': only .pfm and 8-bit .png images are decoded here (convert .exr / .tga)");
+}
 static void write_pfm(const std::string& path, const float* rgb, int w, int h) {
     std::ofstream f(path, std::ios::binary);
     if (!f) throw Invalid("cannot create '" + path + "'");
@@ -645,13 +719,12 @@ struct Builder {
             std::string fn = p.one_string("filename", "");
             if (fn.empty()) throw Invalid("Texture \"" + name + "\": imagemap without \"filename\"");
             const std::string path = resolve(fn);
-            if (path.size() < 4 || path.substr(path.size() - 4) != ".pfm") throw Unsupported("Texture \"" + name + "\": only .pfm image maps are on this path");
             std::vector<float> rgb;
             int w = 0, h = 0;
-            read_pfm(path, &rgb, &w, &h);
+            read_image(path, &rgb, &w, &h);
             if ((w & (w - 1)) || (h & (h - 1))) throw Unsupported("Texture \"" + name + "\": image sides must be powers of two on this path (no resampling)");
             const float scale = p.one_float("scale", 1.0f);
-            const bool gamma = p.one_bool("gamma", false);  // default: true for .tga / .png only (imagemap.rs:129)
+            const bool gamma = p.one_bool("gamma", has_ext(path, ".png") || has_ext(path, ".tga"));  // imagemap.rs:129
             const std::string wrap = p.one_string("wrap", "repeat");
             t.type = B200PT_TEX_IMAGEMAP;
             t.wrap = wrap == "black" ? 1 : (wrap == "clamp" ? 2 : 0);
@@ -797,10 +870,9 @@ struct Builder {
             std::memcpy(l.light_to_world, gs.ctm.m.m, 64); std::memcpy(l.world_to_light, gs.ctm.inv.m, 64);
             std::string map = p.one_string("mapname", "");
             if (!map.empty()) {
-                if (map.size() < 4 || map.substr(map.size() - 4) != ".pfm") throw Unsupported("infinite light \"mapname\": only .pfm images are decoded here (convert '" + map + "')");
                 auto img = std::make_unique<std::vector<float>>();
                 int w = 0, h = 0;
-                read_pfm(resolve(map), img.get(), &w, &h);
+                read_image(resolve(map), img.get(), &w, &h);
                 l.map_rgb = img->data(); l.map_width = w; l.map_height = h;
                 L->images.push_back(std::move(img));
             }
@@ -827,10 +899,9 @@ struct Builder {
             std::memcpy(l.light_to_world, gs.ctm.m.m, 64); std::memcpy(l.world_to_light, gs.ctm.inv.m, 64);
             std::string map = p.one_string("mapname", "");
             if (!map.empty()) {
-                if (map.size() < 4 || map.substr(map.size() - 4) != ".pfm") throw Unsupported("goniometric light \"mapname\": only .pfm images are decoded here (convert '" + map + "': 8-bit values / 255, no gamma, image_io.rs:192-218)");
                 auto img = std::make_unique<std::vector<float>>();
                 int w = 0, h = 0;
-                read_pfm(resolve(map), img.get(), &w, &h);
+                read_image(resolve(map), img.get(), &w, &h);
                 l.map_rgb = img->data(); l.map_width = w; l.map_height = h;
                 L->images.push_back(std::move(img));
             }

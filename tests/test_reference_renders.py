@@ -90,14 +90,14 @@ BODY = {
     %(cube)s
   AttributeEnd
 ''',
-    # the light's image: tests/golden/ref_renders/goniometric-upward-downward.png = scenes/images/..., handed over as a PFM holding
-    # the reference's decode of an 8-bit image (value / 255, no gamma: core/src/image_io.rs:192-218); 1572 x 790, so MIPMap::new
-    # resamples it to 2048 x 1024 (Lanczos) before the lookups
+    # the light's image: tests/golden/ref_renders/goniometric-upward-downward.png = scenes/images/..., decoded by the loader as the
+    # reference decodes an 8-bit image (value / 255, no gamma: core/src/image_io.rs:192-218); 1572 x 790, so MIPMap::new resamples
+    # it to 2048 x 1024 (Lanczos) before the lookups
     "goniometric": '''  AttributeBegin
     Translate -5 0 5
     Rotate 135 1 0 0
     Rotate 60 0 1 0
-    LightSource "goniometric" "rgb I" [.4 .45 .5] "rgb scale" [200 200 200] "float fov" 45 "string mapname" "gonio.pfm"
+    LightSource "goniometric" "rgb I" [.4 .45 .5] "rgb scale" [200 200 200] "float fov" 45 "string mapname" "gonio.png"
   AttributeEnd
   AttributeBegin
     Rotate 45 0 0 1
@@ -171,11 +171,9 @@ def scene_file(tmp_path, which, ground_kd=None, spp=128, inside=1.0, outside=0.0
     p = tmp_path / ("%s_%s_%d_%g_%d.pbrt" % (which, ground_kd, spp, inside, len(texture_extra)))
     ground = GROUND % (ground_kd, ground_kd, ground_kd) if ground_kd is not None else GROUND_CHECKS % dict(a=ALBEDO[which][0], b=ALBEDO[which][1], extra=texture_extra)
     xres, yres = RESOLUTION.get(which, (400, 400))
-    if which == "goniometric" and not (tmp_path / "gonio.pfm").exists():
-        from PIL import Image
-        import __graft_entry__ as ge
-        px = np.array(Image.open(os.path.join(HERE, "golden", "ref_renders", "goniometric-upward-downward.png")).convert("RGB"))
-        ge.load_package().write_pfm(str(tmp_path / "gonio.pfm"), px.astype(F32) / F32(255.0))
+    if which == "goniometric" and not (tmp_path / "gonio.png").exists():
+        import shutil
+        shutil.copyfile(os.path.join(HERE, "golden", "ref_renders", "goniometric-upward-downward.png"), str(tmp_path / "gonio.png"))
     p.write_text(HEAD % dict(camera=CAMERA[which][0], spp=spp, xres=xres, yres=yres) + BODY[which] % dict(cube=CUBE, inside=inside, outside=outside) + ground)
     return str(p)
 

@@ -280,3 +280,21 @@ def test_loader_spot_light_and_other_cameras_match_the_mirror(tmp_path, pkg, ora
     assert bytes(C.cast(a.spectrum_textures, C.POINTER(pkg.SpectrumTexture))[0]) == bytes(C.cast(b.spectrum_textures, C.POINTER(pkg.SpectrumTexture))[0])
     ra, rb = oracle.OracleScene(ld).render(nthreads=2)[0], oracle.OracleScene(sd).render(nthreads=2)[0]
     assert ra.shape == rb.shape == (16, 20, 3) and ra.any() and ss.rel_rmse(ra, rb) <= 2e-2
+
+
+@pytest.mark.parametrize("mode", ["RGB", "RGBA", "L", "LA", "P"])
+def test_loader_decodes_8_bit_pngs_like_the_reference(tmp_path, pkg, mode):
+    """read_8_bit (core/src/image_io.rs:192-218): image::open(..).into_rgb8(), value / 255, no gamma - for every 8-bit PNG
+    colour type (the decoder inflates with zlib and undoes all five scanline filters; PIL is the independent decoder)."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    a = np.clip(np.cumsum(rng.integers(-9, 10, (23, 31, 3)), axis=1) + 128, 0, 255).astype(np.uint8)  # smooth rows: the encoder picks varied filters
+    Image.fromarray(a).convert(mode).save(str(tmp_path / "m.png"))
+    (tmp_path / "s.pbrt").write_text('Camera "perspective"\nWorldBegin\nLightSource "goniometric" "string mapname" "m.png"\n'
+                                     'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 1 1 0 1 0 1 1]\nWorldEnd\n')
+    ld = pkg.load_pbrt(str(tmp_path / "s.pbrt"))
+    light = C.cast(ld.to_desc().lights, C.POINTER(pkg.Light))[0]
+    assert (light.type, light.map_width, light.map_height) == (pkg.LIGHT_GONIOMETRIC, 31, 23)
+    got = _arr(light.map_rgb, 23 * 31 * 3, np.float32).reshape(23, 31, 3)
+    want = np.array(Image.open(str(tmp_path / "m.png")).convert("RGB")).astype(np.float32) / np.float32(255)
+    assert np.array_equal(got, want)

@@ -256,3 +256,39 @@ def test_gpu_reproduces_the_references_own_render(gpu, tmp_path, which):
     def render(path):
         return gpu.PathIntegrator(gpu.load_pbrt(path)).render()
     _check_scene(render, tmp_path, which, "gpu")
+
+
+REFERENCE_SCENES = "/root/reference/scenes"
+SHIPPED = {"point": "lights/point.pbrt", "spot": "lights/spot.pbrt", "goniometric": "lights/goniometric.pbrt", "distant": "lights/distant.pbrt",
+           "infinite-no-map": "lights/infinite-no-map.pbrt", "triangles-alpha-mask": "shapes/triangles-alpha-mask.pbrt", "perspective": "cameras/perspective.pbrt",
+           "orthographic": "cameras/orthographic.pbrt", "environment": "cameras/environment.pbrt", "instances": "objects/instances.pbrt"}
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_SCENES), reason="the reference tree is only present in the build container")
+def test_shipped_scene_files_load_unchanged_and_render_to_the_references_images():
+    """The ten scene files themselves, read where they lie (Include "../geometry/cube.pbrt", the goniometric light's PNG): they
+    are exactly the shipped files this path accepts, their descriptions equal the ones the tests above build, and two of them
+    rendered straight from the file give the reference's PNG."""
+    import glob
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    loaded = {}
+    for f in sorted(glob.glob(REFERENCE_SCENES + "/*/*.pbrt")):
+        rel = os.path.relpath(f, REFERENCE_SCENES)
+        if rel.startswith("geometry/"):
+            continue
+        try:
+            loaded[rel] = pkg.load_pbrt(f)
+        except pkg.B200PTError:
+            pass
+    assert sorted(loaded) == sorted(SHIPPED.values())
+    for which, rel in SHIPPED.items():
+        assert loaded[rel].output == "renders/" + rel.replace(".pbrt", ".png")
+    for which in ("point", "goniometric"):
+        img = encode_8bit(_oracle_render_loaded(loaded[SHIPPED[which]]))
+        assert np.array_equal(img, reference_png(which)), which
+
+
+def _oracle_render_loaded(ld):
+    import oracle_lib as ol
+    return ol.OracleScene(ld).render()[0]

@@ -368,7 +368,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-path", action="store_true", help="skip the path-tracing (samples/s) leg")
-    ap.add_argument("--path-iters", type=int, default=5)
+    ap.add_argument("--path-iters", type=int, default=9)
     ap.add_argument("--no-c4-rays", action="store_true", help="skip the HBM-resident C4-rays roofline line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY: pinned by execution for Whitted-class renders, see oracle_math.h.
 //
 // BVHAccel (SAH build, flatten, closest-hit / any-hit traversal) and the
 // watertight Triangle test, restated from accelerators/src/bvh/{mod,common,sah}.rs,

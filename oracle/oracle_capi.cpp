@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY: pinned by execution for Whitted-class renders, see oracle_math.h.
 //
 // extern "C" surface of the CPU oracle, loaded with ctypes by tests/, by
 // __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference

@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY UNPINNED for this file: no render of the reference
+// uses the HLBVH split method (see oracle_math.h for what is pinned by execution).
 //
 // BVHAccel::new with SplitMethod::HLBVH, restated from accelerators/src/bvh/hlbvh.rs:33-449 and morton.rs:37-120.
 //

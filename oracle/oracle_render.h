@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY: pinned by execution for Whitted-class renders, see oracle_math.h.
 //
 // PathIntegrator::li, direct lighting, BSDFs, materials, lights, camera, film
 // and the tile-parallel render loop, restated from the reference files cited at

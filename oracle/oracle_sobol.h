@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.h header).  PARITY UNPINNED for this file: no render of the reference on this
+// path uses the Sobol sampler; its tables are checked against the reference's literals (see oracle_math.h for what is pinned by execution).
 //
 // SobolSampler, restated from samplers/src/sobol.rs:25-196 and core/src/low_discrepency.rs:1770-1845
 // (sobol_interval_to_index, sobol_sample_f32).

@@ -73,6 +73,12 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi needs 50-500 ms (box dependent) before its first line: wait for it, so that the 20 ms samples fall
+            # INTO the warm-up + timed region that follows instead of after it (a ~140 ms region once ended with no sample at all)
+            t0 = time.perf_counter()
+            while not self.rows and self.proc.poll() is None and time.perf_counter() - t0 < 5.0:
+                time.sleep(0.005)
+            self.n_before = len(self.rows)
         except Exception:
             self.proc = None
 
@@ -90,7 +96,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[getattr(self, "n_before", 0):] or self.rows:  # the rows sampled after start() returned: warm-up + timed steps
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])

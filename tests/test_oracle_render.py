@@ -129,3 +129,41 @@ def test_instanced_scene_agrees_with_baked_geometry(pkg, oracle):
     assert abs(a.mean() - b.mean()) <= 2e-3 * b.mean()
     close = np.isclose(a, b, rtol=1e-3, atol=1e-4).all(2)
     assert close.mean() >= 0.97, close.mean()
+
+
+def test_orthographic_and_environment_camera_rays_closed_form(pkg, oracle):
+    """OrthographicCamera (orthographic_camera.rs:64-93): all rays share the direction camera_to_world((0, 0, 1)), their origins
+    lie on the film plane through the eye, one screen-window step per pixel.  EnvironmentCamera (environment_camera.rs:38-53):
+    origin at the eye, direction (sin t cos p, cos t, sin t sin p) with t = pi y / yres, p = 2 pi x / xres in camera space."""
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    import numpy as np
+
+    def scene(kind):
+        sd = SceneDescription()
+        m = sd.add_material(type="matte")
+        sd.add_mesh(np.array([[0, 0, 5, 1, 0, 5, 0, 1, 5]], dtype=np.float32), m)
+        sd.add_point_light((0, 0, 0), (1, 1, 1))
+        sd.camera.update(type=kind, eye=(1.0, 2.0, -3.0), look=(1.0, 2.0, 0.0), up=(0, 1, 0), screenwindow=(-2.0, 2.0, -1.0, 1.0))
+        sd.film.update(xresolution=8, yresolution=4)
+        sd.sampler.update(type="halton", pixelsamples=1, samplepixelcenter=True)
+        return sd
+
+    ps = np.array([(x, y, 0) for y in range(4) for x in range(8)], dtype=np.int32)
+    rays = oracle.OracleScene(scene("orthographic")).camera_rays(ps)
+    o, d = rays["o"].astype(np.float64), rays["d"].astype(np.float64)
+    assert np.allclose(d, [0, 0, 1], atol=1e-6)  # looking down +z
+    # pbrt's look_at is left-handed: raster x runs towards world -x here... the film plane is z = -3; pixel centres (x + .5, y + .5)
+    assert np.allclose(o[:, 2], -3.0, atol=1e-5)
+    xs, ys = o[:, 0].reshape(4, 8), o[:, 1].reshape(4, 8)
+    assert np.allclose(np.abs(np.diff(xs, axis=1)), 4.0 / 8, atol=1e-5) and np.allclose(np.abs(np.diff(ys, axis=0)), 2.0 / 4, atol=1e-5)
+    assert np.allclose(xs.mean(), 1.0, atol=1e-5) and np.allclose(ys.mean(), 2.0, atol=1e-5)  # centred on the eye
+    rays = oracle.OracleScene(scene("environment")).camera_rays(ps)
+    o, d = rays["o"].astype(np.float64), rays["d"].astype(np.float64)
+    assert np.allclose(o, [1.0, 2.0, -3.0], atol=1e-5)
+    t = np.pi * (ps[:, 1] + 0.5) / 4.0
+    p = 2 * np.pi * (ps[:, 0] + 0.5) / 8.0
+    cam = np.stack([np.sin(t) * np.cos(p), np.cos(t), np.sin(t) * np.sin(p)], axis=1)
+    # camera space -> world for this look_at: z forward (+z world), y up; x = right-handedness of pbrt's look_at (left-handed: x -> -x)
+    assert np.allclose(np.abs(d[:, 1]), np.abs(cam[:, 1]), atol=1e-5) and np.allclose(np.abs(d[:, 2]), np.abs(cam[:, 2]), atol=1e-5)
+    assert np.allclose(np.abs(d[:, 0]), np.abs(cam[:, 0]), atol=1e-5) and np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+    assert np.allclose(d[:, 1], cam[:, 1], atol=1e-5) and np.allclose(d[:, 2], cam[:, 2], atol=1e-5)  # y and z keep their sign

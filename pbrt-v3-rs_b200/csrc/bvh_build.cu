@@ -701,10 +701,20 @@ __global__ void __launch_bounds__(kBlock) k_hl_bounds(const float* __restrict__ 
     uint32_t key[6];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { key[k] = i < n ? fkey(pb[6 * (size_t)i + k]) : 0xffffffffu; key[3 + k] = i < n ? fkey(pb[6 * (size_t)i + 3 + k]) : 0u; }
+    // warp reduction, then one thread per block folds the warps' results: 6 global atomics per block instead of per warp
+    // (10 M primitives: 1.9 M atomics on six addresses took 1.27 ms of a 3.9 ms build)
+    __shared__ uint32_t part[kBlock / 32][6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         uint32_t r = k < 3 ? __reduce_min_sync(kFull, key[k]) : __reduce_max_sync(kFull, key[k]);
-        if ((threadIdx.x & 31) == 0) { if (k < 3) atomicMin(&acc[k], r); else atomicMax(&acc[k], r); }
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        uint32_t r = part[0][k];
+        for (int w = 1; w < kBlock / 32; ++w) r = k < 3 ? min(r, part[w][k]) : max(r, part[w][k]);
+        if (k < 3) atomicMin(&acc[k], r); else atomicMax(&acc[k], r);
     }
 }
 __device__ inline uint32_t spread3(uint32_t x) {  // left_shift_3 (morton.rs:102-120), debug_assert compiled out

@@ -95,6 +95,9 @@ enum { B200PT_LIGHT_POINT = 0, B200PT_LIGHT_AREA = 1, B200PT_LIGHT_INFINITE = 2,
        B200PT_LIGHT_GONIOMETRIC = 5, /* lights/src/goniometric.rs: pos = p_light, L = I * scale, world_to_light, and the "mapname" image in
                                       * map_rgb (decoded, as for an infinite light): the intensity in direction w is scaled by the image
                                       * at (phi, theta) of world_to_light(w) with y and z swapped - MIPMap::lookup_triangle(st, 0) (:101-115) */
+       B200PT_LIGHT_PROJECTION = 6, /* lights/src/projection.rs: pos = p_light, L = I * scale, world_to_light, the image in map_rgb (NULL: 1),
+                                     * fov = "fov" in degrees (the projection is Transform::perspective(fov, 1e-3, 1e30); the screen window follows
+                                     * from the image's aspect, :84-88), cos_total_width = z of the normalised screen corner (:92-95; power() only) */
        B200PT_LIGHT_SPOT = 4 /* lights/src/spot.rs: pos = p_light = light_to_world(0), L = I * scale, world_to_light = the inverse of
                               * ctm * Translate(from) * dir_to_z^-1 (spot.rs:209-226), cos_total_width / cos_falloff_start =
                               * cos(radians(coneangle)), cos(radians(coneangle - conedeltaangle)) (spot.rs:57-58) */ };
@@ -111,7 +114,9 @@ typedef struct b200pt_light {
      * (the reference then uses the 1x1 image [L]). */
     const float* map_rgb;
     int32_t map_width, map_height;
-    float cos_total_width, cos_falloff_start; /* spot */
+    float cos_total_width, cos_falloff_start; /* spot; projection: cos_total_width */
+    float fov;                                /* projection: "fov" (degrees) */
+    int32_t pad_;
 } b200pt_light;
 
 /* cameras/src/perspective_camera.rs + core/src/camera.rs:276-306: the two
@@ -365,7 +370,7 @@ int b200pt_sobol_interval_tables(const uint32_t* sobol_matrices_32, int m, uint6
  * directlighting integrator with uniform / power / spatial light sampling; bvh accelerator with splitmethod sah / hlbvh;
  * trianglemesh / plymesh shapes with P, N, S, uv/st, alpha, shadowalpha (float textures: constant, checkerboard, dots,
  * imagemap); matte / plastic / glass / metal / mirror with constant parameters (a matte / plastic "Kd" may be a constant or
- * checkerboard spectrum texture); point / spot / goniometric / distant / infinite / diffuse area lights (image maps: .pfm and
+ * checkerboard spectrum texture); point / spot / projection / goniometric / distant / infinite / diffuse area lights (image maps: .pfm and
  * 8-bit .png); rgb / color /
  * blackbody spectra; transforms, attribute and transform stacks, named materials, object instancing, Include) and builds the BVHs
  * with b200pt_bvh_build_sah (on the GPU once a device is bound) / b200pt_bvh_build_hlbvh.  Anything else returns

@@ -571,6 +571,11 @@ inline RGB light_power(const RenderScene& sc, int li) {
     const b200pt_light& l = sc.lights[li];
     if (l.type == B200PT_LIGHT_POINT) return kFourPi * light_L(l);
     if (l.type == B200PT_LIGHT_DISTANT) return light_L(l) * kPi * sc.world_radius * sc.world_radius;  // distant.rs:92-95
+    if (l.type == B200PT_LIGHT_PROJECTION) {  // projection.rs:173-183
+        RGB spec(1.0f);
+        if (!sc.inf_map[(size_t)li].pyramid.empty()) spec = sc.inf_map[(size_t)li].lookup_triangle(P2(0.5f, 0.5f), 0.5f);
+        return spec * light_L(l) * kTwoPi * (1.0f - l.cos_total_width);
+    }
     if (l.type == B200PT_LIGHT_GONIOMETRIC) {  // goniometric.rs:140-150
         RGB spec(1.0f);
         if (!sc.inf_map[(size_t)li].pyramid.empty()) spec = sc.inf_map[(size_t)li].lookup_triangle(P2(0.5f, 0.5f), 0.5f);
@@ -669,7 +674,7 @@ inline RenderScene* scene_create(const b200pt_scene_desc* d) {
         const b200pt_light& l = s->lights[i];
         if (l.type == B200PT_LIGHT_AREA)
             s->light_area[i] = triangle_area(s->accel.vert(l.prim, 0), s->accel.vert(l.prim, 1), s->accel.vert(l.prim, 2));
-        if (l.type == B200PT_LIGHT_GONIOMETRIC && l.map_rgb && l.map_width > 0 && l.map_height > 0) {  // GonioPhotometricLight::new, goniometric.rs:71-90
+        if ((l.type == B200PT_LIGHT_GONIOMETRIC || l.type == B200PT_LIGHT_PROJECTION) && l.map_rgb && l.map_width > 0 && l.map_height > 0) {  // GonioPhotometricLight::new, goniometric.rs:71-90; ProjectionLight::new, projection.rs:62-75
             std::vector<RGB> texels((size_t)l.map_width * l.map_height);
             for (size_t k = 0; k < texels.size(); ++k) texels[k] = RGB(l.map_rgb[3 * k], l.map_rgb[3 * k + 1], l.map_rgb[3 * k + 2]);
             s->inf_map[i].build(l.map_width, l.map_height, texels);
@@ -950,6 +955,29 @@ struct LiSample {
 // DiffuseAreaLight::l, diffuse.rs:220-226
 inline RGB area_l(const b200pt_light& l, V3 n, V3 w) { return (l.two_sided || dot(n, w) > 0.0f) ? light_L(l) : RGB(); }
 
+// ProjectionLight::projection (projection.rs:115-139).  light_projection = Transform::perspective(fov, 1e-3, 1e30): its x / y rows are
+// (inv_tan, 0, 0, 0) / (0, inv_tan, 0, 0) and w = z, so transform_point is (inv_tan x, inv_tan y, ..) * (1 / z).
+inline RGB projection_light_scale(const RenderScene& sc, int li, V3 w) {
+    const b200pt_light& l = sc.lights[(size_t)li];
+    V3 wl = xf_vector(m4_from(l.world_to_light), w);
+    if (wl.z < 1e-3f) return RGB();
+    const Float inv_tan = 1.0f / std::tan(to_radians(l.fov) / 2.0f);
+    const Float xp = inv_tan * wl.x, yp = inv_tan * wl.y, wp = wl.z;
+    Float px = xp, py = yp;
+    if (wp != 1.0f) { Float inv = 1.0f / wp; px = xp * inv; py = yp * inv; }
+    const bool has_map = !sc.inf_map[(size_t)li].pyramid.empty();
+    const Float aspect = (l.map_rgb && l.map_width > 0 && l.map_height > 0) ? (Float)l.map_width / (Float)l.map_height : 1.0f;
+    Float x0, y0, x1, y1;
+    if (aspect > 1.0f) { x0 = -aspect; y0 = -1.0f; x1 = aspect; y1 = 1.0f; }
+    else { x0 = -1.0f; y0 = -1.0f / aspect; x1 = 1.0f; y1 = 1.0f / aspect; }
+    if (!(px >= x0 && px <= x1 && py >= y0 && py <= y1)) return RGB();
+    if (!has_map) return RGB(1.0f);
+    Float ox = px - x0, oy = py - y0;  // Bounds2::offset, bounds2.rs:161-173
+    if (x1 > x0) ox /= x1 - x0;
+    if (y1 > y0) oy /= y1 - y0;
+    return sc.inf_map[(size_t)li].lookup_triangle(P2(ox, oy), 0.0f);
+}
+
 inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hit, P2 u) {
     const b200pt_light& l = sc.lights[li];
     LiSample r;
@@ -959,6 +987,15 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
         r.pdf = 1.0f;
         r.p1 = pl;
         r.value = light_L(l) / distance_squared(pl, hit.p);
+        r.valid = true;
+        return r;
+    }
+    if (l.type == B200PT_LIGHT_PROJECTION) {  // projection.rs:160-171 with projection(), :115-139
+        V3 pl(l.pos[0], l.pos[1], l.pos[2]);
+        r.wi = normalize(pl - hit.p);
+        r.pdf = 1.0f;
+        r.p1 = pl;
+        r.value = light_L(l) * projection_light_scale(sc, li, -r.wi) / distance_squared(pl, hit.p);
         r.valid = true;
         return r;
     }
@@ -1053,7 +1090,7 @@ inline LiSample light_sample_li(const RenderScene& sc, int li, const SurfHit& hi
 // Light::pdf_li
 inline Float light_pdf_li(const RenderScene& sc, int li, const SurfHit& hit, V3 wi) {
     const b200pt_light& l = sc.lights[li];
-    if (l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT || l.type == B200PT_LIGHT_GONIOMETRIC) return 0.0f;
+    if (l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT || l.type == B200PT_LIGHT_GONIOMETRIC || l.type == B200PT_LIGHT_PROJECTION) return 0.0f;
     if (l.type == B200PT_LIGHT_AREA) {  // Shape::pdf_solid_angle, shape.rs:81-107
         Ray ray = spawn_ray(hit, wi);
         V3 p0 = sc.accel.vert(l.prim, 0), p1 = sc.accel.vert(l.prim, 1), p2 = sc.accel.vert(l.prim, 2);
@@ -1071,7 +1108,7 @@ inline Float light_pdf_li(const RenderScene& sc, int li, const SurfHit& hit, V3 
     if (sin_t == 0.0f) return 0.0f;
     return sc.inf_distr[li].pdf(P2(phi * kInvTwoPi, theta * kInvPi)) / (kTwoPi * kPi * sin_t);
 }
-inline bool light_is_delta(const b200pt_light& l) { return l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT || l.type == B200PT_LIGHT_GONIOMETRIC; }  // DELTA_POSITION | DELTA_DIRECTION
+inline bool light_is_delta(const b200pt_light& l) { return l.type == B200PT_LIGHT_POINT || l.type == B200PT_LIGHT_DISTANT || l.type == B200PT_LIGHT_SPOT || l.type == B200PT_LIGHT_GONIOMETRIC || l.type == B200PT_LIGHT_PROJECTION; }  // DELTA_POSITION | DELTA_DIRECTION
 
 // core/src/integrator/common.rs:146-299 (handle_media = false, specular = false)
 inline RGB estimate_direct(RenderScene& sc, const SurfHit& hit, const BSDF& bsdf, P2 u_scatter, int li, P2 u_light) {

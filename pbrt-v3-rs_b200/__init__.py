@@ -27,7 +27,7 @@ MISS = 0xFFFFFFFF
 PRIM_FLIP_NORMAL, PRIM_ALPHA_ZERO, PRIM_SHADOW_ALPHA_ZERO = 1, 2, 4
 PRIM_REVERSE_ORIENTATION, PRIM_HAS_UV, PRIM_HAS_NORMALS, PRIM_HAS_TANGENTS = 8, 16, 32, 64
 MAT_MATTE, MAT_PLASTIC, MAT_GLASS, MAT_METAL, MAT_MIRROR = 0, 1, 2, 3, 4
-LIGHT_POINT, LIGHT_AREA, LIGHT_INFINITE, LIGHT_DISTANT, LIGHT_SPOT, LIGHT_GONIOMETRIC = 0, 1, 2, 3, 4, 5
+LIGHT_POINT, LIGHT_AREA, LIGHT_INFINITE, LIGHT_DISTANT, LIGHT_SPOT, LIGHT_GONIOMETRIC, LIGHT_PROJECTION = 0, 1, 2, 3, 4, 5, 6
 SAMPLER_HALTON, SAMPLER_ZEROTWO, SAMPLER_SOBOL = 0, 1, 2
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 INTEGRATOR_PATH, INTEGRATOR_WHITTED, INTEGRATOR_DIRECT = 0, 1, 2
@@ -66,7 +66,7 @@ class Light(C.Structure):
     _fields_ = [("type", C.c_int32), ("pos", C.c_float * 3), ("L", C.c_float * 3), ("prim", C.c_int32),
                 ("two_sided", C.c_int32), ("light_to_world", C.c_float * 16), ("world_to_light", C.c_float * 16),
                 ("map_rgb", C.c_void_p), ("map_width", C.c_int32), ("map_height", C.c_int32),
-                ("cos_total_width", C.c_float), ("cos_falloff_start", C.c_float)]
+                ("cos_total_width", C.c_float), ("cos_falloff_start", C.c_float), ("fov", C.c_float), ("pad_", C.c_int32)]
 
 
 CAMERA_PERSPECTIVE, CAMERA_ORTHOGRAPHIC, CAMERA_ENVIRONMENT = 0, 1, 2

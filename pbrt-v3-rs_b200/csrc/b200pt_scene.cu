@@ -1473,7 +1473,7 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
     for (int i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type >= 0 && d->materials[i].type < 5) s->material_classes |= 1u << d->materials[i].type;
         else { b200pt_set_error("b200pt_scene_create: unknown material type"); delete sc; return B200PT_ERR_INVALID; }
-    for (int i = 0; i < d->n_lights; ++i) if (d->lights[i].type == B200PT_LIGHT_POINT || d->lights[i].type == B200PT_LIGHT_DISTANT || d->lights[i].type == B200PT_LIGHT_SPOT || d->lights[i].type == B200PT_LIGHT_GONIOMETRIC) ++s->n_point_lights;  // delta lights
+    for (int i = 0; i < d->n_lights; ++i) if (d->lights[i].type == B200PT_LIGHT_POINT || d->lights[i].type == B200PT_LIGHT_DISTANT || d->lights[i].type == B200PT_LIGHT_SPOT || d->lights[i].type == B200PT_LIGHT_GONIOMETRIC || d->lights[i].type == B200PT_LIGHT_PROJECTION) ++s->n_point_lights;  // delta lights
     auto fail = [&](int code) { b200pt_scene_destroy(sc); return code; };
     DeviceScene& D = s->dev;
     std::memset(&D, 0, sizeof(D));
@@ -1648,8 +1648,9 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
             inf_distr.push_back(dd);
             RGB spec = rgb(em.power_lookup[0], em.power_lookup[1], em.power_lookup[2]);  // infinite.rs:177-186
             power = kPi * radius * radius * spec;
-        } else if (l.type == B200PT_LIGHT_GONIOMETRIC) {
-            // GonioPhotometricLight::new (goniometric.rs:59-100): MIPMap over the image; power = 4 pi I lookup_triangle((.5, .5), .5) (:140-150)
+        } else if (l.type == B200PT_LIGHT_GONIOMETRIC || l.type == B200PT_LIGHT_PROJECTION) {
+            // GonioPhotometricLight::new (goniometric.rs:59-100) / ProjectionLight::new (projection.rs:50-110): MIPMap over the image;
+            // power = 4 pi I lookup_triangle((.5, .5), .5) (goniometric.rs:140-150) or lookup * I * 2 pi (1 - cos_total_width) (projection.rs:173-183)
             o.inf_slot = (int)inf_distr.size();
             b2host::EnvMapTables em;
             const float one[3] = {1.0f, 1.0f, 1.0f};
@@ -1662,7 +1663,16 @@ int b200pt_scene_create(const b200pt_scene_desc* d, b200pt_scene** out) {
             if ((rc = dev_upload(s, em.texels, &tex))) return fail(rc);
             dd.texels = (const float4*)tex;
             inf_distr.push_back(dd);
-            power = kFourPi * Lr * rgb(em.power_lookup[0], em.power_lookup[1], em.power_lookup[2]);
+            const RGB spec = rgb(em.power_lookup[0], em.power_lookup[1], em.power_lookup[2]);
+            if (l.type == B200PT_LIGHT_GONIOMETRIC) power = kFourPi * Lr * spec;
+            else {
+                power = spec * Lr * (kPi * 2.0f) * (1.0f - l.cos_total_width);
+                const bool has_map = l.map_rgb && l.map_width > 0 && l.map_height > 0;
+                const float aspect = has_map ? (float)l.map_width / (float)l.map_height : 1.0f;
+                o.l2w[0] = 1.0f / std::tan(l.fov * (3.14159265358979323846f / 180.0f) / 2.0f);  // Transform::perspective, transform.rs:244
+                if (aspect > 1.0f) { o.l2w[1] = -aspect; o.l2w[2] = -1.0f; o.l2w[3] = aspect; o.l2w[4] = 1.0f; }
+                else { o.l2w[1] = -1.0f; o.l2w[2] = -1.0f / aspect; o.l2w[3] = 1.0f; o.l2w[4] = 1.0f / aspect; }
+            }
         } else { b200pt_set_error("b200pt_scene_create: unknown light type"); return fail(B200PT_ERR_INVALID); }
         power_y[(size_t)i] = lum_y(power);
     }

@@ -889,8 +889,8 @@ struct Builder {
             const float inv = 1.0f / len;  // Vector3::normalize = self / length = self * (1 / length)
             l.pos[0] = inv * w.x; l.pos[1] = inv * w.y; l.pos[2] = inv * w.z;
             std::memcpy(l.light_to_world, gs.ctm.m.m, 64); std::memcpy(l.world_to_light, gs.ctm.inv.m, 64);
-        } else if (name == "goniometric") {  // goniometric.rs:219-238 + GonioPhotometricLight::new :59-100
-            l.type = B200PT_LIGHT_GONIOMETRIC;
+        } else if (name == "goniometric" || name == "projection") {  // goniometric.rs:219-238 + GonioPhotometricLight::new :59-100; projection.rs:266-288 + ::new :50-110
+            l.type = name == "projection" ? B200PT_LIGHT_PROJECTION : B200PT_LIGHT_GONIOMETRIC;
             float I[3];
             p.one_rgb("I", one, I);
             for (int c = 0; c < 3; ++c) l.L[c] = I[c] * sc[c];
@@ -904,6 +904,15 @@ struct Builder {
                 read_image(resolve(map), img.get(), &w, &h);
                 l.map_rgb = img->data(); l.map_width = w; l.map_height = h;
                 L->images.push_back(std::move(img));
+            }
+            if (name == "projection") {
+                l.fov = p.one_float("fov", 45.0f);
+                const float aspect = l.map_rgb ? (float)l.map_width / (float)l.map_height : 1.0f;
+                const float cx = aspect > 1.0f ? aspect : 1.0f, cy = aspect > 1.0f ? 1.0f : 1.0f / aspect;  // screen_bounds.p_max
+                const Xf s2l = xf_inverse(xf_perspective(l.fov, 1e-3f, 1e30f));
+                const V3 wc = xf_point(s2l.m, v3(cx, cy, 0.0f));
+                const float inv = 1.0f / std::sqrt(wc.x * wc.x + wc.y * wc.y + wc.z * wc.z);
+                l.cos_total_width = wc.z * inv;  // Vector3::normalize = self * (1 / length)
             }
         } else if (name == "spot") {  // spot.rs:200-237 + SpotLight::new :44-60
             l.type = B200PT_LIGHT_SPOT;
@@ -933,7 +942,7 @@ struct Builder {
             const float rad = 3.14159265358979323846f / 180.0f;  // f32::to_radians
             l.cos_total_width = std::cos(cone_angle * rad);
             l.cos_falloff_start = std::cos((cone_angle - cone_delta) * rad);
-        } else throw Unsupported("LightSource \"" + name + "\" is outside this path (point, spot, goniometric, distant, infinite)");
+        } else throw Unsupported("LightSource \"" + name + "\" is not one of the reference's lights (point, spot, projection, goniometric, distant, infinite)");
         L->lights.push_back(l);
     }
 

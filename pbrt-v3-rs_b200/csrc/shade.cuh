@@ -455,8 +455,8 @@ template <uint32_t KM = KM_ALL> B2_D BxDFSample bsdf_sample_f(const BSDF& b, V3 
 }
 
 // ---- lights -------------------------------------------------------------------------
-enum : int { LT_POINT = 0, LT_AREA = 1, LT_INFINITE = 2, LT_DISTANT = 3, LT_SPOT = 4, LT_GONIO = 5 };
-B2_D bool light_is_delta(int type) { return type == LT_POINT || type == LT_DISTANT || type == LT_SPOT || type == LT_GONIO; }  // light.rs: DELTA_POSITION | DELTA_DIRECTION
+enum : int { LT_POINT = 0, LT_AREA = 1, LT_INFINITE = 2, LT_DISTANT = 3, LT_SPOT = 4, LT_GONIO = 5, LT_PROJECTION = 6 };
+B2_D bool light_is_delta(int type) { return type == LT_POINT || type == LT_DISTANT || type == LT_SPOT || type == LT_GONIO || type == LT_PROJECTION; }  // light.rs: DELTA_POSITION | DELTA_DIRECTION
 struct DLight {
     int type;
     int prim;        // area: original primitive index
@@ -466,7 +466,7 @@ struct DLight {
     float area;      // area: Triangle::area (host, f32); spot: cos_total_width
     float L[3];
     float cos_falloff_start;  // spot
-    float l2w[9];    // infinite: upper 3x3 of light_to_world (row-major)
+    float l2w[9];    // infinite: upper 3x3 of light_to_world (row-major); projection: inv_tan, then the screen window x0 y0 x1 y1
     float w2l[9];    // infinite, spot: upper 3x3 of world_to_light
 };
 // Environment map of an InfiniteAreaLight (host_envmap.cpp): level 0 of its MIPMap (float4 texels already multiplied by
@@ -549,6 +549,20 @@ B2_D RGB gonio_scale(const DLight& l, const DInfDistr& D, V3 w_world) {
     const float t = wp.y; wp.y = wp.z; wp.z = t;
     P2 st = mk2(spherical_phi(wp) * kInvTwoPi, spherical_theta(wp) * kInvPi);
     return inf_lookup(D, st);
+}
+// ProjectionLight::projection (projection.rs:115-139): Transform::perspective(fov, 1e-3, 1e30).transform_point is
+// (inv_tan x, inv_tan y, ..) * (1 / z); outside the screen window or behind the near plane the light is black
+B2_D RGB projection_scale(const DLight& l, const DInfDistr& D, V3 w_world) {
+    const V3 wl = xf3(l.w2l, w_world);
+    if (wl.z < 1e-3f) return rgb1(0.0f);
+    const float inv_tan = l.l2w[0], x0 = l.l2w[1], y0 = l.l2w[2], x1 = l.l2w[3], y1 = l.l2w[4];
+    float px = inv_tan * wl.x, py = inv_tan * wl.y;
+    if (wl.z != 1.0f) { const float inv = 1.0f / wl.z; px = px * inv; py = py * inv; }
+    if (!(px >= x0 && px <= x1 && py >= y0 && py <= y1)) return rgb1(0.0f);
+    float ox = px - x0, oy = py - y0;  // Bounds2::offset
+    if (x1 > x0) ox /= x1 - x0;
+    if (y1 > y0) oy /= y1 - y0;
+    return inf_lookup(D, mk2(ox, oy));
 }
 // DiffuseAreaLight::l, diffuse.rs:220-226
 B2_D RGB area_l(const DLight& l, V3 n, V3 w) { return (l.two_sided || dot(n, w) > 0.0f) ? ldrgb(l.L) : rgb1(0.0f); }

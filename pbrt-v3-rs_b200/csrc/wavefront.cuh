@@ -294,6 +294,13 @@ B2_D LightSample sample_light(const DeviceScene& S, const DLight& light, const S
         lp1 = pl;
         Li = ldrgb(light.L) / distance_squared(pl, sh.p);
         li_valid = true;
+    } else if (light.type == LT_PROJECTION) {  // projection.rs:160-171
+        V3 pl = mk(light.pos[0], light.pos[1], light.pos[2]);
+        wi = normalize(pl - sh.p);
+        light_pdf = 1.0f;
+        lp1 = pl;
+        Li = ldrgb(light.L) * projection_scale(light, S.inf_distr[light.inf_slot], -wi) / distance_squared(pl, sh.p);
+        li_valid = true;
     } else if (light.type == LT_GONIO) {  // goniometric.rs:127-138
         V3 pl = mk(light.pos[0], light.pos[1], light.pos[2]);
         wi = normalize(pl - sh.p);

@@ -298,6 +298,25 @@ class SceneDescription:
         self.lights.append(dict(type="goniometric", L=tuple(I), pos=tuple(float(c) for c in m[:3, 3]), light_to_world=m.reshape(-1),
                                 world_to_light=_m4_inverse(m).reshape(-1), image=img))
 
+    def add_projection_light(self, I, image=None, light_to_world=None, fov=45.0):
+        """LightSource "projection" (lights/src/projection.rs): a point light at light_to_world(0) that projects ``image``
+        ((h, w, 3) floats, top row first; None = white) along the light's +z with the given field of view."""
+        m = np.eye(4, dtype=F32) if light_to_world is None else np.asarray(light_to_world, dtype=F32).reshape(4, 4)
+        img = None if image is None else np.ascontiguousarray(image, dtype=F32)
+        aspect = F32(1.0) if img is None else F32(img.shape[1]) / F32(img.shape[0])
+        cx, cy = (aspect, F32(1.0)) if aspect > 1 else (F32(1.0), F32(1.0) / aspect)
+        # w_corner = normalize(screen_to_light(p_max)), projection.rs:92-95, with light_projection = Transform::perspective(fov, 1e-3, 1e30)
+        n, f = F32(1e-3), F32(1e30)
+        persp = np.eye(4, dtype=F32)
+        persp[2, 2] = f / (f - n); persp[2, 3] = -f * n / (f - n); persp[3, 2] = F32(1); persp[3, 3] = F32(0)
+        inv_tan = F32(1) / F32(math.tan(float(F32(fov) * F32(math.pi / 180.0)) / 2.0))
+        s2l = _m4_mul(_m4_inverse(persp), np.diag([F32(1) / inv_tan, F32(1) / inv_tan, F32(1), F32(1)]).astype(F32))
+        q = s2l @ np.array([cx, cy, 0.0, 1.0], dtype=F32)
+        wc = (q[:3] / q[3]).astype(F32)
+        cos_total = float(wc[2] / np.sqrt(np.sum(wc * wc, dtype=F32), dtype=F32))
+        self.lights.append(dict(type="projection", L=tuple(I), pos=tuple(float(c) for c in m[:3, 3]), light_to_world=m.reshape(-1),
+                                world_to_light=_m4_inverse(m).reshape(-1), image=img, fov=float(fov), cos_total_width=cos_total))
+
     def add_distant_light(self, L, w_light):
         """LightSource "distant" (lights/src/distant.rs): radiance ``L`` arriving from direction ``w_light`` (towards the
         light, world space; normalised here the way Vector3::normalize does: v * (1 / |v|))."""
@@ -480,9 +499,11 @@ class SceneDescription:
             elif l["type"] == "distant":
                 Lt.type = LIGHT_DISTANT
                 Lt.pos[:] = l["pos"]
-            elif l["type"] == "goniometric":
-                Lt.type = 5
+            elif l["type"] in ("goniometric", "projection"):
+                Lt.type = 5 if l["type"] == "goniometric" else 6
                 Lt.pos[:] = l["pos"]
+                if l["type"] == "projection":
+                    Lt.fov, Lt.cos_total_width = l["fov"], l["cos_total_width"]
                 if l.get("image") is not None:
                     keep.append(l["image"])
                     Lt.map_rgb = l["image"].ctypes.data_as(C.c_void_p)

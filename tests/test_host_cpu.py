@@ -35,7 +35,7 @@ def test_integration_md_binds_every_declared_symbol(pkg):
 def test_struct_sizes_match_header(pkg):
     assert pkg.RAY_DTYPE.itemsize == 32 and pkg.HIT_DTYPE.itemsize == 16 and pkg.NODE_DTYPE.itemsize == 32
     assert C.sizeof(pkg.Material) == 4 + 15 * 4 + 3 * 4 + 4
-    assert C.sizeof(pkg.Light) == 168 + 8 + 4 + 4 + 8  # 164 bytes of scalars, padded to 168 for the map pointer; map size; the spot light's two cosines
+    assert C.sizeof(pkg.Light) == 168 + 8 + 4 + 4 + 8 + 8  # 164 bytes of scalars, padded to 168 for the map pointer; map size; the spot light's two cosines; the projection light's fov + padding
     assert C.sizeof(pkg.Film) == 8 + 16 + 8 + 1024 + 8
     assert C.sizeof(pkg.FloatTexture) == 4 + 16 + 8 + 12 + 8  # 40 bytes of scalars, then the texel pointer
 

@@ -661,3 +661,29 @@ def test_goniometric_light_matches_oracle(gpu, oracle, integrator, with_map):
     ref, stats, _ = osc.render()
     assert img_g.mean() > 0.01 and ss.rel_rmse(img_g, ref) <= TOL
     assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("integrator,with_map", [("whitted", True), ("path", True), ("directlighting", False)])
+def test_projection_light_matches_oracle(gpu, oracle, integrator, with_map):
+    """ProjectionLight (lights/src/projection.rs): a point light that projects an image through Transform::perspective(fov, 1e-3,
+    1e30) - black behind the near plane and outside the screen window, MIPMap::lookup_triangle(st, 0) inside; power
+    lookup * I * 2 pi (1 - cos_total_width) in the light distribution."""
+    from pbrt_v3_rs_b200 import workloads as wl
+    sd = ss.one_material_scene(wl, ss.MATERIALS["plastic"], light="area", res=32, spp=8, maxdepth=4, strategy="power")
+    rng = np.random.default_rng(6)
+    img = (rng.uniform(0.0, 1.0, size=(10, 24, 3)) ** 2).astype(np.float32) if with_map else None
+    # the light above the scene looking down (+z of the light = world -y), slightly rotated about its axis
+    c, s_ = np.float32(np.cos(0.4)), np.float32(np.sin(0.4))
+    m = np.array([[c, -s_, 0, 0.3], [0, 0, -1, 3.5], [s_, c, 0, -0.5], [0, 0, 0, 1]], dtype=np.float32)
+    sd.add_projection_light((80, 75, 70), image=img, light_to_world=m, fov=60.0)
+    sd.integrator.update(name=integrator)
+    integ = gpu.PathIntegrator(sd)
+    osc = oracle.OracleScene(sd)
+    ps = _pairs(32, 4)
+    li, _ = integ.li(ps)
+    assert np.isclose(li, osc.li(ps), rtol=2e-3, atol=1e-5).all(1).mean() >= 0.999
+    img_g = integ.render()
+    ref, stats, _ = osc.render()
+    assert img_g.mean() > 0.01 and ss.rel_rmse(img_g, ref) <= TOL
+    assert [int(x) for x in integ.ray_counts()] == [int(x) for x in stats[:3]]

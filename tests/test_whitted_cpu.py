@@ -203,3 +203,39 @@ def test_mirror_reflects_an_emitter_closed_form(pkg, oracle, integrator):
     sd.integrator.update(name=integrator, maxdepth=4)
     img = oracle.OracleScene(sd).render(nthreads=1)[0]
     assert np.allclose(img, np.array([0.9 * 3, 0.8 * 2, 0.7 * 1]), rtol=1e-5)
+
+
+def test_projection_light_on_matte_floor_closed_form(pkg, oracle):
+    """ProjectionLight (lights/src/projection.rs:115-171): a point light whose intensity is the image at the perspective
+    projection of the light-space direction - here a 2 x 1 image (left half red, right half green; aspect 2 -> screen window
+    [-2, 2] x [-1, 1]), the light 2 above a matte floor looking straight down with fov 90: floor point (x, z) sees the texel at
+    s = (x' / d + 2) / 4, t = (y' / d + 1) / 2 (bilinear over the two texels with repeat wrap), black outside the window."""
+    kd, I, h = np.array([0.5, 0.25, 0.125]), 8.0, 2.0
+    sd = _floor_scene(kd=tuple(kd), res=33)
+    sd.lights.clear()
+    sd.camera.update(fov=100.0)
+    img = np.array([[[1, 0, 0], [0, 1, 0]]], dtype=np.float32)
+    # light space: +z = world -y (down), x = world x, y = world z
+    l2w = np.array([[1, 0, 0, 0], [0, 0, -1, h], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.float32)
+    sd.add_projection_light((I, I, I), image=img, light_to_world=l2w, fov=90.0)
+    sc = oracle.OracleScene(sd)
+    ps = np.array([(x, y, 0) for y in range(33) for x in range(33)], dtype=np.int32)
+    li = sc.li(ps, nthreads=1).astype(np.float64)
+    rays = sc.camera_rays(ps)
+    o, d = rays["o"].astype(np.float64), rays["d"].astype(np.float64)
+    p = o + (-o[:, 1] / d[:, 1])[:, None] * d
+    to_light = np.array([0.0, h, 0.0]) - p
+    d2 = (to_light ** 2).sum(1)
+    wl = np.stack([p[:, 0], p[:, 2], np.full(len(p), h)], axis=1)  # light-space direction towards the floor point (z = depth)
+    px, py = wl[:, 0] / wl[:, 2], wl[:, 1] / wl[:, 2]  # fov 90: inv_tan = 1
+    inside = (np.abs(px) <= 2) & (np.abs(py) <= 1)
+    s = (px + 2) / 4
+    # MIPMap::lookup_triangle(st, 0) over 2 x 1 texels, repeat wrap: texel centres at s = .25 (red) and .75 (green)
+    fs = s * 2 - 0.5
+    s0 = np.floor(fs); ds = fs - s0
+    tex = np.array([[1, 0, 0], [0, 1, 0]], dtype=np.float64)
+    c = tex[(s0.astype(int)) % 2] * (1 - ds)[:, None] + tex[(s0.astype(int) + 1) % 2] * ds[:, None]
+    expect = (kd[None, :] / np.pi) * (I * c / d2[:, None]) * (to_light[:, 1] / np.sqrt(d2))[:, None] * inside[:, None]
+    edge = (np.abs(np.abs(px) - 2) < 1e-3) | (np.abs(np.abs(py) - 1) < 1e-3)
+    assert np.allclose(li[~edge], expect[~edge], rtol=3e-4, atol=1e-6)
+    assert inside.sum() > 100 and (~inside).sum() > 100

@@ -298,3 +298,42 @@ def test_loader_decodes_8_bit_pngs_like_the_reference(tmp_path, pkg, mode):
     got = _arr(light.map_rgb, 23 * 31 * 3, np.float32).reshape(23, 31, 3)
     want = np.array(Image.open(str(tmp_path / "m.png")).convert("RGB")).astype(np.float32) / np.float32(255)
     assert np.array_equal(got, want)
+
+
+def test_loader_projection_light_matches_the_mirror(tmp_path, pkg, oracle):
+    """LightSource "projection" with a PNG map under Translate / Rotate: type, position, fov, the image and cos_total_width (z of
+    the normalised screen corner through the numerically inverted perspective matrix, projection.rs:90-95) equal the mirror's."""
+    from PIL import Image
+    from pbrt_v3_rs_b200 import workloads as wl
+    from pbrt_v3_rs_b200.scene import SceneDescription
+    rng = np.random.default_rng(9)
+    px = rng.integers(0, 256, (6, 14, 3)).astype(np.uint8)
+    Image.fromarray(px).save(str(tmp_path / "slide.png"))
+    quad = wl.ground_quad()
+    (tmp_path / "s.pbrt").write_text('\n'.join([
+        'LookAt 0 1.2 -4  0 -0.1 0  0 1 0', 'Camera "perspective" "float fov" 40', 'Film "image" "integer xresolution" [20] "integer yresolution" [16] "string filename" "o.png"',
+        'Sampler "halton" "integer pixelsamples" 4', 'Integrator "whitted"', 'WorldBegin',
+        'AttributeBegin', 'Translate 0.5 3 0', 'Rotate 90 1 0 0', 'LightSource "projection" "rgb I" [30 30 30] "float fov" 50 "string mapname" "slide.png"', 'AttributeEnd',
+        'Material "matte"', 'Shape "trianglemesh" "integer indices" [0 1 2 3 4 5] "point P" [%s]' % _fl(quad), 'WorldEnd']) + '\n')
+    sd = SceneDescription()
+    sd.add_mesh(quad, sd.add_material(type="matte"))
+    c, s_ = np.float32(np.cos(np.float32(np.deg2rad(np.float32(90))))), np.float32(np.sin(np.float32(np.deg2rad(np.float32(90)))))
+    T = np.eye(4, dtype=np.float32); T[0, 3], T[1, 3] = 0.5, 3.0
+    R = np.array([[1, 0, 0, 0], [0, c, -s_, 0], [0, s_, c, 0], [0, 0, 0, 1]], dtype=np.float32)
+    sd.add_projection_light((30, 30, 30), image=px.astype(np.float32) / np.float32(255), light_to_world=(T @ R).astype(np.float32), fov=50.0)
+    sd.camera.update(eye=(0.0, 1.2, -4.0), look=(0.0, -0.1, 0.0), up=(0, 1, 0), fov=40.0)
+    sd.film.update(xresolution=20, yresolution=16)
+    sd.sampler.update(type="halton", pixelsamples=4)
+    sd.integrator.update(name="whitted")
+    ld = pkg.load_pbrt(str(tmp_path / "s.pbrt"))
+    a, b = ld.to_desc(), sd.to_desc()
+    la, lb = C.cast(a.lights, C.POINTER(pkg.Light))[0], C.cast(b.lights, C.POINTER(pkg.Light))[0]
+    assert la.type == lb.type == pkg.LIGHT_PROJECTION and la.fov == lb.fov == 50.0 and (la.map_width, la.map_height) == (lb.map_width, lb.map_height) == (14, 6)
+    assert np.allclose(list(la.pos), list(lb.pos), atol=1e-6) and np.allclose(list(la.world_to_light), list(lb.world_to_light), atol=1e-6)
+    assert np.array_equal(_arr(la.map_rgb, 6 * 14 * 3, np.float32), _arr(lb.map_rgb, 6 * 14 * 3, np.float32))
+    assert np.isclose(la.cos_total_width, lb.cos_total_width, rtol=1e-6)
+    # closed form: corner (aspect, 1) of the screen window at fov 50 -> direction (a t, t, 1) with t = tan(25 deg)
+    t = np.tan(np.deg2rad(25.0)); asp = 14.0 / 6.0
+    assert np.isclose(la.cos_total_width, 1.0 / np.sqrt((asp * t) ** 2 + t ** 2 + 1.0), rtol=1e-5)
+    ra, rb = oracle.OracleScene(ld).render(nthreads=2)[0], oracle.OracleScene(sd).render(nthreads=2)[0]
+    assert ra.any() and ss.rel_rmse(ra, rb) <= 2e-2

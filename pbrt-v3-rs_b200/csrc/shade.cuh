@@ -544,7 +544,8 @@ B2_D RGB infinite_le(const DLight& l, const DInfDistr& D, V3 ray_d) {
     return inf_lookup(D, st);
 }
 // GonioPhotometricLight::scale (goniometric.rs:101-115): the map at the spherical coordinates of the light-space direction with y and z swapped
-B2_D RGB gonio_scale(const DLight& l, const DInfDistr& D, V3 w_world) {
+// (out of line, like projection_scale below: rare lights must not grow every shade kernel's instruction footprint)
+__device__ __noinline__ RGB gonio_scale(const DLight& l, const DInfDistr& D, V3 w_world) {
     V3 wp = normalize(xf3(l.w2l, w_world));
     const float t = wp.y; wp.y = wp.z; wp.z = t;
     P2 st = mk2(spherical_phi(wp) * kInvTwoPi, spherical_theta(wp) * kInvPi);
@@ -552,7 +553,7 @@ B2_D RGB gonio_scale(const DLight& l, const DInfDistr& D, V3 w_world) {
 }
 // ProjectionLight::projection (projection.rs:115-139): Transform::perspective(fov, 1e-3, 1e30).transform_point is
 // (inv_tan x, inv_tan y, ..) * (1 / z); outside the screen window or behind the near plane the light is black
-B2_D RGB projection_scale(const DLight& l, const DInfDistr& D, V3 w_world) {
+__device__ __noinline__ RGB projection_scale(const DLight& l, const DInfDistr& D, V3 w_world) {
     const V3 wl = xf3(l.w2l, w_world);
     if (wl.z < 1e-3f) return rgb1(0.0f);
     const float inv_tan = l.l2w[0], x0 = l.l2w[1], y0 = l.l2w[2], x1 = l.l2w[3], y1 = l.l2w[4];

@@ -298,3 +298,22 @@ def test_textures_show_in_the_image(gpu):
     a = gpu.PathIntegrator(_textured_scene(wl)).render()
     b = gpu.PathIntegrator(_textured_scene(wl, aamode="none")).render()
     assert ss.rel_rmse(a, b) > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("integrator", ["path", "whitted"])
+def test_wave_splitting_keeps_the_textured_image(gpu, integrator, monkeypatch):
+    """The camera-ray differentials are per path of a WAVE (and, for the tree integrators, travel on the per-path stack): cutting
+    the render into several waves must not change a bit of a textured image."""
+    from pbrt_v3_rs_b200 import workloads as wl
+
+    def film(log2):
+        if log2 is None:
+            monkeypatch.delenv("B200PT_WAVE_LOG2", raising=False)
+        else:
+            monkeypatch.setenv("B200PT_WAVE_LOG2", str(log2))
+        sd = _textured_scene(wl, integrator=integrator, res=64, spp=8, glass=integrator == "whitted")
+        return gpu.PathIntegrator(sd).render_rows()
+
+    one, many = film(None), film(13)  # 32 768 paths: one wave vs four
+    assert np.array_equal(one, many)

@@ -38,6 +38,8 @@
 //
 // HBM-bound integer/min-max work: nothing here is a contraction.
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -444,6 +446,40 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t* block_sum, uint3
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
+}
+
+// Exclusive scan of a LARGE array in place (the radix sort's 64 x n_blocks histogram: 2.5 M counters for 10 M primitives, which the
+// one-block scan above walked in 2 442 sequential steps = 1.6 ms per pass, 8 of the build's 13 ms): sums of 1024-element chunks,
+// k_scan_blocks over those few sums, then every chunk scans itself and adds its offset.
+__global__ void __launch_bounds__(1024) k_scan_chunk_sums(const uint32_t* __restrict__ a, uint32_t n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    uint32_t v = i < n ? a[i] : 0;
+    v = __reduce_add_sync(kFull, v);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t t = __reduce_add_sync(kFull, wsum[threadIdx.x]);
+        if (threadIdx.x == 0) sums[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_chunks(uint32_t* __restrict__ a, uint32_t n, const uint32_t* __restrict__ sums_excl) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    const uint32_t v = i < n ? a[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = wsum[threadIdx.x], xs = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(kFull, xs, d); if (threadIdx.x >= d) xs += y; }
+        wsum[threadIdx.x] = xs - w;  // exclusive
+    }
+    __syncthreads();
+    if (i < n) a[i] = sums_excl[blockIdx.x] + wsum[threadIdx.x >> 5] + x - v;
 }
 
 // 7. T[i] = number of predicate-true positions before i (whole array)
@@ -1126,7 +1162,8 @@ static size_t hlbvh_scratch_bytes(uint32_t n) {
     const size_t nb = ((size_t)n + kBlock - 1) / kBlock;
     return 4 * padded(4 * (size_t)n) + padded(4 * 64 * nb) + padded(n) + padded(4 * nb) + padded(4 * (size_t)n) + padded(4 * (size_t)n) + padded(64 * (size_t)n) +
            padded(4 * 8192) + padded(32 * 8192) * 2 + padded(8 * 8192) * 2 + padded(sizeof(Ctl)) + padded(64) +
-           7 * padded(4 * (2 * (size_t)n + 8)) + padded(24 * (2 * (size_t)n + 8)) + 2 * padded(4 * 32);  // level-parallel treelet state (HlLevels)
+           7 * padded(4 * (2 * (size_t)n + 8)) + padded(24 * (2 * (size_t)n + 8)) + 2 * padded(4 * 32) +  // level-parallel treelet state (HlLevels)
+           padded(4 * (64 * nb / 1024 + 2));                                                              // chunk sums of the histogram scan
 }
 
 int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prims, b200pt_bvh_node* d_nodes, int64_t* n_nodes_out, uint32_t* d_ordered,
@@ -1137,12 +1174,23 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
     const uint32_t n = (uint32_t)n64;
     max_prims &= 0xff;
     std::lock_guard<std::mutex> lock(ws().mu);
+    // B200PT_HLBVH_TIMING=1: host-side wall clock of the build's phases on stderr (where a build's time goes besides its kernels)
+    static const bool timing = [] { const char* e = std::getenv("B200PT_HLBVH_TIMING"); return e && e[0] == '1'; }();
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        std::fprintf(stderr, "[hlbvh] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     if (int rc = workspace_reserve(hlbvh_scratch_bytes(n))) return rc;
+    lap("workspace");
     Arena A{ws().base, ws().cap};
     const uint32_t n_blocks = blocks(n, kBlock);
     uint32_t* code[2] = {A.take<uint32_t>(n), A.take<uint32_t>(n)};
     uint32_t* val[2] = {A.take<uint32_t>(n), A.take<uint32_t>(n)};
     uint32_t* hist = A.take<uint32_t>(64 * (size_t)n_blocks);
+    const uint32_t n_chunks = blocks(64 * (uint64_t)n_blocks, 1024);
+    uint32_t* chunk_sums = A.take<uint32_t>(n_chunks);
     uint8_t* flag = A.take<uint8_t>(n);
     uint32_t* block_sum = A.take<uint32_t>(n_blocks);
     uint32_t* T = A.take<uint32_t>(n);
@@ -1167,9 +1215,11 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
     int cur = 0;
     for (int pass = 0; pass < 5; ++pass) {  // morton.rs:60-100
         k_hl_hist<<<n_blocks, kBlock, 0, st>>>(code[cur], n, 6 * pass, hist, n_blocks);
-        k_scan_blocks<<<1, 1024, 0, st>>>(hist, 64 * n_blocks);
+        k_scan_chunk_sums<<<n_chunks, 1024, 0, st>>>(hist, 64 * n_blocks, chunk_sums);
+        k_scan_blocks<<<1, 1024, 0, st>>>(chunk_sums, n_chunks);
+        k_scan_chunks<<<n_chunks, 1024, 0, st>>>(hist, 64 * n_blocks, chunk_sums);
         k_hl_scatter<<<n_blocks, kBlock, 0, st>>>(code[cur], val[cur], n, 6 * pass, hist, n_blocks, code[cur ^ 1], val[cur ^ 1]);
-        launches += 3;
+        launches += 5;
         cur ^= 1;
     }
     k_hl_flags<<<n_blocks, kBlock, 0, st>>>(code[cur], n, flag, block_sum);
@@ -1183,6 +1233,7 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
     B2_CUDA(cudaMemcpyAsync(&last_flag, flag + (n - 1), 1, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     const uint32_t n_treelets = last[0] + last_flag;
+    lap("morton + sort + starts");
     if (n_treelets == 0 || n_treelets > 4096) { b200pt_set_error("b200pt_bvh_build_hlbvh_device: internal error: treelet count"); return B200PT_ERR_INVALID; }
     static const bool serial_treelets = [] { const char* e = std::getenv("B200PT_HLBVH_TREELETS"); return e && std::strcmp(e, "serial") == 0; }();  // A/B: one thread per treelet
     if (serial_treelets) k_hl_treelets<<<blocks(n_treelets, 64), 64, 0, st>>>(d_prim_bounds, code[cur], val[cur], n, starts, n_treelets, max_prims, tmp, sizes, ctl);
@@ -1208,6 +1259,7 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
     }
     k_hl_gather_roots<<<blocks(n_treelets, 128), 128, 0, st>>>(tmp, starts, n_treelets, d_roots);
     launches += 2;
+    lap("treelets");
     std::vector<b200pt_bvh_node> roots(n_treelets), upper(n_treelets);
     std::vector<uint32_t> h_sizes(n_treelets);
     std::vector<int64_t> upper_index(n_treelets), base(n_treelets);
@@ -1218,8 +1270,10 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
     B2_CUDA(cudaStreamSynchronize(st));
     g_launches.fetch_add(launches);
     if (h.error) { b200pt_set_error("b200pt_bvh_build_hlbvh: leaf with >= 65536 primitives (reference asserts)"); return B200PT_ERR_INVALID; }
+    lap("read-back");
     int64_t n_upper = 0, total = 0;
     if (int rc = b200pt_hlbvh_upper_layout(roots.data(), h_sizes.data(), n_treelets, upper.data(), upper_index.data(), &n_upper, base.data(), &total)) return rc;
+    lap("upper SAH tree (host)");
     B2_CUDA(cudaMemcpyAsync(d_base, base.data(), n_treelets * 8, cudaMemcpyHostToDevice, st));
     if (n_upper > 0) {
         B2_CUDA(cudaMemcpyAsync(d_upper, upper.data(), (size_t)n_upper * sizeof(b200pt_bvh_node), cudaMemcpyHostToDevice, st));
@@ -1231,6 +1285,7 @@ int bvh_build_hlbvh_device(const float* d_prim_bounds, int64_t n64, int max_prim
     g_launches.fetch_add(n_upper > 0 ? 2 : 1);
     B2_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
     B2_CUDA(cudaGetLastError());
+    lap("emit");
     *n_nodes_out = total;
     return B200PT_OK;
 }
